@@ -1,0 +1,104 @@
+/* rcsb -- C ABI of the B200 batched rigid-body backend for Robot Control Stack.
+ *
+ * The reference has no C-ABI plugin table for its simulator; its boundary is the pybind11 module
+ * rcs._core (/root/reference/src/pybind/rcs.cpp:420-527) whose C++ side reaches libmujoco through
+ * mjModel* / mjData* (/root/reference/src/sim/sim.cpp, SimRobot.cpp, SimGripper.cpp). Every entry
+ * point below names the reference interface it replaces; INTEGRATION.md shows the pybind/ctypes stub
+ * a maintainer would add. Plain pointers and sizes only; device pointers are raw CUDA addresses.
+ *
+ * All functions return 0 on success and a negative code on failure unless stated otherwise;
+ * rcsb_last_error() returns a description. There is no CPU execution path: without a CUDA device
+ * rcsb_model_upload / rcsb_batch_* fail with RCSB_ERR_CUDA.
+ */
+#ifndef RCSB_H
+#define RCSB_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rcsb_model rcsb_model;
+typedef struct rcsb_batch rcsb_batch;
+
+enum { RCSB_OK = 0, RCSB_ERR_FIELD = -1, RCSB_ERR_SIZE = -2, RCSB_ERR_MODEL = -3, RCSB_ERR_CUDA = -4, RCSB_ERR_ARG = -5 };
+
+/* op bits of rcsb_batch_run, executed in this order for every selected environment */
+enum {
+  RCSB_RUN_GRIPPER_RESET = 1 << 0,   /* SimGripper::reset              SimGripper.cpp:158-165 */
+  RCSB_RUN_SIM_RESET = 1 << 1,       /* Sim::reset                     sim.cpp:117-138 */
+  RCSB_RUN_ROBOT_RESET = 1 << 2,     /* SimRobot::reset                SimRobot.cpp:193-216 */
+  RCSB_RUN_ENV_RESET_FLAGS = 1 << 3, /* GripperWrapper.reset           python/rcs/envs/base.py:703-708 */
+  RCSB_RUN_ACT_JOINTS_REL = 1 << 4,  /* RelativeActionSpace.action + RobotEnv.step   base.py:469-488, 255-288 */
+  RCSB_RUN_ACT_JOINTS_ABS = 1 << 5,  /* RobotEnv.step (JOINTS)         base.py:255-288 */
+  RCSB_RUN_ACT_GRIPPER_BIN = 1 << 6, /* GripperWrapper.action (binary) base.py:721-735 */
+  RCSB_RUN_SET_JOINTS = 1 << 7,      /* SimRobot::set_joint_position   SimRobot.cpp:123-131 */
+  RCSB_RUN_SET_GRIPPER = 1 << 8,     /* SimGripper::set_normalized_width  SimGripper.cpp:79-92 */
+  RCSB_RUN_SET_JOINTS_HARD = 1 << 9, /* SimRobot::set_joints_hard      SimRobot.cpp:197-205 */
+  RCSB_RUN_STEP_K = 1 << 10,         /* Sim::step(k)                   sim.cpp:108-115 */
+  RCSB_RUN_STEP_CONV = 1 << 11,      /* Sim::step_until_convergence    sim.cpp:84-106 */
+  RCSB_RUN_OBS = 1 << 12             /* RobotEnv.get_obs + info        base.py:246-253, envs/sim.py:60-66,125-131 */
+};
+
+const char* rcsb_last_error(void);
+int rcsb_version(void);
+int rcsb_real_bytes(void); /* sizeof(real) the library was built with (8: float64, as the reference) */
+
+/* ---- model: replaces mjModel (python/rcs/sim/sim.py:47-55 hands mjModel/mjData addresses to Sim) ---- */
+rcsb_model* rcsb_model_new(void);
+void rcsb_model_free(rcsb_model* m);
+int rcsb_model_set_int(rcsb_model* m, const char* field, const int* v, int n);
+int rcsb_model_set_real(rcsb_model* m, const char* field, const double* v, int n);
+int rcsb_model_set_mesh_vertices(rcsb_model* m, const double* xyz, int nvert);
+int rcsb_model_finalize(rcsb_model* m);         /* validates sizes, computes the workspace layout (host only) */
+int rcsb_model_upload(rcsb_model* m, int device); /* copies constants and hull vertices to the CUDA device */
+/* sizes of one environment's rows: reals, doubles, ints, obs reals, info ints */
+int rcsb_model_dims(const rcsb_model* m, int* nsr, int* nsd, int* nsi, int* obs_dim, int* info_dim);
+/* column offsets inside the real row: qpos, qvel, ctrl, qacc_warmstart, rcs tail */
+int rcsb_model_offsets(const rcsb_model* m, int* o_qpos, int* o_qvel, int* o_ctrl, int* o_warm, int* o_tail);
+
+/* ---- batch: replaces N x (mjData + Sim + SimRobot + SimGripper) ----
+ * sr/sd/si are caller-owned DEVICE arrays [n_envs][nsr] reals, [n_envs][nsd] doubles, [n_envs][nsi] ints
+ * (allocated by the host language, e.g. torch tensors). stream is a cudaStream_t (may be 0). */
+rcsb_batch* rcsb_batch_new(rcsb_model* m, int n_envs, void* sr, void* sd, void* si, void* stream);
+void rcsb_batch_free(rcsb_batch* b);
+int rcsb_batch_init_state(rcsb_batch* b); /* SimRobotState/SimGripperState defaults + mj_resetData on every env */
+
+/* One launch: for every env (mask_dev == NULL) or every env with mask_dev[env] != 0, run the ops in
+ * `ops`. act_joints_dev [n_envs][njoints] reals, act_gripper_dev [n_envs] reals, obs_dev
+ * [n_envs][obs_dim] reals, info_dev [n_envs][info_dim] ints: device pointers, NULL where unused.
+ * jlow/jhigh: host arrays [njoints] (joint limits of robots_meta_config, Robot.h:24-95). */
+int rcsb_batch_run(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps, const void* act_joints_dev,
+                   const void* act_gripper_dev, const unsigned char* mask_dev, double max_mov, const double* jlow,
+                   const double* jhigh, void* obs_dev, int* info_dev);
+
+/* Host-buffer variant of one env.step(): copies actions host->device, runs `ops`, copies obs/info
+ * device->host on the batch stream and synchronises. Host buffers should be pinned. */
+int rcsb_batch_run_host(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps, const double* act_joints_host,
+                        const double* act_gripper_host, double max_mov, const double* jlow, const double* jhigh,
+                        double* obs_host, int* info_host);
+
+/* thin aliases with the reference's method names (all envs) */
+int rcsb_sim_step(rcsb_batch* b, int k);                          /* Sim::step                 sim.cpp:108 */
+int rcsb_sim_step_until_convergence(rcsb_batch* b, int max_steps); /* Sim::step_until_convergence sim.cpp:84 */
+int rcsb_sim_reset(rcsb_batch* b);                                 /* Sim::reset                sim.cpp:117 */
+int rcsb_robot_set_joint_position(rcsb_batch* b, const void* q_dev); /* SimRobot.cpp:123 */
+int rcsb_robot_set_joints_hard(rcsb_batch* b, const void* q_dev);    /* SimRobot.cpp:197 */
+int rcsb_robot_reset(rcsb_batch* b);                                 /* SimRobot.cpp:216 */
+int rcsb_gripper_set_normalized_width(rcsb_batch* b, const void* width_dev); /* SimGripper.cpp:79 */
+int rcsb_gripper_reset(rcsb_batch* b);                                        /* SimGripper.cpp:165 */
+int rcsb_env_get_obs(rcsb_batch* b, void* obs_dev, int* info_dev);            /* base.py:246-253 */
+
+/* Pin::inverse for every env (Kinematics.cpp:28-68): pose_dev [n][7] xyz+quat(xyzw) in the robot base
+ * frame, q0_dev [n][njoints]; writes q_out_dev [n][ik_nq] and success_dev [n]. */
+int rcsb_ik_inverse(rcsb_batch* b, const void* pose_dev, const void* q0_dev, void* q_out_dev, int* success_dev,
+                    int* iters_dev);
+/* SimRobot::set_cartesian_position for every env (SimRobot.cpp:145-155) */
+int rcsb_robot_set_cartesian_position(rcsb_batch* b, const void* pose_dev);
+
+/* evidence counters */
+long long rcsb_launch_count(void); /* kernels launched by this library since load */
+int rcsb_kernel_occupancy(rcsb_batch* b, int* warps_per_cta, int* smem_bytes, int* grid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,686 @@
+// Per-environment smooth dynamics and collision detection, one environment per warp.
+//
+// B200-native re-design of the arithmetic the reference reaches through mj_step1
+// (/root/reference/src/sim/sim.cpp:110): forward kinematics, tree COM frames, composite rigid
+// body mass matrix + Cholesky, velocity-stage bias forces (RNE with zero acceleration), passive
+// damping and gravity compensation, broad + narrow phase collision. MuJoCo's "com frame" spatial
+// vectors make every tree recursion except forward kinematics a sum over ancestor / descendant
+// sets, so those stages are flat parallel-fors over (body | dof | matrix entry) work items with
+// precompiled bit masks instead of serial tree walks.
+#pragma once
+#include "rcsb_warp.cuh"
+
+struct Ctx {
+  const RcsbModel* md;  // model constants (shared memory on device)
+  real* w;              // this warp's real workspace (shared memory)
+  int* wi;              // this warp's int workspace (shared memory)
+  const real* verts;    // convex hull vertex pool (global memory, read-only)
+  double* clk;          // this warp's simulation time + callback clocks (always double)
+  int lane;
+};
+#define WR(name) (c.w + m.o_##name)
+#define WI(name) (c.wi + m.oi_##name)
+
+// misc int slots in the workspace
+enum { MI_NCON = 0, MI_NEFC, MI_NE, MI_NF, MI_NL, MI_NCAND, MI_SOLVER_ITER, MI_WARN, MI_COUNT };
+
+// ------------------------------------------------------------------ dense Cholesky on shared memory
+// A (n x n, row-major) -> strictly-lower part holds L, dinv[j] = 1 / L[j][j]. A's diagonal is left
+// untouched so that no lane overwrites a value other lanes still read.
+RCSB_DEV void chol_factor(const Ctx& c, real* A, real* dinv, int n) {
+  for (int j = 0; j < n; j++) {
+    RCSB_SYNC();
+    real d = A[j * n + j];
+    for (int k = 0; k < j; k++) d -= A[j * n + k] * A[j * n + k];
+    if (d < RCSB_MINVAL) d = RCSB_MINVAL;
+    real inv = (real)1 / r_sqrt(d);
+    PFOR(ii, n - j - 1) {
+      int i = j + 1 + ii;
+      real t = A[i * n + j];
+      for (int k = 0; k < j; k++) t -= A[i * n + k] * A[j * n + k];
+      A[i * n + j] = t * inv;
+    }
+    if (c.lane == 0) dinv[j] = inv;
+  }
+  RCSB_SYNC();
+}
+// x <- (L L^T)^{-1} x ; y is scratch of length n
+RCSB_DEV void chol_solve(const Ctx& c, const real* L, const real* dinv, int n, real* x, real* y) {
+  for (int k = 0; k < n; k++) {
+    RCSB_SYNC();
+    real xk = x[k] * dinv[k];
+    PFOR(ii, n - k - 1) {
+      int i = k + 1 + ii;
+      x[i] -= L[i * n + k] * xk;
+    }
+    if (c.lane == 0) y[k] = xk;
+  }
+  for (int k = n - 1; k >= 0; k--) {
+    RCSB_SYNC();
+    real yk = y[k] * dinv[k];
+    PFOR(i, k) { y[i] -= L[k * n + i] * yk; }
+    if (c.lane == 0) x[k] = yk;
+  }
+  RCSB_SYNC();
+}
+
+// ------------------------------------------------------------------ forward kinematics
+RCSB_DEV void st_kinematics(const Ctx& c) {
+  const RcsbModel& m = *c.md;
+  real* q = WR(q);
+  real* sc = WR(tmp);
+  PFOR(b, m.nb) {
+    if (m.b_jtype[b] == RCSB_JNT_HINGE) {
+      real a = (real)0.5 * (q[m.b_qadr[b]] - m.qpos0[m.b_qadr[b]]);
+      sc[2 * b] = sin(a);
+      sc[2 * b + 1] = cos(a);
+    }
+  }
+  RCSB_SYNC();
+  if (c.lane == 0) {
+    for (int b = 0; b < m.nb; b++) {
+      int p = m.b_parent[b];
+      real pos[3], quat[4];
+      real* anchor = WR(janchor) + 3 * b;
+      real* axis = WR(jaxis) + 3 * b;
+      if (m.b_jtype[b] == RCSB_JNT_FREE) {
+        real* qq = q + m.b_qadr[b];
+        quat_normalize(qq + 3);
+        copy3(pos, qq);
+        quat[0] = qq[3]; quat[1] = qq[4]; quat[2] = qq[5]; quat[3] = qq[6];
+        copy3(anchor, pos);
+        axis[0] = 0; axis[1] = 0; axis[2] = 1;
+      } else {
+        real v[3], R[9];
+        if (p < 0) {
+          copy3(pos, m.b_pos[b]);
+          quat[0] = m.b_quat[b][0]; quat[1] = m.b_quat[b][1]; quat[2] = m.b_quat[b][2]; quat[3] = m.b_quat[b][3];
+        } else {
+          mulmat3(v, WR(bmat) + 9 * p, m.b_pos[b]);
+          const real* pp = WR(bpos) + 3 * p;
+          pos[0] = pp[0] + v[0]; pos[1] = pp[1] + v[1]; pos[2] = pp[2] + v[2];
+          quat_mul(quat, WR(bquat) + 4 * p, m.b_quat[b]);
+        }
+        quat_to_mat(R, quat);
+        mulmat3(axis, R, m.b_jaxis[b]);
+        mulmat3(v, R, m.b_jpos[b]);
+        anchor[0] = pos[0] + v[0]; anchor[1] = pos[1] + v[1]; anchor[2] = pos[2] + v[2];
+        if (m.b_jtype[b] == RCSB_JNT_SLIDE) {
+          real qq = q[m.b_qadr[b]] - m.qpos0[m.b_qadr[b]];
+          pos[0] += axis[0] * qq; pos[1] += axis[1] * qq; pos[2] += axis[2] * qq;
+        } else {
+          real s = sc[2 * b], ql[4] = {sc[2 * b + 1], m.b_jaxis[b][0] * s, m.b_jaxis[b][1] * s, m.b_jaxis[b][2] * s}, qn[4];
+          quat_mul(qn, quat, ql);
+          quat[0] = qn[0]; quat[1] = qn[1]; quat[2] = qn[2]; quat[3] = qn[3];
+          quat_to_mat(R, quat);
+          mulmat3(v, R, m.b_jpos[b]);
+          pos[0] = anchor[0] - v[0]; pos[1] = anchor[1] - v[1]; pos[2] = anchor[2] - v[2];
+        }
+      }
+      quat_normalize(quat);
+      copy3(WR(bpos) + 3 * b, pos);
+      real* bq = WR(bquat) + 4 * b;
+      bq[0] = quat[0]; bq[1] = quat[1]; bq[2] = quat[2]; bq[3] = quat[3];
+      quat_to_mat(WR(bmat) + 9 * b, quat);
+    }
+  }
+  RCSB_SYNC();
+}
+
+// world pose of collidable geom g
+RCSB_DEV void geom_frame(const Ctx& c, int g, real* pos, real* mat) {
+  const RcsbModel& m = *c.md;
+  int b = m.g_body[g];
+  real Rl[9];
+  quat_to_mat(Rl, m.g_quat[g]);
+  if (b < 0) {
+    copy3(pos, m.g_pos[g]);
+    for (int i = 0; i < 9; i++) mat[i] = Rl[i];
+  } else {
+    const real* R = WR(bmat) + 9 * b;
+    const real* p = WR(bpos) + 3 * b;
+    real v[3];
+    mulmat3(v, R, m.g_pos[g]);
+    pos[0] = p[0] + v[0]; pos[1] = p[1] + v[1]; pos[2] = p[2] + v[2];
+    for (int r = 0; r < 3; r++)
+      for (int k = 0; k < 3; k++) mat[3 * r + k] = R[3 * r] * Rl[k] + R[3 * r + 1] * Rl[3 + k] + R[3 * r + 2] * Rl[6 + k];
+  }
+}
+
+// ------------------------------------------------------------------ COM frames, inertias, motion axes, geom centres
+RCSB_DEV void st_com(const Ctx& c) {
+  const RcsbModel& m = *c.md;
+  PFOR(b, m.nb) {
+    real v[3];
+    const real* R = WR(bmat) + 9 * b;
+    const real* p = WR(bpos) + 3 * b;
+    mulmat3(v, R, m.b_ipos[b]);
+    real* o = WR(bcom) + 3 * b;
+    o[0] = p[0] + v[0]; o[1] = p[1] + v[1]; o[2] = p[2] + v[2];
+    mulmat3(v, R, m.b_gcpos[b]);
+    o = WR(bgc) + 3 * b;
+    o[0] = p[0] + v[0]; o[1] = p[1] + v[1]; o[2] = p[2] + v[2];
+  }
+  RCSB_SYNC();
+  PFOR(r, m.nroot) {
+    real s[3] = {0, 0, 0};
+    for (int b = 0; b < m.nb; b++)
+      if (m.b_root[b] == r) {
+        const real* o = WR(bcom) + 3 * b;
+        s[0] += m.b_mass[b] * o[0]; s[1] += m.b_mass[b] * o[1]; s[2] += m.b_mass[b] * o[2];
+      }
+    real* rc = WR(rootcom) + 3 * r;
+    rc[0] = s[0] * m.r_invmass[r]; rc[1] = s[1] * m.r_invmass[r]; rc[2] = s[2] * m.r_invmass[r];
+  }
+  RCSB_SYNC();
+  PFOR(b, m.nb) {  // inertia about the tree COM, world axes
+    const real* R = WR(bmat) + 9 * b;
+    const real* I = m.b_inertia[b];
+    const real* rc = WR(rootcom) + 3 * m.b_root[b];
+    const real* bc = WR(bcom) + 3 * b;
+    real mass = m.b_mass[b], d[3] = {bc[0] - rc[0], bc[1] - rc[1], bc[2] - rc[2]};
+    real A[9];  // R * I
+    for (int r = 0; r < 3; r++) {
+      real r0 = R[3 * r], r1 = R[3 * r + 1], r2 = R[3 * r + 2];
+      A[3 * r] = r0 * I[0] + r1 * I[3] + r2 * I[4];
+      A[3 * r + 1] = r0 * I[3] + r1 * I[1] + r2 * I[5];
+      A[3 * r + 2] = r0 * I[4] + r1 * I[5] + r2 * I[2];
+    }
+    real dd = dot3(d, d);
+    real* ci = WR(cinert) + 10 * b;
+    ci[0] = A[0] * R[0] + A[1] * R[1] + A[2] * R[2] + mass * (dd - d[0] * d[0]);
+    ci[1] = A[3] * R[3] + A[4] * R[4] + A[5] * R[5] + mass * (dd - d[1] * d[1]);
+    ci[2] = A[6] * R[6] + A[7] * R[7] + A[8] * R[8] + mass * (dd - d[2] * d[2]);
+    ci[3] = A[0] * R[3] + A[1] * R[4] + A[2] * R[5] - mass * d[0] * d[1];
+    ci[4] = A[0] * R[6] + A[1] * R[7] + A[2] * R[8] - mass * d[0] * d[2];
+    ci[5] = A[3] * R[6] + A[4] * R[7] + A[5] * R[8] - mass * d[1] * d[2];
+    ci[6] = mass * d[0]; ci[7] = mass * d[1]; ci[8] = mass * d[2];
+    ci[9] = mass;
+  }
+  PFOR(j, m.nv) {  // motion axis of dof j about the tree COM
+    int b = m.d_body[j];
+    const real* rc = WR(rootcom) + 3 * m.b_root[b];
+    const real* an = WR(janchor) + 3 * b;
+    real off[3] = {rc[0] - an[0], rc[1] - an[1], rc[2] - an[2]};
+    real* cd = WR(cdof) + 6 * j;
+    int jt = m.b_jtype[b];
+    if (jt == RCSB_JNT_FREE) {
+      int a = j - m.b_dadr[b];
+      if (a < 3) {
+        cd[0] = cd[1] = cd[2] = 0;
+        cd[3] = a == 0; cd[4] = a == 1; cd[5] = a == 2;
+      } else {
+        const real* R = WR(bmat) + 9 * b;
+        real ax[3] = {R[a - 3], R[3 + a - 3], R[6 + a - 3]};
+        copy3(cd, ax);
+        cross3(cd + 3, ax, off);
+      }
+    } else if (jt == RCSB_JNT_SLIDE) {
+      cd[0] = cd[1] = cd[2] = 0;
+      copy3(cd + 3, WR(jaxis) + 3 * b);
+    } else {
+      copy3(cd, WR(jaxis) + 3 * b);
+      cross3(cd + 3, WR(jaxis) + 3 * b, off);
+    }
+  }
+  PFOR(g, m.ng) {  // geom centres for the broad phase
+    int b = m.g_body[g];
+    real* o = WR(gpos) + 3 * g;
+    if (b < 0) copy3(o, m.g_pos[g]);
+    else {
+      real v[3];
+      mulmat3(v, WR(bmat) + 9 * b, m.g_pos[g]);
+      const real* p = WR(bpos) + 3 * b;
+      o[0] = p[0] + v[0]; o[1] = p[1] + v[1]; o[2] = p[2] + v[2];
+    }
+  }
+  if (c.lane == 0) {  // attachment site pose (SimRobot::get_cartesian_position reads it after the step)
+    int b = m.rb_site_body;
+    real* sp = WR(rcs) + RCSB_S_SITEPOS;
+    real Rl[9];
+    quat_to_mat(Rl, m.rb_site_quat);
+    if (b < 0) {
+      copy3(sp, m.rb_site_pos);
+      for (int i = 0; i < 9; i++) sp[3 + i] = Rl[i];
+    } else {
+      const real* R = WR(bmat) + 9 * b;
+      const real* p = WR(bpos) + 3 * b;
+      real v[3];
+      mulmat3(v, R, m.rb_site_pos);
+      sp[0] = p[0] + v[0]; sp[1] = p[1] + v[1]; sp[2] = p[2] + v[2];
+      for (int r = 0; r < 3; r++)
+        for (int k = 0; k < 3; k++) sp[3 + 3 * r + k] = R[3 * r] * Rl[k] + R[3 * r + 1] * Rl[3 + k] + R[3 * r + 2] * Rl[6 + k];
+    }
+  }
+  RCSB_SYNC();
+}
+
+// ------------------------------------------------------------------ composite inertia, mass matrix, factorisation
+RCSB_DEV void st_crb(const Ctx& c) {
+  const RcsbModel& m = *c.md;
+  int nv = m.nv;
+  PFOR(e, m.nb * 10) {
+    int b = e / 10, k = e - 10 * b;
+    real s = 0;
+    uint32_t mask = m.b_descmask[b];
+    for (int d = b; d < m.nb; d++)
+      if ((mask >> d) & 1u) s += WR(cinert)[10 * d + k];
+    WR(crb)[e] = s;
+  }
+  RCSB_SYNC();
+  real* buf = WR(tmp);
+  PFOR(i, nv) { mul_inert_vec(buf + 6 * i, WR(crb) + 10 * m.d_body[i], WR(cdof) + 6 * i); }
+  RCSB_SYNC();
+  PFOR(e, nv * nv) {
+    int i = e / nv, j = e - i * nv;
+    if (j <= i) {
+      real val = 0;
+      if ((m.d_ancmask[i] >> j) & 1u) {
+        const real* cd = WR(cdof) + 6 * j;
+        const real* bf = buf + 6 * i;
+        val = cd[0] * bf[0] + cd[1] * bf[1] + cd[2] * bf[2] + cd[3] * bf[3] + cd[4] * bf[4] + cd[5] * bf[5];
+        if (i == j) val += m.d_armature[i];
+      }
+      WR(M)[i * nv + j] = val;
+      WR(M)[j * nv + i] = val;
+      WR(L)[i * nv + j] = val;
+      WR(L)[j * nv + i] = val;
+    }
+  }
+  chol_factor(c, WR(L), WR(L) + nv * nv, nv);
+}
+
+// ------------------------------------------------------------------ velocity stage: bias, passive, gravity compensation
+RCSB_DEV void st_velocity(const Ctx& c) {
+  const RcsbModel& m = *c.md;
+  int nv = m.nv;
+  const real* v = WR(v);
+  PFOR(j, nv) {
+    real* cdd = WR(cdofdot) + 6 * j;
+    if (m.d_dotzero[j]) {
+      for (int k = 0; k < 6; k++) cdd[k] = 0;
+    } else {
+      real pre[6] = {0, 0, 0, 0, 0, 0};
+      uint32_t mask = m.d_premask[j];
+      for (int i = 0; i < nv; i++)
+        if ((mask >> i) & 1u) {
+          const real* cd = WR(cdof) + 6 * i;
+          for (int k = 0; k < 6; k++) pre[k] += cd[k] * v[i];
+        }
+      cross_motion(cdd, pre, WR(cdof) + 6 * j);
+    }
+  }
+  PFOR(b, m.nb) {
+    real cv[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t mask = m.b_dofmask[b];
+    for (int i = 0; i < nv; i++)
+      if ((mask >> i) & 1u) {
+        const real* cd = WR(cdof) + 6 * i;
+        for (int k = 0; k < 6; k++) cv[k] += cd[k] * v[i];
+      }
+    for (int k = 0; k < 6; k++) WR(cvel)[6 * b + k] = cv[k];
+  }
+  RCSB_SYNC();
+  PFOR(b, m.nb) {
+    real ca[6] = {0, 0, 0, -m.gravity[0], -m.gravity[1], -m.gravity[2]};
+    uint32_t mask = m.b_dofmask[b];
+    for (int i = 0; i < nv; i++)
+      if ((mask >> i) & 1u) {
+        const real* cd = WR(cdofdot) + 6 * i;
+        for (int k = 0; k < 6; k++) ca[k] += cd[k] * v[i];
+      }
+    real Ia[6], Iv[6], x[6];
+    mul_inert_vec(Ia, WR(cinert) + 10 * b, ca);
+    mul_inert_vec(Iv, WR(cinert) + 10 * b, WR(cvel) + 6 * b);
+    cross_force(x, WR(cvel) + 6 * b, Iv);
+    for (int k = 0; k < 6; k++) WR(cfrc)[6 * b + k] = Ia[k] + x[k];
+  }
+  RCSB_SYNC();
+  PFOR(j, nv) {
+    int bj = m.d_body[j];
+    uint32_t mask = m.b_descmask[bj];
+    const real* cd = WR(cdof) + 6 * j;
+    const real* rc = WR(rootcom) + 3 * m.b_root[bj];
+    real f[6] = {0, 0, 0, 0, 0, 0}, gc = 0;
+    for (int b = bj; b < m.nb; b++)
+      if ((mask >> b) & 1u) {
+        const real* cf = WR(cfrc) + 6 * b;
+        for (int k = 0; k < 6; k++) f[k] += cf[k];
+        real gm = m.b_gcmass[b];
+        if (gm != 0) {
+          const real* p = WR(bgc) + 3 * b;
+          real off[3] = {p[0] - rc[0], p[1] - rc[1], p[2] - rc[2]}, t[3];
+          cross3(t, cd, off);
+          gc -= gm * ((cd[3] + t[0]) * m.gravity[0] + (cd[4] + t[1]) * m.gravity[1] + (cd[5] + t[2]) * m.gravity[2]);
+        }
+      }
+    WR(bias)[j] = cd[0] * f[0] + cd[1] * f[1] + cd[2] * f[2] + cd[3] * f[3] + cd[4] * f[4] + cd[5] * f[5];
+    WR(gravc)[j] = gc;
+    WR(passive)[j] = -m.d_damping[j] * v[j] + (m.d_actgravcomp[j] ? (real)0 : gc);
+  }
+  RCSB_SYNC();
+}
+
+// ------------------------------------------------------------------ collision
+// support mapping of geom g (world pose gp, gR) along world direction dir; warp-cooperative for meshes
+RCSB_DEV void support(const Ctx& c, int g, const real* gp, const real* gR, const real* dir, real* out) {
+  const RcsbModel& m = *c.md;
+  real dl[3], v[3] = {0, 0, 0};
+  mulmatT3(dl, gR, dir);
+  int type = m.g_type[g];
+  if (type == RCSB_GEOM_MESH) {
+    const real* verts = c.verts + 3 * m.g_vertadr[g];
+    int n = m.g_vertnum[g], best = 0x7fffffff;
+    real bd = (real)-1e300;
+    PFOR(i, n) {
+      real s = RCSB_LDG(verts + 3 * i) * dl[0] + RCSB_LDG(verts + 3 * i + 1) * dl[1] + RCSB_LDG(verts + 3 * i + 2) * dl[2];
+#if defined(RCSB_HOST_EMU) && defined(RCSB_EMU_REVERSE)
+      if (s > bd || (s == bd && i < best)) { bd = s; best = i; }
+#else
+      if (s > bd) { bd = s; best = i; }
+#endif
+    }
+    warp_argmax(bd, best);
+    v[0] = RCSB_LDG(verts + 3 * best); v[1] = RCSB_LDG(verts + 3 * best + 1); v[2] = RCSB_LDG(verts + 3 * best + 2);
+  } else if (type == RCSB_GEOM_BOX) {
+    for (int k = 0; k < 3; k++) v[k] = dl[k] >= 0 ? m.g_size[g][k] : -m.g_size[g][k];
+  } else if (type == RCSB_GEOM_CAPSULE) {
+    real n = norm3(dl);
+    if (n > RCSB_MINVAL) for (int k = 0; k < 3; k++) v[k] = m.g_size[g][0] * dl[k] / n;
+    v[2] += dl[2] >= 0 ? m.g_size[g][1] : -m.g_size[g][1];
+  } else if (type == RCSB_GEOM_SPHERE) {
+    real n = norm3(dl);
+    if (n > RCSB_MINVAL) for (int k = 0; k < 3; k++) v[k] = m.g_size[g][0] * dl[k] / n;
+  }
+  mulmat3(out, gR, v);
+  out[0] += gp[0]; out[1] += gp[1]; out[2] += gp[2];
+}
+
+struct Sup { real v[3], v1[3], v2[3]; };
+struct PairFrames { int g1, g2; real p1[3], R1[9], p2[3], R2[9]; };
+
+RCSB_DEV void mink_support(const Ctx& c, const PairFrames& pf, const real* dir, Sup& s) {
+  real nd[3] = {-dir[0], -dir[1], -dir[2]};
+  support(c, pf.g1, pf.p1, pf.R1, dir, s.v1);
+  support(c, pf.g2, pf.p2, pf.R2, nd, s.v2);
+  s.v[0] = s.v1[0] - s.v2[0]; s.v[1] = s.v1[1] - s.v2[1]; s.v[2] = s.v1[2] - s.v2[2];
+}
+RCSB_DEV real origin_tri_dist(const real* A, const real* B, const real* C, real* w) {
+  // closest point of triangle ABC to the origin (Ericson, Real-Time Collision Detection 5.1.5)
+  real ab[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]}, ac[3] = {C[0] - A[0], C[1] - A[1], C[2] - A[2]};
+  real ap[3] = {-A[0], -A[1], -A[2]};
+  real d1 = dot3(ab, ap), d2 = dot3(ac, ap);
+  bool done = false;
+  if (d1 <= 0 && d2 <= 0) { copy3(w, A); done = true; }
+  real bp[3] = {-B[0], -B[1], -B[2]};
+  real d3 = dot3(ab, bp), d4 = dot3(ac, bp);
+  if (!done && d3 >= 0 && d4 <= d3) { copy3(w, B); done = true; }
+  real vc = d1 * d4 - d3 * d2;
+  if (!done && vc <= 0 && d1 >= 0 && d3 <= 0) {
+    real t = d1 / (d1 - d3);
+    for (int k = 0; k < 3; k++) w[k] = A[k] + t * ab[k];
+    done = true;
+  }
+  real cp[3] = {-C[0], -C[1], -C[2]};
+  real d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+  if (!done && d6 >= 0 && d5 <= d6) { copy3(w, C); done = true; }
+  real vb = d5 * d2 - d1 * d6;
+  if (!done && vb <= 0 && d2 >= 0 && d6 <= 0) {
+    real t = d2 / (d2 - d6);
+    for (int k = 0; k < 3; k++) w[k] = A[k] + t * ac[k];
+    done = true;
+  }
+  real va = d3 * d6 - d5 * d4;
+  if (!done && va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
+    real t = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+    for (int k = 0; k < 3; k++) w[k] = B[k] + t * (C[k] - B[k]);
+    done = true;
+  }
+  if (!done) {
+    real den = (real)1 / (va + vb + vc), vv = vb * den, uu = vc * den;
+    for (int k = 0; k < 3; k++) w[k] = A[k] + ab[k] * vv + ac[k] * uu;
+  }
+  return r_sqrt(dot3(w, w));
+}
+RCSB_DEV void portal_dir(const Sup* s, real* dir) {
+  real a[3] = {s[2].v[0] - s[1].v[0], s[2].v[1] - s[1].v[1], s[2].v[2] - s[1].v[2]};
+  real b[3] = {s[3].v[0] - s[1].v[0], s[3].v[1] - s[1].v[1], s[3].v[2] - s[1].v[2]};
+  cross3(dir, a, b);
+  normalize3(dir);
+}
+RCSB_DEV int portal_reach_tol(const Sup* s, const Sup& v4, const real* dir) {
+  real dv4 = dot3(v4.v, dir);
+  real a = dv4 - dot3(s[1].v, dir), b = dv4 - dot3(s[2].v, dir), cc = dv4 - dot3(s[3].v, dir);
+  real mn = a < b ? a : b;
+  mn = mn < cc ? mn : cc;
+  return mn <= (real)1e-6;
+}
+RCSB_DEV void expand_portal(Sup* s, const Sup& v4) {
+  real x[3];
+  cross3(x, v4.v, s[0].v);
+  if (dot3(s[1].v, x) > 0) {
+    if (dot3(s[2].v, x) > 0) s[1] = v4; else s[3] = v4;
+  } else {
+    if (dot3(s[3].v, x) > 0) s[2] = v4; else s[1] = v4;
+  }
+}
+// Minkowski Portal Refinement penetration query (algorithm of libccd's ccdMPRPenetration, which
+// MuJoCo 3.2.6 uses for convex pairs). Warp-uniform control flow; only support() is cooperative.
+RCSB_DEV int mpr_penetration(const Ctx& c, const PairFrames& pf, real* depth, real* dir_out, real* pos) {
+  Sup s[4], v4;
+  real dir[3], va[3], vb[3];
+  for (int k = 0; k < 3; k++) { s[0].v1[k] = pf.p1[k]; s[0].v2[k] = pf.p2[k]; s[0].v[k] = pf.p1[k] - pf.p2[k]; }
+  if (r_abs(s[0].v[0]) < (real)1e-12 && r_abs(s[0].v[1]) < (real)1e-12 && r_abs(s[0].v[2]) < (real)1e-12) s[0].v[0] += (real)1e-5;
+  dir[0] = -s[0].v[0]; dir[1] = -s[0].v[1]; dir[2] = -s[0].v[2];
+  normalize3(dir);
+  mink_support(c, pf, dir, s[1]);
+  if (dot3(s[1].v, dir) <= 0) return 0;
+  cross3(dir, s[0].v, s[1].v);
+  if (dot3(dir, dir) < (real)1e-24) {
+    *depth = norm3(s[1].v);
+    for (int k = 0; k < 3; k++) { dir_out[k] = s[1].v[k]; pos[k] = (real)0.5 * (s[1].v1[k] + s[1].v2[k]); }
+    normalize3(dir_out);
+    return 1;
+  }
+  normalize3(dir);
+  mink_support(c, pf, dir, s[2]);
+  if (dot3(s[2].v, dir) <= 0) return 0;
+  for (int k = 0; k < 3; k++) { va[k] = s[1].v[k] - s[0].v[k]; vb[k] = s[2].v[k] - s[0].v[k]; }
+  cross3(dir, va, vb);
+  normalize3(dir);
+  if (dot3(dir, s[0].v) > 0) {
+    Sup t = s[1]; s[1] = s[2]; s[2] = t;
+    dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2];
+  }
+  for (int it = 0;; it++) {
+    if (it > 100) return 0;
+    mink_support(c, pf, dir, s[3]);
+    if (dot3(s[3].v, dir) <= 0) return 0;
+    int cont = 0;
+    cross3(va, s[1].v, s[3].v);
+    if (dot3(va, s[0].v) < (real)-1e-18) { s[2] = s[3]; cont = 1; }
+    if (!cont) {
+      cross3(va, s[3].v, s[2].v);
+      if (dot3(va, s[0].v) < (real)-1e-18) { s[1] = s[3]; cont = 1; }
+    }
+    if (!cont) break;
+    for (int k = 0; k < 3; k++) { va[k] = s[1].v[k] - s[0].v[k]; vb[k] = s[2].v[k] - s[0].v[k]; }
+    cross3(dir, va, vb);
+    normalize3(dir);
+  }
+  for (int it = 0;; it++) {
+    portal_dir(s, dir);
+    if (dot3(s[1].v, dir) >= 0) break;
+    mink_support(c, pf, dir, v4);
+    if (dot3(v4.v, dir) < 0 || portal_reach_tol(s, v4, dir) || it >= 50) return 0;
+    expand_portal(s, v4);
+  }
+  for (int it = 0;; it++) {
+    portal_dir(s, dir);
+    mink_support(c, pf, dir, v4);
+    if (portal_reach_tol(s, v4, dir) || it >= 50) {
+      real w[3];
+      *depth = origin_tri_dist(s[1].v, s[2].v, s[3].v, w);
+      if (*depth < (real)1e-12) copy3(dir_out, dir);
+      else { copy3(dir_out, w); normalize3(dir_out); }
+      // contact position: barycentric blend of the witness points (libccd findPos)
+      real b[4], vec[3], sum;
+      portal_dir(s, dir);
+      cross3(vec, s[1].v, s[2].v); b[0] = dot3(vec, s[3].v);
+      cross3(vec, s[3].v, s[2].v); b[1] = dot3(vec, s[0].v);
+      cross3(vec, s[0].v, s[1].v); b[2] = dot3(vec, s[3].v);
+      cross3(vec, s[2].v, s[1].v); b[3] = dot3(vec, s[0].v);
+      sum = b[0] + b[1] + b[2] + b[3];
+      if (sum <= 0) {
+        b[0] = 0;
+        cross3(vec, s[2].v, s[3].v); b[1] = dot3(vec, dir);
+        cross3(vec, s[3].v, s[1].v); b[2] = dot3(vec, dir);
+        cross3(vec, s[1].v, s[2].v); b[3] = dot3(vec, dir);
+        sum = b[1] + b[2] + b[3];
+      }
+      real p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0};
+      for (int i = 0; i < 4; i++)
+        for (int k = 0; k < 3; k++) { p1[k] += b[i] * s[i].v1[k]; p2[k] += b[i] * s[i].v2[k]; }
+      for (int k = 0; k < 3; k++) pos[k] = (real)0.5 * (p1[k] + p2[k]) / sum;
+      return 1;
+    }
+    expand_portal(s, v4);
+  }
+}
+
+// append one contact (all lanes call with identical arguments; lane 0 writes)
+RCSB_DEV void add_contact(const Ctx& c, int& ncon, int g1, int g2, real dist, const real* pos, const real* normal,
+                          real margin, real gap) {
+  const RcsbModel& m = *c.md;
+  if (ncon >= m.maxcon) {
+    if (c.lane == 0) WI(misc)[MI_WARN] += 1;
+    return;
+  }
+  if (c.lane == 0) {
+    real* cr = WR(con) + RCSB_C_REALS * ncon;
+    int* ci = WI(con) + RCSB_CI_INTS * ncon;
+    cr[RCSB_C_DIST] = dist;
+    copy3(cr + RCSB_C_POS, pos);
+    copy3(cr + RCSB_C_FRAME, normal);
+    make_frame(cr + RCSB_C_FRAME);
+    cr[RCSB_C_INCMARGIN] = margin - gap;
+    ci[RCSB_CI_G0] = g1; ci[RCSB_CI_G1] = g2;
+    int p1 = m.g_priority[g1], p2 = m.g_priority[g2];
+    real mix, fr[3];
+    int dim;
+    if (p1 == p2) {
+      real s1 = m.g_solmix[g1], s2 = m.g_solmix[g2];
+      if (s1 >= RCSB_MINVAL && s2 >= RCSB_MINVAL) mix = s1 / (s1 + s2);
+      else if (s1 < RCSB_MINVAL && s2 < RCSB_MINVAL) mix = (real)0.5;
+      else mix = s1 < RCSB_MINVAL ? (real)0 : (real)1;
+      for (int k = 0; k < 3; k++) fr[k] = m.g_friction[g1][k] > m.g_friction[g2][k] ? m.g_friction[g1][k] : m.g_friction[g2][k];
+      dim = m.g_condim[g1] > m.g_condim[g2] ? m.g_condim[g1] : m.g_condim[g2];
+    } else {
+      int g = p1 > p2 ? g1 : g2;
+      mix = p1 > p2 ? (real)1 : (real)0;
+      for (int k = 0; k < 3; k++) fr[k] = m.g_friction[g][k];
+      dim = m.g_condim[g];
+    }
+    ci[RCSB_CI_DIM] = dim;
+    ci[RCSB_CI_EFC] = -1;
+    const real *r1 = m.g_solref[g1], *r2 = m.g_solref[g2];
+    if (r1[0] > 0 && r2[0] > 0) for (int k = 0; k < 2; k++) cr[RCSB_C_SOLREF + k] = mix * r1[k] + (1 - mix) * r2[k];
+    else for (int k = 0; k < 2; k++) cr[RCSB_C_SOLREF + k] = r1[k] < r2[k] ? r1[k] : r2[k];
+    for (int k = 0; k < 5; k++) cr[RCSB_C_SOLIMP + k] = mix * m.g_solimp[g1][k] + (1 - mix) * m.g_solimp[g2][k];
+    for (int k = 0; k < 3; k++) cr[RCSB_C_FRIC + k] = fr[k] < (real)1e-5 ? (real)1e-5 : fr[k];  // slide, spin, roll
+    cr[RCSB_C_MU] = 0;
+  }
+  ncon++;
+}
+
+RCSB_DEV void st_collision(const Ctx& c) {
+  const RcsbModel& m = *c.md;
+  // ---- broad phase: bounding spheres (plane: signed distance), compacted in pair order
+  int ncand = 0;
+  for (int base = 0; base < m.npair; base += RCSB_NLANES) {
+    int p = base + c.lane, hit = 0;
+    if (p < m.npair) {
+      int g1 = m.pair[p][0], g2 = m.pair[p][1];
+      real margin = m.g_margin[g1] > m.g_margin[g2] ? m.g_margin[g1] : m.g_margin[g2];
+      const real *a = WR(gpos) + 3 * g1, *b = WR(gpos) + 3 * g2;
+      real d[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+      if (m.g_type[g1] == RCSB_GEOM_PLANE) {
+        real R[9];
+        quat_to_mat(R, m.g_quat[g1]);  // planes are static in all supported scenes
+        real n[3] = {R[2], R[5], R[8]};
+        hit = !(dot3(d, n) > m.g_rbound[g2] + margin);
+      } else {
+        real bound = m.g_rbound[g1] + m.g_rbound[g2] + margin;
+        hit = !(dot3(d, d) > bound * bound);
+      }
+    }
+#ifdef RCSB_HOST_EMU
+    if (hit) { if (ncand < RCSB_MAXCAND) WI(cand)[ncand] = p; ncand++; }
+#else
+    unsigned mask = warp_ballot(hit);
+    if (hit) {
+      int slot = ncand + __popc(mask & ((1u << c.lane) - 1u));
+      if (slot < RCSB_MAXCAND) WI(cand)[slot] = p;
+    }
+    ncand += __popc(mask);
+#endif
+  }
+  if (ncand > RCSB_MAXCAND) {
+    if (c.lane == 0) WI(misc)[MI_WARN] += 1;
+    ncand = RCSB_MAXCAND;
+  }
+  RCSB_SYNC();
+  // ---- narrow phase, candidates in pair order
+  int ncon = 0;
+  for (int ic = 0; ic < ncand; ic++) {
+    int p = WI(cand)[ic];
+    PairFrames pf;
+    pf.g1 = m.pair[p][0]; pf.g2 = m.pair[p][1];
+    real margin = m.g_margin[pf.g1] > m.g_margin[pf.g2] ? m.g_margin[pf.g1] : m.g_margin[pf.g2];
+    real gap = m.g_gap[pf.g1] > m.g_gap[pf.g2] ? m.g_gap[pf.g1] : m.g_gap[pf.g2];
+    geom_frame(c, pf.g1, pf.p1, pf.R1);
+    geom_frame(c, pf.g2, pf.p2, pf.R2);
+    int t1 = m.g_type[pf.g1], t2 = m.g_type[pf.g2];
+    if (t1 == RCSB_GEOM_PLANE) {
+      real n[3] = {pf.R1[2], pf.R1[5], pf.R1[8]};
+      if (t2 == RCSB_GEOM_MESH) {
+        real nd[3] = {-n[0], -n[1], -n[2]}, v[3], pos[3];
+        support(c, pf.g2, pf.p2, pf.R2, nd, v);
+        real dist = (v[0] - pf.p1[0]) * n[0] + (v[1] - pf.p1[1]) * n[1] + (v[2] - pf.p1[2]) * n[2];
+        if (!(dist > margin)) {
+          for (int k = 0; k < 3; k++) pos[k] = v[k] - (real)0.5 * dist * n[k];
+          add_contact(c, ncon, pf.g1, pf.g2, dist, pos, n, margin, gap);
+        }
+      } else if (t2 == RCSB_GEOM_BOX) {
+        int cnt = 0;
+        for (int i = 0; i < 8 && cnt < 4; i++) {
+          const real* sz = m.g_size[pf.g2];
+          real loc[3] = {(i & 1) ? sz[0] : -sz[0], (i & 2) ? sz[1] : -sz[1], (i & 4) ? sz[2] : -sz[2]}, cw[3], pos[3];
+          mulmat3(cw, pf.R2, loc);
+          cw[0] += pf.p2[0]; cw[1] += pf.p2[1]; cw[2] += pf.p2[2];
+          real dist = (cw[0] - pf.p1[0]) * n[0] + (cw[1] - pf.p1[1]) * n[1] + (cw[2] - pf.p1[2]) * n[2];
+          if (dist > margin) continue;
+          for (int k = 0; k < 3; k++) pos[k] = cw[k] - (real)0.5 * dist * n[k];
+          add_contact(c, ncon, pf.g1, pf.g2, dist, pos, n, margin, gap);
+          cnt++;
+        }
+      } else if (t2 == RCSB_GEOM_CAPSULE) {
+        real r = m.g_size[pf.g2][0], hl = m.g_size[pf.g2][1];
+        real ax[3] = {pf.R2[2] * hl, pf.R2[5] * hl, pf.R2[8] * hl};
+        for (int s = 0; s < 2; s++) {
+          real cw[3], pos[3];
+          for (int k = 0; k < 3; k++) cw[k] = pf.p2[k] + (s == 0 ? ax[k] : -ax[k]);
+          real dist = (cw[0] - pf.p1[0]) * n[0] + (cw[1] - pf.p1[1]) * n[1] + (cw[2] - pf.p1[2]) * n[2] - r;
+          if (dist > margin) continue;
+          for (int k = 0; k < 3; k++) pos[k] = cw[k] - n[k] * (r + (real)0.5 * dist);
+          add_contact(c, ncon, pf.g1, pf.g2, dist, pos, n, margin, gap);
+        }
+      }
+    } else {
+      real depth, dir[3], pos[3];
+      if (mpr_penetration(c, pf, &depth, dir, pos)) add_contact(c, ncon, pf.g1, pf.g2, -depth, pos, dir, margin, gap);
+    }
+  }
+  if (c.lane == 0) { WI(misc)[MI_NCON] = ncon; WI(misc)[MI_NCAND] = ncand; }
+  RCSB_SYNC();
+}

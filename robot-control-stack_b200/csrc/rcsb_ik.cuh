@@ -1,0 +1,237 @@
+// Batched damped-least-squares CLIK: the algorithm of rcs.common.Pin::inverse
+// (/root/reference/src/rcs/Kinematics.cpp:28-68; eps 1e-4, IT_MAX 1000, DT 0.1, damp 1e-6 from
+// include/rcs/Kinematics.h:32-35), which the reference runs on Pinocchio (forwardKinematics,
+// computeFrameJacobian LOCAL, log6, Jlog6, 6x6 LDLT, integrate). One environment per thread: the
+// loop is a ~100-iteration serial chain of tiny dense operations on a 6 x nq Jacobian, so the
+// parallelism is across environments; the 6x6 solves are far too small for tensor-core tiles.
+#pragma once
+#include "rcsb_env.cuh"
+
+enum { IK_SCRATCH_REALS = 8, IK_MAXQ = 9 };
+
+RCSB_DEV void ik_site_fk(const RcsbModel& m, const real* q, int nqm, real* R, real* p, real* J) {
+  // chain root -> site body
+  int chain[RCSB_MAXB], n = 0;
+  for (int b = m.rb_site_body; b >= 0; b = m.b_parent[b]) chain[n++] = b;
+  real pos[3] = {0, 0, 0}, quat[4] = {1, 0, 0, 0}, Rm[9], v[3], qn[4];
+  real anchors[RCSB_MAXB][3], axes[RCSB_MAXB][3];
+  int jtype[RCSB_MAXB], jdof[RCSB_MAXB], nj = 0;
+  for (int ci = n - 1; ci >= 0; ci--) {
+    int b = chain[ci];
+    quat_to_mat(Rm, quat);
+    mulmat3(v, Rm, m.b_pos[b]);
+    pos[0] += v[0]; pos[1] += v[1]; pos[2] += v[2];
+    quat_mul(qn, quat, m.b_quat[b]);
+    quat[0] = qn[0]; quat[1] = qn[1]; quat[2] = qn[2]; quat[3] = qn[3];
+    if (m.b_jtype[b] != RCSB_JNT_FREE) {
+      int qa = m.b_qadr[b];
+      real qj = (qa < nqm ? q[qa] : (real)0) - m.qpos0[qa];
+      quat_to_mat(Rm, quat);
+      mulmat3(axes[nj], Rm, m.b_jaxis[b]);
+      mulmat3(v, Rm, m.b_jpos[b]);
+      anchors[nj][0] = pos[0] + v[0]; anchors[nj][1] = pos[1] + v[1]; anchors[nj][2] = pos[2] + v[2];
+      jtype[nj] = m.b_jtype[b];
+      jdof[nj] = m.b_dadr[b];
+      if (m.b_jtype[b] == RCSB_JNT_SLIDE) {
+        pos[0] += axes[nj][0] * qj; pos[1] += axes[nj][1] * qj; pos[2] += axes[nj][2] * qj;
+      } else {
+        real s = sin((real)0.5 * qj), ql[4] = {cos((real)0.5 * qj), m.b_jaxis[b][0] * s, m.b_jaxis[b][1] * s, m.b_jaxis[b][2] * s};
+        quat_mul(qn, quat, ql);
+        quat[0] = qn[0]; quat[1] = qn[1]; quat[2] = qn[2]; quat[3] = qn[3];
+        quat_to_mat(Rm, quat);
+        mulmat3(v, Rm, m.b_jpos[b]);
+        pos[0] = anchors[nj][0] - v[0]; pos[1] = anchors[nj][1] - v[1]; pos[2] = anchors[nj][2] - v[2];
+      }
+      nj++;
+    }
+    quat_normalize(quat);
+  }
+  real qs[4];
+  quat_to_mat(Rm, quat);
+  mulmat3(v, Rm, m.rb_site_pos);
+  p[0] = pos[0] + v[0]; p[1] = pos[1] + v[1]; p[2] = pos[2] + v[2];
+  quat_mul(qs, quat, m.rb_site_quat);
+  quat_to_mat(R, qs);
+  if (J) {
+    for (int i = 0; i < 6 * nqm; i++) J[i] = 0;
+    for (int a = 0; a < nj; a++) {
+      if (jdof[a] >= nqm) continue;
+      real lin[3], ang[3] = {0, 0, 0}, r[3], l[3], w[3];
+      if (jtype[a] == RCSB_JNT_HINGE) {
+        r[0] = p[0] - anchors[a][0]; r[1] = p[1] - anchors[a][1]; r[2] = p[2] - anchors[a][2];
+        cross3(lin, axes[a], r);
+        copy3(ang, axes[a]);
+      } else {
+        copy3(lin, axes[a]);
+      }
+      mulmatT3(l, R, lin);
+      mulmatT3(w, R, ang);
+      for (int k = 0; k < 3; k++) { J[k * nqm + jdof[a]] = l[k]; J[(3 + k) * nqm + jdof[a]] = w[k]; }
+    }
+  }
+}
+RCSB_DEV void ik_log3(const real* R, real* w, real* theta) {
+  real ct = (real)0.5 * (R[0] + R[4] + R[8] - 1);
+  ct = ct > 1 ? (real)1 : (ct < -1 ? (real)-1 : ct);
+  real t = acos(ct);
+  *theta = t;
+  if (t < (real)1e-8) { w[0] = (real)0.5 * (R[7] - R[5]); w[1] = (real)0.5 * (R[2] - R[6]); w[2] = (real)0.5 * (R[3] - R[1]); return; }
+  if (t > (real)3.14159265358979323846 - (real)1e-4) {
+    real a[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};
+    for (int k = 0; k < 3; k++) {
+      real vv = (real)0.5 * (R[4 * k] - ct) / (1 - ct) * 2;
+      real s = r_sqrt(vv > 0 ? vv * (real)0.5 : (real)0);
+      w[k] = t * (a[k] < 0 ? -s : s);
+    }
+    return;
+  }
+  real f = t / (2 * sin(t));
+  w[0] = f * (R[7] - R[5]); w[1] = f * (R[2] - R[6]); w[2] = f * (R[3] - R[1]);
+}
+RCSB_DEV void ik_log6(const real* R, const real* p, real* out) {
+  real w[3], t, alpha, beta;
+  ik_log3(R, w, &t);
+  real t2 = t * t;
+  if (t < (real)1e-4) { alpha = 1 - t2 / 12 - t2 * t2 / 720; beta = (real)1 / 12 + t2 / 720; }
+  else { real st = sin(t), ct = cos(t); alpha = t * st / (2 * (1 - ct)); beta = 1 / t2 - st / (2 * t * (1 - ct)); }
+  real wxp[3], wp = dot3(w, p);
+  cross3(wxp, w, p);
+  for (int k = 0; k < 3; k++) out[k] = alpha * p[k] - (real)0.5 * wxp[k] + beta * wp * w[k];
+  copy3(out + 3, w);
+}
+RCSB_DEV void ik_skew(const real* v, real* S) {
+  S[0] = 0; S[1] = -v[2]; S[2] = v[1]; S[3] = v[2]; S[4] = 0; S[5] = -v[0]; S[6] = -v[1]; S[7] = v[0]; S[8] = 0;
+}
+RCSB_DEV void ik_jlog6(const real* R, const real* p, real* J6) {
+  real w[3], t;
+  ik_log3(R, w, &t);
+  real TL[9], alpha, diag, S[9];
+  if (t < (real)1e-4) { alpha = (real)1 / 12 + t * t / 720; diag = (real)0.5 * (2 - t * t / 6); }
+  else { real st = sin(t), ct = cos(t); alpha = 1 / (t * t) - st / (2 * t * (1 - ct)); diag = (real)0.5 * (t * st / (1 - ct)); }
+  for (int r = 0; r < 3; r++)
+    for (int cc = 0; cc < 3; cc++) TL[3 * r + cc] = alpha * w[r] * w[cc];
+  TL[0] += diag; TL[4] += diag; TL[8] += diag;
+  ik_skew(w, S);
+  for (int i = 0; i < 9; i++) TL[i] += (real)0.5 * S[i];
+  real t2 = t * t, beta, bdot;
+  if (t < (real)1e-4) { beta = (real)1 / 12 + t2 / 720; bdot = (real)1 / 360; }
+  else {
+    real st = sin(t), ct = cos(t), tinv = 1 / t, t2inv = tinv * tinv, inv = 1 / (2 * (1 - ct));
+    beta = t2inv - st * tinv * inv;
+    bdot = -2 * t2inv * t2inv + (1 + st * tinv) * t2inv * inv;
+  }
+  real wTp = dot3(w, p), v3[3], B[9], TR[9];
+  for (int k = 0; k < 3; k++) v3[k] = (bdot * wTp) * w[k] - (t2 * bdot + 2 * beta) * p[k];
+  ik_skew(p, S);
+  for (int r = 0; r < 3; r++)
+    for (int cc = 0; cc < 3; cc++) B[3 * r + cc] = (real)0.5 * S[3 * r + cc] + v3[r] * w[cc] + beta * w[r] * p[cc];
+  B[0] += wTp * beta; B[4] += wTp * beta; B[8] += wTp * beta;
+  for (int r = 0; r < 3; r++)
+    for (int cc = 0; cc < 3; cc++) TR[3 * r + cc] = B[3 * r] * TL[cc] + B[3 * r + 1] * TL[3 + cc] + B[3 * r + 2] * TL[6 + cc];
+  for (int i = 0; i < 36; i++) J6[i] = 0;
+  for (int r = 0; r < 3; r++)
+    for (int cc = 0; cc < 3; cc++) {
+      J6[6 * r + cc] = TL[3 * r + cc];
+      J6[6 * r + 3 + cc] = TR[3 * r + cc];
+      J6[6 * (3 + r) + 3 + cc] = TL[3 * r + cc];
+    }
+}
+RCSB_DEV void ik_ldlt6(const real* A, real* b) {
+  real Lm[36], D[6];
+  for (int i = 0; i < 36; i++) Lm[i] = 0;
+  for (int j = 0; j < 6; j++) {
+    real s = A[6 * j + j];
+    for (int k = 0; k < j; k++) s -= Lm[6 * j + k] * Lm[6 * j + k] * D[k];
+    D[j] = s;
+    Lm[6 * j + j] = 1;
+    for (int i = j + 1; i < 6; i++) {
+      real t = A[6 * i + j];
+      for (int k = 0; k < j; k++) t -= Lm[6 * i + k] * Lm[6 * j + k] * D[k];
+      Lm[6 * i + j] = t / s;
+    }
+  }
+  for (int i = 0; i < 6; i++) for (int k = 0; k < i; k++) b[i] -= Lm[6 * i + k] * b[k];
+  for (int i = 0; i < 6; i++) b[i] /= D[i];
+  for (int i = 5; i >= 0; i--) for (int k = i + 1; k < 6; k++) b[i] -= Lm[6 * k + i] * b[k];
+}
+
+// returns success; q_out[nqm]
+RCSB_DEV int ik_solve(const RcsbModel& m, const real* pose7, const real* q0, int nq0, real* q_out, int* iters_out) {
+  const int nqm = m.rb_ik_nq < IK_MAXQ ? m.rb_ik_nq : IK_MAXQ;
+  real inv_tcp[7], goal[7], Rd[9];
+  pose_inverse(m.rb_tcp_offset, inv_tcp);
+  pose_mul(pose7, inv_tcp, goal);
+  Quat qg = {goal[3], goal[4], goal[5], goal[6]};
+  q_to_mat(qg, Rd);
+  real q[IK_MAXQ], J[6 * IK_MAXQ], Jn[6 * IK_MAXQ];
+  for (int i = 0; i < nqm; i++) q[i] = i < nq0 ? q0[i] : (real)0;
+  int success = 0, it;
+  for (it = 0;; it++) {
+    real R[9], p[3], Ri[9], pi[3], err[6];
+    ik_site_fk(m, q, nqm, R, p, J);
+    real dp[3] = {goal[0] - p[0], goal[1] - p[1], goal[2] - p[2]};
+    for (int r = 0; r < 3; r++)
+      for (int cc = 0; cc < 3; cc++) Ri[3 * r + cc] = R[r] * Rd[cc] + R[3 + r] * Rd[3 + cc] + R[6 + r] * Rd[6 + cc];
+    mulmatT3(pi, R, dp);
+    ik_log6(Ri, pi, err);
+    real en = 0;
+    for (int k = 0; k < 6; k++) en += err[k] * err[k];
+    if (r_sqrt(en) < (real)1e-4) { success = 1; break; }
+    if (it >= 1000) break;
+    real Rinv[9], pinv[3], Jl[36], JJt[36], y[6];
+    for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) Rinv[3 * r + cc] = Ri[3 * cc + r];
+    mulmat3(pinv, Rinv, pi);
+    pinv[0] = -pinv[0]; pinv[1] = -pinv[1]; pinv[2] = -pinv[2];
+    ik_jlog6(Rinv, pinv, Jl);
+    for (int r = 0; r < 6; r++)
+      for (int cc = 0; cc < nqm; cc++) {
+        real s = 0;
+        for (int k = 0; k < 6; k++) s += Jl[6 * r + k] * J[k * nqm + cc];
+        Jn[r * nqm + cc] = -s;
+      }
+    for (int r = 0; r < 6; r++)
+      for (int cc = 0; cc < 6; cc++) {
+        real s = 0;
+        for (int k = 0; k < nqm; k++) s += Jn[r * nqm + k] * Jn[cc * nqm + k];
+        JJt[6 * r + cc] = s;
+      }
+    for (int k = 0; k < 6; k++) { JJt[7 * k] += (real)1e-6; y[k] = err[k]; }
+    ik_ldlt6(JJt, y);
+    for (int cc = 0; cc < nqm; cc++) {
+      real s = 0;
+      for (int k = 0; k < 6; k++) s += Jn[k * nqm + cc] * y[k];
+      q[cc] += -s * (real)0.1;
+    }
+  }
+  if (iters_out) *iters_out = it;
+  if (success) for (int k = 0; k < nqm; k++) q_out[k] = q[k];
+  return success;
+}
+
+// one environment per thread; apply != 0 restates SimRobot::set_cartesian_position (SimRobot.cpp:145-155)
+RCSB_DEV void ik_env(const RcsbModel* sm, real* /*scratch*/, int /*lane*/, int env, const real* pose, const real* q0,
+                     real* q_out, int* success, int* iters, int apply, real* sr, int* si) {
+  const RcsbModel& m = *sm;
+  const int nj = m.rb_njoints, nqm = m.rb_ik_nq < IK_MAXQ ? m.rb_ik_nq : IK_MAXQ;
+  real q0l[RCSB_MAXJ], q[IK_MAXQ];
+  real* row = sr ? sr + (size_t)env * m.nsr : nullptr;
+  for (int i = 0; i < nj; i++) q0l[i] = apply ? row[m.o_q + m.rb_qadr[i]] : q0[(size_t)env * nj + i];
+  int it = 0;
+  int ok = ik_solve(m, pose + (size_t)env * 7, q0l, nj, q, &it);
+  if (iters) iters[env] = it;
+  if (success) success[env] = ok;
+  if (q_out && ok) for (int i = 0; i < nqm; i++) q_out[(size_t)env * nqm + i] = q[i];
+  if (apply) {
+    int* irow = si + (size_t)env * RCSB_I_TAIL;
+    irow[RCSB_I_IK_SUCCESS] = ok;
+    if (ok) {  // set_joint_position(joint_vals)
+      for (int i = 0; i < nj; i++) {
+        row[m.o_rcs + RCSB_S_TARGET + i] = q[i];
+        row[m.o_rcs + RCSB_S_PREV + i] = row[m.o_q + m.rb_qadr[i]];
+        row[m.o_ctrl + m.rb_act[i]] = q[i];
+      }
+      irow[RCSB_I_MOVING] = 1;
+      irow[RCSB_I_ARRIVED] = 0;
+    }
+  }
+}

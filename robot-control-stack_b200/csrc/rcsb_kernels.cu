@@ -1,0 +1,388 @@
+// CUDA kernels + C ABI (include/rcsb.h) of the batched rigid-body backend. sm_100a only.
+//
+// Execution model: persistent CTAs (one per SM), W warps each, one environment per warp at a time.
+// The model constants are staged once per CTA into shared memory with a TMA bulk copy
+// (cp.async.bulk + mbarrier); each warp owns a private shared-memory workspace that holds the
+// environment's state and every intermediate of the physics step for all substeps of a launch, so
+// HBM is touched once per launch per environment (row in, row out). Warps pull environment indices
+// from a global atomic counter, which load-balances step_until_convergence where environments need
+// different numbers of substeps.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rcsb.h"
+#include "rcsb_env.cuh"
+#include "rcsb_ik.cuh"
+#include "rcsb_layout.h"
+
+// ------------------------------------------------------------------ TMA bulk copy helpers (sm_90+/sm_100a PTX)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+  } while (!ok);
+}
+
+#define RCSB_MODEL_BYTES ((sizeof(RcsbModel) + 15) & ~(size_t)15)
+#define RCSB_SMEM_HEADER (RCSB_MODEL_BYTES + 16)
+// warps per CTA are bounded by the per-warp shared-memory workspace (about 22 KB for the FR3 scenes),
+// so the register budget per thread can be generous
+#define RCSB_MAX_WARPS 10
+
+extern __shared__ __align__(128) unsigned char rcsb_smem[];
+
+__device__ __forceinline__ Ctx make_ctx(const RcsbModel* sm, const real* verts, size_t ws_bytes) {
+  int warp = threadIdx.x >> 5;
+  unsigned char* base = rcsb_smem + RCSB_SMEM_HEADER + (size_t)warp * ws_bytes;
+  Ctx c;
+  c.md = sm;
+  c.w = (real*)base;
+  c.clk = (double*)(base + (size_t)sm->ws_reals * sizeof(real));
+  c.wi = (int*)(base + (size_t)sm->ws_reals * sizeof(real) + (size_t)sm->ws_doubles * sizeof(double));
+  c.verts = verts;
+  c.lane = threadIdx.x & 31;
+  return c;
+}
+__device__ __forceinline__ const RcsbModel* stage_model(const RcsbModel* gm) {
+  RcsbModel* sm = (RcsbModel*)rcsb_smem;
+  uint64_t* bar = (uint64_t*)(rcsb_smem + RCSB_MODEL_BYTES);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, (uint32_t)RCSB_MODEL_BYTES);
+    tma_bulk_g2s(sm, gm, (uint32_t)RCSB_MODEL_BYTES, bar);
+  }
+  mbar_wait(bar, 0);
+  return sm;
+}
+
+// ------------------------------------------------------------------ the per-launch program kernel
+__global__ void __launch_bounds__(RCSB_MAX_WARPS * 32, 1)
+rcsb_k_run(const RcsbModel* __restrict__ gm, const real* __restrict__ verts, real* __restrict__ sr, double* __restrict__ sd,
+           int* __restrict__ si, RcsbLaunch L, int* __restrict__ counter, size_t ws_bytes) {
+  const RcsbModel* sm = stage_model(gm);
+  Ctx c = make_ctx(sm, verts, ws_bytes);
+  for (;;) {
+    int env = 0;
+    if (c.lane == 0) env = atomicAdd(counter, 1);
+    env = __shfl_sync(0xffffffffu, env, 0);
+    if (env >= L.N) break;
+    if (L.mask && !L.mask[env]) continue;
+    load_env(c, sr + (size_t)env * sm->nsr, sd + (size_t)env * RCSB_D_TAIL, si + (size_t)env * RCSB_I_TAIL);
+    run_env_program(c, L, env);
+    store_env(c, sr + (size_t)env * sm->nsr, sd + (size_t)env * RCSB_D_TAIL, si + (size_t)env * RCSB_I_TAIL);
+    __syncwarp();
+  }
+}
+
+// Pin::inverse for every environment, one environment per thread (rcsb_ik.cuh)
+__global__ void __launch_bounds__(128)
+rcsb_k_ik(const RcsbModel* __restrict__ gm, const real* __restrict__ pose, const real* __restrict__ q0, real* __restrict__ q_out,
+          int* __restrict__ success, int* __restrict__ iters, int N, int apply, real* __restrict__ sr, int* __restrict__ si) {
+  const RcsbModel* sm = stage_model(gm);
+  for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < N; env += gridDim.x * blockDim.x)
+    ik_env(sm, nullptr, 0, env, pose, q0, q_out, success, iters, apply, sr, si);
+}
+
+// ------------------------------------------------------------------ host side
+static thread_local std::string g_err;
+static long long g_launches = 0;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_OK(call)                                                                                  \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) return fail(RCSB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct rcsb_model {
+  RcsbModel h;
+  std::vector<real> verts;
+  bool finalized = false;
+  int device = -1;
+  RcsbModel* d_model = nullptr;
+  real* d_verts = nullptr;
+};
+struct rcsb_batch {
+  rcsb_model* m;
+  int n;
+  real* sr; double* sd; int* si;
+  cudaStream_t stream;
+  int* d_counter = nullptr;
+  int warps = 0, grid = 0;
+  size_t smem = 0, ws_bytes = 0;
+  // staging for the host-buffer path
+  real *d_act_joints = nullptr, *d_act_gripper = nullptr, *d_obs = nullptr;
+  int* d_info = nullptr;
+  real *h_act = nullptr, *h_obs = nullptr;
+};
+
+extern "C" {
+const char* rcsb_last_error(void) { return g_err.c_str(); }
+int rcsb_version(void) { return 100; }
+int rcsb_real_bytes(void) { return (int)sizeof(real); }
+long long rcsb_launch_count(void) { return g_launches; }
+
+rcsb_model* rcsb_model_new(void) {
+  rcsb_model* m = new rcsb_model();
+  memset(&m->h, 0, sizeof(RcsbModel));
+  return m;
+}
+void rcsb_model_free(rcsb_model* m) {
+  if (!m) return;
+  if (m->d_model) cudaFree(m->d_model);
+  if (m->d_verts) cudaFree(m->d_verts);
+  delete m;
+}
+int rcsb_model_set_int(rcsb_model* m, const char* field, const int* v, int n) {
+  int rc = rcsb_model_set_field(&m->h, field, v, n, 0);
+  if (rc == -1) return fail(RCSB_ERR_FIELD, std::string("unknown int field ") + field);
+  if (rc == -2) return fail(RCSB_ERR_SIZE, std::string("bad size/type for field ") + field);
+  return RCSB_OK;
+}
+int rcsb_model_set_real(rcsb_model* m, const char* field, const double* v, int n) {
+  int rc = rcsb_model_set_field(&m->h, field, v, n, 1);
+  if (rc == -1) return fail(RCSB_ERR_FIELD, std::string("unknown real field ") + field);
+  if (rc == -2) return fail(RCSB_ERR_SIZE, std::string("bad size/type for field ") + field);
+  return RCSB_OK;
+}
+int rcsb_model_set_mesh_vertices(rcsb_model* m, const double* xyz, int nvert) {
+  m->verts.resize((size_t)3 * (nvert > 0 ? nvert : 1));
+  for (int i = 0; i < 3 * nvert; i++) m->verts[i] = (real)xyz[i];
+  return RCSB_OK;
+}
+int rcsb_model_finalize(rcsb_model* m) {
+  if (rcsb_model_finalize_layout(&m->h) != 0) return fail(RCSB_ERR_MODEL, "model dimensions out of range");
+  if ((m->h.nsr * sizeof(real)) % 16 != 0) return fail(RCSB_ERR_MODEL, "state row is not 16-byte granular");
+  m->finalized = true;
+  return RCSB_OK;
+}
+int rcsb_model_upload(rcsb_model* m, int device) {
+  if (!m->finalized) return fail(RCSB_ERR_MODEL, "rcsb_model_finalize not called");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(RCSB_ERR_CUDA, "no CUDA device: this backend has no CPU execution path");
+  CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(RCSB_ERR_CUDA, "sm_100a (B200) device required");
+  std::vector<unsigned char> padded(RCSB_MODEL_BYTES, 0);
+  memcpy(padded.data(), &m->h, sizeof(RcsbModel));
+  CUDA_OK(cudaMalloc(&m->d_model, RCSB_MODEL_BYTES));
+  CUDA_OK(cudaMemcpy(m->d_model, padded.data(), RCSB_MODEL_BYTES, cudaMemcpyHostToDevice));
+  if (m->verts.empty()) m->verts.resize(3);
+  CUDA_OK(cudaMalloc(&m->d_verts, m->verts.size() * sizeof(real)));
+  CUDA_OK(cudaMemcpy(m->d_verts, m->verts.data(), m->verts.size() * sizeof(real), cudaMemcpyHostToDevice));
+  m->device = device;
+  return RCSB_OK;
+}
+int rcsb_model_dims(const rcsb_model* m, int* nsr, int* nsd, int* nsi, int* obs_dim, int* info_dim) {
+  if (!m->finalized) return fail(RCSB_ERR_MODEL, "rcsb_model_finalize not called");
+  if (nsr) *nsr = m->h.nsr;
+  if (nsd) *nsd = RCSB_D_TAIL;
+  if (nsi) *nsi = RCSB_I_TAIL;
+  if (obs_dim) *obs_dim = RCSB_OBS_DIM;
+  if (info_dim) *info_dim = RCSB_INFO_DIM;
+  return RCSB_OK;
+}
+int rcsb_model_offsets(const rcsb_model* m, int* o_qpos, int* o_qvel, int* o_ctrl, int* o_warm, int* o_tail) {
+  if (!m->finalized) return fail(RCSB_ERR_MODEL, "rcsb_model_finalize not called");
+  if (o_qpos) *o_qpos = m->h.o_q;
+  if (o_qvel) *o_qvel = m->h.o_v;
+  if (o_ctrl) *o_ctrl = m->h.o_ctrl;
+  if (o_warm) *o_warm = m->h.o_warm;
+  if (o_tail) *o_tail = m->h.o_rcs;
+  return RCSB_OK;
+}
+
+rcsb_batch* rcsb_batch_new(rcsb_model* m, int n_envs, void* sr, void* sd, void* si, void* stream) {
+  if (!m || !m->d_model) { fail(RCSB_ERR_MODEL, "model not uploaded (rcsb_model_upload)"); return nullptr; }
+  if (n_envs <= 0 || !sr || !sd || !si) { fail(RCSB_ERR_ARG, "bad batch arguments"); return nullptr; }
+  rcsb_batch* b = new rcsb_batch();
+  b->m = m; b->n = n_envs; b->sr = (real*)sr; b->sd = (double*)sd; b->si = (int*)si; b->stream = (cudaStream_t)stream;
+  cudaSetDevice(m->device);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, m->device);
+  b->ws_bytes = rcsb_ws_bytes(&m->h);
+  size_t avail = prop.sharedMemPerBlockOptin;
+  int w = (int)((avail - RCSB_SMEM_HEADER) / b->ws_bytes);
+  if (w > RCSB_MAX_WARPS) w = RCSB_MAX_WARPS;
+  if (w < 1) { fail(RCSB_ERR_MODEL, "workspace does not fit in shared memory"); delete b; return nullptr; }
+  b->warps = w;
+  b->smem = RCSB_SMEM_HEADER + (size_t)w * b->ws_bytes;
+  b->grid = prop.multiProcessorCount;
+  int need = (n_envs + w - 1) / w;
+  if (b->grid > need) b->grid = need;
+  if (cudaFuncSetAttribute(rcsb_k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem) != cudaSuccess ||
+      cudaFuncSetAttribute(rcsb_k_ik, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCSB_SMEM_HEADER) != cudaSuccess ||
+      cudaMalloc(&b->d_counter, sizeof(int)) != cudaSuccess) {
+    fail(RCSB_ERR_CUDA, std::string("batch setup: ") + cudaGetErrorString(cudaGetLastError()));
+    delete b;
+    return nullptr;
+  }
+  return b;
+}
+void rcsb_batch_free(rcsb_batch* b) {
+  if (!b) return;
+  cudaFree(b->d_counter); cudaFree(b->d_act_joints); cudaFree(b->d_act_gripper); cudaFree(b->d_obs); cudaFree(b->d_info);
+  if (b->h_act) cudaFreeHost(b->h_act);
+  if (b->h_obs) cudaFreeHost(b->h_obs);
+  delete b;
+}
+int rcsb_kernel_occupancy(rcsb_batch* b, int* warps_per_cta, int* smem_bytes, int* grid) {
+  if (warps_per_cta) *warps_per_cta = b->warps;
+  if (smem_bytes) *smem_bytes = (int)b->smem;
+  if (grid) *grid = b->grid;
+  return RCSB_OK;
+}
+
+int rcsb_batch_run(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps, const void* act_joints_dev,
+                   const void* act_gripper_dev, const unsigned char* mask_dev, double max_mov, const double* jlow,
+                   const double* jhigh, void* obs_dev, int* info_dev) {
+  if (!b) return fail(RCSB_ERR_ARG, "null batch");
+  const unsigned needs_joints = RCSB_OP_ACT_JOINTS_REL | RCSB_OP_ACT_JOINTS_ABS | RCSB_OP_SET_JOINTS | RCSB_OP_SET_JOINTS_HARD;
+  if ((ops & needs_joints) && !act_joints_dev) return fail(RCSB_ERR_ARG, "act_joints_dev required for the requested ops");
+  if ((ops & (RCSB_OP_ACT_GRIPPER_BIN | RCSB_OP_SET_GRIPPER)) && !act_gripper_dev)
+    return fail(RCSB_ERR_ARG, "act_gripper_dev required for the requested ops");
+  if ((ops & RCSB_OP_ACT_JOINTS_REL) && (!jlow || !jhigh)) return fail(RCSB_ERR_ARG, "joint limits required");
+  RcsbLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.N = b->n; L.ops = ops; L.k = k; L.max_convergence_steps = max_convergence_steps;
+  L.act_joints = (const real*)act_joints_dev; L.act_gripper = (const real*)act_gripper_dev; L.mask = mask_dev;
+  L.max_mov = (real)max_mov;
+  for (int i = 0; i < b->m->h.rb_njoints && i < RCSB_MAXJ; i++) {
+    L.jlow[i] = jlow ? (real)jlow[i] : 0;
+    L.jhigh[i] = jhigh ? (real)jhigh[i] : 0;
+  }
+  L.obs = (real*)obs_dev; L.info = info_dev;
+  CUDA_OK(cudaSetDevice(b->m->device));
+  CUDA_OK(cudaMemsetAsync(b->d_counter, 0, sizeof(int), b->stream));
+  rcsb_k_run<<<b->grid, b->warps * 32, b->smem, b->stream>>>(b->m->d_model, b->m->d_verts, b->sr, b->sd, b->si, L, b->d_counter,
+                                                            b->ws_bytes);
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return RCSB_OK;
+}
+
+int rcsb_batch_init_state(rcsb_batch* b) {
+  CUDA_OK(cudaSetDevice(b->m->device));
+  CUDA_OK(cudaMemsetAsync(b->sr, 0, (size_t)b->n * b->m->h.nsr * sizeof(real), b->stream));
+  CUDA_OK(cudaMemsetAsync(b->sd, 0, (size_t)b->n * RCSB_D_TAIL * sizeof(double), b->stream));
+  std::vector<int> row(RCSB_I_TAIL, 0), all((size_t)b->n * RCSB_I_TAIL);
+  row[RCSB_I_IK_SUCCESS] = 1;  // SimRobotState::ik_success = true (SimRobot.h:53)
+  row[RCSB_I_CONVERGED] = 1;   // Sim::converged = true (sim.h:46)
+  for (int e = 0; e < b->n; e++) memcpy(&all[(size_t)e * RCSB_I_TAIL], row.data(), sizeof(int) * RCSB_I_TAIL);
+  CUDA_OK(cudaMemcpyAsync(b->si, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  // mj_resetData, then the constructors' m_reset() calls (SimRobot.cpp:42, SimGripper.cpp:38)
+  int rc = rcsb_batch_run(b, RCSB_OP_SIM_RESET | RCSB_OP_ROBOT_RESET | RCSB_OP_GRIPPER_RESET | RCSB_OP_ENV_RESET_FLAGS, 0, 0, nullptr,
+                          nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  return RCSB_OK;
+}
+
+static int ensure_staging(rcsb_batch* b) {
+  if (b->d_act_joints) return RCSB_OK;
+  size_t n = (size_t)b->n;
+  CUDA_OK(cudaMalloc(&b->d_act_joints, n * RCSB_MAXJ * sizeof(real)));
+  CUDA_OK(cudaMalloc(&b->d_act_gripper, n * sizeof(real)));
+  CUDA_OK(cudaMalloc(&b->d_obs, n * RCSB_OBS_DIM * sizeof(real)));
+  CUDA_OK(cudaMalloc(&b->d_info, n * RCSB_INFO_DIM * sizeof(int)));
+  return RCSB_OK;
+}
+int rcsb_batch_run_host(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps, const double* act_joints_host,
+                        const double* act_gripper_host, double max_mov, const double* jlow, const double* jhigh,
+                        double* obs_host, int* info_host) {
+  if (sizeof(real) != sizeof(double)) return fail(RCSB_ERR_ARG, "host-buffer path requires a float64 build");
+  int rc = ensure_staging(b);
+  if (rc) return rc;
+  CUDA_OK(cudaSetDevice(b->m->device));
+  int nj = b->m->h.rb_njoints;
+  if (act_joints_host)
+    CUDA_OK(cudaMemcpyAsync(b->d_act_joints, act_joints_host, (size_t)b->n * nj * sizeof(real), cudaMemcpyHostToDevice, b->stream));
+  if (act_gripper_host)
+    CUDA_OK(cudaMemcpyAsync(b->d_act_gripper, act_gripper_host, (size_t)b->n * sizeof(real), cudaMemcpyHostToDevice, b->stream));
+  rc = rcsb_batch_run(b, ops, k, max_convergence_steps, act_joints_host ? b->d_act_joints : nullptr,
+                      act_gripper_host ? b->d_act_gripper : nullptr, nullptr, max_mov, jlow, jhigh, obs_host ? b->d_obs : nullptr,
+                      info_host ? b->d_info : nullptr);
+  if (rc) return rc;
+  if (obs_host)
+    CUDA_OK(cudaMemcpyAsync(obs_host, b->d_obs, (size_t)b->n * RCSB_OBS_DIM * sizeof(real), cudaMemcpyDeviceToHost, b->stream));
+  if (info_host)
+    CUDA_OK(cudaMemcpyAsync(info_host, b->d_info, (size_t)b->n * RCSB_INFO_DIM * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  return RCSB_OK;
+}
+
+int rcsb_sim_step(rcsb_batch* b, int k) {
+  return rcsb_batch_run(b, RCSB_OP_STEP_K, k, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+}
+int rcsb_sim_step_until_convergence(rcsb_batch* b, int max_steps) {
+  return rcsb_batch_run(b, RCSB_OP_STEP_CONV, 0, max_steps, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+}
+int rcsb_sim_reset(rcsb_batch* b) {
+  return rcsb_batch_run(b, RCSB_OP_SIM_RESET, 0, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+}
+int rcsb_robot_set_joint_position(rcsb_batch* b, const void* q_dev) {
+  return rcsb_batch_run(b, RCSB_OP_SET_JOINTS, 0, 0, q_dev, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+}
+int rcsb_robot_set_joints_hard(rcsb_batch* b, const void* q_dev) {
+  return rcsb_batch_run(b, RCSB_OP_SET_JOINTS_HARD, 0, 0, q_dev, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+}
+int rcsb_robot_reset(rcsb_batch* b) {
+  return rcsb_batch_run(b, RCSB_OP_ROBOT_RESET, 0, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+}
+int rcsb_gripper_set_normalized_width(rcsb_batch* b, const void* width_dev) {
+  return rcsb_batch_run(b, RCSB_OP_SET_GRIPPER, 0, 0, nullptr, width_dev, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+}
+int rcsb_gripper_reset(rcsb_batch* b) {
+  return rcsb_batch_run(b, RCSB_OP_GRIPPER_RESET, 0, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+}
+int rcsb_env_get_obs(rcsb_batch* b, void* obs_dev, int* info_dev) {
+  return rcsb_batch_run(b, RCSB_OP_OBS, 0, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, obs_dev, info_dev);
+}
+
+static int launch_ik(rcsb_batch* b, const void* pose_dev, const void* q0_dev, void* q_out_dev, int* success_dev, int* iters_dev,
+                     int apply) {
+  if (!b || !pose_dev) return fail(RCSB_ERR_ARG, "null argument");
+  CUDA_OK(cudaSetDevice(b->m->device));
+  int threads = 128, grid = (b->n + threads - 1) / threads;
+  rcsb_k_ik<<<grid, threads, RCSB_SMEM_HEADER, b->stream>>>(b->m->d_model, (const real*)pose_dev, (const real*)q0_dev,
+                                                           (real*)q_out_dev, success_dev, iters_dev, b->n, apply, b->sr, b->si);
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return RCSB_OK;
+}
+int rcsb_ik_inverse(rcsb_batch* b, const void* pose_dev, const void* q0_dev, void* q_out_dev, int* success_dev, int* iters_dev) {
+  if (!q0_dev || !q_out_dev || !success_dev) return fail(RCSB_ERR_ARG, "null argument");
+  return launch_ik(b, pose_dev, q0_dev, q_out_dev, success_dev, iters_dev, 0);
+}
+int rcsb_robot_set_cartesian_position(rcsb_batch* b, const void* pose_dev) {
+  return launch_ik(b, pose_dev, nullptr, nullptr, nullptr, nullptr, 1);
+}
+}  // extern "C"

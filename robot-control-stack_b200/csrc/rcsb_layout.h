@@ -1,0 +1,110 @@
+// Host-side helpers shared by the CUDA library and the test-only host emulation build:
+// named-field access to RcsbModel and the per-warp workspace layout.
+#pragma once
+#include <stddef.h>
+#include <string.h>
+
+#include "rcsb_types.h"
+
+struct RcsbField { const char* name; size_t off; size_t bytes; int kind; };  // kind: 0 int32/uint32, 1 real, 2 uint8
+#define RCSB_FI(f) {#f, offsetof(RcsbModel, f), sizeof(((RcsbModel*)0)->f), 0}
+#define RCSB_FR(f) {#f, offsetof(RcsbModel, f), sizeof(((RcsbModel*)0)->f), 1}
+#define RCSB_FB(f) {#f, offsetof(RcsbModel, f), sizeof(((RcsbModel*)0)->f), 2}
+
+static const RcsbField rcsb_model_fields[] = {
+    RCSB_FI(nq), RCSB_FI(nv), RCSB_FI(nu), RCSB_FI(nb), RCSB_FI(ng), RCSB_FI(npair), RCSB_FI(nt), RCSB_FI(neq),
+    RCSB_FI(nroot), RCSB_FI(nmeshvert), RCSB_FI(cone_elliptic), RCSB_FI(implicitfast), RCSB_FI(iterations),
+    RCSB_FI(ls_iterations), RCSB_FI(noslip_iterations), RCSB_FI(maxcon), RCSB_FI(maxefc),
+    RCSB_FR(timestep), RCSB_FR(gravity), RCSB_FR(impratio), RCSB_FR(tolerance), RCSB_FR(ls_tolerance),
+    RCSB_FR(noslip_tolerance), RCSB_FR(meaninertia),
+    RCSB_FI(b_parent), RCSB_FI(b_jtype), RCSB_FI(b_qadr), RCSB_FI(b_dadr), RCSB_FI(b_ndof), RCSB_FI(b_root),
+    RCSB_FI(b_ancmask), RCSB_FI(b_descmask), RCSB_FI(b_dofmask),
+    RCSB_FR(b_pos), RCSB_FR(b_quat), RCSB_FR(b_jpos), RCSB_FR(b_jaxis), RCSB_FR(b_mass), RCSB_FR(b_ipos),
+    RCSB_FR(b_inertia), RCSB_FR(b_gcmass), RCSB_FR(b_gcpos),
+    RCSB_FI(d_body), RCSB_FI(d_qadr), RCSB_FI(d_limited), RCSB_FI(d_actfrclimited), RCSB_FI(d_actgravcomp),
+    RCSB_FI(d_dotzero), RCSB_FI(d_premask), RCSB_FI(d_ancmask),
+    RCSB_FR(d_armature), RCSB_FR(d_damping), RCSB_FR(d_frictionloss), RCSB_FR(d_invweight0), RCSB_FR(d_range),
+    RCSB_FR(d_margin), RCSB_FR(d_solref), RCSB_FR(d_solimp), RCSB_FR(d_actfrcrange), RCSB_FR(qpos0), RCSB_FR(r_invmass),
+    RCSB_FI(g_body), RCSB_FI(g_type), RCSB_FI(g_vertadr), RCSB_FI(g_vertnum), RCSB_FI(g_origid), RCSB_FI(g_role),
+    RCSB_FI(g_condim), RCSB_FI(g_priority),
+    RCSB_FR(g_pos), RCSB_FR(g_quat), RCSB_FR(g_size), RCSB_FR(g_rbound), RCSB_FR(g_aabb), RCSB_FR(g_friction),
+    RCSB_FR(g_solref), RCSB_FR(g_solimp), RCSB_FR(g_solmix), RCSB_FR(g_margin), RCSB_FR(g_gap), RCSB_FR(g_invweight),
+    RCSB_FB(pair),
+    RCSB_FR(t_coef), RCSB_FI(e_dof1), RCSB_FI(e_dof2), RCSB_FI(e_active), RCSB_FR(e_poly), RCSB_FR(e_solref),
+    RCSB_FR(e_solimp),
+    RCSB_FI(a_trntype), RCSB_FI(a_trnid), RCSB_FI(a_ctrllimited), RCSB_FI(a_forcelimited), RCSB_FR(a_gear),
+    RCSB_FR(a_gain), RCSB_FR(a_bias), RCSB_FR(a_ctrlrange), RCSB_FR(a_forcerange),
+    RCSB_FI(rb_njoints), RCSB_FI(rb_qadr), RCSB_FI(rb_act), RCSB_FI(rb_site_body), RCSB_FI(rb_register_convergence),
+    RCSB_FI(rb_ik_nq), RCSB_FR(rb_site_pos), RCSB_FR(rb_site_quat), RCSB_FR(rb_base_pos), RCSB_FR(rb_base_quat),
+    RCSB_FR(rb_tcp_offset), RCSB_FR(rb_q_home), RCSB_FR(rb_joint_tol), RCSB_FR(rb_cb_period),
+    RCSB_FI(gr_enabled), RCSB_FI(gr_act), RCSB_FI(gr_qadr), RCSB_FR(gr_eps_inner), RCSB_FR(gr_eps_outer),
+    RCSB_FR(gr_cb_period), RCSB_FR(gr_max_act), RCSB_FR(gr_min_act), RCSB_FR(gr_max_joint), RCSB_FR(gr_min_joint),
+};
+#define RCSB_NFIELDS ((int)(sizeof(rcsb_model_fields) / sizeof(rcsb_model_fields[0])))
+
+// Set a model field from host doubles / ints. Reals are always passed as double and converted to `real`.
+static inline int rcsb_model_set_field(RcsbModel* m, const char* name, const void* data, int count, int src_is_double) {
+  for (int i = 0; i < RCSB_NFIELDS; i++) {
+    const RcsbField& f = rcsb_model_fields[i];
+    if (strcmp(f.name, name) != 0) continue;
+    char* dst = (char*)m + f.off;
+    if (f.kind == 1) {
+      if (!src_is_double || (size_t)count * sizeof(real) > f.bytes) return -2;
+      for (int k = 0; k < count; k++) ((real*)dst)[k] = (real)((const double*)data)[k];
+    } else if (f.kind == 0) {
+      if (src_is_double || (size_t)count * sizeof(int) > f.bytes) return -2;
+      memcpy(dst, data, (size_t)count * sizeof(int));
+    } else {
+      if (src_is_double || (size_t)count > f.bytes) return -2;
+      for (int k = 0; k < count; k++) ((uint8_t*)dst)[k] = (uint8_t)((const int*)data)[k];
+    }
+    return 0;
+  }
+  return -1;
+}
+
+// Workspace layout. The first nsr reals mirror the env's HBM row: q | v | ctrl | warm | RCS tail.
+static inline int rcsb_model_finalize_layout(RcsbModel* m) {
+  if (m->nq <= 0 || m->nq > RCSB_MAXQ || m->nv <= 0 || m->nv > RCSB_MAXV || m->nu > RCSB_MAXU || m->nb > RCSB_MAXB ||
+      m->ng > RCSB_MAXG || m->npair > RCSB_MAXPAIR || m->nt > RCSB_MAXT || m->neq > RCSB_MAXEQ ||
+      m->nroot > RCSB_MAXROOT || m->rb_njoints > RCSB_MAXJ || m->maxcon < 1 || m->maxefc < 1)
+    return -1;
+  int nq = m->nq, nv = m->nv, nu = m->nu, nb = m->nb, o = 0;
+#define RCSB_ALLOC(field, n) do { m->field = o; o += (n); } while (0)
+  RCSB_ALLOC(o_q, nq); RCSB_ALLOC(o_v, nv); RCSB_ALLOC(o_ctrl, nu); RCSB_ALLOC(o_warm, nv);
+  RCSB_ALLOC(o_rcs, RCSB_S_TAIL);
+  m->nsr = o;
+  m->o_site = m->o_rcs + RCSB_S_SITEPOS;
+  RCSB_ALLOC(o_bpos, 3 * nb); RCSB_ALLOC(o_bquat, 4 * nb); RCSB_ALLOC(o_bmat, 9 * nb); RCSB_ALLOC(o_bcom, 3 * nb);
+  RCSB_ALLOC(o_bgc, 3 * nb); RCSB_ALLOC(o_janchor, 3 * nb); RCSB_ALLOC(o_jaxis, 3 * nb);
+  RCSB_ALLOC(o_rootcom, 3 * m->nroot);
+  RCSB_ALLOC(o_cinert, 10 * nb); RCSB_ALLOC(o_crb, 10 * nb); RCSB_ALLOC(o_cdof, 6 * nv); RCSB_ALLOC(o_cdofdot, 6 * nv);
+  RCSB_ALLOC(o_cvel, 6 * nb); RCSB_ALLOC(o_cacc, 6 * nb); RCSB_ALLOC(o_cfrc, 6 * nb);
+  RCSB_ALLOC(o_M, nv * nv); RCSB_ALLOC(o_L, nv * nv + nv); RCSB_ALLOC(o_H, nv * nv + nv);
+  RCSB_ALLOC(o_bias, nv); RCSB_ALLOC(o_passive, nv); RCSB_ALLOC(o_gravc, nv); RCSB_ALLOC(o_actfrc, nv);
+  RCSB_ALLOC(o_smooth, nv); RCSB_ALLOC(o_qacc_smooth, nv); RCSB_ALLOC(o_qacc, nv); RCSB_ALLOC(o_qfc, nv);
+  RCSB_ALLOC(o_grad, nv); RCSB_ALLOC(o_search, nv); RCSB_ALLOC(o_Ma, nv); RCSB_ALLOC(o_Mv, nv);
+  RCSB_ALLOC(o_tmp, 6 * nv + 2 * nb + 8);
+  RCSB_ALLOC(o_alen, nu); RCSB_ALLOC(o_avel, nu); RCSB_ALLOC(o_aforce, nu);
+  RCSB_ALLOC(o_gpos, 3 * m->ng);
+  RCSB_ALLOC(o_con, RCSB_C_REALS * m->maxcon);
+  RCSB_ALLOC(o_J, m->maxefc * nv);
+  RCSB_ALLOC(o_efc, RCSB_E_NARR * m->maxefc);
+  RCSB_ALLOC(o_conehess, 9 * m->maxcon);
+  RCSB_ALLOC(o_noslip, (nv + 2 * m->maxcon) * nv + nv + 4 * m->maxcon);
+  o = (o + 1) & ~1;  // keep the double clock block 16-byte aligned when real is 8 bytes
+  m->ws_reals = o;
+  m->ws_doubles = RCSB_D_TAIL;
+  o = 0;
+  RCSB_ALLOC(oi_con, RCSB_CI_INTS * m->maxcon);
+  RCSB_ALLOC(oi_efc, RCSB_EI_NARR * m->maxefc);
+  RCSB_ALLOC(oi_cand, RCSB_MAXCAND);
+  RCSB_ALLOC(oi_misc, 8 /* MI_COUNT */ + RCSB_I_TAIL);
+  m->ws_ints = (o + 3) & ~3;
+#undef RCSB_ALLOC
+  return 0;
+}
+static inline size_t rcsb_ws_bytes(const RcsbModel* m) {
+  size_t b = (size_t)m->ws_reals * sizeof(real) + (size_t)m->ws_doubles * sizeof(double) + (size_t)m->ws_ints * sizeof(int);
+  return (b + 15) & ~(size_t)15;
+}

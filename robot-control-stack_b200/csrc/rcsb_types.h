@@ -1,0 +1,127 @@
+// Device-side model and per-environment state layout of the batched rigid-body backend.
+//
+// The model is the "fused" form of the compiled scene (rcs_b200/devmodel.py): bodies without joints
+// are folded into their nearest moving ancestor (or into the world), so the kinematic tree holds one
+// body per joint; only collidable geoms are kept. It restates the mjModel subset that
+// /root/reference/src/sim/{sim,SimRobot,SimGripper}.cpp reach through mjModel*/mjData*.
+#pragma once
+#include <stdint.h>
+
+#ifndef RCSB_REAL
+#define RCSB_REAL double  // reference arithmetic is float64 (mjtNum, Eigen double)
+#endif
+typedef RCSB_REAL real;
+
+enum {
+  RCSB_MAXB = 12,     // moving bodies
+  RCSB_MAXV = 16,     // dofs
+  RCSB_MAXQ = 18,     // qpos
+  RCSB_MAXU = 8,      // actuators
+  RCSB_MAXG = 32,     // collidable geoms
+  RCSB_MAXPAIR = 320, // candidate geom pairs
+  RCSB_MAXT = 2,      // fixed tendons
+  RCSB_MAXEQ = 2,     // joint equalities
+  RCSB_MAXROOT = 4,   // kinematic trees
+  RCSB_MAXJ = 8,      // robot arm joints
+  RCSB_MAXCAND = 64,  // narrowphase candidates per step
+};
+
+enum { RCSB_JNT_FREE = 0, RCSB_JNT_SLIDE = 2, RCSB_JNT_HINGE = 3 };
+enum { RCSB_GEOM_PLANE = 0, RCSB_GEOM_SPHERE = 2, RCSB_GEOM_CAPSULE = 3, RCSB_GEOM_BOX = 6, RCSB_GEOM_MESH = 7 };
+enum { RCSB_TRN_JOINT = 0, RCSB_TRN_TENDON = 3 };
+enum { RCSB_EQ = 0, RCSB_FRICTION_DOF = 1, RCSB_LIMIT = 3, RCSB_CONTACT_PYR = 6, RCSB_CONTACT_ELL = 7 };
+enum { RCSB_SATISFIED = 0, RCSB_QUADRATIC = 1, RCSB_LINEARNEG = 2, RCSB_LINEARPOS = 3, RCSB_CONE = 4 };
+// geom role bits for the RCS collision callbacks (SimRobot.cpp:172-182, SimGripper.cpp:108-130)
+enum { RCSB_ROLE_ARM = 1, RCSB_ROLE_GRIPPER = 2, RCSB_ROLE_FINGER = 4, RCSB_ROLE_IGNORED = 8 };
+// callback kinds, in the registration order of SimRobot / SimGripper constructors
+enum { RCSB_CB_ARRIVED = 0, RCSB_CB_MOVING = 1, RCSB_CB_ROBOT_CONV = 2, RCSB_CB_ROBOT_COLL = 3, RCSB_CB_GRIP_CONV = 4,
+       RCSB_CB_GRIP_COLL = 5, RCSB_NCB = 6 };
+
+struct RcsbModel {
+  // ---- sizes / options
+  int nq, nv, nu, nb, ng, npair, nt, neq, nroot, nmeshvert;
+  int cone_elliptic, implicitfast, iterations, ls_iterations, noslip_iterations;
+  int maxcon, maxefc;  // per-env capacities of the contact / constraint workspaces
+  real timestep, gravity[3], impratio, tolerance, ls_tolerance, noslip_tolerance, meaninertia;
+  // ---- moving bodies (one joint each)
+  int b_parent[RCSB_MAXB], b_jtype[RCSB_MAXB], b_qadr[RCSB_MAXB], b_dadr[RCSB_MAXB], b_ndof[RCSB_MAXB], b_root[RCSB_MAXB];
+  uint32_t b_ancmask[RCSB_MAXB];   // moving-body ancestors incl. self
+  uint32_t b_descmask[RCSB_MAXB];  // descendants incl. self
+  uint32_t b_dofmask[RCSB_MAXB];   // dofs of self and all ancestors
+  real b_pos[RCSB_MAXB][3], b_quat[RCSB_MAXB][4];  // frame in parent moving body (or world) at qpos0
+  real b_jpos[RCSB_MAXB][3], b_jaxis[RCSB_MAXB][3];
+  real b_mass[RCSB_MAXB], b_ipos[RCSB_MAXB][3], b_inertia[RCSB_MAXB][6];  // xx yy zz xy xz yz about COM, body axes
+  real b_gcmass[RCSB_MAXB], b_gcpos[RCSB_MAXB][3];                        // sum(gravcomp*mass) and its centre
+  // ---- dofs
+  int d_body[RCSB_MAXV], d_qadr[RCSB_MAXV], d_limited[RCSB_MAXV], d_actfrclimited[RCSB_MAXV], d_actgravcomp[RCSB_MAXV],
+      d_dotzero[RCSB_MAXV];
+  uint32_t d_premask[RCSB_MAXV];  // dofs whose velocity enters cdof_dot of this dof
+  uint32_t d_ancmask[RCSB_MAXV];  // ancestor dofs incl. self (sparsity of M)
+  real d_armature[RCSB_MAXV], d_damping[RCSB_MAXV], d_frictionloss[RCSB_MAXV], d_invweight0[RCSB_MAXV];
+  real d_range[RCSB_MAXV][2], d_margin[RCSB_MAXV], d_solref[RCSB_MAXV][2], d_solimp[RCSB_MAXV][5],
+      d_actfrcrange[RCSB_MAXV][2];
+  real qpos0[RCSB_MAXQ];
+  // ---- kinematic trees
+  real r_invmass[RCSB_MAXROOT];
+  // ---- collidable geoms
+  int g_body[RCSB_MAXG], g_type[RCSB_MAXG], g_vertadr[RCSB_MAXG], g_vertnum[RCSB_MAXG], g_origid[RCSB_MAXG],
+      g_role[RCSB_MAXG], g_condim[RCSB_MAXG], g_priority[RCSB_MAXG];
+  real g_pos[RCSB_MAXG][3], g_quat[RCSB_MAXG][4];  // in the moving body frame (world frame if g_body < 0)
+  real g_size[RCSB_MAXG][3], g_rbound[RCSB_MAXG], g_aabb[RCSB_MAXG][6], g_friction[RCSB_MAXG][3], g_solref[RCSB_MAXG][2],
+      g_solimp[RCSB_MAXG][5], g_solmix[RCSB_MAXG], g_margin[RCSB_MAXG], g_gap[RCSB_MAXG], g_invweight[RCSB_MAXG];
+  uint8_t pair[RCSB_MAXPAIR][2];  // collidable-geom indices, lower geom type first
+  // ---- tendons, equalities, actuators
+  real t_coef[RCSB_MAXT][RCSB_MAXV];
+  int e_dof1[RCSB_MAXEQ], e_dof2[RCSB_MAXEQ], e_active[RCSB_MAXEQ];
+  real e_poly[RCSB_MAXEQ][5], e_solref[RCSB_MAXEQ][2], e_solimp[RCSB_MAXEQ][5];
+  int a_trntype[RCSB_MAXU], a_trnid[RCSB_MAXU], a_ctrllimited[RCSB_MAXU], a_forcelimited[RCSB_MAXU];
+  real a_gear[RCSB_MAXU], a_gain[RCSB_MAXU], a_bias[RCSB_MAXU][3], a_ctrlrange[RCSB_MAXU][2], a_forcerange[RCSB_MAXU][2];
+  // ---- RCS device layer: SimRobot / SimGripper configuration
+  int rb_njoints, rb_qadr[RCSB_MAXJ], rb_act[RCSB_MAXJ], rb_site_body, rb_register_convergence, rb_ik_nq;
+  real rb_site_pos[3], rb_site_quat[4], rb_base_pos[3], rb_base_quat[4] /* wxyz */, rb_tcp_offset[7] /* xyz+xyzw */;
+  real rb_q_home[RCSB_MAXJ], rb_joint_tol, rb_cb_period;
+  int gr_enabled, gr_act, gr_qadr;
+  real gr_eps_inner, gr_eps_outer, gr_cb_period, gr_max_act, gr_min_act, gr_max_joint, gr_min_joint;
+  // ---- per-warp workspace layout (offsets in reals / ints), filled by rcsb_model_finalize
+  int ws_reals, ws_ints, nsr;  // nsr = reals per env in HBM (dynamic state + RCS tail)
+  int o_q, o_v, o_ctrl, o_warm, o_bpos, o_bquat, o_bmat, o_bcom, o_bgc, o_janchor, o_jaxis, o_rootcom, o_cinert, o_crb,
+      o_cdof, o_cdofdot, o_cvel, o_cacc, o_cfrc, o_M, o_L, o_H, o_bias, o_passive, o_gravc, o_actfrc, o_smooth,
+      o_qacc_smooth, o_qacc, o_qfc, o_grad, o_search, o_Ma, o_Mv, o_tmp, o_alen, o_avel, o_aforce, o_gpos, o_con,
+      o_J, o_efc, o_conehess, o_noslip, o_site, o_rcs;
+  int ws_doubles;  // RCSB_D_TAIL doubles per warp follow the reals
+  int oi_con, oi_efc, oi_cand, oi_misc;
+};
+
+// per-contact record in the workspace (reals)
+enum { RCSB_C_DIST = 0, RCSB_C_POS = 1, RCSB_C_FRAME = 4, RCSB_C_FRIC = 13, RCSB_C_SOLREF = 16, RCSB_C_SOLIMP = 18,
+       RCSB_C_MU = 23, RCSB_C_INCMARGIN = 24, RCSB_C_REALS = 25 };
+enum { RCSB_CI_G0 = 0, RCSB_CI_G1 = 1, RCSB_CI_DIM = 2, RCSB_CI_EFC = 3, RCSB_CI_INTS = 4 };
+// per-constraint-row scalars (reals), stored as arrays of length maxefc each
+enum { RCSB_E_POS = 0, RCSB_E_MARGIN, RCSB_E_FLOSS, RCSB_E_D, RCSB_E_R, RCSB_E_AREF, RCSB_E_FORCE, RCSB_E_JAR, RCSB_E_JV,
+       RCSB_E_B, RCSB_E_K, RCSB_E_NARR };
+enum { RCSB_EI_TYPE = 0, RCSB_EI_ID, RCSB_EI_STATE, RCSB_EI_NARR };
+
+// ---- per-environment persistent state in HBM: struct-of-arrays by field group, env-major rows
+//   sr[N][nsr]  reals  : qpos[nq] qvel[nv] ctrl[nu] qacc_warmstart[nv] | RCS tail (RCSB_S_*)
+//   sd[N][RCSB_D_TAIL] doubles : simulation time and callback clocks (always double: the callback
+//                        cadence depends on float64 accumulation of time, sim.cpp:14-23)
+//   si[N][RCSB_I_TAIL] ints   : flags and counters
+enum {
+  RCSB_S_PREV = 0,                          // previous_angles[MAXJ]   (SimRobotState)
+  RCSB_S_TARGET = RCSB_S_PREV + RCSB_MAXJ,  // target_angles[MAXJ]
+  RCSB_S_GLCW = RCSB_S_TARGET + RCSB_MAXJ,  // gripper last_commanded_width
+  RCSB_S_GLW,                               // gripper last_width
+  RCSB_S_GCMD,                              // GripperWrapper._last_gripper_cmd (-1 = None), base.py:684-735
+  RCSB_S_PREVACT,                           // RobotEnv.prev_action joints[MAXJ], base.py:268-287
+  RCSB_S_SITEPOS = RCSB_S_PREVACT + RCSB_MAXJ,  // attachment site xpos[3] from the last step1
+  RCSB_S_SITEMAT = RCSB_S_SITEPOS + 3,      // attachment site xmat[9]
+  RCSB_S_TAIL = RCSB_S_SITEMAT + 9,
+};
+enum { RCSB_D_TIME = 0, RCSB_D_CBLAST = 1, RCSB_D_TAIL = 1 + RCSB_NCB };
+enum {
+  RCSB_I_IK_SUCCESS = 0, RCSB_I_COLLISION, RCSB_I_MOVING, RCSB_I_ARRIVED, RCSB_I_G_MOVING, RCSB_I_G_COLLISION,
+  RCSB_I_CONVERGED, RCSB_I_CONV_STEPS, RCSB_I_CBRET,  // RCSB_NCB last_return_value flags follow
+  RCSB_I_NCON = RCSB_I_CBRET + RCSB_NCB, RCSB_I_NEFC, RCSB_I_SOLVER_ITER, RCSB_I_WARN, RCSB_I_TOTAL_STEPS,
+  RCSB_I_HAVE_PREV_ACTION,  // RobotEnv.prev_action is not None (base.py:268-272)
+  RCSB_I_TAIL
+};

@@ -1,0 +1,151 @@
+"""Vector Gym-style env over the fused per-env programs of the CUDA backend.
+
+One `step()` is ONE kernel launch that restates, per environment, the reference wrapper stack
+RelativeActionSpace -> GripperWrapperSim -> GripperWrapper -> RobotSimWrapper -> RobotEnv
+(/root/reference/python/rcs/envs/base.py:246-288,469-488,710-735; envs/sim.py:49-76,125-131): action
+transform, gripper command, dedupe against the previous action, set_joint_position, Sim.step(k) or
+step_until_convergence, then the observation / info pack. Keys and conventions follow the reference
+(`tquat` = xyz + quat(xyzw), `joints`, `xyzrpy`, `gripper`; info `collision`, `ik_success`,
+`is_sim_converged`, `gripper_width`, `is_grasped`), with a leading env axis.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from rcs_b200 import _lib, common
+from rcs_b200.envs.base import Box, ControlMode, Dict, RelativeTo
+
+
+class SimVectorEnv:
+    DEFAULT_MAX_JOINT_MOV = np.deg2rad(5)
+
+    def __init__(self, simulation, robot, gripper, control_mode: ControlMode, max_relative_movement=None,
+                 relative_to: RelativeTo = RelativeTo.LAST_STEP, binary_gripper: bool = True):
+        self.sim, self.robot, self.gripper = simulation, robot, gripper
+        self.control_mode, self.relative_to = control_mode, relative_to
+        self.num_envs = simulation.num_envs
+        self.relative = max_relative_movement is not None
+        self.max_mov = max_relative_movement
+        b = simulation.batch
+        self.dev = b.dev
+        meta = common.robots_meta_config(robot.get_config().robot_type)
+        self.jlow, self.jhigh = meta.joint_limits[0].copy(), meta.joint_limits[1].copy()
+        self.dof = meta.dof
+        if control_mode != ControlMode.JOINTS and self.relative:
+            raise NotImplementedError("relative Cartesian actions are a 'next' row; use absolute TQuat/TRPY or JOINTS")
+        if self.relative and relative_to != RelativeTo.LAST_STEP:
+            raise NotImplementedError("RelativeTo.CONFIGURED_ORIGIN")
+        if not binary_gripper:
+            raise NotImplementedError("continuous gripper actions")
+        spaces = {}
+        if control_mode == ControlMode.JOINTS:
+            if self.relative:
+                assert isinstance(self.max_mov, float), "in joint control max_mov must be a float (rad)"
+                spaces["joints"] = Box([-self.max_mov] * self.dof, [self.max_mov] * self.dof, self.dev)
+            else:
+                spaces["joints"] = Box(self.jlow, self.jhigh, self.dev)
+        elif control_mode == ControlMode.CARTESIAN_TRPY:
+            spaces["xyzrpy"] = Box([-0.855, -0.855, 0, -np.pi, -np.pi, -np.pi], [0.855, 0.855, 1.188, np.pi, np.pi, np.pi], self.dev)
+        else:
+            spaces["tquat"] = Box([-0.855, -0.855, 0, -1, -1, -1, -1], [0.855, 0.855, 1.188, 1, 1, 1, 1], self.dev)
+        if gripper is not None:
+            spaces["gripper"] = Box(np.zeros(()), np.ones(()), self.dev)
+        self.action_space = Dict(spaces, self.num_envs)
+        self._zeros = torch.zeros(self.num_envs, dtype=torch.float64, device=self.dev)
+        self._false = torch.zeros(self.num_envs, dtype=torch.bool, device=self.dev)
+        # pinned host staging for the host-buffer path
+        self._h_act = self._h_grip = self._h_obs = self._h_info = None
+
+    # ------------------------------------------------------------------ helpers
+    def _substeps(self):
+        cfg = self.sim.get_config()
+        return round(1 / cfg.frequency / self.sim.model.opt.timestep)  # envs/sim.py:53
+
+    def _step_ops(self):
+        cfg = self.sim.get_config()
+        ops = _lib.OBS | (_lib.STEP_K if cfg.async_control else _lib.STEP_CONV)
+        if self.control_mode == ControlMode.JOINTS:
+            ops |= _lib.ACT_JOINTS_REL if self.relative else _lib.ACT_JOINTS_ABS
+        if self.gripper is not None:
+            ops |= _lib.ACT_GRIPPER_BIN
+        return ops, cfg
+
+    def _pack(self):
+        b = self.sim.batch
+        o, f = b.obs, b.info
+        obs = {"tquat": o[:, 0:7], "joints": o[:, 7:7 + self.dof], "xyzrpy": o[:, 14:20]}
+        info = {"collision": f[:, 0].bool(), "ik_success": f[:, 1].bool(), "is_sim_converged": f[:, 2].bool()}
+        if self.gripper is not None:
+            obs["gripper"] = o[:, 20]
+            info["gripper_width"] = o[:, 21]
+            info["is_grasped"] = f[:, 3].bool()
+        return obs, info, f[:, 4].bool()
+
+    # ------------------------------------------------------------------ gym API
+    def reset(self, seed=None, options=None):
+        """envs/sim.py:68-76 under base.py:703-708 and base.py:462-467: gripper.reset(); sim.reset();
+        robot.reset(); sim.step(1); get_obs()."""
+        b = self.sim.batch
+        ops = _lib.SIM_RESET | _lib.ROBOT_RESET | _lib.ENV_RESET_FLAGS | _lib.STEP_K | _lib.OBS
+        if self.gripper is not None:
+            ops |= _lib.GRIPPER_RESET
+        b.run(ops, k=1, want_obs=True)
+        obs, info, _ = self._pack()
+        return obs, {}
+
+    def step(self, action: dict):
+        b = self.sim.batch
+        ops, cfg = self._step_ops()
+        aj = ag = None
+        if self.control_mode == ControlMode.JOINTS:
+            if "joints" not in action:
+                raise RuntimeError("Given type is not matching control mode!")  # base.py:257-266
+            aj = action["joints"].to(device=self.dev, dtype=torch.float64).contiguous()
+        else:
+            key = "xyzrpy" if self.control_mode == ControlMode.CARTESIAN_TRPY else "tquat"
+            if key not in action:
+                raise RuntimeError("Given type is not matching control mode!")
+            self.robot.set_cartesian_position(self._to_pose7(action[key]))
+        if self.gripper is not None:
+            assert "gripper" in action, "Gripper action not found."  # base.py:724
+            ag = action["gripper"].to(device=self.dev, dtype=torch.float64).reshape(-1).contiguous()
+        b.run(ops, k=self._substeps(), max_convergence_steps=cfg.max_convergence_steps, act_joints=aj, act_gripper=ag,
+              max_mov=float(self.max_mov) if (self.relative and self.control_mode == ControlMode.JOINTS) else 0.0,
+              jlow=self.jlow, jhigh=self.jhigh, want_obs=True)
+        obs, info, truncated = self._pack()
+        return obs, self._zeros, self._false, truncated, info
+
+    def _to_pose7(self, a: torch.Tensor) -> torch.Tensor:
+        a = a.to(device=self.dev, dtype=torch.float64)
+        if a.shape[-1] == 7:
+            q = a[:, 3:7]
+            return torch.cat([a[:, :3], q / q.norm(dim=1, keepdim=True)], dim=1).contiguous()
+        r, p, y = a[:, 3] / 2, a[:, 4] / 2, a[:, 5] / 2  # Rz(yaw) Ry(pitch) Rx(roll), Pose.h:37-43
+        cr, sr, cp, sp, cy, sy = r.cos(), r.sin(), p.cos(), p.sin(), y.cos(), y.sin()
+        q = torch.stack([sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy,
+                         cr * cp * cy + sr * sp * sy], dim=1)
+        return torch.cat([a[:, :3], q], dim=1).contiguous()
+
+    # ------------------------------------------------------------------ host-buffer path (what a CPU-side policy sees)
+    def step_host(self, joints_host: torch.Tensor, gripper_host: torch.Tensor | None):
+        """Same step through pinned HOST buffers: H2D of the actions, the fused launch, D2H of obs/info and a
+        stream synchronise all happen inside the call. Returns (obs_host [N,22], info_host [N,8]) pinned tensors."""
+        b = self.sim.batch
+        if self._h_obs is None:
+            self._h_obs = torch.zeros((self.num_envs, b.model.obs_dim), dtype=torch.float64).pin_memory()
+            self._h_info = torch.zeros((self.num_envs, b.model.info_dim), dtype=torch.int32).pin_memory()
+        ops, cfg = self._step_ops()
+        b.run_host(ops, self._substeps(), cfg.max_convergence_steps, joints_host, gripper_host,
+                   float(self.max_mov) if self.relative else 0.0, self.jlow, self.jhigh, self._h_obs, self._h_info)
+        return self._h_obs, self._h_info
+
+    def close(self):
+        pass
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def get_wrapper_attr(self, name):
+        return getattr(self, name)

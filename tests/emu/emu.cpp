@@ -1,0 +1,53 @@
+// TEST INFRASTRUCTURE ONLY. Host emulation of the per-warp device code (csrc/*.cuh compiled with
+// RCSB_HOST_EMU: one host "lane", barriers/shuffles are no-ops). It lets the CPU-only test tier check
+// the kernel *source logic* against the oracle without a GPU. It is never built into, linked by or
+// reachable from the shipped library (robot-control-stack_b200/csrc/librcsb.so), which has no CPU path.
+#define RCSB_HOST_EMU 1
+#include <stdlib.h>
+#include <vector>
+
+#include "../../robot-control-stack_b200/csrc/rcsb_env.cuh"
+#include "../../robot-control-stack_b200/csrc/rcsb_layout.h"
+
+extern "C" {
+RcsbModel* emu_model_new() { return (RcsbModel*)calloc(1, sizeof(RcsbModel)); }
+void emu_model_free(RcsbModel* m) { free(m); }
+int emu_model_set_int(RcsbModel* m, const char* f, const int* v, int n) { return rcsb_model_set_field(m, f, v, n, 0); }
+int emu_model_set_real(RcsbModel* m, const char* f, const double* v, int n) { return rcsb_model_set_field(m, f, v, n, 1); }
+int emu_model_finalize(RcsbModel* m) { return rcsb_model_finalize_layout(m); }
+int emu_nsr(const RcsbModel* m) { return m->nsr; }
+int emu_sizes(int* out) { out[0] = RCSB_S_TAIL; out[1] = RCSB_D_TAIL; out[2] = RCSB_I_TAIL; out[3] = RCSB_OBS_DIM; out[4] = RCSB_INFO_DIM; out[5] = (int)sizeof(real); return 0; }
+
+// run the per-launch program over N environments, serially
+void emu_run(const RcsbModel* m, const real* verts, real* sr, double* sd, int* si, int N, unsigned ops, int k,
+             int max_conv, const real* act_joints, const real* act_gripper, const unsigned char* mask, real max_mov,
+             const real* jlow, const real* jhigh, real* obs, int* info, real* dbg_ws) {
+  std::vector<real> w(m->ws_reals);
+  std::vector<int> wi(m->ws_ints);
+  double clk[RCSB_D_TAIL];
+  RcsbLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.N = N; L.ops = ops; L.k = k; L.max_convergence_steps = max_conv;
+  L.act_joints = act_joints; L.act_gripper = act_gripper; L.mask = mask; L.max_mov = max_mov;
+  for (int i = 0; i < RCSB_MAXJ; i++) { L.jlow[i] = jlow ? jlow[i] : 0; L.jhigh[i] = jhigh ? jhigh[i] : 0; }
+  L.obs = obs; L.info = info;
+  for (int e = 0; e < N; e++) {
+    if (mask && !mask[e]) continue;
+    Ctx c = {m, w.data(), wi.data(), verts, clk, 0};
+    load_env(c, sr + (size_t)e * m->nsr, sd + (size_t)e * RCSB_D_TAIL, si + (size_t)e * RCSB_I_TAIL);
+    run_env_program(c, L, e);
+    store_env(c, sr + (size_t)e * m->nsr, sd + (size_t)e * RCSB_D_TAIL, si + (size_t)e * RCSB_I_TAIL);
+    if (dbg_ws) memcpy(dbg_ws + (size_t)e * m->ws_reals, w.data(), sizeof(real) * m->ws_reals);
+  }
+}
+int emu_offset(const RcsbModel* m, const char* name) {
+#define OFF(n) if (!strcmp(name, #n)) return m->o_##n;
+  OFF(q) OFF(v) OFF(ctrl) OFF(warm) OFF(bpos) OFF(bquat) OFF(bmat) OFF(bcom) OFF(rootcom) OFF(cinert) OFF(crb) OFF(cdof)
+  OFF(M) OFF(L) OFF(H) OFF(bias) OFF(passive) OFF(gravc) OFF(actfrc) OFF(smooth) OFF(qacc_smooth) OFF(qacc) OFF(qfc)
+  OFF(gpos) OFF(con) OFF(J) OFF(efc) OFF(rcs)
+#undef OFF
+  if (!strcmp(name, "ws_reals")) return m->ws_reals;
+  if (!strcmp(name, "maxefc")) return m->maxefc;
+  return -1;
+}
+}

@@ -1,0 +1,85 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes driver of tests/emu/libemu.so (host emulation of the device code)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "..", "..", "robot-control-stack_b200", "csrc")
+
+
+def build(reverse=False):
+    so = os.path.join(_HERE, "libemu_rev.so" if reverse else "libemu.so")
+    srcs = [os.path.join(_HERE, "emu.cpp")] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".h"))]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unused-function", "-o", so, os.path.join(_HERE, "emu.cpp")]
+        if reverse:
+            cmd.insert(1, "-DRCSB_EMU_REVERSE=1")
+        subprocess.check_call(cmd)
+    return so
+
+
+OPS = dict(GRIPPER_RESET=1, SIM_RESET=2, ROBOT_RESET=4, ENV_RESET_FLAGS=8, ACT_JOINTS_REL=16, ACT_JOINTS_ABS=32,
+           ACT_GRIPPER_BIN=64, SET_JOINTS=128, SET_GRIPPER=256, SET_JOINTS_HARD=512, STEP_K=1024, STEP_CONV=2048, OBS=4096)
+
+
+class Emu:
+    def __init__(self, fields, verts, N, reverse=False):
+        L = C.CDLL(build(reverse))
+        self.L = L
+        vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
+        L.emu_model_new.restype = vp
+        L.emu_model_set_int.argtypes = [vp, C.c_char_p, ip, C.c_int]
+        L.emu_model_set_real.argtypes = [vp, C.c_char_p, dp, C.c_int]
+        L.emu_model_finalize.argtypes = [vp]
+        L.emu_nsr.argtypes = [vp]
+        L.emu_offset.argtypes = [vp, C.c_char_p]
+        L.emu_run.argtypes = [vp, dp, dp, dp, ip, C.c_int, C.c_uint, C.c_int, C.c_int, dp, dp, C.c_void_p, C.c_double,
+                              dp, dp, dp, ip, dp]
+        self.m = L.emu_model_new()
+        for name, (arr, is_real) in fields.items():
+            a = np.ascontiguousarray(arr).ravel()
+            if is_real:
+                rc = L.emu_model_set_real(self.m, name.encode(), a.ctypes.data_as(dp), a.size)
+            else:
+                rc = L.emu_model_set_int(self.m, name.encode(), a.ctypes.data_as(ip), a.size)
+            assert rc == 0, (name, rc)
+        assert L.emu_model_finalize(self.m) == 0
+        sz = (C.c_int * 6)()
+        L.emu_sizes(sz)
+        self.S_TAIL, self.D_TAIL, self.I_TAIL, self.OBS_DIM, self.INFO_DIM, self.real_bytes = list(sz)
+        assert self.real_bytes == 8
+        self.nsr = L.emu_nsr(self.m)
+        self.N = N
+        self.verts = np.ascontiguousarray(verts, dtype=np.float64)
+        self.sr = np.zeros((N, self.nsr))
+        self.sd = np.zeros((N, self.D_TAIL))
+        self.si = np.zeros((N, self.I_TAIL), dtype=np.int32)
+        self.si[:, 0] = 1  # ik_success = true (SimRobotState default)
+        self.obs = np.zeros((N, self.OBS_DIM))
+        self.info = np.zeros((N, self.INFO_DIM), dtype=np.int32)
+        self.ws = np.zeros((N, self.off("ws_reals")))
+
+    def off(self, name):
+        return self.L.emu_offset(self.m, name.encode())
+
+    def run(self, ops, k=0, max_conv=500, act_joints=None, act_gripper=None, max_mov=0.0, jlow=None, jhigh=None):
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+        code = 0
+        for o in ops:
+            code |= OPS[o]
+        aj = np.ascontiguousarray(act_joints, dtype=np.float64) if act_joints is not None else None
+        ag = np.ascontiguousarray(act_gripper, dtype=np.float64) if act_gripper is not None else None
+        lo = np.zeros(8); hi = np.zeros(8)
+        if jlow is not None:
+            lo[:len(jlow)] = jlow; hi[:len(jhigh)] = jhigh
+        self.L.emu_run(self.m, self.verts.ctypes.data_as(dp), self.sr.ctypes.data_as(dp), self.sd.ctypes.data_as(dp),
+                       self.si.ctypes.data_as(ip), self.N, code, k, max_conv,
+                       aj.ctypes.data_as(dp) if aj is not None else None, ag.ctypes.data_as(dp) if ag is not None else None,
+                       None, float(max_mov), lo.ctypes.data_as(dp), hi.ctypes.data_as(dp), self.obs.ctypes.data_as(dp),
+                       self.info.ctypes.data_as(ip), self.ws.ctypes.data_as(dp))
+
+    def wsf(self, name, n, env=0):
+        o = self.off(name)
+        return self.ws[env, o:o + n]

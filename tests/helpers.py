@@ -1,0 +1,55 @@
+"""Shared fixtures for the parity tests: compiled scene, oracle objects, config objects."""
+import os
+import sys
+from types import SimpleNamespace as NS
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "robot-control-stack_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from rcs_b200 import mjcf  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+MODELS = os.path.join(ROOT, "robot-control-stack_b200", "rcs_b200", "models")
+Q_HOME = np.array([0, -np.pi / 4, 0, -3 * np.pi / 4, 0, np.pi / 2, np.pi / 4])
+JLOW = np.array([-2.3093, -1.5133, -2.4937, -2.7478, -2.4800, 0.8521, -2.6895])
+JHIGH = np.array([2.3093, 1.5133, 2.4937, -0.4461, 2.4800, 4.2094, 2.6895])
+_cache = {}
+
+
+def scene(name="fr3_empty_world"):
+    if name not in _cache:
+        _cache[name] = mjcf.load_model(os.path.join(MODELS, name + ".npz"))
+    return _cache[name]
+
+
+def robot_ns(tcp=(0, 0, 0, 0, 0, 0, 1.0)):
+    return NS(joints=[f"fr3_joint{i}_0" for i in range(1, 8)], actuators=[f"fr3_joint{i}_0" for i in range(1, 8)],
+              arm_collision_geoms=[f"fr3_link{i}_collision_0" for i in range(8)], attachment_site="attachment_site_0",
+              base="base_0", tcp_offset=list(tcp), q_home=Q_HOME, joint_rotational_tolerance=0.05 * np.pi / 180,
+              seconds_between_callbacks=0.1, register_convergence_callback=True, ik_nq=9)
+
+
+def gripper_ns():
+    return NS(actuator="actuator8_0", joint="finger_joint1_0",
+              collision_geoms=["hand_c_0", "d435i_collision_0", "finger_0_left_0", "finger_0_right_0"],
+              collision_geoms_fingers=["finger_0_left_0", "finger_0_right_0"], ignored_collision_geoms=[],
+              epsilon_inner=0.005, epsilon_outer=0.005, seconds_between_callbacks=0.05, max_actuator_width=255.0,
+              min_actuator_width=0.0, max_joint_width=0.04, min_joint_width=0.0)
+
+
+def oracle_sim(M, tcp=None):
+    m = O.Model(M)
+    return m, O.Sim(m, O.robot_cfg(M, tcp_offset=tcp), O.gripper_cfg(M))
+
+
+def workload_actions(nenv, nsteps, seed=0):
+    """joints ~ U(-0.0873, 0.0873)^7, gripper ~ Bernoulli(0.5), env-major."""
+    rng = np.random.default_rng(seed)
+    a = np.zeros((nenv, nsteps, 8))
+    a[:, :, :7] = rng.uniform(-np.deg2rad(5), np.deg2rad(5), (nenv, nsteps, 7))
+    a[:, :, 7] = rng.integers(0, 2, (nenv, nsteps))
+    return a

@@ -1,0 +1,149 @@
+"""GPU parity proper: CUDA kernels (through the C ABI) vs the CPU oracle on identical inputs.
+
+Tolerances (float64 on both sides; the two implementations differ structurally -- fused body tree,
+mask-based recursions, warp-parallel reductions -- so agreement is to rounding, not bitwise):
+  qpos / qvel after one step from identical state .... 1e-12 abs
+  trajectories of <= 170 steps ........................ 1e-9 abs
+  contact pair indexing (geom ids, count) ............. exact
+"""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from helpers import O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from rcs_b200 import _lib, batch
+    M = H.scene()
+    dm = batch.DeviceModel(M, H.robot_ns(), H.gripper_ns())
+    return M, dm, _lib, batch
+
+
+def test_library_is_cuda(setup):
+    M, dm, _lib, batch = setup
+    assert _lib.lib().rcsb_real_bytes() == 8
+    assert torch.cuda.is_available()
+
+
+def test_single_step_parity_random_states(setup):
+    M, dm, _lib, batch = setup
+    N = 256
+    b = batch.Batch(dm, N)
+    rng = np.random.default_rng(1)
+    q = np.zeros((N, 9)); v = np.zeros((N, 9)); ctrl = np.zeros((N, 8))
+    q[:, :7] = H.Q_HOME + rng.uniform(-0.4, 0.4, (N, 7))
+    q[:, 7] = q[:, 8] = rng.uniform(0.001, 0.039, N)
+    v[:, :7] = rng.uniform(-1, 1, (N, 7)); v[:, 7] = v[:, 8] = rng.uniform(-0.05, 0.05, N)
+    ctrl[:, :7] = q[:, :7] + rng.uniform(-0.2, 0.2, (N, 7)); ctrl[:, 7] = rng.uniform(0, 255, N)
+    b.qpos.copy_(torch.as_tensor(q)); b.qvel.copy_(torch.as_tensor(v)); b.ctrl.copy_(torch.as_tensor(ctrl))
+    b.run(_lib.STEP_K, k=1)
+    torch.cuda.synchronize()
+    gq, gv, gw = b.qpos.cpu().numpy(), b.qvel.cpu().numpy(), b.qacc_warmstart.cpu().numpy()
+    m = O.Model(M)
+    for e in range(N):
+        d = O.Data(m)
+        d.qpos[:] = q[e]; d.qvel[:] = v[e]; d.ctrl[:] = ctrl[e]
+        d.step()
+        assert np.abs(gq[e] - d.qpos).max() < 1e-12
+        assert np.abs(gv[e] - d.qvel).max() < 1e-11
+        assert np.abs(gw[e] - d.qacc_warmstart).max() < 1e-7 * max(1.0, np.abs(d.qacc_warmstart).max())
+
+
+def test_env_workload_trajectory_parity(setup):
+    """The benchmark workload (JOINTS relative, binary gripper, async 17 substeps, reset every 10 steps)
+    for 16 envs x 20 steps against the oracle's env loop: observations must agree."""
+    M, dm, _lib, batch = setup
+    N, T = 16, 20
+    acts = H.workload_actions(N, T, seed=0)
+    m = O.Model(M)
+    sec, psteps, ref_obs = O.bench_env_steps(m, O.robot_cfg(M), O.gripper_cfg(M), acts, nthreads=4, episode_len=10,
+                                             async_control=True, joint_low=H.JLOW, joint_high=H.JHIGH, want_obs=True)
+    b = batch.Batch(dm, N)
+    reset_ops = _lib.GRIPPER_RESET | _lib.SIM_RESET | _lib.ROBOT_RESET | _lib.ENV_RESET_FLAGS | _lib.STEP_K | _lib.OBS
+    step_ops = _lib.ACT_JOINTS_REL | _lib.ACT_GRIPPER_BIN | _lib.STEP_K | _lib.OBS
+    b.run(reset_ops, k=1, want_obs=True)
+    worst = 0.0
+    for t in range(T):
+        if t > 0 and t % 10 == 0:
+            b.run(reset_ops, k=1, want_obs=True)
+        aj = torch.as_tensor(acts[:, t, :7].copy(), device=b.dev)
+        ag = torch.as_tensor(acts[:, t, 7].copy(), device=b.dev)
+        b.run(step_ops, k=17, act_joints=aj, act_gripper=ag, max_mov=np.deg2rad(5), jlow=H.JLOW, jhigh=H.JHIGH, want_obs=True)
+        g = b.obs.cpu().numpy()
+        # tquat, joints, gripper: direct compare; xyzrpy: compare only away from the Eigen euler branch cut
+        err = np.abs(g[:, :14] - ref_obs[:, t, :14]).max()
+        worst = max(worst, err)
+        assert err < 1e-9, (t, err)
+        assert np.array_equal(g[:, 20], ref_obs[:, t, 20])
+        safe = np.abs(np.abs(ref_obs[:, t, 19]) - np.pi / 2) < 1.4  # yaw well inside (0, pi)
+        safe &= (ref_obs[:, t, 19] > 0.05) & (ref_obs[:, t, 19] < np.pi - 0.05)
+        assert np.abs(g[safe, 14:20] - ref_obs[safe, t, 14:20]).max(initial=0) < 1e-8
+    print("worst obs error", worst)
+
+
+def test_floor_collision_contacts_exact(setup):
+    """Arm driven into the floor (the reference's own collision test pose, python/tests/test_sim_envs.py:347-360):
+    contact count and geom pair indexing must match the oracle exactly while the contact is well-conditioned;
+    state must stay within 1e-6."""
+    M, dm, _lib, batch = setup
+    N = 4
+    b = batch.Batch(dm, N)
+    m, s = H.oracle_sim(M)
+    tgt = np.array([0, 1.78, 0, -1.45, 0, 0, 0.0])
+    s.gripper_reset(); s.reset(); s.robot_reset(); s.step(1)
+    b.run(_lib.GRIPPER_RESET | _lib.SIM_RESET | _lib.ROBOT_RESET | _lib.ENV_RESET_FLAGS | _lib.STEP_K, k=1)
+    s.set_joint_position(tgt)
+    b.run(_lib.SET_JOINTS, act_joints=torch.as_tensor(np.tile(tgt, (N, 1)), device=b.dev))
+    hit = False
+    for it in range(40):
+        s.step(10)
+        b.run(_lib.STEP_K, k=10)
+        ncon = int(b.si[0, 14].item())
+        assert ncon == int(s.data.ncon[0]), it
+        hit |= ncon > 0
+        assert np.abs(b.qpos[0].cpu().numpy() - s.data.qpos).max() < 1e-6, it
+        assert np.abs(b.qvel[0].cpu().numpy() - s.data.qvel).max() < 1e-4, it
+    assert hit
+
+
+def test_step_until_convergence_parity(setup):
+    M, dm, _lib, batch = setup
+    N = 8
+    rng = np.random.default_rng(3)
+    b = batch.Batch(dm, N)
+    b.run(_lib.GRIPPER_RESET | _lib.SIM_RESET | _lib.ROBOT_RESET | _lib.ENV_RESET_FLAGS | _lib.STEP_K, k=1)
+    tg = H.Q_HOME + rng.uniform(-0.3, 0.3, (N, 7))
+    b.run(_lib.SET_JOINTS | _lib.STEP_CONV, max_convergence_steps=500, act_joints=torch.as_tensor(tg, device=b.dev))
+    steps = b.si[:, 7].cpu().numpy(); conv = b.si[:, 6].cpu().numpy()
+    for e in range(N):
+        m, s = H.oracle_sim(M)
+        s.gripper_reset(); s.reset(); s.robot_reset(); s.step(1)
+        s.set_joint_position(tg[e]); s.step_until_convergence()
+        assert s.convergence_steps() == steps[e]
+        assert s.is_converged() == bool(conv[e])
+        assert np.abs(b.qpos[e].cpu().numpy() - s.data.qpos).max() < 1e-9
+
+
+def test_ik_parity(setup):
+    M, dm, _lib, batch = setup
+    N = 64
+    rng = np.random.default_rng(5)
+    b = batch.Batch(dm, N)
+    m = O.Model(M)
+    site = O.robot_cfg(M).attachment_site
+    poses = np.zeros((N, 7)); q0 = np.tile(H.Q_HOME, (N, 1))
+    for e in range(N):
+        qt = H.Q_HOME + rng.uniform(-0.3, 0.3, 7)
+        poses[e] = O.ik_forward(m, site, 9, qt)
+    q, ok, it = b.ik_inverse(torch.as_tensor(poses, device=b.dev), torch.as_tensor(q0, device=b.dev))
+    q, ok, it = q.cpu().numpy(), ok.cpu().numpy(), it.cpu().numpy()
+    for e in range(N):
+        qr, itr = O.ik_inverse(m, site, 9, poses[e], q0[e])
+        assert (qr is not None) == bool(ok[e])
+        assert itr == it[e]
+        assert np.abs(qr - q[e]).max() < 1e-9
