@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: env-steps/sec, FR3 joint control (BASELINE.json metric).
+
+Workload: fr3_empty_world, ControlMode.JOINTS relative to the last
+step with max_relative_movement = 5 deg, binary gripper, SimConfig(async_control=True, frequency=30) => 17
+physics substeps per env.step(); actions joints ~ U(-5deg, 5deg)^7, gripper ~ Bernoulli(0.5), seed 0;
+episodes of 10 steps then reset(). ENVS_PER_GPU environments per GPU (weak scaling across GPUs).
+
+A "step" is one env.step() of all environments = one fused kernel launch (action transform, 17 substeps,
+observation pack); every 10th step is preceded by the reset launch, inside the timed region.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl ours|reference]
+Under torchrun (N > 1) every rank drives one GPU; rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "robot-control-stack_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+SUBSTEPS = 17
+EPISODE = 10
+MAX_MOV = float(np.deg2rad(5))
+# algorithmic bytes of one env.step() of one env in float64: per substep read
+# qpos+qvel+ctrl+warmstart+time and write qpos+qvel+warmstart+time = 512 B; plus action 8x8 B, obs 21x8 B, 3 flags
+BYTES_PER_PHYSICS_STEP = 512
+BYTES_PER_ENV_STEP = SUBSTEPS * BYTES_PER_PHYSICS_STEP + 64 + 168 + 3
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.rows, self.stop_flag, self.index = [], False, index
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.t.start()
+
+    def stop(self):
+        self.stop_flag = True
+        self.t.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference(nthreads, target_seconds, episode_len=EPISODE):
+    """The reference path's CPU restatement (oracle) on all host cores over a bounded sample of the workload."""
+    import helpers as H
+    from helpers import O
+    M = H.scene()
+    m, rc, gc = O.Model(M), O.robot_cfg(M), O.gripper_cfg(M)
+    nenv = nthreads
+    probe = H.workload_actions(nenv, 20, seed=0)
+    sec, _, _ = O.bench_env_steps(m, rc, gc, probe, nthreads, episode_len, True, MAX_MOV, H.JLOW, H.JHIGH)
+    rate = nenv * 20 / max(sec, 1e-9)
+    nsteps = int(max(20, min(20000, target_seconds * rate / nenv)))
+    acts = H.workload_actions(nenv, nsteps, seed=0)
+    sec, psteps, _ = O.bench_env_steps(m, rc, gc, acts, nthreads, episode_len, True, MAX_MOV, H.JLOW, H.JHIGH)
+    return {"value": nenv * nsteps / sec, "unit": "env-steps/s", "cores": nthreads, "kind": "port",
+            "sample": f"{nenv} envs x {nsteps} env.step() ({psteps} physics steps) in {sec:.2f} s, one env per thread",
+            "physics_steps_per_s": psteps / sec}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals, samples = [], []
+    for _ in range(args.warmup):
+        cpu_reference(cores, 0.5)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = cpu_reference(cores, max(1.0, 20.0 / max(args.steps, 1)))
+        vals.append(r["value"])
+        samples.append(r["sample"])
+    dt = time.perf_counter() - t0
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": "env-steps/sec FR3 joint-control (async 30 Hz, 17 substeps)", "value": v,
+            "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "fr3_empty_world JOINTS rel 5deg + binary gripper, async 17 substeps, reset every 10 steps",
+                       "note": "CPU restatement of the reference path (libmujoco 3.2.6 / Pinocchio unavailable offline); "
+                               "each step is a bounded sample"},
+            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": samples[-1]},
+            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import helpers as H
+    from rcs_b200 import _lib, batch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    distributed = world > 1
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if distributed:
+        dist.init_process_group("nccl", device_id=dev)
+    N, K, W = args.envs, args.steps, args.warmup
+    M = H.scene()
+    dm = batch.DeviceModel(M, H.robot_ns(), H.gripper_ns(), device=local)
+    stream = torch.cuda.current_stream(dev)
+    b = batch.Batch(dm, N)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    total = K + W
+    acts_j = (torch.rand((total, N, 7), dtype=torch.float64, device=dev, generator=gen) * 2 - 1) * MAX_MOV
+    acts_g = torch.randint(0, 2, (total, N), device=dev, generator=gen).to(torch.float64)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    obs_all = torch.empty((world, N, dm.obs_dim), dtype=torch.float64, device=dev) if distributed else None
+    reset_ops = _lib.GRIPPER_RESET | _lib.SIM_RESET | _lib.ROBOT_RESET | _lib.ENV_RESET_FLAGS | _lib.STEP_K | _lib.OBS
+    step_ops = _lib.ACT_JOINTS_REL | _lib.ACT_GRIPPER_BIN | _lib.STEP_K | _lib.OBS
+    launches_before = None
+
+    def one_step(i):
+        n = 0
+        if i % EPISODE == 0:
+            b.run(reset_ops, k=1, want_obs=True)
+            n += 1
+        b.run(step_ops, k=SUBSTEPS, act_joints=acts_j[i], act_gripper=acts_g[i], max_mov=MAX_MOV, jlow=H.JLOW, jhigh=H.JHIGH,
+              want_obs=True)
+        n += 1
+        if distributed:  # the one exchange step: vectorised observation return on every rank
+            dist.all_gather_into_tensor(obs_all.view(-1), b.obs.view(-1))
+        return n
+
+    for i in range(W):
+        one_step(i)
+        flush.zero_()
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches = 0
+    launches_before = _lib.lib().rcsb_launch_count()
+    for i in range(K):
+        flush.zero_()  # L2 flush between timed iterations (outside the timed events)
+        ev[i][0].record(stream)
+        if (W + i) % EPISODE == 0:
+            b.run(reset_ops, k=1, want_obs=True)
+        kev[i][0].record(stream)
+        b.run(step_ops, k=SUBSTEPS, act_joints=acts_j[W + i], act_gripper=acts_g[W + i], max_mov=MAX_MOV, jlow=H.JLOW,
+              jhigh=H.JHIGH, want_obs=True)
+        kev[i][1].record(stream)
+        if distributed:
+            dist.all_gather_into_tensor(obs_all.view(-1), b.obs.view(-1))
+        ev[i][1].record(stream)
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = _lib.lib().rcsb_launch_count() - launches_before
+    clocks = sampler.stop() if rank == 0 else None
+    ms = sum(a.elapsed_time(c) for a, c in ev)
+    kms = [a.elapsed_time(c) for a, c in kev]
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * N * K / (ms_max * 1e-3)
+
+    # ---- end to end through host buffers (rank-local; aggregate = sum over ranks measured as world * N / max time)
+    from rcs_b200.envs.base import ControlMode
+    h_j = torch.empty((N, 7), dtype=torch.float64).pin_memory()
+    h_g = torch.empty((N,), dtype=torch.float64).pin_memory()
+    h_obs = torch.empty((N, dm.obs_dim), dtype=torch.float64).pin_memory()
+    h_info = torch.empty((N, dm.info_dim), dtype=torch.int32).pin_memory()
+    src_j, src_g = acts_j.cpu(), acts_g.cpu()
+    e2e_steps = min(K, 50)
+    for i in range(3):
+        h_j.copy_(src_j[i]); h_g.copy_(src_g[i])
+        b.run_host(step_ops, SUBSTEPS, 500, h_j, h_g, MAX_MOV, H.JLOW, H.JHIGH, h_obs, h_info)
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        h_j.copy_(src_j[W + i]); h_g.copy_(src_g[W + i])  # the host-side policy output of this step
+        if (W + i) % EPISODE == 0:
+            b.run(reset_ops, k=1, want_obs=True)
+        b.run_host(step_ops, SUBSTEPS, 500, h_j, h_g, MAX_MOV, H.JLOW, H.JHIGH, h_obs, h_info)
+        _ = float(h_obs[0, 0])  # consume the result on the host
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * e2e_steps / float(te.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        kavg_ms = float(np.mean(kms))
+        achieved = N * BYTES_PER_ENV_STEP / (kavg_ms * 1e-3) / 1e9
+        occ = b.occupancy()
+        line = {
+            "metric": "env-steps/sec FR3 joint-control (async 30 Hz, 17 substeps)", "value": value, "unit": "env-steps/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{N} x FR3 fr3_empty_world per GPU, JOINTS relative 5deg + binary gripper, random actions, "
+                                   f"async {SUBSTEPS} substeps/env.step, reset every {EPISODE} steps",
+                       "envs_per_gpu": N, "total_envs": N * world, "physics_steps_per_s": value * SUBSTEPS,
+                       "l2": "256 MB buffer written between timed steps (L2 flush)",
+                       "timing": "CUDA events per step on the launch stream, summed; max over ranks",
+                       "kernel": "rcsb_k_run", **occ},
+            "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(N * 8 * 8),
+                    "d2h_bytes_per_step": int(N * (dm.obs_dim * 8 + dm.info_dim * 4)), "steps": e2e_steps},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel_ms": kavg_ms,
+                         "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP,
+                         "note": "ALU/latency-bound path (~100 flop/B, SURVEY.md 8d): HBM fraction is low by construction"},
+            "clocks": clocks,
+        }
+        if world == 1:
+            try:
+                line["cpu_baseline"] = cpu_reference(os.cpu_count() or 1, args.cpu_seconds)
+            except Exception as e:  # the oracle is only a reported baseline
+                line["cpu_baseline"] = {"error": str(e)}
+        print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

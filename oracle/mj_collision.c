@@ -211,6 +211,10 @@ int rcso_convex_convex(const rcso_model* m, const rcso_data* d, int g1, int g2, 
   (void)margin; /* margin is 0 in all shipped scenes: only penetrating pairs produce contacts */
   double depth, dir[3];
   if (!mpr_penetration(m, d, g1, g2, &depth, dir, pos)) return 0;
+  /* exactly touching pairs (the finger pads at qpos0 after every reset) give depth = +-1e-17 with an
+   * arbitrary direction; MuJoCo's analytic box-box reports dist = 0 there, which is excluded from the
+   * constraint set (dist >= includemargin). Dropping depth < 1e-12 gives the same constraint set. */
+  if (depth < 1e-12) return 0;
   *dist = -depth;
   /* the MPR direction runs from the interior point cA-cB through the origin, i.e. from g1 towards g2:
    * it is the contact normal (translating g2 by depth*dir separates the pair) */

@@ -678,7 +678,8 @@ RCSB_DEV void st_collision(const Ctx& c) {
       }
     } else {
       real depth, dir[3], pos[3];
-      if (mpr_penetration(c, pf, &depth, dir, pos)) add_contact(c, ncon, pf.g1, pf.g2, -depth, pos, dir, margin, gap);
+      // depth < 1e-12: exactly touching pair (finger pads at qpos0), not a constraint; see oracle/mj_collision.c
+      if (mpr_penetration(c, pf, &depth, dir, pos) && depth >= (real)1e-12) add_contact(c, ncon, pf.g1, pf.g2, -depth, pos, dir, margin, gap);
     }
   }
   if (c.lane == 0) { WI(misc)[MI_NCON] = ncon; WI(misc)[MI_NCAND] = ncand; }
