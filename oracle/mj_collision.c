@@ -309,6 +309,38 @@ static void plane_capsule(const rcso_model* m, rcso_data* d, int gp, int g, doub
   }
 }
 
+/* world centre of the geom's bounding volume (local AABB centre) */
+static void bv_center(const rcso_model* m, const rcso_data* d, int g, double* c) {
+  mulmat3(c, d->geom_xmat + 9 * g, m->geom_aabb + 6 * g);
+  c[0] += d->geom_xpos[3 * g]; c[1] += d->geom_xpos[3 * g + 1]; c[2] += d->geom_xpos[3 * g + 2];
+}
+/* oriented-box separating-axis test on the geoms' local AABBs (mid-phase; exact for box-box). 1 = separated */
+static int obb_separated(const rcso_model* m, const rcso_data* d, int g1, int g2, double margin) {
+  const double *A = d->geom_xmat + 9 * g1, *B = d->geom_xmat + 9 * g2;
+  const double *ha = m->geom_aabb + 6 * g1 + 3, *hb = m->geom_aabb + 6 * g2 + 3;
+  double ca[3], cb[3], R[9], AR[9], t[3], dv[3];
+  bv_center(m, d, g1, ca); bv_center(m, d, g2, cb);
+  for (int k = 0; k < 3; k++) dv[k] = cb[k] - ca[k];
+  mulmatT3(t, A, dv);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      R[3 * i + j] = A[i] * B[j] + A[3 + i] * B[3 + j] + A[6 + i] * B[6 + j];
+      AR[3 * i + j] = fabs(R[3 * i + j]) + 1e-12;
+    }
+  for (int i = 0; i < 3; i++)
+    if (fabs(t[i]) > ha[i] + hb[0] * AR[3 * i] + hb[1] * AR[3 * i + 1] + hb[2] * AR[3 * i + 2] + margin) return 1;
+  for (int j = 0; j < 3; j++)
+    if (fabs(t[0] * R[j] + t[1] * R[3 + j] + t[2] * R[6 + j]) > ha[0] * AR[j] + ha[1] * AR[3 + j] + ha[2] * AR[6 + j] + hb[j] + margin) return 1;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      double ra = ha[i1] * AR[3 * i2 + j] + ha[i2] * AR[3 * i1 + j];
+      double rb = hb[j1] * AR[3 * i + j2] + hb[j2] * AR[3 * i + j1];
+      if (fabs(t[i2] * R[3 * i1 + j] - t[i1] * R[3 * i2 + j]) > ra + rb + margin) return 1;
+    }
+  return 0;
+}
+
 void rcso_collision(const rcso_model* m, rcso_data* d) {
   d->ncon = 0;
   for (int p = 0; p < m->npair; p++) {
@@ -320,17 +352,28 @@ void rcso_collision(const rcso_model* m, rcso_data* d) {
     if (t1 == GEOM_PLANE) {
       const double* Rp = d->geom_xmat + 9 * g1;
       double n[3] = {Rp[2], Rp[5], Rp[8]}, dif[3];
-      for (int k = 0; k < 3; k++) dif[k] = d->geom_xpos[3 * g2 + k] - d->geom_xpos[3 * g1 + k];
-      if (dot3(dif, n) > m->geom_rbound[g2] + margin) continue;
+      double c2[3];
+      bv_center(m, d, g2, c2);
+      for (int k = 0; k < 3; k++) dif[k] = c2[k] - d->geom_xpos[3 * g1 + k];
+      if (dot3(dif, n) > m->geom_bsphere[4 * g2 + 3] + margin) continue;
+      { /* oriented box against the plane */
+        const double* B = d->geom_xmat + 9 * g2; const double* hb = m->geom_aabb + 6 * g2 + 3;
+        double r = 0;
+        for (int j = 0; j < 3; j++) r += hb[j] * fabs(n[0] * B[j] + n[1] * B[3 + j] + n[2] * B[6 + j]);
+        if (dot3(dif, n) - r > margin) continue;
+      }
       if (t2 == GEOM_MESH) plane_mesh(m, d, g1, g2, margin, gap);
       else if (t2 == GEOM_BOX) plane_box(m, d, g1, g2, margin, gap);
       else if (t2 == GEOM_CAPSULE) plane_capsule(m, d, g1, g2, margin, gap);
       continue;
     }
     double dif[3];
-    for (int k = 0; k < 3; k++) dif[k] = d->geom_xpos[3 * g2 + k] - d->geom_xpos[3 * g1 + k];
-    double bound = m->geom_rbound[g1] + m->geom_rbound[g2] + margin;
+    double c1[3], c2[3];
+    bv_center(m, d, g1, c1); bv_center(m, d, g2, c2);
+    for (int k = 0; k < 3; k++) dif[k] = c2[k] - c1[k];
+    double bound = m->geom_bsphere[4 * g1 + 3] + m->geom_bsphere[4 * g2 + 3] + margin;
     if (dot3(dif, dif) > bound * bound) continue;
+    if (obb_separated(m, d, g1, g2, margin)) continue;
     double dist, pos[3], normal[3];
     if (rcso_convex_convex(m, d, g1, g2, margin, &dist, pos, normal)) add_contact(m, d, g1, g2, dist, pos, normal, margin, gap);
   }

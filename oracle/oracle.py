@@ -24,7 +24,7 @@ _REAL_FIELDS = ["body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass",
                 "body_invweight0", "jnt_pos", "jnt_axis", "jnt_range", "jnt_margin", "jnt_solref", "jnt_solimp",
                 "jnt_actfrcrange", "dof_armature", "dof_damping", "dof_frictionloss", "dof_invweight0", "qpos0",
                 "geom_size", "geom_pos", "geom_quat", "geom_friction", "geom_solref", "geom_solimp", "geom_solmix",
-                "geom_margin", "geom_gap", "geom_rbound", "geom_aabb", "mesh_vert", "site_pos", "site_quat",
+                "geom_margin", "geom_gap", "geom_rbound", "geom_aabb", "geom_bsphere", "mesh_vert", "site_pos", "site_quat",
                 "tendon_coef", "tendon_invweight0", "eq_polycoef", "eq_solref", "eq_solimp", "actuator_gear",
                 "actuator_gainprm", "actuator_biasprm", "actuator_ctrlrange", "actuator_forcerange"]
 

@@ -27,13 +27,13 @@ enum { MI_NCON = 0, MI_NEFC, MI_NE, MI_NF, MI_NL, MI_NCAND, MI_SOLVER_ITER, MI_W
 // ------------------------------------------------------------------ dense Cholesky on shared memory
 // A (n x n, row-major) -> strictly-lower part holds L, dinv[j] = 1 / L[j][j]. A's diagonal is left
 // untouched so that no lane overwrites a value other lanes still read.
-RCSB_DEV void chol_factor(const Ctx& c, real* A, real* dinv, int n) {
+RCSB_DEV_NOINLINE void chol_factor(const Ctx& c, real* A, real* dinv, int n) {
   for (int j = 0; j < n; j++) {
     RCSB_SYNC();
     real d = A[j * n + j];
     for (int k = 0; k < j; k++) d -= A[j * n + k] * A[j * n + k];
     if (d < RCSB_MINVAL) d = RCSB_MINVAL;
-    real inv = (real)1 / r_sqrt(d);
+    real inv = r_rsqrt(d);
     PFOR(ii, n - j - 1) {
       int i = j + 1 + ii;
       real t = A[i * n + j];
@@ -45,7 +45,7 @@ RCSB_DEV void chol_factor(const Ctx& c, real* A, real* dinv, int n) {
   RCSB_SYNC();
 }
 // x <- (L L^T)^{-1} x ; y is scratch of length n
-RCSB_DEV void chol_solve(const Ctx& c, const real* L, const real* dinv, int n, real* x, real* y) {
+RCSB_DEV_NOINLINE void chol_solve(const Ctx& c, const real* L, const real* dinv, int n, real* x, real* y) {
   for (int k = 0; k < n; k++) {
     RCSB_SYNC();
     real xk = x[k] * dinv[k];
@@ -223,13 +223,13 @@ RCSB_DEV void st_com(const Ctx& c) {
       cross3(cd + 3, WR(jaxis) + 3 * b, off);
     }
   }
-  PFOR(g, m.ng) {  // geom centres for the broad phase
+  PFOR(g, m.ng) {  // bounding-volume centres for the broad phase
     int b = m.g_body[g];
     real* o = WR(gpos) + 3 * g;
-    if (b < 0) copy3(o, m.g_pos[g]);
+    if (b < 0) copy3(o, m.g_bpos[g]);
     else {
       real v[3];
-      mulmat3(v, WR(bmat) + 9 * b, m.g_pos[g]);
+      mulmat3(v, WR(bmat) + 9 * b, m.g_bpos[g]);
       const real* p = WR(bpos) + 3 * b;
       o[0] = p[0] + v[0]; o[1] = p[1] + v[1]; o[2] = p[2] + v[2];
     }
@@ -466,7 +466,7 @@ RCSB_DEV void expand_portal(Sup* s, const Sup& v4) {
 }
 // Minkowski Portal Refinement penetration query (algorithm of libccd's ccdMPRPenetration, which
 // MuJoCo 3.2.6 uses for convex pairs). Warp-uniform control flow; only support() is cooperative.
-RCSB_DEV int mpr_penetration(const Ctx& c, const PairFrames& pf, real* depth, real* dir_out, real* pos) {
+RCSB_DEV_NOINLINE int mpr_penetration(const Ctx& c, const PairFrames& pf, real* depth, real* dir_out, real* pos) {
   Sup s[4], v4;
   real dir[3], va[3], vb[3];
   for (int k = 0; k < 3; k++) { s[0].v1[k] = pf.p1[k]; s[0].v2[k] = pf.p2[k]; s[0].v[k] = pf.p1[k] - pf.p2[k]; }
@@ -593,10 +593,51 @@ RCSB_DEV void add_contact(const Ctx& c, int& ncon, int g1, int g2, real dist, co
   ncon++;
 }
 
+// append `value` to `list` for every lane with `hit`, preserving lane order; returns the new count (uniform)
+RCSB_DEV int compact_append(const Ctx& c, int hit, int value, int count, int* list) {
+#ifdef RCSB_HOST_EMU
+  if (hit) { if (count < RCSB_MAXCAND) list[count] = value; count++; }
+  return count;
+#else
+  unsigned mask = warp_ballot(hit);
+  if (hit) {
+    int slot = count + __popc(mask & ((1u << c.lane) - 1u));
+    if (slot < RCSB_MAXCAND) list[slot] = value;
+  }
+  return count + __popc(mask);
+#endif
+}
+// separating-axis test of two oriented boxes (rotation A/B row-major, centres ca/cb, half sizes ha/hb); 1 = separated
+RCSB_DEV int obb_separated(const real* A, const real* ca, const real* ha, const real* B, const real* cb, const real* hb,
+                           real margin) {
+  real R[9], AR[9], t[3], dv[3] = {cb[0] - ca[0], cb[1] - ca[1], cb[2] - ca[2]};
+  mulmatT3(t, A, dv);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      R[3 * i + j] = A[i] * B[j] + A[3 + i] * B[3 + j] + A[6 + i] * B[6 + j];
+      AR[3 * i + j] = r_abs(R[3 * i + j]) + (real)1e-12;
+    }
+  for (int i = 0; i < 3; i++)
+    if (r_abs(t[i]) > ha[i] + hb[0] * AR[3 * i] + hb[1] * AR[3 * i + 1] + hb[2] * AR[3 * i + 2] + margin) return 1;
+  for (int j = 0; j < 3; j++)
+    if (r_abs(t[0] * R[j] + t[1] * R[3 + j] + t[2] * R[6 + j]) > ha[0] * AR[j] + ha[1] * AR[3 + j] + ha[2] * AR[6 + j] + hb[j] + margin) return 1;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      real ra = ha[i1] * AR[3 * i2 + j] + ha[i2] * AR[3 * i1 + j];
+      real rb = hb[j1] * AR[3 * i + j2] + hb[j2] * AR[3 * i + j1];
+      if (r_abs(t[i2] * R[3 * i1 + j] - t[i1] * R[3 * i2 + j]) > ra + rb + margin) return 1;
+    }
+  return 0;
+}
+
 RCSB_DEV void st_collision(const Ctx& c) {
   const RcsbModel& m = *c.md;
-  // ---- broad phase: bounding spheres (plane: signed distance), compacted in pair order
-  int ncand = 0;
+  // ---- broad phase: bounding spheres about the local AABB centres (plane: signed distance), one pair per lane,
+  //      survivors compacted in pair order
+  int* candA = WI(cand);
+  int* candB = WI(cand) + RCSB_MAXCAND;
+  int ncandA = 0;
   for (int base = 0; base < m.npair; base += RCSB_NLANES) {
     int p = base + c.lane, hit = 0;
     if (p < m.npair) {
@@ -614,26 +655,46 @@ RCSB_DEV void st_collision(const Ctx& c) {
         hit = !(dot3(d, d) > bound * bound);
       }
     }
-#ifdef RCSB_HOST_EMU
-    if (hit) { if (ncand < RCSB_MAXCAND) WI(cand)[ncand] = p; ncand++; }
-#else
-    unsigned mask = warp_ballot(hit);
-    if (hit) {
-      int slot = ncand + __popc(mask & ((1u << c.lane) - 1u));
-      if (slot < RCSB_MAXCAND) WI(cand)[slot] = p;
-    }
-    ncand += __popc(mask);
-#endif
+    ncandA = compact_append(c, hit, p, ncandA, candA);
   }
-  if (ncand > RCSB_MAXCAND) {
+  if (ncandA > RCSB_MAXCAND) {
     if (c.lane == 0) WI(misc)[MI_WARN] += 1;
-    ncand = RCSB_MAXCAND;
+    ncandA = RCSB_MAXCAND;
+  }
+  RCSB_SYNC();
+  // ---- mid phase: oriented boxes (local AABBs) by separating axes, one candidate per lane. Conservative: a
+  //      rejected pair cannot intersect (the hull lies inside its box), so the contact set is unchanged.
+  int ncand = 0;
+  for (int base = 0; base < ncandA; base += RCSB_NLANES) {
+    int ic = base + c.lane, hit = 0, p = 0;
+    if (ic < ncandA) {
+      p = candA[ic];
+      int g1 = m.pair[p][0], g2 = m.pair[p][1];
+      real margin = m.g_margin[g1] > m.g_margin[g2] ? m.g_margin[g1] : m.g_margin[g2];
+      real p2[3], R2[9];
+      geom_frame(c, g2, p2, R2);
+      const real* c2 = WR(gpos) + 3 * g2;
+      const real* hb = m.g_aabb[g2] + 3;
+      if (m.g_type[g1] == RCSB_GEOM_PLANE) {
+        real R1[9];
+        quat_to_mat(R1, m.g_quat[g1]);
+        real n[3] = {R1[2], R1[5], R1[8]}, r = 0;
+        for (int j = 0; j < 3; j++) r += hb[j] * r_abs(n[0] * R2[j] + n[1] * R2[3 + j] + n[2] * R2[6 + j]);
+        real dist = (c2[0] - m.g_pos[g1][0]) * n[0] + (c2[1] - m.g_pos[g1][1]) * n[1] + (c2[2] - m.g_pos[g1][2]) * n[2];
+        hit = !(dist - r > margin);
+      } else {
+        real p1[3], R1[9];
+        geom_frame(c, g1, p1, R1);
+        hit = !obb_separated(R1, WR(gpos) + 3 * g1, m.g_aabb[g1] + 3, R2, c2, hb, margin);
+      }
+    }
+    ncand = compact_append(c, hit, p, ncand, candB);
   }
   RCSB_SYNC();
   // ---- narrow phase, candidates in pair order
   int ncon = 0;
   for (int ic = 0; ic < ncand; ic++) {
-    int p = WI(cand)[ic];
+    int p = candB[ic];
     PairFrames pf;
     pf.g1 = m.pair[p][0]; pf.g2 = m.pair[p][1];
     real margin = m.g_margin[pf.g1] > m.g_margin[pf.g2] ? m.g_margin[pf.g1] : m.g_margin[pf.g2];

@@ -27,7 +27,7 @@ static const RcsbField rcsb_model_fields[] = {
     RCSB_FR(d_margin), RCSB_FR(d_solref), RCSB_FR(d_solimp), RCSB_FR(d_actfrcrange), RCSB_FR(qpos0), RCSB_FR(r_invmass),
     RCSB_FI(g_body), RCSB_FI(g_type), RCSB_FI(g_vertadr), RCSB_FI(g_vertnum), RCSB_FI(g_origid), RCSB_FI(g_role),
     RCSB_FI(g_condim), RCSB_FI(g_priority),
-    RCSB_FR(g_pos), RCSB_FR(g_quat), RCSB_FR(g_size), RCSB_FR(g_rbound), RCSB_FR(g_aabb), RCSB_FR(g_friction),
+    RCSB_FR(g_pos), RCSB_FR(g_quat), RCSB_FR(g_bpos), RCSB_FR(g_size), RCSB_FR(g_rbound), RCSB_FR(g_aabb), RCSB_FR(g_friction),
     RCSB_FR(g_solref), RCSB_FR(g_solimp), RCSB_FR(g_solmix), RCSB_FR(g_margin), RCSB_FR(g_gap), RCSB_FR(g_invweight),
     RCSB_FB(pair),
     RCSB_FR(t_coef), RCSB_FI(e_dof1), RCSB_FI(e_dof2), RCSB_FI(e_active), RCSB_FR(e_poly), RCSB_FR(e_solref),
@@ -75,30 +75,38 @@ static inline int rcsb_model_finalize_layout(RcsbModel* m) {
   RCSB_ALLOC(o_rcs, RCSB_S_TAIL);
   m->nsr = o;
   m->o_site = m->o_rcs + RCSB_S_SITEPOS;
+  // region K: position/velocity-stage scratch, dead once st_make_constraint has built the constraint rows
+  const int k_begin = o;
   RCSB_ALLOC(o_bpos, 3 * nb); RCSB_ALLOC(o_bquat, 4 * nb); RCSB_ALLOC(o_bmat, 9 * nb); RCSB_ALLOC(o_bcom, 3 * nb);
   RCSB_ALLOC(o_bgc, 3 * nb); RCSB_ALLOC(o_janchor, 3 * nb); RCSB_ALLOC(o_jaxis, 3 * nb);
   RCSB_ALLOC(o_rootcom, 3 * m->nroot);
   RCSB_ALLOC(o_cinert, 10 * nb); RCSB_ALLOC(o_crb, 10 * nb); RCSB_ALLOC(o_cdof, 6 * nv); RCSB_ALLOC(o_cdofdot, 6 * nv);
   RCSB_ALLOC(o_cvel, 6 * nb); RCSB_ALLOC(o_cacc, 6 * nb); RCSB_ALLOC(o_cfrc, 6 * nb);
-  RCSB_ALLOC(o_M, nv * nv); RCSB_ALLOC(o_L, nv * nv + nv); RCSB_ALLOC(o_H, nv * nv + nv);
+  RCSB_ALLOC(o_gpos, 3 * m->ng);
+  const int k_end = o;
+  // region S: solver / integrator scratch, first written after st_make_constraint -> aliases region K
+  o = k_begin;
+  RCSB_ALLOC(o_H, nv * nv + nv);
+  RCSB_ALLOC(o_grad, nv); RCSB_ALLOC(o_search, nv); RCSB_ALLOC(o_Ma, nv); RCSB_ALLOC(o_Mv, nv);
+  RCSB_ALLOC(o_conehess, 9 * m->maxcon);
+  RCSB_ALLOC(o_noslip, (nv + 2 * m->maxcon) * nv + nv + 4 * m->maxcon);
+  if (o < k_end) o = k_end;
+  // persistent across the whole step
+  RCSB_ALLOC(o_M, nv * nv); RCSB_ALLOC(o_L, nv * nv + nv);
   RCSB_ALLOC(o_bias, nv); RCSB_ALLOC(o_passive, nv); RCSB_ALLOC(o_gravc, nv); RCSB_ALLOC(o_actfrc, nv);
   RCSB_ALLOC(o_smooth, nv); RCSB_ALLOC(o_qacc_smooth, nv); RCSB_ALLOC(o_qacc, nv); RCSB_ALLOC(o_qfc, nv);
-  RCSB_ALLOC(o_grad, nv); RCSB_ALLOC(o_search, nv); RCSB_ALLOC(o_Ma, nv); RCSB_ALLOC(o_Mv, nv);
   RCSB_ALLOC(o_tmp, 6 * nv + 2 * nb + 8);
   RCSB_ALLOC(o_alen, nu); RCSB_ALLOC(o_avel, nu); RCSB_ALLOC(o_aforce, nu);
-  RCSB_ALLOC(o_gpos, 3 * m->ng);
   RCSB_ALLOC(o_con, RCSB_C_REALS * m->maxcon);
   RCSB_ALLOC(o_J, m->maxefc * nv);
   RCSB_ALLOC(o_efc, RCSB_E_NARR * m->maxefc);
-  RCSB_ALLOC(o_conehess, 9 * m->maxcon);
-  RCSB_ALLOC(o_noslip, (nv + 2 * m->maxcon) * nv + nv + 4 * m->maxcon);
   o = (o + 1) & ~1;  // keep the double clock block 16-byte aligned when real is 8 bytes
   m->ws_reals = o;
   m->ws_doubles = RCSB_D_TAIL;
   o = 0;
   RCSB_ALLOC(oi_con, RCSB_CI_INTS * m->maxcon);
   RCSB_ALLOC(oi_efc, RCSB_EI_NARR * m->maxefc);
-  RCSB_ALLOC(oi_cand, RCSB_MAXCAND);
+  RCSB_ALLOC(oi_cand, 2 * RCSB_MAXCAND);
   RCSB_ALLOC(oi_misc, 8 /* MI_COUNT */ + RCSB_I_TAIL);
   m->ws_ints = (o + 3) & ~3;
 #undef RCSB_ALLOC

@@ -319,7 +319,7 @@ RCSB_DEV real constraint_update(const Ctx& c, int nefc, int ncon, int want_hess)
 }
 
 // cost at acceleration vector `acc` (shared memory): fills Ma, jar, force, state; returns total cost
-RCSB_DEV real total_cost(const Ctx& c, const real* acc, int nefc, int ncon, int want_hess, real* gauss_out) {
+RCSB_DEV_NOINLINE real total_cost(const Ctx& c, const real* acc, int nefc, int ncon, int want_hess, real* gauss_out) {
   const RcsbModel& m = *c.md;
   const int nv = m.nv;
   real g = 0;
@@ -342,7 +342,7 @@ RCSB_DEV real total_cost(const Ctx& c, const real* acc, int nefc, int ncon, int 
 }
 
 // value, first and second derivative of the cost along the search direction at step alpha
-RCSB_DEV void line_eval(const Ctx& c, int nefc, int ncon, real alpha, real qG0, real qG1, real qG2, real* val, real* d1,
+RCSB_DEV_NOINLINE void line_eval(const Ctx& c, int nefc, int ncon, real alpha, real qG0, real qG1, real qG2, real* val, real* d1,
                         real* d2) {
   const RcsbModel& m = *c.md;
   const real* jar = EFC(RCSB_E_JAR);
@@ -435,7 +435,7 @@ RCSB_DEV void compute_qfc(const Ctx& c, int nefc) {
 }
 
 // ------------------------------------------------------------------ noslip post-pass
-RCSB_DEV void solve_noslip(const Ctx& c, int nefc, int ncon) {
+RCSB_DEV_NOINLINE void solve_noslip(const Ctx& c, int nefc, int ncon) {
   const RcsbModel& m = *c.md;
   const int nv = m.nv;
   int ne = WI(misc)[MI_NE], nf = WI(misc)[MI_NF];
@@ -568,14 +568,15 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
     return;
   }
   // warm start: keep qacc_warmstart only if its cost beats qacc_smooth's
-  real cost_warm = total_cost(c, WR(warm), nefc, ncon, 0, nullptr);
+  real gauss;
   real cost_smooth = total_cost(c, WR(qacc_smooth), nefc, ncon, 0, nullptr);
-  const real* start = cost_warm < cost_smooth ? WR(warm) : WR(qacc_smooth);
+  real cost = total_cost(c, WR(warm), nefc, ncon, 1, &gauss);
+  const int use_warm = cost < cost_smooth;
+  const real* start = use_warm ? WR(warm) : WR(qacc_smooth);
   PFOR(k, nv) { WR(qacc)[k] = start[k]; }
   RCSB_SYNC();
   real scale = (real)1 / (m.meaninertia * (nv > 1 ? nv : 1));
-  real gauss;
-  real cost = total_cost(c, WR(qacc), nefc, ncon, 1, &gauss);
+  if (!use_warm) cost = total_cost(c, WR(qacc), nefc, ncon, 1, &gauss);
   int iter = 0;
   const int* state = EFCI(RCSB_EI_STATE);
   while (iter < m.iterations) {

@@ -67,6 +67,7 @@ struct RcsbModel {
   int g_body[RCSB_MAXG], g_type[RCSB_MAXG], g_vertadr[RCSB_MAXG], g_vertnum[RCSB_MAXG], g_origid[RCSB_MAXG],
       g_role[RCSB_MAXG], g_condim[RCSB_MAXG], g_priority[RCSB_MAXG];
   real g_pos[RCSB_MAXG][3], g_quat[RCSB_MAXG][4];  // in the moving body frame (world frame if g_body < 0)
+  real g_bpos[RCSB_MAXG][3];  // bounding-volume centre (local AABB centre) in the moving body frame; g_rbound is about it
   real g_size[RCSB_MAXG][3], g_rbound[RCSB_MAXG], g_aabb[RCSB_MAXG][6], g_friction[RCSB_MAXG][3], g_solref[RCSB_MAXG][2],
       g_solimp[RCSB_MAXG][5], g_solmix[RCSB_MAXG], g_margin[RCSB_MAXG], g_gap[RCSB_MAXG], g_invweight[RCSB_MAXG];
   uint8_t pair[RCSB_MAXPAIR][2];  // collidable-geom indices, lower geom type first

@@ -12,6 +12,7 @@
 
 #ifdef RCSB_HOST_EMU
 #define RCSB_DEV static inline
+#define RCSB_DEV_NOINLINE static
 #define RCSB_NLANES 1
 #define RCSB_SYNC() ((void)0)
 #ifdef RCSB_EMU_REVERSE  // run every parallel-for backwards: results must not depend on lane order
@@ -29,6 +30,8 @@ RCSB_DEV int warp_bcast_i(int x, int src) { return x; }
 #define RCSB_LDG(p) (*(p))
 #else
 #define RCSB_DEV __device__ __forceinline__
+// large routines called from several sites: keep one copy (the hot loop already overflows the instruction cache)
+#define RCSB_DEV_NOINLINE __device__ __noinline__
 #define RCSB_NLANES 32
 #define RCSB_SYNC() __syncwarp()
 #define PFOR(i, n) for (int i = (int)(threadIdx.x & 31); i < (n); i += 32)
@@ -65,6 +68,11 @@ RCSB_DEV int warp_bcast_i(int x, int src) { return __shfl_sync(0xffffffffu, x, s
 #define RCSB_MINVAL ((real)1e-15)
 RCSB_DEV real r_sqrt(real x) { return sqrt(x); }
 RCSB_DEV real r_abs(real x) { return fabs(x); }
+#ifdef RCSB_HOST_EMU
+RCSB_DEV real r_rsqrt(real x) { return (real)1 / sqrt(x); }
+#else
+RCSB_DEV real r_rsqrt(real x) { return (real)1 / sqrt(x); }  // IEEE path kept: rsqrt() differs from the oracle in the last bits
+#endif
 RCSB_DEV real dot3(const real* a, const real* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 RCSB_DEV void cross3(real* r, const real* a, const real* b) {
   real x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];

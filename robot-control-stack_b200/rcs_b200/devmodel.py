@@ -213,7 +213,10 @@ def build_device_fields(M: dict, robot_cfg=None, gripper_cfg=None, maxcon: int |
     put("g_priority", [M["geom_priority"][g] for g in col], False)
     put("g_pos", g_pos, True)
     put("g_quat", g_quat, True)
-    for f in ("size", "rbound", "aabb", "friction", "solref", "solimp", "solmix", "margin", "gap"):
+    # bounding volume: sphere about the local AABB centre (broad phase) and the oriented AABB itself (mid phase)
+    put("g_bpos", [gp + quat_to_mat(gq) @ M["geom_aabb"][g][:3] for g, gp, gq in zip(col, g_pos, g_quat)], True)
+    put("g_rbound", [M["geom_bsphere"][g][3] for g in col], True)
+    for f in ("size", "aabb", "friction", "solref", "solimp", "solmix", "margin", "gap"):
         put("g_" + f, [M["geom_" + f][g] for g in col], True)
     put("g_invweight", [M["body_invweight0"][M["geom_bodyid"][g]][0] for g in col], True)
     pairs = []

@@ -735,6 +735,19 @@ def compile_mjcf(path: str) -> dict:
         elif g["type"] == GEOM_CYLINDER:
             aabb[gi, 3:] = [g["size"][0], g["size"][0], g["size"][1]]
     M["geom_aabb"] = aabb
+    # bounding sphere about the local AABB centre (tighter than geom_rbound, which is about the geom origin)
+    bs = np.zeros((ngeom, 4))
+    for gi, g in enumerate(geoms):
+        bs[gi, :3] = aabb[gi, :3]
+        if g["type"] == GEOM_MESH and g["hull"] is not None:
+            bs[gi, 3] = float(np.linalg.norm(g["hull"] - aabb[gi, :3], axis=1).max())
+        elif g["type"] == GEOM_CAPSULE:
+            bs[gi, 3] = g["size"][0] + g["size"][1]
+        elif g["type"] == GEOM_SPHERE:
+            bs[gi, 3] = g["size"][0]
+        else:
+            bs[gi, 3] = float(np.linalg.norm(aabb[gi, 3:]))
+    M["geom_bsphere"] = bs
 
     M["site_names"] = [s["name"] for s in sites]
     M["site_bodyid"] = np.array([s["body"] for s in sites], dtype=np.int32)
