@@ -254,7 +254,10 @@ RCSB_DEV void run_env_program(const Ctx& c, const RcsbLaunch& L, int env) {
   if (ops & RCSB_OP_SET_JOINTS) op_set_joint_position(c, L.act_joints + (size_t)env * m.rb_njoints);
   if ((ops & RCSB_OP_SET_GRIPPER) && m.gr_enabled) op_set_gripper(c, L.act_gripper[env]);
   if (ops & RCSB_OP_STEP_K) {  // sim.cpp:108-115
-    for (int i = 0; i < L.k; i++) physics_step(c, &c.clk[RCSB_D_TIME]);
+    for (int i = 0; i < L.k; i++) {
+      RCSB_BLOCK_SYNC();  // fixed-k mode: keep the CTA's warps in the same stage so they share instruction-cache lines
+      physics_step(c, &c.clk[RCSB_D_TIME]);
+    }
   }
   if (ops & RCSB_OP_STEP_CONV) {  // sim.cpp:84-106
     int steps = 0, converged = 0;

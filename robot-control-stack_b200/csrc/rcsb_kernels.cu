@@ -86,6 +86,26 @@ rcsb_k_run(const RcsbModel* __restrict__ gm, const real* __restrict__ verts, rea
            int* __restrict__ si, RcsbLaunch L, int* __restrict__ counter, size_t ws_bytes) {
   const RcsbModel* sm = stage_model(gm);
   Ctx c = make_ctx(sm, verts, ws_bytes);
+  if (L.ops & RCSB_OP_STEP_K) {
+    // Fixed-substep launch: static env -> warp mapping. Every warp of the CTA runs the same number of rounds and
+    // hits exactly L.k CTA barriers per round (inside run_env_program, or here when it has no environment), which
+    // keeps the warps in the same stage of the step so that they share instruction-cache lines.
+    const int W = blockDim.x >> 5, per_round = gridDim.x * W;
+    const int rounds = (L.N + per_round - 1) / per_round;
+    for (int r = 0; r < rounds; r++) {
+      int env = r * per_round + (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+      bool valid = env < L.N && !(L.mask && !L.mask[env]);
+      if (valid) {
+        load_env(c, sr + (size_t)env * sm->nsr, sd + (size_t)env * RCSB_D_TAIL, si + (size_t)env * RCSB_I_TAIL);
+        run_env_program(c, L, env);
+        store_env(c, sr + (size_t)env * sm->nsr, sd + (size_t)env * RCSB_D_TAIL, si + (size_t)env * RCSB_I_TAIL);
+        __syncwarp();
+      } else {
+        for (int i = 0; i < L.k; i++) __syncthreads();
+      }
+    }
+    return;
+  }
   for (;;) {
     int env = 0;
     if (c.lane == 0) env = atomicAdd(counter, 1);

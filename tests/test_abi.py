@@ -1,0 +1,62 @@
+"""The C-ABI library loads on a machine without a GPU, exports every symbol include/rcsb.h declares, and fails
+loudly (no CPU fallback) when asked to run without a CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import helpers as H
+
+ROOT = H.ROOT
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "rcsb.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(rcsb_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def test_header_symbols_are_exported():
+    from rcs_b200 import _lib
+    L = C.CDLL(_lib.LIB_PATH)
+    syms = _declared_symbols()
+    assert len(syms) >= 28
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/rcsb.h but not exported"
+    assert set(_lib.EXPORTS) <= set(syms)
+
+
+def test_model_builds_on_host_and_upload_fails_without_gpu():
+    import numpy as np
+    import torch
+    from rcs_b200 import _lib, devmodel
+    L = _lib.lib()
+    assert L.rcsb_real_bytes() == 8
+    fields, verts = devmodel.build_device_fields(H.scene(), H.robot_ns(), H.gripper_ns())
+    m = L.rcsb_model_new()
+    for name, (arr, is_real) in fields.items():
+        a = np.ascontiguousarray(arr).ravel()
+        if is_real:
+            rc = L.rcsb_model_set_real(m, name.encode(), a.ctypes.data_as(C.POINTER(C.c_double)), a.size)
+        else:
+            rc = L.rcsb_model_set_int(m, name.encode(), a.ctypes.data_as(C.POINTER(C.c_int)), a.size)
+        assert rc == 0, name
+    assert L.rcsb_model_set_int(m, b"no_such_field", None, 0) == -1
+    assert L.rcsb_model_finalize(m) == 0
+    d = [C.c_int(0) for _ in range(5)]
+    assert L.rcsb_model_dims(m, *[C.byref(x) for x in d]) == 0
+    assert d[0].value * 8 % 16 == 0 and d[3].value == 22
+    if not torch.cuda.is_available():
+        assert L.rcsb_model_upload(m, 0) == -4  # RCSB_ERR_CUDA: no CPU execution path
+        assert b"no CPU" in L.rcsb_last_error()
+    L.rcsb_model_free(m)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "robot-control-stack_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "rcs_oracle" not in txt, f

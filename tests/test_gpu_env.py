@@ -1,0 +1,126 @@
+"""Port of the reference's behavioural tests (/root/reference/python/tests/test_sim_envs.py) against the mirrored
+API on the CUDA backend, for num_envs = 1 (reference semantics) and num_envs > 1 (batched extension)."""
+import numpy as np
+import pytest
+import torch
+
+import helpers  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(control_mode, num_envs=1, gripper=True, max_rel=None, async_control=False):
+    from rcs_b200 import sim
+    from rcs_b200.envs.creators import SimEnvCreator
+    from rcs_b200.envs.utils import default_sim_gripper_cfg, default_sim_robot_cfg
+    cfg = default_sim_robot_cfg("fr3_empty_world")
+    return SimEnvCreator()(control_mode, cfg, gripper_cfg=default_sim_gripper_cfg() if gripper else None,
+                           sim_cfg=sim.SimConfig(async_control=async_control), max_relative_movement=max_rel,
+                           num_envs=num_envs)
+
+
+def test_double_reset_and_zero_action_joints():  # test_sim_envs.py:304-331
+    from rcs_b200.envs.base import ControlMode
+    env = _mk(ControlMode.JOINTS, gripper=False)
+    env.reset()
+    obs0, _ = env.reset()
+    obs, _, _, _, info = env.step({"joints": obs0["joints"].clone()})
+    assert bool(info["ik_success"][0])
+    assert np.allclose(obs["joints"].cpu().numpy(), obs0["joints"].cpu().numpy(), atol=0.01, rtol=0)
+
+
+def test_non_zero_action_joints():  # test_sim_envs.py:333-345
+    from rcs_b200.envs.base import ControlMode
+    env = _mk(ControlMode.JOINTS, gripper=False)
+    obs0, _ = env.reset()
+    tgt = obs0["joints"] + torch.tensor([[0.1, 0.1, 0.1, 0.1, -0.1, -0.1, 0.1]], dtype=torch.float64, device=obs0["joints"].device)
+    obs, _, _, _, info = env.step({"joints": tgt})
+    assert bool(info["ik_success"][0])
+    assert np.allclose(obs["joints"].cpu().numpy(), tgt.cpu().numpy(), atol=0.01, rtol=0)
+
+
+def test_collision_joints():  # test_sim_envs.py:347-360
+    from rcs_b200.envs.base import ControlMode
+    env = _mk(ControlMode.JOINTS, gripper=True)
+    env.reset()
+    act = {"joints": torch.tensor([[0, 1.78, 0, -1.45, 0, 0, 0]], dtype=torch.float64), "gripper": torch.tensor([1.0], dtype=torch.float64)}
+    _, _, _, _, info = env.step(act)
+    assert bool(info["collision"][0]) and bool(info["ik_success"][0])
+
+
+def test_cartesian_tquat_move_x():  # test_sim_envs.py:202-221: +0.2 m in x reached within is_close(0.1 rad, 0.01 m)
+    from rcs_b200 import common
+    from rcs_b200.envs.base import ControlMode
+    env = _mk(ControlMode.CARTESIAN_TQuat, gripper=False)
+    obs0, _ = env.reset()
+    t = obs0["tquat"].clone()
+    t[:, 0] += 0.2
+    obs, _, _, trunc, info = env.step({"tquat": t})
+    assert bool(info["ik_success"][0])
+    a, b = obs["tquat"][0].cpu().numpy(), t[0].cpu().numpy()
+    assert common.Pose(translation=a[:3], quaternion=a[3:]).is_close(common.Pose(translation=b[:3], quaternion=b[3:]), eps_r=0.1, eps_t=0.01)
+
+
+def test_cartesian_collision_and_ik_failure():  # test_sim_envs.py:252-271 (floor) and SimRobot.cpp:149-154
+    from rcs_b200.envs.base import ControlMode
+    env = _mk(ControlMode.CARTESIAN_TQuat, gripper=True)
+    obs0, _ = env.reset()
+    t = obs0["tquat"].clone()
+    t[:, 2] = -0.05
+    _, _, _, _, info = env.step({"tquat": t, "gripper": torch.tensor([1.0], dtype=torch.float64)})
+    assert bool(info["collision"][0]) and bool(info["ik_success"][0])
+    env2 = _mk(ControlMode.CARTESIAN_TQuat, gripper=False)
+    obs0, _ = env2.reset()
+    far = obs0["tquat"].clone(); far[:, 0] = 2.0
+    obs, _, _, trunc, info = env2.step({"tquat": far})
+    assert not bool(info["ik_success"][0]) and bool(trunc[0])
+    assert np.allclose(obs["joints"].cpu().numpy(), obs0["joints"].cpu().numpy(), atol=1e-3)  # ctrl untouched
+
+
+def test_direct_api_matches_reference_semantics():
+    """examples/fr3/fr3_direct_control.py:62-200 call pattern: set_cartesian_position -> step_until_convergence."""
+    from rcs_b200 import common, sim
+    from rcs_b200.envs.utils import default_sim_gripper_cfg, default_sim_robot_cfg
+    cfg = default_sim_robot_cfg("fr3_empty_world")
+    simulation = sim.Sim(cfg.mjcf_scene_path)
+    ik = sim.Pin(cfg.kinematic_model_path, cfg.attachment_site, urdf=False)
+    robot = sim.SimRobot(simulation, ik, cfg)
+    gripper = sim.SimGripper(simulation, default_sim_gripper_cfg())
+    simulation.reset(); robot.reset(); simulation.step(1)
+    p0 = robot.get_cartesian_position()
+    assert isinstance(p0, common.Pose)
+    robot.set_cartesian_position(p0 * common.Pose(translation=np.array([0.05, 0, 0])))
+    simulation.step_until_convergence()
+    st = robot.get_state()
+    assert st.ik_success and not st.collision
+    p1 = robot.get_cartesian_position()
+    assert abs((p1.translation() - p0.translation())[2]) < 0.02
+    with pytest.raises(ValueError):
+        gripper.set_normalized_width(1.5)
+    gripper.open(); simulation.step(200)
+    assert gripper.get_normalized_width() > 0.5
+    with pytest.raises(RuntimeError, match="No geom named"):
+        bad = default_sim_robot_cfg("fr3_empty_world"); bad.arm_collision_geoms = ["nope"]
+        sim.SimRobot(sim.Sim(cfg.mjcf_scene_path), None, bad)
+    q = ik.inverse(p0, robot.get_joint_position())
+    assert q is not None and q.shape == (9,)
+    assert ik.forward(q[:7]).is_close(p0, 1e-3, 1e-3)
+
+
+def test_batched_relative_joint_env_async():
+    """The benchmark wiring (examples/fr3/fr3_env_joint_control.py:34-41) with num_envs = 512, async 30 Hz."""
+    from rcs_b200.envs.base import ControlMode
+    env = _mk(ControlMode.JOINTS, num_envs=512, gripper=True, max_rel=float(np.deg2rad(5)), async_control=True)
+    obs, _ = env.reset()
+    assert obs["joints"].shape == (512, 7) and obs["tquat"].shape == (512, 7) and obs["xyzrpy"].shape == (512, 6)
+    q_prev = obs["joints"].clone()
+    for _ in range(5):
+        act = env.action_space.sample()
+        obs, rew, term, trunc, info = env.step(act)
+        assert float((obs["joints"] - q_prev).abs().max()) < np.deg2rad(5) + 0.05
+        q_prev = obs["joints"].clone()
+    assert obs["gripper"].shape == (512,) and info["gripper_width"].shape == (512,)
+    assert not bool(term.any()) and float(rew.abs().max()) == 0.0
+    h_j = torch.zeros((512, 7), dtype=torch.float64).pin_memory(); h_g = torch.ones(512, dtype=torch.float64).pin_memory()
+    ho, hi = env.step_host(h_j, h_g)
+    assert ho.shape == (512, 22) and np.isfinite(ho.numpy()).all()
