@@ -97,6 +97,8 @@ int rcsb_robot_set_cartesian_position(rcsb_batch* b, const void* pose_dev);
 /* evidence counters */
 long long rcsb_launch_count(void); /* kernels launched by this library since load */
 int rcsb_kernel_occupancy(rcsb_batch* b, int* warps_per_cta, int* smem_bytes, int* grid);
+/* profiling build only (-DRCSB_STAGE_TIMING): accumulated clock64() cycles per physics stage of warp 0 / CTA 0, then reset */
+int rcsb_debug_stage_cycles(unsigned long long* out16);
 
 #ifdef __cplusplus
 }

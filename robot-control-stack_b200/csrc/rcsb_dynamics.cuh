@@ -17,52 +17,98 @@ struct Ctx {
   const real* verts;    // convex hull vertex pool (global memory, read-only)
   double* clk;          // this warp's simulation time + callback clocks (always double)
   int lane;
+  int lockstep;         // fixed-substep launch: CTA barriers between stages keep the warps on the same code
 };
 #define WR(name) (c.w + m.o_##name)
 #define WI(name) (c.wi + m.oi_##name)
 
 // misc int slots in the workspace
-enum { MI_NCON = 0, MI_NEFC, MI_NE, MI_NF, MI_NL, MI_NCAND, MI_SOLVER_ITER, MI_WARN, MI_COUNT };
+enum { MI_NCON = 0, MI_NEFC, MI_NE, MI_NF, MI_NL, MI_HAVE_L, MI_SOLVER_ITER, MI_WARN, MI_COUNT };
 
-// ------------------------------------------------------------------ dense Cholesky on shared memory
-// A (n x n, row-major) -> strictly-lower part holds L, dinv[j] = 1 / L[j][j]. A's diagonal is left
-// untouched so that no lane overwrites a value other lanes still read.
+// ------------------------------------------------------------------ dense Cholesky / triangular solves
+// A (n x n, row-major, shared memory) -> strictly-lower part holds L, dinv[j] = 1 / L[j][j]; A's diagonal is left
+// untouched. Device version: lane i owns row i in registers, pivots and multipliers travel by warp shuffles
+// (right-looking, no shared-memory round trips, no barriers inside the factorisation). The host-emulation build
+// keeps the plain column version (one lane).
+#ifdef RCSB_HOST_EMU
 RCSB_DEV_NOINLINE void chol_factor(const Ctx& c, real* A, real* dinv, int n) {
   for (int j = 0; j < n; j++) {
-    RCSB_SYNC();
     real d = A[j * n + j];
     for (int k = 0; k < j; k++) d -= A[j * n + k] * A[j * n + k];
     if (d < RCSB_MINVAL) d = RCSB_MINVAL;
-    real inv = r_rsqrt(d);
-    PFOR(ii, n - j - 1) {
-      int i = j + 1 + ii;
+    real inv = (real)1 / r_sqrt(d);
+    for (int i = j + 1; i < n; i++) {
       real t = A[i * n + j];
       for (int k = 0; k < j; k++) t -= A[i * n + k] * A[j * n + k];
       A[i * n + j] = t * inv;
     }
-    if (c.lane == 0) dinv[j] = inv;
+    dinv[j] = inv;
   }
-  RCSB_SYNC();
 }
 // x <- (L L^T)^{-1} x ; y is scratch of length n
 RCSB_DEV_NOINLINE void chol_solve(const Ctx& c, const real* L, const real* dinv, int n, real* x, real* y) {
   for (int k = 0; k < n; k++) {
-    RCSB_SYNC();
     real xk = x[k] * dinv[k];
-    PFOR(ii, n - k - 1) {
-      int i = k + 1 + ii;
-      x[i] -= L[i * n + k] * xk;
-    }
-    if (c.lane == 0) y[k] = xk;
+    for (int i = k + 1; i < n; i++) x[i] -= L[i * n + k] * xk;
+    y[k] = xk;
   }
   for (int k = n - 1; k >= 0; k--) {
-    RCSB_SYNC();
     real yk = y[k] * dinv[k];
-    PFOR(i, k) { y[i] -= L[k * n + i] * yk; }
-    if (c.lane == 0) x[k] = yk;
+    for (int i = 0; i < k; i++) y[i] -= L[k * n + i] * yk;
+    x[k] = yk;
+  }
+}
+#else
+RCSB_DEV_NOINLINE void chol_factor(const Ctx& c, real* A, real* dinv, int n) {
+  const int lane = c.lane;
+  real a[RCSB_MAXV];
+  RCSB_SYNC();
+#pragma unroll
+  for (int k = 0; k < RCSB_MAXV; k++) a[k] = (lane < n && k <= lane) ? A[lane * n + k] : (real)0;
+#pragma unroll
+  for (int j = 0; j < RCSB_MAXV; j++) {
+    if (j >= n) break;
+    real d = warp_bcast(a[j], j);
+    if (d < RCSB_MINVAL) d = RCSB_MINVAL;
+    real inv = rsqrt(d);
+    real lij = a[j] * inv;  // lane > j: L[lane][j]; lane == j: L[j][j]
+    a[j] = lane == j ? inv : lij;
+#pragma unroll
+    for (int k = j + 1; k < RCSB_MAXV; k++) {
+      if (k >= n) break;
+      real lkj = warp_bcast(lij, k);
+      if (lane >= k) a[k] -= lij * lkj;
+    }
+  }
+  if (lane < n) {
+#pragma unroll
+    for (int k = 0; k < RCSB_MAXV; k++) {
+      if (k < lane) A[lane * n + k] = a[k];
+      else if (k == lane) dinv[lane] = a[k];
+    }
   }
   RCSB_SYNC();
 }
+// x <- (L L^T)^{-1} x ; lane i carries x[i]; y is unused scratch (kept for the common signature)
+RCSB_DEV_NOINLINE void chol_solve(const Ctx& c, const real* L, const real* dinv, int n, real* x, real* y) {
+  const int lane = c.lane;
+  RCSB_SYNC();
+  real xi = lane < n ? x[lane] : (real)0;
+  real di = lane < n ? dinv[lane] : (real)0;
+  for (int j = 0; j < n; j++) {  // forward: L z = x
+    real zj = warp_bcast(xi * di, j);
+    if (lane == j) xi = zj;
+    else if (lane > j && lane < n) xi -= L[lane * n + j] * zj;
+  }
+  for (int j = n - 1; j >= 0; j--) {  // backward: L^T w = z
+    real wj = warp_bcast(xi * di, j);
+    if (lane == j) xi = wj;
+    else if (lane < j) xi -= L[j * n + lane] * wj;
+  }
+  if (lane < n) x[lane] = xi;
+  RCSB_SYNC();
+}
+#endif
 
 // ------------------------------------------------------------------ forward kinematics
 RCSB_DEV void st_kinematics(const Ctx& c) {
@@ -101,21 +147,40 @@ RCSB_DEV void st_kinematics(const Ctx& c) {
           pos[0] = pp[0] + v[0]; pos[1] = pp[1] + v[1]; pos[2] = pp[2] + v[2];
           quat_mul(quat, WR(bquat) + 4 * p, m.b_quat[b]);
         }
-        quat_to_mat(R, quat);
-        mulmat3(axis, R, m.b_jaxis[b]);
-        mulmat3(v, R, m.b_jpos[b]);
-        anchor[0] = pos[0] + v[0]; anchor[1] = pos[1] + v[1]; anchor[2] = pos[2] + v[2];
+        const real* jp = m.b_jpos[b];
+        const bool jp0 = jp[0] == 0 && jp[1] == 0 && jp[2] == 0;  // every shipped joint sits at its body origin
         if (m.b_jtype[b] == RCSB_JNT_SLIDE) {
+          quat_normalize(quat);
+          quat_to_mat(R, quat);
+          mulmat3(axis, R, m.b_jaxis[b]);
+          mulmat3(v, R, jp);
+          anchor[0] = pos[0] + v[0]; anchor[1] = pos[1] + v[1]; anchor[2] = pos[2] + v[2];
           real qq = q[m.b_qadr[b]] - m.qpos0[m.b_qadr[b]];
           pos[0] += axis[0] * qq; pos[1] += axis[1] * qq; pos[2] += axis[2] * qq;
         } else {
+          if (jp0) copy3(anchor, pos);
+          else {
+            quat_to_mat(R, quat);
+            mulmat3(v, R, jp);
+            anchor[0] = pos[0] + v[0]; anchor[1] = pos[1] + v[1]; anchor[2] = pos[2] + v[2];
+          }
           real s = sc[2 * b], ql[4] = {sc[2 * b + 1], m.b_jaxis[b][0] * s, m.b_jaxis[b][1] * s, m.b_jaxis[b][2] * s}, qn[4];
           quat_mul(qn, quat, ql);
           quat[0] = qn[0]; quat[1] = qn[1]; quat[2] = qn[2]; quat[3] = qn[3];
+          quat_normalize(quat);
           quat_to_mat(R, quat);
-          mulmat3(v, R, m.b_jpos[b]);
-          pos[0] = anchor[0] - v[0]; pos[1] = anchor[1] - v[1]; pos[2] = anchor[2] - v[2];
+          mulmat3(axis, R, m.b_jaxis[b]);  // a rotation about the joint axis leaves the axis in place
+          if (!jp0) {
+            mulmat3(v, R, jp);
+            pos[0] = anchor[0] - v[0]; pos[1] = anchor[1] - v[1]; pos[2] = anchor[2] - v[2];
+          }
         }
+        copy3(WR(bpos) + 3 * b, pos);
+        real* bq = WR(bquat) + 4 * b;
+        bq[0] = quat[0]; bq[1] = quat[1]; bq[2] = quat[2]; bq[3] = quat[3];
+        real* bm = WR(bmat) + 9 * b;
+        for (int i = 0; i < 9; i++) bm[i] = R[i];
+        continue;
       }
       quat_normalize(quat);
       copy3(WR(bpos) + 3 * b, pos);
@@ -287,7 +352,9 @@ RCSB_DEV void st_crb(const Ctx& c) {
       WR(L)[j * nv + i] = val;
     }
   }
-  chol_factor(c, WR(L), WR(L) + nv * nv, nv);
+  // the factorisation of M is deferred (ensure_chol_M): the all-equality solver path never needs it
+  if (c.lane == 0) c.wi[m.oi_misc + MI_HAVE_L] = 0;
+  RCSB_SYNC();
 }
 
 // ------------------------------------------------------------------ velocity stage: bias, passive, gravity compensation
@@ -466,7 +533,11 @@ RCSB_DEV void expand_portal(Sup* s, const Sup& v4) {
 }
 // Minkowski Portal Refinement penetration query (algorithm of libccd's ccdMPRPenetration, which
 // MuJoCo 3.2.6 uses for convex pairs). Warp-uniform control flow; only support() is cooperative.
-RCSB_DEV_NOINLINE int mpr_penetration(const Ctx& c, const PairFrames& pf, real* depth, real* dir_out, real* pos) {
+// When the query ends on a support check "the Minkowski difference does not reach past the origin along dir",
+// dir is a separating direction; it is handed back through sep (sep[3] = 1) so the caller can re-validate it with
+// a single support pair on the next substeps instead of repeating the whole query.
+RCSB_DEV_NOINLINE int mpr_penetration(const Ctx& c, const PairFrames& pf, real* depth, real* dir_out, real* pos, real* sep) {
+  sep[3] = 0;
   Sup s[4], v4;
   real dir[3], va[3], vb[3];
   for (int k = 0; k < 3; k++) { s[0].v1[k] = pf.p1[k]; s[0].v2[k] = pf.p2[k]; s[0].v[k] = pf.p1[k] - pf.p2[k]; }
@@ -474,7 +545,7 @@ RCSB_DEV_NOINLINE int mpr_penetration(const Ctx& c, const PairFrames& pf, real* 
   dir[0] = -s[0].v[0]; dir[1] = -s[0].v[1]; dir[2] = -s[0].v[2];
   normalize3(dir);
   mink_support(c, pf, dir, s[1]);
-  if (dot3(s[1].v, dir) <= 0) return 0;
+  if (dot3(s[1].v, dir) <= 0) { copy3(sep, dir); sep[3] = 1; return 0; }
   cross3(dir, s[0].v, s[1].v);
   if (dot3(dir, dir) < (real)1e-24) {
     *depth = norm3(s[1].v);
@@ -484,7 +555,7 @@ RCSB_DEV_NOINLINE int mpr_penetration(const Ctx& c, const PairFrames& pf, real* 
   }
   normalize3(dir);
   mink_support(c, pf, dir, s[2]);
-  if (dot3(s[2].v, dir) <= 0) return 0;
+  if (dot3(s[2].v, dir) <= 0) { copy3(sep, dir); sep[3] = 1; return 0; }
   for (int k = 0; k < 3; k++) { va[k] = s[1].v[k] - s[0].v[k]; vb[k] = s[2].v[k] - s[0].v[k]; }
   cross3(dir, va, vb);
   normalize3(dir);
@@ -495,7 +566,7 @@ RCSB_DEV_NOINLINE int mpr_penetration(const Ctx& c, const PairFrames& pf, real* 
   for (int it = 0;; it++) {
     if (it > 100) return 0;
     mink_support(c, pf, dir, s[3]);
-    if (dot3(s[3].v, dir) <= 0) return 0;
+    if (dot3(s[3].v, dir) <= 0) { copy3(sep, dir); sep[3] = 1; return 0; }
     int cont = 0;
     cross3(va, s[1].v, s[3].v);
     if (dot3(va, s[0].v) < (real)-1e-18) { s[2] = s[3]; cont = 1; }
@@ -512,7 +583,8 @@ RCSB_DEV_NOINLINE int mpr_penetration(const Ctx& c, const PairFrames& pf, real* 
     portal_dir(s, dir);
     if (dot3(s[1].v, dir) >= 0) break;
     mink_support(c, pf, dir, v4);
-    if (dot3(v4.v, dir) < 0 || portal_reach_tol(s, v4, dir) || it >= 50) return 0;
+    if (dot3(v4.v, dir) < 0) { copy3(sep, dir); sep[3] = 1; return 0; }
+    if (portal_reach_tol(s, v4, dir) || it >= 50) return 0;
     expand_portal(s, v4);
   }
   for (int it = 0;; it++) {
@@ -740,9 +812,29 @@ RCSB_DEV void st_collision(const Ctx& c) {
     } else {
       real depth, dir[3], pos[3];
       // depth < 1e-12: exactly touching pair (finger pads at qpos0), not a constraint; see oracle/mj_collision.c
-      if (mpr_penetration(c, pf, &depth, dir, pos) && depth >= (real)1e-12) add_contact(c, ncon, pf.g1, pf.g2, -depth, pos, dir, margin, gap);
+      // Separating-direction cache (4 direct-mapped slots, lives for the launch): a direction that separated the pair
+      // on an earlier substep is re-checked with one support pair; disjoint pairs stay disjoint for many substeps
+      // (link5 / link7 overlap in their boxes in every pose), so the full query runs about once per env.step().
+      real* sc = WR(sepcache) + 4 * (p & 3);
+      int skip = 0;
+      if (sc[0] == (real)p) {
+        Sup s;
+        mink_support(c, pf, sc + 1, s);
+        skip = dot3(s.v, sc + 1) <= 0;
+      }
+      if (!skip) {
+        real sep[4];
+        int hit = mpr_penetration(c, pf, &depth, dir, pos, sep);
+        if (hit && depth >= (real)1e-12) add_contact(c, ncon, pf.g1, pf.g2, -depth, pos, dir, margin, gap);
+        RCSB_SYNC();
+        if (c.lane == 0) {
+          if (!hit && sep[3] != 0) { sc[0] = (real)p; sc[1] = sep[0]; sc[2] = sep[1]; sc[3] = sep[2]; }
+          else if (sc[0] == (real)p) sc[0] = -1;
+        }
+        RCSB_SYNC();
+      }
     }
   }
-  if (c.lane == 0) { WI(misc)[MI_NCON] = ncon; WI(misc)[MI_NCAND] = ncand; }
+  if (c.lane == 0) WI(misc)[MI_NCON] = ncon;
   RCSB_SYNC();
 }

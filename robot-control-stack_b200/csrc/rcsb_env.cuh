@@ -148,6 +148,7 @@ RCSB_DEV void load_env(const Ctx& c, const real* sr, const double* sd, const int
   PFOR(i, RCSB_D_TAIL) { c.clk[i] = sd[i]; }
   PFOR(i, RCSB_I_TAIL) { c.wi[m.oi_misc + MI_COUNT + i] = si[i]; }
   PFOR(i, MI_COUNT) { c.wi[m.oi_misc + i] = 0; }
+  PFOR(i, 4) { WR(sepcache)[4 * i] = -1; }
   RCSB_SYNC();
 }
 RCSB_DEV void store_env(const Ctx& c, real* sr, double* sd, int* si) {
@@ -255,7 +256,6 @@ RCSB_DEV void run_env_program(const Ctx& c, const RcsbLaunch& L, int env) {
   if ((ops & RCSB_OP_SET_GRIPPER) && m.gr_enabled) op_set_gripper(c, L.act_gripper[env]);
   if (ops & RCSB_OP_STEP_K) {  // sim.cpp:108-115
     for (int i = 0; i < L.k; i++) {
-      RCSB_BLOCK_SYNC();  // fixed-k mode: keep the CTA's warps in the same stage so they share instruction-cache lines
       physics_step(c, &c.clk[RCSB_D_TIME]);
     }
   }

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -62,6 +63,7 @@ __device__ __forceinline__ Ctx make_ctx(const RcsbModel* sm, const real* verts, 
   c.wi = (int*)(base + (size_t)sm->ws_reals * sizeof(real) + (size_t)sm->ws_doubles * sizeof(double));
   c.verts = verts;
   c.lane = threadIdx.x & 31;
+  c.lockstep = 0;
   return c;
 }
 __device__ __forceinline__ const RcsbModel* stage_model(const RcsbModel* gm) {
@@ -88,8 +90,9 @@ rcsb_k_run(const RcsbModel* __restrict__ gm, const real* __restrict__ verts, rea
   Ctx c = make_ctx(sm, verts, ws_bytes);
   if (L.ops & RCSB_OP_STEP_K) {
     // Fixed-substep launch: static env -> warp mapping. Every warp of the CTA runs the same number of rounds and
-    // hits exactly L.k CTA barriers per round (inside run_env_program, or here when it has no environment), which
+    // hits exactly L.k * RCSB_STAGE_BARRIERS CTA barriers per round (inside run_env_program, or here when it has no environment), which
     // keeps the warps in the same stage of the step so that they share instruction-cache lines.
+    c.lockstep = 1;
     const int W = blockDim.x >> 5, per_round = gridDim.x * W;
     const int rounds = (L.N + per_round - 1) / per_round;
     for (int r = 0; r < rounds; r++) {
@@ -101,7 +104,7 @@ rcsb_k_run(const RcsbModel* __restrict__ gm, const real* __restrict__ verts, rea
         store_env(c, sr + (size_t)env * sm->nsr, sd + (size_t)env * RCSB_D_TAIL, si + (size_t)env * RCSB_I_TAIL);
         __syncwarp();
       } else {
-        for (int i = 0; i < L.k; i++) __syncthreads();
+        for (int i = 0; i < L.k * RCSB_STAGE_BARRIERS; i++) __syncthreads();
       }
     }
     return;
@@ -251,6 +254,10 @@ rcsb_batch* rcsb_batch_new(rcsb_model* m, int n_envs, void* sr, void* sd, void* 
   size_t avail = prop.sharedMemPerBlockOptin;
   int w = (int)((avail - RCSB_SMEM_HEADER) / b->ws_bytes);
   if (w > RCSB_MAX_WARPS) w = RCSB_MAX_WARPS;
+  if (const char* ov = getenv("RCSB_WARPS")) {  // tuning / profiling knob: fewer warps per CTA
+    int o = atoi(ov);
+    if (o >= 1 && o < w) w = o;
+  }
   if (w < 1) { fail(RCSB_ERR_MODEL, "workspace does not fit in shared memory"); delete b; return nullptr; }
   b->warps = w;
   b->smem = RCSB_SMEM_HEADER + (size_t)w * b->ws_bytes;
@@ -272,6 +279,18 @@ void rcsb_batch_free(rcsb_batch* b) {
   if (b->h_act) cudaFreeHost(b->h_act);
   if (b->h_obs) cudaFreeHost(b->h_obs);
   delete b;
+}
+int rcsb_debug_stage_cycles(unsigned long long* out16) {
+#ifdef RCSB_STAGE_TIMING
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpyFromSymbol(out16, rcsb_stage_cycles, 16 * sizeof(unsigned long long)));
+  unsigned long long z[16] = {0};
+  CUDA_OK(cudaMemcpyToSymbol(rcsb_stage_cycles, z, sizeof(z)));
+  return RCSB_OK;
+#else
+  for (int i = 0; i < 16; i++) out16[i] = 0;
+  return fail(RCSB_ERR_ARG, "library built without RCSB_STAGE_TIMING");
+#endif
 }
 int rcsb_kernel_occupancy(rcsb_batch* b, int* warps_per_cta, int* smem_bytes, int* grid) {
   if (warps_per_cta) *warps_per_cta = b->warps;

@@ -32,7 +32,7 @@ static const RcsbField rcsb_model_fields[] = {
     RCSB_FB(pair),
     RCSB_FR(t_coef), RCSB_FI(e_dof1), RCSB_FI(e_dof2), RCSB_FI(e_active), RCSB_FR(e_poly), RCSB_FR(e_solref),
     RCSB_FR(e_solimp),
-    RCSB_FI(a_trntype), RCSB_FI(a_trnid), RCSB_FI(a_ctrllimited), RCSB_FI(a_forcelimited), RCSB_FR(a_gear),
+    RCSB_FI(n_special), RCSB_FI(a_special), RCSB_FR(d_kvdiag), RCSB_FI(a_trntype), RCSB_FI(a_trnid), RCSB_FI(a_ctrllimited), RCSB_FI(a_forcelimited), RCSB_FR(a_gear),
     RCSB_FR(a_gain), RCSB_FR(a_bias), RCSB_FR(a_ctrlrange), RCSB_FR(a_forcerange),
     RCSB_FI(rb_njoints), RCSB_FI(rb_qadr), RCSB_FI(rb_act), RCSB_FI(rb_site_body), RCSB_FI(rb_register_convergence),
     RCSB_FI(rb_ik_nq), RCSB_FR(rb_site_pos), RCSB_FR(rb_site_quat), RCSB_FR(rb_base_pos), RCSB_FR(rb_base_quat),
@@ -100,6 +100,7 @@ static inline int rcsb_model_finalize_layout(RcsbModel* m) {
   RCSB_ALLOC(o_con, RCSB_C_REALS * m->maxcon);
   RCSB_ALLOC(o_J, m->maxefc * nv);
   RCSB_ALLOC(o_efc, RCSB_E_NARR * m->maxefc);
+  RCSB_ALLOC(o_sepcache, 16);  // 4 x (pair tag, separating direction), valid for one launch
   o = (o + 1) & ~1;  // keep the double clock block 16-byte aligned when real is 8 bytes
   m->ws_reals = o;
   m->ws_doubles = RCSB_D_TAIL;

@@ -20,6 +20,7 @@ RCSB_DEV void get_impedance(const real* solimp, real pos, real margin, real* imp
   if (x >= 1) { *imp = dmax; return; }
   if (x <= 0) { *imp = dmin; return; }
   if (power == 1) y = x;
+  else if (power == 2) y = x <= mid ? x * x / mid : 1 - (1 - x) * (1 - x) / (1 - mid);  // the default; avoids pow()
   else if (x <= mid) y = pow(x, power) / pow(mid, power - 1);
   else y = 1 - pow(1 - x, power) / pow(1 - mid, power - 1);
   *imp = dmin + y * (dmax - dmin);
@@ -245,9 +246,24 @@ RCSB_DEV void st_actuation(const Ctx& c) {
     WR(actfrc)[k] = s;
     real sm = WR(passive)[k] - WR(bias)[k] + s;
     WR(smooth)[k] = sm;
-    WR(qacc_smooth)[k] = sm;
   }
-  chol_solve(c, WR(L), WR(L) + nv * nv, nv, WR(qacc_smooth), WR(tmp));
+  RCSB_SYNC();
+}
+// Cholesky factor of M on demand (o_L holds a copy of M until then)
+RCSB_DEV void ensure_chol_M(const Ctx& c) {
+  const RcsbModel& m = *c.md;
+  if (!WI(misc)[MI_HAVE_L]) {
+    chol_factor(c, WR(L), WR(L) + m.nv * m.nv, m.nv);
+    if (c.lane == 0) WI(misc)[MI_HAVE_L] = 1;
+    RCSB_SYNC();
+  }
+}
+// qacc_smooth = M^-1 qfrc_smooth (mj_fwdAcceleration); only the general solver path and nefc == 0 need it
+RCSB_DEV void compute_qacc_smooth(const Ctx& c) {
+  const RcsbModel& m = *c.md;
+  ensure_chol_M(c);
+  PFOR(k, m.nv) { WR(qacc_smooth)[k] = WR(smooth)[k]; }
+  chol_solve(c, WR(L), WR(L) + m.nv * m.nv, m.nv, WR(qacc_smooth), WR(tmp));
 }
 
 // ------------------------------------------------------------------ constraint cost, forces, states
@@ -562,11 +578,50 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
   const int nv = m.nv;
   int nefc = WI(misc)[MI_NEFC], ncon = WI(misc)[MI_NCON];
   if (nefc == 0) {
+    compute_qacc_smooth(c);
     PFOR(k, nv) { WR(qacc)[k] = WR(qacc_smooth)[k]; WR(qfc)[k] = 0; }
     if (c.lane == 0) WI(misc)[MI_SOLVER_ITER] = 0;
     RCSB_SYNC();
     return;
   }
+  if (WI(misc)[MI_NE] == nefc) {
+    // Every row is an equality (always-active quadratic): the strictly convex cost is an unconstrained quadratic
+    // whose minimiser solves (M + J^T D J) qacc = qfrc_smooth + J^T D aref. This is the point the Newton iteration
+    // with exact line search reaches in one step; no cost evaluations, line search or factorisation of M needed.
+    PFOR(e, nv * nv) {
+      int a = e / nv, b = e - a * nv;
+      if (b > a) continue;
+      real h = WR(M)[e];
+      for (int r = 0; r < nefc; r++) h += EFC(RCSB_E_D)[r] * WR(J)[r * nv + a] * WR(J)[r * nv + b];
+      WR(H)[a * nv + b] = h;
+      WR(H)[b * nv + a] = h;
+    }
+    PFOR(k, nv) {
+      real s = WR(smooth)[k];
+      for (int r = 0; r < nefc; r++) s += EFC(RCSB_E_D)[r] * EFC(RCSB_E_AREF)[r] * WR(J)[r * nv + k];
+      WR(qacc)[k] = s;
+    }
+    chol_factor(c, WR(H), WR(H) + nv * nv, nv);
+    chol_solve(c, WR(H), WR(H) + nv * nv, nv, WR(qacc), WR(tmp));
+    PFOR(r, nefc) {
+      real s = 0;
+      for (int k = 0; k < nv; k++) s += WR(J)[r * nv + k] * WR(qacc)[k];
+      real jar = s - EFC(RCSB_E_AREF)[r];
+      EFC(RCSB_E_JAR)[r] = jar;
+      EFC(RCSB_E_FORCE)[r] = -EFC(RCSB_E_D)[r] * jar;
+      EFCI(RCSB_EI_STATE)[r] = RCSB_QUADRATIC;
+    }
+    RCSB_SYNC();
+    PFOR(k, nv) {
+      real s = 0;
+      for (int r = 0; r < nefc; r++) s += WR(J)[r * nv + k] * EFC(RCSB_E_FORCE)[r];
+      WR(qfc)[k] = s;
+    }
+    if (c.lane == 0) WI(misc)[MI_SOLVER_ITER] = 1;
+    RCSB_SYNC();
+    return;
+  }
+  compute_qacc_smooth(c);
   // warm start: keep qacc_warmstart only if its cost beats qacc_smooth's
   real gauss;
   real cost_smooth = total_cost(c, WR(qacc_smooth), nefc, ncon, 0, nullptr);
@@ -653,9 +708,10 @@ RCSB_DEV void st_integrate(const Ctx& c) {
   PFOR(e, nv * nv) {
     int i = e / nv, j = e - i * nv;
     if (j > i) continue;
-    real dv = (i == j) ? -m.d_damping[i] : (real)0;
+    real dv = (i == j) ? -m.d_damping[i] + (m.implicitfast ? m.d_kvdiag[i] : (real)0) : (real)0;
     if (m.implicitfast) {
-      for (int a = 0; a < m.nu; a++) {
+      for (int sa = 0; sa < m.n_special; sa++) {
+        int a = m.a_special[sa];
         real bv = m.a_bias[a][2];
         if (bv == 0) continue;
         real fa = WR(aforce)[a];
@@ -824,25 +880,43 @@ RCSB_DEV void reset_data(const Ctx& c, double* time) {  // mj_resetData
   *time = 0;
   RCSB_SYNC();
 }
+// RCSB_STAGE: CTA barrier (lockstep launches only) + the stage; the profiling build (-DRCSB_STAGE_TIMING) also
+// accumulates clock64() per stage for warp 0 of CTA 0 into rcsb_stage_cycles[].
+#if defined(RCSB_STAGE_TIMING) && !defined(RCSB_HOST_EMU)
+__device__ unsigned long long rcsb_stage_cycles[16];
+#define RCSB_STAGE(idx, call)                                                                        \
+  do {                                                                                               \
+    RCSB_BLOCK_SYNC();                                                                               \
+    long long t0_ = clock64();                                                                       \
+    call;                                                                                            \
+    if (blockIdx.x == 0 && threadIdx.x == 0) rcsb_stage_cycles[idx] += (unsigned long long)(clock64() - t0_); \
+  } while (0)
+#else
+#define RCSB_STAGE(idx, call) do { RCSB_BLOCK_SYNC(); call; } while (0)
+#endif
 RCSB_DEV void physics_step(const Ctx& c, double* time) {
   const RcsbModel& m = *c.md;
   if (state_is_bad(c)) {
     if (c.lane == 0) WI(misc)[MI_WARN] += 1;
     reset_data(c, time);
   }
+  // In lockstep (fixed-substep) launches every stage starts behind a CTA barrier: the hot step is ~200 KB of
+  // straight-line code, far larger than the instruction cache, so warps that run the same stage together share
+  // each fetched line instead of streaming the whole program once per warp. RCSB_STAGE_BARRIERS of them per step.
   // ---- mj_step1
-  st_kinematics(c);
-  st_com(c);
-  st_crb(c);
-  st_collision(c);
-  st_velocity(c);
-  st_make_constraint(c);
+  RCSB_STAGE(0, st_kinematics(c));
+  RCSB_STAGE(1, st_com(c));
+  RCSB_STAGE(2, st_crb(c));
+  RCSB_STAGE(3, st_collision(c));
+  RCSB_STAGE(4, st_velocity(c));
+  RCSB_STAGE(5, st_make_constraint(c));
   // ---- RCS plain callbacks see pre-integration time and qpos
   invoke_callbacks(c, *time);
   // ---- mj_step2
-  st_actuation(c);
-  st_constraint_solve(c);
-  st_integrate(c);
+  RCSB_STAGE(6, st_actuation(c));
+  RCSB_STAGE(7, st_constraint_solve(c));
+  RCSB_STAGE(8, st_integrate(c));
+  RCSB_BLOCK_SYNC();
   *time += (double)m.timestep;
   if (c.lane == 0) RI(RCSB_I_TOTAL_STEPS) += 1;
 }

@@ -76,6 +76,9 @@ struct RcsbModel {
   int e_dof1[RCSB_MAXEQ], e_dof2[RCSB_MAXEQ], e_active[RCSB_MAXEQ];
   real e_poly[RCSB_MAXEQ][5], e_solref[RCSB_MAXEQ][2], e_solimp[RCSB_MAXEQ][5];
   int a_trntype[RCSB_MAXU], a_trnid[RCSB_MAXU], a_ctrllimited[RCSB_MAXU], a_forcelimited[RCSB_MAXU];
+  // implicitfast derivative: joint actuators that can never be force-clamped fold into a per-dof constant
+  int n_special, a_special[RCSB_MAXU];  // actuators that need the per-step treatment (tendon transmission or forcerange)
+  real d_kvdiag[RCSB_MAXV];             // sum of bias2*gear^2 of the folded joint actuators
   real a_gear[RCSB_MAXU], a_gain[RCSB_MAXU], a_bias[RCSB_MAXU][3], a_ctrlrange[RCSB_MAXU][2], a_forcerange[RCSB_MAXU][2];
   // ---- RCS device layer: SimRobot / SimGripper configuration
   int rb_njoints, rb_qadr[RCSB_MAXJ], rb_act[RCSB_MAXJ], rb_site_body, rb_register_convergence, rb_ik_nq;
@@ -88,7 +91,7 @@ struct RcsbModel {
   int o_q, o_v, o_ctrl, o_warm, o_bpos, o_bquat, o_bmat, o_bcom, o_bgc, o_janchor, o_jaxis, o_rootcom, o_cinert, o_crb,
       o_cdof, o_cdofdot, o_cvel, o_cacc, o_cfrc, o_M, o_L, o_H, o_bias, o_passive, o_gravc, o_actfrc, o_smooth,
       o_qacc_smooth, o_qacc, o_qfc, o_grad, o_search, o_Ma, o_Mv, o_tmp, o_alen, o_avel, o_aforce, o_gpos, o_con,
-      o_J, o_efc, o_conehess, o_noslip, o_site, o_rcs;
+      o_J, o_efc, o_conehess, o_noslip, o_site, o_rcs, o_sepcache;
   int ws_doubles;  // RCSB_D_TAIL doubles per warp follow the reals
   int oi_con, oi_efc, oi_cand, oi_misc;
 };

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.abspath(os.path.join(_HERE, "..", "csrc", "librcsb.so"))
+LIB_PATH = os.environ.get("RCSB_LIB_PATH") or os.path.abspath(os.path.join(_HERE, "..", "csrc", "librcsb.so"))
 _LIB = None
 
 
@@ -77,4 +77,4 @@ EXPORTS = ["rcsb_last_error", "rcsb_version", "rcsb_real_bytes", "rcsb_model_new
            "rcsb_sim_step_until_convergence", "rcsb_sim_reset", "rcsb_robot_set_joint_position",
            "rcsb_robot_set_joints_hard", "rcsb_robot_reset", "rcsb_gripper_set_normalized_width",
            "rcsb_gripper_reset", "rcsb_env_get_obs", "rcsb_ik_inverse", "rcsb_robot_set_cartesian_position",
-           "rcsb_launch_count", "rcsb_kernel_occupancy"]
+           "rcsb_launch_count", "rcsb_kernel_occupancy", "rcsb_debug_stage_cycles"]

@@ -239,6 +239,16 @@ def build_device_fields(M: dict, robot_cfg=None, gripper_cfg=None, maxcon: int |
                     for t, tt in zip(M["actuator_trnid"], M["actuator_trntype"])], False)
     put("a_ctrllimited", M["actuator_ctrllimited"], False)
     put("a_forcelimited", M["actuator_forcelimited"], False)
+    # implicitfast damping derivative: fold never-clamped joint actuators into a per-dof constant
+    kvdiag, special = np.zeros(nv), []
+    for a in range(nu):
+        if M["actuator_trntype"][a] == mjcf.TRN_JOINT and not M["actuator_forcelimited"][a]:
+            kvdiag[M["jnt_dofadr"][M["actuator_trnid"][a]]] += M["actuator_biasprm"][a][2] * M["actuator_gear"][a] ** 2
+        else:
+            special.append(a)
+    put("d_kvdiag", kvdiag, True)
+    put("n_special", [len(special)], False)
+    put("a_special", special if special else [0], False)
     put("a_gear", M["actuator_gear"], True)
     put("a_gain", M["actuator_gainprm"][:, 0], True)
     put("a_bias", M["actuator_biasprm"], True)

@@ -33,7 +33,7 @@ void emu_run(const RcsbModel* m, const real* verts, real* sr, double* sd, int* s
   L.obs = obs; L.info = info;
   for (int e = 0; e < N; e++) {
     if (mask && !mask[e]) continue;
-    Ctx c = {m, w.data(), wi.data(), verts, clk, 0};
+    Ctx c = {m, w.data(), wi.data(), verts, clk, 0, 0};
     load_env(c, sr + (size_t)e * m->nsr, sd + (size_t)e * RCSB_D_TAIL, si + (size_t)e * RCSB_I_TAIL);
     run_env_program(c, L, e);
     store_env(c, sr + (size_t)e * m->nsr, sd + (size_t)e * RCSB_D_TAIL, si + (size_t)e * RCSB_I_TAIL);
