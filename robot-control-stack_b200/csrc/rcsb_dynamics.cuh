@@ -59,33 +59,55 @@ RCSB_DEV_NOINLINE void chol_solve(const Ctx& c, const real* L, const real* dinv,
   }
 }
 #else
-RCSB_DEV_NOINLINE void chol_factor(const Ctx& c, real* A, real* dinv, int n) {
+// Size-specialised body: with N a compile-time constant every loop unrolls and the row a[] stays in registers.
+template <int N>
+RCSB_DEV void chol_factor_n(const Ctx& c, real* A, real* dinv) {
   const int lane = c.lane;
-  real a[RCSB_MAXV];
-  RCSB_SYNC();
+  real a[N];
 #pragma unroll
-  for (int k = 0; k < RCSB_MAXV; k++) a[k] = (lane < n && k <= lane) ? A[lane * n + k] : (real)0;
+  for (int k = 0; k < N; k++) a[k] = (lane < N && k <= lane) ? A[lane * N + k] : (real)0;
 #pragma unroll
-  for (int j = 0; j < RCSB_MAXV; j++) {
-    if (j >= n) break;
+  for (int j = 0; j < N; j++) {
     real d = warp_bcast(a[j], j);
     if (d < RCSB_MINVAL) d = RCSB_MINVAL;
     real inv = rsqrt(d);
     real lij = a[j] * inv;  // lane > j: L[lane][j]; lane == j: L[j][j]
     a[j] = lane == j ? inv : lij;
 #pragma unroll
-    for (int k = j + 1; k < RCSB_MAXV; k++) {
-      if (k >= n) break;
+    for (int k = j + 1; k < N; k++) {
       real lkj = warp_bcast(lij, k);
       if (lane >= k) a[k] -= lij * lkj;
     }
   }
-  if (lane < n) {
+  if (lane < N) {
 #pragma unroll
-    for (int k = 0; k < RCSB_MAXV; k++) {
-      if (k < lane) A[lane * n + k] = a[k];
+    for (int k = 0; k < N; k++) {
+      if (k < lane) A[lane * N + k] = a[k];
       else if (k == lane) dinv[lane] = a[k];
     }
+  }
+}
+RCSB_DEV_NOINLINE void chol_factor(const Ctx& c, real* A, real* dinv, int n) {
+  RCSB_SYNC();
+  switch (n) {  // dof counts of the supported scenes: xArm7 (7), FR3 + fingers (9), FR3 + fingers + free cube (15)
+    case 7: chol_factor_n<7>(c, A, dinv); break;
+    case 9: chol_factor_n<9>(c, A, dinv); break;
+    case 15: chol_factor_n<15>(c, A, dinv); break;
+    default:  // any other size: column version on shared memory
+      for (int j = 0; j < n; j++) {
+        RCSB_SYNC();
+        real d = A[j * n + j];
+        for (int k = 0; k < j; k++) d -= A[j * n + k] * A[j * n + k];
+        if (d < RCSB_MINVAL) d = RCSB_MINVAL;
+        real inv = rsqrt(d);
+        PFOR(ii, n - j - 1) {
+          int i = j + 1 + ii;
+          real t = A[i * n + j];
+          for (int k = 0; k < j; k++) t -= A[i * n + k] * A[j * n + k];
+          A[i * n + j] = t * inv;
+        }
+        if (c.lane == 0) dinv[j] = inv;
+      }
   }
   RCSB_SYNC();
 }
@@ -111,82 +133,91 @@ RCSB_DEV_NOINLINE void chol_solve(const Ctx& c, const real* L, const real* dinv,
 #endif
 
 // ------------------------------------------------------------------ forward kinematics
+// Rotation-matrix form: every body's local transform (static offset composed with its joint motion) is built in
+// parallel, one lane per body; the chain is then walked with 12 lanes per body (9 matrix entries + 3 position
+// entries, each a 3-term dot product), so the serial depth per body is a handful of FMAs instead of a lane-serial
+// quaternion chain.
 RCSB_DEV void st_kinematics(const Ctx& c) {
   const RcsbModel& m = *c.md;
   real* q = WR(q);
-  real* sc = WR(tmp);
+  real* Rl = WR(bquat);            // scratch: local rotation [nb][9] then local translation [nb][3] (o_bquat holds 12*nb)
+  real* tl = Rl + 9 * m.nb;
   PFOR(b, m.nb) {
-    if (m.b_jtype[b] == RCSB_JNT_HINGE) {
-      real a = (real)0.5 * (q[m.b_qadr[b]] - m.qpos0[m.b_qadr[b]]);
-      sc[2 * b] = sin(a);
-      sc[2 * b + 1] = cos(a);
+    real* R = Rl + 9 * b;
+    real* t = tl + 3 * b;
+    if (m.b_jtype[b] == RCSB_JNT_FREE) {
+      real* qq = q + m.b_qadr[b];
+      quat_normalize(qq + 3);
+      quat_to_mat(R, qq + 3);
+      copy3(t, qq);
+    } else {
+      real Rb[9];
+      quat_to_mat(Rb, m.b_quat[b]);
+      const real* u = m.b_jaxis[b];
+      const real* jp = m.b_jpos[b];
+      real qq = q[m.b_qadr[b]] - m.qpos0[m.b_qadr[b]];
+      if (m.b_jtype[b] == RCSB_JNT_SLIDE) {
+        real v[3];
+        mulmat3(v, Rb, u);
+        for (int i = 0; i < 9; i++) R[i] = Rb[i];
+        t[0] = m.b_pos[b][0] + v[0] * qq; t[1] = m.b_pos[b][1] + v[1] * qq; t[2] = m.b_pos[b][2] + v[2] * qq;
+      } else {
+        real s = sin(qq), co = cos(qq), oc = 1 - co;  // Rodrigues rotation about the joint axis
+        real Rj[9] = {co + oc * u[0] * u[0], oc * u[0] * u[1] - s * u[2], oc * u[0] * u[2] + s * u[1],
+                      oc * u[1] * u[0] + s * u[2], co + oc * u[1] * u[1], oc * u[1] * u[2] - s * u[0],
+                      oc * u[2] * u[0] - s * u[1], oc * u[2] * u[1] + s * u[0], co + oc * u[2] * u[2]};
+        for (int r = 0; r < 3; r++)
+          for (int k = 0; k < 3; k++) R[3 * r + k] = Rb[3 * r] * Rj[k] + Rb[3 * r + 1] * Rj[3 + k] + Rb[3 * r + 2] * Rj[6 + k];
+        // the body origin moves when the joint anchor is off-origin: t = b_pos + Rb*(jp - Rj*jp)
+        real w[3], v[3];
+        mulmat3(w, Rj, jp);
+        w[0] = jp[0] - w[0]; w[1] = jp[1] - w[1]; w[2] = jp[2] - w[2];
+        mulmat3(v, Rb, w);
+        t[0] = m.b_pos[b][0] + v[0]; t[1] = m.b_pos[b][1] + v[1]; t[2] = m.b_pos[b][2] + v[2];
+      }
     }
   }
   RCSB_SYNC();
-  if (c.lane == 0) {
-    for (int b = 0; b < m.nb; b++) {
-      int p = m.b_parent[b];
-      real pos[3], quat[4];
-      real* anchor = WR(janchor) + 3 * b;
-      real* axis = WR(jaxis) + 3 * b;
-      if (m.b_jtype[b] == RCSB_JNT_FREE) {
-        real* qq = q + m.b_qadr[b];
-        quat_normalize(qq + 3);
-        copy3(pos, qq);
-        quat[0] = qq[3]; quat[1] = qq[4]; quat[2] = qq[5]; quat[3] = qq[6];
-        copy3(anchor, pos);
-        axis[0] = 0; axis[1] = 0; axis[2] = 1;
+  for (int b = 0; b < m.nb; b++) {
+    const int p = m.b_parent[b];
+    PFOR(e, 12) {
+      if (e < 9) {
+        int r = e / 3, k = e - 3 * r;
+        real val;
+        if (p < 0) val = Rl[9 * b + e];
+        else {
+          const real* Rp = WR(bmat) + 9 * p + 3 * r;
+          const real* Rc = Rl + 9 * b + k;
+          val = Rp[0] * Rc[0] + Rp[1] * Rc[3] + Rp[2] * Rc[6];
+        }
+        WR(bmat)[9 * b + e] = val;
       } else {
-        real v[3], R[9];
-        if (p < 0) {
-          copy3(pos, m.b_pos[b]);
-          quat[0] = m.b_quat[b][0]; quat[1] = m.b_quat[b][1]; quat[2] = m.b_quat[b][2]; quat[3] = m.b_quat[b][3];
-        } else {
-          mulmat3(v, WR(bmat) + 9 * p, m.b_pos[b]);
-          const real* pp = WR(bpos) + 3 * p;
-          pos[0] = pp[0] + v[0]; pos[1] = pp[1] + v[1]; pos[2] = pp[2] + v[2];
-          quat_mul(quat, WR(bquat) + 4 * p, m.b_quat[b]);
+        int r = e - 9;
+        real val;
+        if (p < 0) val = tl[3 * b + r];
+        else {
+          const real* Rp = WR(bmat) + 9 * p + 3 * r;
+          const real* tc = tl + 3 * b;
+          val = WR(bpos)[3 * p + r] + Rp[0] * tc[0] + Rp[1] * tc[1] + Rp[2] * tc[2];
         }
-        const real* jp = m.b_jpos[b];
-        const bool jp0 = jp[0] == 0 && jp[1] == 0 && jp[2] == 0;  // every shipped joint sits at its body origin
-        if (m.b_jtype[b] == RCSB_JNT_SLIDE) {
-          quat_normalize(quat);
-          quat_to_mat(R, quat);
-          mulmat3(axis, R, m.b_jaxis[b]);
-          mulmat3(v, R, jp);
-          anchor[0] = pos[0] + v[0]; anchor[1] = pos[1] + v[1]; anchor[2] = pos[2] + v[2];
-          real qq = q[m.b_qadr[b]] - m.qpos0[m.b_qadr[b]];
-          pos[0] += axis[0] * qq; pos[1] += axis[1] * qq; pos[2] += axis[2] * qq;
-        } else {
-          if (jp0) copy3(anchor, pos);
-          else {
-            quat_to_mat(R, quat);
-            mulmat3(v, R, jp);
-            anchor[0] = pos[0] + v[0]; anchor[1] = pos[1] + v[1]; anchor[2] = pos[2] + v[2];
-          }
-          real s = sc[2 * b], ql[4] = {sc[2 * b + 1], m.b_jaxis[b][0] * s, m.b_jaxis[b][1] * s, m.b_jaxis[b][2] * s}, qn[4];
-          quat_mul(qn, quat, ql);
-          quat[0] = qn[0]; quat[1] = qn[1]; quat[2] = qn[2]; quat[3] = qn[3];
-          quat_normalize(quat);
-          quat_to_mat(R, quat);
-          mulmat3(axis, R, m.b_jaxis[b]);  // a rotation about the joint axis leaves the axis in place
-          if (!jp0) {
-            mulmat3(v, R, jp);
-            pos[0] = anchor[0] - v[0]; pos[1] = anchor[1] - v[1]; pos[2] = anchor[2] - v[2];
-          }
-        }
-        copy3(WR(bpos) + 3 * b, pos);
-        real* bq = WR(bquat) + 4 * b;
-        bq[0] = quat[0]; bq[1] = quat[1]; bq[2] = quat[2]; bq[3] = quat[3];
-        real* bm = WR(bmat) + 9 * b;
-        for (int i = 0; i < 9; i++) bm[i] = R[i];
-        continue;
+        WR(bpos)[3 * b + r] = val;
       }
-      quat_normalize(quat);
-      copy3(WR(bpos) + 3 * b, pos);
-      real* bq = WR(bquat) + 4 * b;
-      bq[0] = quat[0]; bq[1] = quat[1]; bq[2] = quat[2]; bq[3] = quat[3];
-      quat_to_mat(WR(bmat) + 9 * b, quat);
+    }
+    RCSB_SYNC();
+  }
+  PFOR(b, m.nb) {
+    real* anchor = WR(janchor) + 3 * b;
+    real* axis = WR(jaxis) + 3 * b;
+    const real* R = WR(bmat) + 9 * b;
+    const real* pos = WR(bpos) + 3 * b;
+    if (m.b_jtype[b] == RCSB_JNT_FREE) {
+      copy3(anchor, pos);
+      axis[0] = 0; axis[1] = 0; axis[2] = 1;
+    } else {
+      real v[3];
+      mulmat3(axis, R, m.b_jaxis[b]);  // a rotation about the joint axis leaves axis and anchor in place
+      mulmat3(v, R, m.b_jpos[b]);
+      anchor[0] = pos[0] + v[0]; anchor[1] = pos[1] + v[1]; anchor[2] = pos[2] + v[2];
     }
   }
   RCSB_SYNC();
@@ -815,7 +846,7 @@ RCSB_DEV void st_collision(const Ctx& c) {
       // Separating-direction cache (4 direct-mapped slots, lives for the launch): a direction that separated the pair
       // on an earlier substep is re-checked with one support pair; disjoint pairs stay disjoint for many substeps
       // (link5 / link7 overlap in their boxes in every pose), so the full query runs about once per env.step().
-      real* sc = WR(sepcache) + 4 * (p & 3);
+      real* sc = WR(sepcache) + 4 * (p & 1);
       int skip = 0;
       if (sc[0] == (real)p) {
         Sup s;

@@ -148,7 +148,7 @@ RCSB_DEV void load_env(const Ctx& c, const real* sr, const double* sd, const int
   PFOR(i, RCSB_D_TAIL) { c.clk[i] = sd[i]; }
   PFOR(i, RCSB_I_TAIL) { c.wi[m.oi_misc + MI_COUNT + i] = si[i]; }
   PFOR(i, MI_COUNT) { c.wi[m.oi_misc + i] = 0; }
-  PFOR(i, 4) { WR(sepcache)[4 * i] = -1; }
+  PFOR(i, 2) { WR(sepcache)[4 * i] = -1; }
   RCSB_SYNC();
 }
 RCSB_DEV void store_env(const Ctx& c, real* sr, double* sd, int* si) {

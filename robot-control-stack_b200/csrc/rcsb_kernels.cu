@@ -49,7 +49,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 #define RCSB_SMEM_HEADER (RCSB_MODEL_BYTES + 16)
 // warps per CTA are bounded by the per-warp shared-memory workspace (about 22 KB for the FR3 scenes),
 // so the register budget per thread can be generous
-#define RCSB_MAX_WARPS 12
+#define RCSB_MAX_WARPS 14
 
 extern __shared__ __align__(128) unsigned char rcsb_smem[];
 

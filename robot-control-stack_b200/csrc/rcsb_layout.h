@@ -77,11 +77,16 @@ static inline int rcsb_model_finalize_layout(RcsbModel* m) {
   m->o_site = m->o_rcs + RCSB_S_SITEPOS;
   // region K: position/velocity-stage scratch, dead once st_make_constraint has built the constraint rows
   const int k_begin = o;
-  RCSB_ALLOC(o_bpos, 3 * nb); RCSB_ALLOC(o_bquat, 4 * nb); RCSB_ALLOC(o_bmat, 9 * nb); RCSB_ALLOC(o_bcom, 3 * nb);
+  RCSB_ALLOC(o_bpos, 3 * nb); RCSB_ALLOC(o_bmat, 9 * nb); RCSB_ALLOC(o_bcom, 3 * nb);
   RCSB_ALLOC(o_bgc, 3 * nb); RCSB_ALLOC(o_janchor, 3 * nb); RCSB_ALLOC(o_jaxis, 3 * nb);
   RCSB_ALLOC(o_rootcom, 3 * m->nroot);
-  RCSB_ALLOC(o_cinert, 10 * nb); RCSB_ALLOC(o_crb, 10 * nb); RCSB_ALLOC(o_cdof, 6 * nv); RCSB_ALLOC(o_cdofdot, 6 * nv);
-  RCSB_ALLOC(o_cvel, 6 * nb); RCSB_ALLOC(o_cacc, 6 * nb); RCSB_ALLOC(o_cfrc, 6 * nb);
+  RCSB_ALLOC(o_cinert, 10 * nb);
+  // kinematics scratch (local rotations/translations, 12*nb) is dead before crb / cdof / cdof_dot are written
+  m->o_bquat = o;
+  RCSB_ALLOC(o_crb, 10 * nb); RCSB_ALLOC(o_cdof, 6 * nv); RCSB_ALLOC(o_cdofdot, 6 * nv);
+  if (o - m->o_bquat < 12 * nb) o = m->o_bquat + 12 * nb;
+  RCSB_ALLOC(o_cvel, 6 * nb); RCSB_ALLOC(o_cfrc, 6 * nb);
+  m->o_cacc = m->o_cfrc;  // unused (the spatial acceleration lives in registers)
   RCSB_ALLOC(o_gpos, 3 * m->ng);
   const int k_end = o;
   // region S: solver / integrator scratch, first written after st_make_constraint -> aliases region K
@@ -95,12 +100,13 @@ static inline int rcsb_model_finalize_layout(RcsbModel* m) {
   RCSB_ALLOC(o_M, nv * nv); RCSB_ALLOC(o_L, nv * nv + nv);
   RCSB_ALLOC(o_bias, nv); RCSB_ALLOC(o_passive, nv); RCSB_ALLOC(o_gravc, nv); RCSB_ALLOC(o_actfrc, nv);
   RCSB_ALLOC(o_smooth, nv); RCSB_ALLOC(o_qacc_smooth, nv); RCSB_ALLOC(o_qacc, nv); RCSB_ALLOC(o_qfc, nv);
-  RCSB_ALLOC(o_tmp, 6 * nv + 2 * nb + 8);
-  RCSB_ALLOC(o_alen, nu); RCSB_ALLOC(o_avel, nu); RCSB_ALLOC(o_aforce, nu);
+  RCSB_ALLOC(o_tmp, 6 * nv + 2);  // crb buffer (6*nv), solve scratch (nv), action staging (njoints)
+  RCSB_ALLOC(o_aforce, nu);
+  m->o_alen = m->o_avel = m->o_aforce;  // actuator length / velocity live in registers
   RCSB_ALLOC(o_con, RCSB_C_REALS * m->maxcon);
   RCSB_ALLOC(o_J, m->maxefc * nv);
   RCSB_ALLOC(o_efc, RCSB_E_NARR * m->maxefc);
-  RCSB_ALLOC(o_sepcache, 16);  // 4 x (pair tag, separating direction), valid for one launch
+  RCSB_ALLOC(o_sepcache, 8);  // 2 x (pair tag, separating direction), valid for one launch
   o = (o + 1) & ~1;  // keep the double clock block 16-byte aligned when real is 8 bytes
   m->ws_reals = o;
   m->ws_doubles = RCSB_D_TAIL;

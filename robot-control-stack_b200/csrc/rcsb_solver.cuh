@@ -877,7 +877,7 @@ RCSB_DEV void reset_data(const Ctx& c, double* time) {  // mj_resetData
   PFOR(i, m.nq) { WR(q)[i] = m.qpos0[i]; }
   PFOR(i, m.nv) { WR(v)[i] = 0; WR(warm)[i] = 0; }
   PFOR(i, m.nu) { WR(ctrl)[i] = 0; }
-  *time = 0;
+  if (c.lane == 0) *time = 0;
   RCSB_SYNC();
 }
 // RCSB_STAGE: CTA barrier (lockstep launches only) + the stage; the profiling build (-DRCSB_STAGE_TIMING) also
@@ -917,6 +917,9 @@ RCSB_DEV void physics_step(const Ctx& c, double* time) {
   RCSB_STAGE(7, st_constraint_solve(c));
   RCSB_STAGE(8, st_integrate(c));
   RCSB_BLOCK_SYNC();
-  *time += (double)m.timestep;
-  if (c.lane == 0) RI(RCSB_I_TOTAL_STEPS) += 1;
+  if (c.lane == 0) {  // the clock lives in shared memory: one writer
+    *time += (double)m.timestep;
+    RI(RCSB_I_TOTAL_STEPS) += 1;
+  }
+  RCSB_SYNC();
 }

@@ -23,7 +23,7 @@ enum {
   RCSB_MAXEQ = 2,     // joint equalities
   RCSB_MAXROOT = 4,   // kinematic trees
   RCSB_MAXJ = 8,      // robot arm joints
-  RCSB_MAXCAND = 64,  // narrowphase candidates per step
+  RCSB_MAXCAND = 48,  // broad-phase survivors per step (28 at the FR3 home pose)
 };
 
 enum { RCSB_JNT_FREE = 0, RCSB_JNT_SLIDE = 2, RCSB_JNT_HINGE = 3 };

@@ -14,7 +14,7 @@ import numpy as np
 from . import mjcf
 from .mjcf import JNT_FREE, quat_mul, quat_to_mat, mat_to_quat
 
-MAXCON_DEFAULT = 8
+MAXCON_DEFAULT = 6  # per-env contact capacity (overflow is counted in the warn flag); Sim(maxcon=...) overrides
 ROLE_ARM, ROLE_GRIPPER, ROLE_FINGER, ROLE_IGNORED = 1, 2, 4, 8
 
 
