@@ -10,20 +10,44 @@
 #pragma once
 #include "rcsb_warp.cuh"
 
+#ifdef RCSB_HOST_EMU
 struct Ctx {
-  const RcsbModel* md;  // model constants (shared memory on device)
-  real* w;              // this warp's real workspace (shared memory)
-  int* wi;              // this warp's int workspace (shared memory)
+  const RcsbModel* md;  // model constants
+  real* w;              // real workspace
+  int* wi;              // int workspace
+  const real* verts;    // convex hull vertex pool
+  double* clk;          // simulation time + callback clocks (always double)
+  int lane;
+  int lockstep;
+};
+#define CMODEL(c) (*(c).md)
+#define CW(c) ((c).w)
+#define CWI(c) ((c).wi)
+#define CCLK(c) ((c).clk)
+#else
+// Device: the model sits at the start of the CTA's dynamic shared memory and every warp owns a workspace window in it.
+// Ctx carries 32-bit byte offsets into that window, and every access is formed from the rcsb_smem symbol, so the
+// compiler addresses shared memory directly (LDS/STS with 32-bit address arithmetic) in every function, inlined or
+// not, instead of falling back to generic 64-bit loads.
+extern __shared__ __align__(128) unsigned char rcsb_smem[];
+struct Ctx {
   const real* verts;    // convex hull vertex pool (global memory, read-only)
-  double* clk;          // this warp's simulation time + callback clocks (always double)
+  uint32_t wb;          // this warp's real workspace (byte offset in shared memory)
+  uint32_t clkb;        // this warp's simulation time + callback clocks (always double)
+  uint32_t wib;         // this warp's int workspace
   int lane;
   int lockstep;         // fixed-substep launch: CTA barriers between stages keep the warps on the same code
 };
-#define WR(name) (c.w + m.o_##name)
-#define WI(name) (c.wi + m.oi_##name)
+#define CMODEL(c) (*(const RcsbModel*)rcsb_smem)
+#define CW(c) ((real*)(rcsb_smem + (c).wb))
+#define CWI(c) ((int*)(rcsb_smem + (c).wib))
+#define CCLK(c) ((double*)(rcsb_smem + (c).clkb))
+#endif
+#define WR(name) (CW(c) + m.o_##name)
+#define WI(name) (CWI(c) + m.oi_##name)
 
 // misc int slots in the workspace
-enum { MI_NCON = 0, MI_NEFC, MI_NE, MI_NF, MI_NL, MI_HAVE_L, MI_SOLVER_ITER, MI_WARN, MI_COUNT };
+enum { MI_NCON = 0, MI_NEFC, MI_NE, MI_NF, MI_NL, MI_HAVE_L, MI_SOLVER_ITER, MI_WARN, MI_OVERFLOW, MI_PAD, MI_COUNT };
 
 // ------------------------------------------------------------------ dense Cholesky / triangular solves
 // A (n x n, row-major, shared memory) -> strictly-lower part holds L, dinv[j] = 1 / L[j][j]; A's diagonal is left
@@ -88,6 +112,8 @@ RCSB_DEV void chol_factor_n(const Ctx& c, real* A, real* dinv) {
   }
 }
 RCSB_DEV_NOINLINE void chol_factor(const Ctx& c, real* A, real* dinv, int n) {
+  __builtin_assume(__isShared(A));
+  __builtin_assume(__isShared(dinv));
   RCSB_SYNC();
   switch (n) {  // dof counts of the supported scenes: xArm7 (7), FR3 + fingers (9), FR3 + fingers + free cube (15)
     case 7: chol_factor_n<7>(c, A, dinv); break;
@@ -114,6 +140,9 @@ RCSB_DEV_NOINLINE void chol_factor(const Ctx& c, real* A, real* dinv, int n) {
 // x <- (L L^T)^{-1} x ; lane i carries x[i]; y is unused scratch (kept for the common signature)
 RCSB_DEV_NOINLINE void chol_solve(const Ctx& c, const real* L, const real* dinv, int n, real* x, real* y) {
   const int lane = c.lane;
+  __builtin_assume(__isShared(L));
+  __builtin_assume(__isShared(dinv));
+  __builtin_assume(__isShared(x));
   RCSB_SYNC();
   real xi = lane < n ? x[lane] : (real)0;
   real di = lane < n ? dinv[lane] : (real)0;
@@ -138,7 +167,7 @@ RCSB_DEV_NOINLINE void chol_solve(const Ctx& c, const real* L, const real* dinv,
 // entries, each a 3-term dot product), so the serial depth per body is a handful of FMAs instead of a lane-serial
 // quaternion chain.
 RCSB_DEV void st_kinematics(const Ctx& c) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   real* q = WR(q);
   real* Rl = WR(bquat);            // scratch: local rotation [nb][9] then local translation [nb][3] (o_bquat holds 12*nb)
   real* tl = Rl + 9 * m.nb;
@@ -205,27 +234,11 @@ RCSB_DEV void st_kinematics(const Ctx& c) {
     }
     RCSB_SYNC();
   }
-  PFOR(b, m.nb) {
-    real* anchor = WR(janchor) + 3 * b;
-    real* axis = WR(jaxis) + 3 * b;
-    const real* R = WR(bmat) + 9 * b;
-    const real* pos = WR(bpos) + 3 * b;
-    if (m.b_jtype[b] == RCSB_JNT_FREE) {
-      copy3(anchor, pos);
-      axis[0] = 0; axis[1] = 0; axis[2] = 1;
-    } else {
-      real v[3];
-      mulmat3(axis, R, m.b_jaxis[b]);  // a rotation about the joint axis leaves axis and anchor in place
-      mulmat3(v, R, m.b_jpos[b]);
-      anchor[0] = pos[0] + v[0]; anchor[1] = pos[1] + v[1]; anchor[2] = pos[2] + v[2];
-    }
-  }
-  RCSB_SYNC();
 }
 
 // world pose of collidable geom g
 RCSB_DEV void geom_frame(const Ctx& c, int g, real* pos, real* mat) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   int b = m.g_body[g];
   real Rl[9];
   quat_to_mat(Rl, m.g_quat[g]);
@@ -244,25 +257,22 @@ RCSB_DEV void geom_frame(const Ctx& c, int g, real* pos, real* mat) {
 }
 
 // ------------------------------------------------------------------ COM frames, inertias, motion axes, geom centres
+// world position of the body's centre of mass
+RCSB_DEV void body_com(const Ctx& c, int b, real* o) {
+  const RcsbModel& m = CMODEL(c);
+  real v[3];
+  const real* p = WR(bpos) + 3 * b;
+  mulmat3(v, WR(bmat) + 9 * b, m.b_ipos[b]);
+  o[0] = p[0] + v[0]; o[1] = p[1] + v[1]; o[2] = p[2] + v[2];
+}
 RCSB_DEV void st_com(const Ctx& c) {
-  const RcsbModel& m = *c.md;
-  PFOR(b, m.nb) {
-    real v[3];
-    const real* R = WR(bmat) + 9 * b;
-    const real* p = WR(bpos) + 3 * b;
-    mulmat3(v, R, m.b_ipos[b]);
-    real* o = WR(bcom) + 3 * b;
-    o[0] = p[0] + v[0]; o[1] = p[1] + v[1]; o[2] = p[2] + v[2];
-    mulmat3(v, R, m.b_gcpos[b]);
-    o = WR(bgc) + 3 * b;
-    o[0] = p[0] + v[0]; o[1] = p[1] + v[1]; o[2] = p[2] + v[2];
-  }
-  RCSB_SYNC();
+  const RcsbModel& m = CMODEL(c);
   PFOR(r, m.nroot) {
     real s[3] = {0, 0, 0};
     for (int b = 0; b < m.nb; b++)
       if (m.b_root[b] == r) {
-        const real* o = WR(bcom) + 3 * b;
+        real o[3];
+        body_com(c, b, o);
         s[0] += m.b_mass[b] * o[0]; s[1] += m.b_mass[b] * o[1]; s[2] += m.b_mass[b] * o[2];
       }
     real* rc = WR(rootcom) + 3 * r;
@@ -273,7 +283,8 @@ RCSB_DEV void st_com(const Ctx& c) {
     const real* R = WR(bmat) + 9 * b;
     const real* I = m.b_inertia[b];
     const real* rc = WR(rootcom) + 3 * m.b_root[b];
-    const real* bc = WR(bcom) + 3 * b;
+    real bc[3];
+    body_com(c, b, bc);
     real mass = m.b_mass[b], d[3] = {bc[0] - rc[0], bc[1] - rc[1], bc[2] - rc[2]};
     real A[9];  // R * I
     for (int r = 0; r < 3; r++) {
@@ -296,38 +307,35 @@ RCSB_DEV void st_com(const Ctx& c) {
   PFOR(j, m.nv) {  // motion axis of dof j about the tree COM
     int b = m.d_body[j];
     const real* rc = WR(rootcom) + 3 * m.b_root[b];
-    const real* an = WR(janchor) + 3 * b;
-    real off[3] = {rc[0] - an[0], rc[1] - an[1], rc[2] - an[2]};
+    const real* R = WR(bmat) + 9 * b;
+    const real* pos = WR(bpos) + 3 * b;
     real* cd = WR(cdof) + 6 * j;
     int jt = m.b_jtype[b];
+    // a rotation about the joint axis leaves axis and anchor in place, so both come from the body frame
+    real axis[3], an[3];
+    if (jt == RCSB_JNT_FREE) copy3(an, pos);
+    else {
+      mulmat3(axis, R, m.b_jaxis[b]);
+      mulmat3(an, R, m.b_jpos[b]);
+      an[0] += pos[0]; an[1] += pos[1]; an[2] += pos[2];
+    }
+    real off[3] = {rc[0] - an[0], rc[1] - an[1], rc[2] - an[2]};
     if (jt == RCSB_JNT_FREE) {
       int a = j - m.b_dadr[b];
       if (a < 3) {
         cd[0] = cd[1] = cd[2] = 0;
         cd[3] = a == 0; cd[4] = a == 1; cd[5] = a == 2;
       } else {
-        const real* R = WR(bmat) + 9 * b;
         real ax[3] = {R[a - 3], R[3 + a - 3], R[6 + a - 3]};
         copy3(cd, ax);
         cross3(cd + 3, ax, off);
       }
     } else if (jt == RCSB_JNT_SLIDE) {
       cd[0] = cd[1] = cd[2] = 0;
-      copy3(cd + 3, WR(jaxis) + 3 * b);
+      copy3(cd + 3, axis);
     } else {
-      copy3(cd, WR(jaxis) + 3 * b);
-      cross3(cd + 3, WR(jaxis) + 3 * b, off);
-    }
-  }
-  PFOR(g, m.ng) {  // bounding-volume centres for the broad phase
-    int b = m.g_body[g];
-    real* o = WR(gpos) + 3 * g;
-    if (b < 0) copy3(o, m.g_bpos[g]);
-    else {
-      real v[3];
-      mulmat3(v, WR(bmat) + 9 * b, m.g_bpos[g]);
-      const real* p = WR(bpos) + 3 * b;
-      o[0] = p[0] + v[0]; o[1] = p[1] + v[1]; o[2] = p[2] + v[2];
+      copy3(cd, axis);
+      cross3(cd + 3, axis, off);
     }
   }
   if (c.lane == 0) {  // attachment site pose (SimRobot::get_cartesian_position reads it after the step)
@@ -353,7 +361,7 @@ RCSB_DEV void st_com(const Ctx& c) {
 
 // ------------------------------------------------------------------ composite inertia, mass matrix, factorisation
 RCSB_DEV void st_crb(const Ctx& c) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   int nv = m.nv;
   PFOR(e, m.nb * 10) {
     int b = e / 10, k = e - 10 * b;
@@ -364,7 +372,7 @@ RCSB_DEV void st_crb(const Ctx& c) {
     WR(crb)[e] = s;
   }
   RCSB_SYNC();
-  real* buf = WR(tmp);
+  real* buf = WR(crbbuf);
   PFOR(i, nv) { mul_inert_vec(buf + 6 * i, WR(crb) + 10 * m.d_body[i], WR(cdof) + 6 * i); }
   RCSB_SYNC();
   PFOR(e, nv * nv) {
@@ -379,18 +387,16 @@ RCSB_DEV void st_crb(const Ctx& c) {
       }
       WR(M)[i * nv + j] = val;
       WR(M)[j * nv + i] = val;
-      WR(L)[i * nv + j] = val;
-      WR(L)[j * nv + i] = val;
     }
   }
-  // the factorisation of M is deferred (ensure_chol_M): the all-equality solver path never needs it
-  if (c.lane == 0) c.wi[m.oi_misc + MI_HAVE_L] = 0;
+  // the factorisation of M is deferred (ensure_chol_M copies M into the solver scratch): the all-equality path never needs it
+  if (c.lane == 0) CWI(c)[m.oi_misc + MI_HAVE_L] = 0;
   RCSB_SYNC();
 }
 
 // ------------------------------------------------------------------ velocity stage: bias, passive, gravity compensation
 RCSB_DEV void st_velocity(const Ctx& c) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   int nv = m.nv;
   const real* v = WR(v);
   PFOR(j, nv) {
@@ -432,27 +438,36 @@ RCSB_DEV void st_velocity(const Ctx& c) {
     mul_inert_vec(Iv, WR(cinert) + 10 * b, WR(cvel) + 6 * b);
     cross_force(x, WR(cvel) + 6 * b, Iv);
     for (int k = 0; k < 6; k++) WR(cfrc)[6 * b + k] = Ia[k] + x[k];
+    // cvel[b] is dead from here on: its slot takes the body's gravity-compensation wrench [torque; force] about the
+    // tree COM (force -gcmass*g applied at the compensated mass centre)
+    real* gw = WR(cvel) + 6 * b;
+    real gm = m.b_gcmass[b];
+    if (gm != 0) {
+      const real* rc = WR(rootcom) + 3 * m.b_root[b];
+      const real* p = WR(bpos) + 3 * b;
+      real o[3], fg[3] = {-gm * m.gravity[0], -gm * m.gravity[1], -gm * m.gravity[2]};
+      mulmat3(o, WR(bmat) + 9 * b, m.b_gcpos[b]);
+      o[0] += p[0] - rc[0]; o[1] += p[1] - rc[1]; o[2] += p[2] - rc[2];
+      cross3(gw, o, fg);
+      copy3(gw + 3, fg);
+    } else {
+      for (int k = 0; k < 6; k++) gw[k] = 0;
+    }
   }
   RCSB_SYNC();
   PFOR(j, nv) {
     int bj = m.d_body[j];
     uint32_t mask = m.b_descmask[bj];
     const real* cd = WR(cdof) + 6 * j;
-    const real* rc = WR(rootcom) + 3 * m.b_root[bj];
-    real f[6] = {0, 0, 0, 0, 0, 0}, gc = 0;
+    real f[6] = {0, 0, 0, 0, 0, 0}, g[6] = {0, 0, 0, 0, 0, 0};
     for (int b = bj; b < m.nb; b++)
       if ((mask >> b) & 1u) {
         const real* cf = WR(cfrc) + 6 * b;
-        for (int k = 0; k < 6; k++) f[k] += cf[k];
-        real gm = m.b_gcmass[b];
-        if (gm != 0) {
-          const real* p = WR(bgc) + 3 * b;
-          real off[3] = {p[0] - rc[0], p[1] - rc[1], p[2] - rc[2]}, t[3];
-          cross3(t, cd, off);
-          gc -= gm * ((cd[3] + t[0]) * m.gravity[0] + (cd[4] + t[1]) * m.gravity[1] + (cd[5] + t[2]) * m.gravity[2]);
-        }
+        const real* gw = WR(cvel) + 6 * b;
+        for (int k = 0; k < 6; k++) { f[k] += cf[k]; g[k] += gw[k]; }
       }
     WR(bias)[j] = cd[0] * f[0] + cd[1] * f[1] + cd[2] * f[2] + cd[3] * f[3] + cd[4] * f[4] + cd[5] * f[5];
+    real gc = cd[0] * g[0] + cd[1] * g[1] + cd[2] * g[2] + cd[3] * g[3] + cd[4] * g[4] + cd[5] * g[5];
     WR(gravc)[j] = gc;
     WR(passive)[j] = -m.d_damping[j] * v[j] + (m.d_actgravcomp[j] ? (real)0 : gc);
   }
@@ -462,7 +477,7 @@ RCSB_DEV void st_velocity(const Ctx& c) {
 // ------------------------------------------------------------------ collision
 // support mapping of geom g (world pose gp, gR) along world direction dir; warp-cooperative for meshes
 RCSB_DEV void support(const Ctx& c, int g, const real* gp, const real* gR, const real* dir, real* out) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   real dl[3], v[3] = {0, 0, 0};
   mulmatT3(dl, gR, dir);
   int type = m.g_type[g];
@@ -654,9 +669,9 @@ RCSB_DEV_NOINLINE int mpr_penetration(const Ctx& c, const PairFrames& pf, real* 
 // append one contact (all lanes call with identical arguments; lane 0 writes)
 RCSB_DEV void add_contact(const Ctx& c, int& ncon, int g1, int g2, real dist, const real* pos, const real* normal,
                           real margin, real gap) {
-  const RcsbModel& m = *c.md;
-  if (ncon >= m.maxcon) {
-    if (c.lane == 0) WI(misc)[MI_WARN] += 1;
+  const RcsbModel& m = CMODEL(c);
+  if (ncon >= m.maxcon) {  // reduced layout: the full-capacity launch redoes this step; full layout: drop and count
+    if (c.lane == 0) WI(misc)[m.cap_reduced ? MI_OVERFLOW : MI_WARN] += 1;
     return;
   }
   if (c.lane == 0) {
@@ -735,11 +750,24 @@ RCSB_DEV int obb_separated(const real* A, const real* ca, const real* ha, const 
 }
 
 RCSB_DEV void st_collision(const Ctx& c) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   // ---- broad phase: bounding spheres about the local AABB centres (plane: signed distance), one pair per lane,
   //      survivors compacted in pair order
-  int* candA = WI(cand);
-  int* candB = WI(cand) + RCSB_MAXCAND;
+  PFOR(g, m.ng) {  // bounding-volume centres for the broad phase
+    int b = m.g_body[g];
+    real* o = WR(gpos) + 3 * g;
+    if (b < 0) copy3(o, m.g_bpos[g]);
+    else {
+      real v[3];
+      mulmat3(v, WR(bmat) + 9 * b, m.g_bpos[g]);
+      const real* p = WR(bpos) + 3 * b;
+      o[0] = p[0] + v[0]; o[1] = p[1] + v[1]; o[2] = p[2] + v[2];
+    }
+  }
+  if (c.lane == 0) WI(misc)[MI_OVERFLOW] = 0;
+  RCSB_SYNC();
+  int* candA = (int*)WR(cand);  // candidate lists live in the stage-local union next to the geom centres
+  int* candB = candA + RCSB_MAXCAND;
   int ncandA = 0;
   for (int base = 0; base < m.npair; base += RCSB_NLANES) {
     int p = base + c.lane, hit = 0;

@@ -32,6 +32,10 @@ struct RcsbLaunch {
   int N, env_offset;
   unsigned ops;
   int k, max_convergence_steps;
+  int lockstep;  // fixed-substep launches: 0 no CTA barriers, 1 one per stage, 2 one per physics step
+  int phase;     // 0: every environment, reduced or full layout; 1: full layout, only the environments in overflow_list
+  int* overflow_list;   // [N] environments the reduced layout could not finish (phase 0 appends, phase 1 consumes)
+  int* overflow_count;
   const real* act_joints;   // [N][njoints]
   const real* act_gripper;  // [N]
   const unsigned char* mask;  // optional [N]: 0 = leave this env untouched
@@ -126,7 +130,7 @@ RCSB_DEV void pose_xyzrpy(const real* a, real* out6) {  // Eigen eulerAngles(2,1
 }
 // SimRobot::get_cartesian_position: base^-1 * Pose(site_xmat, site_xpos) * tcp_offset
 RCSB_DEV void robot_cartesian_position(const Ctx& c, real* pose7) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   const real* sp = WR(rcs) + RCSB_S_SITEPOS;
   real site[7], base[7], binv[7], t[7];
   Quat qs = q_norm(q_from_mat(sp + 3));
@@ -143,16 +147,16 @@ RCSB_DEV void robot_cartesian_position(const Ctx& c, real* pose7) {
 
 // ------------------------------------------------------------------ state row <-> workspace
 RCSB_DEV void load_env(const Ctx& c, const real* sr, const double* sd, const int* si) {
-  const RcsbModel& m = *c.md;
-  PFOR(i, m.nsr) { c.w[i] = sr[i]; }
-  PFOR(i, RCSB_D_TAIL) { c.clk[i] = sd[i]; }
-  PFOR(i, RCSB_I_TAIL) { c.wi[m.oi_misc + MI_COUNT + i] = si[i]; }
-  PFOR(i, MI_COUNT) { c.wi[m.oi_misc + i] = 0; }
+  const RcsbModel& m = CMODEL(c);
+  PFOR(i, m.nsr) { CW(c)[i] = sr[i]; }
+  PFOR(i, RCSB_D_TAIL) { CCLK(c)[i] = sd[i]; }
+  PFOR(i, RCSB_I_TAIL) { CWI(c)[m.oi_misc + MI_COUNT + i] = si[i]; }
+  PFOR(i, MI_COUNT) { CWI(c)[m.oi_misc + i] = 0; }
   PFOR(i, 2) { WR(sepcache)[4 * i] = -1; }
   RCSB_SYNC();
 }
 RCSB_DEV void store_env(const Ctx& c, real* sr, double* sd, int* si) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   RCSB_SYNC();
   if (c.lane == 0) {
     RI(RCSB_I_NCON) = WI(misc)[MI_NCON];
@@ -161,14 +165,14 @@ RCSB_DEV void store_env(const Ctx& c, real* sr, double* sd, int* si) {
     RI(RCSB_I_WARN) += WI(misc)[MI_WARN];
   }
   RCSB_SYNC();
-  PFOR(i, m.nsr) { sr[i] = c.w[i]; }
-  PFOR(i, RCSB_D_TAIL) { sd[i] = c.clk[i]; }
-  PFOR(i, RCSB_I_TAIL) { si[i] = c.wi[m.oi_misc + MI_COUNT + i]; }
+  PFOR(i, m.nsr) { sr[i] = CW(c)[i]; }
+  PFOR(i, RCSB_D_TAIL) { sd[i] = CCLK(c)[i]; }
+  PFOR(i, RCSB_I_TAIL) { si[i] = CWI(c)[m.oi_misc + MI_COUNT + i]; }
 }
 
 // ------------------------------------------------------------------ device-layer ops
 RCSB_DEV void op_set_joint_position(const Ctx& c, const real* qd) {  // SimRobot.cpp:123-131
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   PFOR(i, m.rb_njoints) {
     RS(RCSB_S_TARGET + i) = qd[i];
     RS(RCSB_S_PREV + i) = WR(q)[m.rb_qadr[i]];
@@ -178,7 +182,7 @@ RCSB_DEV void op_set_joint_position(const Ctx& c, const real* qd) {  // SimRobot
   RCSB_SYNC();
 }
 RCSB_DEV void op_set_gripper(const Ctx& c, real width) {  // SimGripper.cpp:79-92 (argument validated on the host)
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   if (c.lane == 0) {
     RS(RCSB_S_GLCW) = width;
     WR(ctrl)[m.gr_act] = width * (m.gr_max_act - m.gr_min_act) + m.gr_min_act;
@@ -187,8 +191,8 @@ RCSB_DEV void op_set_gripper(const Ctx& c, real width) {  // SimGripper.cpp:79-9
 }
 
 // the whole per-launch program for the environment loaded in the workspace
-RCSB_DEV void run_env_program(const Ctx& c, const RcsbLaunch& L, int env) {
-  const RcsbModel& m = *c.md;
+RCSB_DEV void run_env_pre_ops(const Ctx& c, const RcsbLaunch& L, int env) {
+  const RcsbModel& m = CMODEL(c);
   const unsigned ops = L.ops;
   if ((ops & RCSB_OP_GRIPPER_RESET) && m.gr_enabled) {  // SimGripper.cpp:158-163
     if (c.lane == 0) {
@@ -203,8 +207,8 @@ RCSB_DEV void run_env_program(const Ctx& c, const RcsbLaunch& L, int env) {
     RCSB_SYNC();
   }
   if (ops & RCSB_OP_SIM_RESET) {  // sim.cpp:117-138
-    reset_data(c, &c.clk[RCSB_D_TIME]);
-    PFOR(i, RCSB_NCB) { c.clk[RCSB_D_CBLAST + i] = 0; }
+    reset_data(c, &CCLK(c)[RCSB_D_TIME]);
+    PFOR(i, RCSB_NCB) { CCLK(c)[RCSB_D_CBLAST + i] = 0; }
     RCSB_SYNC();
   }
   if (ops & RCSB_OP_ROBOT_RESET) {  // SimRobot.cpp:193-205
@@ -254,25 +258,56 @@ RCSB_DEV void run_env_program(const Ctx& c, const RcsbLaunch& L, int env) {
   }
   if (ops & RCSB_OP_SET_JOINTS) op_set_joint_position(c, L.act_joints + (size_t)env * m.rb_njoints);
   if ((ops & RCSB_OP_SET_GRIPPER) && m.gr_enabled) op_set_gripper(c, L.act_gripper[env]);
+}
+// CTA barriers a lockstep warp owes for `nsteps` physics steps it does not run
+RCSB_DEV void skip_step_barriers(const Ctx& c, int nsteps) {
+#ifndef RCSB_HOST_EMU
+  int n = c.lockstep == 1 ? nsteps * RCSB_STAGE_BARRIERS : (c.lockstep == 2 ? nsteps : 0);
+  for (int i = 0; i < n; i++) __syncthreads();
+#endif
+}
+RCSB_DEV void run_env_program(const Ctx& c, const RcsbLaunch& L, int env) {
+  const RcsbModel& m = CMODEL(c);
+  const unsigned ops = L.ops;
+  const int resuming = L.phase == 1;
+  int overflow = 0;
+  if (!resuming) run_env_pre_ops(c, L, env);
   if (ops & RCSB_OP_STEP_K) {  // sim.cpp:108-115
-    for (int i = 0; i < L.k; i++) {
-      physics_step(c, &c.clk[RCSB_D_TIME]);
+    const int k = resuming ? RI(RCSB_I_RESUME) : L.k;
+    for (int i = 0; i < k; i++) {
+      if (physics_step(c, &CCLK(c)[RCSB_D_TIME])) {
+        overflow = k - i;
+        skip_step_barriers(c, k - i - 1);
+        break;
+      }
     }
   }
   if (ops & RCSB_OP_STEP_CONV) {  // sim.cpp:84-106
     int steps = 0, converged = 0;
     RCSB_SYNC();
-    PFOR(i, RCSB_NCB) { RI(RCSB_I_CBRET + i) = 0; }
+    if (resuming) steps = RI(RCSB_I_CONV_STEPS);
+    else PFOR(i, RCSB_NCB) { RI(RCSB_I_CBRET + i) = 0; }
     RCSB_SYNC();
     while (!converged && (L.max_convergence_steps == -1 || steps < L.max_convergence_steps)) {
-      physics_step(c, &c.clk[RCSB_D_TIME]);
+      if (physics_step(c, &CCLK(c)[RCSB_D_TIME])) { overflow = 1; break; }
       steps++;
-      converged = invoke_condition_callbacks(c, c.clk[RCSB_D_TIME]);
+      converged = invoke_condition_callbacks(c, CCLK(c)[RCSB_D_TIME]);
     }
     RCSB_SYNC();
     if (c.lane == 0) { RI(RCSB_I_CONVERGED) = converged; RI(RCSB_I_CONV_STEPS) = steps; }
     RCSB_SYNC();
   }
+  RCSB_SYNC();
+  if (c.lane == 0) {
+    RI(RCSB_I_RESUME) = overflow;
+#ifndef RCSB_HOST_EMU
+    if (overflow) L.overflow_list[atomicAdd(L.overflow_count, 1)] = env;
+#else
+    if (overflow) L.overflow_list[(*L.overflow_count)++] = env;
+#endif
+  }
+  RCSB_SYNC();
+  if (overflow) return;  // the full-capacity launch finishes the steps and packs the observation
   if ((ops & RCSB_OP_OBS) && c.lane == 0) {
     real pose[7];
     robot_cartesian_position(c, pose);

@@ -49,18 +49,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 #define RCSB_SMEM_HEADER (RCSB_MODEL_BYTES + 16)
 // warps per CTA are bounded by the per-warp shared-memory workspace (about 22 KB for the FR3 scenes),
 // so the register budget per thread can be generous
-#define RCSB_MAX_WARPS 14
-
-extern __shared__ __align__(128) unsigned char rcsb_smem[];
+#ifndef RCSB_MAX_WARPS
+#define RCSB_MAX_WARPS 28
+#endif
 
 __device__ __forceinline__ Ctx make_ctx(const RcsbModel* sm, const real* verts, size_t ws_bytes) {
   int warp = threadIdx.x >> 5;
-  unsigned char* base = rcsb_smem + RCSB_SMEM_HEADER + (size_t)warp * ws_bytes;
   Ctx c;
-  c.md = sm;
-  c.w = (real*)base;
-  c.clk = (double*)(base + (size_t)sm->ws_reals * sizeof(real));
-  c.wi = (int*)(base + (size_t)sm->ws_reals * sizeof(real) + (size_t)sm->ws_doubles * sizeof(double));
+  c.wb = (uint32_t)(RCSB_SMEM_HEADER + (size_t)warp * ws_bytes);
+  c.clkb = c.wb + (uint32_t)((size_t)sm->ws_reals * sizeof(real));
+  c.wib = c.clkb + (uint32_t)((size_t)sm->ws_doubles * sizeof(double));
   c.verts = verts;
   c.lane = threadIdx.x & 31;
   c.lockstep = 0;
@@ -86,13 +84,15 @@ __device__ __forceinline__ const RcsbModel* stage_model(const RcsbModel* gm) {
 __global__ void __launch_bounds__(RCSB_MAX_WARPS * 32, 1)
 rcsb_k_run(const RcsbModel* __restrict__ gm, const real* __restrict__ verts, real* __restrict__ sr, double* __restrict__ sd,
            int* __restrict__ si, RcsbLaunch L, int* __restrict__ counter, size_t ws_bytes) {
+  if (L.phase == 1 && *L.overflow_count == 0) return;  // the common case: nothing outgrew the reduced layout
   const RcsbModel* sm = stage_model(gm);
   Ctx c = make_ctx(sm, verts, ws_bytes);
-  if (L.ops & RCSB_OP_STEP_K) {
+  if ((L.ops & RCSB_OP_STEP_K) && L.phase == 0) {
     // Fixed-substep launch: static env -> warp mapping. Every warp of the CTA runs the same number of rounds and
     // hits exactly L.k * RCSB_STAGE_BARRIERS CTA barriers per round (inside run_env_program, or here when it has no environment), which
     // keeps the warps in the same stage of the step so that they share instruction-cache lines.
-    c.lockstep = 1;
+    c.lockstep = L.lockstep;
+    const int nbar = L.lockstep == 1 ? L.k * RCSB_STAGE_BARRIERS : (L.lockstep == 2 ? L.k : 0);
     const int W = blockDim.x >> 5, per_round = gridDim.x * W;
     const int rounds = (L.N + per_round - 1) / per_round;
     for (int r = 0; r < rounds; r++) {
@@ -104,8 +104,23 @@ rcsb_k_run(const RcsbModel* __restrict__ gm, const real* __restrict__ verts, rea
         store_env(c, sr + (size_t)env * sm->nsr, sd + (size_t)env * RCSB_D_TAIL, si + (size_t)env * RCSB_I_TAIL);
         __syncwarp();
       } else {
-        for (int i = 0; i < L.k * RCSB_STAGE_BARRIERS; i++) __syncthreads();
+        for (int i = 0; i < nbar; i++) __syncthreads();
       }
+    }
+    return;
+  }
+  if (L.phase == 1) {  // environments the reduced layout handed over: dynamic scheduling over the overflow list
+    const int n = *L.overflow_count;
+    for (;;) {
+      int i = 0;
+      if (c.lane == 0) i = atomicAdd(counter, 1);
+      i = __shfl_sync(0xffffffffu, i, 0);
+      if (i >= n) break;
+      int env = L.overflow_list[i];
+      load_env(c, sr + (size_t)env * sm->nsr, sd + (size_t)env * RCSB_D_TAIL, si + (size_t)env * RCSB_I_TAIL);
+      run_env_program(c, L, env);
+      store_env(c, sr + (size_t)env * sm->nsr, sd + (size_t)env * RCSB_D_TAIL, si + (size_t)env * RCSB_I_TAIL);
+      __syncwarp();
     }
     return;
   }
@@ -142,7 +157,10 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
   } while (0)
 
 struct rcsb_model {
-  RcsbModel h;
+  RcsbModel h;        // full-capacity layout
+  RcsbModel hr;       // reduced-capacity layout (has_reduced)
+  bool has_reduced = false;
+  RcsbModel* d_model_r = nullptr;
   std::vector<real> verts;
   bool finalized = false;
   int device = -1;
@@ -154,9 +172,12 @@ struct rcsb_batch {
   int n;
   real* sr; double* sd; int* si;
   cudaStream_t stream;
-  int* d_counter = nullptr;
-  int warps = 0, grid = 0;
+  int* d_counter = nullptr;   // [0] env cursor phase 0, [1] overflow cursor phase 1, [2] overflow count
+  int* d_overflow = nullptr;  // [n] overflow list
+  int warps = 0, grid = 0, lockstep = 1;
   size_t smem = 0, ws_bytes = 0;
+  int warps_full = 0, grid_full = 0;  // phase 1 (full layout) launch shape when a reduced layout exists
+  size_t smem_full = 0, ws_bytes_full = 0;
   // staging for the host-buffer path
   real *d_act_joints = nullptr, *d_act_gripper = nullptr, *d_obs = nullptr;
   int* d_info = nullptr;
@@ -177,6 +198,7 @@ rcsb_model* rcsb_model_new(void) {
 void rcsb_model_free(rcsb_model* m) {
   if (!m) return;
   if (m->d_model) cudaFree(m->d_model);
+  if (m->d_model_r) cudaFree(m->d_model_r);
   if (m->d_verts) cudaFree(m->d_verts);
   delete m;
 }
@@ -200,6 +222,13 @@ int rcsb_model_set_mesh_vertices(rcsb_model* m, const double* xyz, int nvert) {
 int rcsb_model_finalize(rcsb_model* m) {
   if (rcsb_model_finalize_layout(&m->h) != 0) return fail(RCSB_ERR_MODEL, "model dimensions out of range");
   if ((m->h.nsr * sizeof(real)) % 16 != 0) return fail(RCSB_ERR_MODEL, "state row is not 16-byte granular");
+  m->h.cap_reduced = 0;
+  m->has_reduced = rcsb_model_make_reduced(&m->h, &m->hr) != 0;
+  if (m->has_reduced) {
+    int need = m->h.neq;
+    for (int j = 0; j < m->h.nv; j++) need += m->h.d_frictionloss[j] > 0;
+    if (m->hr.maxefc < need + 2) return fail(RCSB_ERR_MODEL, "fast_maxefc must cover the equality and friction-loss rows plus 2");
+  }
   m->finalized = true;
   return RCSB_OK;
 }
@@ -217,6 +246,11 @@ int rcsb_model_upload(rcsb_model* m, int device) {
   memcpy(padded.data(), &m->h, sizeof(RcsbModel));
   CUDA_OK(cudaMalloc(&m->d_model, RCSB_MODEL_BYTES));
   CUDA_OK(cudaMemcpy(m->d_model, padded.data(), RCSB_MODEL_BYTES, cudaMemcpyHostToDevice));
+  if (m->has_reduced) {
+    memcpy(padded.data(), &m->hr, sizeof(RcsbModel));
+    CUDA_OK(cudaMalloc(&m->d_model_r, RCSB_MODEL_BYTES));
+    CUDA_OK(cudaMemcpy(m->d_model_r, padded.data(), RCSB_MODEL_BYTES, cudaMemcpyHostToDevice));
+  }
   if (m->verts.empty()) m->verts.resize(3);
   CUDA_OK(cudaMalloc(&m->d_verts, m->verts.size() * sizeof(real)));
   CUDA_OK(cudaMemcpy(m->d_verts, m->verts.data(), m->verts.size() * sizeof(real), cudaMemcpyHostToDevice));
@@ -250,23 +284,31 @@ rcsb_batch* rcsb_batch_new(rcsb_model* m, int n_envs, void* sr, void* sd, void* 
   cudaSetDevice(m->device);
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, m->device);
-  b->ws_bytes = rcsb_ws_bytes(&m->h);
   size_t avail = prop.sharedMemPerBlockOptin;
-  int w = (int)((avail - RCSB_SMEM_HEADER) / b->ws_bytes);
-  if (w > RCSB_MAX_WARPS) w = RCSB_MAX_WARPS;
+  int cap = RCSB_MAX_WARPS;
   if (const char* ov = getenv("RCSB_WARPS")) {  // tuning / profiling knob: fewer warps per CTA
     int o = atoi(ov);
-    if (o >= 1 && o < w) w = o;
+    if (o >= 1 && o < cap) cap = o;
   }
-  if (w < 1) { fail(RCSB_ERR_MODEL, "workspace does not fit in shared memory"); delete b; return nullptr; }
-  b->warps = w;
-  b->smem = RCSB_SMEM_HEADER + (size_t)w * b->ws_bytes;
-  b->grid = prop.multiProcessorCount;
-  int need = (n_envs + w - 1) / w;
-  if (b->grid > need) b->grid = need;
-  if (cudaFuncSetAttribute(rcsb_k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem) != cudaSuccess ||
+  if (const char* ov = getenv("RCSB_LOCKSTEP")) b->lockstep = atoi(ov);  // 0 none, 1 per stage, 2 per step
+  auto shape = [&](const RcsbModel& h, size_t& ws, int& warps, size_t& smem, int& grid) {
+    ws = rcsb_ws_bytes(&h);
+    warps = (int)((avail - RCSB_SMEM_HEADER) / ws);
+    if (warps > cap) warps = cap;
+    if (warps < 1) return false;
+    smem = RCSB_SMEM_HEADER + (size_t)warps * ws;
+    grid = prop.multiProcessorCount;
+    int need = (n_envs + warps - 1) / warps;
+    if (grid > need) grid = need;
+    return true;
+  };
+  bool ok = shape(m->has_reduced ? m->hr : m->h, b->ws_bytes, b->warps, b->smem, b->grid);
+  if (ok && m->has_reduced) ok = shape(m->h, b->ws_bytes_full, b->warps_full, b->smem_full, b->grid_full);
+  if (!ok) { fail(RCSB_ERR_MODEL, "workspace does not fit in shared memory"); delete b; return nullptr; }
+  size_t smem_max = b->smem > b->smem_full ? b->smem : b->smem_full;
+  if (cudaFuncSetAttribute(rcsb_k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess ||
       cudaFuncSetAttribute(rcsb_k_ik, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCSB_SMEM_HEADER) != cudaSuccess ||
-      cudaMalloc(&b->d_counter, sizeof(int)) != cudaSuccess) {
+      cudaMalloc(&b->d_counter, 4 * sizeof(int)) != cudaSuccess || cudaMalloc(&b->d_overflow, (size_t)n_envs * sizeof(int)) != cudaSuccess) {
     fail(RCSB_ERR_CUDA, std::string("batch setup: ") + cudaGetErrorString(cudaGetLastError()));
     delete b;
     return nullptr;
@@ -275,7 +317,7 @@ rcsb_batch* rcsb_batch_new(rcsb_model* m, int n_envs, void* sr, void* sd, void* 
 }
 void rcsb_batch_free(rcsb_batch* b) {
   if (!b) return;
-  cudaFree(b->d_counter); cudaFree(b->d_act_joints); cudaFree(b->d_act_gripper); cudaFree(b->d_obs); cudaFree(b->d_info);
+  cudaFree(b->d_counter); cudaFree(b->d_overflow); cudaFree(b->d_act_joints); cudaFree(b->d_act_gripper); cudaFree(b->d_obs); cudaFree(b->d_info);
   if (b->h_act) cudaFreeHost(b->h_act);
   if (b->h_obs) cudaFreeHost(b->h_obs);
   delete b;
@@ -310,7 +352,7 @@ int rcsb_batch_run(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps
   if ((ops & RCSB_OP_ACT_JOINTS_REL) && (!jlow || !jhigh)) return fail(RCSB_ERR_ARG, "joint limits required");
   RcsbLaunch L;
   memset(&L, 0, sizeof(L));
-  L.N = b->n; L.ops = ops; L.k = k; L.max_convergence_steps = max_convergence_steps;
+  L.N = b->n; L.ops = ops; L.lockstep = b->lockstep; L.k = k; L.max_convergence_steps = max_convergence_steps;
   L.act_joints = (const real*)act_joints_dev; L.act_gripper = (const real*)act_gripper_dev; L.mask = mask_dev;
   L.max_mov = (real)max_mov;
   for (int i = 0; i < b->m->h.rb_njoints && i < RCSB_MAXJ; i++) {
@@ -319,11 +361,20 @@ int rcsb_batch_run(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps
   }
   L.obs = (real*)obs_dev; L.info = info_dev;
   CUDA_OK(cudaSetDevice(b->m->device));
-  CUDA_OK(cudaMemsetAsync(b->d_counter, 0, sizeof(int), b->stream));
-  rcsb_k_run<<<b->grid, b->warps * 32, b->smem, b->stream>>>(b->m->d_model, b->m->d_verts, b->sr, b->sd, b->si, L, b->d_counter,
-                                                            b->ws_bytes);
+  CUDA_OK(cudaMemsetAsync(b->d_counter, 0, 4 * sizeof(int), b->stream));
+  L.phase = 0; L.overflow_list = b->d_overflow; L.overflow_count = b->d_counter + 2;
+  const bool two = b->m->has_reduced;
+  rcsb_k_run<<<b->grid, b->warps * 32, b->smem, b->stream>>>(two ? b->m->d_model_r : b->m->d_model, b->m->d_verts, b->sr, b->sd,
+                                                            b->si, L, b->d_counter, b->ws_bytes);
   g_launches++;
   CUDA_OK(cudaGetLastError());
+  if (two && (ops & (RCSB_OP_STEP_K | RCSB_OP_STEP_CONV))) {  // finishes the environments that outgrew the reduced layout
+    L.phase = 1; L.lockstep = 0;
+    rcsb_k_run<<<b->grid_full, b->warps_full * 32, b->smem_full, b->stream>>>(b->m->d_model, b->m->d_verts, b->sr, b->sd, b->si, L,
+                                                                             b->d_counter + 1, b->ws_bytes_full);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+  }
   return RCSB_OK;
 }
 

@@ -14,7 +14,7 @@ struct RcsbField { const char* name; size_t off; size_t bytes; int kind; };  // 
 static const RcsbField rcsb_model_fields[] = {
     RCSB_FI(nq), RCSB_FI(nv), RCSB_FI(nu), RCSB_FI(nb), RCSB_FI(ng), RCSB_FI(npair), RCSB_FI(nt), RCSB_FI(neq),
     RCSB_FI(nroot), RCSB_FI(nmeshvert), RCSB_FI(cone_elliptic), RCSB_FI(implicitfast), RCSB_FI(iterations),
-    RCSB_FI(ls_iterations), RCSB_FI(noslip_iterations), RCSB_FI(maxcon), RCSB_FI(maxefc),
+    RCSB_FI(ls_iterations), RCSB_FI(noslip_iterations), RCSB_FI(maxcon), RCSB_FI(maxefc), RCSB_FI(fast_maxcon), RCSB_FI(fast_maxefc),
     RCSB_FR(timestep), RCSB_FR(gravity), RCSB_FR(impratio), RCSB_FR(tolerance), RCSB_FR(ls_tolerance),
     RCSB_FR(noslip_tolerance), RCSB_FR(meaninertia),
     RCSB_FI(b_parent), RCSB_FI(b_jtype), RCSB_FI(b_qadr), RCSB_FI(b_dadr), RCSB_FI(b_ndof), RCSB_FI(b_root),
@@ -64,6 +64,13 @@ static inline int rcsb_model_set_field(RcsbModel* m, const char* name, const voi
 }
 
 // Workspace layout. The first nsr reals mirror the env's HBM row: q | v | ctrl | warm | RCS tail.
+// Lifetimes within one physics step (stage order: kinematics, com, crb, collision, velocity, make_constraint,
+// callbacks, actuation, constraint solve, integrate) decide what may share memory:
+//   region K  position-stage results read up to make_constraint: bpos bmat rootcom cinert cdof
+//   region U  stage-local scratch, one union: kinematics local frames | crb + crb buffer | geom centres + broad-phase
+//             candidate lists | cdofdot cvel cfrc
+//   region S  solver / integrator scratch, first written after make_constraint -> aliases K and U
+//   persistent across the step: M, force vectors, contacts, constraint rows
 static inline int rcsb_model_finalize_layout(RcsbModel* m) {
   if (m->nq <= 0 || m->nq > RCSB_MAXQ || m->nv <= 0 || m->nv > RCSB_MAXV || m->nu > RCSB_MAXU || m->nb > RCSB_MAXB ||
       m->ng > RCSB_MAXG || m->npair > RCSB_MAXPAIR || m->nt > RCSB_MAXT || m->neq > RCSB_MAXEQ ||
@@ -71,38 +78,36 @@ static inline int rcsb_model_finalize_layout(RcsbModel* m) {
     return -1;
   int nq = m->nq, nv = m->nv, nu = m->nu, nb = m->nb, o = 0;
 #define RCSB_ALLOC(field, n) do { m->field = o; o += (n); } while (0)
+#define RCSB_MAX(a, b) ((a) > (b) ? (a) : (b))
   RCSB_ALLOC(o_q, nq); RCSB_ALLOC(o_v, nv); RCSB_ALLOC(o_ctrl, nu); RCSB_ALLOC(o_warm, nv);
   RCSB_ALLOC(o_rcs, RCSB_S_TAIL);
   m->nsr = o;
   m->o_site = m->o_rcs + RCSB_S_SITEPOS;
-  // region K: position/velocity-stage scratch, dead once st_make_constraint has built the constraint rows
   const int k_begin = o;
-  RCSB_ALLOC(o_bpos, 3 * nb); RCSB_ALLOC(o_bmat, 9 * nb); RCSB_ALLOC(o_bcom, 3 * nb);
-  RCSB_ALLOC(o_bgc, 3 * nb); RCSB_ALLOC(o_janchor, 3 * nb); RCSB_ALLOC(o_jaxis, 3 * nb);
-  RCSB_ALLOC(o_rootcom, 3 * m->nroot);
-  RCSB_ALLOC(o_cinert, 10 * nb);
-  // kinematics scratch (local rotations/translations, 12*nb) is dead before crb / cdof / cdof_dot are written
-  m->o_bquat = o;
-  RCSB_ALLOC(o_crb, 10 * nb); RCSB_ALLOC(o_cdof, 6 * nv); RCSB_ALLOC(o_cdofdot, 6 * nv);
-  if (o - m->o_bquat < 12 * nb) o = m->o_bquat + 12 * nb;
-  RCSB_ALLOC(o_cvel, 6 * nb); RCSB_ALLOC(o_cfrc, 6 * nb);
-  m->o_cacc = m->o_cfrc;  // unused (the spatial acceleration lives in registers)
-  RCSB_ALLOC(o_gpos, 3 * m->ng);
-  const int k_end = o;
-  // region S: solver / integrator scratch, first written after st_make_constraint -> aliases region K
+  RCSB_ALLOC(o_bpos, 3 * nb); RCSB_ALLOC(o_bmat, 9 * nb); RCSB_ALLOC(o_rootcom, 3 * m->nroot);
+  RCSB_ALLOC(o_cinert, 10 * nb); RCSB_ALLOC(o_cdof, 6 * nv);
+  const int u_begin = o;
+  int u_end = u_begin;
+  RCSB_ALLOC(o_bquat, 12 * nb);  // kinematics: local rotations [nb][9] + local translations [nb][3]
+  u_end = RCSB_MAX(u_end, o); o = u_begin;
+  RCSB_ALLOC(o_crb, 10 * nb); RCSB_ALLOC(o_crbbuf, 6 * nv);
+  u_end = RCSB_MAX(u_end, o); o = u_begin;
+  RCSB_ALLOC(o_gpos, 3 * m->ng); RCSB_ALLOC(o_cand, (2 * RCSB_MAXCAND * (int)sizeof(int) + (int)sizeof(real) - 1) / (int)sizeof(real));
+  u_end = RCSB_MAX(u_end, o); o = u_begin;
+  RCSB_ALLOC(o_cdofdot, 6 * nv); RCSB_ALLOC(o_cvel, 6 * nb); RCSB_ALLOC(o_cfrc, 6 * nb);
+  u_end = RCSB_MAX(u_end, o);
+  const int k_end = u_end;
   o = k_begin;
-  RCSB_ALLOC(o_H, nv * nv + nv);
+  RCSB_ALLOC(o_H, nv * nv + nv); RCSB_ALLOC(o_L, nv * nv + nv);
   RCSB_ALLOC(o_grad, nv); RCSB_ALLOC(o_search, nv); RCSB_ALLOC(o_Ma, nv); RCSB_ALLOC(o_Mv, nv);
+  RCSB_ALLOC(o_tmp, RCSB_MAX(nv, RCSB_MAXJ) + 2);  // triangular-solve scratch (host emulation), action staging
   RCSB_ALLOC(o_conehess, 9 * m->maxcon);
   RCSB_ALLOC(o_noslip, (nv + 2 * m->maxcon) * nv + nv + 4 * m->maxcon);
   if (o < k_end) o = k_end;
-  // persistent across the whole step
-  RCSB_ALLOC(o_M, nv * nv); RCSB_ALLOC(o_L, nv * nv + nv);
+  RCSB_ALLOC(o_M, nv * nv);
   RCSB_ALLOC(o_bias, nv); RCSB_ALLOC(o_passive, nv); RCSB_ALLOC(o_gravc, nv); RCSB_ALLOC(o_actfrc, nv);
   RCSB_ALLOC(o_smooth, nv); RCSB_ALLOC(o_qacc_smooth, nv); RCSB_ALLOC(o_qacc, nv); RCSB_ALLOC(o_qfc, nv);
-  RCSB_ALLOC(o_tmp, 6 * nv + 2);  // crb buffer (6*nv), solve scratch (nv), action staging (njoints)
   RCSB_ALLOC(o_aforce, nu);
-  m->o_alen = m->o_avel = m->o_aforce;  // actuator length / velocity live in registers
   RCSB_ALLOC(o_con, RCSB_C_REALS * m->maxcon);
   RCSB_ALLOC(o_J, m->maxefc * nv);
   RCSB_ALLOC(o_efc, RCSB_E_NARR * m->maxefc);
@@ -113,11 +118,21 @@ static inline int rcsb_model_finalize_layout(RcsbModel* m) {
   o = 0;
   RCSB_ALLOC(oi_con, RCSB_CI_INTS * m->maxcon);
   RCSB_ALLOC(oi_efc, RCSB_EI_NARR * m->maxefc);
-  RCSB_ALLOC(oi_cand, 2 * RCSB_MAXCAND);
   RCSB_ALLOC(oi_misc, 8 /* MI_COUNT */ + RCSB_I_TAIL);
   m->ws_ints = (o + 3) & ~3;
 #undef RCSB_ALLOC
+#undef RCSB_MAX
   return 0;
+}
+// The reduced-capacity copy of a finalised model (see RcsbModel::fast_maxcon); returns 0 when there is none.
+static inline int rcsb_model_make_reduced(const RcsbModel* full, RcsbModel* out) {
+  if (full->fast_maxcon <= 0 || full->fast_maxefc <= 0 || (full->fast_maxcon >= full->maxcon && full->fast_maxefc >= full->maxefc))
+    return 0;
+  *out = *full;
+  if (out->fast_maxcon < out->maxcon) out->maxcon = out->fast_maxcon;
+  if (out->fast_maxefc < out->maxefc) out->maxefc = out->fast_maxefc;
+  out->cap_reduced = 1;
+  return rcsb_model_finalize_layout(out) == 0;
 }
 static inline size_t rcsb_ws_bytes(const RcsbModel* m) {
   size_t b = (size_t)m->ws_reals * sizeof(real) + (size_t)m->ws_doubles * sizeof(double) + (size_t)m->ws_ints * sizeof(int);

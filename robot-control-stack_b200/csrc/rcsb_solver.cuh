@@ -28,7 +28,7 @@ RCSB_DEV void get_impedance(const real* solimp, real pos, real margin, real* imp
 
 // frame-row . translational Jacobian column k of a world point attached to moving body `body`
 RCSB_DEV real jac_dot(const Ctx& c, int body, int k, const real* pos, const real* dirv) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   if (body < 0 || !((m.b_dofmask[body] >> k) & 1u)) return 0;
   const real* cd = WR(cdof) + 6 * k;
   const real* rc = WR(rootcom) + 3 * m.b_root[body];
@@ -38,7 +38,7 @@ RCSB_DEV real jac_dot(const Ctx& c, int body, int k, const real* pos, const real
 }
 
 RCSB_DEV void st_make_constraint(const Ctx& c) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   const int nv = m.nv, maxefc = m.maxefc;
   const real* q = WR(q);
   int* etype = EFCI(RCSB_EI_TYPE);
@@ -61,9 +61,13 @@ RCSB_DEV void st_make_constraint(const Ctx& c) {
       real qj = q[m.d_qadr[j]];
       for (int side = 0; side < 2; side++) {
         real dist = side ? (m.d_range[j][1] - qj) : (qj - m.d_range[j][0]);
-        if (dist < m.d_margin[j] && nefc < maxefc) {
-          if (c.lane == 0) { etype[nefc] = RCSB_LIMIT; eid[nefc] = 2 * j + side; }
-          nefc++; nl++;
+        if (dist < m.d_margin[j]) {
+          if (nefc < maxefc) {
+            if (c.lane == 0) { etype[nefc] = RCSB_LIMIT; eid[nefc] = 2 * j + side; }
+            nefc++; nl++;
+          } else if (c.lane == 0) {
+            WI(misc)[m.cap_reduced ? MI_OVERFLOW : MI_WARN] += 1;
+          }
         }
       }
     }
@@ -80,7 +84,7 @@ RCSB_DEV void st_make_constraint(const Ctx& c) {
           for (int r = 0; r < rows; r++) { etype[nefc + r] = m.cone_elliptic ? RCSB_CONTACT_ELL : RCSB_CONTACT_PYR; eid[nefc + r] = ci; }
         nefc += rows;
       } else if (c.lane == 0) {
-        WI(misc)[MI_WARN] += 1;
+        WI(misc)[m.cap_reduced ? MI_OVERFLOW : MI_WARN] += 1;
       }
     }
     if (c.lane == 0) cii[RCSB_CI_EFC] = addr;
@@ -213,7 +217,7 @@ RCSB_DEV void st_make_constraint(const Ctx& c) {
 
 // ------------------------------------------------------------------ actuation and smooth acceleration
 RCSB_DEV void st_actuation(const Ctx& c) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   const int nv = m.nv;
   PFOR(a, m.nu) {
     real len, vel;
@@ -251,8 +255,9 @@ RCSB_DEV void st_actuation(const Ctx& c) {
 }
 // Cholesky factor of M on demand (o_L holds a copy of M until then)
 RCSB_DEV void ensure_chol_M(const Ctx& c) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   if (!WI(misc)[MI_HAVE_L]) {
+    PFOR(e, m.nv * m.nv) { WR(L)[e] = WR(M)[e]; }
     chol_factor(c, WR(L), WR(L) + m.nv * m.nv, m.nv);
     if (c.lane == 0) WI(misc)[MI_HAVE_L] = 1;
     RCSB_SYNC();
@@ -260,7 +265,7 @@ RCSB_DEV void ensure_chol_M(const Ctx& c) {
 }
 // qacc_smooth = M^-1 qfrc_smooth (mj_fwdAcceleration); only the general solver path and nefc == 0 need it
 RCSB_DEV void compute_qacc_smooth(const Ctx& c) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   ensure_chol_M(c);
   PFOR(k, m.nv) { WR(qacc_smooth)[k] = WR(smooth)[k]; }
   chol_solve(c, WR(L), WR(L) + m.nv * m.nv, m.nv, WR(qacc_smooth), WR(tmp));
@@ -270,7 +275,7 @@ RCSB_DEV void compute_qacc_smooth(const Ctx& c) {
 struct CostOut { real cost, gauss; };
 
 RCSB_DEV real constraint_update(const Ctx& c, int nefc, int ncon, int want_hess) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   const real* jar = EFC(RCSB_E_JAR);
   real* force = EFC(RCSB_E_FORCE);
   int* state = EFCI(RCSB_EI_STATE);
@@ -336,9 +341,12 @@ RCSB_DEV real constraint_update(const Ctx& c, int nefc, int ncon, int want_hess)
 
 // cost at acceleration vector `acc` (shared memory): fills Ma, jar, force, state; returns total cost
 RCSB_DEV_NOINLINE real total_cost(const Ctx& c, const real* acc, int nefc, int ncon, int want_hess, real* gauss_out) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   const int nv = m.nv;
   real g = 0;
+#ifndef RCSB_HOST_EMU
+  __builtin_assume(__isShared(acc));
+#endif
   PFOR(i, nv) {
     real s = 0;
     for (int j = 0; j < nv; j++) s += WR(M)[i * nv + j] * acc[j];
@@ -360,7 +368,7 @@ RCSB_DEV_NOINLINE real total_cost(const Ctx& c, const real* acc, int nefc, int n
 // value, first and second derivative of the cost along the search direction at step alpha
 RCSB_DEV_NOINLINE void line_eval(const Ctx& c, int nefc, int ncon, real alpha, real qG0, real qG1, real qG2, real* val, real* d1,
                         real* d2) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   const real* jar = EFC(RCSB_E_JAR);
   const real* Jv = EFC(RCSB_E_JV);
   const int* etype = EFCI(RCSB_EI_TYPE);
@@ -439,7 +447,7 @@ RCSB_DEV real line_search(const Ctx& c, int nefc, int ncon, real qG0, real qG1, 
 }
 
 RCSB_DEV void compute_qfc(const Ctx& c, int nefc) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   const int nv = m.nv;
   PFOR(k, nv) {
     real s = 0;
@@ -452,7 +460,7 @@ RCSB_DEV void compute_qfc(const Ctx& c, int nefc) {
 
 // ------------------------------------------------------------------ noslip post-pass
 RCSB_DEV_NOINLINE void solve_noslip(const Ctx& c, int nefc, int ncon) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   const int nv = m.nv;
   int ne = WI(misc)[MI_NE], nf = WI(misc)[MI_NF];
   int any = nf > 0;
@@ -574,7 +582,7 @@ RCSB_DEV_NOINLINE void solve_noslip(const Ctx& c, int nefc, int ncon) {
 
 // ------------------------------------------------------------------ constrained acceleration (Newton)
 RCSB_DEV void st_constraint_solve(const Ctx& c) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   const int nv = m.nv;
   int nefc = WI(misc)[MI_NEFC], ncon = WI(misc)[MI_NCON];
   if (nefc == 0) {
@@ -702,7 +710,7 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
 
 // ------------------------------------------------------------------ implicitfast / Euler integration + mj_advance
 RCSB_DEV void st_integrate(const Ctx& c) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   const int nv = m.nv;
   const real h = m.timestep;
   PFOR(e, nv * nv) {
@@ -760,16 +768,16 @@ RCSB_DEV void st_integrate(const Ctx& c) {
 // Persistent per-env RCS state lives in the workspace region o_rcs (reals: RCSB_S_* tail) and
 // oi_rcs (ints: RCSB_I_*). Semantics: sim.cpp:14-61, SimRobot.cpp:156-191, SimGripper.cpp:93-151.
 #define RS(i) (WR(rcs)[(i)])
-#define RI(i) (c.wi[m.oi_misc + MI_COUNT + (i)])
+#define RI(i) (CWI(c)[m.oi_misc + MI_COUNT + (i)])
 
 RCSB_DEV real gripper_width(const Ctx& c) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   real w = (WR(q)[m.gr_qadr] - m.gr_min_joint) / (m.gr_max_joint - m.gr_min_joint);
   return w < 0 ? (real)0 : (w > 1 ? (real)1 : w);
 }
 // all lanes evaluate callbacks redundantly on identical data; lane 0 commits state
 RCSB_DEV int run_callback(const Ctx& c, int kind) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   int ret = 0;
   if (kind == RCSB_CB_ARRIVED) {
     real mx = 0;
@@ -829,30 +837,30 @@ RCSB_DEV real cb_period(const RcsbModel& m, int kind) { return kind <= RCSB_CB_R
 
 // plain callbacks between the two halves of the step (sim.cpp:38-47); clocks compare in double
 RCSB_DEV void invoke_callbacks(const Ctx& c, double time) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   for (int kind = RCSB_CB_ARRIVED; kind <= RCSB_CB_MOVING; kind++) {
     if (!cb_registered(m, kind)) continue;
-    double dt = time - c.clk[RCSB_D_CBLAST + kind];
+    double dt = time - CCLK(c)[RCSB_D_CBLAST + kind];
     if (dt > (double)cb_period(m, kind)) {
       run_callback(c, kind);
-      if (c.lane == 0) c.clk[RCSB_D_CBLAST + kind] = time;
+      if (c.lane == 0) CCLK(c)[RCSB_D_CBLAST + kind] = time;
       RCSB_SYNC();
     }
   }
 }
 // condition callbacks after the step (sim.cpp:49-61): any-list first, then all-list
 RCSB_DEV int invoke_condition_callbacks(const Ctx& c, double time) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   const int any_list[2] = {RCSB_CB_ROBOT_COLL, RCSB_CB_GRIP_COLL};
   const int all_list[2] = {RCSB_CB_ROBOT_CONV, RCSB_CB_GRIP_CONV};
   for (int pass = 0; pass < 2; pass++)
     for (int i = 0; i < 2; i++) {
       int kind = pass == 0 ? any_list[i] : all_list[i];
       if (!cb_registered(m, kind)) continue;
-      double dt = time - c.clk[RCSB_D_CBLAST + kind];
+      double dt = time - CCLK(c)[RCSB_D_CBLAST + kind];
       if (dt > (double)cb_period(m, kind)) {
         int r = run_callback(c, kind);
-        if (c.lane == 0) { RI(RCSB_I_CBRET + kind) = r; c.clk[RCSB_D_CBLAST + kind] = time; }
+        if (c.lane == 0) { RI(RCSB_I_CBRET + kind) = r; CCLK(c)[RCSB_D_CBLAST + kind] = time; }
         RCSB_SYNC();
       }
     }
@@ -866,14 +874,14 @@ RCSB_DEV int invoke_condition_callbacks(const Ctx& c, double time) {
 
 // ------------------------------------------------------------------ one physics step (step1; callbacks; step2)
 RCSB_DEV int state_is_bad(const Ctx& c) {
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   int bad = 0;
   PFOR(i, m.nq) { real x = WR(q)[i]; if (!(x == x) || x > (real)1e10 || x < (real)-1e10) bad = 1; }
   PFOR(i, m.nv) { real x = WR(v)[i]; if (!(x == x) || x > (real)1e10 || x < (real)-1e10) bad = 1; }
   return warp_any(bad);
 }
 RCSB_DEV void reset_data(const Ctx& c, double* time) {  // mj_resetData
-  const RcsbModel& m = *c.md;
+  const RcsbModel& m = CMODEL(c);
   PFOR(i, m.nq) { WR(q)[i] = m.qpos0[i]; }
   PFOR(i, m.nv) { WR(v)[i] = 0; WR(warm)[i] = 0; }
   PFOR(i, m.nu) { WR(ctrl)[i] = 0; }
@@ -894,8 +902,10 @@ __device__ unsigned long long rcsb_stage_cycles[16];
 #else
 #define RCSB_STAGE(idx, call) do { RCSB_BLOCK_SYNC(); call; } while (0)
 #endif
-RCSB_DEV void physics_step(const Ctx& c, double* time) {
-  const RcsbModel& m = *c.md;
+// returns 1 when the step did not fit the reduced workspace layout: nothing persistent was changed, the caller hands
+// the environment to the full-capacity launch
+RCSB_DEV int physics_step(const Ctx& c, double* time) {
+  const RcsbModel& m = CMODEL(c);
   if (state_is_bad(c)) {
     if (c.lane == 0) WI(misc)[MI_WARN] += 1;
     reset_data(c, time);
@@ -910,16 +920,22 @@ RCSB_DEV void physics_step(const Ctx& c, double* time) {
   RCSB_STAGE(3, st_collision(c));
   RCSB_STAGE(4, st_velocity(c));
   RCSB_STAGE(5, st_make_constraint(c));
+  if (m.cap_reduced && WI(misc)[MI_OVERFLOW]) {
+    for (int i = 0; i < 3; i++) RCSB_BLOCK_SYNC();  // the barriers of the stages this warp skips
+    RCSB_STEP_SYNC();
+    return 1;
+  }
   // ---- RCS plain callbacks see pre-integration time and qpos
   invoke_callbacks(c, *time);
   // ---- mj_step2
   RCSB_STAGE(6, st_actuation(c));
   RCSB_STAGE(7, st_constraint_solve(c));
   RCSB_STAGE(8, st_integrate(c));
-  RCSB_BLOCK_SYNC();
+  RCSB_STEP_SYNC();
   if (c.lane == 0) {  // the clock lives in shared memory: one writer
     *time += (double)m.timestep;
     RI(RCSB_I_TOTAL_STEPS) += 1;
   }
   RCSB_SYNC();
+  return 0;
 }

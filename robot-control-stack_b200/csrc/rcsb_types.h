@@ -42,6 +42,11 @@ struct RcsbModel {
   int nq, nv, nu, nb, ng, npair, nt, neq, nroot, nmeshvert;
   int cone_elliptic, implicitfast, iterations, ls_iterations, noslip_iterations;
   int maxcon, maxefc;  // per-env capacities of the contact / constraint workspaces
+  // Two workspace layouts share one kernel: the full-capacity one above and a reduced one (fast_maxcon / fast_maxefc,
+  // 0 = none) that is small enough for twice the warps per SM. A launch runs every environment in the reduced layout
+  // first; an environment whose contact / constraint count does not fit (cap_reduced != 0 in the model copy it ran
+  // with) stops before the step that overflowed and is finished by a second launch in the full layout.
+  int fast_maxcon, fast_maxefc, cap_reduced;
   real timestep, gravity[3], impratio, tolerance, ls_tolerance, noslip_tolerance, meaninertia;
   // ---- moving bodies (one joint each)
   int b_parent[RCSB_MAXB], b_jtype[RCSB_MAXB], b_qadr[RCSB_MAXB], b_dadr[RCSB_MAXB], b_ndof[RCSB_MAXB], b_root[RCSB_MAXB];
@@ -88,12 +93,12 @@ struct RcsbModel {
   real gr_eps_inner, gr_eps_outer, gr_cb_period, gr_max_act, gr_min_act, gr_max_joint, gr_min_joint;
   // ---- per-warp workspace layout (offsets in reals / ints), filled by rcsb_model_finalize
   int ws_reals, ws_ints, nsr;  // nsr = reals per env in HBM (dynamic state + RCS tail)
-  int o_q, o_v, o_ctrl, o_warm, o_bpos, o_bquat, o_bmat, o_bcom, o_bgc, o_janchor, o_jaxis, o_rootcom, o_cinert, o_crb,
-      o_cdof, o_cdofdot, o_cvel, o_cacc, o_cfrc, o_M, o_L, o_H, o_bias, o_passive, o_gravc, o_actfrc, o_smooth,
-      o_qacc_smooth, o_qacc, o_qfc, o_grad, o_search, o_Ma, o_Mv, o_tmp, o_alen, o_avel, o_aforce, o_gpos, o_con,
+  int o_q, o_v, o_ctrl, o_warm, o_bpos, o_bquat, o_bmat, o_rootcom, o_cinert, o_crb, o_crbbuf,
+      o_cdof, o_cdofdot, o_cvel, o_cfrc, o_M, o_L, o_H, o_bias, o_passive, o_gravc, o_actfrc, o_smooth,
+      o_qacc_smooth, o_qacc, o_qfc, o_grad, o_search, o_Ma, o_Mv, o_tmp, o_aforce, o_gpos, o_cand, o_con,
       o_J, o_efc, o_conehess, o_noslip, o_site, o_rcs, o_sepcache;
   int ws_doubles;  // RCSB_D_TAIL doubles per warp follow the reals
-  int oi_con, oi_efc, oi_cand, oi_misc;
+  int oi_con, oi_efc, oi_misc;
 };
 
 // per-contact record in the workspace (reals)
@@ -127,5 +132,6 @@ enum {
   RCSB_I_CONVERGED, RCSB_I_CONV_STEPS, RCSB_I_CBRET,  // RCSB_NCB last_return_value flags follow
   RCSB_I_NCON = RCSB_I_CBRET + RCSB_NCB, RCSB_I_NEFC, RCSB_I_SOLVER_ITER, RCSB_I_WARN, RCSB_I_TOTAL_STEPS,
   RCSB_I_HAVE_PREV_ACTION,  // RobotEnv.prev_action is not None (base.py:268-272)
+  RCSB_I_RESUME,  // substeps this launch still owes the environment (it outgrew the reduced workspace layout)
   RCSB_I_TAIL
 };

@@ -16,6 +16,7 @@
 #define RCSB_NLANES 1
 #define RCSB_SYNC() ((void)0)
 #define RCSB_BLOCK_SYNC() ((void)0)
+#define RCSB_STEP_SYNC() ((void)0)
 #ifdef RCSB_EMU_REVERSE  // run every parallel-for backwards: results must not depend on lane order
 #define PFOR(i, n) for (int i = (n)-1; i >= 0; --i)
 #else
@@ -37,7 +38,8 @@ RCSB_DEV int warp_bcast_i(int x, int src) { return x; }
 #define RCSB_SYNC() __syncwarp()
 // CTA-wide barrier used only in fixed-substep launches, where every warp of the CTA (including warps without an
 // environment, see rcsb_k_run) executes exactly the same number of them
-#define RCSB_BLOCK_SYNC() do { if (c.lockstep) __syncthreads(); } while (0)
+#define RCSB_BLOCK_SYNC() do { if (c.lockstep == 1) __syncthreads(); } while (0)
+#define RCSB_STEP_SYNC() do { if (c.lockstep) __syncthreads(); } while (0)
 #define RCSB_STAGE_BARRIERS 10  // CTA barriers per physics step in lockstep mode (physics_step)
 #define PFOR(i, n) for (int i = (int)(threadIdx.x & 31); i < (n); i += 32)
 RCSB_DEV real warp_sum(real x) {

@@ -21,10 +21,11 @@ def _ip(a):
 
 
 class DeviceModel:
-    def __init__(self, M: dict, robot_cfg=None, gripper_cfg=None, maxcon: int | None = None, device: int = 0):
+    def __init__(self, M: dict, robot_cfg=None, gripper_cfg=None, maxcon: int | None = None, device: int = 0,
+                 fast_maxcon: int | None = None):
         L = _lib.lib()
         self.M = M
-        self.fields, self.verts = devmodel.build_device_fields(M, robot_cfg, gripper_cfg, maxcon)
+        self.fields, self.verts = devmodel.build_device_fields(M, robot_cfg, gripper_cfg, maxcon, fast_maxcon)
         self.ptr = L.rcsb_model_new()
         for name, (arr, is_real) in self.fields.items():
             a = np.ascontiguousarray(arr).ravel()

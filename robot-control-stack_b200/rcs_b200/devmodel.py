@@ -14,6 +14,8 @@ import numpy as np
 from . import mjcf
 from .mjcf import JNT_FREE, quat_mul, quat_to_mat, mat_to_quat
 
+FAST_MAXCON_DEFAULT = 1  # contact capacity of the reduced workspace layout
+FAST_LIMIT_ROWS = 4      # simultaneously active joint-limit rows the reduced layout holds
 MAXCON_DEFAULT = 6  # per-env contact capacity (overflow is counted in the warn flag); Sim(maxcon=...) overrides
 ROLE_ARM, ROLE_GRIPPER, ROLE_FINGER, ROLE_IGNORED = 1, 2, 4, 8
 
@@ -25,7 +27,8 @@ def _name_id(names, name, kind):
         raise RuntimeError(f"No {kind} named {name}") from None
 
 
-def build_device_fields(M: dict, robot_cfg=None, gripper_cfg=None, maxcon: int | None = None) -> tuple[dict, np.ndarray]:
+def build_device_fields(M: dict, robot_cfg=None, gripper_cfg=None, maxcon: int | None = None,
+                        fast_maxcon: int | None = None) -> tuple[dict, np.ndarray]:
     """Returns ({field: (np.ndarray, is_real)}, mesh_vert[nvert,3]).
 
     robot_cfg: object with joints, actuators, arm_collision_geoms, attachment_site, base, tcp_offset (7,: xyz+xyzw),
@@ -322,6 +325,14 @@ def build_device_fields(M: dict, robot_cfg=None, gripper_cfg=None, maxcon: int |
                  ("ls_iterations", M["opt_ls_iterations"]), ("noslip_iterations", M["opt_noslip_iterations"]),
                  ("maxcon", mc), ("maxefc", M["neq"] + nfl + nlim + rows_per_con * mc)):
         put(f, [v], False)
+    # Reduced-capacity workspace layout (rcsb_types.h: fast_maxcon): environments whose contacts / active limits fit it
+    # run at twice the warps per SM; the others are finished by a second launch in the full layout. Scenes with free
+    # bodies rest on contacts all the time, so they default to the full layout only.
+    has_free = bool((np.asarray(M["jnt_type"]) == 0).any())
+    fmc = int(fast_maxcon) if fast_maxcon is not None else (0 if has_free else FAST_MAXCON_DEFAULT)
+    fmc = min(fmc, mc)
+    put("fast_maxcon", [fmc], False)
+    put("fast_maxefc", [M["neq"] + nfl + min(nlim, FAST_LIMIT_ROWS) + rows_per_con * fmc if fmc > 0 else 0], False)
     for f, v in (("timestep", M["opt_timestep"]), ("impratio", M["opt_impratio"]), ("tolerance", M["opt_tolerance"]),
                  ("ls_tolerance", M["opt_ls_tolerance"]), ("noslip_tolerance", M["opt_noslip_tolerance"]),
                  ("meaninertia", M["stat_meaninertia"])):

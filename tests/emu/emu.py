@@ -25,18 +25,19 @@ OPS = dict(GRIPPER_RESET=1, SIM_RESET=2, ROBOT_RESET=4, ENV_RESET_FLAGS=8, ACT_J
 
 
 class Emu:
-    def __init__(self, fields, verts, N, reverse=False):
+    def __init__(self, fields, verts, N, reverse=False, use_reduced=True):
         L = C.CDLL(build(reverse))
         self.L = L
         vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
         L.emu_model_new.restype = vp
         L.emu_model_set_int.argtypes = [vp, C.c_char_p, ip, C.c_int]
         L.emu_model_set_real.argtypes = [vp, C.c_char_p, dp, C.c_int]
-        L.emu_model_finalize.argtypes = [vp]
+        L.emu_model_finalize.argtypes = [vp, C.c_int]
         L.emu_nsr.argtypes = [vp]
-        L.emu_offset.argtypes = [vp, C.c_char_p]
+        L.emu_offset.argtypes = [vp, C.c_char_p, C.c_int]
+        L.emu_has_reduced.argtypes = [vp]
         L.emu_run.argtypes = [vp, dp, dp, dp, ip, C.c_int, C.c_uint, C.c_int, C.c_int, dp, dp, C.c_void_p, C.c_double,
-                              dp, dp, dp, ip, dp]
+                              dp, dp, dp, ip, dp, ip]
         self.m = L.emu_model_new()
         for name, (arr, is_real) in fields.items():
             a = np.ascontiguousarray(arr).ravel()
@@ -45,7 +46,8 @@ class Emu:
             else:
                 rc = L.emu_model_set_int(self.m, name.encode(), a.ctypes.data_as(ip), a.size)
             assert rc == 0, (name, rc)
-        assert L.emu_model_finalize(self.m) == 0
+        assert L.emu_model_finalize(self.m, int(use_reduced)) == 0
+        self.has_reduced = bool(L.emu_has_reduced(self.m))
         sz = (C.c_int * 6)()
         L.emu_sizes(sz)
         self.S_TAIL, self.D_TAIL, self.I_TAIL, self.OBS_DIM, self.INFO_DIM, self.real_bytes = list(sz)
@@ -60,9 +62,11 @@ class Emu:
         self.obs = np.zeros((N, self.OBS_DIM))
         self.info = np.zeros((N, self.INFO_DIM), dtype=np.int32)
         self.ws = np.zeros((N, self.off("ws_reals")))
+        self.layout = np.zeros(N, dtype=np.int32)  # 1 = the env last ran in the reduced layout
+        self.handed_over = 0                        # envs the reduced layout passed to the full one in the last run
 
-    def off(self, name):
-        return self.L.emu_offset(self.m, name.encode())
+    def off(self, name, reduced=0):
+        return self.L.emu_offset(self.m, name.encode(), int(reduced))
 
     def run(self, ops, k=0, max_conv=500, act_joints=None, act_gripper=None, max_mov=0.0, jlow=None, jhigh=None):
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
@@ -74,12 +78,12 @@ class Emu:
         lo = np.zeros(8); hi = np.zeros(8)
         if jlow is not None:
             lo[:len(jlow)] = jlow; hi[:len(jhigh)] = jhigh
-        self.L.emu_run(self.m, self.verts.ctypes.data_as(dp), self.sr.ctypes.data_as(dp), self.sd.ctypes.data_as(dp),
+        self.handed_over = self.L.emu_run(self.m, self.verts.ctypes.data_as(dp), self.sr.ctypes.data_as(dp), self.sd.ctypes.data_as(dp),
                        self.si.ctypes.data_as(ip), self.N, code, k, max_conv,
                        aj.ctypes.data_as(dp) if aj is not None else None, ag.ctypes.data_as(dp) if ag is not None else None,
                        None, float(max_mov), lo.ctypes.data_as(dp), hi.ctypes.data_as(dp), self.obs.ctypes.data_as(dp),
-                       self.info.ctypes.data_as(ip), self.ws.ctypes.data_as(dp))
+                       self.info.ctypes.data_as(ip), self.ws.ctypes.data_as(dp), self.layout.ctypes.data_as(ip))
 
     def wsf(self, name, n, env=0):
-        o = self.off(name)
+        o = self.off(name, self.layout[env])
         return self.ws[env, o:o + n]
