@@ -592,42 +592,84 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
     RCSB_SYNC();
     return;
   }
-  if (WI(misc)[MI_NE] == nefc) {
-    // Every row is an equality (always-active quadratic): the strictly convex cost is an unconstrained quadratic
-    // whose minimiser solves (M + J^T D J) qacc = qfrc_smooth + J^T D aref. This is the point the Newton iteration
-    // with exact line search reaches in one step; no cost evaluations, line search or factorisation of M needed.
-    PFOR(e, nv * nv) {
-      int a = e / nv, b = e - a * nv;
-      if (b > a) continue;
-      real h = WR(M)[e];
-      for (int r = 0; r < nefc; r++) h += EFC(RCSB_E_D)[r] * WR(J)[r * nv + a] * WR(J)[r * nv + b];
-      WR(H)[a * nv + b] = h;
-      WR(H)[b * nv + a] = h;
-    }
-    PFOR(k, nv) {
-      real s = WR(smooth)[k];
-      for (int r = 0; r < nefc; r++) s += EFC(RCSB_E_D)[r] * EFC(RCSB_E_AREF)[r] * WR(J)[r * nv + k];
-      WR(qacc)[k] = s;
-    }
-    chol_factor(c, WR(H), WR(H) + nv * nv, nv);
-    chol_solve(c, WR(H), WR(H) + nv * nv, nv, WR(qacc), WR(tmp));
+  if (ncon == 0 && !(WI(misc)[MI_NF] > 0 && m.noslip_iterations > 0)) {
+    // Direct active-set solve for equality / friction-loss / joint-limit rows. The cost is strictly convex and piecewise
+    // quadratic in qacc: with the zone of every row fixed (quadratic, linear with constant force, or inactive) the
+    // stationarity condition is the linear system
+    //   (M + sum_quadratic D J^T J) qacc = qfrc_smooth + sum_quadratic D aref J^T + sum_linear force J^T,
+    // and a solution whose rows land in the zones that were assumed satisfies the optimality conditions of the whole
+    // problem, i.e. it IS the minimiser the Newton iteration converges to. Zones are guessed (limits active, friction
+    // from the warm start), solved, checked, and re-guessed from the solution at most twice; all-equality problems
+    // verify on the first pass. Only if that fails does the general Newton path below run.
+    int* state = EFCI(RCSB_EI_STATE);
+    const int* etype = EFCI(RCSB_EI_TYPE);
     PFOR(r, nefc) {
-      real s = 0;
-      for (int k = 0; k < nv; k++) s += WR(J)[r * nv + k] * WR(qacc)[k];
-      real jar = s - EFC(RCSB_E_AREF)[r];
-      EFC(RCSB_E_JAR)[r] = jar;
-      EFC(RCSB_E_FORCE)[r] = -EFC(RCSB_E_D)[r] * jar;
-      EFCI(RCSB_EI_STATE)[r] = RCSB_QUADRATIC;
+      int st = RCSB_QUADRATIC;
+      if (etype[r] == RCSB_FRICTION_DOF) {
+        real x = -EFC(RCSB_E_AREF)[r];
+        for (int k = 0; k < nv; k++) x += WR(J)[r * nv + k] * WR(warm)[k];
+        real f = EFC(RCSB_E_FLOSS)[r], R = EFC(RCSB_E_R)[r];
+        st = x <= -R * f ? RCSB_LINEARNEG : (x >= R * f ? RCSB_LINEARPOS : RCSB_QUADRATIC);
+      }
+      state[r] = st;
     }
     RCSB_SYNC();
-    PFOR(k, nv) {
-      real s = 0;
-      for (int r = 0; r < nefc; r++) s += WR(J)[r * nv + k] * EFC(RCSB_E_FORCE)[r];
-      WR(qfc)[k] = s;
+    int verified = 0, attempt = 0;
+    for (; attempt < 3 && !verified; attempt++) {
+      PFOR(e, nv * nv) {
+        int a = e / nv, b = e - a * nv;
+        if (b > a) continue;
+        real h = WR(M)[e];
+        for (int r = 0; r < nefc; r++)
+          if (state[r] == RCSB_QUADRATIC) h += EFC(RCSB_E_D)[r] * WR(J)[r * nv + a] * WR(J)[r * nv + b];
+        WR(H)[a * nv + b] = h;
+        WR(H)[b * nv + a] = h;
+      }
+      PFOR(k, nv) {
+        real s = WR(smooth)[k];
+        for (int r = 0; r < nefc; r++) {
+          int st = state[r];
+          if (st == RCSB_QUADRATIC) s += EFC(RCSB_E_D)[r] * EFC(RCSB_E_AREF)[r] * WR(J)[r * nv + k];
+          else if (st == RCSB_LINEARNEG) s += EFC(RCSB_E_FLOSS)[r] * WR(J)[r * nv + k];
+          else if (st == RCSB_LINEARPOS) s -= EFC(RCSB_E_FLOSS)[r] * WR(J)[r * nv + k];
+        }
+        WR(qacc)[k] = s;
+      }
+      chol_factor(c, WR(H), WR(H) + nv * nv, nv);
+      chol_solve(c, WR(H), WR(H) + nv * nv, nv, WR(qacc), WR(tmp));
+      int changed = 0;
+      PFOR(r, nefc) {
+        real s = 0;
+        for (int k = 0; k < nv; k++) s += WR(J)[r * nv + k] * WR(qacc)[k];
+        real jar = s - EFC(RCSB_E_AREF)[r], D = EFC(RCSB_E_D)[r], force;
+        int type = etype[r], st;
+        if (type == RCSB_EQ) { st = RCSB_QUADRATIC; force = -D * jar; }
+        else if (type == RCSB_FRICTION_DOF) {
+          real f = EFC(RCSB_E_FLOSS)[r], R = EFC(RCSB_E_R)[r];
+          if (jar <= -R * f) { st = RCSB_LINEARNEG; force = f; }
+          else if (jar >= R * f) { st = RCSB_LINEARPOS; force = -f; }
+          else { st = RCSB_QUADRATIC; force = -D * jar; }
+        } else {
+          if (jar < 0) { st = RCSB_QUADRATIC; force = -D * jar; } else { st = RCSB_SATISFIED; force = 0; }
+        }
+        if (st != state[r]) changed = 1;
+        state[r] = st;
+        EFC(RCSB_E_JAR)[r] = jar;
+        EFC(RCSB_E_FORCE)[r] = force;
+      }
+      verified = !warp_any(changed);
+      RCSB_SYNC();
     }
-    if (c.lane == 0) WI(misc)[MI_SOLVER_ITER] = 1;
-    RCSB_SYNC();
-    return;
+    if (verified) {
+      PFOR(k, nv) {
+        real s = 0;
+        for (int r = 0; r < nefc; r++) s += WR(J)[r * nv + k] * EFC(RCSB_E_FORCE)[r];
+        WR(qfc)[k] = s;
+      }
+      if (c.lane == 0) WI(misc)[MI_SOLVER_ITER] = attempt;
+      RCSB_SYNC();
+      return;
+    }
   }
   compute_qacc_smooth(c);
   // warm start: keep qacc_warmstart only if its cost beats qacc_smooth's
