@@ -1,0 +1,46 @@
+// Execution context of one environment's warp, shared by every kernel variant (rcsb_variant.cuh).
+#pragma once
+#include "rcsb_warp.cuh"
+
+#ifdef RCSB_HOST_EMU
+struct Ctx {
+  const RcsbModel* md;  // model constants
+  real* w;              // real workspace
+  int* wi;              // int workspace
+  const real* verts;    // convex hull vertex pool
+  double* clk;          // simulation time + callback clocks (always double)
+  int lane;
+  int lockstep;
+};
+#define CMODEL(c) (*(c).md)
+#define CW(c) ((c).w)
+#define CWI(c) ((c).wi)
+#define CCLK(c) ((c).clk)
+#else
+// Device: the model sits at the start of the CTA's dynamic shared memory and every warp owns a workspace window in it.
+// Ctx carries 32-bit byte offsets into that window, and every access is formed from the rcsb_smem symbol, so the
+// compiler addresses shared memory directly (LDS/STS with 32-bit address arithmetic) in every function, inlined or
+// not, instead of falling back to generic 64-bit loads.
+extern __shared__ __align__(128) unsigned char rcsb_smem[];
+struct Ctx {
+  const real* verts;    // convex hull vertex pool (global memory, read-only)
+  uint32_t wb;          // this warp's real workspace (byte offset in shared memory)
+  uint32_t clkb;        // this warp's simulation time + callback clocks (always double)
+  uint32_t wib;         // this warp's int workspace
+  int lane;
+  int lockstep;         // fixed-substep launch: CTA barriers between stages keep the warps on the same code
+};
+#define CMODEL(c) (*(const RcsbModel*)rcsb_smem)
+#define CW(c) ((real*)(rcsb_smem + (c).wb))
+#define CWI(c) ((int*)(rcsb_smem + (c).wib))
+#define CCLK(c) ((double*)(rcsb_smem + (c).clkb))
+#endif
+
+// misc int slots in the workspace
+enum { MI_NCON = 0, MI_NEFC, MI_NE, MI_NF, MI_NL, MI_HAVE_L, MI_SOLVER_ITER, MI_WARN, MI_OVERFLOW, MI_PAD, MI_COUNT };
+
+#define WR(name) (CW(c) + LAY.o_##name)
+#define WI(name) (CWI(c) + LAY.oi_##name)
+#if defined(RCSB_STAGE_TIMING) && !defined(RCSB_HOST_EMU)
+extern __device__ unsigned long long rcsb_stage_cycles[16];
+#endif

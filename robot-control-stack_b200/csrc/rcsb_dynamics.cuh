@@ -7,47 +7,6 @@
 // vectors make every tree recursion except forward kinematics a sum over ancestor / descendant
 // sets, so those stages are flat parallel-fors over (body | dof | matrix entry) work items with
 // precompiled bit masks instead of serial tree walks.
-#pragma once
-#include "rcsb_warp.cuh"
-
-#ifdef RCSB_HOST_EMU
-struct Ctx {
-  const RcsbModel* md;  // model constants
-  real* w;              // real workspace
-  int* wi;              // int workspace
-  const real* verts;    // convex hull vertex pool
-  double* clk;          // simulation time + callback clocks (always double)
-  int lane;
-  int lockstep;
-};
-#define CMODEL(c) (*(c).md)
-#define CW(c) ((c).w)
-#define CWI(c) ((c).wi)
-#define CCLK(c) ((c).clk)
-#else
-// Device: the model sits at the start of the CTA's dynamic shared memory and every warp owns a workspace window in it.
-// Ctx carries 32-bit byte offsets into that window, and every access is formed from the rcsb_smem symbol, so the
-// compiler addresses shared memory directly (LDS/STS with 32-bit address arithmetic) in every function, inlined or
-// not, instead of falling back to generic 64-bit loads.
-extern __shared__ __align__(128) unsigned char rcsb_smem[];
-struct Ctx {
-  const real* verts;    // convex hull vertex pool (global memory, read-only)
-  uint32_t wb;          // this warp's real workspace (byte offset in shared memory)
-  uint32_t clkb;        // this warp's simulation time + callback clocks (always double)
-  uint32_t wib;         // this warp's int workspace
-  int lane;
-  int lockstep;         // fixed-substep launch: CTA barriers between stages keep the warps on the same code
-};
-#define CMODEL(c) (*(const RcsbModel*)rcsb_smem)
-#define CW(c) ((real*)(rcsb_smem + (c).wb))
-#define CWI(c) ((int*)(rcsb_smem + (c).wib))
-#define CCLK(c) ((double*)(rcsb_smem + (c).clkb))
-#endif
-#define WR(name) (CW(c) + m.o_##name)
-#define WI(name) (CWI(c) + m.oi_##name)
-
-// misc int slots in the workspace
-enum { MI_NCON = 0, MI_NEFC, MI_NE, MI_NF, MI_NL, MI_HAVE_L, MI_SOLVER_ITER, MI_WARN, MI_OVERFLOW, MI_PAD, MI_COUNT };
 
 // ------------------------------------------------------------------ dense Cholesky / triangular solves
 // A (n x n, row-major, shared memory) -> strictly-lower part holds L, dinv[j] = 1 / L[j][j]; A's diagonal is left
@@ -170,8 +129,8 @@ RCSB_DEV void st_kinematics(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
   real* q = WR(q);
   real* Rl = WR(bquat);            // scratch: local rotation [nb][9] then local translation [nb][3] (o_bquat holds 12*nb)
-  real* tl = Rl + 9 * m.nb;
-  PFOR(b, m.nb) {
+  real* tl = Rl + 9 * MD(nb);
+  PFOR(b, MD(nb)) {
     real* R = Rl + 9 * b;
     real* t = tl + 3 * b;
     if (m.b_jtype[b] == RCSB_JNT_FREE) {
@@ -207,7 +166,7 @@ RCSB_DEV void st_kinematics(const Ctx& c) {
     }
   }
   RCSB_SYNC();
-  for (int b = 0; b < m.nb; b++) {
+  for (int b = 0; b < MD(nb); b++) {
     const int p = m.b_parent[b];
     PFOR(e, 12) {
       if (e < 9) {
@@ -267,9 +226,9 @@ RCSB_DEV void body_com(const Ctx& c, int b, real* o) {
 }
 RCSB_DEV void st_com(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
-  PFOR(r, m.nroot) {
+  PFOR(r, MD(nroot)) {
     real s[3] = {0, 0, 0};
-    for (int b = 0; b < m.nb; b++)
+    for (int b = 0; b < MD(nb); b++)
       if (m.b_root[b] == r) {
         real o[3];
         body_com(c, b, o);
@@ -279,7 +238,7 @@ RCSB_DEV void st_com(const Ctx& c) {
     rc[0] = s[0] * m.r_invmass[r]; rc[1] = s[1] * m.r_invmass[r]; rc[2] = s[2] * m.r_invmass[r];
   }
   RCSB_SYNC();
-  PFOR(b, m.nb) {  // inertia about the tree COM, world axes
+  PFOR(b, MD(nb)) {  // inertia about the tree COM, world axes
     const real* R = WR(bmat) + 9 * b;
     const real* I = m.b_inertia[b];
     const real* rc = WR(rootcom) + 3 * m.b_root[b];
@@ -304,7 +263,7 @@ RCSB_DEV void st_com(const Ctx& c) {
     ci[6] = mass * d[0]; ci[7] = mass * d[1]; ci[8] = mass * d[2];
     ci[9] = mass;
   }
-  PFOR(j, m.nv) {  // motion axis of dof j about the tree COM
+  PFOR(j, MD(nv)) {  // motion axis of dof j about the tree COM
     int b = m.d_body[j];
     const real* rc = WR(rootcom) + 3 * m.b_root[b];
     const real* R = WR(bmat) + 9 * b;
@@ -362,12 +321,12 @@ RCSB_DEV void st_com(const Ctx& c) {
 // ------------------------------------------------------------------ composite inertia, mass matrix, factorisation
 RCSB_DEV void st_crb(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
-  int nv = m.nv;
-  PFOR(e, m.nb * 10) {
+  int nv = MD(nv);
+  PFOR(e, MD(nb) * 10) {
     int b = e / 10, k = e - 10 * b;
     real s = 0;
     uint32_t mask = m.b_descmask[b];
-    for (int d = b; d < m.nb; d++)
+    for (int d = b; d < MD(nb); d++)
       if ((mask >> d) & 1u) s += WR(cinert)[10 * d + k];
     WR(crb)[e] = s;
   }
@@ -390,14 +349,14 @@ RCSB_DEV void st_crb(const Ctx& c) {
     }
   }
   // the factorisation of M is deferred (ensure_chol_M copies M into the solver scratch): the all-equality path never needs it
-  if (c.lane == 0) CWI(c)[m.oi_misc + MI_HAVE_L] = 0;
+  if (c.lane == 0) CWI(c)[LAY.oi_misc + MI_HAVE_L] = 0;
   RCSB_SYNC();
 }
 
 // ------------------------------------------------------------------ velocity stage: bias, passive, gravity compensation
 RCSB_DEV void st_velocity(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
-  int nv = m.nv;
+  int nv = MD(nv);
   const real* v = WR(v);
   PFOR(j, nv) {
     real* cdd = WR(cdofdot) + 6 * j;
@@ -414,7 +373,7 @@ RCSB_DEV void st_velocity(const Ctx& c) {
       cross_motion(cdd, pre, WR(cdof) + 6 * j);
     }
   }
-  PFOR(b, m.nb) {
+  PFOR(b, MD(nb)) {
     real cv[6] = {0, 0, 0, 0, 0, 0};
     uint32_t mask = m.b_dofmask[b];
     for (int i = 0; i < nv; i++)
@@ -425,7 +384,7 @@ RCSB_DEV void st_velocity(const Ctx& c) {
     for (int k = 0; k < 6; k++) WR(cvel)[6 * b + k] = cv[k];
   }
   RCSB_SYNC();
-  PFOR(b, m.nb) {
+  PFOR(b, MD(nb)) {
     real ca[6] = {0, 0, 0, -m.gravity[0], -m.gravity[1], -m.gravity[2]};
     uint32_t mask = m.b_dofmask[b];
     for (int i = 0; i < nv; i++)
@@ -460,7 +419,7 @@ RCSB_DEV void st_velocity(const Ctx& c) {
     uint32_t mask = m.b_descmask[bj];
     const real* cd = WR(cdof) + 6 * j;
     real f[6] = {0, 0, 0, 0, 0, 0}, g[6] = {0, 0, 0, 0, 0, 0};
-    for (int b = bj; b < m.nb; b++)
+    for (int b = bj; b < MD(nb); b++)
       if ((mask >> b) & 1u) {
         const real* cf = WR(cfrc) + 6 * b;
         const real* gw = WR(cvel) + 6 * b;
@@ -670,8 +629,8 @@ RCSB_DEV_NOINLINE int mpr_penetration(const Ctx& c, const PairFrames& pf, real* 
 RCSB_DEV void add_contact(const Ctx& c, int& ncon, int g1, int g2, real dist, const real* pos, const real* normal,
                           real margin, real gap) {
   const RcsbModel& m = CMODEL(c);
-  if (ncon >= m.maxcon) {  // reduced layout: the full-capacity launch redoes this step; full layout: drop and count
-    if (c.lane == 0) WI(misc)[m.cap_reduced ? MI_OVERFLOW : MI_WARN] += 1;
+  if (ncon >= MD(maxcon)) {  // reduced layout: the full-capacity launch redoes this step; full layout: drop and count
+    if (c.lane == 0) WI(misc)[MD(cap_reduced) ? MI_OVERFLOW : MI_WARN] += 1;
     return;
   }
   if (c.lane == 0) {
@@ -753,7 +712,7 @@ RCSB_DEV void st_collision(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
   // ---- broad phase: bounding spheres about the local AABB centres (plane: signed distance), one pair per lane,
   //      survivors compacted in pair order
-  PFOR(g, m.ng) {  // bounding-volume centres for the broad phase
+  PFOR(g, MD(ng)) {  // bounding-volume centres for the broad phase
     int b = m.g_body[g];
     real* o = WR(gpos) + 3 * g;
     if (b < 0) copy3(o, m.g_bpos[g]);
@@ -769,9 +728,9 @@ RCSB_DEV void st_collision(const Ctx& c) {
   int* candA = (int*)WR(cand);  // candidate lists live in the stage-local union next to the geom centres
   int* candB = candA + RCSB_MAXCAND;
   int ncandA = 0;
-  for (int base = 0; base < m.npair; base += RCSB_NLANES) {
+  for (int base = 0; base < MD(npair); base += RCSB_NLANES) {
     int p = base + c.lane, hit = 0;
-    if (p < m.npair) {
+    if (p < MD(npair)) {
       int g1 = m.pair[p][0], g2 = m.pair[p][1];
       real margin = m.g_margin[g1] > m.g_margin[g2] ? m.g_margin[g1] : m.g_margin[g2];
       const real *a = WR(gpos) + 3 * g1, *b = WR(gpos) + 3 * g2;

@@ -5,44 +5,6 @@
 //   SimGripper set/get/reset                        /root/reference/src/sim/SimGripper.cpp:79-165
 //   RelativeActionSpace / GripperWrapper / RobotEnv /root/reference/python/rcs/envs/base.py:246-288,469-488,710-735
 //   RobotSimWrapper / GripperWrapperSim             /root/reference/python/rcs/envs/sim.py:49-76,125-131
-#pragma once
-#include "rcsb_solver.cuh"
-
-// op bits, executed in this order within one launch
-enum {
-  RCSB_OP_GRIPPER_RESET = 1 << 0,   // SimGripper::reset
-  RCSB_OP_SIM_RESET = 1 << 1,       // Sim::reset (mj_resetData + callback clocks)
-  RCSB_OP_ROBOT_RESET = 1 << 2,     // SimRobot::reset (set_joints_hard(q_home))
-  RCSB_OP_ENV_RESET_FLAGS = 1 << 3, // GripperWrapper.reset: _last_gripper_cmd = None
-  RCSB_OP_ACT_JOINTS_REL = 1 << 4,  // RelativeActionSpace (LAST_STEP) + RobotEnv.step dedupe + set_joint_position
-  RCSB_OP_ACT_JOINTS_ABS = 1 << 5,  // RobotEnv.step dedupe + set_joint_position
-  RCSB_OP_ACT_GRIPPER_BIN = 1 << 6, // GripperWrapper.action, binary
-  RCSB_OP_SET_JOINTS = 1 << 7,      // SimRobot::set_joint_position (direct API, no dedupe)
-  RCSB_OP_SET_GRIPPER = 1 << 8,     // SimGripper::set_normalized_width
-  RCSB_OP_SET_JOINTS_HARD = 1 << 9, // SimRobot::set_joints_hard
-  RCSB_OP_STEP_K = 1 << 10,         // Sim::step(k)
-  RCSB_OP_STEP_CONV = 1 << 11,      // Sim::step_until_convergence
-  RCSB_OP_OBS = 1 << 12,            // RobotEnv.get_obs + wrappers' observation/info
-};
-enum { RCSB_OBS_DIM = 22, RCSB_INFO_DIM = 8 };
-// obs row: tquat[7] joints[7] xyzrpy[6] gripper[1] gripper_width[1]
-// info row: collision, ik_success, is_sim_converged, is_grasped, truncated, robot_collision, gripper_collision, conv_steps
-
-struct RcsbLaunch {
-  int N, env_offset;
-  unsigned ops;
-  int k, max_convergence_steps;
-  int lockstep;  // fixed-substep launches: 0 no CTA barriers, 1 one per stage, 2 one per physics step
-  int phase;     // 0: every environment, reduced or full layout; 1: full layout, only the environments in overflow_list
-  int* overflow_list;   // [N] environments the reduced layout could not finish (phase 0 appends, phase 1 consumes)
-  int* overflow_count;
-  const real* act_joints;   // [N][njoints]
-  const real* act_gripper;  // [N]
-  const unsigned char* mask;  // optional [N]: 0 = leave this env untouched
-  real max_mov, jlow[RCSB_MAXJ], jhigh[RCSB_MAXJ];
-  real* obs;   // [N][RCSB_OBS_DIM] or null
-  int* info;   // [N][RCSB_INFO_DIM] or null
-};
 
 // ------------------------------------------------------------------ Pose math (xyz + quat xyzw), Eigen semantics
 struct Quat { real x, y, z, w; };
@@ -148,10 +110,10 @@ RCSB_DEV void robot_cartesian_position(const Ctx& c, real* pose7) {
 // ------------------------------------------------------------------ state row <-> workspace
 RCSB_DEV void load_env(const Ctx& c, const real* sr, const double* sd, const int* si) {
   const RcsbModel& m = CMODEL(c);
-  PFOR(i, m.nsr) { CW(c)[i] = sr[i]; }
+  PFOR(i, LAY.nsr) { CW(c)[i] = sr[i]; }
   PFOR(i, RCSB_D_TAIL) { CCLK(c)[i] = sd[i]; }
-  PFOR(i, RCSB_I_TAIL) { CWI(c)[m.oi_misc + MI_COUNT + i] = si[i]; }
-  PFOR(i, MI_COUNT) { CWI(c)[m.oi_misc + i] = 0; }
+  PFOR(i, RCSB_I_TAIL) { CWI(c)[LAY.oi_misc + MI_COUNT + i] = si[i]; }
+  PFOR(i, MI_COUNT) { CWI(c)[LAY.oi_misc + i] = 0; }
   PFOR(i, 2) { WR(sepcache)[4 * i] = -1; }
   RCSB_SYNC();
 }
@@ -165,15 +127,15 @@ RCSB_DEV void store_env(const Ctx& c, real* sr, double* sd, int* si) {
     RI(RCSB_I_WARN) += WI(misc)[MI_WARN];
   }
   RCSB_SYNC();
-  PFOR(i, m.nsr) { sr[i] = CW(c)[i]; }
+  PFOR(i, LAY.nsr) { sr[i] = CW(c)[i]; }
   PFOR(i, RCSB_D_TAIL) { sd[i] = CCLK(c)[i]; }
-  PFOR(i, RCSB_I_TAIL) { si[i] = CWI(c)[m.oi_misc + MI_COUNT + i]; }
+  PFOR(i, RCSB_I_TAIL) { si[i] = CWI(c)[LAY.oi_misc + MI_COUNT + i]; }
 }
 
 // ------------------------------------------------------------------ device-layer ops
 RCSB_DEV void op_set_joint_position(const Ctx& c, const real* qd) {  // SimRobot.cpp:123-131
   const RcsbModel& m = CMODEL(c);
-  PFOR(i, m.rb_njoints) {
+  PFOR(i, MD(rb_njoints)) {
     RS(RCSB_S_TARGET + i) = qd[i];
     RS(RCSB_S_PREV + i) = WR(q)[m.rb_qadr[i]];
     WR(ctrl)[m.rb_act[i]] = qd[i];
@@ -194,7 +156,7 @@ RCSB_DEV void op_set_gripper(const Ctx& c, real width) {  // SimGripper.cpp:79-9
 RCSB_DEV void run_env_pre_ops(const Ctx& c, const RcsbLaunch& L, int env) {
   const RcsbModel& m = CMODEL(c);
   const unsigned ops = L.ops;
-  if ((ops & RCSB_OP_GRIPPER_RESET) && m.gr_enabled) {  // SimGripper.cpp:158-163
+  if ((ops & RCSB_OP_GRIPPER_RESET) && MD(gr_enabled)) {  // SimGripper.cpp:158-163
     if (c.lane == 0) {
       RS(RCSB_S_GLCW) = 0; RS(RCSB_S_GLW) = 0; RI(RCSB_I_G_MOVING) = 0; RI(RCSB_I_G_COLLISION) = 0;
       WR(q)[m.gr_qadr] = m.gr_max_joint;
@@ -212,20 +174,20 @@ RCSB_DEV void run_env_pre_ops(const Ctx& c, const RcsbLaunch& L, int env) {
     RCSB_SYNC();
   }
   if (ops & RCSB_OP_ROBOT_RESET) {  // SimRobot.cpp:193-205
-    PFOR(i, m.rb_njoints) { WR(q)[m.rb_qadr[i]] = m.rb_q_home[i]; WR(ctrl)[m.rb_act[i]] = m.rb_q_home[i]; }
+    PFOR(i, MD(rb_njoints)) { WR(q)[m.rb_qadr[i]] = m.rb_q_home[i]; WR(ctrl)[m.rb_act[i]] = m.rb_q_home[i]; }
     RCSB_SYNC();
   }
   if (ops & RCSB_OP_SET_JOINTS_HARD) {
-    PFOR(i, m.rb_njoints) {
-      real v = L.act_joints[(size_t)env * m.rb_njoints + i];
+    PFOR(i, MD(rb_njoints)) {
+      real v = L.act_joints[(size_t)env * MD(rb_njoints) + i];
       WR(q)[m.rb_qadr[i]] = v; WR(ctrl)[m.rb_act[i]] = v;
     }
     RCSB_SYNC();
   }
   if (ops & (RCSB_OP_ACT_JOINTS_REL | RCSB_OP_ACT_JOINTS_ABS)) {
     real* jt = WR(tmp);
-    PFOR(i, m.rb_njoints) {
-      real a = L.act_joints[(size_t)env * m.rb_njoints + i];
+    PFOR(i, MD(rb_njoints)) {
+      real a = L.act_joints[(size_t)env * MD(rb_njoints) + i];
       if (ops & RCSB_OP_ACT_JOINTS_REL) {  // base.py:475-488
         real lim = a < -L.max_mov ? -L.max_mov : (a > L.max_mov ? L.max_mov : a);
         real v = WR(q)[m.rb_qadr[i]] + lim;
@@ -234,7 +196,7 @@ RCSB_DEV void run_env_pre_ops(const Ctx& c, const RcsbLaunch& L, int env) {
       jt[i] = a;
     }
     RCSB_SYNC();
-    if ((ops & RCSB_OP_ACT_GRIPPER_BIN) && m.gr_enabled) {  // base.py:721-735
+    if ((ops & RCSB_OP_ACT_GRIPPER_BIN) && MD(gr_enabled)) {  // base.py:721-735
       real g = rint(L.act_gripper[env]);
       g = g < 0 ? (real)0 : (g > 1 ? (real)1 : g);
       op_set_gripper(c, g == 0 ? (real)0 : (real)1);
@@ -242,22 +204,22 @@ RCSB_DEV void run_env_pre_ops(const Ctx& c, const RcsbLaunch& L, int env) {
       RCSB_SYNC();
     }
     int changed = !RI(RCSB_I_HAVE_PREV_ACTION);  // base.py:268-272: not allclose(a, prev, atol=1e-3, rtol=0)
-    for (int i = 0; i < m.rb_njoints; i++)
+    for (int i = 0; i < MD(rb_njoints); i++)
       if (!(r_abs(jt[i] - RS(RCSB_S_PREVACT + i)) <= (real)1e-3)) changed = 1;
     RCSB_SYNC();
     if (changed) op_set_joint_position(c, jt);
-    PFOR(i, m.rb_njoints) { RS(RCSB_S_PREVACT + i) = jt[i]; }
+    PFOR(i, MD(rb_njoints)) { RS(RCSB_S_PREVACT + i) = jt[i]; }
     if (c.lane == 0) RI(RCSB_I_HAVE_PREV_ACTION) = 1;
     RCSB_SYNC();
-  } else if ((ops & RCSB_OP_ACT_GRIPPER_BIN) && m.gr_enabled) {
+  } else if ((ops & RCSB_OP_ACT_GRIPPER_BIN) && MD(gr_enabled)) {
     real g = rint(L.act_gripper[env]);
     g = g < 0 ? (real)0 : (g > 1 ? (real)1 : g);
     op_set_gripper(c, g == 0 ? (real)0 : (real)1);
     if (c.lane == 0) RS(RCSB_S_GCMD) = g;
     RCSB_SYNC();
   }
-  if (ops & RCSB_OP_SET_JOINTS) op_set_joint_position(c, L.act_joints + (size_t)env * m.rb_njoints);
-  if ((ops & RCSB_OP_SET_GRIPPER) && m.gr_enabled) op_set_gripper(c, L.act_gripper[env]);
+  if (ops & RCSB_OP_SET_JOINTS) op_set_joint_position(c, L.act_joints + (size_t)env * MD(rb_njoints));
+  if ((ops & RCSB_OP_SET_GRIPPER) && MD(gr_enabled)) op_set_gripper(c, L.act_gripper[env]);
 }
 // CTA barriers a lockstep warp owes for `nsteps` physics steps it does not run
 RCSB_DEV void skip_step_barriers(const Ctx& c, int nsteps) {
@@ -314,16 +276,16 @@ RCSB_DEV void run_env_program(const Ctx& c, const RcsbLaunch& L, int env) {
     if (L.obs) {
       real* o = L.obs + (size_t)env * RCSB_OBS_DIM;
       for (int i = 0; i < 7; i++) o[i] = pose[i];
-      for (int i = 0; i < 7; i++) o[7 + i] = i < m.rb_njoints ? WR(q)[m.rb_qadr[i]] : (real)0;
+      for (int i = 0; i < 7; i++) o[7 + i] = i < MD(rb_njoints) ? WR(q)[m.rb_qadr[i]] : (real)0;
       pose_xyzrpy(pose, o + 14);
-      real gw = m.gr_enabled ? gripper_width(c) : (real)0;
+      real gw = MD(gr_enabled) ? gripper_width(c) : (real)0;
       o[20] = RS(RCSB_S_GCMD) < 0 ? (real)1 : RS(RCSB_S_GCMD);
       o[21] = gw;
     }
     if (L.info) {
       int* f = L.info + (size_t)env * RCSB_INFO_DIM;
-      real gw = m.gr_enabled ? gripper_width(c) : (real)0;
-      int rc = RI(RCSB_I_COLLISION), gc = m.gr_enabled ? RI(RCSB_I_G_COLLISION) : 0;
+      real gw = MD(gr_enabled) ? gripper_width(c) : (real)0;
+      int rc = RI(RCSB_I_COLLISION), gc = MD(gr_enabled) ? RI(RCSB_I_G_COLLISION) : 0;
       f[0] = rc || gc;                       // envs/sim.py:61,127-128
       f[1] = RI(RCSB_I_IK_SUCCESS);
       f[2] = RI(RCSB_I_CONVERGED);

@@ -4,8 +4,6 @@
 // computeFrameJacobian LOCAL, log6, Jlog6, 6x6 LDLT, integrate). One environment per thread: the
 // loop is a ~100-iteration serial chain of tiny dense operations on a 6 x nq Jacobian, so the
 // parallelism is across environments; the 6x6 solves are far too small for tensor-core tiles.
-#pragma once
-#include "rcsb_env.cuh"
 
 enum { IK_SCRATCH_REALS = 8, IK_MAXQ = 9 };
 
@@ -214,8 +212,8 @@ RCSB_DEV void ik_env(const RcsbModel* sm, real* /*scratch*/, int /*lane*/, int e
   const RcsbModel& m = *sm;
   const int nj = m.rb_njoints, nqm = m.rb_ik_nq < IK_MAXQ ? m.rb_ik_nq : IK_MAXQ;
   real q0l[RCSB_MAXJ], q[IK_MAXQ];
-  real* row = sr ? sr + (size_t)env * m.nsr : nullptr;
-  for (int i = 0; i < nj; i++) q0l[i] = apply ? row[m.o_q + m.rb_qadr[i]] : q0[(size_t)env * nj + i];
+  real* row = sr ? sr + (size_t)env * m.lay.nsr : nullptr;
+  for (int i = 0; i < nj; i++) q0l[i] = apply ? row[m.lay.o_q + m.rb_qadr[i]] : q0[(size_t)env * nj + i];
   int it = 0;
   int ok = ik_solve(m, pose + (size_t)env * 7, q0l, nj, q, &it);
   if (iters) iters[env] = it;
@@ -226,9 +224,9 @@ RCSB_DEV void ik_env(const RcsbModel* sm, real* /*scratch*/, int /*lane*/, int e
     irow[RCSB_I_IK_SUCCESS] = ok;
     if (ok) {  // set_joint_position(joint_vals)
       for (int i = 0; i < nj; i++) {
-        row[m.o_rcs + RCSB_S_TARGET + i] = q[i];
-        row[m.o_rcs + RCSB_S_PREV + i] = row[m.o_q + m.rb_qadr[i]];
-        row[m.o_ctrl + m.rb_act[i]] = q[i];
+        row[m.lay.o_rcs + RCSB_S_TARGET + i] = q[i];
+        row[m.lay.o_rcs + RCSB_S_PREV + i] = row[m.lay.o_q + m.rb_qadr[i]];
+        row[m.lay.o_ctrl + m.rb_act[i]] = q[i];
       }
       irow[RCSB_I_MOVING] = 1;
       irow[RCSB_I_ARRIVED] = 0;

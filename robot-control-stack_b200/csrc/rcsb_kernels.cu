@@ -17,9 +17,8 @@
 #include <vector>
 
 #include "../../include/rcsb.h"
-#include "rcsb_env.cuh"
-#include "rcsb_ik.cuh"
 #include "rcsb_layout.h"
+#include "rcsb_ctx.cuh"
 
 // ------------------------------------------------------------------ TMA bulk copy helpers (sm_90+/sm_100a PTX)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -53,17 +52,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 #define RCSB_MAX_WARPS 28
 #endif
 
-__device__ __forceinline__ Ctx make_ctx(const RcsbModel* sm, const real* verts, size_t ws_bytes) {
-  int warp = threadIdx.x >> 5;
-  Ctx c;
-  c.wb = (uint32_t)(RCSB_SMEM_HEADER + (size_t)warp * ws_bytes);
-  c.clkb = c.wb + (uint32_t)((size_t)sm->ws_reals * sizeof(real));
-  c.wib = c.clkb + (uint32_t)((size_t)sm->ws_doubles * sizeof(double));
-  c.verts = verts;
-  c.lane = threadIdx.x & 31;
-  c.lockstep = 0;
-  return c;
-}
 __device__ __forceinline__ const RcsbModel* stage_model(const RcsbModel* gm) {
   RcsbModel* sm = (RcsbModel*)rcsb_smem;
   uint64_t* bar = (uint64_t*)(rcsb_smem + RCSB_MODEL_BYTES);
@@ -80,63 +68,61 @@ __device__ __forceinline__ const RcsbModel* stage_model(const RcsbModel* gm) {
   return sm;
 }
 
-// ------------------------------------------------------------------ the per-launch program kernel
-__global__ void __launch_bounds__(RCSB_MAX_WARPS * 32, 1)
-rcsb_k_run(const RcsbModel* __restrict__ gm, const real* __restrict__ verts, real* __restrict__ sr, double* __restrict__ sd,
-           int* __restrict__ si, RcsbLaunch L, int* __restrict__ counter, size_t ws_bytes) {
-  if (L.phase == 1 && *L.overflow_count == 0) return;  // the common case: nothing outgrew the reduced layout
-  const RcsbModel* sm = stage_model(gm);
-  Ctx c = make_ctx(sm, verts, ws_bytes);
-  if ((L.ops & RCSB_OP_STEP_K) && L.phase == 0) {
-    // Fixed-substep launch: static env -> warp mapping. Every warp of the CTA runs the same number of rounds and
-    // hits exactly L.k * RCSB_STAGE_BARRIERS CTA barriers per round (inside run_env_program, or here when it has no environment), which
-    // keeps the warps in the same stage of the step so that they share instruction-cache lines.
-    c.lockstep = L.lockstep;
-    const int nbar = L.lockstep == 1 ? L.k * RCSB_STAGE_BARRIERS : (L.lockstep == 2 ? L.k : 0);
-    const int W = blockDim.x >> 5, per_round = gridDim.x * W;
-    const int rounds = (L.N + per_round - 1) / per_round;
-    for (int r = 0; r < rounds; r++) {
-      int env = r * per_round + (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
-      bool valid = env < L.N && !(L.mask && !L.mask[env]);
-      if (valid) {
-        load_env(c, sr + (size_t)env * sm->nsr, sd + (size_t)env * RCSB_D_TAIL, si + (size_t)env * RCSB_I_TAIL);
-        run_env_program(c, L, env);
-        store_env(c, sr + (size_t)env * sm->nsr, sd + (size_t)env * RCSB_D_TAIL, si + (size_t)env * RCSB_I_TAIL);
-        __syncwarp();
-      } else {
-        for (int i = 0; i < nbar; i++) __syncthreads();
-      }
-    }
-    return;
+
+// ------------------------------------------------------------------ kernel variants
+#ifdef RCSB_STAGE_TIMING
+__device__ unsigned long long rcsb_stage_cycles[16];
+#endif
+#define RCSB_VARIANT_NS rcsb_generic
+#define RCSB_KERNEL rcsb_k_run
+#include "rcsb_variant.cuh"
+#undef RCSB_VARIANT_NS
+#undef RCSB_KERNEL
+
+#ifndef RCSB_NO_FIXED_VARIANTS
+// fr3_empty_world (FR3 + Franka hand, no free bodies): reduced (1 contact, 8 rows) and full (6 contacts, 28 rows) layouts
+#define RCSB_SHAPE_FR3(maxcon, maxefc, reduced) {9, 9, 8, 9, 24, 182, 1, 1, 1, maxcon, maxefc, 7, 1, 1, 5, reduced, 1}
+#define RCSB_VARIANT_NS rcsb_fr3_reduced
+#define RCSB_KERNEL rcsb_k_run_fr3_reduced
+#define RCSB_FIXED_SHAPE RCSB_SHAPE_FR3(1, 8, 1)
+#include "rcsb_variant.cuh"
+#undef RCSB_VARIANT_NS
+#undef RCSB_KERNEL
+#undef RCSB_FIXED_SHAPE
+#define RCSB_VARIANT_NS rcsb_fr3_full
+#define RCSB_KERNEL rcsb_k_run_fr3_full
+#define RCSB_FIXED_SHAPE RCSB_SHAPE_FR3(6, 28, 0)
+#include "rcsb_variant.cuh"
+#undef RCSB_VARIANT_NS
+#undef RCSB_KERNEL
+#undef RCSB_FIXED_SHAPE
+#endif
+
+typedef void (*rcsb_launch_fn)(int, int, size_t, cudaStream_t, const RcsbModel*, const real*, real*, double*, int*, const RcsbLaunch&,
+                               int*, size_t);
+typedef cudaError_t (*rcsb_smem_fn)(size_t);
+struct RcsbVariant { const char* name; int fixed; RcsbShape shape; rcsb_launch_fn launch; rcsb_smem_fn set_smem; };
+static bool shape_equal(const RcsbShape& a, const RcsbShape& b) { return memcmp(&a, &b, sizeof(RcsbShape)) == 0; }
+// the most specialised variant compiled for this model's shape (the generic one always matches)
+static RcsbVariant pick_variant(const RcsbModel& h) {
+  RcsbShape s = rcsb_model_shape(&h);
+  const char* force = getenv("RCSB_VARIANT");  // "generic" disables the fixed-shape kernels (testing / tuning)
+  if (!(force && !strcmp(force, "generic"))) {
+#ifndef RCSB_NO_FIXED_VARIANTS
+    if (shape_equal(s, rcsb_fr3_reduced::shape())) return {"fr3_reduced", 1, s, rcsb_fr3_reduced::launch, rcsb_fr3_reduced::set_smem};
+    if (shape_equal(s, rcsb_fr3_full::shape())) return {"fr3_full", 1, s, rcsb_fr3_full::launch, rcsb_fr3_full::set_smem};
+#endif
   }
-  if (L.phase == 1) {  // environments the reduced layout handed over: dynamic scheduling over the overflow list
-    const int n = *L.overflow_count;
-    for (;;) {
-      int i = 0;
-      if (c.lane == 0) i = atomicAdd(counter, 1);
-      i = __shfl_sync(0xffffffffu, i, 0);
-      if (i >= n) break;
-      int env = L.overflow_list[i];
-      load_env(c, sr + (size_t)env * sm->nsr, sd + (size_t)env * RCSB_D_TAIL, si + (size_t)env * RCSB_I_TAIL);
-      run_env_program(c, L, env);
-      store_env(c, sr + (size_t)env * sm->nsr, sd + (size_t)env * RCSB_D_TAIL, si + (size_t)env * RCSB_I_TAIL);
-      __syncwarp();
-    }
-    return;
-  }
-  for (;;) {
-    int env = 0;
-    if (c.lane == 0) env = atomicAdd(counter, 1);
-    env = __shfl_sync(0xffffffffu, env, 0);
-    if (env >= L.N) break;
-    if (L.mask && !L.mask[env]) continue;
-    load_env(c, sr + (size_t)env * sm->nsr, sd + (size_t)env * RCSB_D_TAIL, si + (size_t)env * RCSB_I_TAIL);
-    run_env_program(c, L, env);
-    store_env(c, sr + (size_t)env * sm->nsr, sd + (size_t)env * RCSB_D_TAIL, si + (size_t)env * RCSB_I_TAIL);
-    __syncwarp();
-  }
+  return {"generic", 0, s, rcsb_generic::launch, rcsb_generic::set_smem};
 }
 
+// IK kernel: one environment per thread
+#define MD(f) (m.f)
+#define LAY (m.lay)
+namespace rcsb_generic {
+#include "rcsb_ik.cuh"
+}
+using rcsb_generic::ik_env;
 // Pin::inverse for every environment, one environment per thread (rcsb_ik.cuh)
 __global__ void __launch_bounds__(128)
 rcsb_k_ik(const RcsbModel* __restrict__ gm, const real* __restrict__ pose, const real* __restrict__ q0, real* __restrict__ q_out,
@@ -145,6 +131,8 @@ rcsb_k_ik(const RcsbModel* __restrict__ gm, const real* __restrict__ pose, const
   for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < N; env += gridDim.x * blockDim.x)
     ik_env(sm, nullptr, 0, env, pose, q0, q_out, success, iters, apply, sr, si);
 }
+#undef MD
+#undef LAY
 
 // ------------------------------------------------------------------ host side
 static thread_local std::string g_err;
@@ -176,6 +164,7 @@ struct rcsb_batch {
   int* d_overflow = nullptr;  // [n] overflow list
   int warps = 0, grid = 0, lockstep = 1;
   size_t smem = 0, ws_bytes = 0;
+  RcsbVariant var, var_full;          // kernel variants of the two phases
   int warps_full = 0, grid_full = 0;  // phase 1 (full layout) launch shape when a reduced layout exists
   size_t smem_full = 0, ws_bytes_full = 0;
   // staging for the host-buffer path
@@ -221,7 +210,7 @@ int rcsb_model_set_mesh_vertices(rcsb_model* m, const double* xyz, int nvert) {
 }
 int rcsb_model_finalize(rcsb_model* m) {
   if (rcsb_model_finalize_layout(&m->h) != 0) return fail(RCSB_ERR_MODEL, "model dimensions out of range");
-  if ((m->h.nsr * sizeof(real)) % 16 != 0) return fail(RCSB_ERR_MODEL, "state row is not 16-byte granular");
+  if ((m->h.lay.nsr * sizeof(real)) % 16 != 0) return fail(RCSB_ERR_MODEL, "state row is not 16-byte granular");
   m->h.cap_reduced = 0;
   m->has_reduced = rcsb_model_make_reduced(&m->h, &m->hr) != 0;
   if (m->has_reduced) {
@@ -259,7 +248,7 @@ int rcsb_model_upload(rcsb_model* m, int device) {
 }
 int rcsb_model_dims(const rcsb_model* m, int* nsr, int* nsd, int* nsi, int* obs_dim, int* info_dim) {
   if (!m->finalized) return fail(RCSB_ERR_MODEL, "rcsb_model_finalize not called");
-  if (nsr) *nsr = m->h.nsr;
+  if (nsr) *nsr = m->h.lay.nsr;
   if (nsd) *nsd = RCSB_D_TAIL;
   if (nsi) *nsi = RCSB_I_TAIL;
   if (obs_dim) *obs_dim = RCSB_OBS_DIM;
@@ -268,11 +257,11 @@ int rcsb_model_dims(const rcsb_model* m, int* nsr, int* nsd, int* nsi, int* obs_
 }
 int rcsb_model_offsets(const rcsb_model* m, int* o_qpos, int* o_qvel, int* o_ctrl, int* o_warm, int* o_tail) {
   if (!m->finalized) return fail(RCSB_ERR_MODEL, "rcsb_model_finalize not called");
-  if (o_qpos) *o_qpos = m->h.o_q;
-  if (o_qvel) *o_qvel = m->h.o_v;
-  if (o_ctrl) *o_ctrl = m->h.o_ctrl;
-  if (o_warm) *o_warm = m->h.o_warm;
-  if (o_tail) *o_tail = m->h.o_rcs;
+  if (o_qpos) *o_qpos = m->h.lay.o_q;
+  if (o_qvel) *o_qvel = m->h.lay.o_v;
+  if (o_ctrl) *o_ctrl = m->h.lay.o_ctrl;
+  if (o_warm) *o_warm = m->h.lay.o_warm;
+  if (o_tail) *o_tail = m->h.lay.o_rcs;
   return RCSB_OK;
 }
 
@@ -305,8 +294,9 @@ rcsb_batch* rcsb_batch_new(rcsb_model* m, int n_envs, void* sr, void* sd, void* 
   bool ok = shape(m->has_reduced ? m->hr : m->h, b->ws_bytes, b->warps, b->smem, b->grid);
   if (ok && m->has_reduced) ok = shape(m->h, b->ws_bytes_full, b->warps_full, b->smem_full, b->grid_full);
   if (!ok) { fail(RCSB_ERR_MODEL, "workspace does not fit in shared memory"); delete b; return nullptr; }
-  size_t smem_max = b->smem > b->smem_full ? b->smem : b->smem_full;
-  if (cudaFuncSetAttribute(rcsb_k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess ||
+  b->var = pick_variant(m->has_reduced ? m->hr : m->h);
+  b->var_full = pick_variant(m->h);
+  if (b->var.set_smem(b->smem) != cudaSuccess || (m->has_reduced && b->var_full.set_smem(b->smem_full) != cudaSuccess) ||
       cudaFuncSetAttribute(rcsb_k_ik, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCSB_SMEM_HEADER) != cudaSuccess ||
       cudaMalloc(&b->d_counter, 4 * sizeof(int)) != cudaSuccess || cudaMalloc(&b->d_overflow, (size_t)n_envs * sizeof(int)) != cudaSuccess) {
     fail(RCSB_ERR_CUDA, std::string("batch setup: ") + cudaGetErrorString(cudaGetLastError()));
@@ -364,14 +354,14 @@ int rcsb_batch_run(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps
   CUDA_OK(cudaMemsetAsync(b->d_counter, 0, 4 * sizeof(int), b->stream));
   L.phase = 0; L.overflow_list = b->d_overflow; L.overflow_count = b->d_counter + 2;
   const bool two = b->m->has_reduced;
-  rcsb_k_run<<<b->grid, b->warps * 32, b->smem, b->stream>>>(two ? b->m->d_model_r : b->m->d_model, b->m->d_verts, b->sr, b->sd,
-                                                            b->si, L, b->d_counter, b->ws_bytes);
+  b->var.launch(b->grid, b->warps * 32, b->smem, b->stream, two ? b->m->d_model_r : b->m->d_model, b->m->d_verts, b->sr, b->sd, b->si,
+                L, b->d_counter, b->ws_bytes);
   g_launches++;
   CUDA_OK(cudaGetLastError());
   if (two && (ops & (RCSB_OP_STEP_K | RCSB_OP_STEP_CONV))) {  // finishes the environments that outgrew the reduced layout
     L.phase = 1; L.lockstep = 0;
-    rcsb_k_run<<<b->grid_full, b->warps_full * 32, b->smem_full, b->stream>>>(b->m->d_model, b->m->d_verts, b->sr, b->sd, b->si, L,
-                                                                             b->d_counter + 1, b->ws_bytes_full);
+    b->var_full.launch(b->grid_full, b->warps_full * 32, b->smem_full, b->stream, b->m->d_model, b->m->d_verts, b->sr, b->sd, b->si, L,
+                       b->d_counter + 1, b->ws_bytes_full);
     g_launches++;
     CUDA_OK(cudaGetLastError());
   }
@@ -380,7 +370,7 @@ int rcsb_batch_run(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps
 
 int rcsb_batch_init_state(rcsb_batch* b) {
   CUDA_OK(cudaSetDevice(b->m->device));
-  CUDA_OK(cudaMemsetAsync(b->sr, 0, (size_t)b->n * b->m->h.nsr * sizeof(real), b->stream));
+  CUDA_OK(cudaMemsetAsync(b->sr, 0, (size_t)b->n * b->m->h.lay.nsr * sizeof(real), b->stream));
   CUDA_OK(cudaMemsetAsync(b->sd, 0, (size_t)b->n * RCSB_D_TAIL * sizeof(double), b->stream));
   std::vector<int> row(RCSB_I_TAIL, 0), all((size_t)b->n * RCSB_I_TAIL);
   row[RCSB_I_IK_SUCCESS] = 1;  // SimRobotState::ik_success = true (SimRobot.h:53)

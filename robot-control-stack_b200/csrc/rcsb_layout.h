@@ -71,20 +71,23 @@ static inline int rcsb_model_set_field(RcsbModel* m, const char* name, const voi
 //             candidate lists | cdofdot cvel cfrc
 //   region S  solver / integrator scratch, first written after make_constraint -> aliases K and U
 //   persistent across the step: M, force vectors, contacts, constraint rows
-static inline int rcsb_model_finalize_layout(RcsbModel* m) {
-  if (m->nq <= 0 || m->nq > RCSB_MAXQ || m->nv <= 0 || m->nv > RCSB_MAXV || m->nu > RCSB_MAXU || m->nb > RCSB_MAXB ||
-      m->ng > RCSB_MAXG || m->npair > RCSB_MAXPAIR || m->nt > RCSB_MAXT || m->neq > RCSB_MAXEQ ||
-      m->nroot > RCSB_MAXROOT || m->rb_njoints > RCSB_MAXJ || m->maxcon < 1 || m->maxefc < 1)
-    return -1;
-  int nq = m->nq, nv = m->nv, nu = m->nu, nb = m->nb, o = 0;
-#define RCSB_ALLOC(field, n) do { m->field = o; o += (n); } while (0)
+#ifdef __CUDACC__
+#define RCSB_HD __host__ __device__
+#else
+#define RCSB_HD
+#endif
+RCSB_HD constexpr RcsbLayout rcsb_make_layout(const RcsbShape& s) {
+  RcsbLayout y = {};
+  const int nq = s.nq, nv = s.nv, nu = s.nu, nb = s.nb;
+  int o = 0;
+#define RCSB_ALLOC(field, n) do { y.field = o; o += (n); } while (0)
 #define RCSB_MAX(a, b) ((a) > (b) ? (a) : (b))
   RCSB_ALLOC(o_q, nq); RCSB_ALLOC(o_v, nv); RCSB_ALLOC(o_ctrl, nu); RCSB_ALLOC(o_warm, nv);
   RCSB_ALLOC(o_rcs, RCSB_S_TAIL);
-  m->nsr = o;
-  m->o_site = m->o_rcs + RCSB_S_SITEPOS;
+  y.nsr = o;
+  y.o_site = y.o_rcs + RCSB_S_SITEPOS;
   const int k_begin = o;
-  RCSB_ALLOC(o_bpos, 3 * nb); RCSB_ALLOC(o_bmat, 9 * nb); RCSB_ALLOC(o_rootcom, 3 * m->nroot);
+  RCSB_ALLOC(o_bpos, 3 * nb); RCSB_ALLOC(o_bmat, 9 * nb); RCSB_ALLOC(o_rootcom, 3 * s.nroot);
   RCSB_ALLOC(o_cinert, 10 * nb); RCSB_ALLOC(o_cdof, 6 * nv);
   const int u_begin = o;
   int u_end = u_begin;
@@ -92,7 +95,7 @@ static inline int rcsb_model_finalize_layout(RcsbModel* m) {
   u_end = RCSB_MAX(u_end, o); o = u_begin;
   RCSB_ALLOC(o_crb, 10 * nb); RCSB_ALLOC(o_crbbuf, 6 * nv);
   u_end = RCSB_MAX(u_end, o); o = u_begin;
-  RCSB_ALLOC(o_gpos, 3 * m->ng); RCSB_ALLOC(o_cand, (2 * RCSB_MAXCAND * (int)sizeof(int) + (int)sizeof(real) - 1) / (int)sizeof(real));
+  RCSB_ALLOC(o_gpos, 3 * s.ng); RCSB_ALLOC(o_cand, (2 * RCSB_MAXCAND * (int)sizeof(int) + (int)sizeof(real) - 1) / (int)sizeof(real));
   u_end = RCSB_MAX(u_end, o); o = u_begin;
   RCSB_ALLOC(o_cdofdot, 6 * nv); RCSB_ALLOC(o_cvel, 6 * nb); RCSB_ALLOC(o_cfrc, 6 * nb);
   u_end = RCSB_MAX(u_end, o);
@@ -101,27 +104,40 @@ static inline int rcsb_model_finalize_layout(RcsbModel* m) {
   RCSB_ALLOC(o_H, nv * nv + nv); RCSB_ALLOC(o_L, nv * nv + nv);
   RCSB_ALLOC(o_grad, nv); RCSB_ALLOC(o_search, nv); RCSB_ALLOC(o_Ma, nv); RCSB_ALLOC(o_Mv, nv);
   RCSB_ALLOC(o_tmp, RCSB_MAX(nv, RCSB_MAXJ) + 2);  // triangular-solve scratch (host emulation), action staging
-  RCSB_ALLOC(o_conehess, 9 * m->maxcon);
-  RCSB_ALLOC(o_noslip, (nv + 2 * m->maxcon) * nv + nv + 4 * m->maxcon);
+  RCSB_ALLOC(o_conehess, 9 * s.maxcon);
+  RCSB_ALLOC(o_noslip, (nv + 2 * s.maxcon) * nv + nv + 4 * s.maxcon);
   if (o < k_end) o = k_end;
   RCSB_ALLOC(o_M, nv * nv);
   RCSB_ALLOC(o_bias, nv); RCSB_ALLOC(o_passive, nv); RCSB_ALLOC(o_gravc, nv); RCSB_ALLOC(o_actfrc, nv);
   RCSB_ALLOC(o_smooth, nv); RCSB_ALLOC(o_qacc_smooth, nv); RCSB_ALLOC(o_qacc, nv); RCSB_ALLOC(o_qfc, nv);
   RCSB_ALLOC(o_aforce, nu);
-  RCSB_ALLOC(o_con, RCSB_C_REALS * m->maxcon);
-  RCSB_ALLOC(o_J, m->maxefc * nv);
-  RCSB_ALLOC(o_efc, RCSB_E_NARR * m->maxefc);
+  RCSB_ALLOC(o_con, RCSB_C_REALS * s.maxcon);
+  RCSB_ALLOC(o_J, s.maxefc * nv);
+  RCSB_ALLOC(o_efc, RCSB_E_NARR * s.maxefc);
   RCSB_ALLOC(o_sepcache, 8);  // 2 x (pair tag, separating direction), valid for one launch
   o = (o + 1) & ~1;  // keep the double clock block 16-byte aligned when real is 8 bytes
-  m->ws_reals = o;
-  m->ws_doubles = RCSB_D_TAIL;
+  y.ws_reals = o;
+  y.ws_doubles = RCSB_D_TAIL;
   o = 0;
-  RCSB_ALLOC(oi_con, RCSB_CI_INTS * m->maxcon);
-  RCSB_ALLOC(oi_efc, RCSB_EI_NARR * m->maxefc);
-  RCSB_ALLOC(oi_misc, 8 /* MI_COUNT */ + RCSB_I_TAIL);
-  m->ws_ints = (o + 3) & ~3;
+  RCSB_ALLOC(oi_con, RCSB_CI_INTS * s.maxcon);
+  RCSB_ALLOC(oi_efc, RCSB_EI_NARR * s.maxefc);
+  RCSB_ALLOC(oi_misc, 10 /* MI_COUNT */ + RCSB_I_TAIL);
+  y.ws_ints = (o + 3) & ~3;
 #undef RCSB_ALLOC
 #undef RCSB_MAX
+  return y;
+}
+static inline RcsbShape rcsb_model_shape(const RcsbModel* m) {
+  RcsbShape s = {m->nq, m->nv, m->nu, m->nb, m->ng, m->npair, m->nt, m->neq, m->nroot, m->maxcon, m->maxefc, m->rb_njoints,
+                 m->cone_elliptic, m->implicitfast, m->noslip_iterations, m->cap_reduced, m->gr_enabled};
+  return s;
+}
+static inline int rcsb_model_finalize_layout(RcsbModel* m) {
+  if (m->nq <= 0 || m->nq > RCSB_MAXQ || m->nv <= 0 || m->nv > RCSB_MAXV || m->nu > RCSB_MAXU || m->nb > RCSB_MAXB ||
+      m->ng > RCSB_MAXG || m->npair > RCSB_MAXPAIR || m->nt > RCSB_MAXT || m->neq > RCSB_MAXEQ ||
+      m->nroot > RCSB_MAXROOT || m->rb_njoints > RCSB_MAXJ || m->maxcon < 1 || m->maxefc < 1)
+    return -1;
+  m->lay = rcsb_make_layout(rcsb_model_shape(m));
   return 0;
 }
 // The reduced-capacity copy of a finalised model (see RcsbModel::fast_maxcon); returns 0 when there is none.
@@ -135,6 +151,6 @@ static inline int rcsb_model_make_reduced(const RcsbModel* full, RcsbModel* out)
   return rcsb_model_finalize_layout(out) == 0;
 }
 static inline size_t rcsb_ws_bytes(const RcsbModel* m) {
-  size_t b = (size_t)m->ws_reals * sizeof(real) + (size_t)m->ws_doubles * sizeof(double) + (size_t)m->ws_ints * sizeof(int);
+  size_t b = (size_t)m->lay.ws_reals * sizeof(real) + (size_t)m->lay.ws_doubles * sizeof(double) + (size_t)m->lay.ws_ints * sizeof(int);
   return (b + 15) & ~(size_t)15;
 }

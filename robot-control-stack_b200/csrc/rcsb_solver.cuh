@@ -3,11 +3,9 @@
 // mj_makeConstraint and mj_step2 (/root/reference/src/sim/sim.cpp:110-112) plus the callbacks RCS runs
 // between and after them (/root/reference/src/sim/sim.cpp:14-61, SimRobot.cpp:156-191,
 // SimGripper.cpp:108-151). One environment per warp; see rcsb_dynamics.cuh.
-#pragma once
-#include "rcsb_dynamics.cuh"
 
-#define EFC(arr) (WR(efc) + (arr)*m.maxefc)
-#define EFCI(arr) (WI(efc) + (arr)*m.maxefc)
+#define EFC(arr) (WR(efc) + (arr)*MD(maxefc))
+#define EFCI(arr) (WI(efc) + (arr)*MD(maxefc))
 
 RCSB_DEV void get_impedance(const real* solimp, real pos, real margin, real* imp) {
   real dmin = solimp[0], dmax = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
@@ -39,14 +37,14 @@ RCSB_DEV real jac_dot(const Ctx& c, int body, int k, const real* pos, const real
 
 RCSB_DEV void st_make_constraint(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
-  const int nv = m.nv, maxefc = m.maxefc;
+  const int nv = MD(nv), maxefc = MD(maxefc);
   const real* q = WR(q);
   int* etype = EFCI(RCSB_EI_TYPE);
   int* eid = EFCI(RCSB_EI_ID);
   int ncon = WI(misc)[MI_NCON];
   int nefc = 0, ne = 0, nf = 0, nl = 0;
   // ---- row table (equality -> friction loss -> limits -> contacts), identical in every lane
-  for (int e = 0; e < m.neq; e++)
+  for (int e = 0; e < MD(neq); e++)
     if (m.e_active[e]) {
       if (c.lane == 0) { etype[nefc] = RCSB_EQ; eid[nefc] = e; }
       nefc++; ne++;
@@ -66,7 +64,7 @@ RCSB_DEV void st_make_constraint(const Ctx& c) {
             if (c.lane == 0) { etype[nefc] = RCSB_LIMIT; eid[nefc] = 2 * j + side; }
             nefc++; nl++;
           } else if (c.lane == 0) {
-            WI(misc)[m.cap_reduced ? MI_OVERFLOW : MI_WARN] += 1;
+            WI(misc)[MD(cap_reduced) ? MI_OVERFLOW : MI_WARN] += 1;
           }
         }
       }
@@ -75,16 +73,16 @@ RCSB_DEV void st_make_constraint(const Ctx& c) {
     const real* cr = WR(con) + RCSB_C_REALS * ci;
     int* cii = WI(con) + RCSB_CI_INTS * ci;
     int dim = cii[RCSB_CI_DIM];
-    int rows = m.cone_elliptic ? dim : (dim == 1 ? 1 : 2 * (dim - 1));
+    int rows = MD(cone_elliptic) ? dim : (dim == 1 ? 1 : 2 * (dim - 1));
     int addr = -1;
     if (cr[RCSB_C_DIST] < cr[RCSB_C_INCMARGIN]) {
       if (nefc + rows <= maxefc) {
         addr = nefc;
         if (c.lane == 0)
-          for (int r = 0; r < rows; r++) { etype[nefc + r] = m.cone_elliptic ? RCSB_CONTACT_ELL : RCSB_CONTACT_PYR; eid[nefc + r] = ci; }
+          for (int r = 0; r < rows; r++) { etype[nefc + r] = MD(cone_elliptic) ? RCSB_CONTACT_ELL : RCSB_CONTACT_PYR; eid[nefc + r] = ci; }
         nefc += rows;
       } else if (c.lane == 0) {
-        WI(misc)[m.cap_reduced ? MI_OVERFLOW : MI_WARN] += 1;
+        WI(misc)[MD(cap_reduced) ? MI_OVERFLOW : MI_WARN] += 1;
       }
     }
     if (c.lane == 0) cii[RCSB_CI_EFC] = addr;
@@ -191,7 +189,7 @@ RCSB_DEV void st_make_constraint(const Ctx& c) {
     EFC(RCSB_E_AREF)[r] = K * imp * (pos - margin);   // stiffness term, consumed below
   }
   RCSB_SYNC();
-  if (m.cone_elliptic) {
+  if (MD(cone_elliptic)) {
     PFOR(ci, ncon) {  // friction rows of elliptic cones: R tied to the normal row through impratio
       real* cr = WR(con) + RCSB_C_REALS * ci;
       const int* cii = WI(con) + RCSB_CI_INTS * ci;
@@ -218,8 +216,8 @@ RCSB_DEV void st_make_constraint(const Ctx& c) {
 // ------------------------------------------------------------------ actuation and smooth acceleration
 RCSB_DEV void st_actuation(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
-  const int nv = m.nv;
-  PFOR(a, m.nu) {
+  const int nv = MD(nv);
+  PFOR(a, MD(nu)) {
     real len, vel;
     if (m.a_trntype[a] == RCSB_TRN_JOINT) {
       int d = m.a_trnid[a];
@@ -241,7 +239,7 @@ RCSB_DEV void st_actuation(const Ctx& c) {
   RCSB_SYNC();
   PFOR(k, nv) {
     real s = 0;
-    for (int a = 0; a < m.nu; a++) {
+    for (int a = 0; a < MD(nu); a++) {
       real mom = m.a_trntype[a] == RCSB_TRN_JOINT ? (m.a_trnid[a] == k ? m.a_gear[a] : (real)0) : m.a_gear[a] * m.t_coef[m.a_trnid[a]][k];
       s += mom * WR(aforce)[a];
     }
@@ -257,8 +255,8 @@ RCSB_DEV void st_actuation(const Ctx& c) {
 RCSB_DEV void ensure_chol_M(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
   if (!WI(misc)[MI_HAVE_L]) {
-    PFOR(e, m.nv * m.nv) { WR(L)[e] = WR(M)[e]; }
-    chol_factor(c, WR(L), WR(L) + m.nv * m.nv, m.nv);
+    PFOR(e, MD(nv) * MD(nv)) { WR(L)[e] = WR(M)[e]; }
+    chol_factor(c, WR(L), WR(L) + MD(nv) * MD(nv), MD(nv));
     if (c.lane == 0) WI(misc)[MI_HAVE_L] = 1;
     RCSB_SYNC();
   }
@@ -267,8 +265,8 @@ RCSB_DEV void ensure_chol_M(const Ctx& c) {
 RCSB_DEV void compute_qacc_smooth(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
   ensure_chol_M(c);
-  PFOR(k, m.nv) { WR(qacc_smooth)[k] = WR(smooth)[k]; }
-  chol_solve(c, WR(L), WR(L) + m.nv * m.nv, m.nv, WR(qacc_smooth), WR(tmp));
+  PFOR(k, MD(nv)) { WR(qacc_smooth)[k] = WR(smooth)[k]; }
+  chol_solve(c, WR(L), WR(L) + MD(nv) * MD(nv), MD(nv), WR(qacc_smooth), WR(tmp));
 }
 
 // ------------------------------------------------------------------ constraint cost, forces, states
@@ -296,7 +294,7 @@ RCSB_DEV real constraint_update(const Ctx& c, int nefc, int ncon, int want_hess)
       else { force[r] = 0; state[r] = RCSB_SATISFIED; }
     }
   }
-  if (m.cone_elliptic) {
+  if (MD(cone_elliptic)) {
     PFOR(ci, ncon) {
       const real* cr = WR(con) + RCSB_C_REALS * ci;
       const int* cii = WI(con) + RCSB_CI_INTS * ci;
@@ -342,7 +340,7 @@ RCSB_DEV real constraint_update(const Ctx& c, int nefc, int ncon, int want_hess)
 // cost at acceleration vector `acc` (shared memory): fills Ma, jar, force, state; returns total cost
 RCSB_DEV_NOINLINE real total_cost(const Ctx& c, const real* acc, int nefc, int ncon, int want_hess, real* gauss_out) {
   const RcsbModel& m = CMODEL(c);
-  const int nv = m.nv;
+  const int nv = MD(nv);
   real g = 0;
 #ifndef RCSB_HOST_EMU
   __builtin_assume(__isShared(acc));
@@ -387,7 +385,7 @@ RCSB_DEV_NOINLINE void line_eval(const Ctx& c, int nefc, int ncon, real alpha, r
       if (x < 0) { v += (real)0.5 * D * x * x; g1 += D * x * jv; g2 += D * jv * jv; }
     }
   }
-  if (m.cone_elliptic) {
+  if (MD(cone_elliptic)) {
     PFOR(ci, ncon) {
       const real* cr = WR(con) + RCSB_C_REALS * ci;
       const int* cii = WI(con) + RCSB_CI_INTS * ci;
@@ -448,7 +446,7 @@ RCSB_DEV real line_search(const Ctx& c, int nefc, int ncon, real qG0, real qG1, 
 
 RCSB_DEV void compute_qfc(const Ctx& c, int nefc) {
   const RcsbModel& m = CMODEL(c);
-  const int nv = m.nv;
+  const int nv = MD(nv);
   PFOR(k, nv) {
     real s = 0;
     for (int r = 0; r < nefc; r++) s += WR(J)[r * nv + k] * EFC(RCSB_E_FORCE)[r];
@@ -461,7 +459,7 @@ RCSB_DEV void compute_qfc(const Ctx& c, int nefc) {
 // ------------------------------------------------------------------ noslip post-pass
 RCSB_DEV_NOINLINE void solve_noslip(const Ctx& c, int nefc, int ncon) {
   const RcsbModel& m = CMODEL(c);
-  const int nv = m.nv;
+  const int nv = MD(nv);
   int ne = WI(misc)[MI_NE], nf = WI(misc)[MI_NF];
   int any = nf > 0;
   for (int ci = 0; ci < ncon; ci++)
@@ -475,7 +473,7 @@ RCSB_DEV_NOINLINE void solve_noslip(const Ctx& c, int nefc, int ncon) {
   }
   // M^-1 J^T of every friction row: [friction-loss rows | 2 rows per contact]
   real* MinvJ = WR(noslip);
-  real* Ablk = MinvJ + (nf + 2 * m.maxcon) * nv;  // 1 value per dof-friction row, 4 per contact
+  real* Ablk = MinvJ + (nf + 2 * MD(maxcon)) * nv;  // 1 value per dof-friction row, 4 per contact
   for (int i = 0; i < nf; i++) {
     PFOR(k, nv) { MinvJ[i * nv + k] = WR(J)[(ne + i) * nv + k]; }
     chol_solve(c, WR(L), WR(L) + nv * nv, nv, MinvJ + i * nv, WR(tmp));
@@ -506,7 +504,7 @@ RCSB_DEV_NOINLINE void solve_noslip(const Ctx& c, int nefc, int ncon) {
   compute_qfc(c, nefc);  // qfc = J^T f for the current forces
   real scale = (real)1 / (m.meaninertia * (nv > 1 ? nv : 1));
   real* f = EFC(RCSB_E_FORCE);
-  for (int iter = 0; iter < m.noslip_iterations; iter++) {
+  for (int iter = 0; iter < MD(noslip_iterations); iter++) {
     real improvement = 0;
     for (int i = 0; i < nf; i++) {
       int r = ne + i;
@@ -525,7 +523,7 @@ RCSB_DEV_NOINLINE void solve_noslip(const Ctx& c, int nefc, int ncon) {
     }
     for (int ci = 0; ci < ncon; ci++) {
       int a = WI(con)[RCSB_CI_INTS * ci + RCSB_CI_EFC];
-      if (a < 0 || WI(con)[RCSB_CI_INTS * ci + RCSB_CI_DIM] < 3 || !m.cone_elliptic) continue;
+      if (a < 0 || WI(con)[RCSB_CI_INTS * ci + RCSB_CI_DIM] < 3 || !MD(cone_elliptic)) continue;
       const real* cr = WR(con) + RCSB_C_REALS * ci;
       real fn = f[a], res[2], old[2] = {f[a + 1], f[a + 2]}, bc[2], v[2] = {0, 0};
       const real* Ac = Ablk + nf + 4 * ci;
@@ -583,7 +581,7 @@ RCSB_DEV_NOINLINE void solve_noslip(const Ctx& c, int nefc, int ncon) {
 // ------------------------------------------------------------------ constrained acceleration (Newton)
 RCSB_DEV void st_constraint_solve(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
-  const int nv = m.nv;
+  const int nv = MD(nv);
   int nefc = WI(misc)[MI_NEFC], ncon = WI(misc)[MI_NCON];
   if (nefc == 0) {
     compute_qacc_smooth(c);
@@ -592,7 +590,7 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
     RCSB_SYNC();
     return;
   }
-  if (ncon == 0 && !(WI(misc)[MI_NF] > 0 && m.noslip_iterations > 0)) {
+  if (ncon == 0 && !(WI(misc)[MI_NF] > 0 && MD(noslip_iterations) > 0)) {
     // Direct active-set solve for equality / friction-loss / joint-limit rows. The cost is strictly convex and piecewise
     // quadratic in qacc: with the zone of every row fixed (quadratic, linear with constant force, or inactive) the
     // stationarity condition is the linear system
@@ -747,19 +745,19 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
   }
   if (c.lane == 0) WI(misc)[MI_SOLVER_ITER] = iter;
   compute_qfc(c, nefc);
-  if (m.noslip_iterations > 0) solve_noslip(c, nefc, ncon);
+  if (MD(noslip_iterations) > 0) solve_noslip(c, nefc, ncon);
 }
 
 // ------------------------------------------------------------------ implicitfast / Euler integration + mj_advance
 RCSB_DEV void st_integrate(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
-  const int nv = m.nv;
+  const int nv = MD(nv);
   const real h = m.timestep;
   PFOR(e, nv * nv) {
     int i = e / nv, j = e - i * nv;
     if (j > i) continue;
-    real dv = (i == j) ? -m.d_damping[i] + (m.implicitfast ? m.d_kvdiag[i] : (real)0) : (real)0;
-    if (m.implicitfast) {
+    real dv = (i == j) ? -m.d_damping[i] + (MD(implicitfast) ? m.d_kvdiag[i] : (real)0) : (real)0;
+    if (MD(implicitfast)) {
       for (int sa = 0; sa < m.n_special; sa++) {
         int a = m.a_special[sa];
         real bv = m.a_bias[a][2];
@@ -784,7 +782,7 @@ RCSB_DEV void st_integrate(const Ctx& c) {
     WR(warm)[k] = WR(qacc)[k];
   }
   RCSB_SYNC();
-  PFOR(b, m.nb) {
+  PFOR(b, MD(nb)) {
     int qa = m.b_qadr[b], da = m.b_dadr[b];
     real* q = WR(q);
     const real* v = WR(v);
@@ -810,7 +808,7 @@ RCSB_DEV void st_integrate(const Ctx& c) {
 // Persistent per-env RCS state lives in the workspace region o_rcs (reals: RCSB_S_* tail) and
 // oi_rcs (ints: RCSB_I_*). Semantics: sim.cpp:14-61, SimRobot.cpp:156-191, SimGripper.cpp:93-151.
 #define RS(i) (WR(rcs)[(i)])
-#define RI(i) (CWI(c)[m.oi_misc + MI_COUNT + (i)])
+#define RI(i) (CWI(c)[LAY.oi_misc + MI_COUNT + (i)])
 
 RCSB_DEV real gripper_width(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
@@ -823,7 +821,7 @@ RCSB_DEV int run_callback(const Ctx& c, int kind) {
   int ret = 0;
   if (kind == RCSB_CB_ARRIVED) {
     real mx = 0;
-    for (int i = 0; i < m.rb_njoints; i++) {
+    for (int i = 0; i < MD(rb_njoints); i++) {
       real e = r_abs(WR(q)[m.rb_qadr[i]] - RS(RCSB_S_TARGET + i));
       mx = e > mx ? e : mx;
     }
@@ -831,13 +829,13 @@ RCSB_DEV int run_callback(const Ctx& c, int kind) {
     if (c.lane == 0) RI(RCSB_I_ARRIVED) = mx < m.rb_joint_tol;
   } else if (kind == RCSB_CB_MOVING) {
     real mx = 0;
-    for (int i = 0; i < m.rb_njoints; i++) {
+    for (int i = 0; i < MD(rb_njoints); i++) {
       real e = r_abs(WR(q)[m.rb_qadr[i]] - RS(RCSB_S_PREV + i));
       mx = e > mx ? e : mx;
     }
     RCSB_SYNC();
     if (c.lane == 0) {
-      for (int i = 0; i < m.rb_njoints; i++) RS(RCSB_S_PREV + i) = WR(q)[m.rb_qadr[i]];
+      for (int i = 0; i < MD(rb_njoints); i++) RS(RCSB_S_PREV + i) = WR(q)[m.rb_qadr[i]];
       RI(RCSB_I_MOVING) = mx > (real)0.0001;
     }
   } else if (kind == RCSB_CB_ROBOT_CONV) {
@@ -873,7 +871,7 @@ RCSB_DEV int run_callback(const Ctx& c, int kind) {
 RCSB_DEV int cb_registered(const RcsbModel& m, int kind) {
   if (kind <= RCSB_CB_ROBOT_CONV) return m.rb_register_convergence;
   if (kind == RCSB_CB_ROBOT_COLL) return 1;
-  return m.gr_enabled;
+  return MD(gr_enabled);
 }
 RCSB_DEV real cb_period(const RcsbModel& m, int kind) { return kind <= RCSB_CB_ROBOT_COLL ? m.rb_cb_period : m.gr_cb_period; }
 
@@ -918,22 +916,21 @@ RCSB_DEV int invoke_condition_callbacks(const Ctx& c, double time) {
 RCSB_DEV int state_is_bad(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
   int bad = 0;
-  PFOR(i, m.nq) { real x = WR(q)[i]; if (!(x == x) || x > (real)1e10 || x < (real)-1e10) bad = 1; }
-  PFOR(i, m.nv) { real x = WR(v)[i]; if (!(x == x) || x > (real)1e10 || x < (real)-1e10) bad = 1; }
+  PFOR(i, MD(nq)) { real x = WR(q)[i]; if (!(x == x) || x > (real)1e10 || x < (real)-1e10) bad = 1; }
+  PFOR(i, MD(nv)) { real x = WR(v)[i]; if (!(x == x) || x > (real)1e10 || x < (real)-1e10) bad = 1; }
   return warp_any(bad);
 }
 RCSB_DEV void reset_data(const Ctx& c, double* time) {  // mj_resetData
   const RcsbModel& m = CMODEL(c);
-  PFOR(i, m.nq) { WR(q)[i] = m.qpos0[i]; }
-  PFOR(i, m.nv) { WR(v)[i] = 0; WR(warm)[i] = 0; }
-  PFOR(i, m.nu) { WR(ctrl)[i] = 0; }
+  PFOR(i, MD(nq)) { WR(q)[i] = m.qpos0[i]; }
+  PFOR(i, MD(nv)) { WR(v)[i] = 0; WR(warm)[i] = 0; }
+  PFOR(i, MD(nu)) { WR(ctrl)[i] = 0; }
   if (c.lane == 0) *time = 0;
   RCSB_SYNC();
 }
 // RCSB_STAGE: CTA barrier (lockstep launches only) + the stage; the profiling build (-DRCSB_STAGE_TIMING) also
 // accumulates clock64() per stage for warp 0 of CTA 0 into rcsb_stage_cycles[].
 #if defined(RCSB_STAGE_TIMING) && !defined(RCSB_HOST_EMU)
-__device__ unsigned long long rcsb_stage_cycles[16];
 #define RCSB_STAGE(idx, call)                                                                        \
   do {                                                                                               \
     RCSB_BLOCK_SYNC();                                                                               \
@@ -962,7 +959,7 @@ RCSB_DEV int physics_step(const Ctx& c, double* time) {
   RCSB_STAGE(3, st_collision(c));
   RCSB_STAGE(4, st_velocity(c));
   RCSB_STAGE(5, st_make_constraint(c));
-  if (m.cap_reduced && WI(misc)[MI_OVERFLOW]) {
+  if (MD(cap_reduced) && WI(misc)[MI_OVERFLOW]) {
     for (int i = 0; i < 3; i++) RCSB_BLOCK_SYNC();  // the barriers of the stages this warp skips
     RCSB_STEP_SYNC();
     return 1;

@@ -37,6 +37,58 @@ enum { RCSB_ROLE_ARM = 1, RCSB_ROLE_GRIPPER = 2, RCSB_ROLE_FINGER = 4, RCSB_ROLE
 enum { RCSB_CB_ARRIVED = 0, RCSB_CB_MOVING = 1, RCSB_CB_ROBOT_CONV = 2, RCSB_CB_ROBOT_COLL = 3, RCSB_CB_GRIP_CONV = 4,
        RCSB_CB_GRIP_COLL = 5, RCSB_NCB = 6 };
 
+// per-contact record in the workspace (reals)
+enum { RCSB_C_DIST = 0, RCSB_C_POS = 1, RCSB_C_FRAME = 4, RCSB_C_FRIC = 13, RCSB_C_SOLREF = 16, RCSB_C_SOLIMP = 18,
+       RCSB_C_MU = 23, RCSB_C_INCMARGIN = 24, RCSB_C_REALS = 25 };
+enum { RCSB_CI_G0 = 0, RCSB_CI_G1 = 1, RCSB_CI_DIM = 2, RCSB_CI_EFC = 3, RCSB_CI_INTS = 4 };
+// per-constraint-row scalars (reals), stored as arrays of length maxefc each
+enum { RCSB_E_POS = 0, RCSB_E_MARGIN, RCSB_E_FLOSS, RCSB_E_D, RCSB_E_R, RCSB_E_AREF, RCSB_E_FORCE, RCSB_E_JAR, RCSB_E_JV,
+       RCSB_E_B, RCSB_E_K, RCSB_E_NARR };
+enum { RCSB_EI_TYPE = 0, RCSB_EI_ID, RCSB_EI_STATE, RCSB_EI_NARR };
+
+// ---- per-environment persistent state in HBM: struct-of-arrays by field group, env-major rows
+//   sr[N][nsr]  reals  : qpos[nq] qvel[nv] ctrl[nu] qacc_warmstart[nv] | RCS tail (RCSB_S_*)
+//   sd[N][RCSB_D_TAIL] doubles : simulation time and callback clocks (always double: the callback
+//                        cadence depends on float64 accumulation of time, sim.cpp:14-23)
+//   si[N][RCSB_I_TAIL] ints   : flags and counters
+enum {
+  RCSB_S_PREV = 0,                          // previous_angles[MAXJ]   (SimRobotState)
+  RCSB_S_TARGET = RCSB_S_PREV + RCSB_MAXJ,  // target_angles[MAXJ]
+  RCSB_S_GLCW = RCSB_S_TARGET + RCSB_MAXJ,  // gripper last_commanded_width
+  RCSB_S_GLW,                               // gripper last_width
+  RCSB_S_GCMD,                              // GripperWrapper._last_gripper_cmd (-1 = None), base.py:684-735
+  RCSB_S_PREVACT,                           // RobotEnv.prev_action joints[MAXJ], base.py:268-287
+  RCSB_S_SITEPOS = RCSB_S_PREVACT + RCSB_MAXJ,  // attachment site xpos[3] from the last step1
+  RCSB_S_SITEMAT = RCSB_S_SITEPOS + 3,      // attachment site xmat[9]
+  RCSB_S_TAIL = RCSB_S_SITEMAT + 9,
+};
+enum { RCSB_D_TIME = 0, RCSB_D_CBLAST = 1, RCSB_D_TAIL = 1 + RCSB_NCB };
+enum {
+  RCSB_I_IK_SUCCESS = 0, RCSB_I_COLLISION, RCSB_I_MOVING, RCSB_I_ARRIVED, RCSB_I_G_MOVING, RCSB_I_G_COLLISION,
+  RCSB_I_CONVERGED, RCSB_I_CONV_STEPS, RCSB_I_CBRET,  // RCSB_NCB last_return_value flags follow
+  RCSB_I_NCON = RCSB_I_CBRET + RCSB_NCB, RCSB_I_NEFC, RCSB_I_SOLVER_ITER, RCSB_I_WARN, RCSB_I_TOTAL_STEPS,
+  RCSB_I_HAVE_PREV_ACTION,  // RobotEnv.prev_action is not None (base.py:268-272)
+  RCSB_I_RESUME,  // substeps this launch still owes the environment (it outgrew the reduced workspace layout)
+  RCSB_I_TAIL
+};
+
+// Per-warp workspace layout: offsets in reals (o_*) and ints (oi_*). A pure function of the model's shape
+// (rcsb_make_layout), so kernels specialised for a fixed shape fold every offset into an instruction immediate.
+struct RcsbLayout {
+  int ws_reals, ws_ints, nsr;  // nsr = reals per env in HBM (dynamic state + RCS tail)
+  int o_q, o_v, o_ctrl, o_warm, o_bpos, o_bquat, o_bmat, o_rootcom, o_cinert, o_crb, o_crbbuf,
+      o_cdof, o_cdofdot, o_cvel, o_cfrc, o_M, o_L, o_H, o_bias, o_passive, o_gravc, o_actfrc, o_smooth,
+      o_qacc_smooth, o_qacc, o_qfc, o_grad, o_search, o_Ma, o_Mv, o_tmp, o_aforce, o_gpos, o_cand, o_con,
+      o_J, o_efc, o_conehess, o_noslip, o_site, o_rcs, o_sepcache;
+  int ws_doubles;  // RCSB_D_TAIL doubles per warp follow the reals
+  int oi_con, oi_efc, oi_misc;
+};
+// The part of a model that fixes code shape: loop bounds, workspace layout, enabled features.
+struct RcsbShape {
+  int nq, nv, nu, nb, ng, npair, nt, neq, nroot, maxcon, maxefc, rb_njoints, cone_elliptic, implicitfast,
+      noslip_iterations, cap_reduced, gr_enabled;
+};
+
 struct RcsbModel {
   // ---- sizes / options
   int nq, nv, nu, nb, ng, npair, nt, neq, nroot, nmeshvert;
@@ -92,46 +144,43 @@ struct RcsbModel {
   int gr_enabled, gr_act, gr_qadr;
   real gr_eps_inner, gr_eps_outer, gr_cb_period, gr_max_act, gr_min_act, gr_max_joint, gr_min_joint;
   // ---- per-warp workspace layout (offsets in reals / ints), filled by rcsb_model_finalize
-  int ws_reals, ws_ints, nsr;  // nsr = reals per env in HBM (dynamic state + RCS tail)
-  int o_q, o_v, o_ctrl, o_warm, o_bpos, o_bquat, o_bmat, o_rootcom, o_cinert, o_crb, o_crbbuf,
-      o_cdof, o_cdofdot, o_cvel, o_cfrc, o_M, o_L, o_H, o_bias, o_passive, o_gravc, o_actfrc, o_smooth,
-      o_qacc_smooth, o_qacc, o_qfc, o_grad, o_search, o_Ma, o_Mv, o_tmp, o_aforce, o_gpos, o_cand, o_con,
-      o_J, o_efc, o_conehess, o_noslip, o_site, o_rcs, o_sepcache;
-  int ws_doubles;  // RCSB_D_TAIL doubles per warp follow the reals
-  int oi_con, oi_efc, oi_misc;
+  RcsbLayout lay;
 };
 
-// per-contact record in the workspace (reals)
-enum { RCSB_C_DIST = 0, RCSB_C_POS = 1, RCSB_C_FRAME = 4, RCSB_C_FRIC = 13, RCSB_C_SOLREF = 16, RCSB_C_SOLIMP = 18,
-       RCSB_C_MU = 23, RCSB_C_INCMARGIN = 24, RCSB_C_REALS = 25 };
-enum { RCSB_CI_G0 = 0, RCSB_CI_G1 = 1, RCSB_CI_DIM = 2, RCSB_CI_EFC = 3, RCSB_CI_INTS = 4 };
-// per-constraint-row scalars (reals), stored as arrays of length maxefc each
-enum { RCSB_E_POS = 0, RCSB_E_MARGIN, RCSB_E_FLOSS, RCSB_E_D, RCSB_E_R, RCSB_E_AREF, RCSB_E_FORCE, RCSB_E_JAR, RCSB_E_JV,
-       RCSB_E_B, RCSB_E_K, RCSB_E_NARR };
-enum { RCSB_EI_TYPE = 0, RCSB_EI_ID, RCSB_EI_STATE, RCSB_EI_NARR };
 
-// ---- per-environment persistent state in HBM: struct-of-arrays by field group, env-major rows
-//   sr[N][nsr]  reals  : qpos[nq] qvel[nv] ctrl[nu] qacc_warmstart[nv] | RCS tail (RCSB_S_*)
-//   sd[N][RCSB_D_TAIL] doubles : simulation time and callback clocks (always double: the callback
-//                        cadence depends on float64 accumulation of time, sim.cpp:14-23)
-//   si[N][RCSB_I_TAIL] ints   : flags and counters
+// op bits, executed in this order within one launch
 enum {
-  RCSB_S_PREV = 0,                          // previous_angles[MAXJ]   (SimRobotState)
-  RCSB_S_TARGET = RCSB_S_PREV + RCSB_MAXJ,  // target_angles[MAXJ]
-  RCSB_S_GLCW = RCSB_S_TARGET + RCSB_MAXJ,  // gripper last_commanded_width
-  RCSB_S_GLW,                               // gripper last_width
-  RCSB_S_GCMD,                              // GripperWrapper._last_gripper_cmd (-1 = None), base.py:684-735
-  RCSB_S_PREVACT,                           // RobotEnv.prev_action joints[MAXJ], base.py:268-287
-  RCSB_S_SITEPOS = RCSB_S_PREVACT + RCSB_MAXJ,  // attachment site xpos[3] from the last step1
-  RCSB_S_SITEMAT = RCSB_S_SITEPOS + 3,      // attachment site xmat[9]
-  RCSB_S_TAIL = RCSB_S_SITEMAT + 9,
+  RCSB_OP_GRIPPER_RESET = 1 << 0,   // SimGripper::reset
+  RCSB_OP_SIM_RESET = 1 << 1,       // Sim::reset (mj_resetData + callback clocks)
+  RCSB_OP_ROBOT_RESET = 1 << 2,     // SimRobot::reset (set_joints_hard(q_home))
+  RCSB_OP_ENV_RESET_FLAGS = 1 << 3, // GripperWrapper.reset: _last_gripper_cmd = None
+  RCSB_OP_ACT_JOINTS_REL = 1 << 4,  // RelativeActionSpace (LAST_STEP) + RobotEnv.step dedupe + set_joint_position
+  RCSB_OP_ACT_JOINTS_ABS = 1 << 5,  // RobotEnv.step dedupe + set_joint_position
+  RCSB_OP_ACT_GRIPPER_BIN = 1 << 6, // GripperWrapper.action, binary
+  RCSB_OP_SET_JOINTS = 1 << 7,      // SimRobot::set_joint_position (direct API, no dedupe)
+  RCSB_OP_SET_GRIPPER = 1 << 8,     // SimGripper::set_normalized_width
+  RCSB_OP_SET_JOINTS_HARD = 1 << 9, // SimRobot::set_joints_hard
+  RCSB_OP_STEP_K = 1 << 10,         // Sim::step(k)
+  RCSB_OP_STEP_CONV = 1 << 11,      // Sim::step_until_convergence
+  RCSB_OP_OBS = 1 << 12,            // RobotEnv.get_obs + wrappers' observation/info
 };
-enum { RCSB_D_TIME = 0, RCSB_D_CBLAST = 1, RCSB_D_TAIL = 1 + RCSB_NCB };
-enum {
-  RCSB_I_IK_SUCCESS = 0, RCSB_I_COLLISION, RCSB_I_MOVING, RCSB_I_ARRIVED, RCSB_I_G_MOVING, RCSB_I_G_COLLISION,
-  RCSB_I_CONVERGED, RCSB_I_CONV_STEPS, RCSB_I_CBRET,  // RCSB_NCB last_return_value flags follow
-  RCSB_I_NCON = RCSB_I_CBRET + RCSB_NCB, RCSB_I_NEFC, RCSB_I_SOLVER_ITER, RCSB_I_WARN, RCSB_I_TOTAL_STEPS,
-  RCSB_I_HAVE_PREV_ACTION,  // RobotEnv.prev_action is not None (base.py:268-272)
-  RCSB_I_RESUME,  // substeps this launch still owes the environment (it outgrew the reduced workspace layout)
-  RCSB_I_TAIL
+enum { RCSB_OBS_DIM = 22, RCSB_INFO_DIM = 8 };
+// obs row: tquat[7] joints[7] xyzrpy[6] gripper[1] gripper_width[1]
+// info row: collision, ik_success, is_sim_converged, is_grasped, truncated, robot_collision, gripper_collision, conv_steps
+
+struct RcsbLaunch {
+  int N, env_offset;
+  unsigned ops;
+  int k, max_convergence_steps;
+  int lockstep;  // fixed-substep launches: 0 no CTA barriers, 1 one per stage, 2 one per physics step
+  int phase;     // 0: every environment, reduced or full layout; 1: full layout, only the environments in overflow_list
+  int* overflow_list;   // [N] environments the reduced layout could not finish (phase 0 appends, phase 1 consumes)
+  int* overflow_count;
+  const real* act_joints;   // [N][njoints]
+  const real* act_gripper;  // [N]
+  const unsigned char* mask;  // optional [N]: 0 = leave this env untouched
+  real max_mov, jlow[RCSB_MAXJ], jhigh[RCSB_MAXJ];
+  real* obs;   // [N][RCSB_OBS_DIM] or null
+  int* info;   // [N][RCSB_INFO_DIM] or null
 };
+

@@ -6,8 +6,12 @@
 #include <stdlib.h>
 #include <vector>
 
-#include "../../robot-control-stack_b200/csrc/rcsb_env.cuh"
 #include "../../robot-control-stack_b200/csrc/rcsb_layout.h"
+#include "../../robot-control-stack_b200/csrc/rcsb_ctx.cuh"
+#define RCSB_VARIANT_NS rcsb_generic
+#define RCSB_KERNEL unused
+#include "../../robot-control-stack_b200/csrc/rcsb_variant.cuh"
+using namespace rcsb_generic;
 
 extern "C" {
 struct EmuModel { RcsbModel full, reduced; int has_reduced; };
@@ -20,23 +24,23 @@ int emu_model_finalize(EmuModel* m, int use_reduced) {
   m->has_reduced = use_reduced && rcsb_model_make_reduced(&m->full, &m->reduced);
   return rc;
 }
-int emu_nsr(const EmuModel* m) { return m->full.nsr; }
+int emu_nsr(const EmuModel* m) { return m->full.lay.nsr; }
 int emu_has_reduced(const EmuModel* m) { return m->has_reduced; }
 int emu_sizes(int* out) { out[0] = RCSB_S_TAIL; out[1] = RCSB_D_TAIL; out[2] = RCSB_I_TAIL; out[3] = RCSB_OBS_DIM; out[4] = RCSB_INFO_DIM; out[5] = (int)sizeof(real); return 0; }
 
 static void run_phase(const RcsbModel* m, const real* verts, real* sr, double* sd, int* si, RcsbLaunch L, const int* envs, int n,
                       const unsigned char* mask, real* dbg_ws, int dbg_stride, int* dbg_layout) {
-  std::vector<real> w(m->ws_reals);
-  std::vector<int> wi(m->ws_ints);
+  std::vector<real> w(m->lay.ws_reals);
+  std::vector<int> wi(m->lay.ws_ints);
   double clk[RCSB_D_TAIL];
   for (int i = 0; i < n; i++) {
     int e = envs ? envs[i] : i;
     if (!envs && mask && !mask[e]) continue;
     Ctx c = {m, w.data(), wi.data(), verts, clk, 0, 0};
-    load_env(c, sr + (size_t)e * m->nsr, sd + (size_t)e * RCSB_D_TAIL, si + (size_t)e * RCSB_I_TAIL);
+    load_env(c, sr + (size_t)e * m->lay.nsr, sd + (size_t)e * RCSB_D_TAIL, si + (size_t)e * RCSB_I_TAIL);
     run_env_program(c, L, e);
-    store_env(c, sr + (size_t)e * m->nsr, sd + (size_t)e * RCSB_D_TAIL, si + (size_t)e * RCSB_I_TAIL);
-    if (dbg_ws) memcpy(dbg_ws + (size_t)e * dbg_stride, w.data(), sizeof(real) * m->ws_reals);
+    store_env(c, sr + (size_t)e * m->lay.nsr, sd + (size_t)e * RCSB_D_TAIL, si + (size_t)e * RCSB_I_TAIL);
+    if (dbg_ws) memcpy(dbg_ws + (size_t)e * dbg_stride, w.data(), sizeof(real) * m->lay.ws_reals);
     if (dbg_layout) dbg_layout[e] = m->cap_reduced;
   }
 }
@@ -54,7 +58,7 @@ int emu_run(const EmuModel* em, const real* verts, real* sr, double* sd, int* si
   std::vector<int> list(N);
   int count = 0;
   L.overflow_list = list.data(); L.overflow_count = &count; L.phase = 0;
-  const int stride = em->full.ws_reals;
+  const int stride = em->full.lay.ws_reals;
   run_phase(em->has_reduced ? &em->reduced : &em->full, verts, sr, sd, si, L, nullptr, N, mask, dbg_ws, stride, dbg_layout);
   int handed = count;
   if (em->has_reduced && handed > 0) {
@@ -66,12 +70,12 @@ int emu_run(const EmuModel* em, const real* verts, real* sr, double* sd, int* si
 }
 int emu_offset(const EmuModel* em, const char* name, int reduced) {
   const RcsbModel* m = reduced ? &em->reduced : &em->full;
-#define OFF(n) if (!strcmp(name, #n)) return m->o_##n;
+#define OFF(n) if (!strcmp(name, #n)) return m->lay.o_##n;
   OFF(q) OFF(v) OFF(ctrl) OFF(warm) OFF(bpos) OFF(bquat) OFF(bmat) OFF(rootcom) OFF(cinert) OFF(crb) OFF(cdof)
   OFF(M) OFF(L) OFF(H) OFF(bias) OFF(passive) OFF(gravc) OFF(actfrc) OFF(smooth) OFF(qacc_smooth) OFF(qacc) OFF(qfc)
   OFF(gpos) OFF(con) OFF(J) OFF(efc) OFF(rcs)
 #undef OFF
-  if (!strcmp(name, "ws_reals")) return m->ws_reals;
+  if (!strcmp(name, "ws_reals")) return m->lay.ws_reals;
   if (!strcmp(name, "maxefc")) return m->maxefc;
   if (!strcmp(name, "maxcon")) return m->maxcon;
   return -1;
