@@ -41,43 +41,103 @@ RCSB_DEV_NOINLINE void chol_solve(const Ctx& c, const real* L, const real* dinv,
     x[k] = yk;
   }
 }
+// factor A in place and solve A x = b for x (in place); when A1 is given, factor it too (same size, no solve)
+RCSB_DEV_NOINLINE void chol_factor_solve(const Ctx& c, real* A, real* dinv, int n, real* x, real* y, real* A1, real* dinv1) {
+  chol_factor(c, A, dinv, n);
+  chol_solve(c, A, dinv, n, x, y);
+  if (A1) chol_factor(c, A1, dinv1, n);
+}
 #else
-// Size-specialised body: with N a compile-time constant every loop unrolls and the row a[] stays in registers.
+// Half-warp formulation for N <= 16: lanes 0..15 hold system 0, lanes 16..31 system 1 (when present); lane li owns row
+// li in registers, pivots and multipliers travel by width-16 shuffles (right-looking, no shared-memory round trips and
+// no barriers inside the factorisation). With N a compile-time constant every loop unrolls.
+RCSB_DEV real half_bcast(real x, int src) { return __shfl_sync(0xffffffffu, x, src, 16); }
 template <int N>
-RCSB_DEV void chol_factor_n(const Ctx& c, real* A, real* dinv) {
-  const int lane = c.lane;
-  real a[N];
-#pragma unroll
-  for (int k = 0; k < N; k++) a[k] = (lane < N && k <= lane) ? A[lane * N + k] : (real)0;
+RCSB_DEV void chol_rows_factor(int li, real (&a)[N]) {
 #pragma unroll
   for (int j = 0; j < N; j++) {
-    real d = warp_bcast(a[j], j);
+    real d = half_bcast(a[j], j);
     if (d < RCSB_MINVAL) d = RCSB_MINVAL;
     real inv = rsqrt(d);
     real lij = a[j] * inv;  // lane > j: L[lane][j]; lane == j: L[j][j]
-    a[j] = lane == j ? inv : lij;
+    a[j] = li == j ? inv : lij;
 #pragma unroll
     for (int k = j + 1; k < N; k++) {
-      real lkj = warp_bcast(lij, k);
-      if (lane >= k) a[k] -= lij * lkj;
+      real lkj = half_bcast(lij, k);
+      if (li >= k) a[k] -= lij * lkj;
     }
   }
-  if (lane < N) {
+}
+// x <- (L L^T)^{-1} x with row li of L in a[] (a[li] = 1 / L[li][li]) and column li of L in col[]
+template <int N>
+RCSB_DEV real chol_rows_solve(int li, const real (&a)[N], const real (&col)[N], real xi) {
+  real di = (real)0;
+#pragma unroll
+  for (int k = 0; k < N; k++) if (k == li) di = a[k];
+#pragma unroll
+  for (int j = 0; j < N; j++) {  // forward: L z = x
+    real zj = half_bcast(xi * di, j);
+    if (li == j) xi = zj;
+    else if (li > j) xi -= a[j] * zj;
+  }
+#pragma unroll
+  for (int j = N - 1; j >= 0; j--) {  // backward: L^T w = z
+    real wj = half_bcast(xi * di, j);
+    if (li == j) xi = wj;
+    else if (li < j) xi -= col[j] * wj;
+  }
+  return xi;
+}
+template <int N>
+RCSB_DEV void chol_n(const Ctx& c, real* A0, real* dinv0, real* x, real* A1, real* dinv1) {
+  const int li = c.lane & 15, half = c.lane >> 4;
+  real* A = half ? A1 : A0;
+  real* dinv = half ? dinv1 : dinv0;
+  const bool on = A != nullptr && li < N;
+  real a[N], col[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) a[k] = (on && k <= li) ? A[li * N + k] : (k == li ? (real)1 : (real)0);
+  chol_rows_factor<N>(li, a);
+  if (on) {
 #pragma unroll
     for (int k = 0; k < N; k++) {
-      if (k < lane) A[lane * N + k] = a[k];
-      else if (k == lane) dinv[lane] = a[k];
+      if (k < li) A[li * N + k] = a[k];
+      else if (k == li) dinv[li] = a[k];
     }
   }
+  if (x == nullptr) return;
+  RCSB_SYNC();
+#pragma unroll
+  for (int j = 0; j < N; j++) col[j] = (!half && li < N && j > li) ? A0[j * N + li] : (real)0;
+  real xi = (!half && li < N) ? x[li] : (real)0;
+  xi = chol_rows_solve<N>(li, a, col, xi);
+  if (!half && li < N) x[li] = xi;
+}
+template <int N>
+RCSB_DEV void chol_solve_n(const Ctx& c, const real* L, const real* dinv, real* x) {
+  const int li = c.lane & 15, half = c.lane >> 4;
+  const bool on = !half && li < N;
+  real a[N], col[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    a[k] = (on && k < li) ? L[li * N + k] : (real)0;
+    col[k] = (on && k > li) ? L[k * N + li] : (real)0;
+  }
+  real di = on ? dinv[li] : (real)1;
+#pragma unroll
+  for (int k = 0; k < N; k++) if (k == li) a[k] = di;
+  real xi = on ? x[li] : (real)0;
+  xi = chol_rows_solve<N>(li, a, col, xi);
+  if (on) x[li] = xi;
 }
 RCSB_DEV_NOINLINE void chol_factor(const Ctx& c, real* A, real* dinv, int n) {
   __builtin_assume(__isShared(A));
   __builtin_assume(__isShared(dinv));
   RCSB_SYNC();
   switch (n) {  // dof counts of the supported scenes: xArm7 (7), FR3 + fingers (9), FR3 + fingers + free cube (15)
-    case 7: chol_factor_n<7>(c, A, dinv); break;
-    case 9: chol_factor_n<9>(c, A, dinv); break;
-    case 15: chol_factor_n<15>(c, A, dinv); break;
+    case 7: chol_n<7>(c, A, dinv, nullptr, nullptr, nullptr); break;
+    case 9: chol_n<9>(c, A, dinv, nullptr, nullptr, nullptr); break;
+    case 15: chol_n<15>(c, A, dinv, nullptr, nullptr, nullptr); break;
     default:  // any other size: column version on shared memory
       for (int j = 0; j < n; j++) {
         RCSB_SYNC();
@@ -96,26 +156,51 @@ RCSB_DEV_NOINLINE void chol_factor(const Ctx& c, real* A, real* dinv, int n) {
   }
   RCSB_SYNC();
 }
-// x <- (L L^T)^{-1} x ; lane i carries x[i]; y is unused scratch (kept for the common signature)
+// x <- (L L^T)^{-1} x ; y is unused scratch (kept for the common signature)
 RCSB_DEV_NOINLINE void chol_solve(const Ctx& c, const real* L, const real* dinv, int n, real* x, real* y) {
   const int lane = c.lane;
   __builtin_assume(__isShared(L));
   __builtin_assume(__isShared(dinv));
   __builtin_assume(__isShared(x));
   RCSB_SYNC();
-  real xi = lane < n ? x[lane] : (real)0;
-  real di = lane < n ? dinv[lane] : (real)0;
-  for (int j = 0; j < n; j++) {  // forward: L z = x
-    real zj = warp_bcast(xi * di, j);
-    if (lane == j) xi = zj;
-    else if (lane > j && lane < n) xi -= L[lane * n + j] * zj;
+  switch (n) {
+    case 7: chol_solve_n<7>(c, L, dinv, x); break;
+    case 9: chol_solve_n<9>(c, L, dinv, x); break;
+    case 15: chol_solve_n<15>(c, L, dinv, x); break;
+    default: {
+      real xi = lane < n ? x[lane] : (real)0;
+      real di = lane < n ? dinv[lane] : (real)0;
+      for (int j = 0; j < n; j++) {  // forward: L z = x
+        real zj = warp_bcast(xi * di, j);
+        if (lane == j) xi = zj;
+        else if (lane > j && lane < n) xi -= L[lane * n + j] * zj;
+      }
+      for (int j = n - 1; j >= 0; j--) {  // backward: L^T w = z
+        real wj = warp_bcast(xi * di, j);
+        if (lane == j) xi = wj;
+        else if (lane < j) xi -= L[j * n + lane] * wj;
+      }
+      if (lane < n) x[lane] = xi;
+    }
   }
-  for (int j = n - 1; j >= 0; j--) {  // backward: L^T w = z
-    real wj = warp_bcast(xi * di, j);
-    if (lane == j) xi = wj;
-    else if (lane < j) xi -= L[j * n + lane] * wj;
+  RCSB_SYNC();
+}
+// factor A in place and solve A x = b for x (in place); when A1 is given, factor it too in the other half-warp
+RCSB_DEV_NOINLINE void chol_factor_solve(const Ctx& c, real* A, real* dinv, int n, real* x, real* y, real* A1, real* dinv1) {
+  __builtin_assume(__isShared(A));
+  __builtin_assume(__isShared(dinv));
+  __builtin_assume(__isShared(x));
+  RCSB_SYNC();
+  switch (n) {
+    case 7: chol_n<7>(c, A, dinv, x, A1, dinv1); break;
+    case 9: chol_n<9>(c, A, dinv, x, A1, dinv1); break;
+    case 15: chol_n<15>(c, A, dinv, x, A1, dinv1); break;
+    default:
+      chol_factor(c, A, dinv, n);
+      chol_solve(c, A, dinv, n, x, y);
+      if (A1) chol_factor(c, A1, dinv1, n);
+      return;
   }
-  if (lane < n) x[lane] = xi;
   RCSB_SYNC();
 }
 #endif
@@ -139,8 +224,7 @@ RCSB_DEV void st_kinematics(const Ctx& c) {
       quat_to_mat(R, qq + 3);
       copy3(t, qq);
     } else {
-      real Rb[9];
-      quat_to_mat(Rb, m.b_quat[b]);
+      const real* Rb = m.b_rot[b];
       const real* u = m.b_jaxis[b];
       const real* jp = m.b_jpos[b];
       real qq = q[m.b_qadr[b]] - m.qpos0[m.b_qadr[b]];
@@ -150,7 +234,9 @@ RCSB_DEV void st_kinematics(const Ctx& c) {
         for (int i = 0; i < 9; i++) R[i] = Rb[i];
         t[0] = m.b_pos[b][0] + v[0] * qq; t[1] = m.b_pos[b][1] + v[1] * qq; t[2] = m.b_pos[b][2] + v[2] * qq;
       } else {
-        real s = sin(qq), co = cos(qq), oc = 1 - co;  // Rodrigues rotation about the joint axis
+        real s, co;
+        sincos(qq, &s, &co);
+        const real oc = 1 - co;  // Rodrigues rotation about the joint axis
         real Rj[9] = {co + oc * u[0] * u[0], oc * u[0] * u[1] - s * u[2], oc * u[0] * u[2] + s * u[1],
                       oc * u[1] * u[0] + s * u[2], co + oc * u[1] * u[1], oc * u[1] * u[2] - s * u[0],
                       oc * u[2] * u[0] - s * u[1], oc * u[2] * u[1] + s * u[0], co + oc * u[2] * u[2]};
@@ -199,8 +285,7 @@ RCSB_DEV void st_kinematics(const Ctx& c) {
 RCSB_DEV void geom_frame(const Ctx& c, int g, real* pos, real* mat) {
   const RcsbModel& m = CMODEL(c);
   int b = m.g_body[g];
-  real Rl[9];
-  quat_to_mat(Rl, m.g_quat[g]);
+  const real* Rl = m.g_rot[g];
   if (b < 0) {
     copy3(pos, m.g_pos[g]);
     for (int i = 0; i < 9; i++) mat[i] = Rl[i];
@@ -300,8 +385,7 @@ RCSB_DEV void st_com(const Ctx& c) {
   if (c.lane == 0) {  // attachment site pose (SimRobot::get_cartesian_position reads it after the step)
     int b = m.rb_site_body;
     real* sp = WR(rcs) + RCSB_S_SITEPOS;
-    real Rl[9];
-    quat_to_mat(Rl, m.rb_site_quat);
+    const real* Rl = m.rb_site_rot;
     if (b < 0) {
       copy3(sp, m.rb_site_pos);
       for (int i = 0; i < 9; i++) sp[3 + i] = Rl[i];
@@ -322,21 +406,20 @@ RCSB_DEV void st_com(const Ctx& c) {
 RCSB_DEV void st_crb(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
   int nv = MD(nv);
-  PFOR(e, MD(nb) * 10) {
-    int b = e / 10, k = e - 10 * b;
-    real s = 0;
-    uint32_t mask = m.b_descmask[b];
-    for (int d = b; d < MD(nb); d++)
-      if ((mask >> d) & 1u) s += WR(cinert)[10 * d + k];
-    WR(crb)[e] = s;
-  }
+  // composite inertias: every body starts from its own inertia, children fold into parents from the leaves up
+  PFOR(e, MD(nb) * 10) { WR(crb)[e] = WR(cinert)[e]; }
   RCSB_SYNC();
+  for (int b = MD(nb) - 1; b > 0; b--) {
+    const int p = m.b_parent[b];
+    if (p >= 0) PFOR(k, 10) { WR(crb)[10 * p + k] += WR(crb)[10 * b + k]; }
+    RCSB_SYNC();
+  }
   real* buf = WR(crbbuf);
   PFOR(i, nv) { mul_inert_vec(buf + 6 * i, WR(crb) + 10 * m.d_body[i], WR(cdof) + 6 * i); }
   RCSB_SYNC();
-  PFOR(e, nv * nv) {
-    int i = e / nv, j = e - i * nv;
-    if (j <= i) {
+  PFOR(t, nv * (nv + 1) / 2) {
+    const int i = m.tri_i[t], j = m.tri_j[t];
+    {
       real val = 0;
       if ((m.d_ancmask[i] >> j) & 1u) {
         const real* cd = WR(cdof) + 6 * j;
@@ -349,50 +432,56 @@ RCSB_DEV void st_crb(const Ctx& c) {
     }
   }
   // the factorisation of M is deferred (ensure_chol_M copies M into the solver scratch): the all-equality path never needs it
-  if (c.lane == 0) CWI(c)[LAY.oi_misc + MI_HAVE_L] = 0;
+  if (c.lane == 0) { CWI(c)[LAY.oi_misc + MI_HAVE_L] = 0; CWI(c)[LAY.oi_misc + MI_HAVE_H2] = 0; }
   RCSB_SYNC();
 }
 
 // ------------------------------------------------------------------ velocity stage: bias, passive, gravity compensation
 RCSB_DEV void st_velocity(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
-  int nv = MD(nv);
+  const int nv = MD(nv), nb = MD(nb);
   const real* v = WR(v);
+  // pass A, root to leaves, one lane per component: spatial velocity of every body about the tree COM
+  for (int b = 0; b < nb; b++) {
+    const int p = m.b_parent[b], da = m.b_dadr[b], nd = m.b_ndof[b];
+    PFOR(k, 6) {
+      real s = p >= 0 ? WR(cvel)[6 * p + k] : (real)0;
+      for (int a = 0; a < nd; a++) s += WR(cdof)[6 * (da + a) + k] * v[da + a];
+      WR(cvel)[6 * b + k] = s;
+    }
+    RCSB_SYNC();
+  }
+  // time derivative of every motion axis: (velocity accumulated before the dof) x axis
   PFOR(j, nv) {
     real* cdd = WR(cdofdot) + 6 * j;
     if (m.d_dotzero[j]) {
       for (int k = 0; k < 6; k++) cdd[k] = 0;
     } else {
-      real pre[6] = {0, 0, 0, 0, 0, 0};
-      uint32_t mask = m.d_premask[j];
-      for (int i = 0; i < nv; i++)
-        if ((mask >> i) & 1u) {
-          const real* cd = WR(cdof) + 6 * i;
-          for (int k = 0; k < 6; k++) pre[k] += cd[k] * v[i];
-        }
+      const int b = m.d_body[j], p = m.b_parent[b];
+      real pre[6];
+      for (int k = 0; k < 6; k++) pre[k] = p >= 0 ? WR(cvel)[6 * p + k] : (real)0;
+      if (m.b_jtype[b] == RCSB_JNT_FREE) {  // rotational dofs of a free joint see its translational velocity
+        const int da = m.b_dadr[b];
+        for (int a = 0; a < 3; a++)
+          for (int k = 0; k < 6; k++) pre[k] += WR(cdof)[6 * (da + a) + k] * v[da + a];
+      }
       cross_motion(cdd, pre, WR(cdof) + 6 * j);
     }
   }
-  PFOR(b, MD(nb)) {
-    real cv[6] = {0, 0, 0, 0, 0, 0};
-    uint32_t mask = m.b_dofmask[b];
-    for (int i = 0; i < nv; i++)
-      if ((mask >> i) & 1u) {
-        const real* cd = WR(cdof) + 6 * i;
-        for (int k = 0; k < 6; k++) cv[k] += cd[k] * v[i];
-      }
-    for (int k = 0; k < 6; k++) WR(cvel)[6 * b + k] = cv[k];
-  }
   RCSB_SYNC();
-  PFOR(b, MD(nb)) {
-    real ca[6] = {0, 0, 0, -m.gravity[0], -m.gravity[1], -m.gravity[2]};
-    uint32_t mask = m.b_dofmask[b];
-    for (int i = 0; i < nv; i++)
-      if ((mask >> i) & 1u) {
-        const real* cd = WR(cdofdot) + 6 * i;
-        for (int k = 0; k < 6; k++) ca[k] += cd[k] * v[i];
-      }
-    real Ia[6], Iv[6], x[6];
+  // pass B, root to leaves: spatial acceleration with qacc = 0 and gravity folded into the root (kept in the cfrc slots)
+  for (int b = 0; b < nb; b++) {
+    const int p = m.b_parent[b], da = m.b_dadr[b], nd = m.b_ndof[b];
+    PFOR(k, 6) {
+      real s = p >= 0 ? WR(cfrc)[6 * p + k] : (k >= 3 ? -m.gravity[k - 3] : (real)0);
+      for (int a = 0; a < nd; a++) s += WR(cdofdot)[6 * (da + a) + k] * v[da + a];
+      WR(cfrc)[6 * b + k] = s;
+    }
+    RCSB_SYNC();
+  }
+  PFOR(b, nb) {
+    real ca[6], Ia[6], Iv[6], x[6];
+    for (int k = 0; k < 6; k++) ca[k] = WR(cfrc)[6 * b + k];
     mul_inert_vec(Ia, WR(cinert) + 10 * b, ca);
     mul_inert_vec(Iv, WR(cinert) + 10 * b, WR(cvel) + 6 * b);
     cross_force(x, WR(cvel) + 6 * b, Iv);
@@ -414,17 +503,20 @@ RCSB_DEV void st_velocity(const Ctx& c) {
     }
   }
   RCSB_SYNC();
+  // leaves to root: every body collects the forces / compensation wrenches of its subtree (lanes 0-5 | 6-11)
+  for (int b = nb - 1; b > 0; b--) {
+    const int p = m.b_parent[b];
+    if (p >= 0) PFOR(k, 12) {
+      real* arr = k < 6 ? WR(cfrc) : WR(cvel) - 6;
+      arr[6 * p + k] += arr[6 * b + k];
+    }
+    RCSB_SYNC();
+  }
   PFOR(j, nv) {
-    int bj = m.d_body[j];
-    uint32_t mask = m.b_descmask[bj];
+    const int bj = m.d_body[j];
     const real* cd = WR(cdof) + 6 * j;
-    real f[6] = {0, 0, 0, 0, 0, 0}, g[6] = {0, 0, 0, 0, 0, 0};
-    for (int b = bj; b < MD(nb); b++)
-      if ((mask >> b) & 1u) {
-        const real* cf = WR(cfrc) + 6 * b;
-        const real* gw = WR(cvel) + 6 * b;
-        for (int k = 0; k < 6; k++) { f[k] += cf[k]; g[k] += gw[k]; }
-      }
+    const real* f = WR(cfrc) + 6 * bj;
+    const real* g = WR(cvel) + 6 * bj;
     WR(bias)[j] = cd[0] * f[0] + cd[1] * f[1] + cd[2] * f[2] + cd[3] * f[3] + cd[4] * f[4] + cd[5] * f[5];
     real gc = cd[0] * g[0] + cd[1] * g[1] + cd[2] * g[2] + cd[3] * g[3] + cd[4] * g[4] + cd[5] * g[5];
     WR(gravc)[j] = gc;
@@ -684,6 +776,19 @@ RCSB_DEV int compact_append(const Ctx& c, int hit, int value, int count, int* li
   return count + __popc(mask);
 #endif
 }
+// slot of this lane's item in a list that holds `count` entries, lanes with `hit` in lane order; advances count
+RCSB_DEV int compact_slot(const Ctx& c, int hit, int& count) {
+#ifdef RCSB_HOST_EMU
+  int slot = count;
+  count += hit ? 1 : 0;
+  return slot;
+#else
+  unsigned mask = warp_ballot(hit);
+  int slot = count + __popc(mask & ((1u << c.lane) - 1u));
+  count += __popc(mask);
+  return slot;
+#endif
+}
 // separating-axis test of two oriented boxes (rotation A/B row-major, centres ca/cb, half sizes ha/hb); 1 = separated
 RCSB_DEV int obb_separated(const real* A, const real* ca, const real* ha, const real* B, const real* cb, const real* hb,
                            real margin) {
@@ -736,8 +841,7 @@ RCSB_DEV void st_collision(const Ctx& c) {
       const real *a = WR(gpos) + 3 * g1, *b = WR(gpos) + 3 * g2;
       real d[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
       if (m.g_type[g1] == RCSB_GEOM_PLANE) {
-        real R[9];
-        quat_to_mat(R, m.g_quat[g1]);  // planes are static in all supported scenes
+        const real* R = m.g_rot[g1];  // planes are static in all supported scenes
         real n[3] = {R[2], R[5], R[8]};
         hit = !(dot3(d, n) > m.g_rbound[g2] + margin);
       } else {
@@ -766,8 +870,7 @@ RCSB_DEV void st_collision(const Ctx& c) {
       const real* c2 = WR(gpos) + 3 * g2;
       const real* hb = m.g_aabb[g2] + 3;
       if (m.g_type[g1] == RCSB_GEOM_PLANE) {
-        real R1[9];
-        quat_to_mat(R1, m.g_quat[g1]);
+        const real* R1 = m.g_rot[g1];
         real n[3] = {R1[2], R1[5], R1[8]}, r = 0;
         for (int j = 0; j < 3; j++) r += hb[j] * r_abs(n[0] * R2[j] + n[1] * R2[3 + j] + n[2] * R2[6 + j]);
         real dist = (c2[0] - m.g_pos[g1][0]) * n[0] + (c2[1] - m.g_pos[g1][1]) * n[1] + (c2[2] - m.g_pos[g1][2]) * n[2];

@@ -20,54 +20,7 @@
 #include "rcsb_layout.h"
 #include "rcsb_ctx.cuh"
 
-// ------------------------------------------------------------------ TMA bulk copy helpers (sm_90+/sm_100a PTX)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(phase)
-        : "memory");
-  } while (!ok);
-}
-
-#define RCSB_MODEL_BYTES ((sizeof(RcsbModel) + 15) & ~(size_t)15)
-#define RCSB_SMEM_HEADER (RCSB_MODEL_BYTES + 16)
-// warps per CTA are bounded by the per-warp shared-memory workspace (about 22 KB for the FR3 scenes),
-// so the register budget per thread can be generous
-#ifndef RCSB_MAX_WARPS
-#define RCSB_MAX_WARPS 28
-#endif
-
-__device__ __forceinline__ const RcsbModel* stage_model(const RcsbModel* gm) {
-  RcsbModel* sm = (RcsbModel*)rcsb_smem;
-  uint64_t* bar = (uint64_t*)(rcsb_smem + RCSB_MODEL_BYTES);
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, (uint32_t)RCSB_MODEL_BYTES);
-    tma_bulk_g2s(sm, gm, (uint32_t)RCSB_MODEL_BYTES, bar);
-  }
-  mbar_wait(bar, 0);
-  return sm;
-}
-
+#include "rcsb_stage.cuh"
 
 // ------------------------------------------------------------------ kernel variants
 #ifdef RCSB_STAGE_TIMING
@@ -80,22 +33,21 @@ __device__ unsigned long long rcsb_stage_cycles[16];
 #undef RCSB_KERNEL
 
 #ifndef RCSB_NO_FIXED_VARIANTS
-// fr3_empty_world (FR3 + Franka hand, no free bodies): reduced (1 contact, 8 rows) and full (6 contacts, 28 rows) layouts
-#define RCSB_SHAPE_FR3(maxcon, maxefc, reduced) {9, 9, 8, 9, 24, 182, 1, 1, 1, maxcon, maxefc, 7, 1, 1, 5, reduced, 1}
-#define RCSB_VARIANT_NS rcsb_fr3_reduced
-#define RCSB_KERNEL rcsb_k_run_fr3_reduced
-#define RCSB_FIXED_SHAPE RCSB_SHAPE_FR3(1, 8, 1)
-#include "rcsb_variant.cuh"
-#undef RCSB_VARIANT_NS
-#undef RCSB_KERNEL
-#undef RCSB_FIXED_SHAPE
-#define RCSB_VARIANT_NS rcsb_fr3_full
-#define RCSB_KERNEL rcsb_k_run_fr3_full
-#define RCSB_FIXED_SHAPE RCSB_SHAPE_FR3(6, 28, 0)
-#include "rcsb_variant.cuh"
-#undef RCSB_VARIANT_NS
-#undef RCSB_KERNEL
-#undef RCSB_FIXED_SHAPE
+// shape-specialised variants live in their own translation units (rcsb_k_fr3_*.cu) so that they compile in parallel;
+// the profiling build (-DRCSB_SINGLE_TU) pulls them in here so that they share rcsb_stage_cycles
+#ifdef RCSB_SINGLE_TU
+#include "rcsb_k_fr3_reduced.cu"
+#include "rcsb_k_fr3_full.cu"
+#else
+#define RCSB_DECLARE_VARIANT(ns)                                                                                        \
+  namespace ns {                                                                                                        \
+  void launch(int, int, size_t, cudaStream_t, const RcsbModel*, const real*, real*, double*, int*, const RcsbLaunch&, int*, size_t); \
+  cudaError_t set_smem(size_t);                                                                                         \
+  RcsbShape shape();                                                                                                    \
+  }
+RCSB_DECLARE_VARIANT(rcsb_fr3_reduced)
+RCSB_DECLARE_VARIANT(rcsb_fr3_full)
+#endif
 #endif
 
 typedef void (*rcsb_launch_fn)(int, int, size_t, cudaStream_t, const RcsbModel*, const real*, real*, double*, int*, const RcsbLaunch&,

@@ -127,6 +127,12 @@ RCSB_HD constexpr RcsbLayout rcsb_make_layout(const RcsbShape& s) {
 #undef RCSB_MAX
   return y;
 }
+static inline void rcsb_host_quat_to_mat(real* M, const real* q) {  // same expression order as quat_to_mat (rcsb_warp.cuh)
+  real w = q[0], x = q[1], y = q[2], z = q[3];
+  M[0] = w * w + x * x - y * y - z * z; M[1] = 2 * (x * y - w * z); M[2] = 2 * (x * z + w * y);
+  M[3] = 2 * (x * y + w * z); M[4] = w * w - x * x + y * y - z * z; M[5] = 2 * (y * z - w * x);
+  M[6] = 2 * (x * z - w * y); M[7] = 2 * (y * z + w * x); M[8] = w * w - x * x - y * y + z * z;
+}
 static inline RcsbShape rcsb_model_shape(const RcsbModel* m) {
   RcsbShape s = {m->nq, m->nv, m->nu, m->nb, m->ng, m->npair, m->nt, m->neq, m->nroot, m->maxcon, m->maxefc, m->rb_njoints,
                  m->cone_elliptic, m->implicitfast, m->noslip_iterations, m->cap_reduced, m->gr_enabled};
@@ -138,6 +144,20 @@ static inline int rcsb_model_finalize_layout(RcsbModel* m) {
       m->nroot > RCSB_MAXROOT || m->rb_njoints > RCSB_MAXJ || m->maxcon < 1 || m->maxefc < 1)
     return -1;
   m->lay = rcsb_make_layout(rcsb_model_shape(m));
+  for (int a = 0; a < RCSB_MAXU; a++)
+    for (int k = 0; k < RCSB_MAXV; k++) {
+      real v = 0;
+      if (a < m->nu && k < m->nv) {
+        if (m->a_trntype[a] == RCSB_TRN_JOINT) v = m->a_trnid[a] == k ? m->a_gear[a] : (real)0;
+        else v = m->a_gear[a] * m->t_coef[m->a_trnid[a]][k];
+      }
+      m->a_moment[a][k] = v;
+    }
+  for (int b = 0; b < m->nb; b++) rcsb_host_quat_to_mat(m->b_rot[b], m->b_quat[b]);
+  for (int g = 0; g < m->ng; g++) rcsb_host_quat_to_mat(m->g_rot[g], m->g_quat[g]);
+  rcsb_host_quat_to_mat(m->rb_site_rot, m->rb_site_quat);
+  for (int i = 0, t = 0; i < RCSB_MAXV; i++)
+    for (int j = 0; j <= i; j++, t++) { m->tri_i[t] = (uint8_t)i; m->tri_j[t] = (uint8_t)j; }
   return 0;
 }
 // The reduced-capacity copy of a finalised model (see RcsbModel::fast_maxcon); returns 0 when there is none.

@@ -49,26 +49,30 @@ RCSB_DEV void st_make_constraint(const Ctx& c) {
       if (c.lane == 0) { etype[nefc] = RCSB_EQ; eid[nefc] = e; }
       nefc++; ne++;
     }
-  for (int j = 0; j < nv; j++)
-    if (m.d_frictionloss[j] > 0) {
-      if (c.lane == 0) { etype[nefc] = RCSB_FRICTION_DOF; eid[nefc] = j; }
-      nefc++; nf++;
-    }
-  for (int j = 0; j < nv; j++)
-    if (m.d_limited[j]) {
+  // friction-loss rows (one per dof with frictionloss > 0) and joint-limit rows (dof j, side s -> item 2j+s), one item
+  // per lane, compacted in item order
+  for (int base = 0; base < nv; base += RCSB_NLANES) {
+    int j = base + c.lane;
+    int hit = j < nv && m.d_frictionloss[j] > 0;
+    int slot = compact_slot(c, hit, nefc);
+    if (hit) { etype[slot] = RCSB_FRICTION_DOF; eid[slot] = j; }
+  }
+  nf = nefc - ne;
+  for (int base = 0; base < 2 * nv; base += RCSB_NLANES) {
+    int item = base + c.lane, j = item >> 1, side = item & 1, hit = 0;
+    if (item < 2 * nv && m.d_limited[j]) {
       real qj = q[m.d_qadr[j]];
-      for (int side = 0; side < 2; side++) {
-        real dist = side ? (m.d_range[j][1] - qj) : (qj - m.d_range[j][0]);
-        if (dist < m.d_margin[j]) {
-          if (nefc < maxefc) {
-            if (c.lane == 0) { etype[nefc] = RCSB_LIMIT; eid[nefc] = 2 * j + side; }
-            nefc++; nl++;
-          } else if (c.lane == 0) {
-            WI(misc)[MD(cap_reduced) ? MI_OVERFLOW : MI_WARN] += 1;
-          }
-        }
-      }
+      real dist = side ? (m.d_range[j][1] - qj) : (qj - m.d_range[j][0]);
+      hit = dist < m.d_margin[j];
     }
+    int slot = compact_slot(c, hit, nefc);
+    if (hit) {
+      if (slot < maxefc) { etype[slot] = RCSB_LIMIT; eid[slot] = item; }
+      else WI(misc)[MD(cap_reduced) ? MI_OVERFLOW : MI_WARN] = 1;
+    }
+  }
+  if (nefc > maxefc) nefc = maxefc;
+  nl = nefc - ne - nf;
   for (int ci = 0; ci < ncon; ci++) {
     const real* cr = WR(con) + RCSB_C_REALS * ci;
     int* cii = WI(con) + RCSB_CI_INTS * ci;
@@ -239,10 +243,7 @@ RCSB_DEV void st_actuation(const Ctx& c) {
   RCSB_SYNC();
   PFOR(k, nv) {
     real s = 0;
-    for (int a = 0; a < MD(nu); a++) {
-      real mom = m.a_trntype[a] == RCSB_TRN_JOINT ? (m.a_trnid[a] == k ? m.a_gear[a] : (real)0) : m.a_gear[a] * m.t_coef[m.a_trnid[a]][k];
-      s += mom * WR(aforce)[a];
-    }
+    for (int a = 0; a < MD(nu); a++) s += m.a_moment[a][k] * WR(aforce)[a];
     if (m.d_actgravcomp[k]) s += WR(gravc)[k];
     if (m.d_actfrclimited[k]) s = s < m.d_actfrcrange[k][0] ? m.d_actfrcrange[k][0] : (s > m.d_actfrcrange[k][1] ? m.d_actfrcrange[k][1] : s);
     WR(actfrc)[k] = s;
@@ -255,6 +256,7 @@ RCSB_DEV void st_actuation(const Ctx& c) {
 RCSB_DEV void ensure_chol_M(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
   if (!WI(misc)[MI_HAVE_L]) {
+    if (c.lane == 0) WI(misc)[MI_HAVE_H2] = 0;  // o_L is about to hold M's factor
     PFOR(e, MD(nv) * MD(nv)) { WR(L)[e] = WR(M)[e]; }
     chol_factor(c, WR(L), WR(L) + MD(nv) * MD(nv), MD(nv));
     if (c.lane == 0) WI(misc)[MI_HAVE_L] = 1;
@@ -579,6 +581,7 @@ RCSB_DEV_NOINLINE void solve_noslip(const Ctx& c, int nefc, int ncon) {
 }
 
 // ------------------------------------------------------------------ constrained acceleration (Newton)
+RCSB_DEV void build_integrator_matrix(const Ctx& c, real* dst);
 RCSB_DEV void st_constraint_solve(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
   const int nv = MD(nv);
@@ -614,10 +617,9 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
     RCSB_SYNC();
     int verified = 0, attempt = 0;
     for (; attempt < 3 && !verified; attempt++) {
-      PFOR(e, nv * nv) {
-        int a = e / nv, b = e - a * nv;
-        if (b > a) continue;
-        real h = WR(M)[e];
+      PFOR(t, nv * (nv + 1) / 2) {
+        const int a = m.tri_i[t], b = m.tri_j[t];
+        real h = WR(M)[a * nv + b];
         for (int r = 0; r < nefc; r++)
           if (state[r] == RCSB_QUADRATIC) h += EFC(RCSB_E_D)[r] * WR(J)[r * nv + a] * WR(J)[r * nv + b];
         WR(H)[a * nv + b] = h;
@@ -633,8 +635,12 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
         }
         WR(qacc)[k] = s;
       }
-      chol_factor(c, WR(H), WR(H) + nv * nv, nv);
-      chol_solve(c, WR(H), WR(H) + nv * nv, nv, WR(qacc), WR(tmp));
+      // the integrator's matrix does not depend on the constraint forces: on the first pass it is factored in the
+      // idle half of the warp (o_L is free here: M's own factor is only needed by the Newton / noslip path)
+      const int dual = attempt == 0 && nv <= 16 && !WI(misc)[MI_HAVE_L];
+      if (dual) build_integrator_matrix(c, WR(L));
+      chol_factor_solve(c, WR(H), WR(H) + nv * nv, nv, WR(qacc), WR(tmp), dual ? WR(L) : nullptr, dual ? WR(L) + nv * nv : nullptr);
+      if (dual && c.lane == 0) WI(misc)[MI_HAVE_H2] = 1;
       int changed = 0;
       PFOR(r, nefc) {
         real s = 0;
@@ -685,10 +691,9 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
   while (iter < m.iterations) {
     compute_qfc(c, nefc);
     // Hessian H = M + J^T diag(D_active) J + cone blocks
-    PFOR(e, nv * nv) {
-      int a = e / nv, b = e - a * nv;
-      if (b > a) continue;
-      real h = WR(M)[e];
+    PFOR(t, nv * (nv + 1) / 2) {
+      const int a = m.tri_i[t], b = m.tri_j[t];
+      real h = WR(M)[a * nv + b];
       for (int r = 0; r < nefc; r++)
         if (state[r] == RCSB_QUADRATIC) h += EFC(RCSB_E_D)[r] * WR(J)[r * nv + a] * WR(J)[r * nv + b];
       for (int ci = 0; ci < ncon; ci++) {
@@ -702,9 +707,8 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
       WR(H)[a * nv + b] = h;
       WR(H)[b * nv + a] = h;
     }
-    chol_factor(c, WR(H), WR(H) + nv * nv, nv);
     PFOR(k, nv) { WR(search)[k] = WR(grad)[k]; }
-    chol_solve(c, WR(H), WR(H) + nv * nv, nv, WR(search), WR(tmp));
+    chol_factor_solve(c, WR(H), WR(H) + nv * nv, nv, WR(search), WR(tmp), nullptr, nullptr);
     PFOR(k, nv) { WR(search)[k] = -WR(search)[k]; }
     RCSB_SYNC();
     real qG1 = 0, qG2 = 0, sn = 0;
@@ -749,13 +753,13 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
 }
 
 // ------------------------------------------------------------------ implicitfast / Euler integration + mj_advance
-RCSB_DEV void st_integrate(const Ctx& c) {
+// M - h * d(passive + actuator force)/d(qvel): the implicitfast system matrix (symmetric; plain M for Euler)
+RCSB_DEV void build_integrator_matrix(const Ctx& c, real* dst) {
   const RcsbModel& m = CMODEL(c);
   const int nv = MD(nv);
   const real h = m.timestep;
-  PFOR(e, nv * nv) {
-    int i = e / nv, j = e - i * nv;
-    if (j > i) continue;
+  PFOR(t, nv * (nv + 1) / 2) {
+    const int i = m.tri_i[t], j = m.tri_j[t], e = i * nv + j;
     real dv = (i == j) ? -m.d_damping[i] + (MD(implicitfast) ? m.d_kvdiag[i] : (real)0) : (real)0;
     if (MD(implicitfast)) {
       for (int sa = 0; sa < m.n_special; sa++) {
@@ -764,19 +768,25 @@ RCSB_DEV void st_integrate(const Ctx& c) {
         if (bv == 0) continue;
         real fa = WR(aforce)[a];
         if (m.a_forcelimited[a] && (fa <= m.a_forcerange[a][0] || fa >= m.a_forcerange[a][1])) continue;
-        real mi, mj;
-        if (m.a_trntype[a] == RCSB_TRN_JOINT) { mi = m.a_trnid[a] == i ? m.a_gear[a] : (real)0; mj = m.a_trnid[a] == j ? m.a_gear[a] : (real)0; }
-        else { mi = m.a_gear[a] * m.t_coef[m.a_trnid[a]][i]; mj = m.a_gear[a] * m.t_coef[m.a_trnid[a]][j]; }
-        dv += bv * mi * mj;
+        dv += bv * m.a_moment[a][i] * m.a_moment[a][j];
       }
     }
     real val = WR(M)[e] - h * dv;
-    WR(H)[i * nv + j] = val;
-    WR(H)[j * nv + i] = val;
+    dst[i * nv + j] = val;
+    dst[j * nv + i] = val;
   }
+}
+RCSB_DEV void st_integrate(const Ctx& c) {
+  const RcsbModel& m = CMODEL(c);
+  const int nv = MD(nv);
+  const real h = m.timestep;
   PFOR(k, nv) { WR(search)[k] = WR(smooth)[k] + WR(qfc)[k]; }
-  chol_factor(c, WR(H), WR(H) + nv * nv, nv);
-  chol_solve(c, WR(H), WR(H) + nv * nv, nv, WR(search), WR(tmp));
+  if (WI(misc)[MI_HAVE_H2]) {  // factored next to the constraint Hessian (st_constraint_solve)
+    chol_solve(c, WR(L), WR(L) + nv * nv, nv, WR(search), WR(tmp));
+  } else {
+    build_integrator_matrix(c, WR(H));
+    chol_factor_solve(c, WR(H), WR(H) + nv * nv, nv, WR(search), WR(tmp), nullptr, nullptr);
+  }
   PFOR(k, nv) {
     WR(v)[k] += h * WR(search)[k];
     WR(warm)[k] = WR(qacc)[k];

@@ -106,6 +106,7 @@ struct RcsbModel {
   uint32_t b_descmask[RCSB_MAXB];  // descendants incl. self
   uint32_t b_dofmask[RCSB_MAXB];   // dofs of self and all ancestors
   real b_pos[RCSB_MAXB][3], b_quat[RCSB_MAXB][4];  // frame in parent moving body (or world) at qpos0
+  real b_rot[RCSB_MAXB][9];                        // rotation matrix of b_quat, derived in rcsb_model_finalize_layout
   real b_jpos[RCSB_MAXB][3], b_jaxis[RCSB_MAXB][3];
   real b_mass[RCSB_MAXB], b_ipos[RCSB_MAXB][3], b_inertia[RCSB_MAXB][6];  // xx yy zz xy xz yz about COM, body axes
   real b_gcmass[RCSB_MAXB], b_gcpos[RCSB_MAXB][3];                        // sum(gravcomp*mass) and its centre
@@ -124,6 +125,7 @@ struct RcsbModel {
   int g_body[RCSB_MAXG], g_type[RCSB_MAXG], g_vertadr[RCSB_MAXG], g_vertnum[RCSB_MAXG], g_origid[RCSB_MAXG],
       g_role[RCSB_MAXG], g_condim[RCSB_MAXG], g_priority[RCSB_MAXG];
   real g_pos[RCSB_MAXG][3], g_quat[RCSB_MAXG][4];  // in the moving body frame (world frame if g_body < 0)
+  real g_rot[RCSB_MAXG][9];                        // rotation matrix of g_quat, derived
   real g_bpos[RCSB_MAXG][3];  // bounding-volume centre (local AABB centre) in the moving body frame; g_rbound is about it
   real g_size[RCSB_MAXG][3], g_rbound[RCSB_MAXG], g_aabb[RCSB_MAXG][6], g_friction[RCSB_MAXG][3], g_solref[RCSB_MAXG][2],
       g_solimp[RCSB_MAXG][5], g_solmix[RCSB_MAXG], g_margin[RCSB_MAXG], g_gap[RCSB_MAXG], g_invweight[RCSB_MAXG];
@@ -136,9 +138,12 @@ struct RcsbModel {
   // implicitfast derivative: joint actuators that can never be force-clamped fold into a per-dof constant
   int n_special, a_special[RCSB_MAXU];  // actuators that need the per-step treatment (tendon transmission or forcerange)
   real d_kvdiag[RCSB_MAXV];             // sum of bias2*gear^2 of the folded joint actuators
+  real a_moment[RCSB_MAXU][RCSB_MAXV];  // d(actuator length)/d(qpos of dof), derived in rcsb_model_finalize_layout
+  uint8_t tri_i[RCSB_MAXV * (RCSB_MAXV + 1) / 2], tri_j[RCSB_MAXV * (RCSB_MAXV + 1) / 2];  // lower-triangle entry list (i >= j), derived
   real a_gear[RCSB_MAXU], a_gain[RCSB_MAXU], a_bias[RCSB_MAXU][3], a_ctrlrange[RCSB_MAXU][2], a_forcerange[RCSB_MAXU][2];
   // ---- RCS device layer: SimRobot / SimGripper configuration
   int rb_njoints, rb_qadr[RCSB_MAXJ], rb_act[RCSB_MAXJ], rb_site_body, rb_register_convergence, rb_ik_nq;
+  real rb_site_rot[9];  // rotation matrix of rb_site_quat, derived
   real rb_site_pos[3], rb_site_quat[4], rb_base_pos[3], rb_base_quat[4] /* wxyz */, rb_tcp_offset[7] /* xyz+xyzw */;
   real rb_q_home[RCSB_MAXJ], rb_joint_tol, rb_cb_period;
   int gr_enabled, gr_act, gr_qadr;

@@ -4,6 +4,11 @@
 //   RCSB_VARIANT_NS   namespace of the variant
 //   RCSB_KERNEL       name of its __global__ entry point
 //   RCSB_FIXED_SHAPE  (optional) brace initialiser of an RcsbShape
+#if defined(RCSB_FIXED_SHAPE) && !defined(RCSB_SINGLE_TU)
+#define RCSB_VARIANT_LINKAGE
+#else
+#define RCSB_VARIANT_LINKAGE static
+#endif
 namespace RCSB_VARIANT_NS {
 #ifdef RCSB_FIXED_SHAPE
 static constexpr RcsbShape kShape = RCSB_FIXED_SHAPE;
@@ -92,17 +97,18 @@ RCSB_KERNEL(const RcsbModel* __restrict__ gm, const real* __restrict__ verts, re
 }
 
 
-static void launch(int grid, int threads, size_t smem, cudaStream_t stream, const RcsbModel* gm, const real* verts, real* sr,
+RCSB_VARIANT_LINKAGE void launch(int grid, int threads, size_t smem, cudaStream_t stream, const RcsbModel* gm, const real* verts, real* sr,
                    double* sd, int* si, const RcsbLaunch& L, int* counter, size_t ws_bytes) {
   RCSB_KERNEL<<<grid, threads, smem, stream>>>(gm, verts, sr, sd, si, L, counter, ws_bytes);
 }
-static cudaError_t set_smem(size_t bytes) {
+RCSB_VARIANT_LINKAGE cudaError_t set_smem(size_t bytes) {
   return cudaFuncSetAttribute(RCSB_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 #ifdef RCSB_FIXED_SHAPE
-static RcsbShape shape() { return kShape; }
+RCSB_VARIANT_LINKAGE RcsbShape shape() { return kShape; }
 #endif
 #endif
 #undef MD
 #undef LAY
+#undef RCSB_VARIANT_LINKAGE
 }  // namespace
