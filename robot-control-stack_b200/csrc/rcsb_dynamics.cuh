@@ -213,11 +213,9 @@ RCSB_DEV_NOINLINE void chol_factor_solve(const Ctx& c, real* A, real* dinv, int 
 RCSB_DEV void st_kinematics(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
   real* q = WR(q);
-  real* Rl = WR(bquat);            // scratch: local rotation [nb][9] then local translation [nb][3] (o_bquat holds 12*nb)
-  real* tl = Rl + 9 * MD(nb);
+  real* L4 = WR(bquat);  // scratch: every body's local frame [R | t] as a 3 x 4 row-major block (o_bquat holds 12*nb)
   PFOR(b, MD(nb)) {
-    real* R = Rl + 9 * b;
-    real* t = tl + 3 * b;
+    real R[9], t[3];
     if (m.b_jtype[b] == RCSB_JNT_FREE) {
       real* qq = q + m.b_qadr[b];
       quat_normalize(qq + 3);
@@ -250,32 +248,27 @@ RCSB_DEV void st_kinematics(const Ctx& c) {
         t[0] = m.b_pos[b][0] + v[0]; t[1] = m.b_pos[b][1] + v[1]; t[2] = m.b_pos[b][2] + v[2];
       }
     }
+    real* o = L4 + 12 * b;
+    for (int r = 0; r < 3; r++) { o[4 * r] = R[3 * r]; o[4 * r + 1] = R[3 * r + 1]; o[4 * r + 2] = R[3 * r + 2]; o[4 * r + 3] = t[r]; }
   }
   RCSB_SYNC();
+  // chain walk, 12 lanes per body: entry (r, k) of [R | p]_world = [R_parent | p_parent] * [R | t]_local
   for (int b = 0; b < MD(nb); b++) {
     const int p = m.b_parent[b];
-    PFOR(e, 12) {
-      if (e < 9) {
-        int r = e / 3, k = e - 3 * r;
-        real val;
-        if (p < 0) val = Rl[9 * b + e];
-        else {
-          const real* Rp = WR(bmat) + 9 * p + 3 * r;
-          const real* Rc = Rl + 9 * b + k;
-          val = Rp[0] * Rc[0] + Rp[1] * Rc[3] + Rp[2] * Rc[6];
-        }
-        WR(bmat)[9 * b + e] = val;
-      } else {
-        int r = e - 9;
-        real val;
-        if (p < 0) val = tl[3 * b + r];
-        else {
-          const real* Rp = WR(bmat) + 9 * p + 3 * r;
-          const real* tc = tl + 3 * b;
-          val = WR(bpos)[3 * p + r] + Rp[0] * tc[0] + Rp[1] * tc[1] + Rp[2] * tc[2];
-        }
-        WR(bpos)[3 * b + r] = val;
+    PFOR1(e, 12) {
+      const int r = e >> 2, k = e & 3;
+      const real* Lc = L4 + 12 * b + k;
+      real val;
+      if (p < 0) val = Lc[4 * r];
+      else {
+        const real* Rp = WR(bmat) + 9 * p + 3 * r;
+        val = k == 3 ? WR(bpos)[3 * p + r] : (real)0;
+        val += Rp[0] * Lc[0];
+        val += Rp[1] * Lc[4];
+        val += Rp[2] * Lc[8];
       }
+      real* dst = k == 3 ? WR(bpos) + 3 * b + r : WR(bmat) + 9 * b + 3 * r + k;
+      *dst = val;
     }
     RCSB_SYNC();
   }
@@ -311,16 +304,19 @@ RCSB_DEV void body_com(const Ctx& c, int b, real* o) {
 }
 RCSB_DEV void st_com(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
-  PFOR(r, MD(nroot)) {
-    real s[3] = {0, 0, 0};
+  real* mc = WR(crb);  // scratch (crb is written later): mass-weighted body COMs
+  PFOR(b, MD(nb)) {
+    real o[3];
+    body_com(c, b, o);
+    mc[3 * b] = m.b_mass[b] * o[0]; mc[3 * b + 1] = m.b_mass[b] * o[1]; mc[3 * b + 2] = m.b_mass[b] * o[2];
+  }
+  RCSB_SYNC();
+  PFOR(e, 3 * MD(nroot)) {
+    const int r = e / 3, k = e - 3 * r;
+    real s = 0;
     for (int b = 0; b < MD(nb); b++)
-      if (m.b_root[b] == r) {
-        real o[3];
-        body_com(c, b, o);
-        s[0] += m.b_mass[b] * o[0]; s[1] += m.b_mass[b] * o[1]; s[2] += m.b_mass[b] * o[2];
-      }
-    real* rc = WR(rootcom) + 3 * r;
-    rc[0] = s[0] * m.r_invmass[r]; rc[1] = s[1] * m.r_invmass[r]; rc[2] = s[2] * m.r_invmass[r];
+      if (m.b_root[b] == r) s += mc[3 * b + k];
+    WR(rootcom)[e] = s * m.r_invmass[r];
   }
   RCSB_SYNC();
   PFOR(b, MD(nb)) {  // inertia about the tree COM, world axes
@@ -382,21 +378,25 @@ RCSB_DEV void st_com(const Ctx& c) {
       cross3(cd + 3, axis, off);
     }
   }
-  if (c.lane == 0) {  // attachment site pose (SimRobot::get_cartesian_position reads it after the step)
-    int b = m.rb_site_body;
+  PFOR1(e, 12) {  // attachment site pose (SimRobot::get_cartesian_position reads it after the step): xpos[3] | xmat[9]
+    const int b = m.rb_site_body;
     real* sp = WR(rcs) + RCSB_S_SITEPOS;
     const real* Rl = m.rb_site_rot;
-    if (b < 0) {
-      copy3(sp, m.rb_site_pos);
-      for (int i = 0; i < 9; i++) sp[3 + i] = Rl[i];
+    if (e < 3) {
+      real val = m.rb_site_pos[e];
+      if (b >= 0) {
+        const real* R = WR(bmat) + 9 * b + 3 * e;
+        val = WR(bpos)[3 * b + e] + (R[0] * m.rb_site_pos[0] + R[1] * m.rb_site_pos[1] + R[2] * m.rb_site_pos[2]);
+      }
+      sp[e] = val;
     } else {
-      const real* R = WR(bmat) + 9 * b;
-      const real* p = WR(bpos) + 3 * b;
-      real v[3];
-      mulmat3(v, R, m.rb_site_pos);
-      sp[0] = p[0] + v[0]; sp[1] = p[1] + v[1]; sp[2] = p[2] + v[2];
-      for (int r = 0; r < 3; r++)
-        for (int k = 0; k < 3; k++) sp[3 + 3 * r + k] = R[3 * r] * Rl[k] + R[3 * r + 1] * Rl[3 + k] + R[3 * r + 2] * Rl[6 + k];
+      const int r = (e - 3) / 3, k = (e - 3) - 3 * r;
+      real val = Rl[3 * r + k];
+      if (b >= 0) {
+        const real* R = WR(bmat) + 9 * b + 3 * r;
+        val = R[0] * Rl[k] + R[1] * Rl[3 + k] + R[2] * Rl[6 + k];
+      }
+      sp[e] = val;
     }
   }
   RCSB_SYNC();
@@ -411,7 +411,7 @@ RCSB_DEV void st_crb(const Ctx& c) {
   RCSB_SYNC();
   for (int b = MD(nb) - 1; b > 0; b--) {
     const int p = m.b_parent[b];
-    if (p >= 0) PFOR(k, 10) { WR(crb)[10 * p + k] += WR(crb)[10 * b + k]; }
+    if (p >= 0) PFOR1(k, 10) { WR(crb)[10 * p + k] += WR(crb)[10 * b + k]; }
     RCSB_SYNC();
   }
   real* buf = WR(crbbuf);
@@ -441,54 +441,41 @@ RCSB_DEV void st_velocity(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
   const int nv = MD(nv), nb = MD(nb);
   const real* v = WR(v);
-  // pass A, root to leaves, one lane per component: spatial velocity of every body about the tree COM
-  for (int b = 0; b < nb; b++) {
-    const int p = m.b_parent[b], da = m.b_dadr[b], nd = m.b_ndof[b];
-    PFOR(k, 6) {
-      real s = p >= 0 ? WR(cvel)[6 * p + k] : (real)0;
-      for (int a = 0; a < nd; a++) s += WR(cdof)[6 * (da + a) + k] * v[da + a];
-      WR(cvel)[6 * b + k] = s;
-    }
+  // pass A, root to leaves along the dof chain, one lane per component: spatial velocity accumulated up to and including
+  // every dof (a body's velocity is that of its last dof)
+  for (int j = 0; j < nv; j++) {
+    const int pj = m.d_parent[j];
+    PFOR1(k, 6) { WR(cvel)[6 * j + k] = (pj >= 0 ? WR(cvel)[6 * pj + k] : (real)0) + WR(cdof)[6 * j + k] * v[j]; }
     RCSB_SYNC();
   }
   // time derivative of every motion axis: (velocity accumulated before the dof) x axis
   PFOR(j, nv) {
     real* cdd = WR(cdofdot) + 6 * j;
-    if (m.d_dotzero[j]) {
+    const int pre = m.d_pre[j];
+    if (m.d_dotzero[j] || pre < 0) {
       for (int k = 0; k < 6; k++) cdd[k] = 0;
     } else {
-      const int b = m.d_body[j], p = m.b_parent[b];
-      real pre[6];
-      for (int k = 0; k < 6; k++) pre[k] = p >= 0 ? WR(cvel)[6 * p + k] : (real)0;
-      if (m.b_jtype[b] == RCSB_JNT_FREE) {  // rotational dofs of a free joint see its translational velocity
-        const int da = m.b_dadr[b];
-        for (int a = 0; a < 3; a++)
-          for (int k = 0; k < 6; k++) pre[k] += WR(cdof)[6 * (da + a) + k] * v[da + a];
-      }
-      cross_motion(cdd, pre, WR(cdof) + 6 * j);
+      cross_motion(cdd, WR(cvel) + 6 * pre, WR(cdof) + 6 * j);
     }
   }
   RCSB_SYNC();
-  // pass B, root to leaves: spatial acceleration with qacc = 0 and gravity folded into the root (kept in the cfrc slots)
-  for (int b = 0; b < nb; b++) {
-    const int p = m.b_parent[b], da = m.b_dadr[b], nd = m.b_ndof[b];
-    PFOR(k, 6) {
-      real s = p >= 0 ? WR(cfrc)[6 * p + k] : (k >= 3 ? -m.gravity[k - 3] : (real)0);
-      for (int a = 0; a < nd; a++) s += WR(cdofdot)[6 * (da + a) + k] * v[da + a];
-      WR(cfrc)[6 * b + k] = s;
+  // pass B: spatial acceleration with qacc = 0 and gravity folded into the root
+  for (int j = 0; j < nv; j++) {
+    const int pj = m.d_parent[j];
+    PFOR1(k, 6) {
+      WR(cacc)[6 * j + k] = (pj >= 0 ? WR(cacc)[6 * pj + k] : (k >= 3 ? -m.gravity[k - 3] : (real)0)) + WR(cdofdot)[6 * j + k] * v[j];
     }
     RCSB_SYNC();
   }
   PFOR(b, nb) {
-    real ca[6], Ia[6], Iv[6], x[6];
-    for (int k = 0; k < 6; k++) ca[k] = WR(cfrc)[6 * b + k];
-    mul_inert_vec(Ia, WR(cinert) + 10 * b, ca);
-    mul_inert_vec(Iv, WR(cinert) + 10 * b, WR(cvel) + 6 * b);
-    cross_force(x, WR(cvel) + 6 * b, Iv);
-    for (int k = 0; k < 6; k++) WR(cfrc)[6 * b + k] = Ia[k] + x[k];
-    // cvel[b] is dead from here on: its slot takes the body's gravity-compensation wrench [torque; force] about the
-    // tree COM (force -gcmass*g applied at the compensated mass centre)
-    real* gw = WR(cvel) + 6 * b;
+    const int jl = m.b_lastdof[b];
+    real Ia[6], Iv[6], x[6];
+    mul_inert_vec(Ia, WR(cinert) + 10 * b, WR(cacc) + 6 * jl);
+    mul_inert_vec(Iv, WR(cinert) + 10 * b, WR(cvel) + 6 * jl);
+    cross_force(x, WR(cvel) + 6 * jl, Iv);
+    for (int k = 0; k < 6; k++) WR(cfrc)[6 * b + k] = Ia[k] + x[k];  // cdof_dot is dead: cfrc shares its slots
+    // gravity-compensation wrench [torque; force] about the tree COM (force -gcmass*g at the compensated mass centre)
+    real* gw = WR(gcw) + 6 * jl;  // the acceleration in this slot was consumed above, by this lane only
     real gm = m.b_gcmass[b];
     if (gm != 0) {
       const real* rc = WR(rootcom) + 3 * m.b_root[b];
@@ -506,9 +493,9 @@ RCSB_DEV void st_velocity(const Ctx& c) {
   // leaves to root: every body collects the forces / compensation wrenches of its subtree (lanes 0-5 | 6-11)
   for (int b = nb - 1; b > 0; b--) {
     const int p = m.b_parent[b];
-    if (p >= 0) PFOR(k, 12) {
-      real* arr = k < 6 ? WR(cfrc) : WR(cvel) - 6;
-      arr[6 * p + k] += arr[6 * b + k];
+    if (p >= 0) PFOR1(k, 12) {
+      if (k < 6) WR(cfrc)[6 * p + k] += WR(cfrc)[6 * b + k];
+      else WR(gcw)[6 * m.b_lastdof[p] + k - 6] += WR(gcw)[6 * m.b_lastdof[b] + k - 6];
     }
     RCSB_SYNC();
   }
@@ -516,7 +503,7 @@ RCSB_DEV void st_velocity(const Ctx& c) {
     const int bj = m.d_body[j];
     const real* cd = WR(cdof) + 6 * j;
     const real* f = WR(cfrc) + 6 * bj;
-    const real* g = WR(cvel) + 6 * bj;
+    const real* g = WR(gcw) + 6 * m.b_lastdof[bj];
     WR(bias)[j] = cd[0] * f[0] + cd[1] * f[1] + cd[2] * f[2] + cd[3] * f[3] + cd[4] * f[4] + cd[5] * f[5];
     real gc = cd[0] * g[0] + cd[1] * g[1] + cd[2] * g[2] + cd[3] * g[3] + cd[4] * g[4] + cd[5] * g[5];
     WR(gravc)[j] = gc;

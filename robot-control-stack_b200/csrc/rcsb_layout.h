@@ -97,7 +97,9 @@ RCSB_HD constexpr RcsbLayout rcsb_make_layout(const RcsbShape& s) {
   u_end = RCSB_MAX(u_end, o); o = u_begin;
   RCSB_ALLOC(o_gpos, 3 * s.ng); RCSB_ALLOC(o_cand, (2 * RCSB_MAXCAND * (int)sizeof(int) + (int)sizeof(real) - 1) / (int)sizeof(real));
   u_end = RCSB_MAX(u_end, o); o = u_begin;
-  RCSB_ALLOC(o_cdofdot, 6 * nv); RCSB_ALLOC(o_cvel, 6 * nb); RCSB_ALLOC(o_cfrc, 6 * nb);
+  RCSB_ALLOC(o_cdofdot, 6 * nv); RCSB_ALLOC(o_cvel, 6 * nv); RCSB_ALLOC(o_cacc, 6 * nv);
+  y.o_gcw = y.o_cacc;  // gravity-compensation wrenches replace the accelerations, body b in the slot of its last dof
+  y.o_cfrc = y.o_cdofdot;  // body forces take over the cdof_dot slots once the accelerations are known (nb <= nv)
   u_end = RCSB_MAX(u_end, o);
   const int k_end = u_end;
   o = k_begin;
@@ -156,6 +158,16 @@ static inline int rcsb_model_finalize_layout(RcsbModel* m) {
   for (int b = 0; b < m->nb; b++) rcsb_host_quat_to_mat(m->b_rot[b], m->b_quat[b]);
   for (int g = 0; g < m->ng; g++) rcsb_host_quat_to_mat(m->g_rot[g], m->g_quat[g]);
   rcsb_host_quat_to_mat(m->rb_site_rot, m->rb_site_quat);
+  for (int b = 0; b < m->nb; b++) {
+    const int da = m->b_dadr[b], nd = m->b_ndof[b], p = m->b_parent[b];
+    m->b_lastdof[b] = da + nd - 1;
+    for (int a = 0; a < nd; a++) {
+      const int j = da + a, up = p >= 0 ? m->b_dadr[p] + m->b_ndof[p] - 1 : -1;
+      m->d_parent[j] = a > 0 ? j - 1 : up;
+      // free joint: the rotational dofs see the velocity after the three translational ones; hinge / slide: the parent's
+      m->d_pre[j] = (m->b_jtype[b] == RCSB_JNT_FREE) ? (a >= 3 ? da + 2 : -1) : up;
+    }
+  }
   for (int i = 0, t = 0; i < RCSB_MAXV; i++)
     for (int j = 0; j <= i; j++, t++) { m->tri_i[t] = (uint8_t)i; m->tri_j[t] = (uint8_t)j; }
   return 0;

@@ -77,7 +77,7 @@ enum {
 struct RcsbLayout {
   int ws_reals, ws_ints, nsr;  // nsr = reals per env in HBM (dynamic state + RCS tail)
   int o_q, o_v, o_ctrl, o_warm, o_bpos, o_bquat, o_bmat, o_rootcom, o_cinert, o_crb, o_crbbuf,
-      o_cdof, o_cdofdot, o_cvel, o_cfrc, o_M, o_L, o_H, o_bias, o_passive, o_gravc, o_actfrc, o_smooth,
+      o_cdof, o_cdofdot, o_cvel, o_cacc, o_cfrc, o_gcw, o_M, o_L, o_H, o_bias, o_passive, o_gravc, o_actfrc, o_smooth,
       o_qacc_smooth, o_qacc, o_qfc, o_grad, o_search, o_Ma, o_Mv, o_tmp, o_aforce, o_gpos, o_cand, o_con,
       o_J, o_efc, o_conehess, o_noslip, o_site, o_rcs, o_sepcache;
   int ws_doubles;  // RCSB_D_TAIL doubles per warp follow the reals
@@ -114,6 +114,10 @@ struct RcsbModel {
   int d_body[RCSB_MAXV], d_qadr[RCSB_MAXV], d_limited[RCSB_MAXV], d_actfrclimited[RCSB_MAXV], d_actgravcomp[RCSB_MAXV],
       d_dotzero[RCSB_MAXV];
   uint32_t d_premask[RCSB_MAXV];  // dofs whose velocity enters cdof_dot of this dof
+  // dof-chain form of the tree, derived in rcsb_model_finalize_layout: the dof whose accumulated spatial velocity
+  // this dof adds to (-1: tree root), the dof whose accumulated velocity enters this dof's cdof_dot (-1: none), and
+  // the last dof of every body (its accumulated velocity / acceleration is the body's)
+  int d_parent[RCSB_MAXV], d_pre[RCSB_MAXV], b_lastdof[RCSB_MAXB];
   uint32_t d_ancmask[RCSB_MAXV];  // ancestor dofs incl. self (sparsity of M)
   real d_armature[RCSB_MAXV], d_damping[RCSB_MAXV], d_frictionloss[RCSB_MAXV], d_invweight0[RCSB_MAXV];
   real d_range[RCSB_MAXV][2], d_margin[RCSB_MAXV], d_solref[RCSB_MAXV][2], d_solimp[RCSB_MAXV][5],

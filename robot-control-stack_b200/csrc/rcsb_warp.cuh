@@ -22,6 +22,7 @@
 #else
 #define PFOR(i, n) for (int i = 0; i < (n); ++i)
 #endif
+#define PFOR1(i, n) PFOR(i, n)
 RCSB_DEV real warp_sum(real x) { return x; }
 RCSB_DEV real warp_max(real x) { return x; }
 RCSB_DEV int warp_any(int p) { return p; }
@@ -42,6 +43,8 @@ RCSB_DEV int warp_bcast_i(int x, int src) { return x; }
 #define RCSB_STEP_SYNC() do { if (c.lockstep) __syncthreads(); } while (0)
 #define RCSB_STAGE_BARRIERS 10  // CTA barriers per physics step in lockstep mode (physics_step)
 #define PFOR(i, n) for (int i = (int)(threadIdx.x & 31); i < (n); i += 32)
+// same for n <= 32 work items: one guarded pass, no loop
+#define PFOR1(i, n) for (int i = (int)(threadIdx.x & 31), once_ = 1; once_ && i < (n); once_ = 0)
 RCSB_DEV real warp_sum(real x) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
