@@ -97,6 +97,10 @@ int rcsb_robot_set_cartesian_position(rcsb_batch* b, const void* pose_dev);
 /* evidence counters */
 long long rcsb_launch_count(void); /* kernels launched by this library since load */
 int rcsb_kernel_occupancy(rcsb_batch* b, int* warps_per_cta, int* smem_bytes, int* grid);
+/* name of the kernel variant a batch launches: phase 0 = every environment (reduced workspace layout when the model has
+   one), phase 1 = full-capacity pass for the environments that outgrew it. "generic" reads the model shape at run time;
+   other names are kernels compiled for one fixed shape (csrc/rcsb_k_*.cu). Env RCSB_VARIANT=generic forces the former. */
+const char* rcsb_kernel_variant(rcsb_batch* b, int phase);
 /* profiling build only (-DRCSB_STAGE_TIMING): accumulated clock64() cycles per physics stage of warp 0 / CTA 0, then reset */
 int rcsb_debug_stage_cycles(unsigned long long* out16);
 

@@ -114,7 +114,7 @@ struct rcsb_batch {
   cudaStream_t stream;
   int* d_counter = nullptr;   // [0] env cursor phase 0, [1] overflow cursor phase 1, [2] overflow count
   int* d_overflow = nullptr;  // [n] overflow list
-  int warps = 0, grid = 0, lockstep = 1;
+  int warps = 0, grid = 0, lockstep = 2;
   size_t smem = 0, ws_bytes = 0;
   RcsbVariant var, var_full;          // kernel variants of the two phases
   int warps_full = 0, grid_full = 0;  // phase 1 (full layout) launch shape when a reduced layout exists
@@ -276,6 +276,7 @@ int rcsb_debug_stage_cycles(unsigned long long* out16) {
   return fail(RCSB_ERR_ARG, "library built without RCSB_STAGE_TIMING");
 #endif
 }
+const char* rcsb_kernel_variant(rcsb_batch* b, int phase) { return phase == 0 ? b->var.name : b->var_full.name; }
 int rcsb_kernel_occupancy(rcsb_batch* b, int* warps_per_cta, int* smem_bytes, int* grid) {
   if (warps_per_cta) *warps_per_cta = b->warps;
   if (smem_bytes) *smem_bytes = (int)b->smem;

@@ -143,4 +143,6 @@ class Batch:
     def occupancy(self):
         a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
         _lib.lib().rcsb_kernel_occupancy(self.ptr, C.byref(a), C.byref(b), C.byref(c))
-        return dict(warps_per_cta=a.value, smem_bytes=b.value, grid=c.value)
+        L = _lib.lib()
+        return dict(warps_per_cta=a.value, smem_bytes=b.value, grid=c.value,
+                    variant=L.rcsb_kernel_variant(self.ptr, 0).decode(), variant_full=L.rcsb_kernel_variant(self.ptr, 1).decode())

@@ -131,3 +131,30 @@ def test_pick_up_scene_cube_contacts(fr3):
         assert int(e.si[0, 14]) == int(d.ncon[0])
         assert np.abs(e.sr[0, :16] - d.qpos).max() < 1e-7, it
     assert int(d.ncon[0]) >= 1
+
+
+def test_reduced_layout_hand_over_is_bit_exact(fr3):
+    """Environments that outgrow the reduced workspace layout (fast_maxcon / fast_maxefc) are finished by the
+    full-capacity pass; the result must equal running everything in the full layout, bit for bit, for STEP_K and
+    for step_until_convergence."""
+    M, F, verts = fr3
+    tgt = np.tile(np.array([0, 1.78, 0, -1.45, 0, 0, 0.0]), (3, 1))  # drives the arm into the floor
+    tgt[1] = H.Q_HOME + 0.1                                          # this one never touches anything
+    outs = []
+    for use_reduced in (True, False):
+        e = Emu(F, verts, 3, use_reduced=use_reduced)
+        assert e.has_reduced == use_reduced
+        e.run(RESET[:-1], k=1)
+        e.run(["SET_JOINTS"], act_joints=tgt)
+        handed = 0
+        for it in range(60):
+            e.run(["STEP_K", "OBS"], k=7)
+            handed += e.handed_over
+        e.run(["STEP_CONV", "OBS"], max_conv=120)
+        handed += e.handed_over
+        outs.append((e.sr.copy(), e.sd.copy(), e.si.copy(), e.obs.copy(), e.info.copy(), handed))
+    assert outs[0][5] > 5 and outs[1][5] == 0, "the floor contacts must exceed the reduced capacity"
+    assert int(outs[0][2][0, 14]) >= 1  # still in contact at the end
+    for a, b in zip(outs[0][:5], outs[1][:5]):
+        assert np.array_equal(a, b)
+    assert not outs[0][2][:, 20].any()  # RCSB_I_RESUME cleared everywhere

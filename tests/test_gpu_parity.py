@@ -174,3 +174,37 @@ def test_ik_parity(setup):
         assert (qr is not None) == bool(ok[e])
         assert itr == it[e]
         assert np.abs(qr - q[e]).max() < 1e-9
+
+
+def _floor_run(batch, _lib, dm, N=96):
+    b = batch.Batch(dm, N)
+    tgt = np.tile(np.array([0, 1.78, 0, -1.45, 0, 0, 0.0]), (N, 1))
+    tgt[1::3] = H.Q_HOME + 0.1  # every third env stays clear of the floor
+    b.run(_lib.GRIPPER_RESET | _lib.SIM_RESET | _lib.ROBOT_RESET | _lib.ENV_RESET_FLAGS | _lib.STEP_K, k=1)
+    b.run(_lib.SET_JOINTS, act_joints=torch.as_tensor(tgt, device=b.dev))
+    for it in range(60):
+        b.run(_lib.STEP_K | _lib.OBS, k=7, want_obs=True)
+    b.run(_lib.STEP_CONV | _lib.OBS, max_convergence_steps=120, want_obs=True)
+    torch.cuda.synchronize()
+    return b, [t.cpu().numpy().copy() for t in (b.sr, b.sd, b.si, b.obs, b.info)]
+
+
+def test_reduced_layout_hand_over_and_kernel_variants_bit_exact(setup, monkeypatch):
+    """(1) envs that outgrow the reduced workspace layout are finished by the full-capacity launch: identical, bit for
+    bit, to a model without a reduced layout; (2) the shape-specialised kernels equal the generic kernel bit for bit."""
+    M, dm, _lib, batch = setup
+    b0, ref = _floor_run(batch, _lib, dm)
+    occ = b0.occupancy()
+    assert occ["variant"] == "fr3_reduced" and occ["variant_full"] == "fr3_full", occ
+    assert int(ref[2][:, 14].max()) >= 1, "floor contacts expected"
+    assert not ref[2][:, 20].any()  # RCSB_I_RESUME cleared
+    dm_full = batch.DeviceModel(M, H.robot_ns(), H.gripper_ns(), fast_maxcon=0)
+    b1, full = _floor_run(batch, _lib, dm_full)
+    assert b1.occupancy()["warps_per_cta"] < occ["warps_per_cta"]
+    for a, c in zip(ref, full):
+        assert np.array_equal(a, c)
+    monkeypatch.setenv("RCSB_VARIANT", "generic")
+    b2, gen = _floor_run(batch, _lib, dm)
+    assert b2.occupancy()["variant"] == "generic"
+    for a, c in zip(ref, gen):
+        assert np.array_equal(a, c)
