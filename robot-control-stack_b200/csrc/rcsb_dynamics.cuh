@@ -548,10 +548,40 @@ RCSB_DEV void support(const Ctx& c, int g, const real* gp, const real* gR, const
 }
 
 struct Sup { real v[3], v1[3], v2[3]; };
-struct PairFrames { int g1, g2; real p1[3], R1[9], p2[3], R2[9]; };
+// world frames of the geom pair in the narrow phase: pointers into the warp's workspace (o_pairfr), filled by pair_frames
+struct PairFrames { int g1, g2; const real *p1, *R1, *p2, *R2; };
 
+// world frames of both geoms of the pair, 12 lanes per geom (3 position + 9 rotation entries), into o_pairfr
+RCSB_DEV void pair_frames(const Ctx& c, PairFrames& pf) {
+  const RcsbModel& m = CMODEL(c);
+  real* fr = WR(pairfr);
+  RCSB_SYNC();  // the previous pair's readers are done
+  PFOR1(e, 24) {
+    const int g = e < 12 ? pf.g1 : pf.g2, i = e < 12 ? e : e - 12, b = m.g_body[g];
+    real val;
+    if (i < 3) {
+      val = m.g_pos[g][i];
+      if (b >= 0) {
+        const real* R = WR(bmat) + 9 * b + 3 * i;
+        val = WR(bpos)[3 * b + i] + (R[0] * m.g_pos[g][0] + R[1] * m.g_pos[g][1] + R[2] * m.g_pos[g][2]);
+      }
+    } else {
+      const int r = (i - 3) / 3, k = (i - 3) - 3 * r;
+      const real* Rl = m.g_rot[g];
+      val = Rl[3 * r + k];
+      if (b >= 0) {
+        const real* R = WR(bmat) + 9 * b + 3 * r;
+        val = R[0] * Rl[k] + R[1] * Rl[3 + k] + R[2] * Rl[6 + k];
+      }
+    }
+    fr[e] = val;
+  }
+  RCSB_SYNC();
+  pf.p1 = fr; pf.R1 = fr + 3; pf.p2 = fr + 12; pf.R2 = fr + 15;
+}
 RCSB_DEV void mink_support(const Ctx& c, const PairFrames& pf, const real* dir, Sup& s) {
   real nd[3] = {-dir[0], -dir[1], -dir[2]};
+  RCSB_SYNC();  // s is shared by the warp: no lane may still be reading the record this call overwrites
   support(c, pf.g1, pf.p1, pf.R1, dir, s.v1);
   support(c, pf.g2, pf.p2, pf.R2, nd, s.v2);
   s.v[0] = s.v1[0] - s.v2[0]; s.v[1] = s.v1[1] - s.v2[1]; s.v[2] = s.v1[2] - s.v2[2];
@@ -609,11 +639,10 @@ RCSB_DEV int portal_reach_tol(const Sup* s, const Sup& v4, const real* dir) {
 RCSB_DEV void expand_portal(Sup* s, const Sup& v4) {
   real x[3];
   cross3(x, v4.v, s[0].v);
-  if (dot3(s[1].v, x) > 0) {
-    if (dot3(s[2].v, x) > 0) s[1] = v4; else s[3] = v4;
-  } else {
-    if (dot3(s[3].v, x) > 0) s[2] = v4; else s[1] = v4;
-  }
+  const int which = dot3(s[1].v, x) > 0 ? (dot3(s[2].v, x) > 0 ? 1 : 3) : (dot3(s[3].v, x) > 0 ? 2 : 1);
+  RCSB_SYNC();  // every lane has taken its decision before the shared portal changes
+  s[which] = v4;
+  RCSB_SYNC();
 }
 // Minkowski Portal Refinement penetration query (algorithm of libccd's ccdMPRPenetration, which
 // MuJoCo 3.2.6 uses for convex pairs). Warp-uniform control flow; only support() is cooperative.
@@ -622,7 +651,12 @@ RCSB_DEV void expand_portal(Sup* s, const Sup& v4) {
 // a single support pair on the next substeps instead of repeating the whole query.
 RCSB_DEV_NOINLINE int mpr_penetration(const Ctx& c, const PairFrames& pf, real* depth, real* dir_out, real* pos, real* sep) {
   sep[3] = 0;
-  Sup s[4], v4;
+  // the portal lives in the warp's workspace: every lane computes the same values, so one shared copy replaces 32
+  // per-thread copies in local memory; warp barriers separate the reads of a record from its replacement
+  const RcsbModel& m = CMODEL(c);
+  (void)m;
+  Sup* s = (Sup*)WR(sup);
+  Sup& v4 = s[4];
   real dir[3], va[3], vb[3];
   for (int k = 0; k < 3; k++) { s[0].v1[k] = pf.p1[k]; s[0].v2[k] = pf.p2[k]; s[0].v[k] = pf.p1[k] - pf.p2[k]; }
   if (r_abs(s[0].v[0]) < (real)1e-12 && r_abs(s[0].v[1]) < (real)1e-12 && r_abs(s[0].v[2]) < (real)1e-12) s[0].v[0] += (real)1e-5;
@@ -643,22 +677,30 @@ RCSB_DEV_NOINLINE int mpr_penetration(const Ctx& c, const PairFrames& pf, real* 
   for (int k = 0; k < 3; k++) { va[k] = s[1].v[k] - s[0].v[k]; vb[k] = s[2].v[k] - s[0].v[k]; }
   cross3(dir, va, vb);
   normalize3(dir);
-  if (dot3(dir, s[0].v) > 0) {
-    Sup t = s[1]; s[1] = s[2]; s[2] = t;
+  const int flip = dot3(dir, s[0].v) > 0;
+  RCSB_SYNC();
+  if (flip) {
+    Sup t1 = s[1], t2 = s[2];
+    RCSB_SYNC();
+    s[1] = t2; s[2] = t1;
     dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2];
   }
+  RCSB_SYNC();
   for (int it = 0;; it++) {
     if (it > 100) return 0;
     mink_support(c, pf, dir, s[3]);
     if (dot3(s[3].v, dir) <= 0) { copy3(sep, dir); sep[3] = 1; return 0; }
     int cont = 0;
     cross3(va, s[1].v, s[3].v);
-    if (dot3(va, s[0].v) < (real)-1e-18) { s[2] = s[3]; cont = 1; }
+    if (dot3(va, s[0].v) < (real)-1e-18) cont = 2;
     if (!cont) {
       cross3(va, s[3].v, s[2].v);
-      if (dot3(va, s[0].v) < (real)-1e-18) { s[1] = s[3]; cont = 1; }
+      if (dot3(va, s[0].v) < (real)-1e-18) cont = 1;
     }
+    RCSB_SYNC();
     if (!cont) break;
+    s[cont] = s[3];
+    RCSB_SYNC();
     for (int k = 0; k < 3; k++) { va[k] = s[1].v[k] - s[0].v[k]; vb[k] = s[2].v[k] - s[0].v[k]; }
     cross3(dir, va, vb);
     normalize3(dir);
@@ -750,15 +792,15 @@ RCSB_DEV void add_contact(const Ctx& c, int& ncon, int g1, int g2, real dist, co
 }
 
 // append `value` to `list` for every lane with `hit`, preserving lane order; returns the new count (uniform)
-RCSB_DEV int compact_append(const Ctx& c, int hit, int value, int count, int* list) {
+RCSB_DEV int compact_append(const Ctx& c, int hit, int value, int count, uint16_t* list) {
 #ifdef RCSB_HOST_EMU
-  if (hit) { if (count < RCSB_MAXCAND) list[count] = value; count++; }
+  if (hit) { if (count < RCSB_MAXCAND) list[count] = (uint16_t)value; count++; }
   return count;
 #else
   unsigned mask = warp_ballot(hit);
   if (hit) {
     int slot = count + __popc(mask & ((1u << c.lane) - 1u));
-    if (slot < RCSB_MAXCAND) list[slot] = value;
+    if (slot < RCSB_MAXCAND) list[slot] = (uint16_t)value;
   }
   return count + __popc(mask);
 #endif
@@ -817,8 +859,8 @@ RCSB_DEV void st_collision(const Ctx& c) {
   }
   if (c.lane == 0) WI(misc)[MI_OVERFLOW] = 0;
   RCSB_SYNC();
-  int* candA = (int*)WR(cand);  // candidate lists live in the stage-local union next to the geom centres
-  int* candB = candA + RCSB_MAXCAND;
+  uint16_t* candA = (uint16_t*)WR(cand);  // candidate lists live in the stage-local union next to the geom centres
+  uint16_t* candB = candA + RCSB_MAXCAND;
   int ncandA = 0;
   for (int base = 0; base < MD(npair); base += RCSB_NLANES) {
     int p = base + c.lane, hit = 0;
@@ -879,8 +921,7 @@ RCSB_DEV void st_collision(const Ctx& c) {
     pf.g1 = m.pair[p][0]; pf.g2 = m.pair[p][1];
     real margin = m.g_margin[pf.g1] > m.g_margin[pf.g2] ? m.g_margin[pf.g1] : m.g_margin[pf.g2];
     real gap = m.g_gap[pf.g1] > m.g_gap[pf.g2] ? m.g_gap[pf.g1] : m.g_gap[pf.g2];
-    geom_frame(c, pf.g1, pf.p1, pf.R1);
-    geom_frame(c, pf.g2, pf.p2, pf.R2);
+    pair_frames(c, pf);
     int t1 = m.g_type[pf.g1], t2 = m.g_type[pf.g2];
     if (t1 == RCSB_GEOM_PLANE) {
       real n[3] = {pf.R1[2], pf.R1[5], pf.R1[8]};
@@ -926,7 +967,7 @@ RCSB_DEV void st_collision(const Ctx& c) {
       real* sc = WR(sepcache) + 4 * (p & 1);
       int skip = 0;
       if (sc[0] == (real)p) {
-        Sup s;
+        Sup& s = ((Sup*)WR(sup))[4];
         mink_support(c, pf, sc + 1, s);
         skip = dot3(s.v, sc + 1) <= 0;
       }

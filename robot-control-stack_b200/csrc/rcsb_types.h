@@ -78,7 +78,7 @@ struct RcsbLayout {
   int ws_reals, ws_ints, nsr;  // nsr = reals per env in HBM (dynamic state + RCS tail)
   int o_q, o_v, o_ctrl, o_warm, o_bpos, o_bquat, o_bmat, o_rootcom, o_cinert, o_crb, o_crbbuf,
       o_cdof, o_cdofdot, o_cvel, o_cacc, o_cfrc, o_gcw, o_M, o_L, o_H, o_bias, o_passive, o_gravc, o_actfrc, o_smooth,
-      o_qacc_smooth, o_qacc, o_qfc, o_grad, o_search, o_Ma, o_Mv, o_tmp, o_aforce, o_gpos, o_cand, o_con,
+      o_qacc_smooth, o_qacc, o_qfc, o_grad, o_search, o_Ma, o_Mv, o_tmp, o_aforce, o_gpos, o_cand, o_pairfr, o_sup, o_con,
       o_J, o_efc, o_conehess, o_noslip, o_site, o_rcs, o_sepcache;
   int ws_doubles;  // RCSB_D_TAIL doubles per warp follow the reals
   int oi_con, oi_efc, oi_misc;
