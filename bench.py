@@ -36,6 +36,15 @@ BYTES_PER_PHYSICS_STEP = 512
 BYTES_PER_ENV_STEP = SUBSTEPS * BYTES_PER_PHYSICS_STEP + 64 + 168 + 3
 
 
+def profiled_traffic():
+    """DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -233,6 +242,7 @@ def run_ours(args):
         kavg_ms = float(np.mean(kms))
         achieved = N * BYTES_PER_ENV_STEP / (kavg_ms * 1e-3) / 1e9
         occ = b.occupancy()
+        prof = profiled_traffic() if N == 4096 else None
         line = {
             "metric": "env-steps/sec FR3 joint-control (async 30 Hz, 17 substeps)", "value": value, "unit": "env-steps/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
@@ -247,9 +257,14 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(N * 8 * 8),
                     "d2h_bytes_per_step": int(N * (dm.obs_dim * 8 + dm.info_dim * 4)), "steps": e2e_steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms": kavg_ms,
+                         "traffic": (prof["dram_bytes_read"] + prof["dram_bytes_write"]) if prof else None,
+                         "peak_source": peak_src, "kernel_ms": kavg_ms,
+                         "algorithmic_bytes_per_launch": N * BYTES_PER_ENV_STEP,
                          "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP,
-                         "note": "ALU/latency-bound path (~100 flop/B, SURVEY.md 8d): HBM fraction is low by construction"},
+                         "ncu": ({k: prof[k] for k in ("ipc_active", "fp64_pipe_pct", "lsu_pipe_pct", "inst_executed", "source")}
+                                 if prof else None),
+                         "note": "instruction-issue / latency bound (~100 flop/B, SURVEY.md 8d): the HBM fraction is low by "
+                                 "construction; ncu.ipc_active of 4 and the pipe utilisations say how busy the SMs are"},
             "clocks": clocks,
         }
         if world == 1:

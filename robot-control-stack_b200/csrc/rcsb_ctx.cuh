@@ -42,5 +42,5 @@ enum { MI_NCON = 0, MI_NEFC, MI_NE, MI_NF, MI_NL, MI_HAVE_L, MI_SOLVER_ITER, MI_
 #define WR(name) (CW(c) + LAY.o_##name)
 #define WI(name) (CWI(c) + LAY.oi_##name)
 #if defined(RCSB_STAGE_TIMING) && !defined(RCSB_HOST_EMU)
-extern __device__ unsigned long long rcsb_stage_cycles[16];
+__device__ unsigned long long rcsb_stage_cycles[16];  // profiling build = one translation unit (RCSB_SINGLE_TU)
 #endif

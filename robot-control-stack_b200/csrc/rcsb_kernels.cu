@@ -23,9 +23,6 @@
 #include "rcsb_stage.cuh"
 
 // ------------------------------------------------------------------ kernel variants
-#ifdef RCSB_STAGE_TIMING
-__device__ unsigned long long rcsb_stage_cycles[16];
-#endif
 #define RCSB_VARIANT_NS rcsb_generic
 #define RCSB_KERNEL rcsb_k_run
 #include "rcsb_variant.cuh"
