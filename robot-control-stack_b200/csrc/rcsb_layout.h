@@ -84,6 +84,7 @@ RCSB_HD constexpr RcsbLayout rcsb_make_layout(const RcsbShape& s) {
 #define RCSB_MAX(a, b) ((a) > (b) ? (a) : (b))
   RCSB_ALLOC(o_q, nq); RCSB_ALLOC(o_v, nv); RCSB_ALLOC(o_ctrl, nu); RCSB_ALLOC(o_warm, nv);
   RCSB_ALLOC(o_rcs, RCSB_S_TAIL);
+  o = (o + 1) & ~1;  // rows stay 16-byte granular in HBM when real is 8 bytes
   y.nsr = o;
   y.o_site = y.o_rcs + RCSB_S_SITEPOS;
   const int k_begin = o;
