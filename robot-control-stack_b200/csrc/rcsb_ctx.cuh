@@ -13,6 +13,7 @@ struct Ctx {
   int lockstep;
 };
 #define CMODEL(c) (*(c).md)
+#define CMODEL_G(c) (*(c).md)
 #define CW(c) ((c).w)
 #define CWI(c) ((c).wi)
 #define CCLK(c) ((c).clk)
@@ -23,6 +24,7 @@ struct Ctx {
 // not, instead of falling back to generic 64-bit loads.
 extern __shared__ __align__(128) unsigned char rcsb_smem[];
 struct Ctx {
+  const RcsbModel* gm;  // the model in global memory (cold tail: fields after cold_begin)
   const real* verts;    // convex hull vertex pool (global memory, read-only)
   uint32_t wb;          // this warp's real workspace (byte offset in shared memory)
   uint32_t clkb;        // this warp's simulation time + callback clocks (always double)
@@ -31,6 +33,7 @@ struct Ctx {
   int lockstep;         // fixed-substep launch: CTA barriers between stages keep the warps on the same code
 };
 #define CMODEL(c) (*(const RcsbModel*)rcsb_smem)
+#define CMODEL_G(c) (*(c).gm)
 #define CW(c) ((real*)(rcsb_smem + (c).wb))
 #define CWI(c) ((int*)(rcsb_smem + (c).wib))
 #define CCLK(c) ((double*)(rcsb_smem + (c).clkb))

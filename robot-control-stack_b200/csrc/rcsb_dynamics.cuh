@@ -818,9 +818,11 @@ RCSB_DEV int compact_slot(const Ctx& c, int hit, int& count) {
   return slot;
 #endif
 }
-// separating-axis test of two oriented boxes (rotation A/B row-major, centres ca/cb, half sizes ha/hb); 1 = separated
+// separating-axis test of two oriented boxes (rotation A/B row-major, centres ca/cb, half sizes ha/hb); 1 = separated.
+// *gap receives a lower bound of the distance between the boxes beyond the margin: the widest clearance over the six
+// face axes (unit vectors), or 0 when only an edge-edge axis separates them.
 RCSB_DEV int obb_separated(const real* A, const real* ca, const real* ha, const real* B, const real* cb, const real* hb,
-                           real margin) {
+                           real margin, real* gap) {
   real R[9], AR[9], t[3], dv[3] = {cb[0] - ca[0], cb[1] - ca[1], cb[2] - ca[2]};
   mulmatT3(t, A, dv);
   for (int i = 0; i < 3; i++)
@@ -828,10 +830,17 @@ RCSB_DEV int obb_separated(const real* A, const real* ca, const real* ha, const 
       R[3 * i + j] = A[i] * B[j] + A[3 + i] * B[3 + j] + A[6 + i] * B[6 + j];
       AR[3 * i + j] = r_abs(R[3 * i + j]) + (real)1e-12;
     }
-  for (int i = 0; i < 3; i++)
-    if (r_abs(t[i]) > ha[i] + hb[0] * AR[3 * i] + hb[1] * AR[3 * i + 1] + hb[2] * AR[3 * i + 2] + margin) return 1;
-  for (int j = 0; j < 3; j++)
-    if (r_abs(t[0] * R[j] + t[1] * R[3 + j] + t[2] * R[6 + j]) > ha[0] * AR[j] + ha[1] * AR[3 + j] + ha[2] * AR[6 + j] + hb[j] + margin) return 1;
+  real best = 0;
+  for (int i = 0; i < 3; i++) {
+    real g = r_abs(t[i]) - (ha[i] + hb[0] * AR[3 * i] + hb[1] * AR[3 * i + 1] + hb[2] * AR[3 * i + 2] + margin);
+    best = g > best ? g : best;
+  }
+  for (int j = 0; j < 3; j++) {
+    real g = r_abs(t[0] * R[j] + t[1] * R[3 + j] + t[2] * R[6 + j]) - (ha[0] * AR[j] + ha[1] * AR[3 + j] + ha[2] * AR[6 + j] + hb[j] + margin);
+    best = g > best ? g : best;
+  }
+  *gap = best;
+  if (best > 0) return 1;
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) {
       int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
@@ -842,8 +851,57 @@ RCSB_DEV int obb_separated(const real* A, const real* ca, const real* ha, const 
   return 0;
 }
 
+// ---- separation budgets (temporal coherence, exact): every collision group (all geom pairs between two bodies) keeps
+// a lower bound of the distance between its geoms beyond the contact margin, measured the last time the group went
+// through the phases below and reduced after every step by an upper bound of the relative displacement the joints on
+// the tree path between the two bodies can have caused (st_integrate). While the budget is positive no pair of the
+// group can be in contact, so the group is skipped; the contact set is the one a full pass would produce.
+#define RCSB_BUDGET_BIG 1e30f
+RCSB_DEV void budget_min(const Ctx& c, float* bud, int g, real gap) {
+  float f = (float)(gap * (real)0.999999);  // never above the measured gap
+  if (!(f > 0)) f = 0;
+#ifdef RCSB_HOST_EMU
+  if (f < bud[g]) bud[g] = f;
+#else
+  atomicMin((unsigned*)(bud + g), __float_as_uint(f));  // non-negative floats order like their bit patterns
+#endif
+}
+RCSB_DEV void budget_reset(const Ctx& c) {  // positions changed by something other than a step: every group is due
+  const RcsbModel& m = CMODEL(c);
+  float* bud = (float*)WR(cbud);
+  PFOR(g, MD(ngrp)) { bud[g] = 0; }
+}
+// after the velocities of the step are final: positions move by h * qvel
+RCSB_DEV void budget_advance(const Ctx& c) {
+  const RcsbModel& m = CMODEL(c);
+  float* bud = (float*)WR(cbud);
+  const real h = m.timestep;
+  PFOR(g, MD(ngrp)) {
+    const float* reach = CMODEL_G(c).grp_reach[g];  // zero off the tree path between the group's bodies
+    real s = 0;
+    for (int j = 0; j < MD(nv); j++) s += r_abs(WR(v)[j]) * (real)RCSB_LDG(reach + j);
+    bud[g] -= (float)(h * s * (real)1.000001) + 1e-6f;
+  }
+}
 RCSB_DEV void st_collision(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
+  float* bud = (float*)WR(cbud);
+  // ---- groups whose separation budget is used up go through the phases; the others cannot be in contact
+  uint32_t act[(RCSB_MAXGRP + 31) / 32] = {0, 0};
+#ifdef RCSB_HOST_EMU
+  for (int g = 0; g < MD(ngrp); g++) if (!(bud[g] > 0)) act[g >> 5] |= 1u << (g & 31);
+#else
+  for (int w = 0; w * 32 < MD(ngrp); w++) {
+    const int g = w * 32 + c.lane;
+    act[w] = warp_ballot(g < MD(ngrp) && !(bud[g] > 0));
+  }
+#endif
+  if (c.lane == 0) { WI(misc)[MI_OVERFLOW] = 0; WI(misc)[MI_NCON] = 0; }
+  if (!(act[0] | act[1])) {
+    RCSB_SYNC();
+    return;
+  }
+  PFOR(g, MD(ngrp)) { if ((act[g >> 5] >> (g & 31)) & 1u) bud[g] = RCSB_BUDGET_BIG; }
   // ---- broad phase: bounding spheres about the local AABB centres (plane: signed distance), one pair per lane,
   //      survivors compacted in pair order
   PFOR(g, MD(ng)) {  // bounding-volume centres for the broad phase
@@ -857,7 +915,6 @@ RCSB_DEV void st_collision(const Ctx& c) {
       o[0] = p[0] + v[0]; o[1] = p[1] + v[1]; o[2] = p[2] + v[2];
     }
   }
-  if (c.lane == 0) WI(misc)[MI_OVERFLOW] = 0;
   RCSB_SYNC();
   uint16_t* candA = (uint16_t*)WR(cand);  // candidate lists live in the stage-local union next to the geom centres
   uint16_t* candB = candA + RCSB_MAXCAND;
@@ -865,24 +922,32 @@ RCSB_DEV void st_collision(const Ctx& c) {
   for (int base = 0; base < MD(npair); base += RCSB_NLANES) {
     int p = base + c.lane, hit = 0;
     if (p < MD(npair)) {
-      int g1 = m.pair[p][0], g2 = m.pair[p][1];
-      real margin = m.g_margin[g1] > m.g_margin[g2] ? m.g_margin[g1] : m.g_margin[g2];
-      const real *a = WR(gpos) + 3 * g1, *b = WR(gpos) + 3 * g2;
-      real d[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
-      if (m.g_type[g1] == RCSB_GEOM_PLANE) {
-        const real* R = m.g_rot[g1];  // planes are static in all supported scenes
-        real n[3] = {R[2], R[5], R[8]};
-        hit = !(dot3(d, n) > m.g_rbound[g2] + margin);
-      } else {
-        real bound = m.g_rbound[g1] + m.g_rbound[g2] + margin;
-        hit = !(dot3(d, d) > bound * bound);
+      const int grp = m.pair_grp[p];
+      if ((act[grp >> 5] >> (grp & 31)) & 1u) {
+        int g1 = m.pair[p][0], g2 = m.pair[p][1];
+        real margin = m.g_margin[g1] > m.g_margin[g2] ? m.g_margin[g1] : m.g_margin[g2];
+        const real *a = WR(gpos) + 3 * g1, *b = WR(gpos) + 3 * g2;
+        real d[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, gap;
+        if (m.g_type[g1] == RCSB_GEOM_PLANE) {
+          const real* R = m.g_rot[g1];  // planes are static in all supported scenes
+          real n[3] = {R[2], R[5], R[8]};
+          gap = dot3(d, n) - (m.g_rbound[g2] + margin);
+          hit = !(dot3(d, n) > m.g_rbound[g2] + margin);
+        } else {
+          real bound = m.g_rbound[g1] + m.g_rbound[g2] + margin;
+          hit = !(dot3(d, d) > bound * bound);
+          gap = hit ? (real)0 : r_sqrt(dot3(d, d)) - bound;
+        }
+        if (!hit) budget_min(c, bud, grp, gap);
       }
     }
     ncandA = compact_append(c, hit, p, ncandA, candA);
   }
-  if (ncandA > RCSB_MAXCAND) {
+  if (ncandA > RCSB_MAXCAND) {  // dropped candidates: their groups stay due
     if (c.lane == 0) WI(misc)[MI_WARN] += 1;
     ncandA = RCSB_MAXCAND;
+    RCSB_SYNC();
+    PFOR(g, MD(ngrp)) { if ((act[g >> 5] >> (g & 31)) & 1u) bud[g] = 0; }
   }
   RCSB_SYNC();
   // ---- mid phase: oriented boxes (local AABBs) by separating axes, one candidate per lane. Conservative: a
@@ -894,7 +959,7 @@ RCSB_DEV void st_collision(const Ctx& c) {
       p = candA[ic];
       int g1 = m.pair[p][0], g2 = m.pair[p][1];
       real margin = m.g_margin[g1] > m.g_margin[g2] ? m.g_margin[g1] : m.g_margin[g2];
-      real p2[3], R2[9];
+      real p2[3], R2[9], gap = 0;
       geom_frame(c, g2, p2, R2);
       const real* c2 = WR(gpos) + 3 * g2;
       const real* hb = m.g_aabb[g2] + 3;
@@ -904,11 +969,13 @@ RCSB_DEV void st_collision(const Ctx& c) {
         for (int j = 0; j < 3; j++) r += hb[j] * r_abs(n[0] * R2[j] + n[1] * R2[3 + j] + n[2] * R2[6 + j]);
         real dist = (c2[0] - m.g_pos[g1][0]) * n[0] + (c2[1] - m.g_pos[g1][1]) * n[1] + (c2[2] - m.g_pos[g1][2]) * n[2];
         hit = !(dist - r > margin);
+        gap = dist - r - margin;
       } else {
         real p1[3], R1[9];
         geom_frame(c, g1, p1, R1);
-        hit = !obb_separated(R1, WR(gpos) + 3 * g1, m.g_aabb[g1] + 3, R2, c2, hb, margin);
+        hit = !obb_separated(R1, WR(gpos) + 3 * g1, m.g_aabb[g1] + 3, R2, c2, hb, margin, &gap);
       }
+      if (!hit) budget_min(c, bud, m.pair_grp[p], gap);
     }
     ncand = compact_append(c, hit, p, ncand, candB);
   }
@@ -922,6 +989,7 @@ RCSB_DEV void st_collision(const Ctx& c) {
     real margin = m.g_margin[pf.g1] > m.g_margin[pf.g2] ? m.g_margin[pf.g1] : m.g_margin[pf.g2];
     real gap = m.g_gap[pf.g1] > m.g_gap[pf.g2] ? m.g_gap[pf.g1] : m.g_gap[pf.g2];
     pair_frames(c, pf);
+    real clear = 0;  // lower bound of the pair's distance beyond the margin when it ends up without a contact
     int t1 = m.g_type[pf.g1], t2 = m.g_type[pf.g2];
     if (t1 == RCSB_GEOM_PLANE) {
       real n[3] = {pf.R1[2], pf.R1[5], pf.R1[8]};
@@ -932,31 +1000,39 @@ RCSB_DEV void st_collision(const Ctx& c) {
         if (!(dist > margin)) {
           for (int k = 0; k < 3; k++) pos[k] = v[k] - (real)0.5 * dist * n[k];
           add_contact(c, ncon, pf.g1, pf.g2, dist, pos, n, margin, gap);
-        }
+        } else clear = dist - margin;
       } else if (t2 == RCSB_GEOM_BOX) {
         int cnt = 0;
+        real mind = (real)1e30;
         for (int i = 0; i < 8 && cnt < 4; i++) {
           const real* sz = m.g_size[pf.g2];
           real loc[3] = {(i & 1) ? sz[0] : -sz[0], (i & 2) ? sz[1] : -sz[1], (i & 4) ? sz[2] : -sz[2]}, cw[3], pos[3];
           mulmat3(cw, pf.R2, loc);
           cw[0] += pf.p2[0]; cw[1] += pf.p2[1]; cw[2] += pf.p2[2];
           real dist = (cw[0] - pf.p1[0]) * n[0] + (cw[1] - pf.p1[1]) * n[1] + (cw[2] - pf.p1[2]) * n[2];
+          mind = dist < mind ? dist : mind;
           if (dist > margin) continue;
           for (int k = 0; k < 3; k++) pos[k] = cw[k] - (real)0.5 * dist * n[k];
           add_contact(c, ncon, pf.g1, pf.g2, dist, pos, n, margin, gap);
           cnt++;
         }
+        if (cnt == 0) clear = mind - margin;
       } else if (t2 == RCSB_GEOM_CAPSULE) {
         real r = m.g_size[pf.g2][0], hl = m.g_size[pf.g2][1];
         real ax[3] = {pf.R2[2] * hl, pf.R2[5] * hl, pf.R2[8] * hl};
+        real mind = (real)1e30;
+        int cnt = 0;
         for (int s = 0; s < 2; s++) {
           real cw[3], pos[3];
           for (int k = 0; k < 3; k++) cw[k] = pf.p2[k] + (s == 0 ? ax[k] : -ax[k]);
           real dist = (cw[0] - pf.p1[0]) * n[0] + (cw[1] - pf.p1[1]) * n[1] + (cw[2] - pf.p1[2]) * n[2] - r;
+          mind = dist < mind ? dist : mind;
           if (dist > margin) continue;
           for (int k = 0; k < 3; k++) pos[k] = cw[k] - n[k] * (r + (real)0.5 * dist);
           add_contact(c, ncon, pf.g1, pf.g2, dist, pos, n, margin, gap);
+          cnt++;
         }
+        if (cnt == 0) clear = mind - margin;
       }
     } else {
       real depth, dir[3], pos[3];
@@ -970,6 +1046,9 @@ RCSB_DEV void st_collision(const Ctx& c) {
         Sup& s = ((Sup*)WR(sup))[4];
         mink_support(c, pf, sc + 1, s);
         skip = dot3(s.v, sc + 1) <= 0;
+        // the Minkowski difference reaches at most dot(s.v, dir) <= 0 along the unit direction: the geoms are at least
+        // that far apart
+        if (skip) clear = -dot3(s.v, sc + 1) - margin;
       }
       if (!skip) {
         real sep[4];
@@ -983,6 +1062,7 @@ RCSB_DEV void st_collision(const Ctx& c) {
         RCSB_SYNC();
       }
     }
+    if (c.lane == 0) budget_min(c, bud, m.pair_grp[p], clear);
   }
   if (c.lane == 0) WI(misc)[MI_NCON] = ncon;
   RCSB_SYNC();

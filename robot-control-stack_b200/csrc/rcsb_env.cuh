@@ -115,6 +115,11 @@ RCSB_DEV void load_env(const Ctx& c, const real* sr, const double* sd, const int
   PFOR(i, RCSB_I_TAIL) { CWI(c)[LAY.oi_misc + MI_COUNT + i] = si[i]; }
   PFOR(i, MI_COUNT) { CWI(c)[LAY.oi_misc + i] = 0; }
   PFOR(i, 2) { WR(sepcache)[4 * i] = -1; }
+  {  // separation budgets are valid only for the qpos they were advanced to
+    int same = 1;
+    PFOR(i, MD(nq)) { if (!(WR(q)[i] == WR(cbq)[i])) same = 0; }
+    if (!warp_all(same)) budget_reset(c);
+  }
   RCSB_SYNC();
 }
 RCSB_DEV void store_env(const Ctx& c, real* sr, double* sd, int* si) {
@@ -156,6 +161,8 @@ RCSB_DEV void op_set_gripper(const Ctx& c, real width) {  // SimGripper.cpp:79-9
 RCSB_DEV void run_env_pre_ops(const Ctx& c, const RcsbLaunch& L, int env) {
   const RcsbModel& m = CMODEL(c);
   const unsigned ops = L.ops;
+  // ops that write qpos directly invalidate the collision groups' separation budgets
+  if (ops & (RCSB_OP_GRIPPER_RESET | RCSB_OP_SIM_RESET | RCSB_OP_ROBOT_RESET | RCSB_OP_SET_JOINTS_HARD)) budget_reset(c);
   if ((ops & RCSB_OP_GRIPPER_RESET) && MD(gr_enabled)) {  // SimGripper.cpp:158-163
     if (c.lane == 0) {
       RS(RCSB_S_GLCW) = 0; RS(RCSB_S_GLW) = 0; RI(RCSB_I_G_MOVING) = 0; RI(RCSB_I_G_COLLISION) = 0;

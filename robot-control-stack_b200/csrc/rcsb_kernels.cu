@@ -111,7 +111,7 @@ struct rcsb_batch {
   cudaStream_t stream;
   int* d_counter = nullptr;   // [0] env cursor phase 0, [1] overflow cursor phase 1, [2] overflow count
   int* d_overflow = nullptr;  // [n] overflow list
-  int warps = 0, grid = 0, lockstep = 2;
+  int warps = 0, grid = 0, lockstep = 1;
   size_t smem = 0, ws_bytes = 0;
   RcsbVariant var, var_full;          // kernel variants of the two phases
   int warps_full = 0, grid_full = 0;  // phase 1 (full layout) launch shape when a reduced layout exists
@@ -245,7 +245,8 @@ rcsb_batch* rcsb_batch_new(rcsb_model* m, int n_envs, void* sr, void* sd, void* 
   if (!ok) { fail(RCSB_ERR_MODEL, "workspace does not fit in shared memory"); delete b; return nullptr; }
   b->var = pick_variant(m->has_reduced ? m->hr : m->h);
   b->var_full = pick_variant(m->h);
-  if (b->var.set_smem(b->smem) != cudaSuccess || (m->has_reduced && b->var_full.set_smem(b->smem_full) != cudaSuccess) ||
+  const size_t smem_max = b->smem > b->smem_full ? b->smem : b->smem_full;  // both phases may use the same kernel
+  if (b->var.set_smem(smem_max) != cudaSuccess || (m->has_reduced && b->var_full.set_smem(smem_max) != cudaSuccess) ||
       cudaFuncSetAttribute(rcsb_k_ik, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCSB_SMEM_HEADER) != cudaSuccess ||
       cudaMalloc(&b->d_counter, 4 * sizeof(int)) != cudaSuccess || cudaMalloc(&b->d_overflow, (size_t)n_envs * sizeof(int)) != cudaSuccess) {
     fail(RCSB_ERR_CUDA, std::string("batch setup: ") + cudaGetErrorString(cudaGetLastError()));
@@ -401,7 +402,8 @@ static int launch_ik(rcsb_batch* b, const void* pose_dev, const void* q0_dev, vo
                      int apply) {
   if (!b || !pose_dev) return fail(RCSB_ERR_ARG, "null argument");
   CUDA_OK(cudaSetDevice(b->m->device));
-  int threads = 128, grid = (b->n + threads - 1) / threads;
+  // one environment per thread and a serial solve per thread: spread the environments over as many SMs as possible
+  int threads = b->n >= 128 * 148 * 4 ? 128 : (b->n >= 64 * 148 * 4 ? 64 : 32), grid = (b->n + threads - 1) / threads;
   rcsb_k_ik<<<grid, threads, RCSB_SMEM_HEADER, b->stream>>>(b->m->d_model, (const real*)pose_dev, (const real*)q0_dev,
                                                            (real*)q_out_dev, success_dev, iters_dev, b->n, apply, b->sr, b->si);
   g_launches++;

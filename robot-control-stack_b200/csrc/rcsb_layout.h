@@ -1,6 +1,7 @@
 // Host-side helpers shared by the CUDA library and the test-only host emulation build:
 // named-field access to RcsbModel and the per-warp workspace layout.
 #pragma once
+#include <math.h>
 #include <stddef.h>
 #include <string.h>
 
@@ -84,6 +85,10 @@ RCSB_HD constexpr RcsbLayout rcsb_make_layout(const RcsbShape& s) {
 #define RCSB_MAX(a, b) ((a) > (b) ? (a) : (b))
   RCSB_ALLOC(o_q, nq); RCSB_ALLOC(o_v, nv); RCSB_ALLOC(o_ctrl, nu); RCSB_ALLOC(o_warm, nv);
   RCSB_ALLOC(o_rcs, RCSB_S_TAIL);
+  // collision groups' separation budgets (floats) and the qpos they refer to: they persist across launches, and a row
+  // whose qpos was changed from outside (host writes, resets) fails the comparison and starts with every group due
+  RCSB_ALLOC(o_cbud, (s.ngrp * (int)sizeof(float) + (int)sizeof(real) - 1) / (int)sizeof(real));
+  RCSB_ALLOC(o_cbq, nq);
   o = (o + 1) & ~1;  // rows stay 16-byte granular in HBM when real is 8 bytes
   y.nsr = o;
   y.o_site = y.o_rcs + RCSB_S_SITEPOS;
@@ -140,7 +145,7 @@ static inline void rcsb_host_quat_to_mat(real* M, const real* q) {  // same expr
 }
 static inline RcsbShape rcsb_model_shape(const RcsbModel* m) {
   RcsbShape s = {m->nq, m->nv, m->nu, m->nb, m->ng, m->npair, m->nt, m->neq, m->nroot, m->maxcon, m->maxefc, m->rb_njoints,
-                 m->cone_elliptic, m->implicitfast, m->noslip_iterations, m->cap_reduced, m->gr_enabled};
+                 m->cone_elliptic, m->implicitfast, m->noslip_iterations, m->cap_reduced, m->gr_enabled, m->ngrp};
   return s;
 }
 static inline int rcsb_model_finalize_layout(RcsbModel* m) {
@@ -148,6 +153,60 @@ static inline int rcsb_model_finalize_layout(RcsbModel* m) {
       m->ng > RCSB_MAXG || m->npair > RCSB_MAXPAIR || m->nt > RCSB_MAXT || m->neq > RCSB_MAXEQ ||
       m->nroot > RCSB_MAXROOT || m->rb_njoints > RCSB_MAXJ || m->maxcon < 1 || m->maxefc < 1)
     return -1;
+  // ---- collision groups: one per pair of bodies that owns candidate geom pairs (world = -1), in order of appearance
+  {
+    int ga[RCSB_MAXGRP], gb[RCSB_MAXGRP];
+    m->ngrp = 0;
+    for (int p = 0; p < m->npair; p++) {
+      int a = m->g_body[m->pair[p][0]], b = m->g_body[m->pair[p][1]], g = -1;
+      if (a > b) { int t = a; a = b; b = t; }
+      for (int i = 0; i < m->ngrp; i++) if (ga[i] == a && gb[i] == b) { g = i; break; }
+      if (g < 0) {
+        if (m->ngrp >= RCSB_MAXGRP) return -1;
+        g = m->ngrp++;
+        ga[g] = a; gb[g] = b;
+        m->grp_mask[g] = (a >= 0 ? m->b_dofmask[a] : 0u) ^ (b >= 0 ? m->b_dofmask[b] : 0u);  // dofs on the tree path
+      }
+      m->pair_grp[p] = (uint8_t)g;
+    }
+    // E[x]: extent of body x's own collidable geoms about its frame origin; off[x]: bound of |origin of x in its parent|
+    real E[RCSB_MAXB], off[RCSB_MAXB];
+    for (int x = 0; x < m->nb; x++) {
+      real e = 0;
+      for (int g = 0; g < m->ng; g++)
+        if (m->g_body[g] == x) {
+          real r = sqrt(m->g_bpos[g][0] * m->g_bpos[g][0] + m->g_bpos[g][1] * m->g_bpos[g][1] + m->g_bpos[g][2] * m->g_bpos[g][2]) + m->g_rbound[g];
+          if (r > e) e = r;
+        }
+      E[x] = e;
+      real o = sqrt(m->b_pos[x][0] * m->b_pos[x][0] + m->b_pos[x][1] * m->b_pos[x][1] + m->b_pos[x][2] * m->b_pos[x][2]);
+      o += 2 * sqrt(m->b_jpos[x][0] * m->b_jpos[x][0] + m->b_jpos[x][1] * m->b_jpos[x][1] + m->b_jpos[x][2] * m->b_jpos[x][2]);
+      if (m->b_jtype[x] == RCSB_JNT_SLIDE) {
+        int j = m->b_dadr[x];
+        real lo = fabs(m->d_range[j][0]), hi = fabs(m->d_range[j][1]);
+        o += m->d_limited[j] ? (lo > hi ? lo : hi) : (real)10;
+      }
+      off[x] = o;
+    }
+    memset(m->grp_reach, 0, sizeof(m->grp_reach));
+    for (int g = 0; g < m->ngrp; g++) {
+      m->grp_body[g][0] = (int8_t)ga[g]; m->grp_body[g][1] = (int8_t)gb[g];
+      for (int j = 0; j < m->nv; j++) {
+        if (!((m->grp_mask[g] >> j) & 1u)) continue;
+        // the dof is an ancestor dof of exactly one of the two bodies: that body's geoms are what it moves
+        const int x = (ga[g] >= 0 && ((m->b_dofmask[ga[g]] >> j) & 1u)) ? ga[g] : gb[g];
+        const int bj = m->d_body[j];
+        const int translational = m->b_jtype[bj] == RCSB_JNT_SLIDE || (m->b_jtype[bj] == RCSB_JNT_FREE && j - m->b_dadr[bj] < 3);
+        real r = 1;
+        if (!translational) {
+          // joint anchor -> origin of its own body -> down the chain to x -> farthest geom point of x
+          r = sqrt(m->b_jpos[bj][0] * m->b_jpos[bj][0] + m->b_jpos[bj][1] * m->b_jpos[bj][1] + m->b_jpos[bj][2] * m->b_jpos[bj][2]) + E[x];
+          for (int k = x; k != bj && k >= 0; k = m->b_parent[k]) r += off[k];
+        }
+        m->grp_reach[g][j] = (float)(r * 1.000001);
+      }
+    }
+  }
   m->lay = rcsb_make_layout(rcsb_model_shape(m));
   for (int a = 0; a < RCSB_MAXU; a++)
     for (int k = 0; k < RCSB_MAXV; k++) {

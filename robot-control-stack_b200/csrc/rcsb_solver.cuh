@@ -792,6 +792,7 @@ RCSB_DEV void st_integrate(const Ctx& c) {
     WR(warm)[k] = WR(qacc)[k];
   }
   RCSB_SYNC();
+  budget_advance(c);  // collision groups: the positions are about to move by h * qvel
   PFOR(b, MD(nb)) {
     int qa = m.b_qadr[b], da = m.b_dadr[b];
     real* q = WR(q);
@@ -811,6 +812,8 @@ RCSB_DEV void st_integrate(const Ctx& c) {
       q[qa] += h * v[da];
     }
   }
+  RCSB_SYNC();
+  PFOR(i, MD(nq)) { WR(cbq)[i] = WR(q)[i]; }  // the qpos the separation budgets now refer to
   RCSB_SYNC();
 }
 
@@ -936,6 +939,7 @@ RCSB_DEV void reset_data(const Ctx& c, double* time) {  // mj_resetData
   PFOR(i, MD(nv)) { WR(v)[i] = 0; WR(warm)[i] = 0; }
   PFOR(i, MD(nu)) { WR(ctrl)[i] = 0; }
   if (c.lane == 0) *time = 0;
+  budget_reset(c);
   RCSB_SYNC();
 }
 // RCSB_STAGE: CTA barrier (lockstep launches only) + the stage; the profiling build (-DRCSB_STAGE_TIMING) also
@@ -960,9 +964,10 @@ RCSB_DEV int physics_step(const Ctx& c, double* time) {
     reset_data(c, time);
   }
   // Lockstep (fixed-substep launches): the step is far more straight-line code than the instruction cache holds, so
-  // the warps of a CTA are re-aligned by a CTA barrier once per step (mode 2, the default, measured best) or before
-  // every stage (mode 1); warps that run the same code together share each fetched line instead of streaming the
-  // whole program once per warp (no barriers: -18 % throughput at 28 warps per SM).
+  // the warps of a CTA are re-aligned by a CTA barrier before every stage (mode 1, the default, measured best since
+  // the collision stage's duration varies per environment) or once per step (mode 2); warps that run the same code
+  // together share each fetched line instead of streaming the whole program once per warp (no barriers: -45 %
+  // throughput at 28 warps per SM).
   // ---- mj_step1
   RCSB_STAGE(0, st_kinematics(c));
   RCSB_STAGE(1, st_com(c));

@@ -24,6 +24,7 @@ enum {
   RCSB_MAXROOT = 4,   // kinematic trees
   RCSB_MAXJ = 8,      // robot arm joints
   RCSB_MAXCAND = 48,  // broad-phase survivors per step (28 at the FR3 home pose)
+  RCSB_MAXGRP = 64,   // collision groups (pairs of bodies that own at least one candidate geom pair)
 };
 
 enum { RCSB_JNT_FREE = 0, RCSB_JNT_SLIDE = 2, RCSB_JNT_HINGE = 3 };
@@ -79,14 +80,14 @@ struct RcsbLayout {
   int o_q, o_v, o_ctrl, o_warm, o_bpos, o_bquat, o_bmat, o_rootcom, o_cinert, o_crb, o_crbbuf,
       o_cdof, o_cdofdot, o_cvel, o_cacc, o_cfrc, o_gcw, o_M, o_L, o_H, o_bias, o_passive, o_gravc, o_actfrc, o_smooth,
       o_qacc_smooth, o_qacc, o_qfc, o_grad, o_search, o_Ma, o_Mv, o_tmp, o_aforce, o_gpos, o_cand, o_pairfr, o_sup, o_con,
-      o_J, o_efc, o_conehess, o_noslip, o_site, o_rcs, o_sepcache;
+      o_J, o_efc, o_conehess, o_noslip, o_site, o_rcs, o_sepcache, o_cbud, o_cbq;
   int ws_doubles;  // RCSB_D_TAIL doubles per warp follow the reals
   int oi_con, oi_efc, oi_misc;
 };
 // The part of a model that fixes code shape: loop bounds, workspace layout, enabled features.
 struct RcsbShape {
   int nq, nv, nu, nb, ng, npair, nt, neq, nroot, maxcon, maxefc, rb_njoints, cone_elliptic, implicitfast,
-      noslip_iterations, cap_reduced, gr_enabled;
+      noslip_iterations, cap_reduced, gr_enabled, ngrp;
 };
 
 struct RcsbModel {
@@ -134,6 +135,12 @@ struct RcsbModel {
   real g_size[RCSB_MAXG][3], g_rbound[RCSB_MAXG], g_aabb[RCSB_MAXG][6], g_friction[RCSB_MAXG][3], g_solref[RCSB_MAXG][2],
       g_solimp[RCSB_MAXG][5], g_solmix[RCSB_MAXG], g_margin[RCSB_MAXG], g_gap[RCSB_MAXG], g_invweight[RCSB_MAXG];
   uint8_t pair[RCSB_MAXPAIR][2];  // collidable-geom indices, lower geom type first
+  // Collision groups, derived in rcsb_model_finalize_layout: all geom pairs between the same two bodies form a group
+  // with one separation budget (rcsb_dynamics.cuh: st_collision). grp_mask = dofs on the tree path between the two
+  // bodies; sum over them of |dq_j| * grp_reach[g][j] (cold tail) bounds the relative displacement of the group's geoms.
+  int ngrp;
+  uint8_t pair_grp[RCSB_MAXPAIR];
+  uint32_t grp_mask[RCSB_MAXGRP];
   // ---- tendons, equalities, actuators
   real t_coef[RCSB_MAXT][RCSB_MAXV];
   int e_dof1[RCSB_MAXEQ], e_dof2[RCSB_MAXEQ], e_active[RCSB_MAXEQ];
@@ -154,6 +161,13 @@ struct RcsbModel {
   real gr_eps_inner, gr_eps_outer, gr_cb_period, gr_max_act, gr_min_act, gr_max_joint, gr_min_joint;
   // ---- per-warp workspace layout (offsets in reals / ints), filled by rcsb_model_finalize
   RcsbLayout lay;
+  // ---- cold tail: NOT staged into shared memory (RCSB_MODEL_HOT_BYTES ends here); device code reaches it through the
+  //      global-memory copy of the model (CMODEL_G), where the few hot rows stay in L1
+  int cold_begin;
+  int8_t grp_body[RCSB_MAXGRP][2];              // the two bodies of every collision group (-1 = world)
+  float grp_reach[RCSB_MAXGRP][RCSB_MAXV];      // per group and dof on its tree path: upper bound, over all poses, of the
+                                                // distance between the joint anchor and any collidable point of the
+                                                // group's body that the dof moves (1 for translational dofs; 0 off the path)
 };
 
 

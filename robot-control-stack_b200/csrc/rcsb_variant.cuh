@@ -24,7 +24,7 @@ static constexpr RcsbLayout kLay = rcsb_make_layout(kShape);
 #include "rcsb_env.cuh"
 
 #ifndef RCSB_HOST_EMU
-__device__ __forceinline__ Ctx make_ctx(const RcsbModel* sm, const real* verts, size_t ws_bytes) {
+__device__ __forceinline__ Ctx make_ctx(const RcsbModel* sm, const RcsbModel* gm, const real* verts, size_t ws_bytes) {
   const RcsbModel& m = *sm;
   (void)m;
   int warp = threadIdx.x >> 5;
@@ -32,6 +32,7 @@ __device__ __forceinline__ Ctx make_ctx(const RcsbModel* sm, const real* verts, 
   c.wb = (uint32_t)(RCSB_SMEM_HEADER + (size_t)warp * ws_bytes);
   c.clkb = c.wb + (uint32_t)((size_t)LAY.ws_reals * sizeof(real));
   c.wib = c.clkb + (uint32_t)((size_t)LAY.ws_doubles * sizeof(double));
+  c.gm = gm;
   c.verts = verts;
   c.lane = threadIdx.x & 31;
   c.lockstep = 0;
@@ -45,7 +46,7 @@ RCSB_KERNEL(const RcsbModel* __restrict__ gm, const real* __restrict__ verts, re
   const RcsbModel* sm = stage_model(gm);
   const RcsbModel& m = *sm;
   (void)m;
-  Ctx c = make_ctx(sm, verts, ws_bytes);
+  Ctx c = make_ctx(sm, gm, verts, ws_bytes);
   if ((L.ops & RCSB_OP_STEP_K) && L.phase == 0) {
     // Fixed-substep launch: static env -> warp mapping. Every warp of the CTA runs the same number of rounds and
     // hits exactly L.k * RCSB_STAGE_BARRIERS CTA barriers per round (inside run_env_program, or here when it has no environment), which

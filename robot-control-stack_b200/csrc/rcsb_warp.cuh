@@ -26,6 +26,7 @@
 RCSB_DEV real warp_sum(real x) { return x; }
 RCSB_DEV real warp_max(real x) { return x; }
 RCSB_DEV int warp_any(int p) { return p; }
+RCSB_DEV int warp_all(int p) { return p; }
 RCSB_DEV unsigned warp_ballot(int p) { return p ? 1u : 0u; }
 RCSB_DEV void warp_argmax(real& v, int& idx) {}
 RCSB_DEV real warp_bcast(real x, int src) { return x; }
@@ -59,6 +60,7 @@ RCSB_DEV real warp_max(real x) {
   return x;
 }
 RCSB_DEV int warp_any(int p) { return __any_sync(0xffffffffu, p); }
+RCSB_DEV int warp_all(int p) { return __all_sync(0xffffffffu, p); }
 RCSB_DEV unsigned warp_ballot(int p) { return __ballot_sync(0xffffffffu, p); }
 // arg-max with ties resolved to the lowest index (== first maximum of a serial scan)
 RCSB_DEV void warp_argmax(real& v, int& idx) {

@@ -158,3 +158,19 @@ def test_reduced_layout_hand_over_is_bit_exact(fr3):
     for a, b in zip(outs[0][:5], outs[1][:5]):
         assert np.array_equal(a, b)
     assert not outs[0][2][:, 20].any()  # RCSB_I_RESUME cleared everywhere
+
+
+def test_separation_budgets_detect_contact_on_the_same_step(fr3):
+    """One long launch (the collision groups' separation budgets are only reset at launch start) driving the arm into
+    the floor: the first contact must appear on exactly the step the oracle (full collision pass every step) sees it,
+    otherwise the trajectories separate."""
+    M, F, verts = fr3
+    tgt = np.array([0, 1.78, 0, -1.45, 0, 0, 0.0])
+    for k in (150, 230, 300, 420):
+        e = Emu(F, verts, 1)
+        mm, s = H.oracle_sim(M)
+        e.run(RESET[:-1], k=1); s.gripper_reset(); s.reset(); s.robot_reset(); s.step(1)
+        e.run(["SET_JOINTS", "STEP_K"], k=k, act_joints=tgt[None]); s.set_joint_position(tgt); s.step(k)
+        assert int(e.si[0, 14]) == int(s.data.ncon[0]), k
+        assert np.abs(e.sr[0, :9] - s.data.qpos).max() < 1e-7, k
+        assert np.abs(e.sr[0, 9:18] - s.data.qvel).max() < 1e-5, k

@@ -32,7 +32,14 @@ for _ in range(steps):
     obs, _, _, trunc, info = env.step(act(obs))
 ev1.record(); torch.cuda.synchronize()
 ms = ev0.elapsed_time(ev1) / steps
+# the IK launch alone (SimRobot::set_cartesian_position for every env)
+a = act(obs); pose = env._to_pose7(a["tquat"])
+torch.cuda.synchronize(); ev0.record()
+for _ in range(5):
+    env.robot.set_cartesian_position(pose)
+ev1.record(); torch.cuda.synchronize()
+ik_ms = ev0.elapsed_time(ev1) / 5
 b = env.sim.batch
-print(json.dumps({"scene": scene, "envs": N, "ms_per_env_step": ms, "env_steps_per_s": N / (ms * 1e-3), "occupancy": b.occupancy(),
+print(json.dumps({"scene": scene, "envs": N, "ms_per_env_step": ms, "ik_ms": ik_ms, "env_steps_per_s": N / (ms * 1e-3), "occupancy": b.occupancy(),
                   "ik_success_frac": float(info["ik_success"].double().mean()), "collision_frac": float(info["collision"].double().mean()),
                   "ncon_mean": float(b.si[:, 14].double().mean()), "warn_max": int(b.si[:, 17].max())}))
