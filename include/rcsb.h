@@ -94,6 +94,13 @@ int rcsb_ik_inverse(rcsb_batch* b, const void* pose_dev, const void* q0_dev, voi
 /* SimRobot::set_cartesian_position for every env (SimRobot.cpp:145-155) */
 int rcsb_robot_set_cartesian_position(rcsb_batch* b, const void* pose_dev);
 
+/* Cartesian Gym action for every env: RelativeActionSpace.action (python/rcs/envs/base.py:490-578, RelativeTo.LAST_STEP
+ * when relative != 0: offset clipped to max_trans [m] / max_rot [rad], applied to the current Cartesian position, xyz
+ * clipped to the workspace box) + RobotEnv.step's dedupe against the previous action and dispatch (base.py:255-288) +
+ * SimRobot::set_cartesian_position (SimRobot.cpp:145-155). kind 0: act_dev [n][6] xyzrpy (CARTESIAN_TRPY); kind 1:
+ * act_dev [n][7] xyz + quat xyzw (CARTESIAN_TQuat). */
+int rcsb_env_cartesian_action(rcsb_batch* b, const void* act_dev, int kind, int relative, double max_trans, double max_rot);
+
 /* evidence counters */
 long long rcsb_launch_count(void); /* kernels launched by this library since load */
 int rcsb_kernel_occupancy(rcsb_batch* b, int* warps_per_cta, int* smem_bytes, int* grid);

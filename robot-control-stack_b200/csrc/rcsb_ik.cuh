@@ -233,3 +233,93 @@ RCSB_DEV void ik_env(const RcsbModel* sm, real* /*scratch*/, int /*lane*/, int e
     }
   }
 }
+
+// ------------------------------------------------------------------ Cartesian actions of the Gym layer, one env per thread
+// RelativeActionSpace.action (python/rcs/envs/base.py:490-578, RelativeTo.LAST_STEP) + RobotEnv.step's dedupe and
+// dispatch (base.py:255-288) + SimRobot::set_cartesian_position (SimRobot.cpp:145-155). act is [N][6] xyzrpy
+// (CARTESIAN_TRPY) or [N][7] xyz + quat xyzw (CARTESIAN_TQuat); relative != 0 applies the clipped offset to the current
+// Cartesian position of the robot.
+enum { RCSB_CART_TRPY = 0, RCSB_CART_TQUAT = 1 };
+RCSB_DEV Quat q_from_rpy(real roll, real pitch, real yaw) {  // Rz(yaw) Ry(pitch) Rx(roll), include/rcs/Pose.h:37-43
+  real cr = cos(roll / 2), sr = sin(roll / 2), cp = cos(pitch / 2), sp = sin(pitch / 2), cy = cos(yaw / 2), sy = sin(yaw / 2);
+  Quat q = {sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy, cr * cp * cy + sr * sp * sy};
+  return q;
+}
+// Pose::limit_rotation_angle (Pose.cpp:184-192): Eigen angularDistance to identity and slerp from identity
+RCSB_DEV Quat q_limit_angle(Quat q, real max_angle) {
+  real vn = r_sqrt(q.x * q.x + q.y * q.y + q.z * q.z);
+  real angle = 2 * atan2(vn, r_abs(q.w));
+  if (!(angle > max_angle && max_angle >= 0)) return q;
+  real t = max_angle / angle;
+  // Eigen's slerp(t, other) from the identity: d = dot = q.w, shortest arc through |d|
+  real d = q.w, ad = r_abs(d), s0, s1;
+  if (ad >= (real)1 - (real)2.220446049250313e-16) { s0 = 1 - t; s1 = t; }
+  else {
+    real theta = acos(ad), st = sin(theta);
+    s0 = sin((1 - t) * theta) / st;
+    s1 = sin(t * theta) / st;
+  }
+  if (d < 0) s1 = -s1;
+  Quat r = {s1 * q.x, s1 * q.y, s1 * q.z, s0 + s1 * q.w};
+  return r;
+}
+RCSB_DEV void robot_cartesian_from_row(const RcsbModel& m, const real* row, real* pose7) {  // as robot_cartesian_position
+  const real* sp = row + m.lay.o_rcs + RCSB_S_SITEPOS;
+  real site[7], base[7], binv[7], t[7];
+  Quat qs = q_norm(q_from_mat(sp + 3));
+  site[0] = sp[0]; site[1] = sp[1]; site[2] = sp[2];
+  site[3] = qs.x; site[4] = qs.y; site[5] = qs.z; site[6] = qs.w;
+  Quat qb = {m.rb_base_quat[1], m.rb_base_quat[2], m.rb_base_quat[3], m.rb_base_quat[0]};
+  qb = q_norm(qb);
+  base[0] = m.rb_base_pos[0]; base[1] = m.rb_base_pos[1]; base[2] = m.rb_base_pos[2];
+  base[3] = qb.x; base[4] = qb.y; base[5] = qb.z; base[6] = qb.w;
+  pose_inverse(base, binv);
+  pose_mul(binv, site, t);
+  pose_mul(t, m.rb_tcp_offset, pose7);
+}
+RCSB_DEV void cart_action_env(const RcsbModel* sm, int env, const real* act, int kind, int relative, real max_trans, real max_rot,
+                              real* sr, int* si) {
+  const RcsbModel& m = *sm;
+  const int na = kind == RCSB_CART_TRPY ? 6 : 7;
+  const real* a = act + (size_t)env * na;
+  real* row = sr + (size_t)env * m.lay.nsr;
+  int* irow = si + (size_t)env * RCSB_I_TAIL;
+  real absact[7];
+  for (int i = 0; i < na; i++) absact[i] = a[i];
+  if (relative) {
+    real origin[7], off[7], prod[7];
+    robot_cartesian_from_row(m, row, origin);
+    Quat qo = kind == RCSB_CART_TRPY ? q_from_rpy(a[3], a[4], a[5]) : q_norm(Quat{a[3], a[4], a[5], a[6]});
+    real tn = r_sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]), sc = (tn > max_trans && max_trans >= 0) ? max_trans / tn : (real)1;
+    qo = q_norm(q_limit_angle(qo, max_rot));
+    off[0] = a[0] * sc; off[1] = a[1] * sc; off[2] = a[2] * sc;
+    off[3] = qo.x; off[4] = qo.y; off[5] = qo.z; off[6] = qo.w;
+    pose_mul(off, origin, prod);  // only its rotation is used: the translations add (base.py:519-522)
+    const real lo[3] = {(real)-0.855, (real)-0.855, (real)0}, hi[3] = {(real)0.855, (real)0.855, (real)1.188};
+    for (int k = 0; k < 3; k++) {
+      real v = origin[k] + off[k];
+      absact[k] = v < lo[k] ? lo[k] : (v > hi[k] ? hi[k] : v);
+    }
+    if (kind == RCSB_CART_TRPY) {
+      real x6[6];
+      pose_xyzrpy(prod, x6);
+      absact[3] = x6[3]; absact[4] = x6[4]; absact[5] = x6[5];
+    } else {
+      absact[3] = prod[3]; absact[4] = prod[4]; absact[5] = prod[5]; absact[6] = prod[6];
+    }
+  }
+  // RobotEnv.step: skip the command when the action equals the previous one (atol 1e-3, rtol 0)
+  real* prev = row + m.lay.o_rcs + RCSB_S_PREVACT;
+  int changed = !irow[RCSB_I_HAVE_PREV_ACTION];
+  for (int i = 0; i < na; i++)
+    if (!(r_abs(absact[i] - prev[i]) <= (real)1e-3)) changed = 1;
+  for (int i = 0; i < na; i++) prev[i] = absact[i];
+  irow[RCSB_I_HAVE_PREV_ACTION] = 1;
+  if (!changed) return;
+  real pose7[7];
+  Quat qt = kind == RCSB_CART_TRPY ? q_from_rpy(absact[3], absact[4], absact[5]) : Quat{absact[3], absact[4], absact[5], absact[6]};
+  qt = q_norm(qt);
+  pose7[0] = absact[0]; pose7[1] = absact[1]; pose7[2] = absact[2];
+  pose7[3] = qt.x; pose7[4] = qt.y; pose7[5] = qt.z; pose7[6] = qt.w;
+  ik_env(sm, nullptr, 0, 0, pose7, nullptr, nullptr, nullptr, nullptr, 1, row, irow);  // env 0 of the row pointers
+}

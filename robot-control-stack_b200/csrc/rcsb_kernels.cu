@@ -72,6 +72,7 @@ namespace rcsb_generic {
 #include "rcsb_ik.cuh"
 }
 using rcsb_generic::ik_env;
+using rcsb_generic::cart_action_env;
 // Pin::inverse for every environment, one environment per thread (rcsb_ik.cuh)
 __global__ void __launch_bounds__(128)
 rcsb_k_ik(const RcsbModel* __restrict__ gm, const real* __restrict__ pose, const real* __restrict__ q0, real* __restrict__ q_out,
@@ -79,6 +80,13 @@ rcsb_k_ik(const RcsbModel* __restrict__ gm, const real* __restrict__ pose, const
   const RcsbModel* sm = stage_model(gm);
   for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < N; env += gridDim.x * blockDim.x)
     ik_env(sm, nullptr, 0, env, pose, q0, q_out, success, iters, apply, sr, si);
+}
+__global__ void __launch_bounds__(128)
+rcsb_k_cart_action(const RcsbModel* __restrict__ gm, const real* __restrict__ act, int kind, int relative, real max_trans, real max_rot,
+                   int N, real* __restrict__ sr, int* __restrict__ si) {
+  const RcsbModel* sm = stage_model(gm);
+  for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < N; env += gridDim.x * blockDim.x)
+    cart_action_env(sm, env, act, kind, relative, max_trans, max_rot, sr, si);
 }
 #undef MD
 #undef LAY
@@ -248,6 +256,7 @@ rcsb_batch* rcsb_batch_new(rcsb_model* m, int n_envs, void* sr, void* sd, void* 
   const size_t smem_max = b->smem > b->smem_full ? b->smem : b->smem_full;  // both phases may use the same kernel
   if (b->var.set_smem(smem_max) != cudaSuccess || (m->has_reduced && b->var_full.set_smem(smem_max) != cudaSuccess) ||
       cudaFuncSetAttribute(rcsb_k_ik, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCSB_SMEM_HEADER) != cudaSuccess ||
+      cudaFuncSetAttribute(rcsb_k_cart_action, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCSB_SMEM_HEADER) != cudaSuccess ||
       cudaMalloc(&b->d_counter, 4 * sizeof(int)) != cudaSuccess || cudaMalloc(&b->d_overflow, (size_t)n_envs * sizeof(int)) != cudaSuccess) {
     fail(RCSB_ERR_CUDA, std::string("batch setup: ") + cudaGetErrorString(cudaGetLastError()));
     delete b;
@@ -406,6 +415,16 @@ static int launch_ik(rcsb_batch* b, const void* pose_dev, const void* q0_dev, vo
   int threads = b->n >= 128 * 148 * 4 ? 128 : (b->n >= 64 * 148 * 4 ? 64 : 32), grid = (b->n + threads - 1) / threads;
   rcsb_k_ik<<<grid, threads, RCSB_SMEM_HEADER, b->stream>>>(b->m->d_model, (const real*)pose_dev, (const real*)q0_dev,
                                                            (real*)q_out_dev, success_dev, iters_dev, b->n, apply, b->sr, b->si);
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return RCSB_OK;
+}
+int rcsb_env_cartesian_action(rcsb_batch* b, const void* act_dev, int kind, int relative, double max_trans, double max_rot) {
+  if (!b || !act_dev || (kind != 0 && kind != 1)) return fail(RCSB_ERR_ARG, "bad argument");
+  CUDA_OK(cudaSetDevice(b->m->device));
+  int threads = b->n >= 128 * 148 * 4 ? 128 : (b->n >= 64 * 148 * 4 ? 64 : 32), grid = (b->n + threads - 1) / threads;
+  rcsb_k_cart_action<<<grid, threads, RCSB_SMEM_HEADER, b->stream>>>(b->m->d_model, (const real*)act_dev, kind, relative, (real)max_trans,
+                                                                     (real)max_rot, b->n, b->sr, b->si);
   g_launches++;
   CUDA_OK(cudaGetLastError());
   return RCSB_OK;

@@ -60,6 +60,7 @@ def lib():
         getattr(L, f).argtypes = [vp, vp]
     L.rcsb_env_get_obs.argtypes = [vp, vp, vp]
     L.rcsb_ik_inverse.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.rcsb_env_cartesian_action.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double]
     L.rcsb_kernel_occupancy.argtypes = [vp, ip, ip, ip]
     L.rcsb_kernel_variant.argtypes = [vp, C.c_int]
     L.rcsb_kernel_variant.restype = cp
@@ -78,5 +79,5 @@ EXPORTS = ["rcsb_last_error", "rcsb_version", "rcsb_real_bytes", "rcsb_model_new
            "rcsb_batch_init_state", "rcsb_batch_run", "rcsb_batch_run_host", "rcsb_sim_step",
            "rcsb_sim_step_until_convergence", "rcsb_sim_reset", "rcsb_robot_set_joint_position",
            "rcsb_robot_set_joints_hard", "rcsb_robot_reset", "rcsb_gripper_set_normalized_width",
-           "rcsb_gripper_reset", "rcsb_env_get_obs", "rcsb_ik_inverse", "rcsb_robot_set_cartesian_position",
+           "rcsb_gripper_reset", "rcsb_env_get_obs", "rcsb_ik_inverse", "rcsb_robot_set_cartesian_position", "rcsb_env_cartesian_action",
            "rcsb_launch_count", "rcsb_kernel_occupancy", "rcsb_kernel_variant", "rcsb_debug_stage_cycles"]

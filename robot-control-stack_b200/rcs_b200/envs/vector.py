@@ -19,6 +19,8 @@ from rcs_b200.envs.base import Box, ControlMode, Dict, RelativeTo
 
 class SimVectorEnv:
     DEFAULT_MAX_JOINT_MOV = np.deg2rad(5)
+    DEFAULT_MAX_CART_MOV = 0.5
+    DEFAULT_MAX_CART_ROT = np.deg2rad(90)
 
     def __init__(self, simulation, robot, gripper, control_mode: ControlMode, max_relative_movement=None,
                  relative_to: RelativeTo = RelativeTo.LAST_STEP, binary_gripper: bool = True):
@@ -32,8 +34,13 @@ class SimVectorEnv:
         meta = common.robots_meta_config(robot.get_config().robot_type)
         self.jlow, self.jhigh = meta.joint_limits[0].copy(), meta.joint_limits[1].copy()
         self.dof = meta.dof
-        if control_mode != ControlMode.JOINTS and self.relative:
-            raise NotImplementedError("relative Cartesian actions are a 'next' row; use absolute TQuat/TRPY or JOINTS")
+        if control_mode != ControlMode.JOINTS and self.relative:  # base.py:377-390
+            mm = self.max_mov
+            if isinstance(mm, (int, float)):
+                mm = (float(mm), self.DEFAULT_MAX_CART_ROT)
+            assert isinstance(mm, tuple) and len(mm) == 2, \
+                "in cartesian control max_mov must be a tuple of maximum translation (in m) and maximum rotation in (rad)"
+            self.max_mov = (float(mm[0]), float(mm[1]))
         if self.relative and relative_to != RelativeTo.LAST_STEP:
             raise NotImplementedError("RelativeTo.CONFIGURED_ORIGIN")
         if not binary_gripper:
@@ -46,9 +53,17 @@ class SimVectorEnv:
             else:
                 spaces["joints"] = Box(self.jlow, self.jhigh, self.dev)
         elif control_mode == ControlMode.CARTESIAN_TRPY:
-            spaces["xyzrpy"] = Box([-0.855, -0.855, 0, -np.pi, -np.pi, -np.pi], [0.855, 0.855, 1.188, np.pi, np.pi, np.pi], self.dev)
+            if self.relative:  # LimitedTRPYRelDictType, base.py:40-50
+                mt, mr = self.max_mov
+                spaces["xyzrpy"] = Box([-mt] * 3 + [-mr] * 3, [mt] * 3 + [mr] * 3, self.dev)
+            else:
+                spaces["xyzrpy"] = Box([-0.855, -0.855, 0, -np.pi, -np.pi, -np.pi], [0.855, 0.855, 1.188, np.pi, np.pi, np.pi], self.dev)
         else:
-            spaces["tquat"] = Box([-0.855, -0.855, 0, -1, -1, -1, -1], [0.855, 0.855, 1.188, 1, 1, 1, 1], self.dev)
+            if self.relative:  # LimitedTQuatRelDictType, base.py:63-73
+                mt = self.max_mov[0]
+                spaces["tquat"] = Box([-mt] * 3 + [-1] * 4, [mt] * 3 + [1] * 4, self.dev)
+            else:
+                spaces["tquat"] = Box([-0.855, -0.855, 0, -1, -1, -1, -1], [0.855, 0.855, 1.188, 1, 1, 1, 1], self.dev)
         if gripper is not None:
             spaces["gripper"] = Box(np.zeros(()), np.ones(()), self.dev)
         self.action_space = Dict(spaces, self.num_envs)
@@ -106,7 +121,12 @@ class SimVectorEnv:
             key = "xyzrpy" if self.control_mode == ControlMode.CARTESIAN_TRPY else "tquat"
             if key not in action:
                 raise RuntimeError("Given type is not matching control mode!")
-            self.robot.set_cartesian_position(self._to_pose7(action[key]))
+            # relative offset / clip / dedupe / IK / set_joint_position for every env in one launch
+            a = action[key].to(device=self.dev, dtype=torch.float64).contiguous()
+            kind = 0 if self.control_mode == ControlMode.CARTESIAN_TRPY else 1
+            assert a.shape == (self.num_envs, 6 if kind == 0 else 7)
+            mt, mr = self.max_mov if self.relative else (0.0, 0.0)
+            _lib.check(_lib.lib().rcsb_env_cartesian_action(b.ptr, a.data_ptr(), kind, int(self.relative), float(mt), float(mr)))
         if self.gripper is not None:
             assert "gripper" in action, "Gripper action not found."  # base.py:724
             ag = action["gripper"].to(device=self.dev, dtype=torch.float64).reshape(-1).contiguous()

@@ -124,3 +124,61 @@ def test_batched_relative_joint_env_async():
     h_j = torch.zeros((512, 7), dtype=torch.float64).pin_memory(); h_g = torch.ones(512, dtype=torch.float64).pin_memory()
     ho, hi = env.step_host(h_j, h_g)
     assert ho.shape == (512, 22) and np.isfinite(ho.numpy()).all()
+
+
+@pytest.mark.parametrize("mode_name", ["CARTESIAN_TRPY", "CARTESIAN_TQuat"])
+def test_relative_cartesian_actions_match_reference_math(mode_name):
+    """RelativeActionSpace (base.py:490-578, LAST_STEP) on the device: offset clipping (translation length, rotation
+    angle by slerp), composition with the current pose, workspace clip, then SimRobot::set_cartesian_position. The
+    expected targets are rebuilt with the host Pose class (pinned by tests/test_pose.py) and the batched IK entry point
+    (pinned against the oracle in test_gpu_parity.py)."""
+    from rcs_b200 import common
+    from rcs_b200.envs.base import ControlMode
+    N = 48
+    mode = getattr(ControlMode, mode_name)
+    max_t, max_r = 0.2, np.deg2rad(45)
+    env = _mk(mode, num_envs=N, gripper=False, max_rel=(max_t, max_r), async_control=True)
+    obs, _ = env.reset()
+    b = env.sim.batch
+    rng = np.random.default_rng(5)
+    xyz = rng.uniform(-0.03, 0.03, (N, 3)); xyz[::4] *= 10          # every fourth offset exceeds the 0.2 m cap
+    rpy = rng.uniform(-0.1, 0.1, (N, 3)); rpy[1::4] *= 12            # some exceed the 45 degree cap
+    if mode == ControlMode.CARTESIAN_TRPY:
+        a = np.concatenate([xyz, rpy], axis=1); key = "xyzrpy"
+    else:
+        quat = np.stack([common.Pose(translation=np.zeros(3), rpy_vector=r).rotation_q() for r in rpy])
+        a = np.concatenate([xyz, quat], axis=1); key = "tquat"
+    tq0 = obs["tquat"].cpu().numpy()
+    q_now = b.qpos[:, :7].clone().contiguous()
+    poses = np.zeros((N, 7))
+    for e in range(N):
+        origin = common.Pose(translation=tq0[e, :3], quaternion=tq0[e, 3:])
+        if mode == ControlMode.CARTESIAN_TRPY:
+            off = common.Pose(translation=a[e, :3], rpy_vector=a[e, 3:])
+        else:
+            off = common.Pose(translation=a[e, :3], quaternion=a[e, 3:])
+        off = off.limit_translation_length(max_t).limit_rotation_angle(max_r)
+        t = np.clip(origin.translation() + off.translation(), [-0.855, -0.855, 0], [0.855, 0.855, 1.188])
+        if mode == ControlMode.CARTESIAN_TRPY:
+            tgt = common.Pose(translation=t, rpy_vector=(off * origin).rotation_rpy().as_vector())
+        else:
+            tgt = common.Pose(translation=t, quaternion=(off * origin).rotation_q())
+        poses[e, :3] = tgt.translation(); poses[e, 3:] = tgt.rotation_q()
+    q_exp, ok, _ = b.ik_inverse(torch.as_tensor(poses, device=b.dev), q_now)
+    assert int(ok.sum()) > N // 2
+    obs1, _, _, _, info = env.step({key: torch.as_tensor(a, device=b.dev)})
+    okn = ok.cpu().numpy().astype(bool)
+    assert np.array_equal(info["ik_success"].cpu().numpy(), okn)
+    ctrl = b.ctrl[:, :7].cpu().numpy()
+    assert np.abs(ctrl[okn] - q_exp.cpu().numpy()[okn, :7]).max() < 1e-9
+    # RobotEnv.step dedupe (base.py:268-287): an absolute action equal to the previous one (atol 1e-3) sends no command.
+    # With LAST_STEP a repeated zero offset yields the current pose twice once the robot has stopped moving.
+    zero = np.zeros_like(a)
+    if mode == ControlMode.CARTESIAN_TQuat:
+        zero[:, 6] = 1
+    za = torch.as_tensor(zero, device=b.dev)
+    for _ in range(40):
+        env.step({key: za})
+    ctrl_before = b.ctrl[:, :7].clone()
+    env.step({key: za})
+    assert (b.ctrl[:, :7] - ctrl_before).abs().max() < 1e-3
