@@ -17,11 +17,57 @@ class SimEnvCreator:
             raise NotImplementedError("SimTilburgHand is out of scope (SURVEY.md 2 row 15)")
         if cameras is not None:
             raise NotImplementedError("SimCameraSet is a 'next' row (SURVEY.md 8f-2)")
-        if sim_wrapper is not None:
-            raise NotImplementedError("SimWrapper task layers are a 'next' row (SURVEY.md 8f-1)")
         simulation = sim.Sim(robot_cfg.mjcf_scene_path, sim_cfg, num_envs=num_envs, device=device)
         ik = sim.Pin(robot_cfg.kinematic_model_path, robot_cfg.attachment_site,
                      urdf=robot_cfg.kinematic_model_path.endswith(".urdf"))
         robot = sim.SimRobot(simulation, ik, robot_cfg)
         gripper = sim.SimGripper(simulation, gripper_cfg) if gripper_cfg is not None else None
-        return SimVectorEnv(simulation, robot, gripper, control_mode, max_relative_movement, relative_to)
+        env = SimVectorEnv(simulation, robot, gripper, control_mode, max_relative_movement, relative_to)
+        if sim_wrapper is not None:  # creators.py:101-103: the task layer wraps the sim env
+            env = sim_wrapper(env, simulation)
+        return env
+
+
+class SimTaskEnvCreator:
+    """creators.py:131-189: relative Cartesian control + a re-placement wrapper + the pick-up success / reward wrapper."""
+
+    def __call__(self, robot_cfg: sim.SimRobotConfig, render_mode: str = "none", control_mode: ControlMode = ControlMode.CARTESIAN_TRPY,
+                 delta_actions: bool = True, cameras=None, hand_cfg=None, gripper_cfg: sim.SimGripperConfig | None = None,
+                 sim_cfg: sim.SimConfig | None = None, random_pos_args: dict | None = None, num_envs: int = 1, device: int = 0):
+        import numpy as np
+        from functools import partial
+        from rcs_b200.envs.task import PickCubeSuccessWrapper, RandomCubePos, RandomObjectPos
+        from rcs_b200.envs.utils import default_sim_gripper_cfg
+        if hand_cfg is not None:
+            raise NotImplementedError("SimTilburgHand is out of scope (SURVEY.md 2 row 15)")
+        if render_mode == "human":
+            raise NotImplementedError("the GUI bridge is out of scope (SURVEY.md 8f-3)")
+        random_env = RandomCubePos
+        if random_pos_args is not None and all(k in random_pos_args for k in ("joint_name", "init_object_pose")):
+            random_env = partial(RandomObjectPos, **random_pos_args)
+        env = SimEnvCreator()(control_mode=control_mode, robot_cfg=robot_cfg, collision_guard=False,
+                              gripper_cfg=gripper_cfg if gripper_cfg is not None else default_sim_gripper_cfg(), sim_cfg=sim_cfg,
+                              cameras=cameras, max_relative_movement=(0.2, float(np.deg2rad(45))) if delta_actions else None,
+                              relative_to=RelativeTo.LAST_STEP, sim_wrapper=random_env, num_envs=num_envs, device=device)
+        return PickCubeSuccessWrapper(env)
+
+
+class FR3SimplePickUpSimEnvCreator:
+    """creators.py:192-224 (gym id rcs/FR3SimplePickUpSim-v0): fr3_simple_pick_up, async 30 Hz, relative TRPY control."""
+
+    def __call__(self, render_mode: str = "none", control_mode: ControlMode = ControlMode.CARTESIAN_TRPY, resolution=None,
+                 frame_rate: int = 0, delta_actions: bool = True, cam_list=None, num_envs: int = 1, device: int = 0):
+        import numpy as np
+        from rcs_b200 import common
+        from rcs_b200.envs.utils import default_sim_robot_cfg
+        if cam_list:
+            raise NotImplementedError("SimCameraSet is a 'next' row (SURVEY.md 8f-2)")
+        robot_cfg = default_sim_robot_cfg(scene="fr3_simple_pick_up")
+        robot_cfg.tcp_offset = common.Pose(translation=np.array([0.0, 0.0, 0.1034]),
+                                           rotation=np.array([[0.707, 0.707, 0], [-0.707, 0.707, 0], [0, 0, 1]]))
+        sim_cfg = sim.SimConfig()
+        sim_cfg.realtime = False
+        sim_cfg.async_control = True
+        sim_cfg.frequency = 30
+        return SimTaskEnvCreator()(robot_cfg, render_mode, control_mode, delta_actions, None, sim_cfg=sim_cfg, num_envs=num_envs,
+                                   device=device)

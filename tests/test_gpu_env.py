@@ -182,3 +182,35 @@ def test_relative_cartesian_actions_match_reference_math(mode_name):
     ctrl_before = b.ctrl[:, :7].clone()
     env.step({key: za})
     assert (b.ctrl[:, :7] - ctrl_before).abs().max() < 1e-3
+
+
+def test_pick_up_task_env_random_cube_and_reward():
+    """FR3SimplePickUpSimEnvCreator (creators.py:192-224) with RandomCubePos and PickCubeSuccessWrapper
+    (envs/sim.py:359-431) on the batched backend: cube re-placed in the +-0.1 m square around the iso pose, reward in
+    [0, 1], success only with the cube above 0.15 + 0.852 m and the gripper closed."""
+    from rcs_b200.envs.creators import FR3SimplePickUpSimEnvCreator
+    N = 32
+    env = FR3SimplePickUpSimEnvCreator()(num_envs=N)
+    obs, _ = env.reset()
+    b = env.sim.batch
+    box = b.qpos[:, 9:16].cpu().numpy()
+    iso = env.unwrapped.robot.to_pose_in_world_coordinates(
+        __import__("rcs_b200").common.Pose(translation=np.array([0.498, 0.0, 0.226]))).translation()
+    assert np.all(np.abs(box[:, 0] - iso[0]) <= 0.1) and np.all(np.abs(box[:, 1] - iso[1]) <= 0.1)
+    assert np.allclose(box[:, 2], 0.0144) and np.all(np.abs(box[:, 3]) <= 1) and np.allclose(box[:, 6], 1)
+    assert len(np.unique(box[:, 0])) > N // 2  # per-env draws
+    gen = torch.Generator(device=b.dev).manual_seed(0)
+    for t in range(4):
+        a = (torch.rand((N, 6), dtype=torch.float64, device=b.dev, generator=gen) * 2 - 1) * torch.tensor([0.01] * 3 + [0.05] * 3, device=b.dev)
+        g = torch.randint(0, 2, (N,), device=b.dev, generator=gen).to(torch.float64)
+        obs, reward, term, trunc, info = env.step({"xyzrpy": a, "gripper": g})
+    assert reward.shape == (N,) and float(reward.min()) >= 0 and float(reward.max()) <= 1
+    assert not bool(term.any()) and not bool(info["success"].any())
+    assert bool(info["ik_success"].all())
+    assert int(b.si[:, 14].min()) >= 1  # the cube rests on the floor: contacts in every env
+    # lift the cube by hand above the success height and close the gripper
+    b.qpos[:, 11] = 0.15 + 0.852 + 0.05
+    b.qvel[:, 9:15] = 0
+    obs, reward, term, trunc, info = env.step({"xyzrpy": torch.zeros((N, 6), dtype=torch.float64, device=b.dev),
+                                               "gripper": torch.zeros((N,), dtype=torch.float64, device=b.dev)})
+    assert bool(term.all()) and bool(info["success"].all()) and np.allclose(reward.cpu().numpy(), 1.0)
