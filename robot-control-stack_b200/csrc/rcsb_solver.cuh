@@ -593,8 +593,11 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
     RCSB_SYNC();
     return;
   }
-  if (ncon == 0 && !(WI(misc)[MI_NF] > 0 && MD(noslip_iterations) > 0)) {
-    // Direct active-set solve for equality / friction-loss / joint-limit rows. The cost is strictly convex and piecewise
+  {
+    // Direct active-set solve. Rows: equality / friction-loss / joint-limit, pyramidal contact rows (plain inequality
+    // rows) and elliptic contacts in their top (separating: inactive) or bottom (force strictly inside the friction
+    // cone, i.e. sticking: every row of the contact a plain quadratic) zone; a contact that lands on the cone surface
+    // hands the problem to the Newton solver. The cost is strictly convex and piecewise
     // quadratic in qacc: with the zone of every row fixed (quadratic, linear with constant force, or inactive) the
     // stationarity condition is the linear system
     //   (M + sum_quadratic D J^T J) qacc = qfrc_smooth + sum_quadratic D aref J^T + sum_linear force J^T,
@@ -615,6 +618,8 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
       state[r] = st;
     }
     RCSB_SYNC();
+    // noslip needs M's own factor in o_L afterwards, so the integrator matrix is not factored alongside then
+    const int need_noslip = MD(noslip_iterations) > 0 && (WI(misc)[MI_NF] > 0 || ncon > 0);
     int verified = 0, attempt = 0;
     for (; attempt < 3 && !verified; attempt++) {
       PFOR(t, nv * (nv + 1) / 2) {
@@ -637,16 +642,18 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
       }
       // the integrator's matrix does not depend on the constraint forces: on the first pass it is factored in the
       // idle half of the warp (o_L is free here: M's own factor is only needed by the Newton / noslip path)
-      const int dual = attempt == 0 && nv <= 16 && !WI(misc)[MI_HAVE_L];
+      const int dual = attempt == 0 && nv <= 16 && !WI(misc)[MI_HAVE_L] && !need_noslip;
       if (dual) build_integrator_matrix(c, WR(L));
       chol_factor_solve(c, WR(H), WR(H) + nv * nv, nv, WR(qacc), WR(tmp), dual ? WR(L) : nullptr, dual ? WR(L) + nv * nv : nullptr);
       if (dual && c.lane == 0) WI(misc)[MI_HAVE_H2] = 1;
-      int changed = 0;
+      int changed = 0, on_cone = 0;
       PFOR(r, nefc) {
         real s = 0;
         for (int k = 0; k < nv; k++) s += WR(J)[r * nv + k] * WR(qacc)[k];
         real jar = s - EFC(RCSB_E_AREF)[r], D = EFC(RCSB_E_D)[r], force;
         int type = etype[r], st;
+        EFC(RCSB_E_JAR)[r] = jar;
+        if (type == RCSB_CONTACT_ELL) continue;  // zone of the whole contact: below
         if (type == RCSB_EQ) { st = RCSB_QUADRATIC; force = -D * jar; }
         else if (type == RCSB_FRICTION_DOF) {
           real f = EFC(RCSB_E_FLOSS)[r], R = EFC(RCSB_E_R)[r];
@@ -658,11 +665,34 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
         }
         if (st != state[r]) changed = 1;
         state[r] = st;
-        EFC(RCSB_E_JAR)[r] = jar;
         EFC(RCSB_E_FORCE)[r] = force;
       }
+      if (MD(cone_elliptic) && ncon > 0) {
+        RCSB_SYNC();
+        const real* jar = EFC(RCSB_E_JAR);
+        PFOR(ci, ncon) {
+          const real* cr = WR(con) + RCSB_C_REALS * ci;
+          const int* cii = WI(con) + RCSB_CI_INTS * ci;
+          const int i = cii[RCSB_CI_EFC], dim = cii[RCSB_CI_DIM];
+          if (i < 0) continue;
+          real mu = cr[RCSB_C_MU], fr = cr[RCSB_C_FRIC], N = jar[i] * mu, T2 = 0;
+          for (int j = 1; j < dim; j++) { real u = jar[i + j] * fr; T2 += u * u; }
+          real T = r_sqrt(T2);
+          int st;
+          if (N >= mu * T || (T <= 0 && N >= 0)) st = RCSB_SATISFIED;
+          else if (mu * N + T <= 0 || (T <= 0 && N < 0)) st = RCSB_QUADRATIC;
+          else { st = RCSB_CONE; on_cone = 1; }
+          for (int j = 0; j < dim; j++) {
+            if (st != state[i + j]) changed = 1;
+            state[i + j] = st;
+            EFC(RCSB_E_FORCE)[i + j] = st == RCSB_QUADRATIC ? -EFC(RCSB_E_D)[i + j] * jar[i + j] : (real)0;
+          }
+        }
+      }
       verified = !warp_any(changed);
+      on_cone = warp_any(on_cone);
       RCSB_SYNC();
+      if (on_cone) { verified = 0; break; }
     }
     if (verified) {
       PFOR(k, nv) {
@@ -672,6 +702,10 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
       }
       if (c.lane == 0) WI(misc)[MI_SOLVER_ITER] = attempt;
       RCSB_SYNC();
+      if (need_noslip) {  // the post-pass works on M's own factor and the unconstrained acceleration
+        compute_qacc_smooth(c);
+        solve_noslip(c, nefc, ncon);
+      }
       return;
     }
   }
