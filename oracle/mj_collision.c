@@ -41,6 +41,10 @@ static void support(const rcso_model* m, const rcso_data* d, int g, const double
   } else if (type == GEOM_SPHERE) {
     double n = norm3(dl);
     if (n > MINVAL) for (int k = 0; k < 3; k++) v[k] = size[0] * dl[k] / n;
+  } else if (type == GEOM_CYLINDER) { /* [3P] mjc_support: rim point in the xy direction, cap by the sign of z */
+    double n = sqrt(dl[0] * dl[0] + dl[1] * dl[1]);
+    if (n > MINVAL) { v[0] = dl[0] / n * size[0]; v[1] = dl[1] / n * size[0]; }
+    v[2] = dl[2] > 0 ? size[1] : (dl[2] < 0 ? -size[1] : 0);
   }
   mulmat3(out, R, v);
   out[0] += p[0]; out[1] += p[1]; out[2] += p[2];

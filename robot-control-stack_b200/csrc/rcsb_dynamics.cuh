@@ -542,6 +542,10 @@ RCSB_DEV void support(const Ctx& c, int g, const real* gp, const real* gR, const
   } else if (type == RCSB_GEOM_SPHERE) {
     real n = norm3(dl);
     if (n > RCSB_MINVAL) for (int k = 0; k < 3; k++) v[k] = m.g_size[g][0] * dl[k] / n;
+  } else if (type == RCSB_GEOM_CYLINDER) {  // rim point in the xy direction, cap by the sign of z
+    real n = r_sqrt(dl[0] * dl[0] + dl[1] * dl[1]);
+    if (n > RCSB_MINVAL) { v[0] = dl[0] / n * m.g_size[g][0]; v[1] = dl[1] / n * m.g_size[g][0]; }
+    v[2] = dl[2] > 0 ? m.g_size[g][1] : (dl[2] < 0 ? -m.g_size[g][1] : (real)0);
   }
   mulmat3(out, gR, v);
   out[0] += gp[0]; out[1] += gp[1]; out[2] += gp[2];

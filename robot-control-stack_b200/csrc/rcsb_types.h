@@ -28,7 +28,7 @@ enum {
 };
 
 enum { RCSB_JNT_FREE = 0, RCSB_JNT_SLIDE = 2, RCSB_JNT_HINGE = 3 };
-enum { RCSB_GEOM_PLANE = 0, RCSB_GEOM_SPHERE = 2, RCSB_GEOM_CAPSULE = 3, RCSB_GEOM_BOX = 6, RCSB_GEOM_MESH = 7 };
+enum { RCSB_GEOM_PLANE = 0, RCSB_GEOM_SPHERE = 2, RCSB_GEOM_CAPSULE = 3, RCSB_GEOM_CYLINDER = 5, RCSB_GEOM_BOX = 6, RCSB_GEOM_MESH = 7 };
 enum { RCSB_TRN_JOINT = 0, RCSB_TRN_TENDON = 3 };
 enum { RCSB_EQ = 0, RCSB_FRICTION_DOF = 1, RCSB_LIMIT = 3, RCSB_CONTACT_PYR = 6, RCSB_CONTACT_ELL = 7 };
 enum { RCSB_SATISFIED = 0, RCSB_QUADRATIC = 1, RCSB_LINEARNEG = 2, RCSB_LINEARPOS = 3, RCSB_CONE = 4 };

@@ -53,3 +53,16 @@ def workload_actions(nenv, nsteps, seed=0):
     a[:, :, :7] = rng.uniform(-np.deg2rad(5), np.deg2rad(5), (nenv, nsteps, 7))
     a[:, :, 7] = rng.integers(0, 2, (nenv, nsteps))
     return a
+
+
+XARM_Q_HOME = np.array([0, -45.0, 0, 15.0, 0, -25.0, 0]) * np.pi / 180
+XARM_JLOW = np.array([-2 * np.pi, -2.094395, -2 * np.pi, -3.92699, -2 * np.pi, -np.pi, -2 * np.pi])
+XARM_JHIGH = np.array([2 * np.pi, 2.059488, 2 * np.pi, 0.191986, 2 * np.pi, 1.692969, 2 * np.pi])
+
+
+def xarm_robot_ns():
+    """examples/xarm7/xarm7_env_joint_control.py:44-66"""
+    return NS(joints=[f"joint{i}" for i in range(1, 8)], actuators=[f"act{i}" for i in range(1, 8)], arm_collision_geoms=[],
+              attachment_site="attachment_site", base="base", tcp_offset=[0, 0, 0, 0, 0, 0, 1.0], q_home=XARM_Q_HOME,
+              joint_rotational_tolerance=0.05 * np.pi / 180, seconds_between_callbacks=0.1, register_convergence_callback=True,
+              ik_nq=7)

@@ -174,3 +174,28 @@ def test_separation_budgets_detect_contact_on_the_same_step(fr3):
         assert int(e.si[0, 14]) == int(s.data.ncon[0]), k
         assert np.abs(e.sr[0, :9] - s.data.qpos).max() < 1e-7, k
         assert np.abs(e.sr[0, 9:18] - s.data.qvel).max() < 1e-5, k
+
+
+def test_xarm7_friction_loss_rows_and_cylinder(fr3):
+    """xarm7_empty_world: 7 friction-loss rows on every step (solved by zone verification, no Newton iteration),
+    pyramidal cone option, a cylinder pedestal in the collision set, no gripper / tendon / equality."""
+    M = H.scene("xarm7_empty_world")
+    F, verts = devmodel.build_device_fields(M, H.xarm_robot_ns(), None)
+    N = 16
+    e = Emu(F, verts, N)
+    rng = np.random.default_rng(11)
+    q = H.XARM_Q_HOME + rng.uniform(-0.3, 0.3, (N, 7))
+    v = rng.uniform(-0.5, 0.5, (N, 7)); v[::3] = 0  # zero velocity: friction rows in their quadratic (sticking) zone
+    ctrl = q + rng.uniform(-0.1, 0.1, (N, 7))
+    e.sr[:, 0:7] = q; e.sr[:, 7:14] = v; e.sr[:, 14:21] = ctrl
+    m = O.Model(M)
+    ds = []
+    for i in range(N):
+        d = O.Data(m); d.qpos[:] = q[i]; d.qvel[:] = v[i]; d.ctrl[:] = ctrl[i]; ds.append(d)
+    for it in range(12):
+        e.run(["STEP_K"], k=5)
+        for i, d in enumerate(ds):
+            d.step(5)
+            assert int(e.si[i, 15]) == int(d.nefc[0]) >= 7
+            assert np.abs(e.sr[i, 0:7] - d.qpos).max() < 1e-9, (it, i)
+            assert np.abs(e.sr[i, 7:14] - d.qvel).max() < 1e-7, (it, i)

@@ -208,3 +208,48 @@ def test_reduced_layout_hand_over_and_kernel_variants_bit_exact(setup, monkeypat
     assert b2.occupancy()["variant"] == "generic"
     for a, c in zip(ref, gen):
         assert np.array_equal(a, c)
+
+
+def test_xarm7_scene_parity(setup):
+    """xarm7_empty_world through the generic kernel variant: friction-loss rows on every dof, pyramidal cones, a cylinder
+    in the collision set, no gripper."""
+    _, _, _lib, batch = setup
+    M = H.scene("xarm7_empty_world")
+    dm = batch.DeviceModel(M, H.xarm_robot_ns(), None)
+    N = 64
+    b = batch.Batch(dm, N)
+    assert b.occupancy()["variant"] == "generic"
+    rng = np.random.default_rng(11)
+    q = H.XARM_Q_HOME + rng.uniform(-0.3, 0.3, (N, 7))
+    v = rng.uniform(-0.5, 0.5, (N, 7)); v[::3] = 0
+    ctrl = q + rng.uniform(-0.1, 0.1, (N, 7))
+    b.qpos.copy_(torch.as_tensor(q)); b.qvel.copy_(torch.as_tensor(v)); b.ctrl.copy_(torch.as_tensor(ctrl))
+    m = O.Model(M)
+    for it in range(6):
+        b.run(_lib.STEP_K, k=10)
+        gq, gv = b.qpos.cpu().numpy(), b.qvel.cpu().numpy()
+        for i in range(0, N, 7):
+            d = O.Data(m); d.qpos[:] = q[i]; d.qvel[:] = v[i]; d.ctrl[:] = ctrl[i]
+            d.step(10 * (it + 1))
+            assert np.abs(gq[i] - d.qpos).max() < 1e-9, (it, i)
+            assert np.abs(gv[i] - d.qvel).max() < 1e-7, (it, i)
+    # the reference-style env surface on the second robot type (examples/xarm7/xarm7_env_joint_control.py)
+    import rcs_b200
+    from rcs_b200 import common, sim
+    from rcs_b200.envs.base import ControlMode
+    from rcs_b200.envs.creators import SimEnvCreator
+    cfg = sim.SimRobotConfig()
+    cfg.actuators = [f"act{i}" for i in range(1, 8)]; cfg.joints = [f"joint{i}" for i in range(1, 8)]
+    cfg.base = "base"; cfg.robot_type = common.RobotType.XArm7; cfg.attachment_site = "attachment_site"
+    cfg.arm_collision_geoms = []
+    cfg.mjcf_scene_path = rcs_b200.scenes["xarm7_empty_world"].mjb
+    cfg.kinematic_model_path = rcs_b200.scenes["xarm7_empty_world"].mjcf_robot
+    env = SimEnvCreator()(ControlMode.JOINTS, cfg, gripper_cfg=None, max_relative_movement=float(np.deg2rad(5)),
+                          sim_cfg=sim.SimConfig(async_control=True), num_envs=32)
+    obs0, _ = env.reset()
+    q0 = obs0["joints"].clone()  # observations are views of the batch's packed buffer
+    assert np.allclose(q0.cpu().numpy(), H.XARM_Q_HOME, atol=2e-3)
+    for t in range(5):
+        obs, _, _, trunc, info = env.step(env.action_space.sample())
+    assert bool(info["ik_success"].all()) and not bool(info["collision"].any())
+    assert float((obs["joints"] - q0).abs().max()) > 1e-3

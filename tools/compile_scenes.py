@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.join(ROOT, "robot-control-stack_b200"))
 from rcs_b200 import mjcf  # noqa: E402
 
 SRC = sys.argv[1] if len(sys.argv) > 1 else "/root/reference/assets/scenes"
-for name in ("fr3_empty_world", "fr3_simple_pick_up"):
+for name in ("fr3_empty_world", "fr3_simple_pick_up", "xarm7_empty_world"):
     M = mjcf.compile_mjcf(os.path.join(SRC, name, "scene.xml"))
     out = os.path.join(ROOT, "robot-control-stack_b200", "rcs_b200", "models", name + ".npz")
     mjcf.save_model(M, out)
