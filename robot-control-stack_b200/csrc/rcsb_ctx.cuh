@@ -31,6 +31,7 @@ struct Ctx {
   uint32_t wib;         // this warp's int workspace
   int lane;
   int lockstep;         // fixed-substep launch: CTA barriers between stages keep the warps on the same code
+  int bar_id, bar_threads;  // named barrier of this warp's group and the number of threads that meet at it
 };
 #define CMODEL(c) (*(const RcsbModel*)rcsb_smem)
 #define CMODEL_G(c) (*(c).gm)

@@ -231,8 +231,8 @@ RCSB_DEV void run_env_pre_ops(const Ctx& c, const RcsbLaunch& L, int env) {
 // CTA barriers a lockstep warp owes for `nsteps` physics steps it does not run
 RCSB_DEV void skip_step_barriers(const Ctx& c, int nsteps) {
 #ifndef RCSB_HOST_EMU
-  int n = c.lockstep == 1 ? nsteps * RCSB_STAGE_BARRIERS : (c.lockstep == 2 ? nsteps : 0);
-  for (int i = 0; i < n; i++) __syncthreads();
+  int n = nsteps * __popc((unsigned)c.lockstep);
+  for (int i = 0; i < n; i++) RCSB_GROUP_BARRIER();
 #endif
 }
 RCSB_DEV void run_env_program(const Ctx& c, const RcsbLaunch& L, int env) {

@@ -13,6 +13,7 @@
 #define RCSB_VARIANT_NS rcsb_fr3_full
 #define RCSB_KERNEL rcsb_k_run_fr3_full
 #define RCSB_FIXED_SHAPE RCSB_SHAPE_FR3(6, 28, 0)
+#define RCSB_VARIANT_WARPS 17  // what the layout leaves room for: registers per thread follow from it
 #include "rcsb_variant.cuh"
 #undef RCSB_VARIANT_NS
 #undef RCSB_KERNEL

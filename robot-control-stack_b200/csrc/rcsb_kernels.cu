@@ -35,22 +35,25 @@
 #ifdef RCSB_SINGLE_TU
 #include "rcsb_k_fr3_reduced.cu"
 #include "rcsb_k_fr3_full.cu"
+#include "rcsb_k_fr3_pickup.cu"
 #else
 #define RCSB_DECLARE_VARIANT(ns)                                                                                        \
   namespace ns {                                                                                                        \
   void launch(int, int, size_t, cudaStream_t, const RcsbModel*, const real*, real*, double*, int*, const RcsbLaunch&, int*, size_t); \
   cudaError_t set_smem(size_t);                                                                                         \
+  int max_warps();                                                                                                      \
   RcsbShape shape();                                                                                                    \
   }
 RCSB_DECLARE_VARIANT(rcsb_fr3_reduced)
 RCSB_DECLARE_VARIANT(rcsb_fr3_full)
+RCSB_DECLARE_VARIANT(rcsb_fr3_pickup)
 #endif
 #endif
 
 typedef void (*rcsb_launch_fn)(int, int, size_t, cudaStream_t, const RcsbModel*, const real*, real*, double*, int*, const RcsbLaunch&,
                                int*, size_t);
 typedef cudaError_t (*rcsb_smem_fn)(size_t);
-struct RcsbVariant { const char* name; int fixed; RcsbShape shape; rcsb_launch_fn launch; rcsb_smem_fn set_smem; };
+struct RcsbVariant { const char* name; int fixed; RcsbShape shape; rcsb_launch_fn launch; rcsb_smem_fn set_smem; int max_warps; };
 static bool shape_equal(const RcsbShape& a, const RcsbShape& b) { return memcmp(&a, &b, sizeof(RcsbShape)) == 0; }
 // the most specialised variant compiled for this model's shape (the generic one always matches)
 static RcsbVariant pick_variant(const RcsbModel& h) {
@@ -58,11 +61,12 @@ static RcsbVariant pick_variant(const RcsbModel& h) {
   const char* force = getenv("RCSB_VARIANT");  // "generic" disables the fixed-shape kernels (testing / tuning)
   if (!(force && !strcmp(force, "generic"))) {
 #ifndef RCSB_NO_FIXED_VARIANTS
-    if (shape_equal(s, rcsb_fr3_reduced::shape())) return {"fr3_reduced", 1, s, rcsb_fr3_reduced::launch, rcsb_fr3_reduced::set_smem};
-    if (shape_equal(s, rcsb_fr3_full::shape())) return {"fr3_full", 1, s, rcsb_fr3_full::launch, rcsb_fr3_full::set_smem};
+    if (shape_equal(s, rcsb_fr3_reduced::shape())) return {"fr3_reduced", 1, s, rcsb_fr3_reduced::launch, rcsb_fr3_reduced::set_smem, rcsb_fr3_reduced::max_warps()};
+    if (shape_equal(s, rcsb_fr3_full::shape())) return {"fr3_full", 1, s, rcsb_fr3_full::launch, rcsb_fr3_full::set_smem, rcsb_fr3_full::max_warps()};
+    if (shape_equal(s, rcsb_fr3_pickup::shape())) return {"fr3_pickup", 1, s, rcsb_fr3_pickup::launch, rcsb_fr3_pickup::set_smem, rcsb_fr3_pickup::max_warps()};
 #endif
   }
-  return {"generic", 0, s, rcsb_generic::launch, rcsb_generic::set_smem};
+  return {"generic", 0, s, rcsb_generic::launch, rcsb_generic::set_smem, rcsb_generic::max_warps()};
 }
 
 // IK kernel: one environment per thread
@@ -119,7 +123,8 @@ struct rcsb_batch {
   cudaStream_t stream;
   int* d_counter = nullptr;   // [0] env cursor phase 0, [1] overflow cursor phase 1, [2] overflow count
   int* d_overflow = nullptr;  // [n] overflow list
-  int warps = 0, grid = 0, lockstep = 1;
+  int bar_groups = 1;
+  int warps = 0, grid = 0, lockstep = 0x2a5;  // barrier mask of fixed-substep launches (rcsb_warp.cuh)
   size_t smem = 0, ws_bytes = 0;
   RcsbVariant var, var_full;          // kernel variants of the two phases
   int warps_full = 0, grid_full = 0;  // phase 1 (full layout) launch shape when a reduced layout exists
@@ -236,11 +241,18 @@ rcsb_batch* rcsb_batch_new(rcsb_model* m, int n_envs, void* sr, void* sd, void* 
     int o = atoi(ov);
     if (o >= 1 && o < cap) cap = o;
   }
-  if (const char* ov = getenv("RCSB_LOCKSTEP")) b->lockstep = atoi(ov);  // 0 none, 1 per stage, 2 per step
-  auto shape = [&](const RcsbModel& h, size_t& ws, int& warps, size_t& smem, int& grid) {
+  if (const char* ov = getenv("RCSB_BAR_GROUPS")) { int g = atoi(ov); if (g >= 1 && g <= 15) b->bar_groups = g; }
+  if (const char* ov = getenv("RCSB_LOCKSTEP")) {  // tuning knob: 0 none, 1 every stage, 2 once per step, 0x.. explicit mask
+    long v = strtol(ov, nullptr, 0);
+    b->lockstep = v == 1 ? RCSB_LOCKSTEP_ALL : (v == 2 ? RCSB_LOCKSTEP_STEP : (int)v);
+  }
+  b->var = pick_variant(m->has_reduced ? m->hr : m->h);
+  b->var_full = pick_variant(m->h);
+  auto shape = [&](const RcsbModel& h, const RcsbVariant& var, size_t& ws, int& warps, size_t& smem, int& grid) {
     ws = rcsb_ws_bytes(&h);
     warps = (int)((avail - RCSB_SMEM_HEADER) / ws);
     if (warps > cap) warps = cap;
+    if (warps > var.max_warps) warps = var.max_warps;  // the kernel's launch bounds
     if (warps < 1) return false;
     smem = RCSB_SMEM_HEADER + (size_t)warps * ws;
     grid = prop.multiProcessorCount;
@@ -248,11 +260,9 @@ rcsb_batch* rcsb_batch_new(rcsb_model* m, int n_envs, void* sr, void* sd, void* 
     if (grid > need) grid = need;
     return true;
   };
-  bool ok = shape(m->has_reduced ? m->hr : m->h, b->ws_bytes, b->warps, b->smem, b->grid);
-  if (ok && m->has_reduced) ok = shape(m->h, b->ws_bytes_full, b->warps_full, b->smem_full, b->grid_full);
+  bool ok = shape(m->has_reduced ? m->hr : m->h, b->var, b->ws_bytes, b->warps, b->smem, b->grid);
+  if (ok && m->has_reduced) ok = shape(m->h, b->var_full, b->ws_bytes_full, b->warps_full, b->smem_full, b->grid_full);
   if (!ok) { fail(RCSB_ERR_MODEL, "workspace does not fit in shared memory"); delete b; return nullptr; }
-  b->var = pick_variant(m->has_reduced ? m->hr : m->h);
-  b->var_full = pick_variant(m->h);
   const size_t smem_max = b->smem > b->smem_full ? b->smem : b->smem_full;  // both phases may use the same kernel
   if (b->var.set_smem(smem_max) != cudaSuccess || (m->has_reduced && b->var_full.set_smem(smem_max) != cudaSuccess) ||
       cudaFuncSetAttribute(rcsb_k_ik, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCSB_SMEM_HEADER) != cudaSuccess ||
@@ -302,7 +312,7 @@ int rcsb_batch_run(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps
   if ((ops & RCSB_OP_ACT_JOINTS_REL) && (!jlow || !jhigh)) return fail(RCSB_ERR_ARG, "joint limits required");
   RcsbLaunch L;
   memset(&L, 0, sizeof(L));
-  L.N = b->n; L.ops = ops; L.lockstep = b->lockstep; L.k = k; L.max_convergence_steps = max_convergence_steps;
+  L.N = b->n; L.ops = ops; L.lockstep = b->lockstep; L.bar_groups = b->bar_groups; L.k = k; L.max_convergence_steps = max_convergence_steps;
   L.act_joints = (const real*)act_joints_dev; L.act_gripper = (const real*)act_gripper_dev; L.mask = mask_dev;
   L.max_mov = (real)max_mov;
   for (int i = 0; i < b->m->h.rb_njoints && i < RCSB_MAXJ; i++) {

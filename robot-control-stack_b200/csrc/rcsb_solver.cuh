@@ -981,13 +981,13 @@ RCSB_DEV void reset_data(const Ctx& c, double* time) {  // mj_resetData
 #if defined(RCSB_STAGE_TIMING) && !defined(RCSB_HOST_EMU)
 #define RCSB_STAGE(idx, call)                                                                        \
   do {                                                                                               \
-    RCSB_BLOCK_SYNC();                                                                               \
+    RCSB_STAGE_SYNC(idx);                                                                            \
     long long t0_ = clock64();                                                                       \
     call;                                                                                            \
     if (blockIdx.x == 0 && threadIdx.x == 0) rcsb_stage_cycles[idx] += (unsigned long long)(clock64() - t0_); \
   } while (0)
 #else
-#define RCSB_STAGE(idx, call) do { RCSB_BLOCK_SYNC(); call; } while (0)
+#define RCSB_STAGE(idx, call) do { RCSB_STAGE_SYNC(idx); call; } while (0)
 #endif
 // returns 1 when the step did not fit the reduced workspace layout: nothing persistent was changed, the caller hands
 // the environment to the full-capacity launch
@@ -1010,7 +1010,7 @@ RCSB_DEV int physics_step(const Ctx& c, double* time) {
   RCSB_STAGE(4, st_velocity(c));
   RCSB_STAGE(5, st_make_constraint(c));
   if (MD(cap_reduced) && WI(misc)[MI_OVERFLOW]) {
-    for (int i = 0; i < 3; i++) RCSB_BLOCK_SYNC();  // the barriers of the stages this warp skips
+    for (int i = 6; i < 9; i++) RCSB_STAGE_SYNC(i);  // the barriers of the stages this warp skips
     RCSB_STEP_SYNC();
     return 1;
   }

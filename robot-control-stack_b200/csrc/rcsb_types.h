@@ -195,7 +195,8 @@ struct RcsbLaunch {
   int N, env_offset;
   unsigned ops;
   int k, max_convergence_steps;
-  int lockstep;  // fixed-substep launches: 0 no CTA barriers, 1 one per stage, 2 one per physics step
+  int bar_groups;  // fixed-substep launches: number of separately aligned warp groups per CTA (named barriers, <= 15)
+  int lockstep;  // fixed-substep launches: mask of CTA barriers (bit i: before stage i of the step, bit 9: at its end)
   int phase;     // 0: every environment, reduced or full layout; 1: full layout, only the environments in overflow_list
   int* overflow_list;   // [N] environments the reduced layout could not finish (phase 0 appends, phase 1 consumes)
   int* overflow_count;

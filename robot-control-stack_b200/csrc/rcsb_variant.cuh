@@ -36,10 +36,14 @@ __device__ __forceinline__ Ctx make_ctx(const RcsbModel* sm, const RcsbModel* gm
   c.verts = verts;
   c.lane = threadIdx.x & 31;
   c.lockstep = 0;
+  c.bar_id = 0; c.bar_threads = blockDim.x;
   return c;
 }
 // ------------------------------------------------------------------ the per-launch program kernel
-__global__ void __launch_bounds__(RCSB_MAX_WARPS * 32, 1)
+#ifndef RCSB_VARIANT_WARPS
+#define RCSB_VARIANT_WARPS RCSB_MAX_WARPS  // warps per CTA the variant is compiled for: fewer warps, more registers each
+#endif
+__global__ void __launch_bounds__(RCSB_VARIANT_WARPS * 32, 1)
 RCSB_KERNEL(const RcsbModel* __restrict__ gm, const real* __restrict__ verts, real* __restrict__ sr, double* __restrict__ sd,
            int* __restrict__ si, RcsbLaunch L, int* __restrict__ counter, size_t ws_bytes) {
   if (L.phase == 1 && *L.overflow_count == 0) return;  // the common case: nothing outgrew the reduced layout
@@ -52,7 +56,13 @@ RCSB_KERNEL(const RcsbModel* __restrict__ gm, const real* __restrict__ verts, re
     // hits exactly L.k * RCSB_STAGE_BARRIERS CTA barriers per round (inside run_env_program, or here when it has no environment), which
     // keeps the warps in the same stage of the step so that they share instruction-cache lines.
     c.lockstep = L.lockstep;
-    const int nbar = L.lockstep == 1 ? L.k * RCSB_STAGE_BARRIERS : (L.lockstep == 2 ? L.k : 0);
+    {  // barrier groups: contiguous blocks of warps, sizes differ by at most one warp
+      const int W_ = blockDim.x >> 5, G_ = L.bar_groups < 1 ? 1 : (L.bar_groups > W_ ? W_ : L.bar_groups), w_ = threadIdx.x >> 5;
+      const int g_ = w_ * G_ / W_, lo_ = (g_ * W_ + G_ - 1) / G_, hi_ = ((g_ + 1) * W_ + G_ - 1) / G_;
+      c.bar_id = 1 + g_;
+      c.bar_threads = (hi_ - lo_) * 32;
+    }
+    const int nbar = L.k * __popc((unsigned)L.lockstep);
     const int W = blockDim.x >> 5, per_round = gridDim.x * W;
     const int rounds = (L.N + per_round - 1) / per_round;
     for (int r = 0; r < rounds; r++) {
@@ -64,7 +74,7 @@ RCSB_KERNEL(const RcsbModel* __restrict__ gm, const real* __restrict__ verts, re
         store_env(c, sr + (size_t)env * LAY.nsr, sd + (size_t)env * RCSB_D_TAIL, si + (size_t)env * RCSB_I_TAIL);
         __syncwarp();
       } else {
-        for (int i = 0; i < nbar; i++) __syncthreads();
+        for (int i = 0; i < nbar; i++) RCSB_GROUP_BARRIER();
       }
     }
     return;
@@ -105,6 +115,7 @@ RCSB_VARIANT_LINKAGE void launch(int grid, int threads, size_t smem, cudaStream_
 RCSB_VARIANT_LINKAGE cudaError_t set_smem(size_t bytes) {
   return cudaFuncSetAttribute(RCSB_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
+RCSB_VARIANT_LINKAGE int max_warps() { return RCSB_VARIANT_WARPS; }
 #ifdef RCSB_FIXED_SHAPE
 RCSB_VARIANT_LINKAGE RcsbShape shape() { return kShape; }
 #endif
@@ -112,4 +123,5 @@ RCSB_VARIANT_LINKAGE RcsbShape shape() { return kShape; }
 #undef MD
 #undef LAY
 #undef RCSB_VARIANT_LINKAGE
+#undef RCSB_VARIANT_WARPS
 }  // namespace

@@ -15,7 +15,7 @@
 #define RCSB_DEV_NOINLINE static
 #define RCSB_NLANES 1
 #define RCSB_SYNC() ((void)0)
-#define RCSB_BLOCK_SYNC() ((void)0)
+#define RCSB_STAGE_SYNC(i) ((void)0)
 #define RCSB_STEP_SYNC() ((void)0)
 #ifdef RCSB_EMU_REVERSE  // run every parallel-for backwards: results must not depend on lane order
 #define PFOR(i, n) for (int i = (n)-1; i >= 0; --i)
@@ -40,9 +40,14 @@ RCSB_DEV int warp_bcast_i(int x, int src) { return x; }
 #define RCSB_SYNC() __syncwarp()
 // CTA-wide barrier used only in fixed-substep launches, where every warp of the CTA (including warps without an
 // environment, see rcsb_k_run) executes exactly the same number of them
-#define RCSB_BLOCK_SYNC() do { if (c.lockstep == 1) __syncthreads(); } while (0)
-#define RCSB_STEP_SYNC() do { if (c.lockstep) __syncthreads(); } while (0)
-#define RCSB_STAGE_BARRIERS 10  // CTA barriers per physics step in lockstep mode (physics_step)
+// c.lockstep is a bit mask: bit i (0..8) = CTA barrier before stage i of the physics step, bit 9 = barrier at its end
+// The CTA's warps are split into bar_groups groups that align separately (named barriers): a straggler only holds
+// back its own group, the other groups fill the issue slots meanwhile.
+#define RCSB_GROUP_BARRIER() asm volatile("bar.sync %0, %1;" ::"r"(c.bar_id), "r"(c.bar_threads) : "memory")
+#define RCSB_STAGE_SYNC(i) do { if ((c.lockstep >> (i)) & 1) RCSB_GROUP_BARRIER(); } while (0)
+#define RCSB_STEP_SYNC() RCSB_STAGE_SYNC(9)
+#define RCSB_LOCKSTEP_ALL 0x3ff
+#define RCSB_LOCKSTEP_STEP 0x200
 #define PFOR(i, n) for (int i = (int)(threadIdx.x & 31); i < (n); i += 32)
 // same for n <= 32 work items: one guarded pass, no loop
 #define PFOR1(i, n) for (int i = (int)(threadIdx.x & 31), once_ = 1; once_ && i < (n); once_ = 0)

@@ -1,7 +1,4 @@
-for cfg in "1 28" "2 28" "0 28"; do set -- $cfg
-RCSB_LOCKSTEP=$1 RCSB_WARPS=$2 python bench.py --steps 20 --warmup 4 --cpu-seconds 0.1 --envs ${ENVS:-4096} 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.readline()); print('lockstep $1 warps',d['config']['warps_per_cta'],'env-steps/s %.0f'%d['value'],'kernel_ms %.3f'%d['roofline']['kernel_ms'])"
-done
-for n in 16384 65536; do python bench.py --steps 10 --warmup 3 --cpu-seconds 0.1 --envs $n 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.readline()); print('envs $n env-steps/s %.0f'%d['value'],'kernel_ms %.3f'%d['roofline']['kernel_ms'], 'e2e %.0f'%d['e2e']['value'])"
-done
+for g in 1 2 4 7 14; do for m in 0x3ff 0x2a5; do
+RCSB_BAR_GROUPS=$g RCSB_LOCKSTEP=$m python bench.py --steps 20 --warmup 4 --cpu-seconds 0.1 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.readline()); print('groups $g mask $m env-steps/s %.0f'%d['value'],'kernel_ms %.3f'%d['roofline']['kernel_ms'])"
+done; done
