@@ -13,6 +13,9 @@
 #define RCSB_VARIANT_NS rcsb_fr3_reduced
 #define RCSB_KERNEL rcsb_k_run_fr3_reduced
 #define RCSB_FIXED_SHAPE RCSB_SHAPE_FR3(1, 8, 1)
+#ifdef RCSB_REDUCED_WARPS
+#define RCSB_VARIANT_WARPS RCSB_REDUCED_WARPS
+#endif
 #include "rcsb_variant.cuh"
 #undef RCSB_VARIANT_NS
 #undef RCSB_KERNEL
