@@ -30,4 +30,19 @@ for k in rows[0]:
 for v,k in sorted(out,reverse=True): print(f"  {k:24s} {v:.2f}")
 PY
 python tools/ncu_funcs.py /tmp/_src.csv HEAD > $out/${tag}_ncu_functions.txt 2>/dev/null
+python - <<PY
+import json,csv
+rows=list(csv.reader(open('/tmp/_raw.csv')))
+d=dict(zip(rows[0],rows[-1])); u=dict(zip(rows[0],rows[1]))
+def val(k):
+    v=float(d[k].replace(',','')); mult={'Mbyte':1e6,'Kbyte':1e3,'Gbyte':1e9,'byte':1}.get(u.get(k,''),1)
+    return v*mult
+t={"kernel":d.get('Kernel Name','').split('(')[0],"source":"profiles/${tag}_ncu_details.txt (ncu --set full, one launch, 4096 envs x 17 substeps)",
+   "dram_bytes_read":val('dram__bytes_read.sum'),"dram_bytes_write":val('dram__bytes_write.sum'),
+   "inst_executed":float(d['smsp__inst_executed.sum']),"ipc_active":float(d['sm__inst_executed.avg.per_cycle_active']),
+   "fp64_pipe_pct":float(d['sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active']),"lsu_pipe_pct":float(d['sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active']),
+   "kernel_ms_under_ncu":float(d['gpu__time_duration.sum'])*({'us':1e-3,'ms':1,'ns':1e-6}.get(u.get('gpu__time_duration.sum','ms'),1)),
+   "envs":4096,"substeps":17}
+json.dump(t,open('$out/${tag}_traffic.json','w'),indent=1)
+PY
 ls -la $out

@@ -2,6 +2,7 @@
 """Per-stage clock64() breakdown of one physics step (profiling build librcsb_prof.so, warp 0 of CTA 0)."""
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ.setdefault("RCSB_LOCKSTEP", "1")  # a barrier before every stage: the per-stage clocks are comparable
 os.environ["RCSB_LIB_PATH"] = os.path.join(ROOT, "robot-control-stack_b200", "csrc", "librcsb_prof.so")
 for p in (ROOT, os.path.join(ROOT, "robot-control-stack_b200"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
