@@ -253,3 +253,42 @@ def test_xarm7_scene_parity(setup):
         obs, _, _, trunc, info = env.step(env.action_space.sample())
     assert bool(info["ik_success"].all()) and not bool(info["collision"].any())
     assert float((obs["joints"] - q0).abs().max()) > 1e-3
+
+
+def test_results_do_not_depend_on_batch_size_or_mask(setup):
+    """Size-independent properties at BASELINE sizes: environment e's trajectory is bit-identical whether it runs alone, in
+    a ragged batch (N not a multiple of the warps per CTA) or in a 4096+ batch spread over every SM (second round of
+    the static env->warp map); environments excluded by the mask keep every bit of their state."""
+    M, dm, _lib, batch = setup
+    T = 3
+    sizes = (1, 29, 4097)
+    acts = H.workload_actions(max(sizes), T, seed=3)
+    reset = _lib.GRIPPER_RESET | _lib.SIM_RESET | _lib.ROBOT_RESET | _lib.ENV_RESET_FLAGS | _lib.STEP_K | _lib.OBS
+    step = _lib.ACT_JOINTS_REL | _lib.ACT_GRIPPER_BIN | _lib.STEP_K | _lib.OBS
+    outs = {}
+    for n in sizes:
+        b = batch.Batch(dm, n)
+        b.run(reset, k=1, want_obs=True)
+        for t in range(T):
+            b.run(step, k=17, act_joints=torch.as_tensor(acts[:n, t, :7].copy(), device=b.dev),
+                  act_gripper=torch.as_tensor(acts[:n, t, 7].copy(), device=b.dev), max_mov=np.deg2rad(5), jlow=H.JLOW,
+                  jhigh=H.JHIGH, want_obs=True)
+        torch.cuda.synchronize()
+        outs[n] = (b.sr.cpu().numpy().copy(), b.obs.cpu().numpy().copy(), b.si.cpu().numpy().copy())
+    for n in sizes[:-1]:
+        for a, c in zip(outs[n], outs[sizes[-1]]):
+            assert np.array_equal(a, c[:n]), n
+    # mask: only every third environment steps
+    n = 96
+    b = batch.Batch(dm, n)
+    b.run(reset, k=1, want_obs=True)
+    before = [t.clone() for t in (b.sr, b.sd, b.si)]
+    mask = torch.zeros(n, dtype=torch.uint8, device=b.dev); mask[::3] = 1
+    b.run(step, k=17, act_joints=torch.as_tensor(acts[:n, 0, :7].copy(), device=b.dev),
+          act_gripper=torch.as_tensor(acts[:n, 0, 7].copy(), device=b.dev), mask=mask, max_mov=np.deg2rad(5), jlow=H.JLOW,
+          jhigh=H.JHIGH, want_obs=True)
+    torch.cuda.synchronize()
+    keep = (mask == 0).cpu().numpy()
+    for x0, x1 in zip(before, (b.sr, b.sd, b.si)):
+        assert np.array_equal(x0.cpu().numpy()[keep], x1.cpu().numpy()[keep])
+    assert not np.array_equal(before[0].cpu().numpy()[::3], b.sr.cpu().numpy()[::3])
