@@ -217,6 +217,35 @@ class Sim:
     def open_gui(self):
         raise NotImplementedError("GUI bridge is out of scope of the batched backend (SURVEY.md 8f-3)")
 
+    # ---- state export / import: the layout of MuJoCo's mjSTATE_FULLPHYSICS vector that the
+    #      reference's GUI bridge ships between processes (src/sim/gui.h:20: time | qpos | qvel | act; act is empty here)
+    def get_state(self) -> torch.Tensor:
+        b = self.batch
+        return torch.cat([b.time[:, None], b.qpos, b.qvel], dim=1)
+
+    def set_state(self, state: torch.Tensor):
+        """Inverse of get_state() for every environment ([num_envs, 1 + nq + nv]); derived quantities follow on the
+        next step, as after mj_setState."""
+        b = self.batch
+        nq, nv = self.model.nq, self.model.nv
+        st = torch.as_tensor(state, dtype=torch.float64, device=b.dev).reshape(self.num_envs, 1 + nq + nv)
+        b.sd[:, 0] = st[:, 0]
+        b.qpos.copy_(st[:, 1:1 + nq])
+        b.qvel.copy_(st[:, 1 + nq:])
+
+    def save_checkpoint(self) -> dict:
+        """Everything the kernels persist per environment (dynamic state, warm start, RCS device-layer state, callback
+        clocks, flags): restoring it resumes bit-identically."""
+        b = self.batch
+        torch.cuda.synchronize(b.dev)
+        return {"sr": b.sr.clone(), "sd": b.sd.clone(), "si": b.si.clone(), "nsr": b.model.nsr}
+
+    def load_checkpoint(self, ckpt: dict):
+        b = self.batch
+        if ckpt["nsr"] != b.model.nsr or ckpt["sr"].shape != b.sr.shape:
+            raise ValueError("checkpoint does not match this scene / number of environments")
+        b.sr.copy_(ckpt["sr"]); b.sd.copy_(ckpt["sd"]); b.si.copy_(ckpt["si"])
+
     # ---- mjData-like views
     @property
     def data(self):

@@ -214,3 +214,33 @@ def test_pick_up_task_env_random_cube_and_reward():
     obs, reward, term, trunc, info = env.step({"xyzrpy": torch.zeros((N, 6), dtype=torch.float64, device=b.dev),
                                                "gripper": torch.zeros((N,), dtype=torch.float64, device=b.dev)})
     assert bool(term.all()) and bool(info["success"].all()) and np.allclose(reward.cpu().numpy(), 1.0)
+
+
+def test_checkpoint_resume_is_bit_exact_and_fullphysics_state_round_trips():
+    """save_checkpoint / load_checkpoint resume bit-identically; get_state / set_state use the mjSTATE_FULLPHYSICS layout
+    (time | qpos | qvel) of the reference's GUI bridge (src/sim/gui.h:20)."""
+    from rcs_b200.envs.base import ControlMode
+    N = 64
+    env = _mk(ControlMode.JOINTS, num_envs=N, gripper=True, max_rel=float(np.deg2rad(5)), async_control=True)
+    env.reset()
+    gen = torch.Generator(device=env.sim.batch.dev).manual_seed(9)
+    acts = [{"joints": (torch.rand((N, 7), dtype=torch.float64, device=env.sim.batch.dev, generator=gen) * 2 - 1) * np.deg2rad(5),
+             "gripper": torch.randint(0, 2, (N,), device=env.sim.batch.dev, generator=gen).to(torch.float64)} for _ in range(6)]
+    for a in acts[:3]:
+        env.step(a)
+    ck = env.sim.save_checkpoint()
+    for a in acts[3:]:
+        env.step(a)
+    b = env.sim.batch
+    first = [t.clone() for t in (b.sr, b.sd, b.si, b.obs)]
+    env.sim.load_checkpoint(ck)
+    for a in acts[3:]:
+        env.step(a)
+    for x, y in zip(first, (b.sr, b.sd, b.si, b.obs)):
+        assert torch.equal(x, y)
+    st = env.sim.get_state()
+    assert st.shape == (N, 1 + 9 + 9) and torch.equal(st[:, 0], b.time) and torch.equal(st[:, 1:10], b.qpos)
+    env2 = _mk(ControlMode.JOINTS, num_envs=N, gripper=True, max_rel=float(np.deg2rad(5)), async_control=True)
+    env2.reset()
+    env2.sim.set_state(st)
+    assert torch.equal(env2.sim.get_state(), st)
