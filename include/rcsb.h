@@ -35,7 +35,8 @@ enum {
   RCSB_RUN_SET_JOINTS_HARD = 1 << 9, /* SimRobot::set_joints_hard      SimRobot.cpp:197-205 */
   RCSB_RUN_STEP_K = 1 << 10,         /* Sim::step(k)                   sim.cpp:108-115 */
   RCSB_RUN_STEP_CONV = 1 << 11,      /* Sim::step_until_convergence    sim.cpp:84-106 */
-  RCSB_RUN_OBS = 1 << 12             /* RobotEnv.get_obs + info        base.py:246-253, envs/sim.py:60-66,125-131 */
+  RCSB_RUN_OBS = 1 << 12,            /* RobotEnv.get_obs + info        base.py:246-253, envs/sim.py:60-66,125-131 */
+  RCSB_RUN_ACT_GRIPPER_CONT = 1 << 13 /* GripperWrapper.action (continuous width) base.py:721-735 */
 };
 
 const char* rcsb_last_error(void);

@@ -158,6 +158,17 @@ RCSB_DEV void op_set_gripper(const Ctx& c, real width) {  // SimGripper.cpp:79-9
 }
 
 // the whole per-launch program for the environment loaded in the workspace
+// GripperWrapper.action (base.py:721-735): binary (round, clip, grasp() / open()) or continuous (clip, set_normalized_width)
+RCSB_DEV void op_gripper_action(const Ctx& c, const RcsbLaunch& L, int env) {
+  const RcsbModel& m = CMODEL(c);
+  if (!(L.ops & (RCSB_OP_ACT_GRIPPER_BIN | RCSB_OP_ACT_GRIPPER_CONT)) || !MD(gr_enabled)) return;
+  real g = L.act_gripper[env];
+  if (L.ops & RCSB_OP_ACT_GRIPPER_BIN) g = rint(g);
+  g = g < 0 ? (real)0 : (g > 1 ? (real)1 : g);
+  op_set_gripper(c, (L.ops & RCSB_OP_ACT_GRIPPER_BIN) ? (g == 0 ? (real)0 : (real)1) : g);
+  if (c.lane == 0) RS(RCSB_S_GCMD) = g;
+  RCSB_SYNC();
+}
 RCSB_DEV void run_env_pre_ops(const Ctx& c, const RcsbLaunch& L, int env) {
   const RcsbModel& m = CMODEL(c);
   const unsigned ops = L.ops;
@@ -203,13 +214,7 @@ RCSB_DEV void run_env_pre_ops(const Ctx& c, const RcsbLaunch& L, int env) {
       jt[i] = a;
     }
     RCSB_SYNC();
-    if ((ops & RCSB_OP_ACT_GRIPPER_BIN) && MD(gr_enabled)) {  // base.py:721-735
-      real g = rint(L.act_gripper[env]);
-      g = g < 0 ? (real)0 : (g > 1 ? (real)1 : g);
-      op_set_gripper(c, g == 0 ? (real)0 : (real)1);
-      if (c.lane == 0) RS(RCSB_S_GCMD) = g;
-      RCSB_SYNC();
-    }
+    op_gripper_action(c, L, env);
     int changed = !RI(RCSB_I_HAVE_PREV_ACTION);  // base.py:268-272: not allclose(a, prev, atol=1e-3, rtol=0)
     for (int i = 0; i < MD(rb_njoints); i++)
       if (!(r_abs(jt[i] - RS(RCSB_S_PREVACT + i)) <= (real)1e-3)) changed = 1;
@@ -218,12 +223,8 @@ RCSB_DEV void run_env_pre_ops(const Ctx& c, const RcsbLaunch& L, int env) {
     PFOR(i, MD(rb_njoints)) { RS(RCSB_S_PREVACT + i) = jt[i]; }
     if (c.lane == 0) RI(RCSB_I_HAVE_PREV_ACTION) = 1;
     RCSB_SYNC();
-  } else if ((ops & RCSB_OP_ACT_GRIPPER_BIN) && MD(gr_enabled)) {
-    real g = rint(L.act_gripper[env]);
-    g = g < 0 ? (real)0 : (g > 1 ? (real)1 : g);
-    op_set_gripper(c, g == 0 ? (real)0 : (real)1);
-    if (c.lane == 0) RS(RCSB_S_GCMD) = g;
-    RCSB_SYNC();
+  } else {
+    op_gripper_action(c, L, env);
   }
   if (ops & RCSB_OP_SET_JOINTS) op_set_joint_position(c, L.act_joints + (size_t)env * MD(rb_njoints));
   if ((ops & RCSB_OP_SET_GRIPPER) && MD(gr_enabled)) op_set_gripper(c, L.act_gripper[env]);

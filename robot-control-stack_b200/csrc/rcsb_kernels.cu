@@ -307,7 +307,7 @@ int rcsb_batch_run(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps
   if (!b) return fail(RCSB_ERR_ARG, "null batch");
   const unsigned needs_joints = RCSB_OP_ACT_JOINTS_REL | RCSB_OP_ACT_JOINTS_ABS | RCSB_OP_SET_JOINTS | RCSB_OP_SET_JOINTS_HARD;
   if ((ops & needs_joints) && !act_joints_dev) return fail(RCSB_ERR_ARG, "act_joints_dev required for the requested ops");
-  if ((ops & (RCSB_OP_ACT_GRIPPER_BIN | RCSB_OP_SET_GRIPPER)) && !act_gripper_dev)
+  if ((ops & (RCSB_OP_ACT_GRIPPER_BIN | RCSB_OP_ACT_GRIPPER_CONT | RCSB_OP_SET_GRIPPER)) && !act_gripper_dev)
     return fail(RCSB_ERR_ARG, "act_gripper_dev required for the requested ops");
   if ((ops & RCSB_OP_ACT_JOINTS_REL) && (!jlow || !jhigh)) return fail(RCSB_ERR_ARG, "joint limits required");
   RcsbLaunch L;

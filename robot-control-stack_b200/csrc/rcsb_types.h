@@ -186,6 +186,7 @@ enum {
   RCSB_OP_STEP_K = 1 << 10,         // Sim::step(k)
   RCSB_OP_STEP_CONV = 1 << 11,      // Sim::step_until_convergence
   RCSB_OP_OBS = 1 << 12,            // RobotEnv.get_obs + wrappers' observation/info
+  RCSB_OP_ACT_GRIPPER_CONT = 1 << 13,  // GripperWrapper.action, continuous width
 };
 enum { RCSB_OBS_DIM = 22, RCSB_INFO_DIM = 8 };
 // obs row: tquat[7] joints[7] xyzrpy[6] gripper[1] gripper_width[1]

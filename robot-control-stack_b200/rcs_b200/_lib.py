@@ -23,6 +23,7 @@ GRIPPER_RESET, SIM_RESET, ROBOT_RESET, ENV_RESET_FLAGS = 1, 2, 4, 8
 ACT_JOINTS_REL, ACT_JOINTS_ABS, ACT_GRIPPER_BIN = 16, 32, 64
 SET_JOINTS, SET_GRIPPER, SET_JOINTS_HARD = 128, 256, 512
 STEP_K, STEP_CONV, OBS = 1024, 2048, 4096
+ACT_GRIPPER_CONT = 8192
 
 
 def lib():

@@ -41,10 +41,11 @@ class SimVectorEnv:
             assert isinstance(mm, tuple) and len(mm) == 2, \
                 "in cartesian control max_mov must be a tuple of maximum translation (in m) and maximum rotation in (rad)"
             self.max_mov = (float(mm[0]), float(mm[1]))
-        if self.relative and relative_to != RelativeTo.LAST_STEP:
-            raise NotImplementedError("RelativeTo.CONFIGURED_ORIGIN")
-        if not binary_gripper:
-            raise NotImplementedError("continuous gripper actions")
+        if self.relative and relative_to != RelativeTo.LAST_STEP and control_mode != ControlMode.JOINTS:
+            raise NotImplementedError("RelativeTo.CONFIGURED_ORIGIN for Cartesian control")
+        self.binary_gripper = binary_gripper
+        self._origin = None        # RelativeActionSpace._origin / _last_action for CONFIGURED_ORIGIN (base.py:443-467)
+        self._last_action = None
         spaces = {}
         if control_mode == ControlMode.JOINTS:
             if self.relative:
@@ -83,7 +84,7 @@ class SimVectorEnv:
         if self.control_mode == ControlMode.JOINTS:
             ops |= _lib.ACT_JOINTS_REL if self.relative else _lib.ACT_JOINTS_ABS
         if self.gripper is not None:
-            ops |= _lib.ACT_GRIPPER_BIN
+            ops |= _lib.ACT_GRIPPER_BIN if self.binary_gripper else _lib.ACT_GRIPPER_CONT
         return ops, cfg
 
     def _pack(self):
@@ -92,7 +93,7 @@ class SimVectorEnv:
         obs = {"tquat": o[:, 0:7], "joints": o[:, 7:7 + self.dof], "xyzrpy": o[:, 14:20]}
         info = {"collision": f[:, 0].bool(), "ik_success": f[:, 1].bool(), "is_sim_converged": f[:, 2].bool()}
         if self.gripper is not None:
-            obs["gripper"] = o[:, 20]
+            obs["gripper"] = o[:, 20] if self.binary_gripper else o[:, 21]  # last command | normalised width (base.py:710-718)
             info["gripper_width"] = o[:, 21]
             info["is_grasped"] = f[:, 3].bool()
         return obs, info, f[:, 4].bool()
@@ -107,6 +108,9 @@ class SimVectorEnv:
             ops |= _lib.GRIPPER_RESET
         b.run(ops, k=1, want_obs=True)
         obs, info, _ = self._pack()
+        if self.relative and self.relative_to == RelativeTo.CONFIGURED_ORIGIN:  # base.py:462-467
+            self._origin = obs["joints"].clone()
+            self._last_action = None
         return obs, {}
 
     def step(self, action: dict):
@@ -117,6 +121,16 @@ class SimVectorEnv:
             if "joints" not in action:
                 raise RuntimeError("Given type is not matching control mode!")  # base.py:257-266
             aj = action["joints"].to(device=self.dev, dtype=torch.float64).contiguous()
+            if self.relative and self.relative_to == RelativeTo.CONFIGURED_ORIGIN:
+                # base.py:479-488: the offset may move by at most max_mov per step; the origin stays where reset() left it
+                if self._origin is None:
+                    self._origin = b.qpos[:, :self.dof].clone()
+                mm = float(self.max_mov)
+                lim = aj.clamp(-mm, mm) if self._last_action is None else (aj - self._last_action).clamp(-mm, mm) + self._last_action
+                self._last_action = lim
+                lo = torch.as_tensor(self.jlow, device=self.dev); hi = torch.as_tensor(self.jhigh, device=self.dev)
+                aj = torch.minimum(torch.maximum(self._origin + lim, lo), hi).contiguous()
+                ops = (ops & ~_lib.ACT_JOINTS_REL) | _lib.ACT_JOINTS_ABS
         else:
             key = "xyzrpy" if self.control_mode == ControlMode.CARTESIAN_TRPY else "tquat"
             if key not in action:

@@ -21,7 +21,7 @@ def build(reverse=False):
 
 
 OPS = dict(GRIPPER_RESET=1, SIM_RESET=2, ROBOT_RESET=4, ENV_RESET_FLAGS=8, ACT_JOINTS_REL=16, ACT_JOINTS_ABS=32,
-           ACT_GRIPPER_BIN=64, SET_JOINTS=128, SET_GRIPPER=256, SET_JOINTS_HARD=512, STEP_K=1024, STEP_CONV=2048, OBS=4096)
+           ACT_GRIPPER_BIN=64, SET_JOINTS=128, SET_GRIPPER=256, SET_JOINTS_HARD=512, STEP_K=1024, STEP_CONV=2048, OBS=4096, ACT_GRIPPER_CONT=8192)
 
 
 class Emu:

@@ -244,3 +244,31 @@ def test_checkpoint_resume_is_bit_exact_and_fullphysics_state_round_trips():
     env2.reset()
     env2.sim.set_state(st)
     assert torch.equal(env2.sim.get_state(), st)
+
+
+def test_configured_origin_and_continuous_gripper():
+    """RelativeTo.CONFIGURED_ORIGIN for joint control (base.py:479-488: offsets are relative to the pose at reset and may
+    grow by at most max_mov per step) and the continuous GripperWrapper mode (base.py:710-735)."""
+    from rcs_b200 import sim
+    from rcs_b200.envs.base import ControlMode, RelativeTo
+    from rcs_b200.envs.utils import default_sim_gripper_cfg, default_sim_robot_cfg
+    from rcs_b200.envs.vector import SimVectorEnv
+    N = 8
+    cfg = default_sim_robot_cfg("fr3_empty_world")
+    simulation = sim.Sim(cfg.mjcf_scene_path, sim.SimConfig(async_control=True), num_envs=N)
+    robot = sim.SimRobot(simulation, sim.Pin(cfg.kinematic_model_path, cfg.attachment_site, urdf=False), cfg)
+    gripper = sim.SimGripper(simulation, default_sim_gripper_cfg())
+    mm = float(np.deg2rad(5))
+    env = SimVectorEnv(simulation, robot, gripper, ControlMode.JOINTS, mm, RelativeTo.CONFIGURED_ORIGIN, binary_gripper=False)
+    obs, _ = env.reset()
+    b = simulation.batch
+    origin = obs["joints"].clone()
+    off = torch.tensor([0.2, -0.2, 0.01, 0.0, 0.0, 0.0, 0.03], dtype=torch.float64, device=b.dev).repeat(N, 1)
+    width = torch.full((N,), 0.37, dtype=torch.float64, device=b.dev)
+    for t in range(1, 4):  # the 0.2 rad offsets are approached in steps of max_mov, the small ones are reached at once
+        obs, _, _, _, info = env.step({"joints": off, "gripper": width})
+        exp = origin + torch.minimum(torch.maximum(off, torch.full_like(off, -t * mm)), torch.full_like(off, t * mm))
+        assert torch.allclose(b.ctrl[:, :7], exp, atol=1e-12)
+        assert torch.allclose(b.ctrl[:, 7], width * 255)
+    # continuous mode: the observation is the measured normalised width, not the last command
+    assert torch.equal(obs["gripper"], info["gripper_width"]) and float(obs["gripper"].min()) >= 0
