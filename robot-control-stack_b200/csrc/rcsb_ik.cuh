@@ -7,53 +7,91 @@
 
 enum { IK_SCRATCH_REALS = 8, IK_MAXQ = 9 };
 
-RCSB_DEV void ik_site_fk(const RcsbModel& m, const real* q, int nqm, real* R, real* p, real* J) {
-  // chain root -> site body
-  int chain[RCSB_MAXB], n = 0;
-  for (int b = m.rb_site_body; b >= 0; b = m.b_parent[b]) chain[n++] = b;
-  real pos[3] = {0, 0, 0}, quat[4] = {1, 0, 0, 0}, Rm[9], v[3], qn[4];
-  real anchors[RCSB_MAXB][3], axes[RCSB_MAXB][3];
-  int jtype[RCSB_MAXB], jdof[RCSB_MAXB], nj = 0;
-  for (int ci = n - 1; ci >= 0; ci--) {
-    int b = chain[ci];
-    quat_to_mat(Rm, quat);
-    mulmat3(v, Rm, m.b_pos[b]);
-    pos[0] += v[0]; pos[1] += v[1]; pos[2] += v[2];
-    quat_mul(qn, quat, m.b_quat[b]);
-    quat[0] = qn[0]; quat[1] = qn[1]; quat[2] = qn[2]; quat[3] = qn[3];
-    if (m.b_jtype[b] != RCSB_JNT_FREE) {
-      int qa = m.b_qadr[b];
-      real qj = (qa < nqm ? q[qa] : (real)0) - m.qpos0[qa];
-      quat_to_mat(Rm, quat);
-      mulmat3(axes[nj], Rm, m.b_jaxis[b]);
-      mulmat3(v, Rm, m.b_jpos[b]);
-      anchors[nj][0] = pos[0] + v[0]; anchors[nj][1] = pos[1] + v[1]; anchors[nj][2] = pos[2] + v[2];
+// NQ / NCH > 0 fix the number of IK joints and the length of the body chain at compile time: every loop unrolls and the
+// Jacobian / chain arrays stay in registers instead of thread-local memory (dynamic indexing); 0 = read them at run time.
+template <int NQ, int NCH>
+RCSB_DEV void ik_site_fk(const RcsbModel& m, const real* q, int nqm_rt, real* R, real* p, real* J) {
+  const int nqm = NQ > 0 ? NQ : nqm_rt;
+  constexpr int CH = NCH > 0 ? NCH : RCSB_MAXB;
+  // chain root -> site body, rotation-matrix form (as st_kinematics): local frame [R | t] of every body from its constant
+  // offset (b_rot, b_pos) and its joint motion (Rodrigues), composed with the parent's world frame
+  int chain[CH], n = 0;
+  if (NCH > 0) {
+    int b = m.rb_site_body;
+#pragma unroll
+    for (int i = 0; i < CH; i++) { chain[i] = b; b = m.b_parent[b >= 0 ? b : 0]; }
+    n = CH;
+  } else {
+    for (int b = m.rb_site_body; b >= 0; b = m.b_parent[b]) chain[n++] = b;
+  }
+  real Rw[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pw[3] = {0, 0, 0};
+  real anchors[CH][3], axes[CH][3];
+  int jtype[CH], jdof[CH], nj = 0;
+#pragma unroll
+  for (int cj = 0; cj < CH; cj++) {
+    const int ci = n - 1 - cj;
+    if (NCH == 0 && ci < 0) break;
+    const int b = chain[NCH > 0 ? CH - 1 - cj : ci];
+    const real* Rb = m.b_rot[b];
+    real Rl[9], tl[3];
+    if (m.b_jtype[b] == RCSB_JNT_FREE) {  // not part of an arm chain: treated as the fixed offset
+      for (int i = 0; i < 9; i++) Rl[i] = Rb[i];
+      copy3(tl, m.b_pos[b]);
+    } else {
+      const int qa = m.b_qadr[b];
+      const real qj = (qa < nqm ? q[qa] : (real)0) - m.qpos0[qa];
+      const real* u = m.b_jaxis[b];
+      const real* jp = m.b_jpos[b];
+      if (m.b_jtype[b] == RCSB_JNT_SLIDE) {
+        real v[3];
+        mulmat3(v, Rb, u);
+        for (int i = 0; i < 9; i++) Rl[i] = Rb[i];
+        tl[0] = m.b_pos[b][0] + v[0] * qj; tl[1] = m.b_pos[b][1] + v[1] * qj; tl[2] = m.b_pos[b][2] + v[2] * qj;
+      } else {
+        real sn, co;
+        sincos(qj, &sn, &co);
+        const real oc = 1 - co;
+        real Rj[9] = {co + oc * u[0] * u[0], oc * u[0] * u[1] - sn * u[2], oc * u[0] * u[2] + sn * u[1],
+                      oc * u[1] * u[0] + sn * u[2], co + oc * u[1] * u[1], oc * u[1] * u[2] - sn * u[0],
+                      oc * u[2] * u[0] - sn * u[1], oc * u[2] * u[1] + sn * u[0], co + oc * u[2] * u[2]};
+        for (int r = 0; r < 3; r++)
+          for (int k = 0; k < 3; k++) Rl[3 * r + k] = Rb[3 * r] * Rj[k] + Rb[3 * r + 1] * Rj[3 + k] + Rb[3 * r + 2] * Rj[6 + k];
+        real w[3], v[3];
+        mulmat3(w, Rj, jp);
+        w[0] = jp[0] - w[0]; w[1] = jp[1] - w[1]; w[2] = jp[2] - w[2];
+        mulmat3(v, Rb, w);
+        tl[0] = m.b_pos[b][0] + v[0]; tl[1] = m.b_pos[b][1] + v[1]; tl[2] = m.b_pos[b][2] + v[2];
+      }
+    }
+    real Rn[9], v[3];
+    mulmat3(v, Rw, tl);
+    pw[0] += v[0]; pw[1] += v[1]; pw[2] += v[2];
+    for (int r = 0; r < 3; r++)
+      for (int k = 0; k < 3; k++) Rn[3 * r + k] = Rw[3 * r] * Rl[k] + Rw[3 * r + 1] * Rl[3 + k] + Rw[3 * r + 2] * Rl[6 + k];
+    for (int i = 0; i < 9; i++) Rw[i] = Rn[i];
+    if (m.b_jtype[b] != RCSB_JNT_FREE) {  // a rotation about the joint axis leaves axis and anchor in place
+      mulmat3(axes[nj], Rw, m.b_jaxis[b]);
+      mulmat3(v, Rw, m.b_jpos[b]);
+      anchors[nj][0] = pw[0] + v[0]; anchors[nj][1] = pw[1] + v[1]; anchors[nj][2] = pw[2] + v[2];
       jtype[nj] = m.b_jtype[b];
       jdof[nj] = m.b_dadr[b];
-      if (m.b_jtype[b] == RCSB_JNT_SLIDE) {
-        pos[0] += axes[nj][0] * qj; pos[1] += axes[nj][1] * qj; pos[2] += axes[nj][2] * qj;
-      } else {
-        real s = sin((real)0.5 * qj), ql[4] = {cos((real)0.5 * qj), m.b_jaxis[b][0] * s, m.b_jaxis[b][1] * s, m.b_jaxis[b][2] * s};
-        quat_mul(qn, quat, ql);
-        quat[0] = qn[0]; quat[1] = qn[1]; quat[2] = qn[2]; quat[3] = qn[3];
-        quat_to_mat(Rm, quat);
-        mulmat3(v, Rm, m.b_jpos[b]);
-        pos[0] = anchors[nj][0] - v[0]; pos[1] = anchors[nj][1] - v[1]; pos[2] = anchors[nj][2] - v[2];
-      }
       nj++;
     }
-    quat_normalize(quat);
   }
-  real qs[4];
-  quat_to_mat(Rm, quat);
-  mulmat3(v, Rm, m.rb_site_pos);
-  p[0] = pos[0] + v[0]; p[1] = pos[1] + v[1]; p[2] = pos[2] + v[2];
-  quat_mul(qs, quat, m.rb_site_quat);
-  quat_to_mat(R, qs);
+  {
+    real v[3];
+    mulmat3(v, Rw, m.rb_site_pos);
+    p[0] = pw[0] + v[0]; p[1] = pw[1] + v[1]; p[2] = pw[2] + v[2];
+    const real* Rs = m.rb_site_rot;
+    for (int r = 0; r < 3; r++)
+      for (int k = 0; k < 3; k++) R[3 * r + k] = Rw[3 * r] * Rs[k] + Rw[3 * r + 1] * Rs[3 + k] + Rw[3 * r + 2] * Rs[6 + k];
+  }
   if (J) {
-    for (int i = 0; i < 6 * nqm; i++) J[i] = 0;
-    for (int a = 0; a < nj; a++) {
-      if (jdof[a] >= nqm) continue;
+#pragma unroll
+    for (int i = 0; i < 6 * (NQ > 0 ? NQ : IK_MAXQ); i++) if (i < 6 * nqm) J[i] = 0;
+#pragma unroll
+    for (int a = 0; a < CH; a++) {
+      if (a >= nj || jdof[a] >= nqm) continue;
       real lin[3], ang[3] = {0, 0, 0}, r[3], l[3], w[3];
       if (jtype[a] == RCSB_JNT_HINGE) {
         r[0] = p[0] - anchors[a][0]; r[1] = p[1] - anchors[a][1]; r[2] = p[2] - anchors[a][2];
@@ -64,7 +102,9 @@ RCSB_DEV void ik_site_fk(const RcsbModel& m, const real* q, int nqm, real* R, re
       }
       mulmatT3(l, R, lin);
       mulmatT3(w, R, ang);
-      for (int k = 0; k < 3; k++) { J[k * nqm + jdof[a]] = l[k]; J[(3 + k) * nqm + jdof[a]] = w[k]; }
+      // fixed-shape path: the dispatcher guarantees that the a-th joint of the chain drives dof a (static column index)
+      const int col = NCH > 0 ? a : jdof[a];
+      for (int k = 0; k < 3; k++) { J[k * nqm + col] = l[k]; J[(3 + k) * nqm + col] = w[k]; }
     }
   }
 }
@@ -154,19 +194,22 @@ RCSB_DEV void ik_ldlt6(const real* A, real* b) {
 }
 
 // returns success; q_out[nqm]
-RCSB_DEV int ik_solve(const RcsbModel& m, const real* pose7, const real* q0, int nq0, real* q_out, int* iters_out) {
-  const int nqm = m.rb_ik_nq < IK_MAXQ ? m.rb_ik_nq : IK_MAXQ;
+template <int NQ, int NCH>
+RCSB_DEV int ik_solve_t(const RcsbModel& m, const real* pose7, const real* q0, int nq0, real* q_out, int* iters_out) {
+  constexpr int QM = NQ > 0 ? NQ : IK_MAXQ;
+  const int nqm = NQ > 0 ? NQ : (m.rb_ik_nq < IK_MAXQ ? m.rb_ik_nq : IK_MAXQ);
   real inv_tcp[7], goal[7], Rd[9];
   pose_inverse(m.rb_tcp_offset, inv_tcp);
   pose_mul(pose7, inv_tcp, goal);
   Quat qg = {goal[3], goal[4], goal[5], goal[6]};
   q_to_mat(qg, Rd);
-  real q[IK_MAXQ], J[6 * IK_MAXQ], Jn[6 * IK_MAXQ];
-  for (int i = 0; i < nqm; i++) q[i] = i < nq0 ? q0[i] : (real)0;
+  real q[QM], J[6 * QM], Jn[6 * QM];
+#pragma unroll
+  for (int i = 0; i < QM; i++) if (i < nqm) q[i] = i < nq0 ? q0[i] : (real)0;
   int success = 0, it;
   for (it = 0;; it++) {
     real R[9], p[3], Ri[9], pi[3], err[6];
-    ik_site_fk(m, q, nqm, R, p, J);
+    ik_site_fk<NQ, NCH>(m, q, nqm, R, p, J);
     real dp[3] = {goal[0] - p[0], goal[1] - p[1], goal[2] - p[2]};
     for (int r = 0; r < 3; r++)
       for (int cc = 0; cc < 3; cc++) Ri[3 * r + cc] = R[r] * Rd[cc] + R[3 + r] * Rd[3 + cc] + R[6 + r] * Rd[6 + cc];
@@ -181,29 +224,54 @@ RCSB_DEV int ik_solve(const RcsbModel& m, const real* pose7, const real* q0, int
     mulmat3(pinv, Rinv, pi);
     pinv[0] = -pinv[0]; pinv[1] = -pinv[1]; pinv[2] = -pinv[2];
     ik_jlog6(Rinv, pinv, Jl);
+#pragma unroll
     for (int r = 0; r < 6; r++)
-      for (int cc = 0; cc < nqm; cc++) {
+#pragma unroll
+      for (int cc = 0; cc < QM; cc++) {
+        if (cc >= nqm) continue;
         real s = 0;
+#pragma unroll
         for (int k = 0; k < 6; k++) s += Jl[6 * r + k] * J[k * nqm + cc];
         Jn[r * nqm + cc] = -s;
       }
+#pragma unroll
     for (int r = 0; r < 6; r++)
+#pragma unroll
       for (int cc = 0; cc < 6; cc++) {
         real s = 0;
-        for (int k = 0; k < nqm; k++) s += Jn[r * nqm + k] * Jn[cc * nqm + k];
+#pragma unroll
+        for (int k = 0; k < QM; k++) if (k < nqm) s += Jn[r * nqm + k] * Jn[cc * nqm + k];
         JJt[6 * r + cc] = s;
       }
     for (int k = 0; k < 6; k++) { JJt[7 * k] += (real)1e-6; y[k] = err[k]; }
     ik_ldlt6(JJt, y);
-    for (int cc = 0; cc < nqm; cc++) {
+#pragma unroll
+    for (int cc = 0; cc < QM; cc++) {
+      if (cc >= nqm) continue;
       real s = 0;
+#pragma unroll
       for (int k = 0; k < 6; k++) s += Jn[k * nqm + cc] * y[k];
       q[cc] += -s * (real)0.1;
     }
   }
   if (iters_out) *iters_out = it;
-  if (success) for (int k = 0; k < nqm; k++) q_out[k] = q[k];
+  if (success) {
+#pragma unroll
+    for (int k = 0; k < QM; k++) if (k < nqm) q_out[k] = q[k];
+  }
   return success;
+}
+// dispatch on the shapes of the shipped arms (FR3 + fingers: 9 joints in the IK model, chain of 7 bodies; xArm7: 7 / 7)
+RCSB_DEV int ik_solve(const RcsbModel& m, const real* pose7, const real* q0, int nq0, real* q_out, int* iters_out) {
+  const int nqm = m.rb_ik_nq < IK_MAXQ ? m.rb_ik_nq : IK_MAXQ;
+  int n = 0, canonical = 1;  // canonical: every chain body has a hinge / slide joint and the i-th one drives dof i
+  for (int b = m.rb_site_body; b >= 0; b = m.b_parent[b]) n++;
+  for (int b = m.rb_site_body, i = n - 1; b >= 0; b = m.b_parent[b], i--)
+    if (m.b_jtype[b] == RCSB_JNT_FREE || m.b_dadr[b] != i) canonical = 0;
+  if (!canonical) return ik_solve_t<0, 0>(m, pose7, q0, nq0, q_out, iters_out);
+  if (nqm == 9 && n == 7) return ik_solve_t<9, 7>(m, pose7, q0, nq0, q_out, iters_out);
+  if (nqm == 7 && n == 7) return ik_solve_t<7, 7>(m, pose7, q0, nq0, q_out, iters_out);
+  return ik_solve_t<0, 0>(m, pose7, q0, nq0, q_out, iters_out);
 }
 
 // one environment per thread; apply != 0 restates SimRobot::set_cartesian_position (SimRobot.cpp:145-155)
