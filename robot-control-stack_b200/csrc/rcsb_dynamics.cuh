@@ -29,7 +29,7 @@ RCSB_DEV_NOINLINE void chol_factor(const Ctx& c, real* A, real* dinv, int n) {
   }
 }
 // x <- (L L^T)^{-1} x ; y is scratch of length n
-RCSB_DEV_NOINLINE void chol_solve(const Ctx& c, const real* L, const real* dinv, int n, real* x, real* y) {
+RCSB_DEV_NOINLINE void chol_solve(const Ctx& c, const real* L, const real* dinv, int n, real* x, real* y, int lo = 0, int hi = 1 << 30) {
   for (int k = 0; k < n; k++) {
     real xk = x[k] * dinv[k];
     for (int i = k + 1; i < n; i++) x[i] -= L[i * n + k] * xk;
@@ -70,18 +70,22 @@ RCSB_DEV void chol_rows_factor(int li, real (&a)[N]) {
 }
 // x <- (L L^T)^{-1} x with row li of L in a[] (a[li] = 1 / L[li][li]) and column li of L in col[]
 template <int N>
-RCSB_DEV real chol_rows_solve(int li, const real (&a)[N], const real (&col)[N], real xi) {
+RCSB_DEV real chol_rows_solve(int li, const real (&a)[N], const real (&col)[N], real xi, int lo = 0, int hi = N) {
+  // [lo, hi): a diagonal block of L outside of which the right-hand side is zero (dofs of one kinematic tree when L
+  // factors M): the other steps would only move zeros around, so they are skipped (uniform branch)
   real di = (real)0;
 #pragma unroll
   for (int k = 0; k < N; k++) if (k == li) di = a[k];
 #pragma unroll
   for (int j = 0; j < N; j++) {  // forward: L z = x
+    if (j < lo || j >= hi) continue;
     real zj = half_bcast(xi * di, j);
     if (li == j) xi = zj;
     else if (li > j) xi -= a[j] * zj;
   }
 #pragma unroll
   for (int j = N - 1; j >= 0; j--) {  // backward: L^T w = z
+    if (j < lo || j >= hi) continue;
     real wj = half_bcast(xi * di, j);
     if (li == j) xi = wj;
     else if (li < j) xi -= col[j] * wj;
@@ -114,9 +118,9 @@ RCSB_DEV void chol_n(const Ctx& c, real* A0, real* dinv0, real* x, real* A1, rea
   if (!half && li < N) x[li] = xi;
 }
 template <int N>
-RCSB_DEV void chol_solve_n(const Ctx& c, const real* L, const real* dinv, real* x) {
+RCSB_DEV void chol_solve_n(const Ctx& c, const real* L, const real* dinv, real* x, int lo, int hi) {
   const int li = c.lane & 15, half = c.lane >> 4;
-  const bool on = !half && li < N;
+  const bool on = !half && li < N && li >= lo && li < hi;
   real a[N], col[N];
 #pragma unroll
   for (int k = 0; k < N; k++) {
@@ -127,7 +131,7 @@ RCSB_DEV void chol_solve_n(const Ctx& c, const real* L, const real* dinv, real* 
 #pragma unroll
   for (int k = 0; k < N; k++) if (k == li) a[k] = di;
   real xi = on ? x[li] : (real)0;
-  xi = chol_rows_solve<N>(li, a, col, xi);
+  xi = chol_rows_solve<N>(li, a, col, xi, lo, hi);
   if (on) x[li] = xi;
 }
 RCSB_DEV_NOINLINE void chol_factor(const Ctx& c, real* A, real* dinv, int n) {
@@ -156,17 +160,18 @@ RCSB_DEV_NOINLINE void chol_factor(const Ctx& c, real* A, real* dinv, int n) {
   }
   RCSB_SYNC();
 }
-// x <- (L L^T)^{-1} x ; y is unused scratch (kept for the common signature)
-RCSB_DEV_NOINLINE void chol_solve(const Ctx& c, const real* L, const real* dinv, int n, real* x, real* y) {
+// x <- (L L^T)^{-1} x ; y is unused scratch (kept for the common signature). [lo, hi): see chol_rows_solve.
+RCSB_DEV_NOINLINE void chol_solve(const Ctx& c, const real* L, const real* dinv, int n, real* x, real* y, int lo = 0, int hi = 1 << 30) {
   const int lane = c.lane;
+  if (hi > n) hi = n;
   __builtin_assume(__isShared(L));
   __builtin_assume(__isShared(dinv));
   __builtin_assume(__isShared(x));
   RCSB_SYNC();
   switch (n) {
-    case 7: chol_solve_n<7>(c, L, dinv, x); break;
-    case 9: chol_solve_n<9>(c, L, dinv, x); break;
-    case 15: chol_solve_n<15>(c, L, dinv, x); break;
+    case 7: chol_solve_n<7>(c, L, dinv, x, lo, hi); break;
+    case 9: chol_solve_n<9>(c, L, dinv, x, lo, hi); break;
+    case 15: chol_solve_n<15>(c, L, dinv, x, lo, hi); break;
     default: {
       real xi = lane < n ? x[lane] : (real)0;
       real di = lane < n ? dinv[lane] : (real)0;

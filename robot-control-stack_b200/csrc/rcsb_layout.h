@@ -230,6 +230,22 @@ static inline int rcsb_model_finalize_layout(RcsbModel* m) {
       m->d_pre[j] = (m->b_jtype[b] == RCSB_JNT_FREE) ? (a >= 3 ? da + 2 : -1) : up;
     }
   }
+  {
+    int lo[RCSB_MAXROOT], hi[RCSB_MAXROOT], cnt[RCSB_MAXROOT], ok = 1;
+    for (int r = 0; r < RCSB_MAXROOT; r++) { lo[r] = m->nv; hi[r] = 0; cnt[r] = 0; }
+    for (int j = 0; j < m->nv; j++) {
+      int r = m->b_root[m->d_body[j]];
+      if (j < lo[r]) lo[r] = j;
+      if (j + 1 > hi[r]) hi[r] = j + 1;
+      cnt[r]++;
+    }
+    for (int r = 0; r < m->nroot; r++) if (cnt[r] != hi[r] - lo[r]) ok = 0;
+    for (int j = 0; j < m->nv; j++) {
+      int r = m->b_root[m->d_body[j]];
+      m->d_tree_lo[j] = ok ? lo[r] : 0;
+      m->d_tree_hi[j] = ok ? hi[r] : m->nv;
+    }
+  }
   for (int i = 0, t = 0; i < RCSB_MAXV; i++)
     for (int j = 0; j <= i; j++, t++) { m->tri_i[t] = (uint8_t)i; m->tri_j[t] = (uint8_t)j; }
   return 0;

@@ -458,6 +458,27 @@ RCSB_DEV void compute_qfc(const Ctx& c, int nefc) {
   RCSB_SYNC();
 }
 
+// smallest range of dofs, made of whole kinematic trees, that holds every non-zero of a constraint Jacobian row: M^-1
+// applied to the row stays inside it (M is block diagonal by tree), so the triangular solves can skip the rest
+RCSB_DEV void row_dof_range(const Ctx& c, const real* row, int* lo_out, int* hi_out) {
+  const RcsbModel& m = CMODEL(c);
+  int lo = MD(nv), hi = 0;
+  PFOR(k, MD(nv)) {
+    if (row[k] != 0) {
+      lo = m.d_tree_lo[k] < lo ? m.d_tree_lo[k] : lo;
+      hi = m.d_tree_hi[k] > hi ? m.d_tree_hi[k] : hi;
+    }
+  }
+#ifndef RCSB_HOST_EMU
+  for (int o = 16; o > 0; o >>= 1) {
+    int l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+    lo = l2 < lo ? l2 : lo;
+    hi = h2 > hi ? h2 : hi;
+  }
+#endif
+  if (hi <= lo) { lo = 0; hi = MD(nv); }
+  *lo_out = lo; *hi_out = hi;
+}
 // ------------------------------------------------------------------ noslip post-pass
 RCSB_DEV_NOINLINE void solve_noslip(const Ctx& c, int nefc, int ncon) {
   const RcsbModel& m = CMODEL(c);
@@ -478,7 +499,9 @@ RCSB_DEV_NOINLINE void solve_noslip(const Ctx& c, int nefc, int ncon) {
   real* Ablk = MinvJ + (nf + 2 * MD(maxcon)) * nv;  // 1 value per dof-friction row, 4 per contact
   for (int i = 0; i < nf; i++) {
     PFOR(k, nv) { MinvJ[i * nv + k] = WR(J)[(ne + i) * nv + k]; }
-    chol_solve(c, WR(L), WR(L) + nv * nv, nv, MinvJ + i * nv, WR(tmp));
+    int lo, hi;
+    row_dof_range(c, WR(J) + (ne + i) * nv, &lo, &hi);
+    chol_solve(c, WR(L), WR(L) + nv * nv, nv, MinvJ + i * nv, WR(tmp), lo, hi);
   }
   for (int ci = 0; ci < ncon; ci++) {
     int a = WI(con)[RCSB_CI_INTS * ci + RCSB_CI_EFC];
@@ -486,7 +509,9 @@ RCSB_DEV_NOINLINE void solve_noslip(const Ctx& c, int nefc, int ncon) {
     for (int j = 0; j < 2; j++) {
       real* x = MinvJ + (nf + 2 * ci + j) * nv;
       PFOR(k, nv) { x[k] = WR(J)[(a + 1 + j) * nv + k]; }
-      chol_solve(c, WR(L), WR(L) + nv * nv, nv, x, WR(tmp));
+      int lo, hi;
+      row_dof_range(c, WR(J) + (a + 1 + j) * nv, &lo, &hi);
+      chol_solve(c, WR(L), WR(L) + nv * nv, nv, x, WR(tmp), lo, hi);
     }
   }
   RCSB_SYNC();

@@ -119,6 +119,9 @@ struct RcsbModel {
   // this dof adds to (-1: tree root), the dof whose accumulated velocity enters this dof's cdof_dot (-1: none), and
   // the last dof of every body (its accumulated velocity / acceleration is the body's)
   int d_parent[RCSB_MAXV], d_pre[RCSB_MAXV], b_lastdof[RCSB_MAXB];
+  // dof range [lo, hi) of the kinematic tree every dof belongs to (M and its Cholesky factor are block diagonal by tree);
+  // the whole range [0, nv) when the trees' dofs are not contiguous
+  int d_tree_lo[RCSB_MAXV], d_tree_hi[RCSB_MAXV];
   uint32_t d_ancmask[RCSB_MAXV];  // ancestor dofs incl. self (sparsity of M)
   real d_armature[RCSB_MAXV], d_damping[RCSB_MAXV], d_frictionloss[RCSB_MAXV], d_invweight0[RCSB_MAXV];
   real d_range[RCSB_MAXV][2], d_margin[RCSB_MAXV], d_solref[RCSB_MAXV][2], d_solimp[RCSB_MAXV][5],
