@@ -56,6 +56,10 @@ int rcsb_model_dims(const rcsb_model* m, int* nsr, int* nsd, int* nsi, int* obs_
 /* column offsets inside the real row: qpos, qvel, ctrl, qacc_warmstart, rcs tail */
 int rcsb_model_offsets(const rcsb_model* m, int* o_qpos, int* o_qvel, int* o_ctrl, int* o_warm, int* o_tail);
 
+/* shared-memory footprint that decides the warps per SM: bytes of one warp's workspace in the reduced layout (0 when the
+ * model has none) and in the full layout, and the bytes the staged model takes per CTA (host only, no device needed) */
+int rcsb_model_workspace_bytes(const rcsb_model* m, int* reduced_bytes, int* full_bytes, int* smem_header_bytes);
+
 /* ---- batch: replaces N x (mjData + Sim + SimRobot + SimGripper) ----
  * sr/sd/si are caller-owned DEVICE arrays [n_envs][nsr] reals, [n_envs][nsd] doubles, [n_envs][nsi] ints
  * (allocated by the host language, e.g. torch tensors). stream is a cudaStream_t (may be 0). */

@@ -293,6 +293,13 @@ int rcsb_debug_stage_cycles(unsigned long long* out16) {
   return fail(RCSB_ERR_ARG, "library built without RCSB_STAGE_TIMING");
 #endif
 }
+int rcsb_model_workspace_bytes(const rcsb_model* m, int* reduced_bytes, int* full_bytes, int* smem_header_bytes) {
+  if (!m->finalized) return fail(RCSB_ERR_MODEL, "rcsb_model_finalize not called");
+  if (reduced_bytes) *reduced_bytes = m->has_reduced ? (int)rcsb_ws_bytes(&m->hr) : 0;
+  if (full_bytes) *full_bytes = (int)rcsb_ws_bytes(&m->h);
+  if (smem_header_bytes) *smem_header_bytes = (int)RCSB_SMEM_HEADER;
+  return RCSB_OK;
+}
 const char* rcsb_kernel_variant(rcsb_batch* b, int phase) { return phase == 0 ? b->var.name : b->var_full.name; }
 int rcsb_kernel_occupancy(rcsb_batch* b, int* warps_per_cta, int* smem_bytes, int* grid) {
   if (warps_per_cta) *warps_per_cta = b->warps;

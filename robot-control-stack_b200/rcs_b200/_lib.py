@@ -46,6 +46,7 @@ def lib():
     L.rcsb_model_upload.argtypes = [vp, C.c_int]
     L.rcsb_model_dims.argtypes = [vp, ip, ip, ip, ip, ip]
     L.rcsb_model_offsets.argtypes = [vp, ip, ip, ip, ip, ip]
+    L.rcsb_model_workspace_bytes.argtypes = [vp, ip, ip, ip]
     L.rcsb_batch_new.restype = vp
     L.rcsb_batch_new.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.rcsb_batch_free.argtypes = [vp]
@@ -76,7 +77,7 @@ def check(rc: int):
 
 EXPORTS = ["rcsb_last_error", "rcsb_version", "rcsb_real_bytes", "rcsb_model_new", "rcsb_model_free",
            "rcsb_model_set_int", "rcsb_model_set_real", "rcsb_model_set_mesh_vertices", "rcsb_model_finalize",
-           "rcsb_model_upload", "rcsb_model_dims", "rcsb_model_offsets", "rcsb_batch_new", "rcsb_batch_free",
+           "rcsb_model_upload", "rcsb_model_dims", "rcsb_model_offsets", "rcsb_model_workspace_bytes", "rcsb_batch_new", "rcsb_batch_free",
            "rcsb_batch_init_state", "rcsb_batch_run", "rcsb_batch_run_host", "rcsb_sim_step",
            "rcsb_sim_step_until_convergence", "rcsb_sim_reset", "rcsb_robot_set_joint_position",
            "rcsb_robot_set_joints_hard", "rcsb_robot_reset", "rcsb_gripper_set_normalized_width",

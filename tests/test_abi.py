@@ -47,6 +47,13 @@ def test_model_builds_on_host_and_upload_fails_without_gpu():
     d = [C.c_int(0) for _ in range(5)]
     assert L.rcsb_model_dims(m, *[C.byref(x) for x in d]) == 0
     assert d[0].value * 8 % 16 == 0 and d[3].value == 22
+    # occupancy guard: 4096 environments are ONE resident wave on a B200 only with 28 warps per SM (148 x 28 = 4144), so
+    # the reduced workspace layout plus the staged model must keep fitting 28 times into the 227 KB of shared memory
+    w = [C.c_int(0) for _ in range(3)]
+    assert L.rcsb_model_workspace_bytes(m, *[C.byref(x) for x in w]) == 0
+    reduced, full, header = [x.value for x in w]
+    assert 0 < reduced < full
+    assert (232448 - header) // reduced >= 28, (reduced, header)
     if not torch.cuda.is_available():
         assert L.rcsb_model_upload(m, 0) == -4  # RCSB_ERR_CUDA: no CPU execution path
         assert b"no CPU" in L.rcsb_last_error()
