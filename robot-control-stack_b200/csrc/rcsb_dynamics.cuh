@@ -552,8 +552,10 @@ RCSB_DEV void support(const Ctx& c, int g, const real* gp, const real* gR, const
     if (n > RCSB_MINVAL) { v[0] = dl[0] / n * m.g_size[g][0]; v[1] = dl[1] / n * m.g_size[g][0]; }
     v[2] = dl[2] > 0 ? m.g_size[g][1] : (dl[2] < 0 ? -m.g_size[g][1] : (real)0);
   }
-  mulmat3(out, gR, v);
-  out[0] += gp[0]; out[1] += gp[1]; out[2] += gp[2];
+  // out may be shared by the warp (MPR portal): every lane stores the same finished value, never a read-modify-write
+  real o[3];
+  mulmat3(o, gR, v);
+  out[0] = o[0] + gp[0]; out[1] = o[1] + gp[1]; out[2] = o[2] + gp[2];
 }
 
 struct Sup { real v[3], v1[3], v2[3]; };
@@ -667,8 +669,12 @@ RCSB_DEV_NOINLINE int mpr_penetration(const Ctx& c, const PairFrames& pf, real* 
   Sup* s = (Sup*)WR(sup);
   Sup& v4 = s[4];
   real dir[3], va[3], vb[3];
-  for (int k = 0; k < 3; k++) { s[0].v1[k] = pf.p1[k]; s[0].v2[k] = pf.p2[k]; s[0].v[k] = pf.p1[k] - pf.p2[k]; }
-  if (r_abs(s[0].v[0]) < (real)1e-12 && r_abs(s[0].v[1]) < (real)1e-12 && r_abs(s[0].v[2]) < (real)1e-12) s[0].v[0] += (real)1e-5;
+  {
+    real v0[3] = {pf.p1[0] - pf.p2[0], pf.p1[1] - pf.p2[1], pf.p1[2] - pf.p2[2]};
+    if (r_abs(v0[0]) < (real)1e-12 && r_abs(v0[1]) < (real)1e-12 && r_abs(v0[2]) < (real)1e-12) v0[0] += (real)1e-5;
+    RCSB_SYNC();
+    for (int k = 0; k < 3; k++) { s[0].v1[k] = pf.p1[k]; s[0].v2[k] = pf.p2[k]; s[0].v[k] = v0[k]; }  // plain stores only
+  }
   dir[0] = -s[0].v[0]; dir[1] = -s[0].v[1]; dir[2] = -s[0].v[2];
   normalize3(dir);
   mink_support(c, pf, dir, s[1]);
