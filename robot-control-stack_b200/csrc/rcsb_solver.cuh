@@ -632,13 +632,18 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
     // verify on the first pass. Only if that fails does the general Newton path below run.
     int* state = EFCI(RCSB_EI_STATE);
     const int* etype = EFCI(RCSB_EI_TYPE);
-    PFOR(r, nefc) {
+    PFOR(r, nefc) {  // zones of the previous step's solution (qacc_warmstart) are the first guess
       int st = RCSB_QUADRATIC;
-      if (etype[r] == RCSB_FRICTION_DOF) {
+      const int type = etype[r];
+      if (type == RCSB_FRICTION_DOF || type == RCSB_LIMIT || type == RCSB_CONTACT_PYR) {
         real x = -EFC(RCSB_E_AREF)[r];
         for (int k = 0; k < nv; k++) x += WR(J)[r * nv + k] * WR(warm)[k];
-        real f = EFC(RCSB_E_FLOSS)[r], R = EFC(RCSB_E_R)[r];
-        st = x <= -R * f ? RCSB_LINEARNEG : (x >= R * f ? RCSB_LINEARPOS : RCSB_QUADRATIC);
+        if (type == RCSB_FRICTION_DOF) {
+          real f = EFC(RCSB_E_FLOSS)[r], R = EFC(RCSB_E_R)[r];
+          st = x <= -R * f ? RCSB_LINEARNEG : (x >= R * f ? RCSB_LINEARPOS : RCSB_QUADRATIC);
+        } else {
+          st = x < 0 ? RCSB_QUADRATIC : RCSB_SATISFIED;
+        }
       }
       state[r] = st;
     }
