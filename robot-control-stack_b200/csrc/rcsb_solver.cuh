@@ -1028,10 +1028,11 @@ RCSB_DEV int physics_step(const Ctx& c, double* time) {
     reset_data(c, time);
   }
   // Lockstep (fixed-substep launches): the step is far more straight-line code than the instruction cache holds, so
-  // the warps of a CTA are re-aligned by a CTA barrier before every stage (mode 1, the default, measured best since
-  // the collision stage's duration varies per environment) or once per step (mode 2); warps that run the same code
-  // together share each fetched line instead of streaming the whole program once per warp (no barriers: -45 %
-  // throughput at 28 warps per SM).
+  // the warps of a CTA are re-aligned by CTA barriers (c.lockstep: bit i = before stage i, bit 9 = end of the step);
+  // warps that run the same code together share each fetched line instead of streaming the whole program once per
+  // warp. Measured best: two barriers per step, before make_constraint (after the stages whose duration varies per
+  // environment: collision groups that are due) and at the end (mask 0x220); a barrier before every stage costs 7 %,
+  // none at all 45 %.
   // ---- mj_step1
   RCSB_STAGE(0, st_kinematics(c));
   RCSB_STAGE(1, st_com(c));
