@@ -3,10 +3,11 @@
 // B200-native re-design of the arithmetic the reference reaches through mj_step1
 // (/root/reference/src/sim/sim.cpp:110): forward kinematics, tree COM frames, composite rigid
 // body mass matrix + Cholesky, velocity-stage bias forces (RNE with zero acceleration), passive
-// damping and gravity compensation, broad + narrow phase collision. MuJoCo's "com frame" spatial
-// vectors make every tree recursion except forward kinematics a sum over ancestor / descendant
-// sets, so those stages are flat parallel-fors over (body | dof | matrix entry) work items with
-// precompiled bit masks instead of serial tree walks.
+// damping and gravity compensation, broad + narrow phase collision with exact temporal coherence.
+// Stages are either parallel-fors over independent work items (body | dof | matrix entry | geom pair)
+// or short root-to-leaf / leaf-to-root passes along the dof chain with one lane per vector component
+// (MuJoCo's "com frame" spatial vectors keep those passes to one fused multiply-add per lane and link).
+// This file is a variant body: rcsb_variant.cuh includes it once per kernel shape (MD() / LAY macros).
 
 // ------------------------------------------------------------------ dense Cholesky / triangular solves
 // A (n x n, row-major, shared memory) -> strictly-lower part holds L, dinv[j] = 1 / L[j][j]; A's diagonal is left

@@ -1,12 +1,16 @@
 // CUDA kernels + C ABI (include/rcsb.h) of the batched rigid-body backend. sm_100a only.
 //
 // Execution model: persistent CTAs (one per SM), W warps each, one environment per warp at a time.
-// The model constants are staged once per CTA into shared memory with a TMA bulk copy
+// The hot part of the model is staged once per CTA into shared memory with a TMA bulk copy
 // (cp.async.bulk + mbarrier); each warp owns a private shared-memory workspace that holds the
 // environment's state and every intermediate of the physics step for all substeps of a launch, so
-// HBM is touched once per launch per environment (row in, row out). Warps pull environment indices
-// from a global atomic counter, which load-balances step_until_convergence where environments need
-// different numbers of substeps.
+// HBM is touched once per launch per environment (row in, row out). Fixed-substep launches map
+// environments to warps statically and keep the warps of a CTA aligned with barriers (instruction
+// cache); step_until_convergence launches pull environment indices from a global atomic counter,
+// which load-balances environments that need different numbers of substeps. Every launch runs in the
+// reduced workspace layout first and hands the environments that outgrow it to a second launch in
+// the full layout (rcsb_types.h: fast_maxcon). The kernel itself exists once per shape variant
+// (rcsb_variant.cuh); this file holds the generic variant, the IK kernels and the host side.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
