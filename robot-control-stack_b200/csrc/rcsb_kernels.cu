@@ -128,7 +128,7 @@ struct rcsb_batch {
   int* d_counter = nullptr;   // [0] env cursor phase 0, [1] overflow cursor phase 1, [2] overflow count
   int* d_overflow = nullptr;  // [n] overflow list
   int bar_groups = 1;
-  int warps = 0, grid = 0, lockstep = 0x220;  // barrier mask of fixed-substep launches (rcsb_warp.cuh)
+  int warps = 0, grid = 0, lockstep = 0x010;  // barrier mask of fixed-substep launches (rcsb_warp.cuh)
   size_t smem = 0, ws_bytes = 0;
   RcsbVariant var, var_full;          // kernel variants of the two phases
   int warps_full = 0, grid_full = 0;  // phase 1 (full layout) launch shape when a reduced layout exists

@@ -1030,9 +1030,9 @@ RCSB_DEV int physics_step(const Ctx& c, double* time) {
   // Lockstep (fixed-substep launches): the step is far more straight-line code than the instruction cache holds, so
   // the warps of a CTA are re-aligned by CTA barriers (c.lockstep: bit i = before stage i, bit 9 = end of the step);
   // warps that run the same code together share each fetched line instead of streaming the whole program once per
-  // warp. Measured best: two barriers per step, before make_constraint (after the stages whose duration varies per
-  // environment: collision groups that are due) and at the end (mask 0x220); a barrier before every stage costs 7 %,
-  // none at all 45 %.
+  // warp. Measured best: ONE barrier per step, right after the collision stage -- the one whose duration varies per
+  // environment (collision groups that are due) -- i.e. before the velocity stage (mask 0x010); a barrier before every
+  // stage costs 10 %, one before the collision stage 24 %, none at all 45 %.
   // ---- mj_step1
   RCSB_STAGE(0, st_kinematics(c));
   RCSB_STAGE(1, st_com(c));

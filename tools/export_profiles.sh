@@ -5,7 +5,6 @@ out=profiles
 mkdir -p $out
 cp gpurun_out/bench.json $out/${tag}_bench.json
 cp gpurun_out/launches.csv $out/${tag}_launches.csv
-[ -s gpurun_out/stage_timing.txt ] && cp gpurun_out/stage_timing.txt $out/${tag}_stage_timing.txt
 ncu -i gpurun_out/run_full.ncu-rep --page details > $out/${tag}_ncu_details.txt 2>/dev/null
 ncu -i gpurun_out/run_full.ncu-rep --page raw --csv > /tmp/_raw.csv 2>/dev/null
 ncu -i gpurun_out/run_full.ncu-rep --page source --csv --print-source cuda,sass > /tmp/_src.csv 2>/dev/null
