@@ -32,6 +32,7 @@ struct Ctx {
   int lane;
   int lockstep;         // fixed-substep launch: CTA barriers between stages keep the warps on the same code
   int bar_id, bar_threads;  // named barrier of this warp's group and the number of threads that meet at it
+  int conv_vote;        // step_until_convergence with a static env -> warp map: CTA-wide vote per step (run_env_program)
 };
 #define CMODEL(c) (*(const RcsbModel*)rcsb_smem)
 #define CMODEL_G(c) (*(c).gm)

@@ -258,10 +258,20 @@ RCSB_DEV void run_env_program(const Ctx& c, const RcsbLaunch& L, int env) {
     if (resuming) steps = RI(RCSB_I_CONV_STEPS);
     else PFOR(i, RCSB_NCB) { RI(RCSB_I_CBRET + i) = 0; }
     RCSB_SYNC();
-    while (!converged && (L.max_convergence_steps == -1 || steps < L.max_convergence_steps)) {
-      if (physics_step(c, &CCLK(c)[RCSB_D_TIME])) { overflow = 1; break; }
-      steps++;
-      converged = invoke_condition_callbacks(c, CCLK(c)[RCSB_D_TIME]);
+    for (;;) {
+      const int alive = !overflow && !converged && (L.max_convergence_steps == -1 || steps < L.max_convergence_steps);
+#ifndef RCSB_HOST_EMU
+      // lockstep launches: one CTA-wide vote per step keeps the warps of the CTA on the same code (instruction cache)
+      // until the last of their environments has converged; warps that are done keep voting
+      if (c.conv_vote) { if (!__syncthreads_or(alive)) break; }
+      else
+#endif
+      if (!alive) break;
+      if (alive) {
+        if (physics_step(c, &CCLK(c)[RCSB_D_TIME])) { overflow = 1; continue; }
+        steps++;
+        converged = invoke_condition_callbacks(c, CCLK(c)[RCSB_D_TIME]);
+      }
     }
     RCSB_SYNC();
     if (c.lane == 0) { RI(RCSB_I_CONVERGED) = converged; RI(RCSB_I_CONV_STEPS) = steps; }

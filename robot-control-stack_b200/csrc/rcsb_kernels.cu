@@ -6,8 +6,8 @@
 // environment's state and every intermediate of the physics step for all substeps of a launch, so
 // HBM is touched once per launch per environment (row in, row out). Fixed-substep launches map
 // environments to warps statically and keep the warps of a CTA aligned with barriers (instruction
-// cache); step_until_convergence launches pull environment indices from a global atomic counter,
-// which load-balances environments that need different numbers of substeps. Every launch runs in the
+// cache); step_until_convergence launches use the same map with a CTA-wide vote per step (or, with
+// RCSB_CONV_VOTE=0, pull environment indices from a global atomic counter). Every launch runs in the
 // reduced workspace layout first and hands the environments that outgrow it to a second launch in
 // the full layout (rcsb_types.h: fast_maxcon). The kernel itself exists once per shape variant
 // (rcsb_variant.cuh); this file holds the generic variant, the IK kernels and the host side.
@@ -127,7 +127,7 @@ struct rcsb_batch {
   cudaStream_t stream;
   int* d_counter = nullptr;   // [0] env cursor phase 0, [1] overflow cursor phase 1, [2] overflow count
   int* d_overflow = nullptr;  // [n] overflow list
-  int bar_groups = 1;
+  int bar_groups = 1, conv_vote = 1;
   int warps = 0, grid = 0, lockstep = 0x010;  // barrier mask of fixed-substep launches (rcsb_warp.cuh)
   size_t smem = 0, ws_bytes = 0;
   RcsbVariant var, var_full;          // kernel variants of the two phases
@@ -245,6 +245,7 @@ rcsb_batch* rcsb_batch_new(rcsb_model* m, int n_envs, void* sr, void* sd, void* 
     int o = atoi(ov);
     if (o >= 1 && o < cap) cap = o;
   }
+  if (const char* ov = getenv("RCSB_CONV_VOTE")) b->conv_vote = atoi(ov) != 0;  // 0 = dynamic scheduling for step_until_convergence
   if (const char* ov = getenv("RCSB_BAR_GROUPS")) { int g = atoi(ov); if (g >= 1 && g <= 15) b->bar_groups = g; }
   if (const char* ov = getenv("RCSB_LOCKSTEP")) {  // tuning knob: 0 none, 1 every stage, 2 once per step, 0x.. explicit mask
     long v = strtol(ov, nullptr, 0);
@@ -323,7 +324,7 @@ int rcsb_batch_run(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps
   if ((ops & RCSB_OP_ACT_JOINTS_REL) && (!jlow || !jhigh)) return fail(RCSB_ERR_ARG, "joint limits required");
   RcsbLaunch L;
   memset(&L, 0, sizeof(L));
-  L.N = b->n; L.ops = ops; L.lockstep = b->lockstep; L.bar_groups = b->bar_groups; L.k = k; L.max_convergence_steps = max_convergence_steps;
+  L.N = b->n; L.ops = ops; L.lockstep = b->lockstep; L.bar_groups = b->bar_groups; L.conv_vote = b->conv_vote; L.k = k; L.max_convergence_steps = max_convergence_steps;
   L.act_joints = (const real*)act_joints_dev; L.act_gripper = (const real*)act_gripper_dev; L.mask = mask_dev;
   L.max_mov = (real)max_mov;
   for (int i = 0; i < b->m->h.rb_njoints && i < RCSB_MAXJ; i++) {

@@ -199,6 +199,7 @@ struct RcsbLaunch {
   int N, env_offset;
   unsigned ops;
   int k, max_convergence_steps;
+  int conv_vote;   // step_until_convergence: 1 = static env -> warp map with a CTA-wide vote per step, 0 = dynamic scheduling
   int bar_groups;  // fixed-substep launches: number of separately aligned warp groups per CTA (named barriers, <= 15)
   int lockstep;  // fixed-substep launches: mask of CTA barriers (bit i: before stage i of the step, bit 9: at its end)
   int phase;     // 0: every environment, reduced or full layout; 1: full layout, only the environments in overflow_list

@@ -37,6 +37,7 @@ __device__ __forceinline__ Ctx make_ctx(const RcsbModel* sm, const RcsbModel* gm
   c.lane = threadIdx.x & 31;
   c.lockstep = 0;
   c.bar_id = 0; c.bar_threads = blockDim.x;
+  c.conv_vote = 0;
   return c;
 }
 // ------------------------------------------------------------------ the per-launch program kernel
@@ -75,6 +76,26 @@ RCSB_KERNEL(const RcsbModel* __restrict__ gm, const real* __restrict__ verts, re
         __syncwarp();
       } else {
         for (int i = 0; i < nbar; i++) RCSB_GROUP_BARRIER();
+      }
+    }
+    return;
+  }
+  if ((L.ops & RCSB_OP_STEP_CONV) && L.phase == 0 && L.conv_vote) {
+    // step_until_convergence with the static map: the warps of a CTA step together until the last of their environments
+    // has converged (a vote per step); warps without an environment in the last round only vote
+    c.conv_vote = 1;
+    const int W = blockDim.x >> 5, per_round = gridDim.x * W;
+    const int rounds = (L.N + per_round - 1) / per_round;
+    for (int r = 0; r < rounds; r++) {
+      int env = r * per_round + (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+      bool valid = env < L.N && !(L.mask && !L.mask[env]);
+      if (valid) {
+        load_env(c, sr + (size_t)env * LAY.nsr, sd + (size_t)env * RCSB_D_TAIL, si + (size_t)env * RCSB_I_TAIL);
+        run_env_program(c, L, env);
+        store_env(c, sr + (size_t)env * LAY.nsr, sd + (size_t)env * RCSB_D_TAIL, si + (size_t)env * RCSB_I_TAIL);
+        __syncwarp();
+      } else {
+        while (__syncthreads_or(0)) {}
       }
     }
     return;
