@@ -292,3 +292,32 @@ def test_results_do_not_depend_on_batch_size_or_mask(setup):
     for x0, x1 in zip(before, (b.sr, b.sd, b.si)):
         assert np.array_equal(x0.cpu().numpy()[keep], x1.cpu().numpy()[keep])
     assert not np.array_equal(before[0].cpu().numpy()[::3], b.sr.cpu().numpy()[::3])
+
+
+def test_kernels_match_committed_step_vectors(setup):
+    """tests/golden/step_vectors.npz (see tests/golden/make_fixtures.py) through the C ABI, all three scenes; the contact
+    counts along the committed floor-collision trajectory are exact."""
+    import os
+    _, _, _lib, batch = setup
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "step_vectors.npz"))
+    for ci in range(len([k for k in G.files if k.endswith("_scene")])):
+        scene, k = str(G[f"c{ci}_scene"]), int(G[f"c{ci}_k"])
+        M = H.scene(scene)
+        rc, gc = (H.xarm_robot_ns(), None) if scene.startswith("xarm7") else (H.robot_ns(), H.gripper_ns())
+        dm = batch.DeviceModel(M, rc, gc)
+        q = G[f"c{ci}_qpos"]
+        b = batch.Batch(dm, len(q))
+        b.qpos.copy_(torch.as_tensor(q)); b.qvel.copy_(torch.as_tensor(G[f"c{ci}_qvel"])); b.ctrl.copy_(torch.as_tensor(G[f"c{ci}_ctrl"]))
+        b.run(_lib.STEP_K, k=k)
+        tol_q, tol_v = (1e-12, 1e-10) if k == 1 else (1e-8, 1e-6)
+        assert np.abs(b.qpos.cpu().numpy() - G[f"c{ci}_qpos_out"]).max() < tol_q, scene
+        assert np.abs(b.qvel.cpu().numpy() - G[f"c{ci}_qvel_out"]).max() < tol_v, scene
+        assert np.array_equal(b.si[:, 14].cpu().numpy(), G[f"c{ci}_ncon_out"]), scene
+    dm = setup[1]
+    b = batch.Batch(dm, 1)
+    b.run(_lib.GRIPPER_RESET | _lib.SIM_RESET | _lib.ROBOT_RESET | _lib.ENV_RESET_FLAGS | _lib.STEP_K, k=1)
+    b.run(_lib.SET_JOINTS, act_joints=torch.as_tensor(np.array([[0, 1.78, 0, -1.45, 0, 0, 0.0]]), device=b.dev))
+    for it in range(len(G["floor_ncon"])):
+        b.run(_lib.STEP_K, k=5)
+        assert int(b.si[0, 14]) == int(G["floor_ncon"][it]), it
+        assert np.abs(b.qpos[0].cpu().numpy() - G["floor_qpos"][it]).max() < 1e-6, it
