@@ -263,7 +263,7 @@ RCSB_DEV void run_env_program(const Ctx& c, const RcsbLaunch& L, int env) {
 #ifndef RCSB_HOST_EMU
       // lockstep launches: one CTA-wide vote per step keeps the warps of the CTA on the same code (instruction cache)
       // until the last of their environments has converged; warps that are done keep voting
-      if (c.conv_vote) { if (!__syncthreads_or(alive)) break; }
+      if (c.conv_vote) { if (!rcsb_cta_vote(alive)) break; }
       else
 #endif
       if (!alive) break;

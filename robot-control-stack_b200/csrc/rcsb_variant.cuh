@@ -95,7 +95,7 @@ RCSB_KERNEL(const RcsbModel* __restrict__ gm, const real* __restrict__ verts, re
         store_env(c, sr + (size_t)env * LAY.nsr, sd + (size_t)env * RCSB_D_TAIL, si + (size_t)env * RCSB_I_TAIL);
         __syncwarp();
       } else {
-        while (__syncthreads_or(0)) {}
+        while (rcsb_cta_vote(0)) {}
       }
     }
     return;

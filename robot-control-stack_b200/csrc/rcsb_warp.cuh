@@ -43,7 +43,13 @@ RCSB_DEV int warp_bcast_i(int x, int src) { return x; }
 // c.lockstep is a bit mask: bit i (0..8) = CTA barrier before stage i of the physics step, bit 9 = barrier at its end
 // The CTA's warps are split into bar_groups groups that align separately (named barriers): a straggler only holds
 // back its own group, the other groups fill the issue slots meanwhile.
-#define RCSB_GROUP_BARRIER() asm volatile("bar.sync %0, %1;" ::"r"(c.bar_id), "r"(c.bar_threads) : "memory")
+// One instruction address for every arrival (out-of-line): warps that run an environment and warps that only keep the
+// barrier count meet at the same barrier instruction, which is also what compute-sanitizer's synccheck expects.
+static __device__ __noinline__ void rcsb_group_barrier(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+static __device__ __noinline__ int rcsb_cta_vote(int pred) { return __syncthreads_or(pred); }
+#define RCSB_GROUP_BARRIER() rcsb_group_barrier(c.bar_id, c.bar_threads)
 #define RCSB_STAGE_SYNC(i) do { if ((c.lockstep >> (i)) & 1) RCSB_GROUP_BARRIER(); } while (0)
 #define RCSB_STEP_SYNC() RCSB_STAGE_SYNC(9)
 #define RCSB_LOCKSTEP_ALL 0x3ff
