@@ -605,6 +605,90 @@ RCSB_DEV_NOINLINE void solve_noslip(const Ctx& c, int nefc, int ncon) {
   RCSB_SYNC();
 }
 
+// General path: MuJoCo's Newton solver (warm start choice, Hessian with cone blocks, exact line search) and the noslip
+// post-pass. Out of line: the direct solve in st_constraint_solve handles almost every step, so this code stays out of
+// the hot instruction stream.
+RCSB_DEV void build_integrator_matrix(const Ctx& c, real* dst);
+RCSB_DEV_NOINLINE void newton_solve(const Ctx& c, int nefc, int ncon) {
+  const RcsbModel& m = CMODEL(c);
+  const int nv = MD(nv);
+  compute_qacc_smooth(c);
+  // warm start: keep qacc_warmstart only if its cost beats qacc_smooth's
+  real gauss;
+  real cost_smooth = total_cost(c, WR(qacc_smooth), nefc, ncon, 0, nullptr);
+  real cost = total_cost(c, WR(warm), nefc, ncon, 1, &gauss);
+  const int use_warm = cost < cost_smooth;
+  const real* start = use_warm ? WR(warm) : WR(qacc_smooth);
+  PFOR(k, nv) { WR(qacc)[k] = start[k]; }
+  RCSB_SYNC();
+  real scale = (real)1 / (m.meaninertia * (nv > 1 ? nv : 1));
+  if (!use_warm) cost = total_cost(c, WR(qacc), nefc, ncon, 1, &gauss);
+  int iter = 0;
+  const int* state = EFCI(RCSB_EI_STATE);
+  while (iter < m.iterations) {
+    compute_qfc(c, nefc);
+    // Hessian H = M + J^T diag(D_active) J + cone blocks
+    PFOR(t, nv * (nv + 1) / 2) {
+      const int a = m.tri_i[t], b = m.tri_j[t];
+      real h = WR(M)[a * nv + b];
+      for (int r = 0; r < nefc; r++)
+        if (state[r] == RCSB_QUADRATIC) h += EFC(RCSB_E_D)[r] * WR(J)[r * nv + a] * WR(J)[r * nv + b];
+      for (int ci = 0; ci < ncon; ci++) {
+        int i = WI(con)[RCSB_CI_INTS * ci + RCSB_CI_EFC];
+        if (i < 0 || state[i] != RCSB_CONE) continue;
+        int dim = WI(con)[RCSB_CI_INTS * ci + RCSB_CI_DIM];
+        const real* Hc = WR(conehess) + 9 * ci;
+        for (int r = 0; r < dim; r++)
+          for (int s = 0; s < dim; s++) h += Hc[3 * r + s] * WR(J)[(i + r) * nv + a] * WR(J)[(i + s) * nv + b];
+      }
+      WR(H)[a * nv + b] = h;
+      WR(H)[b * nv + a] = h;
+    }
+    PFOR(k, nv) { WR(search)[k] = WR(grad)[k]; }
+    chol_factor_solve(c, WR(H), WR(H) + nv * nv, nv, WR(search), WR(tmp), nullptr, nullptr);
+    PFOR(k, nv) { WR(search)[k] = -WR(search)[k]; }
+    RCSB_SYNC();
+    real qG1 = 0, qG2 = 0, sn = 0;
+    PFOR(i, nv) {
+      real s = 0;
+      for (int j = 0; j < nv; j++) s += WR(M)[i * nv + j] * WR(search)[j];
+      WR(Mv)[i] = s;
+      qG1 += WR(search)[i] * (WR(Ma)[i] - WR(smooth)[i]);
+      qG2 += (real)0.5 * WR(search)[i] * s;
+      sn += WR(search)[i] * WR(search)[i];
+    }
+    PFOR(r, nefc) {
+      real s = 0;
+      for (int k = 0; k < nv; k++) s += WR(J)[r * nv + k] * WR(search)[k];
+      EFC(RCSB_E_JV)[r] = s;
+    }
+    RCSB_SYNC();
+    qG1 = warp_sum(qG1); qG2 = warp_sum(qG2); sn = r_sqrt(warp_sum(sn));
+    if (sn < RCSB_MINVAL) break;
+    real gtol = m.tolerance * m.ls_tolerance * sn / scale;
+    real alpha = line_search(c, nefc, ncon, gauss, qG1, qG2, gtol, m.ls_iterations);
+    if (alpha == 0) break;
+    PFOR(k, nv) { WR(qacc)[k] += alpha * WR(search)[k]; }
+    RCSB_SYNC();
+    real oldcost = cost;
+    cost = total_cost(c, WR(qacc), nefc, ncon, 1, &gauss);
+    iter++;
+    real gn = 0;
+    PFOR(k, nv) {
+      real s = 0;
+      for (int r = 0; r < nefc; r++) s += WR(J)[r * nv + k] * EFC(RCSB_E_FORCE)[r];
+      real g = WR(Ma)[k] - WR(smooth)[k] - s;
+      gn += g * g;
+    }
+    gn = warp_sum(gn);
+    real improvement = scale * (oldcost - cost), gradient = scale * r_sqrt(gn);
+    if (improvement < m.tolerance || gradient < m.tolerance) break;
+  }
+  if (c.lane == 0) WI(misc)[MI_SOLVER_ITER] = iter;
+  compute_qfc(c, nefc);
+  if (MD(noslip_iterations) > 0) solve_noslip(c, nefc, ncon);
+}
+
 // ------------------------------------------------------------------ constrained acceleration (Newton)
 RCSB_DEV void build_integrator_matrix(const Ctx& c, real* dst);
 RCSB_DEV void st_constraint_solve(const Ctx& c) {
@@ -739,81 +823,7 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
       return;
     }
   }
-  compute_qacc_smooth(c);
-  // warm start: keep qacc_warmstart only if its cost beats qacc_smooth's
-  real gauss;
-  real cost_smooth = total_cost(c, WR(qacc_smooth), nefc, ncon, 0, nullptr);
-  real cost = total_cost(c, WR(warm), nefc, ncon, 1, &gauss);
-  const int use_warm = cost < cost_smooth;
-  const real* start = use_warm ? WR(warm) : WR(qacc_smooth);
-  PFOR(k, nv) { WR(qacc)[k] = start[k]; }
-  RCSB_SYNC();
-  real scale = (real)1 / (m.meaninertia * (nv > 1 ? nv : 1));
-  if (!use_warm) cost = total_cost(c, WR(qacc), nefc, ncon, 1, &gauss);
-  int iter = 0;
-  const int* state = EFCI(RCSB_EI_STATE);
-  while (iter < m.iterations) {
-    compute_qfc(c, nefc);
-    // Hessian H = M + J^T diag(D_active) J + cone blocks
-    PFOR(t, nv * (nv + 1) / 2) {
-      const int a = m.tri_i[t], b = m.tri_j[t];
-      real h = WR(M)[a * nv + b];
-      for (int r = 0; r < nefc; r++)
-        if (state[r] == RCSB_QUADRATIC) h += EFC(RCSB_E_D)[r] * WR(J)[r * nv + a] * WR(J)[r * nv + b];
-      for (int ci = 0; ci < ncon; ci++) {
-        int i = WI(con)[RCSB_CI_INTS * ci + RCSB_CI_EFC];
-        if (i < 0 || state[i] != RCSB_CONE) continue;
-        int dim = WI(con)[RCSB_CI_INTS * ci + RCSB_CI_DIM];
-        const real* Hc = WR(conehess) + 9 * ci;
-        for (int r = 0; r < dim; r++)
-          for (int s = 0; s < dim; s++) h += Hc[3 * r + s] * WR(J)[(i + r) * nv + a] * WR(J)[(i + s) * nv + b];
-      }
-      WR(H)[a * nv + b] = h;
-      WR(H)[b * nv + a] = h;
-    }
-    PFOR(k, nv) { WR(search)[k] = WR(grad)[k]; }
-    chol_factor_solve(c, WR(H), WR(H) + nv * nv, nv, WR(search), WR(tmp), nullptr, nullptr);
-    PFOR(k, nv) { WR(search)[k] = -WR(search)[k]; }
-    RCSB_SYNC();
-    real qG1 = 0, qG2 = 0, sn = 0;
-    PFOR(i, nv) {
-      real s = 0;
-      for (int j = 0; j < nv; j++) s += WR(M)[i * nv + j] * WR(search)[j];
-      WR(Mv)[i] = s;
-      qG1 += WR(search)[i] * (WR(Ma)[i] - WR(smooth)[i]);
-      qG2 += (real)0.5 * WR(search)[i] * s;
-      sn += WR(search)[i] * WR(search)[i];
-    }
-    PFOR(r, nefc) {
-      real s = 0;
-      for (int k = 0; k < nv; k++) s += WR(J)[r * nv + k] * WR(search)[k];
-      EFC(RCSB_E_JV)[r] = s;
-    }
-    RCSB_SYNC();
-    qG1 = warp_sum(qG1); qG2 = warp_sum(qG2); sn = r_sqrt(warp_sum(sn));
-    if (sn < RCSB_MINVAL) break;
-    real gtol = m.tolerance * m.ls_tolerance * sn / scale;
-    real alpha = line_search(c, nefc, ncon, gauss, qG1, qG2, gtol, m.ls_iterations);
-    if (alpha == 0) break;
-    PFOR(k, nv) { WR(qacc)[k] += alpha * WR(search)[k]; }
-    RCSB_SYNC();
-    real oldcost = cost;
-    cost = total_cost(c, WR(qacc), nefc, ncon, 1, &gauss);
-    iter++;
-    real gn = 0;
-    PFOR(k, nv) {
-      real s = 0;
-      for (int r = 0; r < nefc; r++) s += WR(J)[r * nv + k] * EFC(RCSB_E_FORCE)[r];
-      real g = WR(Ma)[k] - WR(smooth)[k] - s;
-      gn += g * g;
-    }
-    gn = warp_sum(gn);
-    real improvement = scale * (oldcost - cost), gradient = scale * r_sqrt(gn);
-    if (improvement < m.tolerance || gradient < m.tolerance) break;
-  }
-  if (c.lane == 0) WI(misc)[MI_SOLVER_ITER] = iter;
-  compute_qfc(c, nefc);
-  if (MD(noslip_iterations) > 0) solve_noslip(c, nefc, ncon);
+  newton_solve(c, nefc, ncon);
 }
 
 // ------------------------------------------------------------------ implicitfast / Euler integration + mj_advance
