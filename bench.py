@@ -54,11 +54,39 @@ def measured_peak():
 
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML (a sample every ~2 ms) when pynvml imports,
+    else nvidia-smi (a sample every ~100 ms)."""
+
     def __init__(self, index):
         self.rows, self.stop_flag, self.index = [], False, index
         self.t = threading.Thread(target=self._run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nvml = None
+
+    def _run_nvml(self):
+        n = self.nvml
+        bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append([str(sm), str(mx)] + ["Active" if r & bits[k] else "Not Active" for k in
+                                                       ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def _run(self):
+        if self.nvml is not None:
+            return self._run_nvml()
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag:
@@ -82,7 +110,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def cpu_reference(nthreads, target_seconds, episode_len=EPISODE):
