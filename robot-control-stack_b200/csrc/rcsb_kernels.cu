@@ -429,12 +429,18 @@ int rcsb_env_get_obs(rcsb_batch* b, void* obs_dev, int* info_dev) {
   return rcsb_batch_run(b, RCSB_OP_OBS, 0, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, obs_dev, info_dev);
 }
 
+// One environment per thread and a long serial solve per thread (250 registers, ~5 k instructions per CLIK iteration).
+// Small batches run in blocks of one full warp spread over the SMs. Smaller blocks (more, mostly idle, warps per SM)
+// were measured slower (4096 envs: 1.19 ms with 4-thread blocks against 0.55 ms): several unaligned warps per SM thrash
+// the instruction cache on the unrolled loop body, the same effect that makes the physics kernel keep its CTA barrier.
+static int ik_block_threads(int n) {
+  return n >= 128 * 148 * 4 ? 128 : (n >= 64 * 148 * 4 ? 64 : 32);
+}
 static int launch_ik(rcsb_batch* b, const void* pose_dev, const void* q0_dev, void* q_out_dev, int* success_dev, int* iters_dev,
                      int apply) {
   if (!b || !pose_dev) return fail(RCSB_ERR_ARG, "null argument");
   CUDA_OK(cudaSetDevice(b->m->device));
-  // one environment per thread and a serial solve per thread: spread the environments over as many SMs as possible
-  int threads = b->n >= 128 * 148 * 4 ? 128 : (b->n >= 64 * 148 * 4 ? 64 : 32), grid = (b->n + threads - 1) / threads;
+  int threads = ik_block_threads(b->n), grid = (b->n + threads - 1) / threads;
   rcsb_k_ik<<<grid, threads, RCSB_SMEM_HEADER, b->stream>>>(b->m->d_model, (const real*)pose_dev, (const real*)q0_dev,
                                                            (real*)q_out_dev, success_dev, iters_dev, b->n, apply, b->sr, b->si);
   g_launches++;
@@ -444,7 +450,7 @@ static int launch_ik(rcsb_batch* b, const void* pose_dev, const void* q0_dev, vo
 int rcsb_env_cartesian_action(rcsb_batch* b, const void* act_dev, int kind, int relative, double max_trans, double max_rot) {
   if (!b || !act_dev || (kind != 0 && kind != 1)) return fail(RCSB_ERR_ARG, "bad argument");
   CUDA_OK(cudaSetDevice(b->m->device));
-  int threads = b->n >= 128 * 148 * 4 ? 128 : (b->n >= 64 * 148 * 4 ? 64 : 32), grid = (b->n + threads - 1) / threads;
+  int threads = ik_block_threads(b->n), grid = (b->n + threads - 1) / threads;
   rcsb_k_cart_action<<<grid, threads, RCSB_SMEM_HEADER, b->stream>>>(b->m->d_model, (const real*)act_dev, kind, relative, (real)max_trans,
                                                                      (real)max_rot, b->n, b->sr, b->si);
   g_launches++;
