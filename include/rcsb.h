@@ -67,6 +67,13 @@ rcsb_batch* rcsb_batch_new(rcsb_model* m, int n_envs, void* sr, void* sd, void* 
 void rcsb_batch_free(rcsb_batch* b);
 int rcsb_batch_init_state(rcsb_batch* b); /* SimRobotState/SimGripperState defaults + mj_resetData on every env */
 
+/* Contact list export, replaces the reads of mjData.contact[i].geom[0/1] / ncon (SimRobot.cpp:172-182,
+ * SimGripper.cpp:108-130): after every following launch that steps, each environment's contact list of the last
+ * mj_step1 is written to ncon_dev [n_envs], geom_dev [n_envs][cap][2] (geom ids of the compiled scene in mjModel
+ * numbering, contact order, -1 beyond ncon) and, when not NULL, real_dev [n_envs][cap][7] reals (dist, pos[3],
+ * normal[3]). ncon_dev == NULL switches the export off. Device pointers owned by the caller. */
+int rcsb_batch_set_contact_export(rcsb_batch* b, int* ncon_dev, int* geom_dev, void* real_dev, int cap);
+
 /* One launch: for every env (mask_dev == NULL) or every env with mask_dev[env] != 0, run the ops in
  * `ops`. act_joints_dev [n_envs][njoints] reals, act_gripper_dev [n_envs] reals, obs_dev
  * [n_envs][obs_dim] reals, info_dev [n_envs][info_dim] ints: device pointers, NULL where unused.

@@ -176,6 +176,18 @@ void rcso_make_constraint(const rcso_model* m, rcso_data* d) {
     for (int j = 1; j < c->dim - 1; j++)
       d->efc_R[a + 1 + j] = d->efc_R[a + 1] * c->friction[0] * c->friction[0] / (c->friction[j] * c->friction[j]);
   }
+  /* pyramidal cones [3P] (mj_makeImpedance): every edge of the pyramid gets Rpy = 2 mu^2 R_first, with the
+   * regularised friction mu = friction[0] / sqrt(impratio) */
+  for (int ci = 0; ci < d->ncon; ci++) {
+    rcso_contact* c = &d->contact[ci];
+    int a = c->efc_address;
+    if (a < 0 || d->efc_type[a] != CNSTR_CONTACT_PYRAMIDAL || c->dim < 3) continue;
+    double ir = m->impratio < MINVAL ? MINVAL : m->impratio;
+    c->mu = c->friction[0] / sqrt(ir);
+    double Rpy = 2 * c->mu * c->mu * d->efc_R[a];
+    if (Rpy < MINVAL) Rpy = MINVAL;
+    for (int j = 0; j < 2 * (c->dim - 1); j++) d->efc_R[a + j] = Rpy;
+  }
   for (int i = 0; i < d->nefc; i++) {
     d->efc_D[i] = 1 / d->efc_R[i];
     double vel = 0;
@@ -568,6 +580,7 @@ void rcso_fwd_constraint(const rcso_model* m, rcso_data* d) {
   int nv = m->nv, nefc = d->nefc;
   if (nefc == 0) {
     memcpy(d->qacc, d->qacc_smooth, sizeof(double) * (size_t)nv);
+    memcpy(d->qacc_warmstart, d->qacc_smooth, sizeof(double) * (size_t)nv);
     zero(d->qfrc_constraint, nv);
     d->solver_iter = 0;
     return;
@@ -581,5 +594,7 @@ void rcso_fwd_constraint(const rcso_model* m, rcso_data* d) {
   free(tmp);
   free(st);
   solve_newton(m, d);
+  /* [3P] mj_fwdConstraint saves the warm start from the main solver's result, BEFORE the noslip post-pass */
+  memcpy(d->qacc_warmstart, d->qacc, sizeof(double) * (size_t)nv);
   if (m->noslip_iterations > 0) solve_noslip(m, d);
 }

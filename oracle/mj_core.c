@@ -214,6 +214,15 @@ void rcso_data_free(rcso_data* d) {
 }
 double* rcso_data_real(rcso_data* d, const char* field, int* n) {
   if (!strcmp(field, "time")) { if (n) *n = 1; return &d->time; }
+  if (!strcmp(field, "contact_real")) {
+    for (int i = 0; i < d->ncon; i++) {
+      double* o = d->contact_flat + 7 * i;
+      o[0] = d->contact[i].dist;
+      for (int k = 0; k < 3; k++) { o[1 + k] = d->contact[i].pos[k]; o[4 + k] = d->contact[i].frame[k]; }
+    }
+    if (n) *n = 7 * d->ncon;
+    return d->contact_flat;
+  }
   static const struct { const char* name; size_t off; } efc[] = {
       {"efc_pos", offsetof(struct rcso_data, efc_pos)}, {"efc_D", offsetof(struct rcso_data, efc_D)},
       {"efc_R", offsetof(struct rcso_data, efc_R)}, {"efc_aref", offsetof(struct rcso_data, efc_aref)},
@@ -670,8 +679,7 @@ void rcso_integrate(const rcso_model* m, rcso_data* d) {
       d->qpos[qa] += h * d->qvel[da];
     }
   }
-  d->time += h;
-  memcpy(d->qacc_warmstart, d->qacc, sizeof(double) * (size_t)nv);
+  d->time += h; /* qacc_warmstart was saved by rcso_fwd_constraint, before noslip */
   free(A);
   free(acc);
 }

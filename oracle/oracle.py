@@ -363,6 +363,15 @@ def ik_forward(model: Model, site: int, nq_model: int, q0, tcp_offset7=(0, 0, 0,
     return out
 
 
+def log3(R):
+    """pinocchio::log3 as the IK uses it (test hook)"""
+    R = np.ascontiguousarray(R, dtype=np.float64).ravel()
+    w = np.zeros(3)
+    lib().rcso_log3.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib().rcso_log3(_dp(R), _dp(w))
+    return w
+
+
 def _p7(x):
     return np.ascontiguousarray(x, dtype=np.float64)
 
@@ -437,7 +446,7 @@ def bench_env_steps(model: Model, rc: RobotCfg, gc: GripperCfg, actions: np.ndar
     low = np.ascontiguousarray(joint_low, dtype=np.float64)
     high = np.ascontiguousarray(joint_high, dtype=np.float64)
     ps = C.c_longlong(0)
-    obs = np.zeros((nenv, nsteps, 21)) if want_obs else None
+    obs = np.zeros((nenv, nsteps, 28)) if want_obs else None  # rcs_glue.c ENV_OBS_STRIDE
     sec = lib().rcso_bench_env_steps(model.ptr, C.byref(rc), C.byref(gc), nenv, nthreads, nsteps, episode_len,
                                      int(async_control), _dp(actions), float(max_mov), _dp(low), _dp(high),
                                      C.byref(ps), _dp(obs) if want_obs else None)

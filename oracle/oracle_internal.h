@@ -70,6 +70,7 @@ struct rcso_data {
   int ncon, nefc, ne, nf, nl;
   rcso_contact contact[MAXCON];
   int contact_geom[2 * MAXCON]; /* flat copy for the python view */
+  double contact_flat[7 * MAXCON]; /* dist, pos[3], normal[3] per contact, for the python view */
   double* efc_J; /* MAXEFC x nv */
   double efc_pos[MAXEFC], efc_margin[MAXEFC], efc_frictionloss[MAXEFC], efc_D[MAXEFC], efc_R[MAXEFC],
       efc_aref[MAXEFC], efc_vel[MAXEFC], efc_force[MAXEFC], efc_b[MAXEFC], efc_KBIP[4 * MAXEFC],

@@ -243,18 +243,22 @@ static void log3(const double* R, double* w, double* theta) { /* pinocchio::log3
   if (ct > 1) ct = 1; if (ct < -1) ct = -1;
   double t = acos(ct);
   *theta = t;
-  if (t < 1e-8) { w[0] = 0.5 * (R[7] - R[5]); w[1] = 0.5 * (R[2] - R[6]); w[2] = 0.5 * (R[3] - R[1]); return; }
-  if (t > M_PI - 1e-4) { /* near pi: extract the axis from the symmetric part */
-    double s[3];
-    for (int k = 0; k < 3; k++) { double v = 0.5 * (R[4 * k] - ct) / (1 - ct) * 2; s[k] = sqrt(v > 0 ? v * 0.5 : 0); }
-    /* signs from the antisymmetric part */
+  /* Pinocchio 3.7 log3: near pi the antisymmetric part vanishes, so the axis comes from the diagonal,
+   * w_k^2 = theta^2 (R_kk - cos theta) / (1 - cos theta), signed by the antisymmetric part (threshold pi - 1e-2);
+   * below eps^(1/4) the factor theta / sin(theta) is taken as 1 */
+  if (t >= M_PI - 1e-2) {
+    double beta = t * t / (1 - ct);
     double a[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};
-    for (int k = 0; k < 3; k++) w[k] = t * (a[k] < 0 ? -s[k] : s[k]);
+    for (int k = 0; k < 3; k++) {
+      double v = (R[4 * k] - ct) * beta;
+      w[k] = (a[k] > 0 ? 1.0 : -1.0) * (v > 0 ? sqrt(v) : 0.0);
+    }
     return;
   }
-  double f = t / (2 * sin(t));
+  double f = 0.5 * (t > 1.220703125e-4 ? t / sin(t) : 1.0);
   w[0] = f * (R[7] - R[5]); w[1] = f * (R[2] - R[6]); w[2] = f * (R[3] - R[1]);
 }
+void rcso_log3(const double* R9_rowmajor, double* w3) { double t; log3(R9_rowmajor, w3, &t); } /* test hook */
 static void log6(const double* R, const double* p, double* out /* [v; w] */) { /* pinocchio::log6 [3P] */
   double w[3], t;
   log3(R, w, &t);
@@ -633,13 +637,25 @@ typedef struct {
   long long physics_steps; double* obs_out;
 } worker_t;
 
-static void env_obs(rcso_sim* s, double gripper_obs, double* obs /* 21 */) { /* base.py:246-253,710-719 */
+#define ENV_OBS_STRIDE 28
+/* obs[0:21] = tquat, joints, xyzrpy, gripper; obs[21] = info["gripper_width"]; obs[22:28] = info flags collision,
+ * ik_success, is_sim_converged, is_grasped, robot collision, gripper collision (envs/sim.py:60-66,125-131) */
+static void env_obs(rcso_sim* s, double gripper_obs, double* obs /* ENV_OBS_STRIDE */) { /* base.py:246-253,710-719 */
   double pose[7];
   rcso_robot_get_cartesian_position(s, pose);
   memcpy(obs, pose, 7 * sizeof(double));
   rcso_robot_get_joint_position(s, obs + 7);
   rcso_pose_xyzrpy(pose, obs + 14);
   obs[20] = gripper_obs;
+  double gw = s->gc.enabled ? rcso_gripper_get_normalized_width(s) : 0;
+  int rc = s->collision, gcol = s->gc.enabled ? s->g_collision : 0;
+  obs[21] = gw;
+  obs[22] = rc || gcol;
+  obs[23] = s->ik_success;
+  obs[24] = rcso_sim_is_converged(s);
+  obs[25] = gw > 0.01 && gw < 0.99;
+  obs[26] = rc;
+  obs[27] = gcol;
 }
 static void env_reset(rcso_sim* s, long long* psteps) { /* base.py:703-708, envs/sim.py:68-76 */
   if (s->gc.enabled) rcso_gripper_reset(s);
@@ -684,7 +700,7 @@ static void* worker(void* arg) {
         rcso_sim_step_until_convergence(s);
         w->physics_steps += s->convergence_steps;
       }
-      if (w->obs_out) env_obs(s, grip_obs, w->obs_out + ((size_t)e * w->nsteps + t) * 21);
+      if (w->obs_out) env_obs(s, grip_obs, w->obs_out + ((size_t)e * w->nsteps + t) * ENV_OBS_STRIDE);
     }
     rcso_sim_free(s);
   }

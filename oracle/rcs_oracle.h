@@ -102,6 +102,9 @@ int rcso_ik_inverse(const rcso_model* m, int site, int nq_model, const double* p
 void rcso_ik_forward(const rcso_model* m, int site, int nq_model, const double* q0, int nq0,
                      const double* tcp_offset7, double* pose7);
 
+/* pinocchio::log3 as used by the IK (test hook: closed-form check near theta = pi) */
+void rcso_log3(const double* R9_rowmajor, double* w3);
+
 /* ---- Pose math, /root/reference/src/rcs/Pose.cpp ---- (pose7 = xyz + quat xyzw) */
 void rcso_pose_mul(const double* a, const double* b, double* out);
 void rcso_pose_inverse(const double* a, double* out);

@@ -288,6 +288,26 @@ RCSB_DEV void run_env_program(const Ctx& c, const RcsbLaunch& L, int env) {
   }
   RCSB_SYNC();
   if (overflow) return;  // the full-capacity launch finishes the steps and packs the observation
+  if (L.con_n && (ops & (RCSB_OP_STEP_K | RCSB_OP_STEP_CONV))) {  // contact list of the last step1, as the callbacks saw it
+    const int ncon = WI(misc)[MI_NCON];
+    if (c.lane == 0) L.con_n[env] = ncon;
+    PFOR(i, L.con_cap) {
+      int* g = L.con_geom + ((size_t)env * L.con_cap + i) * 2;
+      real* o = L.con_real ? L.con_real + ((size_t)env * L.con_cap + i) * RCSB_CON_EXPORT_REALS : nullptr;
+      if (i < ncon) {
+        const int* ci = WI(con) + RCSB_CI_INTS * i;
+        const real* cr = WR(con) + RCSB_C_REALS * i;
+        g[0] = m.g_origid[ci[RCSB_CI_G0]]; g[1] = m.g_origid[ci[RCSB_CI_G1]];
+        if (o) {
+          o[0] = cr[RCSB_C_DIST];
+          for (int k = 0; k < 3; k++) { o[1 + k] = cr[RCSB_C_POS + k]; o[4 + k] = cr[RCSB_C_FRAME + k]; }
+        }
+      } else {
+        g[0] = g[1] = -1;
+        if (o) for (int k = 0; k < RCSB_CON_EXPORT_REALS; k++) o[k] = 0;
+      }
+    }
+  }
   if ((ops & RCSB_OP_OBS) && c.lane == 0) {
     real pose[7];
     robot_cartesian_position(c, pose);

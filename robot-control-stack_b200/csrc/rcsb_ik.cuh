@@ -113,17 +113,18 @@ RCSB_DEV void ik_log3(const real* R, real* w, real* theta) {
   ct = ct > 1 ? (real)1 : (ct < -1 ? (real)-1 : ct);
   real t = acos(ct);
   *theta = t;
-  if (t < (real)1e-8) { w[0] = (real)0.5 * (R[7] - R[5]); w[1] = (real)0.5 * (R[2] - R[6]); w[2] = (real)0.5 * (R[3] - R[1]); return; }
-  if (t > (real)3.14159265358979323846 - (real)1e-4) {
-    real a[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};
+  // Pinocchio 3.7 log3: near pi the axis comes from the diagonal, w_k^2 = theta^2 (R_kk - cos) / (1 - cos), signed by the
+  // antisymmetric part (threshold pi - 1e-2); below eps^(1/4) the factor theta / sin(theta) is taken as 1
+  if (t >= (real)3.14159265358979323846 - (real)1e-2) {
+    const real beta = t * t / (1 - ct);
+    const real a[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};
     for (int k = 0; k < 3; k++) {
-      real vv = (real)0.5 * (R[4 * k] - ct) / (1 - ct) * 2;
-      real s = r_sqrt(vv > 0 ? vv * (real)0.5 : (real)0);
-      w[k] = t * (a[k] < 0 ? -s : s);
+      real v = (R[4 * k] - ct) * beta;
+      w[k] = (a[k] > 0 ? (real)1 : (real)-1) * (v > 0 ? r_sqrt(v) : (real)0);
     }
     return;
   }
-  real f = t / (2 * sin(t));
+  const real f = (real)0.5 * (t > (real)1.220703125e-4 ? t / sin(t) : (real)1);
   w[0] = f * (R[7] - R[5]); w[1] = f * (R[2] - R[6]); w[2] = f * (R[3] - R[1]);
 }
 RCSB_DEV void ik_log6(const real* R, const real* p, real* out) {

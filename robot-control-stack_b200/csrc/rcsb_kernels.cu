@@ -109,6 +109,20 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
     if (e_ != cudaSuccess) return fail(RCSB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
+// every entry point that touches the device selects the model's device and puts the caller's current device back
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    err = prev == device ? cudaSuccess : cudaSetDevice(device);
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define DEVICE_OK(device)   \
+  DeviceGuard guard_(device); \
+  if (guard_.err != cudaSuccess) return fail(RCSB_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(guard_.err))
+
 struct rcsb_model {
   RcsbModel h;        // full-capacity layout
   RcsbModel hr;       // reduced-capacity layout (has_reduced)
@@ -137,6 +151,9 @@ struct rcsb_batch {
   real *d_act_joints = nullptr, *d_act_gripper = nullptr, *d_obs = nullptr;
   int* d_info = nullptr;
   real *h_act = nullptr, *h_obs = nullptr;
+  // optional contact export (rcsb_batch_set_contact_export)
+  int *con_n = nullptr, *con_geom = nullptr, con_cap = 0;
+  real* con_real = nullptr;
 };
 
 extern "C" {
@@ -193,7 +210,7 @@ int rcsb_model_upload(rcsb_model* m, int device) {
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
     return fail(RCSB_ERR_CUDA, "no CUDA device: this backend has no CPU execution path");
-  CUDA_OK(cudaSetDevice(device));
+  DEVICE_OK(device);
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) return fail(RCSB_ERR_CUDA, "sm_100a (B200) device required");
@@ -236,7 +253,7 @@ rcsb_batch* rcsb_batch_new(rcsb_model* m, int n_envs, void* sr, void* sd, void* 
   if (n_envs <= 0 || !sr || !sd || !si) { fail(RCSB_ERR_ARG, "bad batch arguments"); return nullptr; }
   rcsb_batch* b = new rcsb_batch();
   b->m = m; b->n = n_envs; b->sr = (real*)sr; b->sd = (double*)sd; b->si = (int*)si; b->stream = (cudaStream_t)stream;
-  cudaSetDevice(m->device);
+  DeviceGuard guard_(m->device);
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, m->device);
   size_t avail = prop.sharedMemPerBlockOptin;
@@ -332,7 +349,8 @@ int rcsb_batch_run(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps
     L.jhigh[i] = jhigh ? (real)jhigh[i] : 0;
   }
   L.obs = (real*)obs_dev; L.info = info_dev;
-  CUDA_OK(cudaSetDevice(b->m->device));
+  L.con_n = b->con_n; L.con_geom = b->con_geom; L.con_real = b->con_real; L.con_cap = b->con_cap;
+  DEVICE_OK(b->m->device);
   CUDA_OK(cudaMemsetAsync(b->d_counter, 0, 4 * sizeof(int), b->stream));
   L.phase = 0; L.overflow_list = b->d_overflow; L.overflow_count = b->d_counter + 2;
   const bool two = b->m->has_reduced;
@@ -350,8 +368,15 @@ int rcsb_batch_run(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps
   return RCSB_OK;
 }
 
+int rcsb_batch_set_contact_export(rcsb_batch* b, int* ncon_dev, int* geom_dev, void* real_dev, int cap) {
+  if (!b) return fail(RCSB_ERR_ARG, "null batch");
+  if (ncon_dev && (!geom_dev || cap < 1)) return fail(RCSB_ERR_ARG, "geom_dev and cap >= 1 required with ncon_dev");
+  b->con_n = ncon_dev; b->con_geom = ncon_dev ? geom_dev : nullptr; b->con_real = ncon_dev ? (real*)real_dev : nullptr;
+  b->con_cap = ncon_dev ? cap : 0;
+  return RCSB_OK;
+}
 int rcsb_batch_init_state(rcsb_batch* b) {
-  CUDA_OK(cudaSetDevice(b->m->device));
+  DEVICE_OK(b->m->device);
   CUDA_OK(cudaMemsetAsync(b->sr, 0, (size_t)b->n * b->m->h.lay.nsr * sizeof(real), b->stream));
   CUDA_OK(cudaMemsetAsync(b->sd, 0, (size_t)b->n * RCSB_D_TAIL * sizeof(double), b->stream));
   std::vector<int> row(RCSB_I_TAIL, 0), all((size_t)b->n * RCSB_I_TAIL);
@@ -383,7 +408,7 @@ int rcsb_batch_run_host(rcsb_batch* b, unsigned ops, int k, int max_convergence_
   if (sizeof(real) != sizeof(double)) return fail(RCSB_ERR_ARG, "host-buffer path requires a float64 build");
   int rc = ensure_staging(b);
   if (rc) return rc;
-  CUDA_OK(cudaSetDevice(b->m->device));
+  DEVICE_OK(b->m->device);
   int nj = b->m->h.rb_njoints;
   if (act_joints_host)
     CUDA_OK(cudaMemcpyAsync(b->d_act_joints, act_joints_host, (size_t)b->n * nj * sizeof(real), cudaMemcpyHostToDevice, b->stream));
@@ -439,7 +464,7 @@ static int ik_block_threads(int n) {
 static int launch_ik(rcsb_batch* b, const void* pose_dev, const void* q0_dev, void* q_out_dev, int* success_dev, int* iters_dev,
                      int apply) {
   if (!b || !pose_dev) return fail(RCSB_ERR_ARG, "null argument");
-  CUDA_OK(cudaSetDevice(b->m->device));
+  DEVICE_OK(b->m->device);
   int threads = ik_block_threads(b->n), grid = (b->n + threads - 1) / threads;
   rcsb_k_ik<<<grid, threads, RCSB_SMEM_HEADER, b->stream>>>(b->m->d_model, (const real*)pose_dev, (const real*)q0_dev,
                                                            (real*)q_out_dev, success_dev, iters_dev, b->n, apply, b->sr, b->si);
@@ -449,7 +474,7 @@ static int launch_ik(rcsb_batch* b, const void* pose_dev, const void* q0_dev, vo
 }
 int rcsb_env_cartesian_action(rcsb_batch* b, const void* act_dev, int kind, int relative, double max_trans, double max_rot) {
   if (!b || !act_dev || (kind != 0 && kind != 1)) return fail(RCSB_ERR_ARG, "bad argument");
-  CUDA_OK(cudaSetDevice(b->m->device));
+  DEVICE_OK(b->m->device);
   int threads = ik_block_threads(b->n), grid = (b->n + threads - 1) / threads;
   rcsb_k_cart_action<<<grid, threads, RCSB_SMEM_HEADER, b->stream>>>(b->m->d_model, (const real*)act_dev, kind, relative, (real)max_trans,
                                                                      (real)max_rot, b->n, b->sr, b->si);

@@ -207,6 +207,21 @@ RCSB_DEV void st_make_constraint(const Ctx& c) {
       }
     }
     RCSB_SYNC();
+  } else {
+    PFOR(ci, ncon) {  // pyramidal cones: every edge gets Rpy = 2 mu^2 R_first, mu = friction / sqrt(impratio)
+      real* cr = WR(con) + RCSB_C_REALS * ci;
+      const int* cii = WI(con) + RCSB_CI_INTS * ci;
+      int a = cii[RCSB_CI_EFC], dim = cii[RCSB_CI_DIM];
+      if (a >= 0 && dim >= 3) {
+        real ir = m.impratio < RCSB_MINVAL ? RCSB_MINVAL : m.impratio;
+        real mu = cr[RCSB_C_FRIC] / r_sqrt(ir);
+        cr[RCSB_C_MU] = mu;
+        real Rpy = 2 * mu * mu * EFC(RCSB_E_R)[a];
+        if (Rpy < RCSB_MINVAL) Rpy = RCSB_MINVAL;
+        for (int j = 0; j < 2 * (dim - 1); j++) EFC(RCSB_E_R)[a + j] = Rpy;
+      }
+    }
+    RCSB_SYNC();
   }
   PFOR(r, nefc) {
     real vel = 0;
@@ -686,6 +701,8 @@ RCSB_DEV_NOINLINE void newton_solve(const Ctx& c, int nefc, int ncon) {
   }
   if (c.lane == 0) WI(misc)[MI_SOLVER_ITER] = iter;
   compute_qfc(c, nefc);
+  PFOR(k, nv) { WR(warm)[k] = WR(qacc)[k]; }  // mj_fwdConstraint saves the warm start before the noslip post-pass
+  RCSB_SYNC();
   if (MD(noslip_iterations) > 0) solve_noslip(c, nefc, ncon);
 }
 
@@ -697,7 +714,7 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
   int nefc = WI(misc)[MI_NEFC], ncon = WI(misc)[MI_NCON];
   if (nefc == 0) {
     compute_qacc_smooth(c);
-    PFOR(k, nv) { WR(qacc)[k] = WR(qacc_smooth)[k]; WR(qfc)[k] = 0; }
+    PFOR(k, nv) { WR(qacc)[k] = WR(qacc_smooth)[k]; WR(warm)[k] = WR(qacc_smooth)[k]; WR(qfc)[k] = 0; }
     if (c.lane == 0) WI(misc)[MI_SOLVER_ITER] = 0;
     RCSB_SYNC();
     return;
@@ -815,6 +832,7 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
         WR(qfc)[k] = s;
       }
       if (c.lane == 0) WI(misc)[MI_SOLVER_ITER] = attempt;
+      PFOR(k, nv) { WR(warm)[k] = WR(qacc)[k]; }  // saved before noslip, as mj_fwdConstraint does
       RCSB_SYNC();
       if (need_noslip) {  // the post-pass works on M's own factor and the unconstrained acceleration
         compute_qacc_smooth(c);
@@ -861,10 +879,7 @@ RCSB_DEV void st_integrate(const Ctx& c) {
     build_integrator_matrix(c, WR(H));
     chol_factor_solve(c, WR(H), WR(H) + nv * nv, nv, WR(search), WR(tmp), nullptr, nullptr);
   }
-  PFOR(k, nv) {
-    WR(v)[k] += h * WR(search)[k];
-    WR(warm)[k] = WR(qacc)[k];
-  }
+  PFOR(k, nv) { WR(v)[k] += h * WR(search)[k]; }  // qacc_warmstart was saved by the constraint solve, before noslip
   RCSB_SYNC();
   budget_advance(c);  // collision groups: the positions are about to move by h * qvel
   PFOR(b, MD(nb)) {

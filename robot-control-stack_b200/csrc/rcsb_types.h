@@ -211,5 +211,13 @@ struct RcsbLaunch {
   real max_mov, jlow[RCSB_MAXJ], jhigh[RCSB_MAXJ];
   real* obs;   // [N][RCSB_OBS_DIM] or null
   int* info;   // [N][RCSB_INFO_DIM] or null
+  // optional export of mjData.contact after the launch's last step (SimRobot.cpp:172-182, SimGripper.cpp:108-130 read
+  // contact[i].geom[0/1]): count, geom ids of the compiled scene (mjModel numbering) in contact order, and
+  // dist | pos[3] | normal[3] per contact; con_cap contacts per environment, unused slots -1 / 0
+  int* con_n;      // [N] or null
+  int* con_geom;   // [N][con_cap][2]
+  real* con_real;  // [N][con_cap][RCSB_CON_EXPORT_REALS] or null
+  int con_cap;
 };
+enum { RCSB_CON_EXPORT_REALS = 7 };
 

@@ -80,6 +80,16 @@ class Batch:
         except Exception:
             pass
 
+    def enable_contact_export(self, cap: int = 8, with_geometry: bool = True):
+        """Keep every environment's contact list (mjData.ncon / contact[i].geom, SimRobot.cpp:172-182) after each
+        stepping launch in self.contact_n [n], self.contact_geom [n, cap, 2] and self.contact_real [n, cap, 7]."""
+        self.contact_n = torch.zeros((self.n,), dtype=torch.int32, device=self.dev)
+        self.contact_geom = torch.full((self.n, cap, 2), -1, dtype=torch.int32, device=self.dev)
+        self.contact_real = torch.zeros((self.n, cap, 7), dtype=torch.float64, device=self.dev) if with_geometry else None
+        _lib.check(_lib.lib().rcsb_batch_set_contact_export(
+            self.ptr, self.contact_n.data_ptr(), self.contact_geom.data_ptr(),
+            self.contact_real.data_ptr() if with_geometry else None, cap))
+
     # ---- column views
     @property
     def qpos(self):

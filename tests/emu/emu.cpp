@@ -44,6 +44,9 @@ static void run_phase(const RcsbModel* m, const real* verts, real* sr, double* s
     if (dbg_layout) dbg_layout[e] = m->cap_reduced;
   }
 }
+// optional contact export, as rcsb_batch_set_contact_export
+static int* g_con_n = nullptr; static int* g_con_geom = nullptr; static real* g_con_real = nullptr; static int g_con_cap = 0;
+void emu_set_contact_export(int* n, int* geom, real* r, int cap) { g_con_n = n; g_con_geom = geom; g_con_real = r; g_con_cap = cap; }
 // run the per-launch program over N environments, serially: reduced layout first (when present), then the full
 // layout for the environments that outgrew it -- the two launches of rcsb_batch_run
 int emu_run(const EmuModel* em, const real* verts, real* sr, double* sd, int* si, int N, unsigned ops, int k,
@@ -55,6 +58,7 @@ int emu_run(const EmuModel* em, const real* verts, real* sr, double* sd, int* si
   L.act_joints = act_joints; L.act_gripper = act_gripper; L.mask = mask; L.max_mov = max_mov;
   for (int i = 0; i < RCSB_MAXJ; i++) { L.jlow[i] = jlow ? jlow[i] : 0; L.jhigh[i] = jhigh ? jhigh[i] : 0; }
   L.obs = obs; L.info = info;
+  L.con_n = g_con_n; L.con_geom = g_con_geom; L.con_real = g_con_real; L.con_cap = g_con_cap;
   std::vector<int> list(N);
   int count = 0;
   L.overflow_list = list.data(); L.overflow_count = &count; L.phase = 0;

@@ -65,6 +65,13 @@ class Emu:
         self.layout = np.zeros(N, dtype=np.int32)  # 1 = the env last ran in the reduced layout
         self.handed_over = 0                        # envs the reduced layout passed to the full one in the last run
 
+    def enable_contact_export(self, cap=8):
+        ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+        self.contact_n = np.zeros(self.N, dtype=np.int32)
+        self.contact_geom = np.full((self.N, cap, 2), -1, dtype=np.int32)
+        self.contact_real = np.zeros((self.N, cap, 7))
+        self.contact_cap = cap
+
     def off(self, name, reduced=0):
         return self.L.emu_offset(self.m, name.encode(), int(reduced))
 
@@ -75,6 +82,12 @@ class Emu:
             code |= OPS[o]
         aj = np.ascontiguousarray(act_joints, dtype=np.float64) if act_joints is not None else None
         ag = np.ascontiguousarray(act_gripper, dtype=np.float64) if act_gripper is not None else None
+        self.L.emu_set_contact_export.argtypes = [ip, ip, dp, C.c_int]
+        if getattr(self, "contact_cap", 0):  # the library keeps one global export target: set it for this instance's run
+            self.L.emu_set_contact_export(self.contact_n.ctypes.data_as(ip), self.contact_geom.ctypes.data_as(ip),
+                                          self.contact_real.ctypes.data_as(dp), self.contact_cap)
+        else:
+            self.L.emu_set_contact_export(None, None, None, 0)
         lo = np.zeros(8); hi = np.zeros(8)
         if jlow is not None:
             lo[:len(jlow)] = jlow; hi[:len(jhigh)] = jhigh

@@ -72,29 +72,38 @@ def test_workload_trajectory_and_lane_order_independence(fr3):
 
 
 def test_floor_collision_contact_indexing_exact(fr3):
+    """north_star: contact-pair indexing is bit-exact. The device code's exported contact list (count, geom ids in
+    mjModel numbering, order) equals the oracle's mjData.contact on every sample of the floor-collision trajectory, and
+    equals the committed floor_pairs fixture; dist / pos / normal agree to rounding."""
+    import os
     M, F, verts = fr3
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "step_vectors.npz"))
     e = Emu(F, verts, 1)
+    e.enable_contact_export(cap=8)
     mm, s = H.oracle_sim(M)
     tgt = np.array([0, 1.78, 0, -1.45, 0, 0, 0.0])
     e.run(RESET[:-1], k=1); s.gripper_reset(); s.reset(); s.robot_reset(); s.step(1)
     e.run(["SET_JOINTS"], act_joints=tgt[None]); s.set_joint_position(tgt)
-    orig = np.asarray(F["g_origid"][0])
     hit = 0
     for it in range(80):
         e.run(["STEP_K"], k=5); s.step(5)
         ncon = int(e.si[0, 14])
-        assert ncon == int(s.data.ncon[0]) and int(e.si[0, 15]) == int(s.data.nefc[0])
+        assert ncon == int(s.data.ncon[0]) == int(e.contact_n[0]) and int(e.si[0, 15]) == int(s.data.nefc[0])
+        ref_pairs = s.data.int("contact_geom").reshape(-1, 2)
+        assert np.array_equal(e.contact_geom[0, :ncon], ref_pairs), (it, e.contact_geom[0, :ncon], ref_pairs)
+        assert (e.contact_geom[0, ncon:] == -1).all()
+        assert np.array_equal(e.contact_geom[0, :6], G["floor_pairs"][it]), it
         if ncon:
             hit += 1
-            con_i = e.ws[0].view(np.int64)  # ints live after the reals; use the oracle list for ids instead
-            ref_pairs = s.data.int("contact_geom").reshape(-1, 2)
-            assert len(ref_pairs) == ncon
+            ref = s.data.real("contact_real").reshape(-1, 7)
+            assert np.abs(e.contact_real[0, :ncon] - ref).max() < 1e-7, it
         assert np.abs(e.sr[0, :9] - s.data.qpos).max() < 1e-6
     assert hit > 10
     # collision flags after a converge call agree
     e.run(["STEP_CONV"]); s.step_until_convergence()
     assert bool(e.si[0, 6]) == s.is_converged() and int(e.si[0, 7]) == s.convergence_steps()
     assert bool(e.si[0, 1]) == s.robot_state()["collision"] and bool(e.si[0, 5]) == s.gripper_state()["collision"]
+    assert s.robot_state()["collision"]
 
 
 def test_step_until_convergence_counts(fr3):

@@ -86,6 +86,10 @@ def test_env_workload_trajectory_parity(setup):
         worst = max(worst, err)
         assert err < 1e-6, (t, err)
         assert np.array_equal(g[:, 20], ref_obs[:, t, 20])
+        assert np.abs(g[:, 21] - ref_obs[:, t, 21]).max() < 1e-6  # info["gripper_width"], SimGripper.cpp:93-106
+        gi = b.info.cpu().numpy()
+        # info: collision, ik_success, is_sim_converged, is_grasped | robot / gripper collision (envs/sim.py:60-66,125-131)
+        assert np.array_equal(gi[:, [0, 1, 2, 3, 5, 6]], ref_obs[:, t, 22:28].astype(np.int32)), t
         safe = np.abs(np.abs(ref_obs[:, t, 19]) - np.pi / 2) < 1.4  # yaw well inside (0, pi)
         safe &= (ref_obs[:, t, 19] > 0.05) & (ref_obs[:, t, 19] < np.pi - 0.05)
         assert np.abs(g[safe, 14:20] - ref_obs[safe, t, 14:20]).max(initial=0) < 1e-5
@@ -115,27 +119,54 @@ def test_generic_state_trajectory_parity(setup):
 
 def test_floor_collision_contacts_exact(setup):
     """Arm driven into the floor (the reference's own collision test pose, python/tests/test_sim_envs.py:347-360):
-    contact count and geom pair indexing must match the oracle exactly while the contact is well-conditioned;
-    state must stay within 1e-6."""
+    north_star's bit-exact contact-pair indexing. The exported contact list (count, geom ids in mjModel numbering,
+    order) equals the oracle's mjData.contact at every sample and the committed floor_pairs fixture; contact geometry
+    agrees to 1e-7, state to 1e-6; SimRobotState.collision / SimGripperState.collision as sampled by the condition
+    callbacks (SimRobot.cpp:172-182, SimGripper.cpp:108-130) are identical."""
+    import os
     M, dm, _lib, batch = setup
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "step_vectors.npz"))
     N = 4
     b = batch.Batch(dm, N)
+    b.enable_contact_export(cap=8)
     m, s = H.oracle_sim(M)
     tgt = np.array([0, 1.78, 0, -1.45, 0, 0, 0.0])
     s.gripper_reset(); s.reset(); s.robot_reset(); s.step(1)
     b.run(_lib.GRIPPER_RESET | _lib.SIM_RESET | _lib.ROBOT_RESET | _lib.ENV_RESET_FLAGS | _lib.STEP_K, k=1)
     s.set_joint_position(tgt)
     b.run(_lib.SET_JOINTS, act_joints=torch.as_tensor(np.tile(tgt, (N, 1)), device=b.dev))
-    hit = False
-    for it in range(40):
-        s.step(10)
-        b.run(_lib.STEP_K, k=10)
+    hits = 0
+    for it in range(90):
+        s.step(5)
+        b.run(_lib.STEP_K, k=5)
         ncon = int(b.si[0, 14].item())
-        assert ncon == int(s.data.ncon[0]), it
-        hit |= ncon > 0
+        assert ncon == int(s.data.ncon[0]) == int(b.contact_n[0]), it
+        cg = b.contact_geom.cpu().numpy()
+        ref_pairs = s.data.int("contact_geom").reshape(-1, 2)
+        for e in range(N):
+            assert np.array_equal(cg[e, :ncon], ref_pairs), (it, e)
+            assert (cg[e, ncon:] == -1).all()
+        assert np.array_equal(cg[0, :6], G["floor_pairs"][it]), it
+        if ncon:
+            hits += 1
+            ref = s.data.real("contact_real").reshape(-1, 7)
+            assert np.abs(b.contact_real[0, :ncon].cpu().numpy() - ref).max() < 1e-7, it
         assert np.abs(b.qpos[0].cpu().numpy() - s.data.qpos).max() < 1e-6, it
         assert np.abs(b.qvel[0].cpu().numpy() - s.data.qvel).max() < 1e-4, it
-    assert hit
+    assert hits > 10
+    # the condition callbacks sample the collision flags; a hit ends step_until_convergence early (sim.cpp:52-55)
+    s.step_until_convergence()
+    b.run(_lib.STEP_CONV | _lib.OBS, max_convergence_steps=500, want_obs=True)
+    si, info = b.si.cpu().numpy(), b.info.cpu().numpy()
+    rs, gs = s.robot_state(), s.gripper_state()
+    assert rs["collision"]
+    for e in range(N):
+        assert bool(si[e, 1]) == rs["collision"] and bool(si[e, 5]) == gs["collision"]
+        assert bool(si[e, 2]) == rs["is_moving"] and bool(si[e, 3]) == rs["is_arrived"]
+        assert bool(si[e, 6]) == s.is_converged() and int(si[e, 7]) == s.convergence_steps()
+        assert bool(info[e, 0]) == (rs["collision"] or gs["collision"]) and bool(info[e, 5]) == rs["collision"]
+        assert bool(info[e, 6]) == gs["collision"]
+        assert abs(b.obs[e, 21].item() - s.gripper_get_normalized_width()) < 1e-6
 
 
 def test_step_until_convergence_parity(setup):
