@@ -49,6 +49,9 @@ void rcsb_model_free(rcsb_model* m);
 int rcsb_model_set_int(rcsb_model* m, const char* field, const int* v, int n);
 int rcsb_model_set_real(rcsb_model* m, const char* field, const double* v, int n);
 int rcsb_model_set_mesh_vertices(rcsb_model* m, const double* xyz, int nvert);
+/* edge graph of the convex hulls (mjModel mesh_graph, used by mjc_PlaneConvex for multi-point plane-mesh contacts):
+ * neighbours of pooled vertex v are nbr[adr[v] .. adr[v+1]) as vertex ids local to the geom's hull; optional */
+int rcsb_model_set_mesh_graph(rcsb_model* m, const int* adr, int nadr, const int* nbr, int nnbr);
 int rcsb_model_finalize(rcsb_model* m);         /* validates sizes, computes the workspace layout (host only) */
 int rcsb_model_upload(rcsb_model* m, int device); /* copies constants and hull vertices to the CUDA device */
 /* sizes of one environment's rows: reals, doubles, ints, obs reals, info ints */

@@ -6,9 +6,15 @@
  * mjc_PlaneBox / mjc_PlaneCapsule; all other pairs go through Minkowski Portal Refinement, the
  * algorithm of libccd's ccdMPRPenetration that MuJoCo 3.2.6 calls for convex pairs (mjc_Convex).
  *
+ * Multi-point pair functions [3P]: plane-mesh (mjc_PlaneConvex) emits the deepest hull vertex plus neighbours
+ * of it in the hull's edge graph that are within the margin and at least 0.3 * rbound away from the points already
+ * taken, 3 contacts at most; box-box (mjc_BoxBox) is the separating-axis test followed by clipping of the incident
+ * face against the reference face (up to 8 points) or the closest points of the two edges.
  * Stated deviations from MuJoCo (all "parity unpinned"):
- *  - plane-mesh emits the single deepest hull vertex (MuJoCo adds up to 3 more support points);
- *  - box-box uses MPR (one contact) instead of mjc_BoxBox's up-to-8-point clipping;
+ *  - the hull's edge graph comes from scipy's qhull at scene-compile time with neighbours in ascending vertex order
+ *    (MuJoCo walks its own qhull graph in qhull's order);
+ *  - box-box follows the classic face-clipping construction, not mjc_BoxBox line by line: same contact count for
+ *    face-face / edge-edge configurations, point order and sub-mm positions may differ;
  *  - contacts are emitted in pair-list order (g1<g2 lexicographic), geom[0] = lower geom type. */
 #include "oracle_internal.h"
 
@@ -268,13 +274,41 @@ static void add_contact(const rcso_model* m, rcso_data* d, int g1, int g2, doubl
 /* ---- plane pair functions ---- */
 static void plane_mesh(const rcso_model* m, rcso_data* d, int gp, int g, double margin, double gap) {
   const double* Rp = d->geom_xmat + 9 * gp;
-  double n[3] = {Rp[2], Rp[5], Rp[8]}, nd[3] = {-Rp[2], -Rp[5], -Rp[8]}, v[3], dif[3], pos[3];
-  support(m, d, g, nd, v);
-  for (int k = 0; k < 3; k++) dif[k] = v[k] - d->geom_xpos[3 * gp + k];
-  double dist = dot3(dif, n);
-  if (dist > margin) return;
-  for (int k = 0; k < 3; k++) pos[k] = v[k] - 0.5 * dist * n[k];
-  add_contact(m, d, gp, g, dist, pos, n, margin, gap);
+  const double* R = d->geom_xmat + 9 * g;
+  const double* pg = d->geom_xpos + 3 * g;
+  double n[3] = {Rp[2], Rp[5], Rp[8]}, nl[3], nd[3] = {-Rp[2], -Rp[5], -Rp[8]};
+  const double* verts = m->mesh_vert + 3 * m->geom_vertadr[g];
+  int nvert = m->geom_vertnum[g], best = 0;
+  double bd = -1e300;
+  mulmatT3(nl, R, nd);
+  for (int i = 0; i < nvert; i++) {
+    double sdot = dot3(verts + 3 * i, nl);
+    if (sdot > bd) { bd = sdot; best = i; }
+  }
+  double taken[3][3];
+  int count = 0;
+  const double thr = 0.3 * m->geom_rbound[g], thr2 = thr * thr; /* tolplanemesh */
+  /* candidates: the support vertex, then its hull-graph neighbours in ascending order */
+  int nb0 = m->mesh_graphadr ? m->mesh_graphadr[m->geom_vertadr[g] + best] : 0;
+  int nb1 = m->mesh_graphadr ? m->mesh_graphadr[m->geom_vertadr[g] + best + 1] : 0;
+  for (int c = -1; c < nb1 - nb0 && count < 3; c++) {
+    int vi = c < 0 ? best : m->mesh_graph[nb0 + c];
+    double v[3], dif[3], pos[3];
+    mulmat3(v, R, verts + 3 * vi);
+    for (int k = 0; k < 3; k++) { v[k] += pg[k]; dif[k] = v[k] - d->geom_xpos[3 * gp + k]; }
+    double dist = dot3(dif, n);
+    if (dist > margin) { if (c < 0) return; continue; }
+    int close = 0;
+    for (int t = 0; t < count; t++) {
+      double e[3] = {v[0] - taken[t][0], v[1] - taken[t][1], v[2] - taken[t][2]};
+      if (dot3(e, e) < thr2) close = 1;
+    }
+    if (close) continue;
+    copy3(taken[count], v);
+    count++;
+    for (int k = 0; k < 3; k++) pos[k] = v[k] - 0.5 * dist * n[k];
+    add_contact(m, d, gp, g, dist, pos, n, margin, gap);
+  }
 }
 static void plane_box(const rcso_model* m, rcso_data* d, int gp, int g, double margin, double gap) {
   const double* Rp = d->geom_xmat + 9 * gp;
@@ -311,6 +345,157 @@ static void plane_capsule(const rcso_model* m, rcso_data* d, int gp, int g, doub
     for (int k = 0; k < 3; k++) pos[k] = c[k] - n[k] * (r + 0.5 * dist);
     add_contact(m, d, gp, g, dist, pos, n, margin, gap);
   }
+}
+
+
+/* ---- box-box [3P: mjc_BoxBox, restated as separating axes + face clipping] ----
+ * Frames: column k of the row-major 3x3 geom_xmat is the box axis k in world coordinates. */
+#define BB_EDGE_FUDGE 1.05 /* an edge-edge axis wins only if it is clearly better than the best face axis */
+static int box_box(const rcso_model* m, rcso_data* d, int g1, int g2, double margin, double gap) {
+  const double *R1 = d->geom_xmat + 9 * g1, *R2 = d->geom_xmat + 9 * g2;
+  const double *p1 = d->geom_xpos + 3 * g1, *p2 = d->geom_xpos + 3 * g2;
+  const double *a = m->geom_size + 3 * g1, *b = m->geom_size + 3 * g2;
+  double Rel[9], Q[9], t[3], dp[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  mulmatT3(t, R1, dp);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      Rel[3 * i + j] = R1[i] * R2[j] + R1[3 + i] * R2[3 + j] + R1[6 + i] * R2[6 + j];
+      Q[3 * i + j] = fabs(Rel[3 * i + j]);
+    }
+  /* face axes: separation s <= margin on every axis or no contact; keep the axis of least penetration */
+  double best = -1e300;
+  int code = -1, flip = 0;
+  for (int i = 0; i < 3; i++) {
+    double s = fabs(t[i]) - (a[i] + b[0] * Q[3 * i] + b[1] * Q[3 * i + 1] + b[2] * Q[3 * i + 2]);
+    if (s > margin) return 0;
+    if (s > best) { best = s; code = i; flip = t[i] < 0; }
+  }
+  for (int j = 0; j < 3; j++) {
+    double tj = t[0] * Rel[j] + t[1] * Rel[3 + j] + t[2] * Rel[6 + j];
+    double s = fabs(tj) - (a[0] * Q[j] + a[1] * Q[3 + j] + a[2] * Q[6 + j] + b[j]);
+    if (s > margin) return 0;
+    if (s > best) { best = s; code = 3 + j; flip = tj < 0; }
+  }
+  /* edge-edge axes a_i x b_j (normalised) */
+  double ebest = -1e300, en[3] = {0, 0, 0};
+  int ecode = -1;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      double l2 = 1 - Rel[3 * i + j] * Rel[3 * i + j];
+      if (l2 < 1e-10) continue; /* parallel edges: covered by the face axes */
+      double l = sqrt(l2);
+      double proj = t[i2] * Rel[3 * i1 + j] - t[i1] * Rel[3 * i2 + j];
+      double ra = a[i1] * Q[3 * i2 + j] + a[i2] * Q[3 * i1 + j];
+      double rb = b[j1] * Q[3 * i + j2] + b[j2] * Q[3 * i + j1];
+      double s = (fabs(proj) - (ra + rb)) / l;
+      if (s > margin) return 0;
+      if (s > ebest) {
+        ebest = s; ecode = 3 * i + j;
+        /* axis in the frame of box 1: e_i x (column j of Rel), pointing from box 1 to box 2 */
+        double ax[3] = {0, 0, 0};
+        ax[i1] = -Rel[3 * i2 + j] / l; ax[i2] = Rel[3 * i1 + j] / l;
+        if (proj < 0) { ax[0] = -ax[0]; ax[1] = -ax[1]; ax[2] = -ax[2]; }
+        en[0] = ax[0]; en[1] = ax[1]; en[2] = ax[2];
+      }
+    }
+  /* exactly touching boxes (the finger pads at qpos0 after every reset) have best = +-1e-18: not a contact, as for
+   * the convex pairs (MuJoCo lists dist = 0 there, which dist >= includemargin keeps out of the constraint set) */
+  if (best > margin - 1e-12) return 0;
+  if (ecode >= 0 && ebest * BB_EDGE_FUDGE > best) { /* separations are negative depths: the edge must be clearly shallower */
+    /* edge-edge: closest points of the two edge lines */
+    int i = ecode / 3, j = ecode % 3;
+    double nw[3];
+    mulmat3(nw, R1, en); /* world normal, from box 1 to box 2 */
+    /* point on the edge of box 1: the vertex most along +n (edge direction left free), of box 2 most along -n */
+    double pa[3], pb[3], ua[3] = {R1[i], R1[3 + i], R1[6 + i]}, ub[3] = {R2[j], R2[3 + j], R2[6 + j]};
+    copy3(pa, p1); copy3(pb, p2);
+    for (int k = 0; k < 3; k++) {
+      if (k != i) {
+        double ak[3] = {R1[k], R1[3 + k], R1[6 + k]};
+        double sg = dot3(nw, ak) > 0 ? a[k] : -a[k];
+        for (int c = 0; c < 3; c++) pa[c] += sg * ak[c];
+      }
+      if (k != j) {
+        double bk[3] = {R2[k], R2[3 + k], R2[6 + k]};
+        double sg = dot3(nw, bk) > 0 ? -b[k] : b[k];
+        for (int c = 0; c < 3; c++) pb[c] += sg * bk[c];
+      }
+    }
+    double w[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
+    double uaub = dot3(ua, ub), q1 = dot3(ua, w), q2 = -dot3(ub, w), den = 1 - uaub * uaub;
+    double alpha = 0, beta = 0;
+    if (den > 1e-10) { alpha = (q1 + uaub * q2) / den; beta = (uaub * q1 + q2) / den; }
+    double pos[3];
+    for (int c = 0; c < 3; c++) pos[c] = 0.5 * ((pa[c] + alpha * ua[c]) + (pb[c] + beta * ub[c]));
+    add_contact(m, d, g1, g2, ebest, pos, nw, margin, gap);
+    return 1;
+  }
+  /* ---- face contact: reference face on box 1 (code < 3) or box 2 ---- */
+  const double *Rr, *Ri, *pr, *pi, *sr, *si;
+  int ax = code < 3 ? code : code - 3;
+  if (code < 3) { Rr = R1; Ri = R2; pr = p1; pi = p2; sr = a; si = b; }
+  else { Rr = R2; Ri = R1; pr = p2; pi = p1; sr = b; si = a; }
+  /* outward normal of the reference face, pointing towards the incident box */
+  double sgn = (code < 3) ? (flip ? -1.0 : 1.0) : (flip ? 1.0 : -1.0);
+  double nr[3] = {sgn * Rr[ax], sgn * Rr[3 + ax], sgn * Rr[6 + ax]};
+  /* incident face: the face of the other box whose outward normal is most opposed to nr */
+  int iax = 0;
+  double md = -1;
+  double isg = 1;
+  for (int k = 0; k < 3; k++) {
+    double dk = nr[0] * Ri[k] + nr[1] * Ri[3 + k] + nr[2] * Ri[6 + k];
+    if (fabs(dk) > md) { md = fabs(dk); iax = k; isg = dk > 0 ? -1.0 : 1.0; }
+  }
+  int u1 = (iax + 1) % 3, u2 = (iax + 2) % 3, r1 = (ax + 1) % 3, r2 = (ax + 2) % 3;
+  /* the 4 vertices of the incident face (world), counter-clockwise in its own (u1, u2) plane */
+  double quad[4][3];
+  static const double cs[4][2] = {{1, 1}, {-1, 1}, {-1, -1}, {1, -1}};
+  for (int v = 0; v < 4; v++)
+    for (int c = 0; c < 3; c++)
+      quad[v][c] = pi[c] + isg * si[iax] * Ri[3 * c + iax] + cs[v][0] * si[u1] * Ri[3 * c + u1] + cs[v][1] * si[u2] * Ri[3 * c + u2];
+  /* to reference-face coordinates: (x, y) along the reference box axes r1, r2; z = height above the reference face */
+  double poly[16][3], tmp[16][3];
+  int np = 4;
+  for (int v = 0; v < 4; v++) {
+    double e[3] = {quad[v][0] - pr[0], quad[v][1] - pr[1], quad[v][2] - pr[2]};
+    poly[v][0] = e[0] * Rr[r1] + e[1] * Rr[3 + r1] + e[2] * Rr[6 + r1];
+    poly[v][1] = e[0] * Rr[r2] + e[1] * Rr[3 + r2] + e[2] * Rr[6 + r2];
+    poly[v][2] = dot3(e, nr) - sr[ax];
+  }
+  /* Sutherland-Hodgman against the four sides of the reference rectangle */
+  for (int side = 0; side < 4; side++) {
+    int c = side >> 1;
+    double sg = (side & 1) ? -1.0 : 1.0, lim = c == 0 ? sr[r1] : sr[r2];
+    int nq = 0;
+    for (int v = 0; v < np; v++) {
+      const double *A = poly[v], *B = poly[(v + 1) % np];
+      double da = lim - sg * A[c], db = lim - sg * B[c];
+      if (da >= 0) { copy3(tmp[nq], A); nq++; }
+      if ((da >= 0) != (db >= 0)) {
+        double f = da / (da - db);
+        for (int k = 0; k < 3; k++) tmp[nq][k] = A[k] + f * (B[k] - A[k]);
+        nq++;
+      }
+    }
+    np = nq;
+    for (int v = 0; v < np; v++) copy3(poly[v], tmp[v]);
+    if (np == 0) break;
+  }
+  /* contacts: clipped points at or below the reference face (within the margin), 8 at most */
+  double nw[3] = {nr[0], nr[1], nr[2]};
+  if (code >= 3) { nw[0] = -nw[0]; nw[1] = -nw[1]; nw[2] = -nw[2]; } /* contact normal runs from geom 1 to geom 2 */
+  int cnt = 0;
+  for (int v = 0; v < np && cnt < 8; v++) {
+    double dist = poly[v][2];
+    if (dist > margin) continue;
+    double pos[3];
+    for (int c = 0; c < 3; c++)
+      pos[c] = pr[c] + poly[v][0] * Rr[3 * c + r1] + poly[v][1] * Rr[3 * c + r2] + (sr[ax] + 0.5 * dist) * nr[c];
+    add_contact(m, d, g1, g2, dist, pos, nw, margin, gap);
+    cnt++;
+  }
+  return cnt;
 }
 
 /* world centre of the geom's bounding volume (local AABB centre) */
@@ -378,6 +563,7 @@ void rcso_collision(const rcso_model* m, rcso_data* d) {
     double bound = m->geom_bsphere[4 * g1 + 3] + m->geom_bsphere[4 * g2 + 3] + margin;
     if (dot3(dif, dif) > bound * bound) continue;
     if (obb_separated(m, d, g1, g2, margin)) continue;
+    if (t1 == GEOM_BOX && t2 == GEOM_BOX) { box_box(m, d, g1, g2, margin, gap); continue; }
     double dist, pos[3], normal[3];
     if (rcso_convex_convex(m, d, g1, g2, margin, &dist, pos, normal)) add_contact(m, d, g1, g2, dist, pos, normal, margin, gap);
   }

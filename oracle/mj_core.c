@@ -89,7 +89,8 @@ static const field_t model_fields[] = {
     MF(geom_type, 1), MF(geom_bodyid, 1), MF(geom_condim, 1), MF(geom_priority, 1), MF(geom_vertadr, 1),
     MF(geom_vertnum, 1), MF(geom_size, 0), MF(geom_pos, 0), MF(geom_quat, 0), MF(geom_friction, 0),
     MF(geom_solref, 0), MF(geom_solimp, 0), MF(geom_solmix, 0), MF(geom_margin, 0), MF(geom_gap, 0),
-    MF(geom_rbound, 0), MF(geom_aabb, 0), MF(geom_bsphere, 0), MF(mesh_vert, 0), MF(pair_geom, 1),
+    MF(geom_rbound, 0), MF(geom_aabb, 0), MF(geom_bsphere, 0), MF(mesh_vert, 0), MF(mesh_graphadr, 1), MF(mesh_graph, 1),
+    MF(pair_geom, 1),
     MF(site_bodyid, 1), MF(site_pos, 0), MF(site_quat, 0), MF(tendon_coef, 0), MF(tendon_invweight0, 0),
     MF(eq_obj1id, 1), MF(eq_obj2id, 1), MF(eq_active0, 1), MF(eq_polycoef, 0), MF(eq_solref, 0), MF(eq_solimp, 0),
     MF(actuator_trntype, 1), MF(actuator_trnid, 1), MF(actuator_ctrllimited, 1), MF(actuator_forcelimited, 1),

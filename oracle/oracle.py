@@ -17,7 +17,7 @@ _LIB = None
 _INT_FIELDS = ["body_parentid", "body_rootid", "body_weldid", "body_jntnum", "body_jntadr", "body_dofnum",
                "body_dofadr", "jnt_type", "jnt_bodyid", "jnt_qposadr", "jnt_dofadr", "jnt_limited",
                "jnt_actfrclimited", "jnt_actgravcomp", "dof_jntid", "dof_bodyid", "dof_parentid", "geom_type",
-               "geom_bodyid", "geom_condim", "geom_priority", "geom_vertadr", "geom_vertnum", "pair_geom",
+               "geom_bodyid", "geom_condim", "geom_priority", "geom_vertadr", "geom_vertnum", "pair_geom", "mesh_graphadr", "mesh_graph",
                "site_bodyid", "eq_obj1id", "eq_obj2id", "eq_active0", "actuator_trntype", "actuator_trnid",
                "actuator_ctrllimited", "actuator_forcelimited"]
 _REAL_FIELDS = ["body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_inertia", "body_gravcomp",

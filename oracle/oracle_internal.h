@@ -38,6 +38,7 @@ struct rcso_model {
   int *geom_type, *geom_bodyid, *geom_condim, *geom_priority, *geom_vertadr, *geom_vertnum;
   double *geom_size, *geom_pos, *geom_quat, *geom_friction, *geom_solref, *geom_solimp, *geom_solmix,
       *geom_margin, *geom_gap, *geom_rbound, *geom_aabb, *geom_bsphere, *mesh_vert;
+  int *mesh_graphadr, *mesh_graph; /* hull edge graph: neighbours of pooled vertex v are mesh_graph[adr[v] .. adr[v+1]), local ids */
   int* pair_geom;
   /* sites */
   int* site_bodyid;

@@ -7,7 +7,8 @@ struct Ctx {
   const RcsbModel* md;  // model constants
   real* w;              // real workspace
   int* wi;              // int workspace
-  const real* verts;    // convex hull vertex pool
+ const real* verts;    // convex hull vertex pool
+  const int* vgraph;    // hull edge graph: [nmeshvert + 1] offsets, then neighbour lists (local vertex ids); may be null
   double* clk;          // simulation time + callback clocks (always double)
   int lane;
   int lockstep;
@@ -26,6 +27,7 @@ extern __shared__ __align__(128) unsigned char rcsb_smem[];
 struct Ctx {
   const RcsbModel* gm;  // the model in global memory (cold tail: fields after cold_begin)
   const real* verts;    // convex hull vertex pool (global memory, read-only)
+  const int* vgraph;    // hull edge graph (global memory): [nmeshvert + 1] offsets, then neighbour lists; may be null
   uint32_t wb;          // this warp's real workspace (byte offset in shared memory)
   uint32_t clkb;        // this warp's simulation time + callback clocks (always double)
   uint32_t wib;         // this warp's int workspace

@@ -807,6 +807,187 @@ RCSB_DEV void add_contact(const Ctx& c, int& ncon, int g1, int g2, real dist, co
   ncon++;
 }
 
+
+// ---- box-box (mjc_BoxBox, restated as separating axes + face clipping; see oracle/mj_collision.c): up to 8 contacts.
+// Every lane runs the same scalar code on identical data (add_contact lets lane 0 write); out of line and rare (finger
+// pads against the cube or each other), so the clipping polygon may live in thread-local memory.
+RCSB_DEV_NOINLINE void box_box(const Ctx& c, int& ncon, const PairFrames& pf, real margin, real gap, real* clear_out) {
+  const RcsbModel& m = CMODEL(c);
+  const real *R1 = pf.R1, *R2 = pf.R2, *p1 = pf.p1, *p2 = pf.p2;
+  const real *a = m.g_size[pf.g1], *b = m.g_size[pf.g2];
+  real Rel[9], Q[9], t[3], dp[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  mulmatT3(t, R1, dp);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      Rel[3 * i + j] = R1[i] * R2[j] + R1[3 + i] * R2[3 + j] + R1[6 + i] * R2[6 + j];
+      Q[3 * i + j] = r_abs(Rel[3 * i + j]);
+    }
+  real best = (real)-1e300;
+  int code = -1, flip = 0;
+  for (int i = 0; i < 3; i++) {
+    real s = r_abs(t[i]) - (a[i] + b[0] * Q[3 * i] + b[1] * Q[3 * i + 1] + b[2] * Q[3 * i + 2]);
+    if (s > best) { best = s; code = i; flip = t[i] < 0; }
+  }
+  for (int j = 0; j < 3; j++) {
+    real tj = t[0] * Rel[j] + t[1] * Rel[3 + j] + t[2] * Rel[6 + j];
+    real s = r_abs(tj) - (a[0] * Q[j] + a[1] * Q[3 + j] + a[2] * Q[6 + j] + b[j]);
+    if (s > best) { best = s; code = 3 + j; flip = tj < 0; }
+  }
+  // a face axis separates the boxes by more than the margin (or they touch exactly): no contact; the clearance feeds the
+  // group's separation budget
+  if (best > margin - (real)1e-12) { *clear_out = best > margin ? best - margin : (real)0; return; }
+  real ebest = (real)-1e300, en[3] = {0, 0, 0};
+  int ecode = -1;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      real l2 = 1 - Rel[3 * i + j] * Rel[3 * i + j];
+      if (l2 < (real)1e-10) continue;
+      real l = r_sqrt(l2);
+      real proj = t[i2] * Rel[3 * i1 + j] - t[i1] * Rel[3 * i2 + j];
+      real ra = a[i1] * Q[3 * i2 + j] + a[i2] * Q[3 * i1 + j];
+      real rb = b[j1] * Q[3 * i + j2] + b[j2] * Q[3 * i + j1];
+      real s = (r_abs(proj) - (ra + rb)) / l;
+      if (s > margin) return;  // separated along an edge-edge axis only: no usable clearance bound (budget stays 0)
+      if (s > ebest) {
+        ebest = s; ecode = 3 * i + j;
+        real ax[3] = {0, 0, 0};
+        ax[i1] = -Rel[3 * i2 + j] / l; ax[i2] = Rel[3 * i1 + j] / l;
+        if (proj < 0) { ax[0] = -ax[0]; ax[1] = -ax[1]; ax[2] = -ax[2]; }
+        en[0] = ax[0]; en[1] = ax[1]; en[2] = ax[2];
+      }
+    }
+  if (ecode >= 0 && ebest * (real)1.05 > best) {  // edge-edge: closest points of the two edge lines
+    const int i = ecode / 3, j = ecode % 3;
+    real nw[3];
+    mulmat3(nw, R1, en);
+    real pa[3], pb[3], ua[3] = {R1[i], R1[3 + i], R1[6 + i]}, ub[3] = {R2[j], R2[3 + j], R2[6 + j]};
+    copy3(pa, p1); copy3(pb, p2);
+    for (int k = 0; k < 3; k++) {
+      if (k != i) {
+        real ak[3] = {R1[k], R1[3 + k], R1[6 + k]};
+        real sg = dot3(nw, ak) > 0 ? a[k] : -a[k];
+        for (int cc = 0; cc < 3; cc++) pa[cc] += sg * ak[cc];
+      }
+      if (k != j) {
+        real bk[3] = {R2[k], R2[3 + k], R2[6 + k]};
+        real sg = dot3(nw, bk) > 0 ? -b[k] : b[k];
+        for (int cc = 0; cc < 3; cc++) pb[cc] += sg * bk[cc];
+      }
+    }
+    real w[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
+    real uaub = dot3(ua, ub), q1 = dot3(ua, w), q2 = -dot3(ub, w), den = 1 - uaub * uaub;
+    real alpha = 0, beta = 0;
+    if (den > (real)1e-10) { alpha = (q1 + uaub * q2) / den; beta = (uaub * q1 + q2) / den; }
+    real pos[3];
+    for (int cc = 0; cc < 3; cc++) pos[cc] = (real)0.5 * ((pa[cc] + alpha * ua[cc]) + (pb[cc] + beta * ub[cc]));
+    add_contact(c, ncon, pf.g1, pf.g2, ebest, pos, nw, margin, gap);
+    return;
+  }
+  // face contact: reference face on box 1 (code < 3) or on box 2
+  const real *Rr, *Ri, *pr, *pi, *sr, *si;
+  const int ax = code < 3 ? code : code - 3;
+  if (code < 3) { Rr = R1; Ri = R2; pr = p1; pi = p2; sr = a; si = b; }
+  else { Rr = R2; Ri = R1; pr = p2; pi = p1; sr = b; si = a; }
+  const real sgn = (code < 3) ? (flip ? (real)-1 : (real)1) : (flip ? (real)1 : (real)-1);
+  const real nr[3] = {sgn * Rr[ax], sgn * Rr[3 + ax], sgn * Rr[6 + ax]};
+  int iax = 0;
+  real md = -1, isg = 1;
+  for (int k = 0; k < 3; k++) {
+    real dk = nr[0] * Ri[k] + nr[1] * Ri[3 + k] + nr[2] * Ri[6 + k];
+    if (r_abs(dk) > md) { md = r_abs(dk); iax = k; isg = dk > 0 ? (real)-1 : (real)1; }
+  }
+  const int u1 = (iax + 1) % 3, u2 = (iax + 2) % 3, r1 = (ax + 1) % 3, r2 = (ax + 2) % 3;
+  real poly[16][3], tmp[16][3];
+  int np = 4;
+  for (int v = 0; v < 4; v++) {
+    const real c0 = (v == 0 || v == 3) ? (real)1 : (real)-1, c1 = v < 2 ? (real)1 : (real)-1;
+    real e[3];
+    for (int cc = 0; cc < 3; cc++)
+      e[cc] = pi[cc] + isg * si[iax] * Ri[3 * cc + iax] + c0 * si[u1] * Ri[3 * cc + u1] + c1 * si[u2] * Ri[3 * cc + u2] - pr[cc];
+    poly[v][0] = e[0] * Rr[r1] + e[1] * Rr[3 + r1] + e[2] * Rr[6 + r1];
+    poly[v][1] = e[0] * Rr[r2] + e[1] * Rr[3 + r2] + e[2] * Rr[6 + r2];
+    poly[v][2] = dot3(e, nr) - sr[ax];
+  }
+  for (int side = 0; side < 4 && np > 0; side++) {  // Sutherland-Hodgman against the reference rectangle
+    const int cx = side >> 1;
+    const real sg = (side & 1) ? (real)-1 : (real)1, lim = cx == 0 ? sr[r1] : sr[r2];
+    int nq = 0;
+    for (int v = 0; v < np; v++) {
+      const real *A = poly[v], *B = poly[(v + 1) % np];
+      real da = lim - sg * A[cx], db = lim - sg * B[cx];
+      if (da >= 0) { copy3(tmp[nq], A); nq++; }
+      if ((da >= 0) != (db >= 0)) {
+        real f = da / (da - db);
+        for (int k = 0; k < 3; k++) tmp[nq][k] = A[k] + f * (B[k] - A[k]);
+        nq++;
+      }
+    }
+    np = nq;
+    for (int v = 0; v < np; v++) copy3(poly[v], tmp[v]);
+  }
+  real nw[3] = {nr[0], nr[1], nr[2]};
+  if (code >= 3) { nw[0] = -nw[0]; nw[1] = -nw[1]; nw[2] = -nw[2]; }  // contact normal runs from geom 1 to geom 2
+  int cnt = 0;
+  for (int v = 0; v < np && cnt < 8; v++) {
+    real dist = poly[v][2];
+    if (dist > margin) continue;
+    real pos[3];
+    for (int cc = 0; cc < 3; cc++)
+      pos[cc] = pr[cc] + poly[v][0] * Rr[3 * cc + r1] + poly[v][1] * Rr[3 * cc + r2] + (sr[ax] + (real)0.5 * dist) * nr[cc];
+    add_contact(c, ncon, pf.g1, pf.g2, dist, pos, nw, margin, gap);
+    cnt++;
+  }
+}
+// ---- plane-mesh (mjc_PlaneConvex): the deepest hull vertex plus neighbours of it in the hull's edge graph that are within
+// the margin and at least 0.3 * rbound away from the points already taken, 3 contacts at most
+RCSB_DEV_NOINLINE void plane_mesh(const Ctx& c, int& ncon, const PairFrames& pf, const real* n, real margin, real gap, real* clear_out) {
+  const RcsbModel& m = CMODEL(c);
+  const int g = pf.g2;
+  const real* verts = c.verts + 3 * m.g_vertadr[g];
+  real nd[3] = {-n[0], -n[1], -n[2]}, dl[3];
+  mulmatT3(dl, pf.R2, nd);
+  int best = 0x7fffffff;
+  real bd = (real)-1e300;
+  PFOR(i, m.g_vertnum[g]) {
+    real s = RCSB_LDG(verts + 3 * i) * dl[0] + RCSB_LDG(verts + 3 * i + 1) * dl[1] + RCSB_LDG(verts + 3 * i + 2) * dl[2];
+#if defined(RCSB_HOST_EMU) && defined(RCSB_EMU_REVERSE)
+    if (s > bd || (s == bd && i < best)) { bd = s; best = i; }
+#else
+    if (s > bd) { bd = s; best = i; }
+#endif
+  }
+  warp_argmax(bd, best);
+  real taken[3][3];
+  int count = 0;
+  const real thr = (real)0.3 * CMODEL_G(c).g_rbound0[g], thr2 = thr * thr;  // tolplanemesh
+  const int nb0 = c.vgraph ? RCSB_LDG(c.vgraph + m.g_vertadr[g] + best) : 0;
+  const int nb1 = c.vgraph ? RCSB_LDG(c.vgraph + m.g_vertadr[g] + best + 1) : 0;
+  const int* nbr = c.vgraph + m.nmeshvert + 1;
+  for (int k = -1; k < nb1 - nb0 && count < 3; k++) {
+    const int vi = k < 0 ? best : RCSB_LDG(nbr + nb0 + k);
+    real vl[3] = {RCSB_LDG(verts + 3 * vi), RCSB_LDG(verts + 3 * vi + 1), RCSB_LDG(verts + 3 * vi + 2)}, v[3], pos[3];
+    mulmat3(v, pf.R2, vl);
+    v[0] += pf.p2[0]; v[1] += pf.p2[1]; v[2] += pf.p2[2];
+    real dist = (v[0] - pf.p1[0]) * n[0] + (v[1] - pf.p1[1]) * n[1] + (v[2] - pf.p1[2]) * n[2];
+    if (dist > margin) {
+      if (k < 0) { *clear_out = dist - margin; return; }
+      continue;
+    }
+    int close = 0;
+    for (int t = 0; t < 3; t++)
+      if (t < count) {
+        real e[3] = {v[0] - taken[t][0], v[1] - taken[t][1], v[2] - taken[t][2]};
+        if (dot3(e, e) < thr2) close = 1;
+      }
+    if (close) continue;
+    for (int t = 0; t < 3; t++) if (t == count) copy3(taken[t], v);
+    count++;
+    for (int kk = 0; kk < 3; kk++) pos[kk] = v[kk] - (real)0.5 * dist * n[kk];
+    add_contact(c, ncon, pf.g1, pf.g2, dist, pos, n, margin, gap);
+  }
+}
+
 // append `value` to `list` for every lane with `hit`, preserving lane order; returns the new count (uniform)
 RCSB_DEV int compact_append(const Ctx& c, int hit, int value, int count, uint16_t* list) {
 #ifdef RCSB_HOST_EMU
@@ -1010,13 +1191,7 @@ RCSB_DEV void st_collision(const Ctx& c) {
     if (t1 == RCSB_GEOM_PLANE) {
       real n[3] = {pf.R1[2], pf.R1[5], pf.R1[8]};
       if (t2 == RCSB_GEOM_MESH) {
-        real nd[3] = {-n[0], -n[1], -n[2]}, v[3], pos[3];
-        support(c, pf.g2, pf.p2, pf.R2, nd, v);
-        real dist = (v[0] - pf.p1[0]) * n[0] + (v[1] - pf.p1[1]) * n[1] + (v[2] - pf.p1[2]) * n[2];
-        if (!(dist > margin)) {
-          for (int k = 0; k < 3; k++) pos[k] = v[k] - (real)0.5 * dist * n[k];
-          add_contact(c, ncon, pf.g1, pf.g2, dist, pos, n, margin, gap);
-        } else clear = dist - margin;
+        plane_mesh(c, ncon, pf, n, margin, gap, &clear);
       } else if (t2 == RCSB_GEOM_BOX) {
         int cnt = 0;
         real mind = (real)1e30;
@@ -1050,6 +1225,8 @@ RCSB_DEV void st_collision(const Ctx& c) {
         }
         if (cnt == 0) clear = mind - margin;
       }
+    } else if (t1 == RCSB_GEOM_BOX && t2 == RCSB_GEOM_BOX) {
+      box_box(c, ncon, pf, margin, gap, &clear);
     } else {
       real depth, dir[3], pos[3];
       // depth < 1e-12: exactly touching pair (finger pads at qpos0), not a constraint; see oracle/mj_collision.c

@@ -1,5 +1,5 @@
-// Shape-specialised kernel variant: fr3_simple_pick_up (FR3 + Franka hand + one free box), full workspace layout
-// (scenes with free bodies rest on contacts and have no reduced layout).
+// Shape-specialised kernel variant: fr3_simple_pick_up (FR3 + Franka hand + one free box), reduced workspace layout
+// (the cube resting on the floor: 4 contacts; a grasp is finished by the generic kernel in the full layout).
 #ifndef RCSB_SINGLE_TU
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -12,8 +12,8 @@
 #endif
 #define RCSB_VARIANT_NS rcsb_fr3_pickup
 #define RCSB_KERNEL rcsb_k_run_fr3_pickup
-#define RCSB_FIXED_SHAPE {16, 15, 8, 10, 25, 206, 1, 1, 2, 6, 28, 7, 1, 1, 5, 0, 1, 47}
-#define RCSB_VARIANT_WARPS 11  // what the layout leaves room for: registers per thread follow from it
+#define RCSB_FIXED_SHAPE {16, 15, 8, 10, 25, 206, 1, 1, 2, 4, 17, 7, 1, 1, 5, 1, 1, 47}
+#define RCSB_VARIANT_WARPS 12  // what the layout leaves room for: registers per thread follow from it
 #include "rcsb_variant.cuh"
 #undef RCSB_VARIANT_NS
 #undef RCSB_KERNEL

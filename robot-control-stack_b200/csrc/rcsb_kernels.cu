@@ -43,7 +43,7 @@
 #else
 #define RCSB_DECLARE_VARIANT(ns)                                                                                        \
   namespace ns {                                                                                                        \
-  void launch(int, int, size_t, cudaStream_t, const RcsbModel*, const real*, real*, double*, int*, const RcsbLaunch&, int*, size_t); \
+  void launch(int, int, size_t, cudaStream_t, const RcsbModel*, const real*, const int*, real*, double*, int*, const RcsbLaunch&, int*, size_t); \
   cudaError_t set_smem(size_t);                                                                                         \
   int max_warps();                                                                                                      \
   RcsbShape shape();                                                                                                    \
@@ -54,8 +54,8 @@ RCSB_DECLARE_VARIANT(rcsb_fr3_pickup)
 #endif
 #endif
 
-typedef void (*rcsb_launch_fn)(int, int, size_t, cudaStream_t, const RcsbModel*, const real*, real*, double*, int*, const RcsbLaunch&,
-                               int*, size_t);
+typedef void (*rcsb_launch_fn)(int, int, size_t, cudaStream_t, const RcsbModel*, const real*, const int*, real*, double*, int*,
+                               const RcsbLaunch&, int*, size_t);
 typedef cudaError_t (*rcsb_smem_fn)(size_t);
 struct RcsbVariant { const char* name; int fixed; RcsbShape shape; rcsb_launch_fn launch; rcsb_smem_fn set_smem; int max_warps; };
 static bool shape_equal(const RcsbShape& a, const RcsbShape& b) { return memcmp(&a, &b, sizeof(RcsbShape)) == 0; }
@@ -129,6 +129,8 @@ struct rcsb_model {
   bool has_reduced = false;
   RcsbModel* d_model_r = nullptr;
   std::vector<real> verts;
+  std::vector<int> vgraph;  // hull edge graph: [nmeshvert + 1] offsets, then the neighbour lists
+  int* d_vgraph = nullptr;
   bool finalized = false;
   int device = -1;
   RcsbModel* d_model = nullptr;
@@ -172,6 +174,7 @@ void rcsb_model_free(rcsb_model* m) {
   if (m->d_model) cudaFree(m->d_model);
   if (m->d_model_r) cudaFree(m->d_model_r);
   if (m->d_verts) cudaFree(m->d_verts);
+  if (m->d_vgraph) cudaFree(m->d_vgraph);
   delete m;
 }
 int rcsb_model_set_int(rcsb_model* m, const char* field, const int* v, int n) {
@@ -191,8 +194,17 @@ int rcsb_model_set_mesh_vertices(rcsb_model* m, const double* xyz, int nvert) {
   for (int i = 0; i < 3 * nvert; i++) m->verts[i] = (real)xyz[i];
   return RCSB_OK;
 }
+int rcsb_model_set_mesh_graph(rcsb_model* m, const int* adr, int nadr, const int* nbr, int nnbr) {
+  if (!m || !adr || nadr < 1 || (nnbr > 0 && !nbr)) return fail(RCSB_ERR_ARG, "bad mesh graph");
+  if (adr[0] != 0 || adr[nadr - 1] != nnbr) return fail(RCSB_ERR_SIZE, "mesh graph offsets do not match the neighbour list");
+  m->vgraph.assign(adr, adr + nadr);
+  m->vgraph.insert(m->vgraph.end(), nbr, nbr + nnbr);
+  return RCSB_OK;
+}
 int rcsb_model_finalize(rcsb_model* m) {
   if (rcsb_model_finalize_layout(&m->h) != 0) return fail(RCSB_ERR_MODEL, "model dimensions out of range");
+  if (!m->vgraph.empty() && ((int)m->vgraph.size() < m->h.nmeshvert + 1 || m->vgraph[m->h.nmeshvert] + m->h.nmeshvert + 1 != (int)m->vgraph.size()))
+    return fail(RCSB_ERR_SIZE, "mesh graph does not cover the vertex pool");
   if ((m->h.lay.nsr * sizeof(real)) % 16 != 0) return fail(RCSB_ERR_MODEL, "state row is not 16-byte granular");
   m->h.cap_reduced = 0;
   m->has_reduced = rcsb_model_make_reduced(&m->h, &m->hr) != 0;
@@ -226,6 +238,10 @@ int rcsb_model_upload(rcsb_model* m, int device) {
   if (m->verts.empty()) m->verts.resize(3);
   CUDA_OK(cudaMalloc(&m->d_verts, m->verts.size() * sizeof(real)));
   CUDA_OK(cudaMemcpy(m->d_verts, m->verts.data(), m->verts.size() * sizeof(real), cudaMemcpyHostToDevice));
+  if (!m->vgraph.empty()) {
+    CUDA_OK(cudaMalloc(&m->d_vgraph, m->vgraph.size() * sizeof(int)));
+    CUDA_OK(cudaMemcpy(m->d_vgraph, m->vgraph.data(), m->vgraph.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
   m->device = device;
   return RCSB_OK;
 }
@@ -354,13 +370,13 @@ int rcsb_batch_run(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps
   CUDA_OK(cudaMemsetAsync(b->d_counter, 0, 4 * sizeof(int), b->stream));
   L.phase = 0; L.overflow_list = b->d_overflow; L.overflow_count = b->d_counter + 2;
   const bool two = b->m->has_reduced;
-  b->var.launch(b->grid, b->warps * 32, b->smem, b->stream, two ? b->m->d_model_r : b->m->d_model, b->m->d_verts, b->sr, b->sd, b->si,
+  b->var.launch(b->grid, b->warps * 32, b->smem, b->stream, two ? b->m->d_model_r : b->m->d_model, b->m->d_verts, b->m->d_vgraph, b->sr, b->sd, b->si,
                 L, b->d_counter, b->ws_bytes);
   g_launches++;
   CUDA_OK(cudaGetLastError());
   if (two && (ops & (RCSB_OP_STEP_K | RCSB_OP_STEP_CONV))) {  // finishes the environments that outgrew the reduced layout
     L.phase = 1; L.lockstep = 0;
-    b->var_full.launch(b->grid_full, b->warps_full * 32, b->smem_full, b->stream, b->m->d_model, b->m->d_verts, b->sr, b->sd, b->si, L,
+    b->var_full.launch(b->grid_full, b->warps_full * 32, b->smem_full, b->stream, b->m->d_model, b->m->d_verts, b->m->d_vgraph, b->sr, b->sd, b->si, L,
                        b->d_counter + 1, b->ws_bytes_full);
     g_launches++;
     CUDA_OK(cudaGetLastError());

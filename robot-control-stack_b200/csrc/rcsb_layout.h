@@ -29,7 +29,7 @@ static const RcsbField rcsb_model_fields[] = {
     RCSB_FI(g_body), RCSB_FI(g_type), RCSB_FI(g_vertadr), RCSB_FI(g_vertnum), RCSB_FI(g_origid), RCSB_FI(g_role),
     RCSB_FI(g_condim), RCSB_FI(g_priority),
     RCSB_FR(g_pos), RCSB_FR(g_quat), RCSB_FR(g_bpos), RCSB_FR(g_size), RCSB_FR(g_rbound), RCSB_FR(g_aabb), RCSB_FR(g_friction),
-    RCSB_FR(g_solref), RCSB_FR(g_solimp), RCSB_FR(g_solmix), RCSB_FR(g_margin), RCSB_FR(g_gap), RCSB_FR(g_invweight),
+    RCSB_FR(g_solref), RCSB_FR(g_solimp), RCSB_FR(g_solmix), RCSB_FR(g_margin), RCSB_FR(g_gap), RCSB_FR(g_invweight), RCSB_FR(g_rbound0),
     RCSB_FB(pair),
     RCSB_FR(t_coef), RCSB_FI(e_dof1), RCSB_FI(e_dof2), RCSB_FI(e_active), RCSB_FR(e_poly), RCSB_FR(e_solref),
     RCSB_FR(e_solimp),

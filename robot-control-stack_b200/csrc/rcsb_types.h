@@ -168,6 +168,7 @@ struct RcsbModel {
   //      global-memory copy of the model (CMODEL_G), where the few hot rows stay in L1
   int cold_begin;
   int8_t grp_body[RCSB_MAXGRP][2];              // the two bodies of every collision group (-1 = world)
+  real g_rbound0[RCSB_MAXG];                    // mjModel geom_rbound (about the geom frame origin): plane-mesh point spacing
   float grp_reach[RCSB_MAXGRP][RCSB_MAXV];      // per group and dof on its tree path: upper bound, over all poses, of the
                                                 // distance between the joint anchor and any collidable point of the
                                                 // group's body that the dof moves (1 for translational dofs; 0 off the path)

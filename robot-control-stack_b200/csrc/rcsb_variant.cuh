@@ -24,7 +24,7 @@ static constexpr RcsbLayout kLay = rcsb_make_layout(kShape);
 #include "rcsb_env.cuh"
 
 #ifndef RCSB_HOST_EMU
-__device__ __forceinline__ Ctx make_ctx(const RcsbModel* sm, const RcsbModel* gm, const real* verts, size_t ws_bytes) {
+__device__ __forceinline__ Ctx make_ctx(const RcsbModel* sm, const RcsbModel* gm, const real* verts, const int* vgraph, size_t ws_bytes) {
   const RcsbModel& m = *sm;
   (void)m;
   int warp = threadIdx.x >> 5;
@@ -34,6 +34,7 @@ __device__ __forceinline__ Ctx make_ctx(const RcsbModel* sm, const RcsbModel* gm
   c.wib = c.clkb + (uint32_t)((size_t)LAY.ws_doubles * sizeof(double));
   c.gm = gm;
   c.verts = verts;
+  c.vgraph = vgraph;
   c.lane = threadIdx.x & 31;
   c.lockstep = 0;
   c.bar_id = 0; c.bar_threads = blockDim.x;
@@ -45,13 +46,13 @@ __device__ __forceinline__ Ctx make_ctx(const RcsbModel* sm, const RcsbModel* gm
 #define RCSB_VARIANT_WARPS RCSB_MAX_WARPS  // warps per CTA the variant is compiled for: fewer warps, more registers each
 #endif
 __global__ void __launch_bounds__(RCSB_VARIANT_WARPS * 32, 1)
-RCSB_KERNEL(const RcsbModel* __restrict__ gm, const real* __restrict__ verts, real* __restrict__ sr, double* __restrict__ sd,
+RCSB_KERNEL(const RcsbModel* __restrict__ gm, const real* __restrict__ verts, const int* __restrict__ vgraph, real* __restrict__ sr, double* __restrict__ sd,
            int* __restrict__ si, RcsbLaunch L, int* __restrict__ counter, size_t ws_bytes) {
   if (L.phase == 1 && *L.overflow_count == 0) return;  // the common case: nothing outgrew the reduced layout
   const RcsbModel* sm = stage_model(gm);
   const RcsbModel& m = *sm;
   (void)m;
-  Ctx c = make_ctx(sm, gm, verts, ws_bytes);
+  Ctx c = make_ctx(sm, gm, verts, vgraph, ws_bytes);
   if ((L.ops & RCSB_OP_STEP_K) && L.phase == 0) {
     // Fixed-substep launch: static env -> warp mapping. Every warp of the CTA runs the same number of rounds and
     // hits exactly L.k * RCSB_STAGE_BARRIERS CTA barriers per round (inside run_env_program, or here when it has no environment), which
@@ -129,9 +130,9 @@ RCSB_KERNEL(const RcsbModel* __restrict__ gm, const real* __restrict__ verts, re
 }
 
 
-RCSB_VARIANT_LINKAGE void launch(int grid, int threads, size_t smem, cudaStream_t stream, const RcsbModel* gm, const real* verts, real* sr,
-                   double* sd, int* si, const RcsbLaunch& L, int* counter, size_t ws_bytes) {
-  RCSB_KERNEL<<<grid, threads, smem, stream>>>(gm, verts, sr, sd, si, L, counter, ws_bytes);
+RCSB_VARIANT_LINKAGE void launch(int grid, int threads, size_t smem, cudaStream_t stream, const RcsbModel* gm, const real* verts,
+                   const int* vgraph, real* sr, double* sd, int* si, const RcsbLaunch& L, int* counter, size_t ws_bytes) {
+  RCSB_KERNEL<<<grid, threads, smem, stream>>>(gm, verts, vgraph, sr, sd, si, L, counter, ws_bytes);
 }
 RCSB_VARIANT_LINKAGE cudaError_t set_smem(size_t bytes) {
   return cudaFuncSetAttribute(RCSB_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);

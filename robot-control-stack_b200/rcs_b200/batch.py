@@ -34,6 +34,8 @@ class DeviceModel:
             else:
                 _lib.check(L.rcsb_model_set_int(self.ptr, name.encode(), _ip(a), a.size))
         _lib.check(L.rcsb_model_set_mesh_vertices(self.ptr, _dp(self.verts), len(self.verts)))
+        gadr, gnbr = devmodel.build_mesh_graph(M)
+        _lib.check(L.rcsb_model_set_mesh_graph(self.ptr, _ip(gadr), len(gadr), _ip(gnbr), int(gadr[-1])))
         _lib.check(L.rcsb_model_finalize(self.ptr))
         d = [C.c_int(0) for _ in range(5)]
         _lib.check(L.rcsb_model_dims(self.ptr, *[C.byref(x) for x in d]))

@@ -14,9 +14,14 @@ import numpy as np
 from . import mjcf
 from .mjcf import JNT_FREE, quat_mul, quat_to_mat, mat_to_quat
 
-FAST_MAXCON_DEFAULT = 1  # contact capacity of the reduced workspace layout
+FAST_MAXCON_DEFAULT = 1  # contact capacity of the reduced workspace layout (scenes without free bodies)
+FAST_MAXCON_FREE = 4     # ... of scenes with free bodies: an object resting on the floor (plane-box: 4 points)
 FAST_LIMIT_ROWS = 4      # simultaneously active joint-limit rows the reduced layout holds
-MAXCON_DEFAULT = 6  # per-env contact capacity (overflow is counted in the warn flag); Sim(maxcon=...) overrides
+# per-env contact capacity of the full layout (overflow is counted in the warn flag); Sim(maxcon=...) overrides.
+# 16: the four small pads of each finger meeting (4 box-box pairs x 4 points); 40: a grasped box (8 pad pairs x 4 points)
+# plus its 4 floor contacts
+MAXCON_DEFAULT = 16
+MAXCON_FREE = 40
 ROLE_ARM, ROLE_GRIPPER, ROLE_FINGER, ROLE_IGNORED = 1, 2, 4, 8
 
 
@@ -25,6 +30,23 @@ def _name_id(names, name, kind):
         return names.index(name)
     except ValueError:
         raise RuntimeError(f"No {kind} named {name}") from None
+
+
+def build_mesh_graph(M: dict):
+    """Hull edge graph (mjcf.mesh_graph_arrays) restricted to the device vertex pool of build_device_fields:
+    (adr[nvert + 1], nbr[...]) with neighbour ids local to each geom's hull."""
+    col = [g for g in range(M["ngeom"]) if M["geom_contype"][g] or M["geom_conaffinity"][g]]
+    used = {int(g) for pr in M["pair_geom"] for g in pr}
+    gadr, gnbr = [0], []
+    for g in (g for g in col if g in used):
+        a, k = int(M["geom_vertadr"][g]), int(M["geom_vertnum"][g])
+        for v in range(a, a + max(k, 0)):
+            if "mesh_graphadr" in M:
+                gnbr.extend(int(x) for x in M["mesh_graph"][int(M["mesh_graphadr"][v]):int(M["mesh_graphadr"][v + 1])])
+            gadr.append(len(gnbr))
+    if len(gadr) == 1:
+        gadr.append(0)  # the vertex pool holds one dummy vertex when the scene has no meshes
+    return np.array(gadr, dtype=np.int32), np.array(gnbr if gnbr else [0], dtype=np.int32)[:max(len(gnbr), 1)]
 
 
 def build_device_fields(M: dict, robot_cfg=None, gripper_cfg=None, maxcon: int | None = None,
@@ -219,6 +241,7 @@ def build_device_fields(M: dict, robot_cfg=None, gripper_cfg=None, maxcon: int |
     # bounding volume: sphere about the local AABB centre (broad phase) and the oriented AABB itself (mid phase)
     put("g_bpos", [gp + quat_to_mat(gq) @ M["geom_aabb"][g][:3] for g, gp, gq in zip(col, g_pos, g_quat)], True)
     put("g_rbound", [M["geom_bsphere"][g][3] for g in col], True)
+    put("g_rbound0", [M["geom_rbound"][g] for g in col], True)
     for f in ("size", "aabb", "friction", "solref", "solimp", "solmix", "margin", "gap"):
         put("g_" + f, [M["geom_" + f][g] for g in col], True)
     put("g_invweight", [M["body_invweight0"][M["geom_bodyid"][g]][0] for g in col], True)
@@ -314,7 +337,8 @@ def build_device_fields(M: dict, robot_cfg=None, gripper_cfg=None, maxcon: int |
             put(f, [v], True)
     put("g_role", roles, False)
     # ---- sizes / options
-    mc = int(maxcon if maxcon is not None else MAXCON_DEFAULT)
+    has_free = bool((np.asarray(M["jnt_type"]) == 0).any())
+    mc = int(maxcon if maxcon is not None else (MAXCON_FREE if has_free else MAXCON_DEFAULT))
     nlim = int(sum(F["d_limited"][0]))
     nfl = int((M["dof_frictionloss"] > 0).sum())
     rows_per_con = 3 if M["opt_cone"] == "elliptic" else 4
@@ -326,10 +350,9 @@ def build_device_fields(M: dict, robot_cfg=None, gripper_cfg=None, maxcon: int |
                  ("maxcon", mc), ("maxefc", M["neq"] + nfl + nlim + rows_per_con * mc)):
         put(f, [v], False)
     # Reduced-capacity workspace layout (rcsb_types.h: fast_maxcon): environments whose contacts / active limits fit it
-    # run at twice the warps per SM; the others are finished by a second launch in the full layout. Scenes with free
-    # bodies rest on contacts all the time, so they default to the full layout only.
-    has_free = bool((np.asarray(M["jnt_type"]) == 0).any())
-    fmc = int(fast_maxcon) if fast_maxcon is not None else (0 if has_free else FAST_MAXCON_DEFAULT)
+    # run at several times the warps per SM; the others are finished by a second launch in the full layout. Scenes with
+    # free bodies rest on contacts all the time: their reduced layout holds the resting contacts of one object.
+    fmc = int(fast_maxcon) if fast_maxcon is not None else (FAST_MAXCON_FREE if has_free else FAST_MAXCON_DEFAULT)
     fmc = min(fmc, mc)
     put("fast_maxcon", [fmc], False)
     put("fast_maxefc", [M["neq"] + nfl + min(nlim, FAST_LIMIT_ROWS) + rows_per_con * fmc if fmc > 0 else 0], False)

@@ -208,6 +208,44 @@ def convex_hull_vertices(verts):
     return hv
 
 
+def hull_edge_graph(hv):
+    """Edge graph of the convex hull of the vertex set hv (all of them hull vertices): for every vertex the ascending
+    list of vertices it shares a (triangulated) hull facet with. MuJoCo builds the same graph with its own qhull at
+    compile time and uses it for plane-mesh multi-contacts (mjc_PlaneConvex) [3P]."""
+    from scipy.spatial import ConvexHull
+
+    nbr = [set() for _ in range(len(hv))]
+    if len(hv) >= 4:
+        try:
+            hull = ConvexHull(hv, qhull_options="Qt")
+            for tri in hull.simplices:
+                for a in tri:
+                    for b in tri:
+                        if a != b:
+                            nbr[a].add(int(b))
+        except Exception:  # degenerate (flat) vertex set: no graph, single-point contacts
+            pass
+    return [sorted(x) for x in nbr]
+
+
+def mesh_graph_arrays(M):
+    """CSR form of hull_edge_graph over the pooled hull vertices: (adr[nmeshvert + 1], nbr[...] local vertex ids)."""
+    nvert = len(M["mesh_vert"])
+    adr = np.zeros(nvert + 1, dtype=np.int32)
+    out = []
+    done = {}
+    for g in range(M["ngeom"]):
+        a, k = int(M["geom_vertadr"][g]), int(M["geom_vertnum"][g])
+        if k <= 0 or a in done:
+            continue
+        done[a] = True
+        for i, lst in enumerate(hull_edge_graph(np.asarray(M["mesh_vert"][a:a + k]))):
+            adr[a + i + 1] = len(lst)
+            out.extend(lst)
+    adr = np.cumsum(adr).astype(np.int32)
+    return adr, np.array(out if out else [0], dtype=np.int32)
+
+
 # ----------------------------------------------------------------------------- defaults
 _DEFAULT_TAGS = ("joint", "geom", "site", "camera", "mesh", "material", "tendon", "equality", "general", "position",
                  "motor", "velocity", "light", "pair")
@@ -720,6 +758,7 @@ def compile_mjcf(path: str) -> dict:
             n += len(g["hull"])
     M["geom_vertadr"], M["geom_vertnum"] = vert_adr, vert_num
     M["mesh_vert"] = np.concatenate(pool, axis=0) if pool else np.zeros((0, 3))
+    M["mesh_graphadr"], M["mesh_graph"] = mesh_graph_arrays(M)
     # local AABB (centre, half-size) in the geom frame for the mid-phase box test
     aabb = np.zeros((ngeom, 6))
     for gi, g in enumerate(geoms):

@@ -28,6 +28,8 @@ int emu_nsr(const EmuModel* m) { return m->full.lay.nsr; }
 int emu_has_reduced(const EmuModel* m) { return m->has_reduced; }
 int emu_sizes(int* out) { out[0] = RCSB_S_TAIL; out[1] = RCSB_D_TAIL; out[2] = RCSB_I_TAIL; out[3] = RCSB_OBS_DIM; out[4] = RCSB_INFO_DIM; out[5] = (int)sizeof(real); return 0; }
 
+static const int* g_vgraph = nullptr;
+void emu_set_mesh_graph(const int* g) { g_vgraph = g; }
 static void run_phase(const RcsbModel* m, const real* verts, real* sr, double* sd, int* si, RcsbLaunch L, const int* envs, int n,
                       const unsigned char* mask, real* dbg_ws, int dbg_stride, int* dbg_layout) {
   std::vector<real> w(m->lay.ws_reals);
@@ -36,7 +38,7 @@ static void run_phase(const RcsbModel* m, const real* verts, real* sr, double* s
   for (int i = 0; i < n; i++) {
     int e = envs ? envs[i] : i;
     if (!envs && mask && !mask[e]) continue;
-    Ctx c = {m, w.data(), wi.data(), verts, clk, 0, 0};
+    Ctx c = {m, w.data(), wi.data(), verts, g_vgraph, clk, 0, 0};
     load_env(c, sr + (size_t)e * m->lay.nsr, sd + (size_t)e * RCSB_D_TAIL, si + (size_t)e * RCSB_I_TAIL);
     run_env_program(c, L, e);
     store_env(c, sr + (size_t)e * m->lay.nsr, sd + (size_t)e * RCSB_D_TAIL, si + (size_t)e * RCSB_I_TAIL);

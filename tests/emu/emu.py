@@ -25,7 +25,7 @@ OPS = dict(GRIPPER_RESET=1, SIM_RESET=2, ROBOT_RESET=4, ENV_RESET_FLAGS=8, ACT_J
 
 
 class Emu:
-    def __init__(self, fields, verts, N, reverse=False, use_reduced=True):
+    def __init__(self, fields, verts, N, reverse=False, use_reduced=True, graph=None):
         L = C.CDLL(build(reverse))
         self.L = L
         vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
@@ -55,6 +55,8 @@ class Emu:
         self.nsr = L.emu_nsr(self.m)
         self.N = N
         self.verts = np.ascontiguousarray(verts, dtype=np.float64)
+        # hull edge graph [nvert + 1 offsets | neighbour lists] (devmodel.build_mesh_graph); None = single-point plane-mesh
+        self.graph = None if graph is None else np.ascontiguousarray(np.concatenate([graph[0], graph[1][:graph[0][-1]]]), dtype=np.int32)
         self.sr = np.zeros((N, self.nsr))
         self.sd = np.zeros((N, self.D_TAIL))
         self.si = np.zeros((N, self.I_TAIL), dtype=np.int32)
@@ -82,6 +84,8 @@ class Emu:
             code |= OPS[o]
         aj = np.ascontiguousarray(act_joints, dtype=np.float64) if act_joints is not None else None
         ag = np.ascontiguousarray(act_gripper, dtype=np.float64) if act_gripper is not None else None
+        self.L.emu_set_mesh_graph.argtypes = [ip]
+        self.L.emu_set_mesh_graph(self.graph.ctypes.data_as(ip) if self.graph is not None else None)
         self.L.emu_set_contact_export.argtypes = [ip, ip, dp, C.c_int]
         if getattr(self, "contact_cap", 0):  # the library keeps one global export target: set it for this instance's run
             self.L.emu_set_contact_export(self.contact_n.ctypes.data_as(ip), self.contact_geom.ctypes.data_as(ip),

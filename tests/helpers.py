@@ -66,3 +66,26 @@ def xarm_robot_ns():
               attachment_site="attachment_site", base="base", tcp_offset=[0, 0, 0, 0, 0, 0, 1.0], q_home=XARM_Q_HOME,
               joint_rotational_tolerance=0.05 * np.pi / 180, seconds_between_callbacks=0.1, register_convergence_callback=True,
               ik_nq=7)
+
+
+FRANKA_HAND_TCP = [0, 0, 0.1034, 0, 0, -0.3826834323650898, 0.9238795325112867]  # Pose.cpp:11-15, normalised
+
+
+def grasp_and_lift_script(M):
+    """Grasp-and-lift on fr3_simple_pick_up as a list of (joint target [7], normalised gripper width, physics steps):
+    open, move above the cube, descend in stages, close on the cube, raise 12 cm. Joint targets come from the oracle's
+    Pin::inverse so that every implementation under test receives identical set_joint_position commands."""
+    m = O.Model(M)
+    site = O.robot_cfg(M).attachment_site
+    q = Q_HOME.copy()
+    script = [(q.copy(), 1.0, 200)]
+    for z, n in ((0.20, 500), (0.15, 250), (0.10, 250), (0.06, 250), (0.03, 250)):
+        sol, _ = O.ik_inverse(m, site, 9, [0.44, 0.1, z, 1, 0, 0, 0], q, FRANKA_HAND_TCP)
+        assert sol is not None
+        q = sol[:7].copy()
+        script.append((q.copy(), 1.0, n))
+    script.append((q.copy(), 0.0, 300))
+    sol, _ = O.ik_inverse(m, site, 9, [0.44, 0.1, 0.15, 1, 0, 0, 0], q, FRANKA_HAND_TCP)
+    assert sol is not None
+    script.append((sol[:7].copy(), 0.0, 500))
+    return script

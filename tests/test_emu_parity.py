@@ -10,6 +10,10 @@ from helpers import O
 from rcs_b200 import devmodel
 from emu.emu import Emu
 
+def _emu(M, F, verts, N, **kw):
+    return Emu(F, verts, N, graph=devmodel.build_mesh_graph(M), **kw)
+
+
 RESET = ["GRIPPER_RESET", "SIM_RESET", "ROBOT_RESET", "ENV_RESET_FLAGS", "STEP_K", "OBS"]
 
 
@@ -23,7 +27,7 @@ def fr3():
 def test_single_step_random_states(fr3):
     M, F, verts = fr3
     N = 64
-    e = Emu(F, verts, N)
+    e = _emu(M, F, verts, N)
     rng = np.random.default_rng(1)
     q = np.zeros((N, 9)); v = np.zeros((N, 9)); ctrl = np.zeros((N, 8))
     q[:, :7] = H.Q_HOME + rng.uniform(-0.4, 0.4, (N, 7)); q[:, 7] = q[:, 8] = rng.uniform(0.001, 0.039, N)
@@ -51,7 +55,7 @@ def test_workload_trajectory_and_lane_order_independence(fr3):
                                   want_obs=True)
     outs = []
     for rev in (False, True):
-        e = Emu(F, verts, N, reverse=rev)
+        e = _emu(M, F, verts, N, reverse=rev)
         e.run(RESET, k=1)
         traj = []
         for t in range(T):
@@ -78,7 +82,7 @@ def test_floor_collision_contact_indexing_exact(fr3):
     import os
     M, F, verts = fr3
     G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "step_vectors.npz"))
-    e = Emu(F, verts, 1)
+    e = _emu(M, F, verts, 1)
     e.enable_contact_export(cap=8)
     mm, s = H.oracle_sim(M)
     tgt = np.array([0, 1.78, 0, -1.45, 0, 0, 0.0])
@@ -111,7 +115,7 @@ def test_step_until_convergence_counts(fr3):
     rng = np.random.default_rng(3)
     N = 4
     tg = H.Q_HOME + rng.uniform(-0.15, 0.15, (N, 7))
-    e = Emu(F, verts, N)
+    e = _emu(M, F, verts, N)
     e.run(RESET[:-1], k=1)
     e.run(["SET_JOINTS", "STEP_CONV"], act_joints=tg, max_conv=500)
     for i in range(N):
@@ -128,7 +132,7 @@ def test_pick_up_scene_cube_contacts(fr3):
     """fr3_simple_pick_up: free joint, box-plane contacts, elliptic cones + noslip in the device code."""
     M = H.scene("fr3_simple_pick_up")
     F, verts = devmodel.build_device_fields(M, H.robot_ns(), H.gripper_ns())
-    e = Emu(F, verts, 1)
+    e = _emu(M, F, verts, 1)
     m = O.Model(M)
     d = O.Data(m)
     q0 = M["qpos0"].copy(); q0[:7] = H.Q_HOME
@@ -151,7 +155,7 @@ def test_reduced_layout_hand_over_is_bit_exact(fr3):
     tgt[1] = H.Q_HOME + 0.1                                          # this one never touches anything
     outs = []
     for use_reduced in (True, False):
-        e = Emu(F, verts, 3, use_reduced=use_reduced)
+        e = _emu(M, F, verts, 3, use_reduced=use_reduced)
         assert e.has_reduced == use_reduced
         e.run(RESET[:-1], k=1)
         e.run(["SET_JOINTS"], act_joints=tgt)
@@ -176,7 +180,7 @@ def test_separation_budgets_detect_contact_on_the_same_step(fr3):
     M, F, verts = fr3
     tgt = np.array([0, 1.78, 0, -1.45, 0, 0, 0.0])
     for k in (150, 230, 300, 420):
-        e = Emu(F, verts, 1)
+        e = _emu(M, F, verts, 1)
         mm, s = H.oracle_sim(M)
         e.run(RESET[:-1], k=1); s.gripper_reset(); s.reset(); s.robot_reset(); s.step(1)
         e.run(["SET_JOINTS", "STEP_K"], k=k, act_joints=tgt[None]); s.set_joint_position(tgt); s.step(k)
@@ -191,7 +195,7 @@ def test_xarm7_friction_loss_rows_and_cylinder(fr3):
     M = H.scene("xarm7_empty_world")
     F, verts = devmodel.build_device_fields(M, H.xarm_robot_ns(), None)
     N = 16
-    e = Emu(F, verts, N)
+    e = _emu(M, F, verts, N)
     rng = np.random.default_rng(11)
     q = H.XARM_Q_HOME + rng.uniform(-0.3, 0.3, (N, 7))
     v = rng.uniform(-0.5, 0.5, (N, 7)); v[::3] = 0  # zero velocity: friction rows in their quadratic (sticking) zone
@@ -208,3 +212,32 @@ def test_xarm7_friction_loss_rows_and_cylinder(fr3):
             assert int(e.si[i, 15]) == int(d.nefc[0]) >= 7
             assert np.abs(e.sr[i, 0:7] - d.qpos).max() < 1e-9, (it, i)
             assert np.abs(e.sr[i, 7:14] - d.qvel).max() < 1e-7, (it, i)
+
+
+def test_grasp_and_lift_contacts_and_state():
+    """fr3_simple_pick_up, config C3's defining behaviour: close the gripper on the cube and raise it 12 cm. The finger pads
+    and the cube are boxes (fr3_0.xml:146-150, fr3_simple_pick_up/scene.xml:31): box-box face clipping gives 4 points per
+    small pad (36 contacts with the 4 floor points), elliptic cones + noslip. Contact count, geom pair ids and order are
+    compared exactly with the oracle at every sample, the state to 1e-6, and the cube must end up lifted."""
+    M = H.scene("fr3_simple_pick_up")
+    F, verts = devmodel.build_device_fields(M, H.robot_ns(H.FRANKA_HAND_TCP), H.gripper_ns())
+    e = _emu(M, F, verts, 1)
+    e.enable_contact_export(cap=40)
+    m, s = H.oracle_sim(M, tcp=H.FRANKA_HAND_TCP)
+    e.run(RESET[:-1], k=1); s.gripper_reset(); s.reset(); s.robot_reset(); s.step(1)
+    peak, worst = 0, 0.0
+    for qt, w, n in H.grasp_and_lift_script(M):
+        e.run(["SET_JOINTS", "SET_GRIPPER"], act_joints=qt[None], act_gripper=np.array([w]))
+        s.set_joint_position(qt); s.gripper_set_normalized_width(w)
+        for _ in range(n // 50):
+            e.run(["STEP_K"], k=50); s.step(50)
+            ncon = int(s.data.ncon[0])
+            peak = max(peak, ncon)
+            assert int(e.contact_n[0]) == ncon == int(e.si[0, 14])
+            assert np.array_equal(e.contact_geom[0, :ncon], s.data.int("contact_geom").reshape(-1, 2))
+            worst = max(worst, np.abs(e.sr[0, :16] - s.data.qpos).max())
+            assert np.abs(e.sr[0, :16] - s.data.qpos).max() < 1e-6
+            assert int(e.si[0, 17]) == 0  # RCSB_I_WARN: nothing dropped
+    print("grasp: peak ncon", peak, "worst |dq|", worst)
+    assert peak >= 30, peak
+    assert s.data.qpos[11] > 0.12 and e.sr[0, 11] > 0.12  # the cube went up with the gripper

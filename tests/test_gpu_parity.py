@@ -352,3 +352,46 @@ def test_kernels_match_committed_step_vectors(setup):
         b.run(_lib.STEP_K, k=5)
         assert int(b.si[0, 14]) == int(G["floor_ncon"][it]), it
         assert np.abs(b.qpos[0].cpu().numpy() - G["floor_qpos"][it]).max() < 1e-6, it
+
+
+def test_grasp_and_lift_parity(setup):
+    """Config C3's defining behaviour on the GPU: close the gripper on the cube of fr3_simple_pick_up and raise it 12 cm
+    (>= 2000 physics steps). Finger pads and cube are boxes: box-box face clipping gives 4 points per small pad (36
+    contacts with the 4 floor points), elliptic cones + noslip, the reduced layout (4 resting contacts) hands the grasp
+    over to the full layout. Against the oracle at every sample: contact count, geom pair ids and order exact, state to
+    1e-6, gripper width / is_grasped / collision flags equal; nothing may be dropped (RCSB_I_WARN == 0)."""
+    _, _, _lib, batch = setup
+    M = H.scene("fr3_simple_pick_up")
+    dm = batch.DeviceModel(M, H.robot_ns(H.FRANKA_HAND_TCP), H.gripper_ns())
+    N = 3
+    b = batch.Batch(dm, N)
+    occ = b.occupancy()
+    assert occ["variant"] == "fr3_pickup", occ
+    b.enable_contact_export(cap=40)
+    m, s = H.oracle_sim(M, tcp=H.FRANKA_HAND_TCP)
+    reset = _lib.GRIPPER_RESET | _lib.SIM_RESET | _lib.ROBOT_RESET | _lib.ENV_RESET_FLAGS | _lib.STEP_K
+    b.run(reset, k=1); s.gripper_reset(); s.reset(); s.robot_reset(); s.step(1)
+    peak, worst = 0, 0.0
+    for qt, w, n in H.grasp_and_lift_script(M):
+        b.run(_lib.SET_JOINTS | _lib.SET_GRIPPER, act_joints=torch.as_tensor(np.tile(qt, (N, 1)), device=b.dev),
+              act_gripper=torch.full((N,), w, dtype=torch.float64, device=b.dev))
+        s.set_joint_position(qt); s.gripper_set_normalized_width(w)
+        for _ in range(n // 50):
+            b.run(_lib.STEP_K | _lib.OBS, k=50, want_obs=True); s.step(50)
+            ncon = int(s.data.ncon[0])
+            peak = max(peak, ncon)
+            cn, cg = b.contact_n.cpu().numpy(), b.contact_geom.cpu().numpy()
+            q, si, obs, info = b.qpos.cpu().numpy(), b.si.cpu().numpy(), b.obs.cpu().numpy(), b.info.cpu().numpy()
+            ref_pairs = s.data.int("contact_geom").reshape(-1, 2)
+            for e in range(N):
+                assert cn[e] == ncon == si[e, 14]
+                assert np.array_equal(cg[e, :ncon], ref_pairs)
+                assert si[e, 17] == 0
+                assert abs(obs[e, 21] - s.gripper_get_normalized_width()) < 1e-6
+                assert bool(info[e, 3]) == s.gripper_is_grasped()
+            worst = max(worst, np.abs(q - s.data.qpos).max())
+            assert np.abs(q - s.data.qpos).max() < 1e-6
+    print("grasp: peak ncon", peak, "worst |dq|", worst)
+    assert peak >= 30
+    assert s.data.qpos[11] > 0.12 and (b.qpos[:, 11] > 0.12).all()
+    assert s.gripper_is_grasped()
