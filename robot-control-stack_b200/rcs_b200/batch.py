@@ -115,7 +115,12 @@ class Batch:
 
     def run(self, ops: int, k: int = 0, max_convergence_steps: int = 500, act_joints: torch.Tensor | None = None,
             act_gripper: torch.Tensor | None = None, mask: torch.Tensor | None = None, max_mov: float = 0.0,
-            jlow=None, jhigh=None, want_obs: bool = False):
+            jlow=None, jhigh=None, want_obs: bool = False, fresh_obs: bool = False):
+        """fresh_obs: pack the observation / info into newly allocated tensors (self.obs / self.info are rebound to
+        them), so that results returned to a caller are never overwritten by a later launch."""
+        if want_obs and fresh_obs:
+            self.obs = torch.empty_like(self.obs)
+            self.info = torch.empty_like(self.info)
         for t in (act_joints, act_gripper):
             if t is not None:
                 assert t.dtype == torch.float64 and t.is_contiguous() and t.device == self.dev

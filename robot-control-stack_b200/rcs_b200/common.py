@@ -167,29 +167,39 @@ class Pose:
     def __init__(self, *args, pose_matrix=None, rotation=None, translation=None, quaternion=None, rpy=None,
                  rpy_vector=None, pose=None):
         t, q, normalize = np.zeros(3), IdentityRotQuatVec(), True
-        if args:
+        if args:  # positional overloads of rcs.cpp:224-237 / Pose.cpp:24-100
             a = args[0]
+            second = np.asarray(args[1], dtype=np.float64) if len(args) > 1 else None
             if isinstance(a, Pose):
                 pose = a
+            elif isinstance(a, RPY):
+                rpy, translation = a, second
             else:
                 a = np.asarray(a, dtype=np.float64)
                 if a.shape == (4, 4):
                     pose_matrix = a
                 elif a.shape == (3, 3):
-                    rotation = a
+                    rotation, translation = a, second
                 elif a.shape == (4,):
-                    quaternion = a
+                    quaternion, translation = a, second
+                elif a.shape == (3,) and second is not None:
+                    rpy_vector, translation = a, second  # Pose(Vector3d rotation, Vector3d translation): rpy first
                 elif a.shape == (3,):
                     translation = a
                 else:
                     raise TypeError("unsupported positional argument for Pose")
-                if len(args) > 1:
-                    translation = np.asarray(args[1], dtype=np.float64)
         if pose is not None:
             t, q, normalize = pose._t.copy(), pose._q.copy(), False
         elif pose_matrix is not None:
             m = np.asarray(pose_matrix, dtype=np.float64)
-            t, q = m[:3, 3].copy(), _q_from_mat(m[:3, :3])
+            # Eigen's Affine3d::rotation() is the polar factor of the linear part (SVD), Pose.cpp:24-38: matters for
+            # rounded matrices such as FrankaHandTCPOffset (0.707 entries)
+            u, _, vt = np.linalg.svd(m[:3, :3])
+            r = u @ vt
+            if np.linalg.det(r) < 0:
+                u[:, -1] = -u[:, -1]
+                r = u @ vt
+            t, q = m[:3, 3].copy(), _q_from_mat(r)
         else:
             if translation is not None:
                 t = np.asarray(translation, dtype=np.float64).reshape(3).copy()

@@ -106,7 +106,7 @@ class SimVectorEnv:
         ops = _lib.SIM_RESET | _lib.ROBOT_RESET | _lib.ENV_RESET_FLAGS | _lib.STEP_K | _lib.OBS
         if self.gripper is not None:
             ops |= _lib.GRIPPER_RESET
-        b.run(ops, k=1, want_obs=True)
+        b.run(ops, k=1, want_obs=True, fresh_obs=True)
         obs, info, _ = self._pack()
         if self.relative and self.relative_to == RelativeTo.CONFIGURED_ORIGIN:  # base.py:462-467
             self._origin = obs["joints"].clone()
@@ -146,9 +146,9 @@ class SimVectorEnv:
             ag = action["gripper"].to(device=self.dev, dtype=torch.float64).reshape(-1).contiguous()
         b.run(ops, k=self._substeps(), max_convergence_steps=cfg.max_convergence_steps, act_joints=aj, act_gripper=ag,
               max_mov=float(self.max_mov) if (self.relative and self.control_mode == ControlMode.JOINTS) else 0.0,
-              jlow=self.jlow, jhigh=self.jhigh, want_obs=True)
-        obs, info, truncated = self._pack()
-        return obs, self._zeros, self._false, truncated, info
+              jlow=self.jlow, jhigh=self.jhigh, want_obs=True, fresh_obs=True)
+        obs, info, truncated = self._pack()  # views of tensors allocated for this step: never overwritten later
+        return obs, torch.zeros_like(self._zeros), torch.zeros_like(self._false), truncated, info
 
     def _to_pose7(self, a: torch.Tensor) -> torch.Tensor:
         a = a.to(device=self.dev, dtype=torch.float64)
@@ -164,8 +164,11 @@ class SimVectorEnv:
     # ------------------------------------------------------------------ host-buffer path (what a CPU-side policy sees)
     def step_host(self, joints_host: torch.Tensor, gripper_host: torch.Tensor | None):
         """Same step through pinned HOST buffers: H2D of the actions, the fused launch, D2H of obs/info and a
-        stream synchronise all happen inside the call. Returns (obs_host [N,22], info_host [N,8]) pinned tensors."""
+        stream synchronise all happen inside the call. Returns (obs_host [N,22], info_host [N,8]) pinned tensors that
+        the NEXT step_host call overwrites (they are the staging buffers themselves: copy what must outlive a step)."""
         b = self.sim.batch
+        if self.control_mode != ControlMode.JOINTS or (self.relative and self.relative_to != RelativeTo.LAST_STEP):
+            raise NotImplementedError("step_host covers joint control (absolute or relative to the last step)")
         if self._h_obs is None:
             self._h_obs = torch.zeros((self.num_envs, b.model.obs_dim), dtype=torch.float64).pin_memory()
             self._h_info = torch.zeros((self.num_envs, b.model.info_dim), dtype=torch.int32).pin_memory()

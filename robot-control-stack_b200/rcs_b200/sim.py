@@ -410,6 +410,21 @@ class SimGripper(common.Gripper):
         pass
 
 
+def _pose7_mul_const(p: torch.Tensor, c7) -> torch.Tensor:
+    """[N, 7] poses (xyz + quat xyzw) times one constant pose, Pose.cpp:173-178 semantics (result quaternion normalised)."""
+    c = torch.as_tensor(np.asarray(c7, dtype=np.float64), device=p.device)
+    x, y, z, w = p[:, 3], p[:, 4], p[:, 5], p[:, 6]
+    qv = p[:, 3:6]
+    t = c[:3].expand_as(qv)
+    uv = 2 * torch.linalg.cross(qv, t)
+    rot = t + w[:, None] * uv + torch.linalg.cross(qv, uv)
+    cx, cy, cz, cw = c[3], c[4], c[5], c[6]
+    q = torch.stack([w * cx + x * cw + y * cz - z * cy, w * cy + y * cw + z * cx - x * cz,
+                     w * cz + z * cw + x * cy - y * cx, w * cw - x * cx - y * cy - z * cz], dim=1)
+    q = q / q.norm(dim=1, keepdim=True)
+    return torch.cat([p[:, :3] + rot, q], dim=1)
+
+
 class Pin(common.Kinematics):
     """`rcs.common.Pin(path, frame_id, urdf)` (/root/reference/src/rcs/Kinematics.cpp:13-81) on the batched
     DLS-CLIK kernel. The kinematic model is the robot of the scene the Sim was built from (the reference's
@@ -431,14 +446,21 @@ class Pin(common.Kinematics):
     def inverse(self, pose, q0, tcp_offset: common.Pose = None):
         b = self._need()
         n = b.n
+        # Kinematics::inverse(pose, q0, tcp_offset = Identity) drives the frame to pose * tcp_offset^-1
+        # (Kinematics.cpp:28-40); the kernel applies the robot config's baked tcp_offset instead, so the goal is
+        # re-expressed as pose * tcp_offset^-1 * cfg_tcp whenever the two differ
         cfg_tcp = self._sim._robot_cfg.tcp_offset
-        if tcp_offset is not None and not tcp_offset.is_close(cfg_tcp, 1e-12, 1e-12):
-            # the device model bakes the robot's tcp_offset; re-express the goal for a different offset
-            pose = pose * tcp_offset.inverse() * cfg_tcp
+        call_tcp = tcp_offset if tcp_offset is not None else common.Pose()
+        fix = None if call_tcp.is_close(cfg_tcp, 1e-12, 1e-12) else call_tcp.inverse() * cfg_tcp
         if isinstance(pose, common.Pose):
+            if fix is not None:
+                pose = pose * fix
             p = torch.as_tensor(pose.as7(), device=b.dev).unsqueeze(0).expand(n, -1).contiguous()
         else:
-            p = pose.to(device=b.dev, dtype=torch.float64).contiguous()
+            p = pose.to(device=b.dev, dtype=torch.float64)
+            if fix is not None:
+                p = _pose7_mul_const(p, fix.as7())
+            p = p.contiguous()
         nj = b.model.njoints
         q0t = torch.as_tensor(np.asarray(q0, dtype=np.float64), device=b.dev) if not isinstance(q0, torch.Tensor) else q0
         if q0t.dim() == 1:

@@ -272,3 +272,31 @@ def test_configured_origin_and_continuous_gripper():
         assert torch.allclose(b.ctrl[:, 7], width * 255)
     # continuous mode: the observation is the measured normalised width, not the last command
     assert torch.equal(obs["gripper"], info["gripper_width"]) and float(obs["gripper"].min()) >= 0
+
+
+def test_pin_inverse_default_tcp_offset_is_identity_with_a_configured_tcp():
+    """Kinematics::inverse(pose, q0, tcp_offset = Identity) (rcs.cpp:289-300): with a robot configured with
+    FrankaHandTCPOffset, get_ik().inverse(p, q0) must drive the attachment frame to p itself (forward(inverse(p)) == p),
+    and inverse(p, q0, cfg_tcp) must equal what set_cartesian_position uses; tensor poses take the same path."""
+    import rcs_b200
+    from rcs_b200 import common, sim
+    from helpers import O
+    import helpers as H
+    s = sim.Sim(rcs_b200.scenes["fr3_empty_world"].mjb, sim.SimConfig(async_control=True), num_envs=4)
+    cfg = sim.SimRobotConfig(); cfg.add_id("0")
+    cfg.tcp_offset = common.Pose(pose_matrix=common.FrankaHandTCPOffset())
+    ik = sim.Pin()
+    robot = sim.SimRobot(s, ik, cfg)
+    M = H.scene()
+    m = O.Model(M); site = O.robot_cfg(M).attachment_site
+    qt = H.Q_HOME + np.array([0.1, -0.1, 0.05, 0.1, -0.05, 0.1, 0.0])
+    flange = O.ik_forward(m, site, 9, qt)                       # pose of the attachment frame at qt
+    goal = common.Pose(translation=flange[:3], quaternion=flange[3:])
+    q = robot.get_ik().inverse(torch.as_tensor(np.tile(goal.as7(), (4, 1))), H.Q_HOME)[0][0].cpu().numpy()
+    qr, _ = O.ik_inverse(m, site, 9, goal.as7(), H.Q_HOME)      # oracle, identity tcp
+    assert np.abs(q - qr).max() < 1e-9
+    assert robot.get_ik().forward(q[:7]).is_close(goal, 1e-3, 1e-3)
+    # explicit tcp_offset equal to the configured one: the goal is the TCP pose
+    tcp_goal = goal * cfg.tcp_offset
+    q2 = robot.get_ik().inverse(torch.as_tensor(np.tile(tcp_goal.as7(), (4, 1))), H.Q_HOME, cfg.tcp_offset)[0][0].cpu().numpy()
+    assert np.abs(q2 - qr).max() < 1e-7

@@ -93,3 +93,35 @@ def test_fk_home_matches_reference_home_matrix():
     p = common.Pose(translation=flange[:3], quaternion=flange[3:]) * tcp
     assert np.abs(p.translation() - HOME_M[:3, 3]).max() < 2e-3
     assert p.is_close(common.Pose(pose_matrix=HOME_M), eps_r=5e-3, eps_t=5e-3)
+
+
+def test_positional_constructor_overloads_follow_the_pybind_signatures():
+    """rcs.cpp:224-237 / Pose.cpp:24-100: Pose(vec3, vec3) is (rpy_vector, translation); RPY instances are accepted."""
+    rpy, t = np.array([0.1, -0.4, 1.2]), np.array([0.3, 0.2, 0.1])
+    ref = common.Pose(translation=t, rpy_vector=rpy)
+    assert common.Pose(rpy, t).is_close(ref, 1e-14, 1e-14)
+    assert common.Pose(common.RPY(*rpy), t).is_close(ref, 1e-14, 1e-14)
+    assert common.Pose(common.RPY(*rpy)).is_close(common.Pose(rpy_vector=rpy), 1e-14, 1e-14)
+    assert np.allclose(common.Pose(t).translation(), t) and np.allclose(common.Pose(t).rotation_q(), [0, 0, 0, 1])
+    q = ref.rotation_q()
+    assert common.Pose(q, t).is_close(ref, 1e-14, 1e-14) and common.Pose(ref.rotation_m(), t).is_close(ref, 1e-12, 1e-14)
+
+
+def test_pose_matrix_uses_the_polar_rotation_like_eigen_affine():
+    """FrankaHandTCPOffset carries 0.707 entries (Pose.cpp:11-15): Eigen's Affine3d::rotation() returns the polar factor,
+    i.e. exactly Rz(-45 deg); the oracle's tcp constant is that rotation."""
+    p = common.Pose(pose_matrix=common.FrankaHandTCPOffset())
+    assert np.allclose(p.rotation_q(), [0, 0, -np.sin(np.pi / 8), np.cos(np.pi / 8)], atol=1e-15)
+    assert np.allclose(p.as7(), H.FRANKA_HAND_TCP, atol=1e-15)
+
+
+def test_log3_closed_form_including_near_pi():
+    """pinocchio::log3 as restated for the IK: w = theta * axis for rotations of any angle, near pi included."""
+    def rod(ax, th):
+        ax = np.asarray(ax, float) / np.linalg.norm(ax)
+        K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K, ax * th
+    for th in (1e-6, 1e-3, 0.5, 2.0, np.pi - 0.02, np.pi - 5e-3, np.pi - 5e-5):
+        for ax in ((0.6, 0.8, 0.0), (0.3, -0.5, 0.8), (-1, 2, 3)):
+            R, w = rod(ax, th)
+            assert np.abs(O.log3(R) - w).max() < 1e-10, (th, ax)
