@@ -91,6 +91,13 @@ int rcsb_batch_run_host(rcsb_batch* b, unsigned ops, int k, int max_convergence_
                         const double* act_gripper_host, double max_mov, const double* jlow, const double* jhigh,
                         double* obs_host, int* info_host);
 
+/* One env.step() of every environment through ONE packed host block each way: act_host [n_envs][njoints + 1] (joint
+ * action, then the gripper action; pinned) -> H2D, the fused launch (`ops` as for rcsb_batch_run, RCSB_RUN_OBS implied),
+ * D2H of obs_host [n_envs][obs_dim] -- the observation row carries the info flags as reals in its last 8 columns --
+ * and a stream synchronise. Replaces the host round trip of SimEnvCreator's env.step (python/rcs/envs/sim.py:49-66). */
+int rcsb_env_step_host(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps, const double* act_host, double max_mov,
+                       const double* jlow, const double* jhigh, double* obs_host);
+
 /* thin aliases with the reference's method names (all envs) */
 int rcsb_sim_step(rcsb_batch* b, int k);                          /* Sim::step                 sim.cpp:108 */
 int rcsb_sim_step_until_convergence(rcsb_batch* b, int max_steps); /* Sim::step_until_convergence sim.cpp:84 */

@@ -1074,9 +1074,9 @@ RCSB_DEV void budget_advance(const Ctx& c) {
   float* bud = (float*)WR(cbud);
   const real h = m.timestep;
   PFOR(g, MD(ngrp)) {
-    const float* reach = CMODEL_G(c).grp_reach[g];  // zero off the tree path between the group's bodies
+    const float* reach = m.grp_reach[g];  // zero off the tree path between the group's bodies
     real s = 0;
-    for (int j = 0; j < MD(nv); j++) s += r_abs(WR(v)[j]) * (real)RCSB_LDG(reach + j);
+    for (int j = 0; j < MD(nv); j++) s += r_abs(WR(v)[j]) * (real)reach[j];
     bud[g] -= (float)(h * s * (real)1.000001) + 1e-6f;
   }
 }
@@ -1230,12 +1230,13 @@ RCSB_DEV void st_collision(const Ctx& c) {
     } else {
       real depth, dir[3], pos[3];
       // depth < 1e-12: exactly touching pair (finger pads at qpos0), not a constraint; see oracle/mj_collision.c
-      // Separating-direction cache (4 direct-mapped slots, lives for the launch): a direction that separated the pair
-      // on an earlier substep is re-checked with one support pair; disjoint pairs stay disjoint for many substeps
-      // (link5 / link7 overlap in their boxes in every pose), so the full query runs about once per env.step().
-      real* sc = WR(sepcache) + 4 * (p & 1);
+      // Separating-direction cache (RCSB_SEPSLOTS direct-mapped slots in the persistent state row): a direction that
+      // separated the pair on an earlier step is re-checked with one support pair; disjoint pairs stay disjoint for many
+      // steps (link5 / link7 overlap in their boxes in every pose), so the full query only runs when a cached direction
+      // stops separating.
+      real* sc = WR(sepcache) + 4 * (p & (RCSB_SEPSLOTS - 1));
       int skip = 0;
-      if (sc[0] == (real)p) {
+      if (sc[0] == (real)(p + 1)) {
         Sup& s = ((Sup*)WR(sup))[4];
         mink_support(c, pf, sc + 1, s);
         skip = dot3(s.v, sc + 1) <= 0;
@@ -1249,8 +1250,8 @@ RCSB_DEV void st_collision(const Ctx& c) {
         if (hit && depth >= (real)1e-12) add_contact(c, ncon, pf.g1, pf.g2, -depth, pos, dir, margin, gap);
         RCSB_SYNC();
         if (c.lane == 0) {
-          if (!hit && sep[3] != 0) { sc[0] = (real)p; sc[1] = sep[0]; sc[2] = sep[1]; sc[3] = sep[2]; }
-          else if (sc[0] == (real)p) sc[0] = -1;
+          if (!hit && sep[3] != 0) { sc[0] = (real)(p + 1); sc[1] = sep[0]; sc[2] = sep[1]; sc[3] = sep[2]; }
+          else if (sc[0] == (real)(p + 1)) sc[0] = 0;
         }
         RCSB_SYNC();
       }

@@ -114,7 +114,6 @@ RCSB_DEV void load_env(const Ctx& c, const real* sr, const double* sd, const int
   PFOR(i, RCSB_D_TAIL) { CCLK(c)[i] = sd[i]; }
   PFOR(i, RCSB_I_TAIL) { CWI(c)[LAY.oi_misc + MI_COUNT + i] = si[i]; }
   PFOR(i, MI_COUNT) { CWI(c)[LAY.oi_misc + i] = 0; }
-  PFOR(i, 2) { WR(sepcache)[4 * i] = -1; }
   {  // separation budgets are valid only for the qpos they were advanced to
     int same = 1;
     PFOR(i, MD(nq)) { if (!(WR(q)[i] == WR(cbq)[i])) same = 0; }
@@ -162,7 +161,7 @@ RCSB_DEV void op_set_gripper(const Ctx& c, real width) {  // SimGripper.cpp:79-9
 RCSB_DEV void op_gripper_action(const Ctx& c, const RcsbLaunch& L, int env) {
   const RcsbModel& m = CMODEL(c);
   if (!(L.ops & (RCSB_OP_ACT_GRIPPER_BIN | RCSB_OP_ACT_GRIPPER_CONT)) || !MD(gr_enabled)) return;
-  real g = L.act_gripper[env];
+  real g = L.act_gripper[(size_t)env * L.act_gstride];
   if (L.ops & RCSB_OP_ACT_GRIPPER_BIN) g = rint(g);
   g = g < 0 ? (real)0 : (g > 1 ? (real)1 : g);
   op_set_gripper(c, (L.ops & RCSB_OP_ACT_GRIPPER_BIN) ? (g == 0 ? (real)0 : (real)1) : g);
@@ -197,7 +196,7 @@ RCSB_DEV void run_env_pre_ops(const Ctx& c, const RcsbLaunch& L, int env) {
   }
   if (ops & RCSB_OP_SET_JOINTS_HARD) {
     PFOR(i, MD(rb_njoints)) {
-      real v = L.act_joints[(size_t)env * MD(rb_njoints) + i];
+      real v = L.act_joints[(size_t)env * L.act_jstride + i];
       WR(q)[m.rb_qadr[i]] = v; WR(ctrl)[m.rb_act[i]] = v;
     }
     RCSB_SYNC();
@@ -205,7 +204,7 @@ RCSB_DEV void run_env_pre_ops(const Ctx& c, const RcsbLaunch& L, int env) {
   if (ops & (RCSB_OP_ACT_JOINTS_REL | RCSB_OP_ACT_JOINTS_ABS)) {
     real* jt = WR(tmp);
     PFOR(i, MD(rb_njoints)) {
-      real a = L.act_joints[(size_t)env * MD(rb_njoints) + i];
+      real a = L.act_joints[(size_t)env * L.act_jstride + i];
       if (ops & RCSB_OP_ACT_JOINTS_REL) {  // base.py:475-488
         real lim = a < -L.max_mov ? -L.max_mov : (a > L.max_mov ? L.max_mov : a);
         real v = WR(q)[m.rb_qadr[i]] + lim;
@@ -226,8 +225,8 @@ RCSB_DEV void run_env_pre_ops(const Ctx& c, const RcsbLaunch& L, int env) {
   } else {
     op_gripper_action(c, L, env);
   }
-  if (ops & RCSB_OP_SET_JOINTS) op_set_joint_position(c, L.act_joints + (size_t)env * MD(rb_njoints));
-  if ((ops & RCSB_OP_SET_GRIPPER) && MD(gr_enabled)) op_set_gripper(c, L.act_gripper[env]);
+  if (ops & RCSB_OP_SET_JOINTS) op_set_joint_position(c, L.act_joints + (size_t)env * L.act_jstride);
+  if ((ops & RCSB_OP_SET_GRIPPER) && MD(gr_enabled)) op_set_gripper(c, L.act_gripper[(size_t)env * L.act_gstride]);
 }
 // CTA barriers a lockstep warp owes for `nsteps` physics steps it does not run
 RCSB_DEV void skip_step_barriers(const Ctx& c, int nsteps) {
@@ -311,26 +310,28 @@ RCSB_DEV void run_env_program(const Ctx& c, const RcsbLaunch& L, int env) {
   if ((ops & RCSB_OP_OBS) && c.lane == 0) {
     real pose[7];
     robot_cartesian_position(c, pose);
+    const real gw = MD(gr_enabled) ? gripper_width(c) : (real)0;
+    const int rc = RI(RCSB_I_COLLISION), gc = MD(gr_enabled) ? RI(RCSB_I_G_COLLISION) : 0;
+    int f[RCSB_INFO_DIM];
+    f[0] = rc || gc;                       // envs/sim.py:61,127-128
+    f[1] = RI(RCSB_I_IK_SUCCESS);
+    f[2] = RI(RCSB_I_CONVERGED);
+    f[3] = gw > (real)0.01 && gw < (real)0.99;  // envs/sim.py:130
+    f[4] = rc || !RI(RCSB_I_IK_SUCCESS);   // truncated, envs/sim.py:66
+    f[5] = rc; f[6] = gc;
+    f[7] = RI(RCSB_I_CONV_STEPS);
     if (L.obs) {
       real* o = L.obs + (size_t)env * RCSB_OBS_DIM;
       for (int i = 0; i < 7; i++) o[i] = pose[i];
       for (int i = 0; i < 7; i++) o[7 + i] = i < MD(rb_njoints) ? WR(q)[m.rb_qadr[i]] : (real)0;
       pose_xyzrpy(pose, o + 14);
-      real gw = MD(gr_enabled) ? gripper_width(c) : (real)0;
       o[20] = RS(RCSB_S_GCMD) < 0 ? (real)1 : RS(RCSB_S_GCMD);
       o[21] = gw;
+      for (int i = 0; i < RCSB_INFO_DIM; i++) o[22 + i] = (real)f[i];
     }
     if (L.info) {
-      int* f = L.info + (size_t)env * RCSB_INFO_DIM;
-      real gw = MD(gr_enabled) ? gripper_width(c) : (real)0;
-      int rc = RI(RCSB_I_COLLISION), gc = MD(gr_enabled) ? RI(RCSB_I_G_COLLISION) : 0;
-      f[0] = rc || gc;                       // envs/sim.py:61,127-128
-      f[1] = RI(RCSB_I_IK_SUCCESS);
-      f[2] = RI(RCSB_I_CONVERGED);
-      f[3] = gw > (real)0.01 && gw < (real)0.99;  // envs/sim.py:130
-      f[4] = rc || !RI(RCSB_I_IK_SUCCESS);   // truncated, envs/sim.py:66
-      f[5] = rc; f[6] = gc;
-      f[7] = RI(RCSB_I_CONV_STEPS);
+      int* fo = L.info + (size_t)env * RCSB_INFO_DIM;
+      for (int i = 0; i < RCSB_INFO_DIM; i++) fo[i] = f[i];
     }
   }
 }

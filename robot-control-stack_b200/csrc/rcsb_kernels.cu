@@ -150,9 +150,10 @@ struct rcsb_batch {
   int warps_full = 0, grid_full = 0;  // phase 1 (full layout) launch shape when a reduced layout exists
   size_t smem_full = 0, ws_bytes_full = 0;
   // staging for the host-buffer path
-  real *d_act_joints = nullptr, *d_act_gripper = nullptr, *d_obs = nullptr;
+  real *d_act_joints = nullptr, *d_act_gripper = nullptr, *d_obs = nullptr, *d_act_packed = nullptr;
   int* d_info = nullptr;
   real *h_act = nullptr, *h_obs = nullptr;
+  int act_jstride = 0, act_gstride = 0;  // non-default action row strides of the next launch (packed host path)
   // optional contact export (rcsb_batch_set_contact_export)
   int *con_n = nullptr, *con_geom = nullptr, con_cap = 0;
   real* con_real = nullptr;
@@ -314,7 +315,7 @@ rcsb_batch* rcsb_batch_new(rcsb_model* m, int n_envs, void* sr, void* sd, void* 
 }
 void rcsb_batch_free(rcsb_batch* b) {
   if (!b) return;
-  cudaFree(b->d_counter); cudaFree(b->d_overflow); cudaFree(b->d_act_joints); cudaFree(b->d_act_gripper); cudaFree(b->d_obs); cudaFree(b->d_info);
+  cudaFree(b->d_counter); cudaFree(b->d_overflow); cudaFree(b->d_act_joints); cudaFree(b->d_act_gripper); cudaFree(b->d_act_packed); cudaFree(b->d_obs); cudaFree(b->d_info);
   if (b->h_act) cudaFreeHost(b->h_act);
   if (b->h_obs) cudaFreeHost(b->h_obs);
   delete b;
@@ -359,6 +360,7 @@ int rcsb_batch_run(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps
   memset(&L, 0, sizeof(L));
   L.N = b->n; L.ops = ops; L.lockstep = b->lockstep; L.bar_groups = b->bar_groups; L.conv_vote = b->conv_vote; L.k = k; L.max_convergence_steps = max_convergence_steps;
   L.act_joints = (const real*)act_joints_dev; L.act_gripper = (const real*)act_gripper_dev; L.mask = mask_dev;
+  L.act_jstride = b->act_jstride > 0 ? b->act_jstride : b->m->h.rb_njoints; L.act_gstride = b->act_gstride > 0 ? b->act_gstride : 1;
   L.max_mov = (real)max_mov;
   for (int i = 0; i < b->m->h.rb_njoints && i < RCSB_MAXJ; i++) {
     L.jlow[i] = jlow ? (real)jlow[i] : 0;
@@ -414,6 +416,7 @@ static int ensure_staging(rcsb_batch* b) {
   size_t n = (size_t)b->n;
   CUDA_OK(cudaMalloc(&b->d_act_joints, n * RCSB_MAXJ * sizeof(real)));
   CUDA_OK(cudaMalloc(&b->d_act_gripper, n * sizeof(real)));
+  CUDA_OK(cudaMalloc(&b->d_act_packed, n * (RCSB_MAXJ + 1) * sizeof(real)));
   CUDA_OK(cudaMalloc(&b->d_obs, n * RCSB_OBS_DIM * sizeof(real)));
   CUDA_OK(cudaMalloc(&b->d_info, n * RCSB_INFO_DIM * sizeof(int)));
   return RCSB_OK;
@@ -438,6 +441,28 @@ int rcsb_batch_run_host(rcsb_batch* b, unsigned ops, int k, int max_convergence_
     CUDA_OK(cudaMemcpyAsync(obs_host, b->d_obs, (size_t)b->n * RCSB_OBS_DIM * sizeof(real), cudaMemcpyDeviceToHost, b->stream));
   if (info_host)
     CUDA_OK(cudaMemcpyAsync(info_host, b->d_info, (size_t)b->n * RCSB_INFO_DIM * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  return RCSB_OK;
+}
+
+int rcsb_env_step_host(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps, const double* act_host, double max_mov,
+                       const double* jlow, const double* jhigh, double* obs_host) {
+  if (sizeof(real) != sizeof(double)) return fail(RCSB_ERR_ARG, "host-buffer path requires a float64 build");
+  if (!b || !act_host || !obs_host) return fail(RCSB_ERR_ARG, "null argument");
+  int rc = ensure_staging(b);
+  if (rc) return rc;
+  DEVICE_OK(b->m->device);
+  const int nj = b->m->h.rb_njoints, stride = nj + 1;
+  // one copy in: the packed action block lands in the joint staging array ([n][MAXJ] reals are reserved, nj + 1 <= MAXJ + 1)
+  if ((size_t)stride > (size_t)RCSB_MAXJ + 1) return fail(RCSB_ERR_ARG, "too many joints");
+  CUDA_OK(cudaMemcpyAsync(b->d_act_packed, act_host, (size_t)b->n * stride * sizeof(real), cudaMemcpyHostToDevice, b->stream));
+  b->act_jstride = stride; b->act_gstride = stride;
+  rc = rcsb_batch_run(b, ops | RCSB_OP_OBS, k, max_convergence_steps, b->d_act_packed, b->d_act_packed + nj, nullptr, max_mov, jlow, jhigh,
+                      b->d_obs, nullptr);
+  b->act_jstride = 0; b->act_gstride = 0;
+  if (rc) return rc;
+  // one copy out: the packed observation block carries the info flags as reals
+  CUDA_OK(cudaMemcpyAsync(obs_host, b->d_obs, (size_t)b->n * RCSB_OBS_DIM * sizeof(real), cudaMemcpyDeviceToHost, b->stream));
   CUDA_OK(cudaStreamSynchronize(b->stream));
   return RCSB_OK;
 }

@@ -89,6 +89,9 @@ RCSB_HD constexpr RcsbLayout rcsb_make_layout(const RcsbShape& s) {
   // whose qpos was changed from outside (host writes, resets) fails the comparison and starts with every group due
   RCSB_ALLOC(o_cbud, (s.ngrp * (int)sizeof(float) + (int)sizeof(real) - 1) / (int)sizeof(real));
   RCSB_ALLOC(o_cbq, nq);
+  // separating-direction cache of the convex narrow phase: RCSB_SEPSLOTS x (pair tag + 1, unit direction). Persistent: a
+  // cached direction is re-validated with one support pair before it is trusted, so it may outlive launches and resets
+  RCSB_ALLOC(o_sepcache, 4 * RCSB_SEPSLOTS);
   o = (o + 1) & ~1;  // rows stay 16-byte granular in HBM when real is 8 bytes
   y.nsr = o;
   y.o_site = y.o_rcs + RCSB_S_SITEPOS;
@@ -124,7 +127,6 @@ RCSB_HD constexpr RcsbLayout rcsb_make_layout(const RcsbShape& s) {
   RCSB_ALLOC(o_con, RCSB_C_REALS * s.maxcon);
   RCSB_ALLOC(o_J, s.maxefc * nv);
   RCSB_ALLOC(o_efc, RCSB_E_NARR * s.maxefc);
-  RCSB_ALLOC(o_sepcache, 8);  // 2 x (pair tag, separating direction), valid for one launch
   o = (o + 1) & ~1;  // keep the double clock block 16-byte aligned when real is 8 bytes
   y.ws_reals = o;
   y.ws_doubles = RCSB_D_TAIL;

@@ -24,6 +24,7 @@ enum {
   RCSB_MAXROOT = 4,   // kinematic trees
   RCSB_MAXJ = 8,      // robot arm joints
   RCSB_MAXCAND = 48,  // broad-phase survivors per step (28 at the FR3 home pose)
+  RCSB_SEPSLOTS = 4,  // direct-mapped slots of the separating-direction cache (convex narrow phase)
   RCSB_MAXGRP = 64,   // collision groups (pairs of bodies that own at least one candidate geom pair)
 };
 
@@ -162,6 +163,10 @@ struct RcsbModel {
   real rb_q_home[RCSB_MAXJ], rb_joint_tol, rb_cb_period;
   int gr_enabled, gr_act, gr_qadr;
   real gr_eps_inner, gr_eps_outer, gr_cb_period, gr_max_act, gr_min_act, gr_max_joint, gr_min_joint;
+  // per group and dof on its tree path: upper bound, over all poses, of the distance between the joint anchor and any
+  // collidable point of the group's body that the dof moves (1 for translational dofs; 0 off the path). Read by every
+  // group on every step (budget_advance), so it is staged with the hot part.
+  float grp_reach[RCSB_MAXGRP][RCSB_MAXV];
   // ---- per-warp workspace layout (offsets in reals / ints), filled by rcsb_model_finalize
   RcsbLayout lay;
   // ---- cold tail: NOT staged into shared memory (RCSB_MODEL_HOT_BYTES ends here); device code reaches it through the
@@ -169,9 +174,6 @@ struct RcsbModel {
   int cold_begin;
   int8_t grp_body[RCSB_MAXGRP][2];              // the two bodies of every collision group (-1 = world)
   real g_rbound0[RCSB_MAXG];                    // mjModel geom_rbound (about the geom frame origin): plane-mesh point spacing
-  float grp_reach[RCSB_MAXGRP][RCSB_MAXV];      // per group and dof on its tree path: upper bound, over all poses, of the
-                                                // distance between the joint anchor and any collidable point of the
-                                                // group's body that the dof moves (1 for translational dofs; 0 off the path)
 };
 
 
@@ -192,8 +194,9 @@ enum {
   RCSB_OP_OBS = 1 << 12,            // RobotEnv.get_obs + wrappers' observation/info
   RCSB_OP_ACT_GRIPPER_CONT = 1 << 13,  // GripperWrapper.action, continuous width
 };
-enum { RCSB_OBS_DIM = 22, RCSB_INFO_DIM = 8 };
-// obs row: tquat[7] joints[7] xyzrpy[6] gripper[1] gripper_width[1]
+enum { RCSB_OBS_DIM = 30, RCSB_INFO_DIM = 8 };
+// obs row: tquat[7] joints[7] xyzrpy[6] gripper[1] gripper_width[1] | the info row again, as reals (one packed block per
+//          environment: what the multi-GPU exchange gathers and what the host-buffer path copies back)
 // info row: collision, ik_success, is_sim_converged, is_grasped, truncated, robot_collision, gripper_collision, conv_steps
 
 struct RcsbLaunch {
@@ -206,8 +209,9 @@ struct RcsbLaunch {
   int phase;     // 0: every environment, reduced or full layout; 1: full layout, only the environments in overflow_list
   int* overflow_list;   // [N] environments the reduced layout could not finish (phase 0 appends, phase 1 consumes)
   int* overflow_count;
-  const real* act_joints;   // [N][njoints]
-  const real* act_gripper;  // [N]
+  const real* act_joints;   // [N][act_jstride], njoints used
+  const real* act_gripper;  // [N][act_gstride], first used
+  int act_jstride, act_gstride;  // row strides in reals (njoints / 1 for separate arrays; a packed [N][njoints + 1] block: both njoints + 1)
   const unsigned char* mask;  // optional [N]: 0 = leave this env untouched
   real max_mov, jlow[RCSB_MAXJ], jhigh[RCSB_MAXJ];
   real* obs;   // [N][RCSB_OBS_DIM] or null

@@ -55,6 +55,7 @@ def lib():
     L.rcsb_batch_set_contact_export.argtypes = [vp, vp, vp, vp, C.c_int]
     L.rcsb_batch_run.argtypes = [vp, C.c_uint, C.c_int, C.c_int, vp, vp, vp, C.c_double, dp, dp, vp, vp]
     L.rcsb_batch_run_host.argtypes = [vp, C.c_uint, C.c_int, C.c_int, vp, vp, C.c_double, dp, dp, vp, vp]
+    L.rcsb_env_step_host.argtypes = [vp, C.c_uint, C.c_int, C.c_int, vp, C.c_double, dp, dp, vp]
     L.rcsb_sim_step.argtypes = [vp, C.c_int]
     L.rcsb_sim_step_until_convergence.argtypes = [vp, C.c_int]
     for f in ("rcsb_sim_reset", "rcsb_robot_reset", "rcsb_gripper_reset"):
@@ -80,7 +81,7 @@ def check(rc: int):
 EXPORTS = ["rcsb_last_error", "rcsb_version", "rcsb_real_bytes", "rcsb_model_new", "rcsb_model_free",
            "rcsb_model_set_int", "rcsb_model_set_real", "rcsb_model_set_mesh_vertices", "rcsb_model_set_mesh_graph", "rcsb_model_finalize",
            "rcsb_model_upload", "rcsb_model_dims", "rcsb_model_offsets", "rcsb_model_workspace_bytes", "rcsb_batch_new", "rcsb_batch_free",
-           "rcsb_batch_init_state", "rcsb_batch_set_contact_export", "rcsb_batch_run", "rcsb_batch_run_host", "rcsb_sim_step",
+           "rcsb_batch_init_state", "rcsb_batch_set_contact_export", "rcsb_batch_run", "rcsb_batch_run_host", "rcsb_env_step_host", "rcsb_sim_step",
            "rcsb_sim_step_until_convergence", "rcsb_sim_reset", "rcsb_robot_set_joint_position",
            "rcsb_robot_set_joints_hard", "rcsb_robot_reset", "rcsb_gripper_set_normalized_width",
            "rcsb_gripper_reset", "rcsb_env_get_obs", "rcsb_ik_inverse", "rcsb_robot_set_cartesian_position", "rcsb_env_cartesian_action",

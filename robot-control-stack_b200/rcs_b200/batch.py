@@ -146,6 +146,16 @@ class Batch:
             _dp(lo) if lo is not None else None, _dp(hi) if hi is not None else None,
             obs_host.data_ptr() if obs_host is not None else None, info_host.data_ptr() if info_host is not None else None))
 
+    def step_host(self, ops: int, k: int, max_convergence_steps: int, act_host: torch.Tensor, max_mov: float, jlow, jhigh,
+                  obs_host: torch.Tensor):
+        """env.step() through one packed pinned block each way (rcsb_env_step_host): act_host [n, njoints + 1],
+        obs_host [n, obs_dim] (info flags in the last 8 columns)."""
+        lo = np.ascontiguousarray(jlow, dtype=np.float64) if jlow is not None else None
+        hi = np.ascontiguousarray(jhigh, dtype=np.float64) if jhigh is not None else None
+        _lib.check(_lib.lib().rcsb_env_step_host(self.ptr, ops, k, max_convergence_steps, act_host.data_ptr(), float(max_mov),
+                                                 _dp(lo) if lo is not None else None, _dp(hi) if hi is not None else None,
+                                                 obs_host.data_ptr()))
+
     def ik_inverse(self, pose: torch.Tensor, q0: torch.Tensor):
         nqm = int(self.model.fields["rb_ik_nq"][0][0])
         q = torch.zeros((self.n, nqm), dtype=torch.float64, device=self.dev)

@@ -58,6 +58,7 @@ int emu_run(const EmuModel* em, const real* verts, real* sr, double* sd, int* si
   memset(&L, 0, sizeof(L));
   L.N = N; L.ops = ops; L.k = k; L.max_convergence_steps = max_conv;
   L.act_joints = act_joints; L.act_gripper = act_gripper; L.mask = mask; L.max_mov = max_mov;
+  L.act_jstride = em->full.rb_njoints; L.act_gstride = 1;
   for (int i = 0; i < RCSB_MAXJ; i++) { L.jlow[i] = jlow ? jlow[i] : 0; L.jhigh[i] = jhigh ? jhigh[i] : 0; }
   L.obs = obs; L.info = info;
   L.con_n = g_con_n; L.con_geom = g_con_geom; L.con_real = g_con_real; L.con_cap = g_con_cap;

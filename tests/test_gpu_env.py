@@ -123,7 +123,7 @@ def test_batched_relative_joint_env_async():
     assert not bool(term.any()) and float(rew.abs().max()) == 0.0
     h_j = torch.zeros((512, 7), dtype=torch.float64).pin_memory(); h_g = torch.ones(512, dtype=torch.float64).pin_memory()
     ho, hi = env.step_host(h_j, h_g)
-    assert ho.shape == (512, 22) and np.isfinite(ho.numpy()).all()
+    assert ho.shape == (512, 30) and np.isfinite(ho.numpy()).all()
 
 
 @pytest.mark.parametrize("mode_name", ["CARTESIAN_TRPY", "CARTESIAN_TQuat"])

@@ -19,9 +19,9 @@ def _worker(rank, world, port, n_total, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from rcs_b200.shard import gather_observations, shard_range
     b, e = shard_range(n_total, rank, world)
-    local = torch.arange(b, e, dtype=torch.float64).unsqueeze(1).repeat(1, 22) + 0.5 * rank * 0
+    local = torch.arange(b, e, dtype=torch.float64).unsqueeze(1).repeat(1, 30) + 0.5 * rank * 0
     full = gather_observations(local, n_total)
-    ok = bool(torch.equal(full[:, 0], torch.arange(n_total, dtype=torch.float64))) and full.shape == (n_total, 22)
+    ok = bool(torch.equal(full[:, 0], torch.arange(n_total, dtype=torch.float64))) and full.shape == (n_total, 30)
     q.put((rank, b, e, ok))
     dist.destroy_process_group()
 
