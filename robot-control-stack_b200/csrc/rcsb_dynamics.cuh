@@ -1063,6 +1063,16 @@ RCSB_DEV void budget_min(const Ctx& c, float* bud, int g, real gap) {
   atomicMin((unsigned*)(bud + g), __float_as_uint(f));  // non-negative floats order like their bit patterns
 #endif
 }
+RCSB_DEV float reach_decode(uint16_t h) {  // upper half of a float32 bit pattern (rcsb_layout.h: rcsb_reach_encode)
+#ifdef RCSB_HOST_EMU
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#else
+  return __uint_as_float((uint32_t)h << 16);
+#endif
+}
 RCSB_DEV void budget_reset(const Ctx& c) {  // positions changed by something other than a step: every group is due
   const RcsbModel& m = CMODEL(c);
   float* bud = (float*)WR(cbud);
@@ -1074,9 +1084,9 @@ RCSB_DEV void budget_advance(const Ctx& c) {
   float* bud = (float*)WR(cbud);
   const real h = m.timestep;
   PFOR(g, MD(ngrp)) {
-    const float* reach = m.grp_reach[g];  // zero off the tree path between the group's bodies
+    const uint16_t* reach = m.grp_reach[g];  // zero off the tree path between the group's bodies
     real s = 0;
-    for (int j = 0; j < MD(nv); j++) s += r_abs(WR(v)[j]) * (real)reach[j];
+    for (int j = 0; j < MD(nv); j++) s += r_abs(WR(v)[j]) * (real)reach_decode(reach[j]);
     bud[g] -= (float)(h * s * (real)1.000001) + 1e-6f;
   }
 }

@@ -139,6 +139,14 @@ RCSB_HD constexpr RcsbLayout rcsb_make_layout(const RcsbShape& s) {
 #undef RCSB_MAX
   return y;
 }
+// group reach table entries: float32 truncated to its upper 16 bits, rounded towards +inf (the bound stays a bound)
+static inline uint16_t rcsb_reach_encode(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  uint16_t h = (uint16_t)(u >> 16);
+  if (u & 0xffffu) h++;  // x >= 0: the next representable value up
+  return h;
+}
 static inline void rcsb_host_quat_to_mat(real* M, const real* q) {  // same expression order as quat_to_mat (rcsb_warp.cuh)
   real w = q[0], x = q[1], y = q[2], z = q[3];
   M[0] = w * w + x * x - y * y - z * z; M[1] = 2 * (x * y - w * z); M[2] = 2 * (x * z + w * y);
@@ -205,7 +213,7 @@ static inline int rcsb_model_finalize_layout(RcsbModel* m) {
           r = sqrt(m->b_jpos[bj][0] * m->b_jpos[bj][0] + m->b_jpos[bj][1] * m->b_jpos[bj][1] + m->b_jpos[bj][2] * m->b_jpos[bj][2]) + E[x];
           for (int k = x; k != bj && k >= 0; k = m->b_parent[k]) r += off[k];
         }
-        m->grp_reach[g][j] = (float)(r * 1.000001);
+        m->grp_reach[g][j] = rcsb_reach_encode((float)(r * 1.000001));
       }
     }
   }

@@ -107,7 +107,7 @@ struct RcsbModel {
   uint32_t b_ancmask[RCSB_MAXB];   // moving-body ancestors incl. self
   uint32_t b_descmask[RCSB_MAXB];  // descendants incl. self
   uint32_t b_dofmask[RCSB_MAXB];   // dofs of self and all ancestors
-  real b_pos[RCSB_MAXB][3], b_quat[RCSB_MAXB][4];  // frame in parent moving body (or world) at qpos0
+  real b_pos[RCSB_MAXB][3];                        // frame in parent moving body (or world) at qpos0 (b_quat: cold tail)
   real b_rot[RCSB_MAXB][9];                        // rotation matrix of b_quat, derived in rcsb_model_finalize_layout
   real b_jpos[RCSB_MAXB][3], b_jaxis[RCSB_MAXB][3];
   real b_mass[RCSB_MAXB], b_ipos[RCSB_MAXB][3], b_inertia[RCSB_MAXB][6];  // xx yy zz xy xz yz about COM, body axes
@@ -133,7 +133,7 @@ struct RcsbModel {
   // ---- collidable geoms
   int g_body[RCSB_MAXG], g_type[RCSB_MAXG], g_vertadr[RCSB_MAXG], g_vertnum[RCSB_MAXG], g_origid[RCSB_MAXG],
       g_role[RCSB_MAXG], g_condim[RCSB_MAXG], g_priority[RCSB_MAXG];
-  real g_pos[RCSB_MAXG][3], g_quat[RCSB_MAXG][4];  // in the moving body frame (world frame if g_body < 0)
+  real g_pos[RCSB_MAXG][3];                        // in the moving body frame (world frame if g_body < 0; g_quat: cold tail)
   real g_rot[RCSB_MAXG][9];                        // rotation matrix of g_quat, derived
   real g_bpos[RCSB_MAXG][3];  // bounding-volume centre (local AABB centre) in the moving body frame; g_rbound is about it
   real g_size[RCSB_MAXG][3], g_rbound[RCSB_MAXG], g_aabb[RCSB_MAXG][6], g_friction[RCSB_MAXG][3], g_solref[RCSB_MAXG][2],
@@ -166,13 +166,15 @@ struct RcsbModel {
   // per group and dof on its tree path: upper bound, over all poses, of the distance between the joint anchor and any
   // collidable point of the group's body that the dof moves (1 for translational dofs; 0 off the path). Read by every
   // group on every step (budget_advance), so it is staged with the hot part.
-  float grp_reach[RCSB_MAXGRP][RCSB_MAXV];
+  // Stored as the upper half of the float32 bit pattern, rounded up (rcsb_reach_encode / rcsb_reach_decode): 2 KB.
+  uint16_t grp_reach[RCSB_MAXGRP][RCSB_MAXV];
   // ---- per-warp workspace layout (offsets in reals / ints), filled by rcsb_model_finalize
   RcsbLayout lay;
   // ---- cold tail: NOT staged into shared memory (RCSB_MODEL_HOT_BYTES ends here); device code reaches it through the
   //      global-memory copy of the model (CMODEL_G), where the few hot rows stay in L1
   int cold_begin;
   int8_t grp_body[RCSB_MAXGRP][2];              // the two bodies of every collision group (-1 = world)
+  real b_quat[RCSB_MAXB][4], g_quat[RCSB_MAXG][4];  // host-side inputs of b_rot / g_rot (rcsb_model_finalize_layout)
   real g_rbound0[RCSB_MAXG];                    // mjModel geom_rbound (about the geom frame origin): plane-mesh point spacing
 };
 
