@@ -1,16 +1,25 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: env-steps/sec, FR3 joint control (BASELINE.json metric).
 
-Workload: fr3_empty_world, ControlMode.JOINTS relative to the last
-step with max_relative_movement = 5 deg, binary gripper, SimConfig(async_control=True, frequency=30) => 17
-physics substeps per env.step(); actions joints ~ U(-5deg, 5deg)^7, gripper ~ Bernoulli(0.5), seed 0;
-episodes of 10 steps then reset(). ENVS_PER_GPU environments per GPU (weak scaling across GPUs).
+Headline workload (SURVEY.md 8d config C2 = BASELINE.json configs[1]): fr3_empty_world,
+ControlMode.JOINTS relative to the last step with max_relative_movement = 5 deg, binary gripper,
+SimConfig(async_control=True, frequency=30) => 17 physics substeps per env.step(); actions joints ~ U(-5deg, 5deg)^7,
+gripper ~ Bernoulli(0.5); episodes of 10 steps then reset(). 4096 environments per GPU (weak scaling across GPUs).
 
-A "step" is one env.step() of all environments = one fused kernel launch (action transform, 17 substeps,
-observation pack); every 10th step is preceded by the reset launch, inside the timed region.
+Everything goes through the product's public API: `SimEnvCreator()(ControlMode.JOINTS, ..., num_envs=N, shard=...)`
+(rcs_b200.envs.creators, the mirror of python/rcs/envs/creators.py:43-128). A "step" is one env.step() of all
+environments = one fused kernel launch (action transform, 17 substeps, observation pack); every 10th step is preceded by
+the reset launch, inside the timed region. Under torchrun every rank drives one GPU through the sharded env
+(rcs_b200.envs.sharded): its block of environments plus the one exchange step of the path, the all-gather of the packed
+observation rows, which runs on a side stream and overlaps the next step.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl ours|reference]
-Under torchrun (N > 1) every rank drives one GPU; rank 0 prints ONE JSON line.
+  value  device-resident: actions already in HBM, env.step_packed / step_async, CUDA events, max over ranks
+  e2e    env.step_host(): pinned host action block -> H2D -> fused launch -> D2H of the packed observation -> sync
+  sweep  sub-records for the other sizes / configs the metric names (C2 @ 16384 and 65536, sync mode, C3 @ 16384 with the
+         on-GPU IK, C4 xArm7 tabletop), each measured the same way with fewer steps
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl ours|reference] [--no-sweep]
+Under torchrun (N > 1) rank 0 prints ONE JSON line.
 """
 import argparse
 import json
@@ -23,26 +32,31 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "robot-control-stack_b200"), os.path.join(ROOT, "tests")):
+for p in (ROOT, os.path.join(ROOT, "robot-control-stack_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
 SUBSTEPS = 17
 EPISODE = 10
 MAX_MOV = float(np.deg2rad(5))
-# algorithmic bytes of one env.step() of one env in float64: per substep read
-# qpos+qvel+ctrl+warmstart+time and write qpos+qvel+warmstart+time = 512 B; plus action 8x8 B, obs 21x8 B, 3 flags
-BYTES_PER_PHYSICS_STEP = 512
-BYTES_PER_ENV_STEP = SUBSTEPS * BYTES_PER_PHYSICS_STEP + 64 + 168 + 3
+# algorithmic bytes of one physics step of one env in float64: read qpos+qvel+ctrl+warmstart+time, write
+# qpos+qvel+warmstart+time; per env.step() add the action (8 x 8 B), the observation (21 x 8 B) and 3 flag bytes
+BYTES_PER_PHYSICS_STEP = {"fr3_empty_world": 512, "fr3_simple_pick_up": 816, "xarm7_tabletop": 8 * (2 * 28 + 2 * 27 + 7 + 2)}
+
+
+def bytes_per_env_step(scene, substeps=SUBSTEPS):
+    return substeps * BYTES_PER_PHYSICS_STEP[scene] + 64 + 168 + 3
 
 
 def profiled_traffic():
     """DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            return json.load(f)
-    except Exception:
-        return None
+    for tag in ("r02", "r01"):
+        try:
+            with open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json")) as f:
+                return json.load(f)
+        except Exception:
+            continue
+    return None
 
 
 def measured_peak():
@@ -54,8 +68,8 @@ def measured_peak():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: NVML (a sample every ~2 ms) when pynvml imports,
-    else nvidia-smi (a sample every ~100 ms)."""
+    """SM clock and throttle reasons sampled from before the warm-up to the end of the timed region: NVML (a sample every
+    ~2 ms) when pynvml imports, else nvidia-smi (a sample every ~100 ms)."""
 
     def __init__(self, index):
         self.rows, self.stop_flag, self.index = [], False, index
@@ -102,33 +116,49 @@ class ClockSampler:
     def start(self):
         self.t.start()
 
+    def mark(self):
+        """samples from here on belong to the timed region"""
+        self.first = len(self.rows)
+
     def stop(self):
         self.stop_flag = True
         self.t.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        rows = self.rows[getattr(self, "first", 0):] or self.rows
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
+                "reasons": reasons, "samples": len(rows), "samples_incl_warmup": len(self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def _oracle():
+    """The CPU restatement of the reference path (oracle/): the one place outside tests/ and smoke() allowed to run it."""
+    from oracle import oracle as O
+    from rcs_b200 import workloads as WL
+    return O, WL
 
 
 def cpu_reference(nthreads, target_seconds, episode_len=EPISODE):
-    """The reference path's CPU restatement (oracle) on all host cores over a bounded sample of the workload."""
-    import helpers as H
-    from helpers import O
-    M = H.scene()
+    """The reference path's CPU restatement on all host cores over a bounded sample of the headline workload."""
+    O, WL = _oracle()
+    M = WL.scene("fr3_empty_world")
     m, rc, gc = O.Model(M), O.robot_cfg(M), O.gripper_cfg(M)
     nenv = nthreads
-    probe = H.workload_actions(nenv, 20, seed=0)
-    sec, _, _ = O.bench_env_steps(m, rc, gc, probe, nthreads, episode_len, True, MAX_MOV, H.JLOW, H.JHIGH)
+    probe = WL.workload_actions(nenv, 20, seed=0)
+    sec, _, _ = O.bench_env_steps(m, rc, gc, probe, nthreads, episode_len, True, MAX_MOV, WL.FR3_JLOW, WL.FR3_JHIGH)
     rate = nenv * 20 / max(sec, 1e-9)
     nsteps = int(max(20, min(20000, target_seconds * rate / nenv)))
-    acts = H.workload_actions(nenv, nsteps, seed=0)
-    sec, psteps, _ = O.bench_env_steps(m, rc, gc, acts, nthreads, episode_len, True, MAX_MOV, H.JLOW, H.JHIGH)
+    acts = WL.workload_actions(nenv, nsteps, seed=0)
+    sec, psteps, _ = O.bench_env_steps(m, rc, gc, acts, nthreads, episode_len, True, MAX_MOV, WL.FR3_JLOW, WL.FR3_JHIGH)
     return {"value": nenv * nsteps / sec, "unit": "env-steps/s", "cores": nthreads, "kind": "port",
-            "sample": f"{nenv} envs x {nsteps} env.step() ({psteps} physics steps) in {sec:.2f} s, one env per thread",
-            "physics_steps_per_s": psteps / sec}
+            "sample": f"{nenv} envs x {nsteps} env.step() ({psteps} physics steps) in {sec:.2f} s, one env per thread "
+                      "(CPU arm runs `cores` independent envs, not 4096: per-env work is identical, envs are independent)",
+            "physics_steps_per_s": psteps / sec,
+            "build": "oracle/Makefile: gcc -O3 -march=x86-64-v3 (portable to the GPU box's host CPU), C port without the "
+                     "reference's Python wrapper cost -- conservative for the GPU/CPU ratio"}
 
 
 def run_reference(args):
@@ -158,151 +188,253 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    import helpers as H
-    from rcs_b200 import _lib, batch
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    distributed = world > 1
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if distributed:
-        dist.init_process_group("nccl", device_id=dev)
-    N, K, W = args.envs, args.steps, args.warmup
-    M = H.scene()
-    dm = batch.DeviceModel(M, H.robot_ns(), H.gripper_ns(), device=local)
-    stream = torch.cuda.current_stream(dev)
-    b = batch.Batch(dm, N)
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+# ------------------------------------------------------------------------------------------------ our arm (GPU)
+class Harness:
+    """Process-wide state of one bench run: rank / device, torch.distributed, the L2 flush buffer."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.distributed = self.world > 1
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.distributed:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        self.stream = torch.cuda.current_stream(self.dev)
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.distributed:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.distributed:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.distributed:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+
+def make_env(h, workload, n_per_gpu):
+    """The product API call a user makes for each workload."""
+    from rcs_b200 import sim, workloads as WL
+    from rcs_b200.envs.base import ControlMode
+    from rcs_b200.envs.creators import FR3SimplePickUpSimEnvCreator, SimEnvCreator
+    from rcs_b200.envs.utils import default_sim_gripper_cfg, default_sim_robot_cfg
+    n_total = n_per_gpu * h.world
+    if workload in ("c2", "c2_sync"):
+        return SimEnvCreator()(ControlMode.JOINTS, default_sim_robot_cfg("fr3_empty_world"), gripper_cfg=default_sim_gripper_cfg(),
+                               sim_cfg=sim.SimConfig(async_control=workload == "c2", frequency=30), max_relative_movement=MAX_MOV,
+                               num_envs=n_total if h.distributed else n_per_gpu, device=h.local, shard=h.distributed)
+    if workload == "c3":
+        return FR3SimplePickUpSimEnvCreator()(num_envs=n_per_gpu, device=h.local)  # per-rank block (task layer is local)
+    if workload == "c4":
+        return SimEnvCreator()(ControlMode.JOINTS, WL.xarm7_tabletop_robot_cfg(), gripper_cfg=None,
+                               sim_cfg=sim.SimConfig(async_control=True, frequency=30), max_relative_movement=MAX_MOV,
+                               num_envs=n_total if h.distributed else n_per_gpu, device=h.local, shard=h.distributed)
+    raise ValueError(workload)
+
+
+def measure(h, workload, n_per_gpu, K, W, sampler=None, want_e2e=True):
+    """One record: K timed env.step() calls of `workload` with n_per_gpu environments on every rank."""
+    torch = h.torch
+    from rcs_b200 import _lib
+    env = make_env(h, workload, n_per_gpu)
+    local = env.unwrapped if workload != "c3" else env.unwrapped
+    b = local.sim.batch
+    N = n_per_gpu
+    gen = torch.Generator(device=h.dev).manual_seed(1234 + h.rank)
     total = K + W
-    acts_j = (torch.rand((total, N, 7), dtype=torch.float64, device=dev, generator=gen) * 2 - 1) * MAX_MOV
-    acts_g = torch.randint(0, 2, (total, N), device=dev, generator=gen).to(torch.float64)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    obs_all = torch.empty((world, N, dm.obs_dim), dtype=torch.float64, device=dev) if distributed else None
-    reset_ops = _lib.GRIPPER_RESET | _lib.SIM_RESET | _lib.ROBOT_RESET | _lib.ENV_RESET_FLAGS | _lib.STEP_K | _lib.OBS
-    step_ops = _lib.ACT_JOINTS_REL | _lib.ACT_GRIPPER_BIN | _lib.STEP_K | _lib.OBS
-    launches_before = None
+    if workload == "c3":  # SURVEY 8d C3: xyz ~ U(-0.01, 0.01)^3, rpy ~ U(-0.05, 0.05)^3, gripper Bernoulli(0.5)
+        scale = torch.tensor([0.01] * 3 + [0.05] * 3, dtype=torch.float64, device=h.dev)
+        acts = [{"xyzrpy": (torch.rand((N, 6), dtype=torch.float64, device=h.dev, generator=gen) * 2 - 1) * scale,
+                 "gripper": torch.randint(0, 2, (N,), device=h.dev, generator=gen).to(torch.float64)} for _ in range(total)]
+        scene, dof = "fr3_simple_pick_up", 7
+    else:
+        dof = local.dof
+        aj = (torch.rand((total, N, dof), dtype=torch.float64, device=h.dev, generator=gen) * 2 - 1) * MAX_MOV
+        ag = torch.randint(0, 2, (total, N), device=h.dev, generator=gen).to(torch.float64)
+        acts = [({"joints": aj[i], "gripper": ag[i]} if local.gripper is not None else {"joints": aj[i]}) for i in range(total)]
+        scene = "xarm7_tabletop" if workload == "c4" else "fr3_empty_world"
+    sharded = h.distributed and workload != "c3"
+    pending = [None]
 
     def one_step(i):
-        n = 0
         if i % EPISODE == 0:
-            b.run(reset_ops, k=1, want_obs=True)
-            n += 1
-        b.run(step_ops, k=SUBSTEPS, act_joints=acts_j[i], act_gripper=acts_g[i], max_mov=MAX_MOV, jlow=H.JLOW, jhigh=H.JHIGH,
-              want_obs=True)
-        n += 1
-        if distributed:  # the one exchange step: vectorised observation return on every rank
-            dist.all_gather_into_tensor(obs_all.view(-1), b.obs.view(-1))
-        return n
+            env.reset()
+        if sharded:  # consume the previous step's gathered observation, launch this one, leave its gather in flight
+            if pending[0] is not None:
+                pending[0].rows()
+            pending[0] = env.step_async(acts[i])
+        elif workload == "c3":
+            env.step(acts[i])
+        else:
+            env.step_packed(acts[i])
 
+    env.reset()
     for i in range(W):
         one_step(i)
-        flush.zero_()
-    torch.cuda.synchronize()
-    if distributed:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    launches = 0
+        h.flush.zero_()
+    h.barrier()
+    if sampler is not None:
+        sampler.mark()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K + 1)]
     launches_before = _lib.lib().rcsb_launch_count()
+    conv_steps = 0.0
     for i in range(K):
-        flush.zero_()  # L2 flush between timed iterations (outside the timed events)
-        ev[i][0].record(stream)
-        if (W + i) % EPISODE == 0:
-            b.run(reset_ops, k=1, want_obs=True)
-        kev[i][0].record(stream)
-        b.run(step_ops, k=SUBSTEPS, act_joints=acts_j[W + i], act_gripper=acts_g[W + i], max_mov=MAX_MOV, jlow=H.JLOW,
-              jhigh=H.JHIGH, want_obs=True)
-        kev[i][1].record(stream)
-        if distributed:
-            dist.all_gather_into_tensor(obs_all.view(-1), b.obs.view(-1))
-        ev[i][1].record(stream)
-    torch.cuda.synchronize()
-    if distributed:
-        dist.barrier()
-    torch.cuda.synchronize()
+        h.flush.zero_()  # L2 flush between timed iterations (outside the timed events)
+        ev[i][0].record(h.stream)
+        one_step(W + i)
+        ev[i][1].record(h.stream)
+        if workload == "c2_sync":
+            conv_steps += float(b.obs[:, 29].sum().item())
+    ev[K][0].record(h.stream)
+    if pending[0] is not None:  # the last gather is waited for inside the timed region
+        pending[0].rows()
+    ev[K][1].record(h.stream)
+    h.barrier()
     launches = _lib.lib().rcsb_launch_count() - launches_before
-    clocks = sampler.stop() if rank == 0 else None
     ms = sum(a.elapsed_time(c) for a, c in ev)
-    kms = [a.elapsed_time(c) for a, c in kev]
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if distributed:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * N * K / (ms_max * 1e-3)
+    ms_max = h.max_over_ranks(ms)
+    value = h.world * N * K / (ms_max * 1e-3)
+    occ = b.occupancy()
+    substeps = SUBSTEPS
+    rec = {"workload": workload, "scene": scene, "envs_per_gpu": N, "total_envs": N * h.world, "steps": K, "warmup": W,
+           "value": value, "unit": "env-steps/s", "ms_per_step": ms_max / K, "gpu_launches": int(launches), **occ}
+    if workload == "c2_sync":
+        mean_sub = h.sum_over_ranks(conv_steps) / (h.world * N * K)
+        rec["substeps_per_env_step"] = mean_sub
+        rec["physics_steps_per_s"] = value * mean_sub
+        substeps = mean_sub
+    else:
+        rec["physics_steps_per_s"] = value * SUBSTEPS
+    peak, peak_src = measured_peak()
+    bpe = bytes_per_env_step(scene, substeps)
+    achieved = value / h.world * bpe / 1e9  # per GPU: algorithmic bytes per env.step x env.steps per second per GPU
+    rec["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                       "algorithmic_bytes_per_env_step": bpe, "peak_source": peak_src, "traffic": None}
+    # ---- end to end through host buffers: env.step_host (JOINTS control with a gripper)
+    if want_e2e and workload in ("c2", "c2_sync"):
+        act_cpu = torch.cat([aj, ag.unsqueeze(-1)], dim=-1).cpu()
+        h_act = torch.empty((N, dof + 1), dtype=torch.float64).pin_memory()
+        steps = min(K, 50)
+        for i in range(3):
+            h_act.copy_(act_cpu[i])
+            local.step_host(h_act)
+        h.barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            h_act.copy_(act_cpu[W + i])  # the host-side policy output of this step
+            if (W + i) % EPISODE == 0:
+                local.reset_packed()
+            out = local.step_host(h_act)
+            _ = float(out[0, 0])  # consume the result on the host
+        e2e_s = h.max_over_ranks(time.perf_counter() - t0)
+        rec["e2e"] = {"value": h.world * N * steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": int(N * (dof + 1) * 8),
+                      "d2h_bytes_per_step": int(N * local.obs_dim * 8), "steps": steps,
+                      "api": "SimVectorEnv.step_host (C ABI rcsb_env_step_host): pinned host action block in, packed observation out"}
+    del env
+    torch.cuda.empty_cache()
+    return rec
 
-    # ---- end to end through host buffers (rank-local; aggregate = sum over ranks measured as world * N / max time)
-    from rcs_b200.envs.base import ControlMode
-    h_j = torch.empty((N, 7), dtype=torch.float64).pin_memory()
-    h_g = torch.empty((N,), dtype=torch.float64).pin_memory()
-    h_obs = torch.empty((N, dm.obs_dim), dtype=torch.float64).pin_memory()
-    h_info = torch.empty((N, dm.info_dim), dtype=torch.int32).pin_memory()
-    src_j, src_g = acts_j.cpu(), acts_g.cpu()
-    e2e_steps = min(K, 50)
-    for i in range(3):
-        h_j.copy_(src_j[i]); h_g.copy_(src_g[i])
-        b.run_host(step_ops, SUBSTEPS, 500, h_j, h_g, MAX_MOV, H.JLOW, H.JHIGH, h_obs, h_info)
-    torch.cuda.synchronize()
-    if distributed:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        h_j.copy_(src_j[W + i]); h_g.copy_(src_g[W + i])  # the host-side policy output of this step
-        if (W + i) % EPISODE == 0:
-            b.run(reset_ops, k=1, want_obs=True)
-        b.run_host(step_ops, SUBSTEPS, 500, h_j, h_g, MAX_MOV, H.JLOW, H.JHIGH, h_obs, h_info)
-        _ = float(h_obs[0, 0])  # consume the result on the host
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if distributed:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * N * e2e_steps / float(te.item())
 
-    if rank == 0:
+def kernel_time_ms(h, n_per_gpu, K=20):
+    """Average duration of the dominant kernel (one fused env.step launch) timed alone with CUDA events on its stream."""
+    torch = h.torch
+    env = make_env(h, "c2", n_per_gpu)
+    local = env.unwrapped
+    gen = torch.Generator(device=h.dev).manual_seed(99)
+    aj = (torch.rand((K + 3, n_per_gpu, 7), dtype=torch.float64, device=h.dev, generator=gen) * 2 - 1) * MAX_MOV
+    ag = torch.randint(0, 2, (K + 3, n_per_gpu), device=h.dev, generator=gen).to(torch.float64)
+    local.reset_packed()
+    ms = []
+    for i in range(K + 3):
+        h.flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(h.stream)
+        local.step_packed({"joints": aj[i], "gripper": ag[i]})
+        e1.record(h.stream)
+        torch.cuda.synchronize()
+        if i >= 3:
+            ms.append(e0.elapsed_time(e1))
+    del env
+    return float(np.mean(ms))
+
+
+def run_ours(args):
+    h = Harness()
+    sampler = ClockSampler(h.local)
+    if h.rank == 0:
+        sampler.start()  # before the warm-up, so that the timed region is covered from its first millisecond
+    N, K, W = args.envs, args.steps, args.warmup
+    head = measure(h, "c2", N, K, W, sampler=sampler)
+    clocks = sampler.stop() if h.rank == 0 else None
+    kms = kernel_time_ms(h, N)
+    sweep = []
+    if not args.no_sweep:
+        plan = [("c2", 16384, 10, 3), ("c2", 65536, 6, 3), ("c2_sync", 4096, 4, 3), ("c3", 16384, 10, 3)]
+        try:
+            from rcs_b200 import workloads as WL
+            if WL.has_scene("xarm7_tabletop"):
+                plan.append(("c4", 8192, 10, 3))  # 65536 environments over 8 GPUs (BASELINE.json configs[3])
+        except Exception:
+            pass
+        for wl, n, k, w in plan:
+            try:
+                sweep.append(measure(h, wl, n, k, w))
+            except Exception as e:  # a sub-record never takes the headline down
+                sweep.append({"workload": wl, "envs_per_gpu": n, "error": f"{type(e).__name__}: {e}"})
+    if h.rank == 0:
         peak, peak_src = measured_peak()
-        kavg_ms = float(np.mean(kms))
-        achieved = N * BYTES_PER_ENV_STEP / (kavg_ms * 1e-3) / 1e9
-        occ = b.occupancy()
+        bpe = bytes_per_env_step("fr3_empty_world")
+        achieved = N * bpe / (kms * 1e-3) / 1e9
         prof = profiled_traffic() if N == 4096 else None
+        occ = {k: head[k] for k in ("warps_per_cta", "smem_bytes", "grid", "variant", "variant_full")}
         line = {
-            "metric": "env-steps/sec FR3 joint-control (async 30 Hz, 17 substeps)", "value": value, "unit": "env-steps/s",
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "metric": "env-steps/sec FR3 joint-control (async 30 Hz, 17 substeps)", "value": head["value"], "unit": "env-steps/s",
+            "n_gpus": h.world, "steps": K, "warmup": W, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{N} x FR3 fr3_empty_world per GPU, JOINTS relative 5deg + binary gripper, random actions, "
-                                   f"async {SUBSTEPS} substeps/env.step, reset every {EPISODE} steps",
-                       "envs_per_gpu": N, "total_envs": N * world, "physics_steps_per_s": value * SUBSTEPS,
+                                   f"async {SUBSTEPS} substeps/env.step, reset every {EPISODE} steps (BASELINE.json configs[1])",
+                       "envs_per_gpu": N, "total_envs": N * h.world, "physics_steps_per_s": head["value"] * SUBSTEPS,
+                       "api": "SimEnvCreator()(ControlMode.JOINTS, ..., num_envs, shard) -> step_packed / step_async (sharded)",
+                       "exchange": "all-gather of the packed observation rows on a side stream, overlapped with the next step"
+                                   if h.distributed else "none (1 GPU)",
                        "l2": "256 MB buffer written between timed steps (L2 flush)",
                        "timing": "CUDA events per step on the launch stream, summed; max over ranks",
-                       "kernel": "rcsb_k_run", **occ},
-            "gpu_launches": int(launches),
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(N * 8 * 8),
-                    "d2h_bytes_per_step": int(N * (dm.obs_dim * 8 + dm.info_dim * 4)), "steps": e2e_steps},
+                       "kernel": "rcsb_k_run_" + str(occ["variant"]), **occ},
+            "gpu_launches": head["gpu_launches"],
+            "e2e": head.get("e2e"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (prof["dram_bytes_read"] + prof["dram_bytes_write"]) if prof else None,
-                         "peak_source": peak_src, "kernel_ms": kavg_ms,
-                         "algorithmic_bytes_per_launch": N * BYTES_PER_ENV_STEP,
-                         "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP,
-                         "ncu": ({k: prof[k] for k in ("ipc_active", "fp64_pipe_pct", "lsu_pipe_pct", "inst_executed", "source")}
+                         "peak_source": peak_src, "kernel_ms": kms,
+                         "algorithmic_bytes_per_launch": N * bpe, "algorithmic_bytes_per_env_step": bpe,
+                         "ncu": ({k: prof[k] for k in ("ipc_active", "fp64_pipe_pct", "lsu_pipe_pct", "inst_executed", "source") if k in prof}
                                  if prof else None),
                          "note": "instruction-issue / latency bound (~100 flop/B, SURVEY.md 8d): the HBM fraction is low by "
                                  "construction; ncu.ipc_active of 4 and the pipe utilisations say how busy the SMs are"},
             "clocks": clocks,
+            "sweep": sweep,
         }
-        if world == 1:
+        if h.world == 1:
             try:
                 line["cpu_baseline"] = cpu_reference(os.cpu_count() or 1, args.cpu_seconds)
             except Exception as e:  # the oracle is only a reported baseline
                 line["cpu_baseline"] = {"error": str(e)}
         print(json.dumps(line))
-    if distributed:
-        dist.destroy_process_group()
+    if h.distributed:
+        h.dist.destroy_process_group()
 
 
 def main():
@@ -313,6 +445,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-sweep", action="store_true", help="headline record only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -115,11 +115,17 @@ class Batch:
 
     def run(self, ops: int, k: int = 0, max_convergence_steps: int = 500, act_joints: torch.Tensor | None = None,
             act_gripper: torch.Tensor | None = None, mask: torch.Tensor | None = None, max_mov: float = 0.0,
-            jlow=None, jhigh=None, want_obs: bool = False, fresh_obs: bool = False):
+            jlow=None, jhigh=None, want_obs: bool = False, fresh_obs: bool = False, obs_out: torch.Tensor | None = None):
         """fresh_obs: pack the observation / info into newly allocated tensors (self.obs / self.info are rebound to
-        them), so that results returned to a caller are never overwritten by a later launch."""
-        if want_obs and fresh_obs:
+        them), so that results returned to a caller are never overwritten by a later launch. obs_out: a contiguous
+        [n, obs_dim] float64 device tensor that receives the packed observation rows instead (e.g. this rank's slice of
+        the all-gather buffer); self.obs is rebound to it."""
+        if obs_out is not None:
+            assert obs_out.shape == self.obs.shape and obs_out.dtype == torch.float64 and obs_out.is_contiguous() and obs_out.device == self.dev
+            self.obs, want_obs = obs_out, True
+        elif want_obs and fresh_obs:
             self.obs = torch.empty_like(self.obs)
+        if want_obs and fresh_obs:
             self.info = torch.empty_like(self.info)
         for t in (act_joints, act_gripper):
             if t is not None:

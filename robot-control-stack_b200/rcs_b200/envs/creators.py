@@ -12,7 +12,25 @@ class SimEnvCreator:
     def __call__(self, control_mode: ControlMode, robot_cfg: sim.SimRobotConfig, collision_guard: bool = False,
                  gripper_cfg: sim.SimGripperConfig | None = None, sim_cfg: sim.SimConfig | None = None, hand_cfg=None,
                  cameras=None, max_relative_movement: float | tuple[float, float] | None = None,
-                 relative_to: RelativeTo = RelativeTo.LAST_STEP, sim_wrapper=None, num_envs: int = 1, device: int = 0):
+                 relative_to: RelativeTo = RelativeTo.LAST_STEP, sim_wrapper=None, num_envs: int = 1, device: int | None = None,
+                 shard: bool = False):
+        """num_envs / device / shard are the additive batched extension. With shard=True under an
+        initialised torch.distributed process group (one process per GPU), num_envs is the TOTAL number of environments:
+        this rank simulates its contiguous block on GPU `device` (default: LOCAL_RANK) and step()/reset() return the
+        all-gathered [num_envs, ...] observation on every rank (rcs_b200.envs.sharded.ShardedVectorEnv)."""
+        n_total = num_envs
+        if shard:
+            import os
+            import torch.distributed as dist
+            from rcs_b200.shard import shard_range
+            if not dist.is_initialized():
+                raise RuntimeError("shard=True needs an initialised torch.distributed process group (one process per GPU)")
+            b0, e0 = shard_range(n_total, dist.get_rank(), dist.get_world_size())
+            num_envs = e0 - b0
+            if device is None:
+                device = int(os.environ.get("LOCAL_RANK", "0"))
+        if device is None:
+            device = 0
         if hand_cfg is not None:
             raise NotImplementedError("SimTilburgHand is out of scope (SURVEY.md 2 row 15)")
         if cameras is not None:
@@ -25,6 +43,9 @@ class SimEnvCreator:
         env = SimVectorEnv(simulation, robot, gripper, control_mode, max_relative_movement, relative_to)
         if sim_wrapper is not None:  # creators.py:101-103: the task layer wraps the sim env
             env = sim_wrapper(env, simulation)
+        if shard:
+            from rcs_b200.envs.sharded import ShardedVectorEnv
+            env = ShardedVectorEnv(env, n_total)
         return env
 
 

@@ -31,6 +31,7 @@ class SimVectorEnv:
         self.max_mov = max_relative_movement
         b = simulation.batch
         self.dev = b.dev
+        self.obs_dim = b.model.obs_dim
         meta = common.robots_meta_config(robot.get_config().robot_type)
         self.jlow, self.jhigh = meta.joint_limits[0].copy(), meta.joint_limits[1].copy()
         self.dof = meta.dof
@@ -71,7 +72,7 @@ class SimVectorEnv:
         self._zeros = torch.zeros(self.num_envs, dtype=torch.float64, device=self.dev)
         self._false = torch.zeros(self.num_envs, dtype=torch.bool, device=self.dev)
         # pinned host staging for the host-buffer path
-        self._h_act = self._h_grip = self._h_obs = self._h_info = None
+        self._h_obs = None
 
     # ------------------------------------------------------------------ helpers
     def _substeps(self):
@@ -87,33 +88,49 @@ class SimVectorEnv:
             ops |= _lib.ACT_GRIPPER_BIN if self.binary_gripper else _lib.ACT_GRIPPER_CONT
         return ops, cfg
 
-    def _pack(self):
-        b = self.sim.batch
-        o, f = b.obs, b.info
+    def unpack(self, o: torch.Tensor):
+        """Packed observation rows [n, obs_dim] (any n: the local block or the gathered block of all ranks) -> the
+        reference's obs / info dicts and the truncated flag. Columns: tquat 0:7, joints 7:14, xyzrpy 14:20, gripper
+        command 20, gripper width 21, then collision, ik_success, is_sim_converged, is_grasped, truncated, robot /
+        gripper collision, convergence steps as reals."""
         obs = {"tquat": o[:, 0:7], "joints": o[:, 7:7 + self.dof], "xyzrpy": o[:, 14:20]}
-        info = {"collision": f[:, 0].bool(), "ik_success": f[:, 1].bool(), "is_sim_converged": f[:, 2].bool()}
+        info = {"collision": o[:, 22] != 0, "ik_success": o[:, 23] != 0, "is_sim_converged": o[:, 24] != 0}
         if self.gripper is not None:
             obs["gripper"] = o[:, 20] if self.binary_gripper else o[:, 21]  # last command | normalised width (base.py:710-718)
             info["gripper_width"] = o[:, 21]
-            info["is_grasped"] = f[:, 3].bool()
-        return obs, info, f[:, 4].bool()
+            info["is_grasped"] = o[:, 25] != 0
+        return obs, info, o[:, 26] != 0
+
+    def _pack(self):
+        return self.unpack(self.sim.batch.obs)
 
     # ------------------------------------------------------------------ gym API
-    def reset(self, seed=None, options=None):
-        """envs/sim.py:68-76 under base.py:703-708 and base.py:462-467: gripper.reset(); sim.reset();
-        robot.reset(); sim.step(1); get_obs()."""
+    def reset_packed(self, obs_out: torch.Tensor | None = None) -> torch.Tensor:
+        """reset() that returns the packed observation rows (written into obs_out when given)."""
         b = self.sim.batch
         ops = _lib.SIM_RESET | _lib.ROBOT_RESET | _lib.ENV_RESET_FLAGS | _lib.STEP_K | _lib.OBS
         if self.gripper is not None:
             ops |= _lib.GRIPPER_RESET
-        b.run(ops, k=1, want_obs=True, fresh_obs=True)
-        obs, info, _ = self._pack()
+        b.run(ops, k=1, want_obs=True, fresh_obs=True, obs_out=obs_out)
+        return b.obs
+
+    def reset(self, seed=None, options=None):
+        """envs/sim.py:68-76 under base.py:703-708 and base.py:462-467: gripper.reset(); sim.reset();
+        robot.reset(); sim.step(1); get_obs()."""
+        b = self.sim.batch
+        obs, info, _ = self.unpack(self.reset_packed())
         if self.relative and self.relative_to == RelativeTo.CONFIGURED_ORIGIN:  # base.py:462-467
             self._origin = obs["joints"].clone()
             self._last_action = None
         return obs, {}
 
     def step(self, action: dict):
+        obs, info, truncated = self.unpack(self.step_packed(action))  # tensors allocated for this step: never overwritten later
+        return obs, torch.zeros_like(self._zeros), torch.zeros_like(self._false), truncated, info
+
+    def step_packed(self, action: dict, obs_out: torch.Tensor | None = None) -> torch.Tensor:
+        """env.step() that returns the packed observation rows [n, obs_dim] (see unpack); with obs_out the kernel writes
+        them straight into that tensor (this rank's slice of the multi-GPU gather buffer)."""
         b = self.sim.batch
         ops, cfg = self._step_ops()
         aj = ag = None
@@ -146,9 +163,8 @@ class SimVectorEnv:
             ag = action["gripper"].to(device=self.dev, dtype=torch.float64).reshape(-1).contiguous()
         b.run(ops, k=self._substeps(), max_convergence_steps=cfg.max_convergence_steps, act_joints=aj, act_gripper=ag,
               max_mov=float(self.max_mov) if (self.relative and self.control_mode == ControlMode.JOINTS) else 0.0,
-              jlow=self.jlow, jhigh=self.jhigh, want_obs=True, fresh_obs=True)
-        obs, info, truncated = self._pack()  # views of tensors allocated for this step: never overwritten later
-        return obs, torch.zeros_like(self._zeros), torch.zeros_like(self._false), truncated, info
+              jlow=self.jlow, jhigh=self.jhigh, want_obs=True, fresh_obs=True, obs_out=obs_out)
+        return b.obs
 
     def _to_pose7(self, a: torch.Tensor) -> torch.Tensor:
         a = a.to(device=self.dev, dtype=torch.float64)
@@ -162,20 +178,21 @@ class SimVectorEnv:
         return torch.cat([a[:, :3], q], dim=1).contiguous()
 
     # ------------------------------------------------------------------ host-buffer path (what a CPU-side policy sees)
-    def step_host(self, joints_host: torch.Tensor, gripper_host: torch.Tensor | None):
-        """Same step through pinned HOST buffers: H2D of the actions, the fused launch, D2H of obs/info and a
-        stream synchronise all happen inside the call. Returns (obs_host [N,22], info_host [N,8]) pinned tensors that
-        the NEXT step_host call overwrites (they are the staging buffers themselves: copy what must outlive a step)."""
+    def step_host(self, act_host: torch.Tensor) -> torch.Tensor:
+        """The same env.step() for a policy that lives on the HOST: act_host is a pinned [n, njoints + 1] float64 block
+        (joint action, then the gripper action). One H2D copy, the fused launch, one D2H copy of the packed observation
+        rows and a stream synchronise happen inside the call (C ABI rcsb_env_step_host). Returns the pinned [n, obs_dim]
+        staging tensor, which the NEXT call overwrites: unpack() / copy what must outlive a step."""
         b = self.sim.batch
-        if self.control_mode != ControlMode.JOINTS or (self.relative and self.relative_to != RelativeTo.LAST_STEP):
-            raise NotImplementedError("step_host covers joint control (absolute or relative to the last step)")
+        if self.control_mode != ControlMode.JOINTS or (self.relative and self.relative_to != RelativeTo.LAST_STEP) or self.gripper is None:
+            raise NotImplementedError("step_host covers joint control with a gripper (absolute or relative to the last step)")
         if self._h_obs is None:
             self._h_obs = torch.zeros((self.num_envs, b.model.obs_dim), dtype=torch.float64).pin_memory()
-            self._h_info = torch.zeros((self.num_envs, b.model.info_dim), dtype=torch.int32).pin_memory()
+        assert act_host.shape == (self.num_envs, self.dof + 1) and act_host.dtype == torch.float64 and act_host.is_contiguous()
         ops, cfg = self._step_ops()
-        b.run_host(ops, self._substeps(), cfg.max_convergence_steps, joints_host, gripper_host,
-                   float(self.max_mov) if self.relative else 0.0, self.jlow, self.jhigh, self._h_obs, self._h_info)
-        return self._h_obs, self._h_info
+        b.step_host(ops, self._substeps(), cfg.max_convergence_steps, act_host,
+                    float(self.max_mov) if self.relative else 0.0, self.jlow, self.jhigh, self._h_obs)
+        return self._h_obs
 
     def close(self):
         pass

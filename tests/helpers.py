@@ -13,17 +13,11 @@ for p in (ROOT, os.path.join(ROOT, "robot-control-stack_b200")):
 from rcs_b200 import mjcf  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
-MODELS = os.path.join(ROOT, "robot-control-stack_b200", "rcs_b200", "models")
-Q_HOME = np.array([0, -np.pi / 4, 0, -3 * np.pi / 4, 0, np.pi / 2, np.pi / 4])
-JLOW = np.array([-2.3093, -1.5133, -2.4937, -2.7478, -2.4800, 0.8521, -2.6895])
-JHIGH = np.array([2.3093, 1.5133, 2.4937, -0.4461, 2.4800, 4.2094, 2.6895])
-_cache = {}
+from rcs_b200 import workloads as WL  # noqa: E402
 
-
-def scene(name="fr3_empty_world"):
-    if name not in _cache:
-        _cache[name] = mjcf.load_model(os.path.join(MODELS, name + ".npz"))
-    return _cache[name]
+MODELS = WL.MODELS
+Q_HOME, JLOW, JHIGH = WL.FR3_Q_HOME, WL.FR3_JLOW, WL.FR3_JHIGH
+scene = WL.scene
 
 
 def robot_ns(tcp=(0, 0, 0, 0, 0, 0, 1.0)):
@@ -46,13 +40,7 @@ def oracle_sim(M, tcp=None):
     return m, O.Sim(m, O.robot_cfg(M, tcp_offset=tcp), O.gripper_cfg(M))
 
 
-def workload_actions(nenv, nsteps, seed=0):
-    """joints ~ U(-0.0873, 0.0873)^7, gripper ~ Bernoulli(0.5), env-major."""
-    rng = np.random.default_rng(seed)
-    a = np.zeros((nenv, nsteps, 8))
-    a[:, :, :7] = rng.uniform(-np.deg2rad(5), np.deg2rad(5), (nenv, nsteps, 7))
-    a[:, :, 7] = rng.integers(0, 2, (nenv, nsteps))
-    return a
+workload_actions = WL.workload_actions
 
 
 XARM_Q_HOME = np.array([0, -45.0, 0, 15.0, 0, -25.0, 0]) * np.pi / 180

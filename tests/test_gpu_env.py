@@ -121,9 +121,13 @@ def test_batched_relative_joint_env_async():
         q_prev = obs["joints"].clone()
     assert obs["gripper"].shape == (512,) and info["gripper_width"].shape == (512,)
     assert not bool(term.any()) and float(rew.abs().max()) == 0.0
-    h_j = torch.zeros((512, 7), dtype=torch.float64).pin_memory(); h_g = torch.ones(512, dtype=torch.float64).pin_memory()
-    ho, hi = env.step_host(h_j, h_g)
+    h_a = torch.zeros((512, 8), dtype=torch.float64).pin_memory(); h_a[:, 7] = 1
+    q_dev = obs["joints"].clone()
+    ho = env.step_host(h_a)                                    # zero relative action, gripper open, through host buffers
     assert ho.shape == (512, 30) and np.isfinite(ho.numpy()).all()
+    oh, ih, trunc_h = env.unpack(ho)
+    assert float((oh["joints"] - q_dev.cpu()).abs().max()) < 0.05 and bool(ih["ik_success"].all()) and not bool(trunc_h.any())
+    assert torch.equal(ho, env.sim.batch.obs.cpu()[:, :30])   # the host block is the device's packed observation
 
 
 @pytest.mark.parametrize("mode_name", ["CARTESIAN_TRPY", "CARTESIAN_TQuat"])
