@@ -44,7 +44,7 @@ struct Ctx {
 #endif
 
 // misc int slots in the workspace
-enum { MI_NCON = 0, MI_NEFC, MI_NE, MI_NF, MI_NL, MI_HAVE_L, MI_SOLVER_ITER, MI_WARN, MI_OVERFLOW, MI_HAVE_H2, MI_COUNT };
+enum { MI_NCON = 0, MI_NEFC, MI_NE, MI_NF, MI_NL, MI_HAVE_L, MI_SOLVER_ITER, MI_WARN, MI_OVERFLOW, MI_HAVE_H2, MI_COUPLED, MI_COUNT };
 
 #define WR(name) (CW(c) + LAY.o_##name)
 #define WI(name) (CWI(c) + LAY.oi_##name)

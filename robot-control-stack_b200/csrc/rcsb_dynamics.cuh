@@ -15,7 +15,7 @@
 // (right-looking, no shared-memory round trips, no barriers inside the factorisation). The host-emulation build
 // keeps the plain column version (one lane).
 #ifdef RCSB_HOST_EMU
-RCSB_DEV_NOINLINE void chol_factor(const Ctx& c, real* A, real* dinv, int n) {
+RCSB_DEV_NOINLINE void chol_factor(const Ctx& c, real* A, real* dinv, int n, int blocks = 0) {
   for (int j = 0; j < n; j++) {
     real d = A[j * n + j];
     for (int k = 0; k < j; k++) d -= A[j * n + k] * A[j * n + k];
@@ -43,10 +43,19 @@ RCSB_DEV_NOINLINE void chol_solve(const Ctx& c, const real* L, const real* dinv,
   }
 }
 // factor A in place and solve A x = b for x (in place); when A1 is given, factor it too (same size, no solve)
-RCSB_DEV_NOINLINE void chol_factor_solve(const Ctx& c, real* A, real* dinv, int n, real* x, real* y, real* A1, real* dinv1) {
+RCSB_DEV_NOINLINE void chol_factor_solve(const Ctx& c, real* A, real* dinv, int n, real* x, real* y, real* A1, real* dinv1,
+                                         int blocks = 0) {
   chol_factor(c, A, dinv, n);
   chol_solve(c, A, dinv, n, x, y);
   if (A1) chol_factor(c, A1, dinv1, n);
+}
+// x <- (L L^T)^{-1} x for a factor that is block diagonal by kinematic tree (dense substitution handles it as is)
+RCSB_DEV_NOINLINE void chol_solve_blocks(const Ctx& c, const real* L, const real* dinv, int n, real* x, real* y) {
+  chol_solve(c, L, dinv, n, x, y);
+}
+// X[r] <- (L L^T)^{-1} X[r] for nrhs right-hand sides (rows of X, row stride n)
+RCSB_DEV_NOINLINE void chol_solve_multi(const Ctx& c, const real* L, const real* dinv, int n, real* X, int nrhs, real* y) {
+  for (int r = 0; r < nrhs; r++) chol_solve(c, L, dinv, n, X + r * n, y);
 }
 #else
 // Half-warp formulation for N <= 16: lanes 0..15 hold system 0, lanes 16..31 system 1 (when present); lane li owns row
@@ -135,9 +144,101 @@ RCSB_DEV void chol_solve_n(const Ctx& c, const real* L, const real* dinv, real* 
   xi = chol_rows_solve<N>(li, a, col, xi, lo, hi);
   if (on) x[li] = xi;
 }
-RCSB_DEV_NOINLINE void chol_factor(const Ctx& c, real* A, real* dinv, int n) {
+// ---- matrices that are block diagonal by kinematic tree (M always; the constraint Hessian while no constraint row
+// couples two trees; the implicit integrator's matrix): two blocks are factored / solved at a time, one per half-warp,
+// with the rows-in-registers scheme above. N bounds the block size at compile time; a block smaller than N is padded
+// with identity rows. Off-block entries of the storage are left as they are (zeros): the result is the Cholesky factor
+// of the whole matrix, so the dense triangular solves stay valid on it.
+template <int N>
+RCSB_DEV void chol_pair(const Ctx& c, real* A, real* dinv, int n, int lo0, int n0, int lo1, int n1, real* x) {
+  const int li = c.lane & 15, half = c.lane >> 4;
+  const int lo = half ? lo1 : lo0, nb = half ? n1 : n0;
+  const bool on = li < nb;
+  real a[N], col[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) a[k] = (on && k <= li) ? A[(lo + li) * n + lo + k] : (k == li ? (real)1 : (real)0);
+  chol_rows_factor<N>(li, a);
+  if (on) {
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      if (k < li) A[(lo + li) * n + lo + k] = a[k];
+      else if (k == li) dinv[lo + li] = a[k];
+    }
+  }
+  if (x == nullptr) return;
+  RCSB_SYNC();
+#pragma unroll
+  for (int j = 0; j < N; j++) col[j] = (on && j > li && j < nb) ? A[(lo + j) * n + lo + li] : (real)0;
+  real xi = on ? x[lo + li] : (real)0;
+  xi = chol_rows_solve<N>(li, a, col, xi);
+  if (on) x[lo + li] = xi;
+}
+template <int N>
+RCSB_DEV void chol_pair_solve(const Ctx& c, const real* L, const real* dinv, int n, int lo0, int n0, int lo1, int n1, real* x) {
+  const int li = c.lane & 15, half = c.lane >> 4;
+  const int lo = half ? lo1 : lo0, nb = half ? n1 : n0;
+  const bool on = li < nb;
+  real a[N], col[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    a[k] = (on && k < li) ? L[(lo + li) * n + lo + k] : (real)0;
+    col[k] = (on && k > li && k < nb) ? L[(lo + k) * n + lo + li] : (real)0;
+  }
+  const real di = on ? dinv[lo + li] : (real)1;
+#pragma unroll
+  for (int k = 0; k < N; k++) if (k == li) a[k] = di;
+  real xi = on ? x[lo + li] : (real)0;
+  xi = chol_rows_solve<N>(li, a, col, xi);
+  if (on) x[lo + li] = xi;
+}
+// tree blocks of the dof range [0, n): returns the count (0 when the trees' dofs are not contiguous blocks <= 9 wide)
+RCSB_DEV int tree_blocks(const RcsbModel& m, int n, int* lo, int* sz) {
+  int nt = 0;
+  for (int j = 0; j < n;) {
+    const int hi = m.d_tree_hi[j];
+    if (m.d_tree_lo[j] != j || hi <= j || hi - j > 9 || nt >= RCSB_MAXROOT) return 0;
+    lo[nt] = j; sz[nt] = hi - j; nt++;
+    j = hi;
+  }
+  return nt;
+}
+// factor (and optionally solve x in place) block by block; returns 0 when the model has no usable block structure
+RCSB_DEV int chol_blocks(const Ctx& c, real* A, real* dinv, int n, real* x) {
+  const RcsbModel& m = CMODEL(c);
+  if (MD(nroot) < 2) return 0;
+  int lo[RCSB_MAXROOT], sz[RCSB_MAXROOT];
+  const int nt = tree_blocks(m, n, lo, sz);
+  if (nt < 2) return 0;
+  RCSB_SYNC();
+  for (int t = 0; t < nt; t += 2) {
+    const int n0 = sz[t], n1 = t + 1 < nt ? sz[t + 1] : 0, l1 = t + 1 < nt ? lo[t + 1] : 0;
+    const int mx = n0 > n1 ? n0 : n1;
+    if (mx <= 7) chol_pair<7>(c, A, dinv, n, lo[t], n0, l1, n1, x);
+    else chol_pair<9>(c, A, dinv, n, lo[t], n0, l1, n1, x);
+  }
+  RCSB_SYNC();
+  return 1;
+}
+RCSB_DEV int chol_blocks_solve(const Ctx& c, const real* L, const real* dinv, int n, real* x) {
+  const RcsbModel& m = CMODEL(c);
+  if (MD(nroot) < 2) return 0;
+  int lo[RCSB_MAXROOT], sz[RCSB_MAXROOT];
+  const int nt = tree_blocks(m, n, lo, sz);
+  if (nt < 2) return 0;
+  RCSB_SYNC();
+  for (int t = 0; t < nt; t += 2) {
+    const int n0 = sz[t], n1 = t + 1 < nt ? sz[t + 1] : 0, l1 = t + 1 < nt ? lo[t + 1] : 0;
+    const int mx = n0 > n1 ? n0 : n1;
+    if (mx <= 7) chol_pair_solve<7>(c, L, dinv, n, lo[t], n0, l1, n1, x);
+    else chol_pair_solve<9>(c, L, dinv, n, lo[t], n0, l1, n1, x);
+  }
+  RCSB_SYNC();
+  return 1;
+}
+RCSB_DEV_NOINLINE void chol_factor(const Ctx& c, real* A, real* dinv, int n, int blocks = 0) {
   __builtin_assume(__isShared(A));
   __builtin_assume(__isShared(dinv));
+  if (blocks && chol_blocks(c, A, dinv, n, nullptr)) return;
   RCSB_SYNC();
   switch (n) {  // dof counts of the supported scenes: xArm7 (7), FR3 + fingers (9), FR3 + fingers + free cube (15)
     case 7: chol_n<7>(c, A, dinv, nullptr, nullptr, nullptr); break;
@@ -192,10 +293,19 @@ RCSB_DEV_NOINLINE void chol_solve(const Ctx& c, const real* L, const real* dinv,
   RCSB_SYNC();
 }
 // factor A in place and solve A x = b for x (in place); when A1 is given, factor it too in the other half-warp
-RCSB_DEV_NOINLINE void chol_factor_solve(const Ctx& c, real* A, real* dinv, int n, real* x, real* y, real* A1, real* dinv1) {
+RCSB_DEV_NOINLINE void chol_factor_solve(const Ctx& c, real* A, real* dinv, int n, real* x, real* y, real* A1, real* dinv1,
+                                         int blocks = 0) {
   __builtin_assume(__isShared(A));
   __builtin_assume(__isShared(dinv));
   __builtin_assume(__isShared(x));
+  if (blocks && chol_blocks(c, A, dinv, n, x)) {  // A1 (the integrator's matrix) is block diagonal whenever A is
+    if (A1) {
+      __builtin_assume(__isShared(A1));
+      __builtin_assume(__isShared(dinv1));
+      chol_blocks(c, A1, dinv1, n, nullptr);
+    }
+    return;
+  }
   RCSB_SYNC();
   switch (n) {
     case 7: chol_n<7>(c, A, dinv, x, A1, dinv1); break;
@@ -206,6 +316,44 @@ RCSB_DEV_NOINLINE void chol_factor_solve(const Ctx& c, real* A, real* dinv, int 
       chol_solve(c, A, dinv, n, x, y);
       if (A1) chol_factor(c, A1, dinv1, n);
       return;
+  }
+  RCSB_SYNC();
+}
+// x <- (L L^T)^{-1} x for a factor that is block diagonal by kinematic tree: both half-warps solve a block each
+RCSB_DEV_NOINLINE void chol_solve_blocks(const Ctx& c, const real* L, const real* dinv, int n, real* x, real* y) {
+  __builtin_assume(__isShared(L));
+  __builtin_assume(__isShared(dinv));
+  __builtin_assume(__isShared(x));
+  if (chol_blocks_solve(c, L, dinv, n, x)) return;
+  chol_solve(c, L, dinv, n, x, y);
+}
+// X[r] <- (L L^T)^{-1} X[r] for nrhs right-hand sides (rows of X, row stride n), one right-hand side per lane: serial
+// substitution restricted to the kinematic trees the row touches (L is block diagonal by tree). The noslip pass needs
+// M^-1 J^T for every friction row; solving them side by side replaces one warp-wide solve per row.
+RCSB_DEV_NOINLINE void chol_solve_multi(const Ctx& c, const real* L, const real* dinv, int n, real* X, int nrhs, real* y) {
+  const RcsbModel& m = CMODEL(c);
+  __builtin_assume(__isShared(L));
+  __builtin_assume(__isShared(dinv));
+  __builtin_assume(__isShared(X));
+  RCSB_SYNC();
+  PFOR(r, nrhs) {
+    real* x = X + r * n;
+    int lo = n, hi = 0;
+    for (int k = 0; k < n; k++)
+      if (x[k] != 0) {
+        lo = m.d_tree_lo[k] < lo ? m.d_tree_lo[k] : lo;
+        hi = m.d_tree_hi[k] > hi ? m.d_tree_hi[k] : hi;
+      }
+    for (int j = lo; j < hi; j++) {  // forward: L z = x
+      const real z = x[j] * dinv[j];
+      x[j] = z;
+      for (int i = j + 1; i < hi; i++) x[i] -= L[i * n + j] * z;
+    }
+    for (int j = hi - 1; j >= lo; j--) {  // backward: L^T w = z
+      const real w = x[j] * dinv[j];
+      x[j] = w;
+      for (int i = lo; i < j; i++) x[i] -= L[j * n + i] * w;
+    }
   }
   RCSB_SYNC();
 }

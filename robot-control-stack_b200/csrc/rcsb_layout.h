@@ -133,7 +133,7 @@ RCSB_HD constexpr RcsbLayout rcsb_make_layout(const RcsbShape& s) {
   o = 0;
   RCSB_ALLOC(oi_con, RCSB_CI_INTS * s.maxcon);
   RCSB_ALLOC(oi_efc, RCSB_EI_NARR * s.maxefc);
-  RCSB_ALLOC(oi_misc, 10 /* MI_COUNT */ + RCSB_I_TAIL);
+  RCSB_ALLOC(oi_misc, 11 /* MI_COUNT */ + RCSB_I_TAIL);
   y.ws_ints = (o + 3) & ~3;
 #undef RCSB_ALLOC
 #undef RCSB_MAX

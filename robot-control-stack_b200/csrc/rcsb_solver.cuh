@@ -91,7 +91,19 @@ RCSB_DEV void st_make_constraint(const Ctx& c) {
     }
     if (c.lane == 0) cii[RCSB_CI_EFC] = addr;
   }
-  if (c.lane == 0) { WI(misc)[MI_NEFC] = nefc; WI(misc)[MI_NE] = ne; WI(misc)[MI_NF] = nf; WI(misc)[MI_NL] = nl; }
+  // does any constraint row couple two kinematic trees? (while none does, the constraint Hessian stays block diagonal by
+  // tree like M itself, and the solver factors the blocks side by side)
+  int coupled = 0;
+  if (MD(nroot) > 1) {
+    for (int e = 0; e < MD(neq); e++)
+      if (m.e_active[e] && m.e_dof2[e] >= 0 && m.d_tree_lo[m.e_dof1[e]] != m.d_tree_lo[m.e_dof2[e]]) coupled = 1;
+    for (int ci = 0; ci < ncon; ci++) {
+      const int* cii = WI(con) + RCSB_CI_INTS * ci;
+      const int b1 = m.g_body[cii[RCSB_CI_G0]], b2 = m.g_body[cii[RCSB_CI_G1]];
+      if (b1 >= 0 && b2 >= 0 && m.b_root[b1] != m.b_root[b2]) coupled = 1;
+    }
+  }
+  if (c.lane == 0) { WI(misc)[MI_NEFC] = nefc; WI(misc)[MI_NE] = ne; WI(misc)[MI_NF] = nf; WI(misc)[MI_NL] = nl; WI(misc)[MI_COUPLED] = coupled; }
   RCSB_SYNC();
   // ---- Jacobian
   PFOR(e, nefc * nv) {
@@ -273,7 +285,7 @@ RCSB_DEV void ensure_chol_M(const Ctx& c) {
   if (!WI(misc)[MI_HAVE_L]) {
     if (c.lane == 0) WI(misc)[MI_HAVE_H2] = 0;  // o_L is about to hold M's factor
     PFOR(e, MD(nv) * MD(nv)) { WR(L)[e] = WR(M)[e]; }
-    chol_factor(c, WR(L), WR(L) + MD(nv) * MD(nv), MD(nv));
+    chol_factor(c, WR(L), WR(L) + MD(nv) * MD(nv), MD(nv), 1);  // M is block diagonal by kinematic tree
     if (c.lane == 0) WI(misc)[MI_HAVE_L] = 1;
     RCSB_SYNC();
   }
@@ -283,7 +295,7 @@ RCSB_DEV void compute_qacc_smooth(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
   ensure_chol_M(c);
   PFOR(k, MD(nv)) { WR(qacc_smooth)[k] = WR(smooth)[k]; }
-  chol_solve(c, WR(L), WR(L) + MD(nv) * MD(nv), MD(nv), WR(qacc_smooth), WR(tmp));
+  chol_solve_blocks(c, WR(L), WR(L) + MD(nv) * MD(nv), MD(nv), WR(qacc_smooth), WR(tmp));
 }
 
 // ------------------------------------------------------------------ constraint cost, forces, states
@@ -512,23 +524,13 @@ RCSB_DEV_NOINLINE void solve_noslip(const Ctx& c, int nefc, int ncon) {
   // M^-1 J^T of every friction row: [friction-loss rows | 2 rows per contact]
   real* MinvJ = WR(noslip);
   real* Ablk = MinvJ + (nf + 2 * MD(maxcon)) * nv;  // 1 value per dof-friction row, 4 per contact
-  for (int i = 0; i < nf; i++) {
-    PFOR(k, nv) { MinvJ[i * nv + k] = WR(J)[(ne + i) * nv + k]; }
-    int lo, hi;
-    row_dof_range(c, WR(J) + (ne + i) * nv, &lo, &hi);
-    chol_solve(c, WR(L), WR(L) + nv * nv, nv, MinvJ + i * nv, WR(tmp), lo, hi);
-  }
+  PFOR(e, nf * nv) { MinvJ[e] = WR(J)[ne * nv + e]; }
   for (int ci = 0; ci < ncon; ci++) {
-    int a = WI(con)[RCSB_CI_INTS * ci + RCSB_CI_EFC];
-    if (a < 0 || WI(con)[RCSB_CI_INTS * ci + RCSB_CI_DIM] < 3) continue;
-    for (int j = 0; j < 2; j++) {
-      real* x = MinvJ + (nf + 2 * ci + j) * nv;
-      PFOR(k, nv) { x[k] = WR(J)[(a + 1 + j) * nv + k]; }
-      int lo, hi;
-      row_dof_range(c, WR(J) + (a + 1 + j) * nv, &lo, &hi);
-      chol_solve(c, WR(L), WR(L) + nv * nv, nv, x, WR(tmp), lo, hi);
-    }
+    const int a = WI(con)[RCSB_CI_INTS * ci + RCSB_CI_EFC];
+    const int live = a >= 0 && WI(con)[RCSB_CI_INTS * ci + RCSB_CI_DIM] >= 3;
+    PFOR(e, 2 * nv) { MinvJ[(nf + 2 * ci) * nv + e] = live ? WR(J)[(a + 1) * nv + e] : (real)0; }
   }
+  chol_solve_multi(c, WR(L), WR(L) + nv * nv, nv, MinvJ, nf + 2 * ncon, WR(tmp));  // all friction rows side by side
   RCSB_SYNC();
   PFOR(i, nf) {
     real s = 0;
@@ -615,7 +617,7 @@ RCSB_DEV_NOINLINE void solve_noslip(const Ctx& c, int nefc, int ncon) {
     if (improvement * scale < m.noslip_tolerance) break;
   }
   PFOR(k, nv) { WR(qacc)[k] = WR(qfc)[k]; }
-  chol_solve(c, WR(L), WR(L) + nv * nv, nv, WR(qacc), WR(tmp));
+  chol_solve_blocks(c, WR(L), WR(L) + nv * nv, nv, WR(qacc), WR(tmp));
   PFOR(k, nv) { WR(qacc)[k] += WR(qacc_smooth)[k]; }
   RCSB_SYNC();
 }
@@ -660,7 +662,7 @@ RCSB_DEV_NOINLINE void newton_solve(const Ctx& c, int nefc, int ncon) {
       WR(H)[b * nv + a] = h;
     }
     PFOR(k, nv) { WR(search)[k] = WR(grad)[k]; }
-    chol_factor_solve(c, WR(H), WR(H) + nv * nv, nv, WR(search), WR(tmp), nullptr, nullptr);
+    chol_factor_solve(c, WR(H), WR(H) + nv * nv, nv, WR(search), WR(tmp), nullptr, nullptr, !WI(misc)[MI_COUPLED]);
     PFOR(k, nv) { WR(search)[k] = -WR(search)[k]; }
     RCSB_SYNC();
     real qG1 = 0, qG2 = 0, sn = 0;
@@ -775,7 +777,8 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
       // idle half of the warp (o_L is free here: M's own factor is only needed by the Newton / noslip path)
       const int dual = attempt == 0 && nv <= 16 && !WI(misc)[MI_HAVE_L] && !need_noslip;
       if (dual) build_integrator_matrix(c, WR(L));
-      chol_factor_solve(c, WR(H), WR(H) + nv * nv, nv, WR(qacc), WR(tmp), dual ? WR(L) : nullptr, dual ? WR(L) + nv * nv : nullptr);
+      chol_factor_solve(c, WR(H), WR(H) + nv * nv, nv, WR(qacc), WR(tmp), dual ? WR(L) : nullptr, dual ? WR(L) + nv * nv : nullptr,
+                        !WI(misc)[MI_COUPLED]);
       if (dual && c.lane == 0) WI(misc)[MI_HAVE_H2] = 1;
       int changed = 0, on_cone = 0;
       PFOR(r, nefc) {
@@ -874,10 +877,10 @@ RCSB_DEV void st_integrate(const Ctx& c) {
   const real h = m.timestep;
   PFOR(k, nv) { WR(search)[k] = WR(smooth)[k] + WR(qfc)[k]; }
   if (WI(misc)[MI_HAVE_H2]) {  // factored next to the constraint Hessian (st_constraint_solve)
-    chol_solve(c, WR(L), WR(L) + nv * nv, nv, WR(search), WR(tmp));
+    chol_solve_blocks(c, WR(L), WR(L) + nv * nv, nv, WR(search), WR(tmp));
   } else {
     build_integrator_matrix(c, WR(H));
-    chol_factor_solve(c, WR(H), WR(H) + nv * nv, nv, WR(search), WR(tmp), nullptr, nullptr);
+    chol_factor_solve(c, WR(H), WR(H) + nv * nv, nv, WR(search), WR(tmp), nullptr, nullptr, 1);
   }
   PFOR(k, nv) { WR(v)[k] += h * WR(search)[k]; }  // qacc_warmstart was saved by the constraint solve, before noslip
   RCSB_SYNC();
