@@ -240,9 +240,10 @@ RCSB_DEV_NOINLINE void chol_factor(const Ctx& c, real* A, real* dinv, int n, int
   __builtin_assume(__isShared(dinv));
   if (blocks && chol_blocks(c, A, dinv, n, nullptr)) return;
   RCSB_SYNC();
-  switch (n) {  // dof counts of the supported scenes: xArm7 (7), FR3 + fingers (9), FR3 + fingers + free cube (15)
+  switch (n) {  // dof counts of the supported scenes: xArm7 (7), FR3 + fingers (9), xArm7 + brick (13), FR3 + fingers + cube (15)
     case 7: chol_n<7>(c, A, dinv, nullptr, nullptr, nullptr); break;
     case 9: chol_n<9>(c, A, dinv, nullptr, nullptr, nullptr); break;
+    case 13: chol_n<13>(c, A, dinv, nullptr, nullptr, nullptr); break;
     case 15: chol_n<15>(c, A, dinv, nullptr, nullptr, nullptr); break;
     default:  // any other size: column version on shared memory
       for (int j = 0; j < n; j++) {
@@ -273,6 +274,7 @@ RCSB_DEV_NOINLINE void chol_solve(const Ctx& c, const real* L, const real* dinv,
   switch (n) {
     case 7: chol_solve_n<7>(c, L, dinv, x, lo, hi); break;
     case 9: chol_solve_n<9>(c, L, dinv, x, lo, hi); break;
+    case 13: chol_solve_n<13>(c, L, dinv, x, lo, hi); break;
     case 15: chol_solve_n<15>(c, L, dinv, x, lo, hi); break;
     default: {
       real xi = lane < n ? x[lane] : (real)0;
@@ -310,6 +312,7 @@ RCSB_DEV_NOINLINE void chol_factor_solve(const Ctx& c, real* A, real* dinv, int 
   switch (n) {
     case 7: chol_n<7>(c, A, dinv, x, A1, dinv1); break;
     case 9: chol_n<9>(c, A, dinv, x, A1, dinv1); break;
+    case 13: chol_n<13>(c, A, dinv, x, A1, dinv1); break;
     case 15: chol_n<15>(c, A, dinv, x, A1, dinv1); break;
     default:
       chol_factor(c, A, dinv, n);

@@ -12,7 +12,7 @@
 #endif
 #define RCSB_VARIANT_NS rcsb_fr3_pickup
 #define RCSB_KERNEL rcsb_k_run_fr3_pickup
-#define RCSB_FIXED_SHAPE {16, 15, 8, 10, 25, 206, 1, 1, 2, 4, 17, 7, 1, 1, 5, 1, 1, 47}
+#define RCSB_FIXED_SHAPE {16, 15, 8, 10, 25, 206, 1, 1, 2, 4, 17, 7, 1, 1, 5, 1, 1, 47, 0}
 #define RCSB_VARIANT_WARPS 12  // what the layout leaves room for: registers per thread follow from it
 #include "rcsb_variant.cuh"
 #undef RCSB_VARIANT_NS

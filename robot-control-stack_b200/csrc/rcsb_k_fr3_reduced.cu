@@ -9,7 +9,7 @@
 #include "rcsb_ctx.cuh"
 #include "rcsb_stage.cuh"
 #endif
-#define RCSB_SHAPE_FR3(maxcon, maxefc, reduced) {9, 9, 8, 9, 24, 182, 1, 1, 1, maxcon, maxefc, 7, 1, 1, 5, reduced, 1, 37}
+#define RCSB_SHAPE_FR3(maxcon, maxefc, reduced) {9, 9, 8, 9, 24, 182, 1, 1, 1, maxcon, maxefc, 7, 1, 1, 5, reduced, 1, 37, 0}
 #define RCSB_VARIANT_NS rcsb_fr3_reduced
 #define RCSB_KERNEL rcsb_k_run_fr3_reduced
 #define RCSB_FIXED_SHAPE RCSB_SHAPE_FR3(1, 8, 1)

@@ -40,6 +40,7 @@
 #include "rcsb_k_fr3_reduced.cu"
 #include "rcsb_k_fr3_full.cu"
 #include "rcsb_k_fr3_pickup.cu"
+#include "rcsb_k_xarm7_tabletop.cu"
 #else
 #define RCSB_DECLARE_VARIANT(ns)                                                                                        \
   namespace ns {                                                                                                        \
@@ -51,6 +52,7 @@
 RCSB_DECLARE_VARIANT(rcsb_fr3_reduced)
 RCSB_DECLARE_VARIANT(rcsb_fr3_full)
 RCSB_DECLARE_VARIANT(rcsb_fr3_pickup)
+RCSB_DECLARE_VARIANT(rcsb_xarm7_tabletop)
 #endif
 #endif
 
@@ -68,6 +70,7 @@ static RcsbVariant pick_variant(const RcsbModel& h) {
     if (shape_equal(s, rcsb_fr3_reduced::shape())) return {"fr3_reduced", 1, s, rcsb_fr3_reduced::launch, rcsb_fr3_reduced::set_smem, rcsb_fr3_reduced::max_warps()};
     if (shape_equal(s, rcsb_fr3_full::shape())) return {"fr3_full", 1, s, rcsb_fr3_full::launch, rcsb_fr3_full::set_smem, rcsb_fr3_full::max_warps()};
     if (shape_equal(s, rcsb_fr3_pickup::shape())) return {"fr3_pickup", 1, s, rcsb_fr3_pickup::launch, rcsb_fr3_pickup::set_smem, rcsb_fr3_pickup::max_warps()};
+    if (shape_equal(s, rcsb_xarm7_tabletop::shape())) return {"xarm7_tabletop", 1, s, rcsb_xarm7_tabletop::launch, rcsb_xarm7_tabletop::set_smem, rcsb_xarm7_tabletop::max_warps()};
 #endif
   }
   return {"generic", 0, s, rcsb_generic::launch, rcsb_generic::set_smem, rcsb_generic::max_warps()};

@@ -117,8 +117,8 @@ RCSB_HD constexpr RcsbLayout rcsb_make_layout(const RcsbShape& s) {
   RCSB_ALLOC(o_H, nv * nv + nv); RCSB_ALLOC(o_L, nv * nv + nv);
   RCSB_ALLOC(o_grad, nv); RCSB_ALLOC(o_search, nv); RCSB_ALLOC(o_Ma, nv); RCSB_ALLOC(o_Mv, nv);
   RCSB_ALLOC(o_tmp, RCSB_MAX(nv, RCSB_MAXJ) + 2);  // triangular-solve scratch (host emulation), action staging
-  RCSB_ALLOC(o_conehess, 9 * s.maxcon);
-  RCSB_ALLOC(o_noslip, (nv + 2 * s.maxcon) * nv + nv + 4 * s.maxcon);
+  RCSB_ALLOC(o_conehess, s.cone_elliptic ? 9 * s.maxcon : 0);
+  RCSB_ALLOC(o_noslip, s.noslip_iterations > 0 ? (s.nfl + 2 * s.maxcon) * nv + s.nfl + 4 * s.maxcon : 0);  // M^-1 J^T of every friction row + diagonal blocks
   if (o < k_end) o = k_end;
   RCSB_ALLOC(o_M, nv * nv);
   RCSB_ALLOC(o_bias, nv); RCSB_ALLOC(o_passive, nv); RCSB_ALLOC(o_gravc, nv); RCSB_ALLOC(o_actfrc, nv);
@@ -155,7 +155,7 @@ static inline void rcsb_host_quat_to_mat(real* M, const real* q) {  // same expr
 }
 static inline RcsbShape rcsb_model_shape(const RcsbModel* m) {
   RcsbShape s = {m->nq, m->nv, m->nu, m->nb, m->ng, m->npair, m->nt, m->neq, m->nroot, m->maxcon, m->maxefc, m->rb_njoints,
-                 m->cone_elliptic, m->implicitfast, m->noslip_iterations, m->cap_reduced, m->gr_enabled, m->ngrp};
+                 m->cone_elliptic, m->implicitfast, m->noslip_iterations, m->cap_reduced, m->gr_enabled, m->ngrp, m->nfl};
   return s;
 }
 static inline int rcsb_model_finalize_layout(RcsbModel* m) {
@@ -217,6 +217,8 @@ static inline int rcsb_model_finalize_layout(RcsbModel* m) {
       }
     }
   }
+  m->nfl = 0;
+  for (int j = 0; j < m->nv; j++) m->nfl += m->d_frictionloss[j] > 0;
   m->lay = rcsb_make_layout(rcsb_model_shape(m));
   for (int a = 0; a < RCSB_MAXU; a++)
     for (int k = 0; k < RCSB_MAXV; k++) {

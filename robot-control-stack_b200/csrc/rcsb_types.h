@@ -88,12 +88,13 @@ struct RcsbLayout {
 // The part of a model that fixes code shape: loop bounds, workspace layout, enabled features.
 struct RcsbShape {
   int nq, nv, nu, nb, ng, npair, nt, neq, nroot, maxcon, maxefc, rb_njoints, cone_elliptic, implicitfast,
-      noslip_iterations, cap_reduced, gr_enabled, ngrp;
+      noslip_iterations, cap_reduced, gr_enabled, ngrp, nfl;  // nfl: dofs with friction loss (rows of the noslip workspace)
 };
 
 struct RcsbModel {
   // ---- sizes / options
   int nq, nv, nu, nb, ng, npair, nt, neq, nroot, nmeshvert;
+  int nfl;  // dofs with frictionloss > 0, derived in rcsb_model_finalize_layout
   int cone_elliptic, implicitfast, iterations, ls_iterations, noslip_iterations;
   int maxcon, maxefc;  // per-env capacities of the contact / constraint workspaces
   // Two workspace layouts share one kernel: the full-capacity one above and a reduced one (fast_maxcon / fast_maxefc,

@@ -27,5 +27,6 @@ scenes: dict[str, Scene] = {
                 mjcf_robot=os.path.join(_MODELS, name + ".npz"), urdf=None, robot_type=common.RobotType.FR3)
     for name in ("fr3_empty_world", "fr3_simple_pick_up")
 }
-scenes["xarm7_empty_world"] = Scene(mjb=os.path.join(_MODELS, "xarm7_empty_world.npz"), mjcf_scene=os.path.join(_MODELS, "xarm7_empty_world.npz"),
-                                    mjcf_robot=os.path.join(_MODELS, "xarm7_empty_world.npz"), urdf=None, robot_type=common.RobotType.XArm7)
+for _name in ("xarm7_empty_world", "xarm7_tabletop"):  # xarm7_tabletop: synthetic config C4 (tools/scenes/xarm7_tabletop.xml)
+    scenes[_name] = Scene(mjb=os.path.join(_MODELS, _name + ".npz"), mjcf_scene=os.path.join(_MODELS, _name + ".npz"),
+                          mjcf_robot=os.path.join(_MODELS, _name + ".npz"), urdf=None, robot_type=common.RobotType.XArm7)

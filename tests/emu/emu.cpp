@@ -75,6 +75,11 @@ int emu_run(const EmuModel* em, const real* verts, real* sr, double* sd, int* si
   }
   return handed;
 }
+// the RcsbShape of a model (what a fixed-shape kernel variant must be compiled for), 19 ints
+void emu_shape(const EmuModel* em, int reduced, int* out) {
+  RcsbShape s = rcsb_model_shape(reduced ? &em->reduced : &em->full);
+  memcpy(out, &s, sizeof(RcsbShape));
+}
 int emu_offset(const EmuModel* em, const char* name, int reduced) {
   const RcsbModel* m = reduced ? &em->reduced : &em->full;
 #define OFF(n) if (!strcmp(name, #n)) return m->lay.o_##n;

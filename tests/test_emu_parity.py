@@ -241,3 +241,38 @@ def test_grasp_and_lift_contacts_and_state():
     print("grasp: peak ncon", peak, "worst |dq|", worst)
     assert peak >= 30, peak
     assert s.data.qpos[11] > 0.12 and e.sr[0, 11] > 0.12  # the cube went up with the gripper
+
+
+def test_xarm7_tabletop_brick_contacts_friction_loss_pyramidal():
+    """Synthetic config C4 (tools/scenes/xarm7_tabletop.xml): xArm7 + table + one free duplo brick. Every step carries 7
+    friction-loss rows, 4 box-box contacts brick-table as pyramidal cones (16 rows, regulariser 2 mu^2 R) and the
+    block-diagonal (arm | brick) solver path; random joint targets. Contact pairs exact, state 1e-7."""
+    M = H.scene("xarm7_tabletop")
+    F, verts = devmodel.build_device_fields(M, H.xarm_robot_ns(), None)
+    N = 4
+    e = _emu(M, F, verts, N)
+    e.enable_contact_export(cap=16)
+    assert e.has_reduced
+    rng = np.random.default_rng(7)
+    q0 = np.tile(M["qpos0"], (N, 1)).astype(float)
+    q0[:, :7] = H.XARM_Q_HOME + rng.uniform(-0.2, 0.2, (N, 7))
+    q0[:, 7:9] += rng.uniform(-0.03, 0.03, (N, 2))
+    q0[1, 9] += 0.01                                   # this brick is dropped from 1 cm
+    ctrl = q0[:, :7] + rng.uniform(-0.1, 0.1, (N, 7))
+    e.sr[:, :14] = q0; e.sr[:, 27:34] = ctrl
+    m = O.Model(M)
+    ds = []
+    for i in range(N):
+        d = O.Data(m); d.qpos[:] = q0[i]; d.ctrl[:] = ctrl[i]; ds.append(d)
+    seen = 0
+    for it in range(20):
+        e.run(["STEP_K"], k=10)
+        for i, d in enumerate(ds):
+            d.step(10)
+            n = int(d.ncon[0])
+            seen = max(seen, n)
+            assert int(e.contact_n[i]) == n and int(e.si[i, 15]) == int(d.nefc[0]), (it, i)
+            assert np.array_equal(e.contact_geom[i, :n], d.int("contact_geom").reshape(-1, 2))
+            assert np.abs(e.sr[i, :14] - d.qpos).max() < 1e-7, (it, i)
+            assert np.abs(e.sr[i, 14:27] - d.qvel).max() < 1e-5, (it, i)
+    assert seen == 4 and int(e.si[:, 17].max()) == 0

@@ -396,3 +396,49 @@ def test_grasp_and_lift_parity(setup):
     assert peak >= 30
     assert s.data.qpos[11] > 0.12 and (b.qpos[:, 11] > 0.12).all()
     assert 0.3 < s.gripper_get_normalized_width() < 0.5 and bool(b.info[0, 3])  # held open by the 32 mm cube
+
+
+def test_xarm7_tabletop_parity_and_arm_brick_push(setup):
+    """Synthetic config C4 (tools/scenes/xarm7_tabletop.xml) on the GPU: friction-loss rows on all 7 joints, the brick
+    resting on the table through 4 box-box points as pyramidal cones, reduced layout + hand-over; then the arm is driven
+    into the brick (mesh-box contacts couple the two kinematic trees: dense solver path). Contact pairs exact, state
+    1e-6 against the oracle."""
+    _, _, _lib, batch = setup
+    M = H.scene("xarm7_tabletop")
+    dm = batch.DeviceModel(M, H.xarm_robot_ns(), None)
+    N = 8
+    b = batch.Batch(dm, N)
+    b.enable_contact_export(cap=24)
+    rng = np.random.default_rng(7)
+    q0 = np.tile(M["qpos0"], (N, 1)).astype(float)
+    q0[:, :7] = H.XARM_Q_HOME + rng.uniform(-0.2, 0.2, (N, 7))
+    q0[:, 7:9] += rng.uniform(-0.03, 0.03, (N, 2))
+    ctrl = q0[:, :7] + rng.uniform(-0.1, 0.1, (N, 7))
+    # environment 0 reaches down to the brick: joint targets found by the oracle's IK for a point just beside the brick
+    m = O.Model(M)
+    site = M["site_names"].index("attachment_site")
+    sol, _ = O.ik_inverse(m, site, 7, [q0[0, 7] - 0.05, q0[0, 8], 0.225, 1, 0, 0, 0], H.XARM_Q_HOME)
+    assert sol is not None
+    sol2, _ = O.ik_inverse(m, site, 7, [q0[0, 7] + 0.08, q0[0, 8], 0.225, 1, 0, 0, 0], sol)
+    assert sol2 is not None
+    q0[0, :7] = sol[:7]; ctrl[0] = sol2[:7]
+    b.qpos.copy_(torch.as_tensor(q0)); b.ctrl.copy_(torch.as_tensor(ctrl))
+    ds = []
+    for i in range(N):
+        d = O.Data(m); d.qpos[:] = q0[i]; d.ctrl[:] = ctrl[i]; ds.append(d)
+    coupled = 0
+    names = M["geom_names"]
+    for it in range(30):
+        b.run(_lib.STEP_K, k=10)
+        cn, cg, q, si = b.contact_n.cpu().numpy(), b.contact_geom.cpu().numpy(), b.qpos.cpu().numpy(), b.si.cpu().numpy()
+        for i, d in enumerate(ds):
+            d.step(10)
+            n = int(d.ncon[0])
+            ref = d.int("contact_geom").reshape(-1, 2)
+            assert cn[i] == n and si[i, 17] == 0, (it, i)
+            assert np.array_equal(cg[i, :n], ref), (it, i)
+            assert np.abs(q[i] - d.qpos).max() < 1e-6, (it, i)
+            coupled += any(("duplo" in names[g1]) != ("duplo" in names[g2]) and not {names[g1], names[g2]} & {"table", "floor"}
+                           for g1, g2 in ref)
+    assert coupled > 0, "the arm of environment 0 should have touched the brick"
+    assert np.abs(q[0, 7:9] - q0[0, 7:9]).max() > 5e-3  # and pushed it
