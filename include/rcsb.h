@@ -122,6 +122,12 @@ int rcsb_robot_set_cartesian_position(rcsb_batch* b, const void* pose_dev);
  * SimRobot::set_cartesian_position (SimRobot.cpp:145-155). kind 0: act_dev [n][6] xyzrpy (CARTESIAN_TRPY); kind 1:
  * act_dev [n][7] xyz + quat xyzw (CARTESIAN_TQuat). */
 int rcsb_env_cartesian_action(rcsb_batch* b, const void* act_dev, int kind, int relative, double max_trans, double max_rot);
+/* The same with relative == 2 for RelativeTo.CONFIGURED_ORIGIN (base.py:443-467, 490-578): origin_dev [n][7] is the pose
+ * RelativeActionSpace.reset() stored (xyz + quat xyzw), last_dev [n][7] / have_last_dev [n] the last clipped offset and
+ * whether there is one (both updated by the call); all three are device arrays owned by the caller. relative 0 / 1 ignore
+ * them. */
+int rcsb_env_cartesian_action_origin(rcsb_batch* b, const void* act_dev, int kind, int relative, double max_trans, double max_rot,
+                                     const void* origin_dev, void* last_dev, int* have_last_dev);
 
 /* evidence counters */
 long long rcsb_launch_count(void); /* kernels launched by this library since load */

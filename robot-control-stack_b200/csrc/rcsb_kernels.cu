@@ -84,7 +84,8 @@ namespace rcsb_generic {
 }
 using rcsb_generic::ik_env;
 using rcsb_generic::cart_action_env;
-// Pin::inverse for every environment, one environment per thread (rcsb_ik.cuh)
+using rcsb_generic::CartOrigin;
+// Pin::inverse for every environment, one environment per thread (rcsb_ik.cuh): large batches
 __global__ void __launch_bounds__(128)
 rcsb_k_ik(const RcsbModel* __restrict__ gm, const real* __restrict__ pose, const real* __restrict__ q0, real* __restrict__ q_out,
           int* __restrict__ success, int* __restrict__ iters, int N, int apply, real* __restrict__ sr, int* __restrict__ si) {
@@ -94,10 +95,26 @@ rcsb_k_ik(const RcsbModel* __restrict__ gm, const real* __restrict__ pose, const
 }
 __global__ void __launch_bounds__(128)
 rcsb_k_cart_action(const RcsbModel* __restrict__ gm, const real* __restrict__ act, int kind, int relative, real max_trans, real max_rot,
-                   int N, real* __restrict__ sr, int* __restrict__ si) {
+                   int N, real* __restrict__ sr, int* __restrict__ si, CartOrigin co) {
   const RcsbModel* sm = stage_model(gm);
   for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < N; env += gridDim.x * blockDim.x)
-    cart_action_env(sm, env, act, kind, relative, max_trans, max_rot, sr, si);
+    cart_action_env(sm, env, act, kind, relative, max_trans, max_rot, sr, si, co);
+}
+// the same two entry points with 8 lanes per environment (4 environments per warp): small and medium batches
+__global__ void __launch_bounds__(128)
+rcsb_k_ik8(const RcsbModel* __restrict__ gm, int nch, const real* __restrict__ pose, const real* __restrict__ q0,
+           real* __restrict__ q_out, int* __restrict__ success, int* __restrict__ iters, int N, int apply, real* __restrict__ sr,
+           int* __restrict__ si) {
+  const RcsbModel* sm = stage_model(gm);
+  const int g = threadIdx.x & 7, env = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, valid = env < N;
+  rcsb_generic::ik_env8(sm, nch, valid ? env : 0, valid, g, pose, q0, q_out, success, iters, apply, sr, si);
+}
+__global__ void __launch_bounds__(128)
+rcsb_k_cart_action8(const RcsbModel* __restrict__ gm, int nch, const real* __restrict__ act, int kind, int relative, real max_trans,
+                    real max_rot, int N, real* __restrict__ sr, int* __restrict__ si, CartOrigin co) {
+  const RcsbModel* sm = stage_model(gm);
+  const int g = threadIdx.x & 7, env = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, valid = env < N;
+  rcsb_generic::cart_action_env8(sm, nch, valid ? env : 0, valid, g, act, kind, relative, max_trans, max_rot, sr, si, co);
 }
 #undef MD
 #undef LAY
@@ -309,6 +326,8 @@ rcsb_batch* rcsb_batch_new(rcsb_model* m, int n_envs, void* sr, void* sd, void* 
   if (b->var.set_smem(smem_max) != cudaSuccess || (m->has_reduced && b->var_full.set_smem(smem_max) != cudaSuccess) ||
       cudaFuncSetAttribute(rcsb_k_ik, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCSB_SMEM_HEADER) != cudaSuccess ||
       cudaFuncSetAttribute(rcsb_k_cart_action, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCSB_SMEM_HEADER) != cudaSuccess ||
+      cudaFuncSetAttribute(rcsb_k_ik8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCSB_SMEM_HEADER) != cudaSuccess ||
+      cudaFuncSetAttribute(rcsb_k_cart_action8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCSB_SMEM_HEADER) != cudaSuccess ||
       cudaMalloc(&b->d_counter, 4 * sizeof(int)) != cudaSuccess || cudaMalloc(&b->d_overflow, (size_t)n_envs * sizeof(int)) != cudaSuccess) {
     fail(RCSB_ERR_CUDA, std::string("batch setup: ") + cudaGetErrorString(cudaGetLastError()));
     delete b;
@@ -498,33 +517,68 @@ int rcsb_env_get_obs(rcsb_batch* b, void* obs_dev, int* info_dev) {
   return rcsb_batch_run(b, RCSB_OP_OBS, 0, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, obs_dev, info_dev);
 }
 
-// One environment per thread and a long serial solve per thread (250 registers, ~5 k instructions per CLIK iteration).
-// Small batches run in blocks of one full warp spread over the SMs. Smaller blocks (more, mostly idle, warps per SM)
-// were measured slower (4096 envs: 1.19 ms with 4-thread blocks against 0.55 ms): several unaligned warps per SM thrash
-// the instruction cache on the unrolled loop body, the same effect that makes the physics kernel keep its CTA barrier.
+// Two mappings of the CLIK solver (rcsb_ik.cuh). One environment per thread: a long serial solve per thread (250
+// registers, ~5 k instructions per iteration) in blocks of one warp spread over the SMs -- the fewest instructions in
+// total, but latency-bound until there are tens of thousands of environments. 8 lanes per environment: ~2.4 x the
+// instructions in total, a quarter of the latency; the choice below (RCSB_IK_LANES=1 / 8 overrides it) follows the
+// measured crossover. The lanes mapping needs a canonical chain (FR3, xArm7).
 static int ik_block_threads(int n) {
   return n >= 128 * 148 * 4 ? 128 : (n >= 64 * 148 * 4 ? 64 : 32);
+}
+static int canonical_chain(const RcsbModel& m) {  // rcsb_ik.cuh: ik_canonical_chain
+  int n = 0;
+  for (int b = m.rb_site_body; b >= 0; b = m.b_parent[b]) n++;
+  if (n < 1 || n > 8) return 0;
+  for (int b = m.rb_site_body, i = n - 1; b >= 0; b = m.b_parent[b], i--)
+    if (m.b_jtype[b] == RCSB_JNT_FREE || m.b_dadr[b] != i || m.b_qadr[b] != i) return 0;
+  return n;
+}
+static int ik_lanes_chain(rcsb_batch* b) {  // chain length when this batch uses the 8-lane kernels, else 0
+  const int nch = canonical_chain(b->m->h);
+  int lanes = b->n <= 8192 ? 8 : 1;
+  if (const char* ov = getenv("RCSB_IK_LANES")) lanes = atoi(ov);
+  return (lanes == 8 && nch > 0) ? nch : 0;
 }
 static int launch_ik(rcsb_batch* b, const void* pose_dev, const void* q0_dev, void* q_out_dev, int* success_dev, int* iters_dev,
                      int apply) {
   if (!b || !pose_dev) return fail(RCSB_ERR_ARG, "null argument");
   DEVICE_OK(b->m->device);
-  int threads = ik_block_threads(b->n), grid = (b->n + threads - 1) / threads;
-  rcsb_k_ik<<<grid, threads, RCSB_SMEM_HEADER, b->stream>>>(b->m->d_model, (const real*)pose_dev, (const real*)q0_dev,
-                                                           (real*)q_out_dev, success_dev, iters_dev, b->n, apply, b->sr, b->si);
+  if (const int nch = ik_lanes_chain(b)) {
+    const int threads = 128, grid = (b->n * 8 + threads - 1) / threads;
+    rcsb_k_ik8<<<grid, threads, RCSB_SMEM_HEADER, b->stream>>>(b->m->d_model, nch, (const real*)pose_dev, (const real*)q0_dev,
+                                                              (real*)q_out_dev, success_dev, iters_dev, b->n, apply, b->sr, b->si);
+  } else {
+    int threads = ik_block_threads(b->n), grid = (b->n + threads - 1) / threads;
+    rcsb_k_ik<<<grid, threads, RCSB_SMEM_HEADER, b->stream>>>(b->m->d_model, (const real*)pose_dev, (const real*)q0_dev,
+                                                             (real*)q_out_dev, success_dev, iters_dev, b->n, apply, b->sr, b->si);
+  }
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return RCSB_OK;
+}
+int rcsb_env_cartesian_action_origin(rcsb_batch* b, const void* act_dev, int kind, int relative, double max_trans, double max_rot,
+                                     const void* origin_dev, void* last_dev, int* have_last_dev) {
+  if (!b || !act_dev || (kind != 0 && kind != 1) || relative < 0 || relative > 2) return fail(RCSB_ERR_ARG, "bad argument");
+  if (relative == 2 && (!origin_dev || !last_dev || !have_last_dev))
+    return fail(RCSB_ERR_ARG, "CONFIGURED_ORIGIN needs the origin / last-offset / have-last device arrays");
+  DEVICE_OK(b->m->device);
+  CartOrigin co = {(const real*)origin_dev, (real*)last_dev, have_last_dev};
+  if (const int nch = ik_lanes_chain(b)) {
+    const int threads = 128, grid = (b->n * 8 + threads - 1) / threads;
+    rcsb_k_cart_action8<<<grid, threads, RCSB_SMEM_HEADER, b->stream>>>(b->m->d_model, nch, (const real*)act_dev, kind, relative,
+                                                                       (real)max_trans, (real)max_rot, b->n, b->sr, b->si, co);
+  } else {
+    int threads = ik_block_threads(b->n), grid = (b->n + threads - 1) / threads;
+    rcsb_k_cart_action<<<grid, threads, RCSB_SMEM_HEADER, b->stream>>>(b->m->d_model, (const real*)act_dev, kind, relative,
+                                                                      (real)max_trans, (real)max_rot, b->n, b->sr, b->si, co);
+  }
   g_launches++;
   CUDA_OK(cudaGetLastError());
   return RCSB_OK;
 }
 int rcsb_env_cartesian_action(rcsb_batch* b, const void* act_dev, int kind, int relative, double max_trans, double max_rot) {
-  if (!b || !act_dev || (kind != 0 && kind != 1)) return fail(RCSB_ERR_ARG, "bad argument");
-  DEVICE_OK(b->m->device);
-  int threads = ik_block_threads(b->n), grid = (b->n + threads - 1) / threads;
-  rcsb_k_cart_action<<<grid, threads, RCSB_SMEM_HEADER, b->stream>>>(b->m->d_model, (const real*)act_dev, kind, relative, (real)max_trans,
-                                                                     (real)max_rot, b->n, b->sr, b->si);
-  g_launches++;
-  CUDA_OK(cudaGetLastError());
-  return RCSB_OK;
+  if (relative != 0 && relative != 1) return fail(RCSB_ERR_ARG, "bad argument");
+  return rcsb_env_cartesian_action_origin(b, act_dev, kind, relative, max_trans, max_rot, nullptr, nullptr, nullptr);
 }
 int rcsb_ik_inverse(rcsb_batch* b, const void* pose_dev, const void* q0_dev, void* q_out_dev, int* success_dev, int* iters_dev) {
   if (!q0_dev || !q_out_dev || !success_dev) return fail(RCSB_ERR_ARG, "null argument");

@@ -66,6 +66,7 @@ def lib():
     L.rcsb_env_get_obs.argtypes = [vp, vp, vp]
     L.rcsb_ik_inverse.argtypes = [vp, vp, vp, vp, vp, vp]
     L.rcsb_env_cartesian_action.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double]
+    L.rcsb_env_cartesian_action_origin.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, vp]
     L.rcsb_kernel_occupancy.argtypes = [vp, ip, ip, ip]
     L.rcsb_kernel_variant.argtypes = [vp, C.c_int]
     L.rcsb_kernel_variant.restype = cp
@@ -84,5 +85,5 @@ EXPORTS = ["rcsb_last_error", "rcsb_version", "rcsb_real_bytes", "rcsb_model_new
            "rcsb_batch_init_state", "rcsb_batch_set_contact_export", "rcsb_batch_run", "rcsb_batch_run_host", "rcsb_env_step_host", "rcsb_sim_step",
            "rcsb_sim_step_until_convergence", "rcsb_sim_reset", "rcsb_robot_set_joint_position",
            "rcsb_robot_set_joints_hard", "rcsb_robot_reset", "rcsb_gripper_set_normalized_width",
-           "rcsb_gripper_reset", "rcsb_env_get_obs", "rcsb_ik_inverse", "rcsb_robot_set_cartesian_position", "rcsb_env_cartesian_action",
+           "rcsb_gripper_reset", "rcsb_env_get_obs", "rcsb_ik_inverse", "rcsb_robot_set_cartesian_position", "rcsb_env_cartesian_action", "rcsb_env_cartesian_action_origin",
            "rcsb_launch_count", "rcsb_kernel_occupancy", "rcsb_kernel_variant", "rcsb_debug_stage_cycles"]

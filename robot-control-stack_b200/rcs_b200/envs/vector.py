@@ -42,8 +42,6 @@ class SimVectorEnv:
             assert isinstance(mm, tuple) and len(mm) == 2, \
                 "in cartesian control max_mov must be a tuple of maximum translation (in m) and maximum rotation in (rad)"
             self.max_mov = (float(mm[0]), float(mm[1]))
-        if self.relative and relative_to != RelativeTo.LAST_STEP and control_mode != ControlMode.JOINTS:
-            raise NotImplementedError("RelativeTo.CONFIGURED_ORIGIN for Cartesian control")
         self.binary_gripper = binary_gripper
         self._origin = None        # RelativeActionSpace._origin / _last_action for CONFIGURED_ORIGIN (base.py:443-467)
         self._last_action = None
@@ -119,9 +117,14 @@ class SimVectorEnv:
         robot.reset(); sim.step(1); get_obs()."""
         b = self.sim.batch
         obs, info, _ = self.unpack(self.reset_packed())
-        if self.relative and self.relative_to == RelativeTo.CONFIGURED_ORIGIN:  # base.py:462-467
-            self._origin = obs["joints"].clone()
-            self._last_action = None
+        if self.relative and self.relative_to == RelativeTo.CONFIGURED_ORIGIN:  # base.py:462-467: set_origin_to_current()
+            if self.control_mode == ControlMode.JOINTS:
+                self._origin = obs["joints"].clone()
+                self._last_action = None
+            else:  # origin pose, last clipped offset and its flag live on the device, next to the state rows
+                self._origin = obs["tquat"].clone().contiguous()
+                self._last_action = torch.zeros((self.num_envs, 7), dtype=torch.float64, device=self.dev)
+                self._have_last = torch.zeros((self.num_envs,), dtype=torch.int32, device=self.dev)
         return obs, {}
 
     def step(self, action: dict):
@@ -157,7 +160,16 @@ class SimVectorEnv:
             kind = 0 if self.control_mode == ControlMode.CARTESIAN_TRPY else 1
             assert a.shape == (self.num_envs, 6 if kind == 0 else 7)
             mt, mr = self.max_mov if self.relative else (0.0, 0.0)
-            _lib.check(_lib.lib().rcsb_env_cartesian_action(b.ptr, a.data_ptr(), kind, int(self.relative), float(mt), float(mr)))
+            if self.relative and self.relative_to == RelativeTo.CONFIGURED_ORIGIN:
+                if self._origin is None:  # step() before reset(): the origin is where the robot is now
+                    self._origin = self.robot.get_cartesian_position_tensor().contiguous()
+                    self._last_action = torch.zeros((self.num_envs, 7), dtype=torch.float64, device=self.dev)
+                    self._have_last = torch.zeros((self.num_envs,), dtype=torch.int32, device=self.dev)
+                _lib.check(_lib.lib().rcsb_env_cartesian_action_origin(
+                    b.ptr, a.data_ptr(), kind, 2, float(mt), float(mr), self._origin.data_ptr(), self._last_action.data_ptr(),
+                    self._have_last.data_ptr()))
+            else:
+                _lib.check(_lib.lib().rcsb_env_cartesian_action(b.ptr, a.data_ptr(), kind, int(self.relative), float(mt), float(mr)))
         if self.gripper is not None:
             assert "gripper" in action, "Gripper action not found."  # base.py:724
             ag = action["gripper"].to(device=self.dev, dtype=torch.float64).reshape(-1).contiguous()

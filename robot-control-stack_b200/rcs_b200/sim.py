@@ -298,13 +298,18 @@ class SimRobot(common.Robot):
             t = t.unsqueeze(0).expand(self._n, -1)
         return t[:, :width].contiguous()
 
-    def get_cartesian_position(self):
+    def get_cartesian_position_tensor(self) -> torch.Tensor:
+        """[num_envs, 7] xyz + quat (xyzw) of every environment (a fresh tensor)."""
         b = self.sim.batch
-        b.run(_lib.OBS, want_obs=True)
-        if self._n == 1:
-            o = b.obs[0, :7].cpu().numpy()
-            return common.Pose(translation=o[:3], quaternion=o[3:7])
+        b.run(_lib.OBS, want_obs=True, fresh_obs=True)
         return b.obs[:, :7].clone()
+
+    def get_cartesian_position(self):
+        o = self.get_cartesian_position_tensor()
+        if self._n == 1:
+            o = o[0].cpu().numpy()
+            return common.Pose(translation=o[:3], quaternion=o[3:7])
+        return o
 
     def set_joint_position(self, q):
         b = self.sim.batch

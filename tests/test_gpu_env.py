@@ -304,3 +304,58 @@ def test_pin_inverse_default_tcp_offset_is_identity_with_a_configured_tcp():
     tcp_goal = goal * cfg.tcp_offset
     q2 = robot.get_ik().inverse(torch.as_tensor(np.tile(tcp_goal.as7(), (4, 1))), H.Q_HOME, cfg.tcp_offset)[0][0].cpu().numpy()
     assert np.abs(q2 - qr).max() < 1e-7
+
+
+@pytest.mark.parametrize("mode_name", ["CARTESIAN_TRPY", "CARTESIAN_TQuat"])
+def test_cartesian_configured_origin_matches_reference_math(mode_name):
+    """RelativeTo.CONFIGURED_ORIGIN for Cartesian control (base.py:443-467, 490-578) on the device: the origin is the pose
+    at reset(); the offset may move by at most (max translation, max rotation) per step relative to the LAST clipped
+    offset (pose_diff = action * last^-1, clipped, re-applied). Expected targets are rebuilt step by step with the host
+    Pose class and solved with the batched IK entry point."""
+    from rcs_b200 import common
+    from rcs_b200.envs.base import ControlMode, RelativeTo
+    from rcs_b200 import sim
+    from rcs_b200.envs.creators import SimEnvCreator
+    from rcs_b200.envs.utils import default_sim_robot_cfg
+    N = 24
+    mode = getattr(ControlMode, mode_name)
+    max_t, max_r = 0.05, np.deg2rad(10)
+    env = SimEnvCreator()(mode, default_sim_robot_cfg("fr3_empty_world"), gripper_cfg=None, sim_cfg=sim.SimConfig(async_control=True),
+                          max_relative_movement=(max_t, max_r), relative_to=RelativeTo.CONFIGURED_ORIGIN, num_envs=N)
+    obs, _ = env.reset()
+    b = env.sim.batch
+    tq0 = obs["tquat"].cpu().numpy().copy()
+    origins = [common.Pose(translation=tq0[e, :3], quaternion=tq0[e, 3:]) for e in range(N)]
+    last = [None] * N
+    rng = np.random.default_rng(9)
+    key = "xyzrpy" if mode == ControlMode.CARTESIAN_TRPY else "tquat"
+    for step in range(4):
+        xyz = rng.uniform(-0.08, 0.08, (N, 3))   # mostly beyond the 5 cm per-step cap
+        rpy = rng.uniform(-0.3, 0.3, (N, 3))     # mostly beyond the 10 degree cap
+        if mode == ControlMode.CARTESIAN_TRPY:
+            a = np.concatenate([xyz, rpy], axis=1)
+        else:
+            a = np.concatenate([xyz, np.stack([common.Pose(rpy_vector=r).rotation_q() for r in rpy])], axis=1)
+        poses = np.zeros((N, 7))
+        for e in range(N):
+            act = common.Pose(translation=a[e, :3], rpy_vector=a[e, 3:]) if mode == ControlMode.CARTESIAN_TRPY else \
+                common.Pose(translation=a[e, :3], quaternion=a[e, 3:])
+            if last[e] is None:
+                off = act.limit_translation_length(max_t).limit_rotation_angle(max_r)
+            else:
+                diff = act * last[e].inverse()
+                off = diff.limit_translation_length(max_t).limit_rotation_angle(max_r) * last[e]
+            last[e] = off
+            t = np.clip(origins[e].translation() + off.translation(), [-0.855, -0.855, 0], [0.855, 0.855, 1.188])
+            if mode == ControlMode.CARTESIAN_TRPY:
+                tgt = common.Pose(translation=t, rpy_vector=(off * origins[e]).rotation_rpy().as_vector())
+            else:
+                tgt = common.Pose(translation=t, quaternion=(off * origins[e]).rotation_q())
+            poses[e, :3] = tgt.translation(); poses[e, 3:] = tgt.rotation_q()
+        q_now = b.qpos[:, :7].clone().contiguous()
+        q_exp, ok, _ = b.ik_inverse(torch.as_tensor(poses, device=b.dev), q_now)
+        _, _, _, _, info = env.step({key: torch.as_tensor(a, device=b.dev)})
+        okn = ok.cpu().numpy().astype(bool)
+        assert okn.sum() > N // 2 and np.array_equal(info["ik_success"].cpu().numpy(), okn), step
+        ctrl = b.ctrl[:, :7].cpu().numpy()
+        assert np.abs(ctrl[okn] - q_exp.cpu().numpy()[okn, :7]).max() < 1e-8, step
