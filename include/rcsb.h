@@ -36,7 +36,8 @@ enum {
   RCSB_RUN_STEP_K = 1 << 10,         /* Sim::step(k)                   sim.cpp:108-115 */
   RCSB_RUN_STEP_CONV = 1 << 11,      /* Sim::step_until_convergence    sim.cpp:84-106 */
   RCSB_RUN_OBS = 1 << 12,            /* RobotEnv.get_obs + info        base.py:246-253, envs/sim.py:60-66,125-131 */
-  RCSB_RUN_ACT_GRIPPER_CONT = 1 << 13 /* GripperWrapper.action (continuous width) base.py:721-735 */
+  RCSB_RUN_ACT_GRIPPER_CONT = 1 << 13, /* GripperWrapper.action (continuous width) base.py:721-735 */
+  RCSB_RUN_FRAMES = 1 << 14           /* internal: body frames for rcsb_camera_depth (mjv_updateScene, camera.cpp:100-118) */
 };
 
 const char* rcsb_last_error(void);
@@ -52,6 +53,9 @@ int rcsb_model_set_mesh_vertices(rcsb_model* m, const double* xyz, int nvert);
 /* edge graph of the convex hulls (mjModel mesh_graph, used by mjc_PlaneConvex for multi-point plane-mesh contacts):
  * neighbours of pooled vertex v are nbr[adr[v] .. adr[v+1]) as vertex ids local to the geom's hull; optional */
 int rcsb_model_set_mesh_graph(rcsb_model* m, const int* adr, int nadr, const int* nbr, int nnbr);
+/* supporting planes of the convex hulls (n . x + d <= 0 inside, geom frame), pooled, with each collidable geom's range:
+ * input of the depth ray-caster (rcsb_camera_depth); optional */
+int rcsb_model_set_mesh_faces(rcsb_model* m, const double* planes, int nface, const int* geom_faceadr, const int* geom_facenum, int ng);
 int rcsb_model_finalize(rcsb_model* m);         /* validates sizes, computes the workspace layout (host only) */
 int rcsb_model_upload(rcsb_model* m, int device); /* copies constants and hull vertices to the CUDA device */
 /* sizes of one environment's rows: reals, doubles, ints, obs reals, info ints */
@@ -128,6 +132,18 @@ int rcsb_env_cartesian_action(rcsb_batch* b, const void* act_dev, int kind, int 
  * them. */
 int rcsb_env_cartesian_action_origin(rcsb_batch* b, const void* act_dev, int kind, int relative, double max_trans, double max_rot,
                                      const void* origin_dev, void* last_dev, int* have_last_dev);
+
+/* SimCameraSet depth frame of every environment (src/sim/camera.cpp:100-140 + python/rcs/camera/sim.py:45-95): the
+ * camera (MuJoCo convention: looks along -z, +y up) sits at cam_pos / cam_rot (row-major) in the frame of moving body
+ * cam_body (-1: world), vertical field of view fovy_deg, width x height pixels; out_dev [n_envs][height][width] uint16,
+ * row 0 = top, = (uint16)(1000 * eye-space depth in metres clipped to [znear, zfar]) with physical_units, else
+ * (uint16)(1000 * OpenGL window-space depth in [0, 1]). Rays are cast against the collidable geoms (convex hulls for
+ * meshes), not rasterised visual meshes. */
+/* world frames of the moving bodies at the current qpos (mjData.xpos / xmat of the bodies that carry a joint):
+ * frames_dev [n_envs][nb][12] reals, position then the row-major rotation; used for camera extrinsics */
+int rcsb_body_frames(rcsb_batch* b, void* frames_dev);
+int rcsb_camera_depth(rcsb_batch* b, int cam_body, const double* cam_pos, const double* cam_rot, double fovy_deg, int width, int height,
+                      double znear, double zfar, int physical_units, void* out_dev);
 
 /* evidence counters */
 long long rcsb_launch_count(void); /* kernels launched by this library since load */

@@ -307,6 +307,21 @@ RCSB_DEV void run_env_program(const Ctx& c, const RcsbLaunch& L, int env) {
       }
     }
   }
+  if ((ops & RCSB_OP_FRAMES) && L.frames) {
+    // kinematics of the CURRENT qpos (as mj_forward would give it to a renderer). The free-joint quaternions are
+    // re-normalised inside st_kinematics: qpos is put back afterwards so that observing never changes the state.
+    real* keep = WR(M);  // rebuilt by every step, and outside the regions the kinematics stage writes
+    PFOR(i, MD(nq)) { keep[i] = WR(q)[i]; }
+    RCSB_SYNC();
+    st_kinematics(c);
+    PFOR(i, MD(nq)) { WR(q)[i] = keep[i]; }
+    real* out = L.frames + (size_t)env * MD(nb) * 12;
+    PFOR(e, MD(nb) * 12) {
+      const int b = e / 12, k = e - 12 * b;
+      out[e] = k < 3 ? WR(bpos)[3 * b + k] : WR(bmat)[9 * b + k - 3];
+    }
+    RCSB_SYNC();
+  }
   if ((ops & RCSB_OP_OBS) && c.lane == 0) {
     real pose[7];
     robot_cartesian_position(c, pose);

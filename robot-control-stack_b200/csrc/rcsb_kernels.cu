@@ -116,6 +116,151 @@ rcsb_k_cart_action8(const RcsbModel* __restrict__ gm, int nch, const real* __res
   const int g = threadIdx.x & 7, env = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, valid = env < N;
   rcsb_generic::cart_action_env8(sm, nch, valid ? env : 0, valid, g, act, kind, relative, max_trans, max_rot, sr, si, co);
 }
+
+// ------------------------------------------------------------------ depth camera: ray-caster over the collision geoms
+// SimCameraSet depth frames (src/sim/camera.cpp:100-140 renders with OpenGL and reads the z-buffer back;
+// python/rcs/camera/sim.py:45-115 turns it into metres and uint16 millimetres). Here every pixel casts one ray against
+// the collidable geoms of its environment: plane, sphere, capsule, cylinder, box analytically, convex meshes by clipping
+// the ray against the supporting planes of the hull. One CTA renders a 16 x 16 tile of one environment's image: the
+// geoms' world frames are put together once per CTA in shared memory from the body frames the step kernel exported.
+struct RcsbCamera {
+  int body;              // moving body the camera rides on (-1: fixed in the world)
+  real pos[3], rot[9];   // camera frame in that body's frame (MuJoCo convention: looks along -z, +y up)
+  real f;                // focal length in pixels: 0.5 * H / tan(fovy / 2)
+  int W, H;
+  real znear, zfar;      // clip planes in metres (mjVisual.map.znear / zfar x mjStatistic.extent)
+  int physical_units;    // 1: millimetres of eye-space depth; 0: 1000 x the OpenGL window-space depth in [0, 1]
+};
+enum { RCSB_CAM_TILE = 16 };
+__device__ __forceinline__ bool ray_geom(const RcsbModel& m, int g, const real* __restrict__ faces, const int* __restrict__ face_adr,
+                                         const int* __restrict__ face_num, const real* o, const real* d, real tmax, real* t_out) {
+  // o, d: ray in the geom frame (d not normalised: t is in units of it)
+  const int type = m.g_type[g];
+  const real* sz = m.g_size[g];
+  real t = -1;
+  if (type == RCSB_GEOM_PLANE) {
+    if (d[2] < 0) t = -o[2] / d[2];
+  } else if (type == RCSB_GEOM_SPHERE) {
+    const real a = d[0] * d[0] + d[1] * d[1] + d[2] * d[2], b = o[0] * d[0] + o[1] * d[1] + o[2] * d[2];
+    const real cc = o[0] * o[0] + o[1] * o[1] + o[2] * o[2] - sz[0] * sz[0], disc = b * b - a * cc;
+    if (disc >= 0) t = (-b - sqrt(disc)) / a;
+  } else if (type == RCSB_GEOM_BOX) {
+    real t0 = 0, t1 = tmax;
+    for (int k = 0; k < 3; k++) {
+      if (d[k] != 0) {
+        real ta = (-sz[k] - o[k]) / d[k], tb = (sz[k] - o[k]) / d[k];
+        if (ta > tb) { real s = ta; ta = tb; tb = s; }
+        t0 = ta > t0 ? ta : t0; t1 = tb < t1 ? tb : t1;
+      } else if (o[k] < -sz[k] || o[k] > sz[k]) t1 = -1;
+    }
+    if (t0 <= t1) t = t0;
+  } else if (type == RCSB_GEOM_CAPSULE || type == RCSB_GEOM_CYLINDER) {
+    const real r = sz[0], hl = sz[1];
+    // side: infinite cylinder about z, accepted while |z| <= hl
+    const real a = d[0] * d[0] + d[1] * d[1], b = o[0] * d[0] + o[1] * d[1], cc = o[0] * o[0] + o[1] * o[1] - r * r;
+    real best = (real)1e300;
+    if (a > 0) {
+      const real disc = b * b - a * cc;
+      if (disc >= 0) {
+        const real ts = (-b - sqrt(disc)) / a, z = o[2] + ts * d[2];
+        if (ts >= 0 && z >= -hl && z <= hl) best = ts;
+      }
+    }
+    for (int s = -1; s <= 1; s += 2) {
+      if (type == RCSB_GEOM_CAPSULE) {  // end spheres
+        const real oz = o[2] - s * hl;
+        const real A = a + d[2] * d[2], B = b + oz * d[2], C = o[0] * o[0] + o[1] * o[1] + oz * oz - r * r, disc = B * B - A * C;
+        if (disc >= 0) {
+          const real ts = (-B - sqrt(disc)) / A;
+          if (ts >= 0 && s * (o[2] + ts * d[2]) >= hl && ts < best) best = ts;
+        }
+      } else if (d[2] != 0) {           // end caps
+        const real ts = (s * hl - o[2]) / d[2], x = o[0] + ts * d[0], y = o[1] + ts * d[1];
+        if (ts >= 0 && s * d[2] < 0 && x * x + y * y <= r * r && ts < best) best = ts;
+      }
+    }
+    if (best < (real)1e299) t = best;
+  } else if (type == RCSB_GEOM_MESH) {
+    real t0 = 0, t1 = tmax;
+    const real* pl = faces + 4 * (size_t)face_adr[g];
+    const int n = face_num[g];
+    for (int i = 0; i < n && t0 <= t1; i++) {
+      const real nx = __ldg(pl + 4 * i), ny = __ldg(pl + 4 * i + 1), nz = __ldg(pl + 4 * i + 2), dd = __ldg(pl + 4 * i + 3);
+      const real den = nx * d[0] + ny * d[1] + nz * d[2], num = -(nx * o[0] + ny * o[1] + nz * o[2] + dd);
+      if (den < 0) { const real tt = num / den; t0 = tt > t0 ? tt : t0; }
+      else if (den > 0) { const real tt = num / den; t1 = tt < t1 ? tt : t1; }
+      else if (num < 0) t1 = -1;
+    }
+    if (n > 0 && t0 <= t1) t = t0;
+  }
+  if (t < 0 || t > tmax) return false;
+  *t_out = t;
+  return true;
+}
+__global__ void __launch_bounds__(RCSB_CAM_TILE * RCSB_CAM_TILE)
+rcsb_k_depth(const RcsbModel* __restrict__ gm, const real* __restrict__ faces, const int* __restrict__ face_adr,
+             const int* __restrict__ face_num, const real* __restrict__ frames, RcsbCamera cam, unsigned short* __restrict__ out, int N) {
+  const RcsbModel& m = *gm;
+  __shared__ real gfr[RCSB_MAXG][12];   // world frame of every geom: position, row-major rotation
+  __shared__ real gbs[RCSB_MAXG][4];    // bounding sphere: centre, radius
+  __shared__ real cfr[12];              // camera frame in the world
+  const int tiles_x = (cam.W + RCSB_CAM_TILE - 1) / RCSB_CAM_TILE, tiles_y = (cam.H + RCSB_CAM_TILE - 1) / RCSB_CAM_TILE;
+  const int env = blockIdx.x / (tiles_x * tiles_y), tile = blockIdx.x - env * tiles_x * tiles_y;
+  const int tid = threadIdx.y * RCSB_CAM_TILE + threadIdx.x;
+  const real* fr = frames + (size_t)env * m.nb * 12;
+  if (tid < m.ng) {
+    const int g = tid, b = m.g_body[g];
+    real p[3] = {0, 0, 0}, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (b >= 0) { for (int i = 0; i < 3; i++) p[i] = fr[12 * b + i]; for (int i = 0; i < 9; i++) R[i] = fr[12 * b + 3 + i]; }
+    const real* Rl = m.g_rot[g];
+    for (int r = 0; r < 3; r++) {
+      gfr[g][r] = p[r] + R[3 * r] * m.g_pos[g][0] + R[3 * r + 1] * m.g_pos[g][1] + R[3 * r + 2] * m.g_pos[g][2];
+      gbs[g][r] = p[r] + R[3 * r] * m.g_bpos[g][0] + R[3 * r + 1] * m.g_bpos[g][1] + R[3 * r + 2] * m.g_bpos[g][2];
+      for (int k = 0; k < 3; k++) gfr[g][3 + 3 * r + k] = R[3 * r] * Rl[k] + R[3 * r + 1] * Rl[3 + k] + R[3 * r + 2] * Rl[6 + k];
+    }
+    gbs[g][3] = m.g_rbound[g];
+  }
+  if (tid == 64) {
+    real p[3] = {0, 0, 0}, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (cam.body >= 0) { for (int i = 0; i < 3; i++) p[i] = fr[12 * cam.body + i]; for (int i = 0; i < 9; i++) R[i] = fr[12 * cam.body + 3 + i]; }
+    for (int r = 0; r < 3; r++) {
+      cfr[r] = p[r] + R[3 * r] * cam.pos[0] + R[3 * r + 1] * cam.pos[1] + R[3 * r + 2] * cam.pos[2];
+      for (int k = 0; k < 3; k++) cfr[3 + 3 * r + k] = R[3 * r] * cam.rot[k] + R[3 * r + 1] * cam.rot[3 + k] + R[3 * r + 2] * cam.rot[6 + k];
+    }
+  }
+  __syncthreads();
+  const int u = (tile % tiles_x) * RCSB_CAM_TILE + threadIdx.x, v = (tile / tiles_x) * RCSB_CAM_TILE + threadIdx.y;
+  if (u >= cam.W || v >= cam.H) return;
+  // pixel centre -> ray in the camera frame (x right, y up, looking along -z), scaled so that t is the eye-space depth
+  const real dc[3] = {(u + (real)0.5 - (real)0.5 * cam.W) / cam.f, -(v + (real)0.5 - (real)0.5 * cam.H) / cam.f, (real)-1};
+  real dw[3], ow[3] = {cfr[0], cfr[1], cfr[2]};
+  for (int r = 0; r < 3; r++) dw[r] = cfr[3 + 3 * r] * dc[0] + cfr[3 + 3 * r + 1] * dc[1] + cfr[3 + 3 * r + 2] * dc[2];
+  const real dlen2 = dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2];
+  real tbest = cam.zfar;
+  for (int g = 0; g < m.ng; g++) {
+    if (m.g_type[g] != RCSB_GEOM_PLANE) {  // bounding sphere: closest approach of the ray to the centre
+      const real cx = gbs[g][0] - ow[0], cy = gbs[g][1] - ow[1], cz = gbs[g][2] - ow[2];
+      const real tc = (cx * dw[0] + cy * dw[1] + cz * dw[2]) / dlen2;
+      const real ex = cx - tc * dw[0], ey = cy - tc * dw[1], ez = cz - tc * dw[2], rr = gbs[g][3];
+      if (ex * ex + ey * ey + ez * ez > rr * rr) continue;
+      if ((tc - tbest) * (tc - tbest) * dlen2 > rr * rr && tc > tbest) continue;  // entirely behind the best hit
+    }
+    real og[3], dg[3], rel[3] = {ow[0] - gfr[g][0], ow[1] - gfr[g][1], ow[2] - gfr[g][2]};
+    const real* R = &gfr[g][3];
+    for (int k = 0; k < 3; k++) {
+      og[k] = R[k] * rel[0] + R[3 + k] * rel[1] + R[6 + k] * rel[2];
+      dg[k] = R[k] * dw[0] + R[3 + k] * dw[1] + R[6 + k] * dw[2];
+    }
+    real t;
+    if (ray_geom(m, g, faces, face_adr, face_num, og, dg, tbest, &t) && t < tbest) tbest = t;
+  }
+  real z = tbest < cam.znear ? cam.znear : tbest;  // eye-space depth, clipped like the view frustum
+  real val;
+  if (cam.physical_units) val = z * (real)1000;                               // camera/sim.py:65-72 then x DEPTH_SCALE
+  else val = (1 - cam.znear / z) / (1 - cam.znear / cam.zfar) * (real)1000;   // window-space depth x DEPTH_SCALE
+  val = val < 0 ? (real)0 : (val > (real)65535 ? (real)65535 : val);
+  out[((size_t)env * cam.H + v) * cam.W + u] = (unsigned short)val;           // astype(np.uint16): truncation
+}
 #undef MD
 #undef LAY
 
@@ -151,6 +296,10 @@ struct rcsb_model {
   std::vector<real> verts;
   std::vector<int> vgraph;  // hull edge graph: [nmeshvert + 1] offsets, then the neighbour lists
   int* d_vgraph = nullptr;
+  std::vector<real> faces;  // hull face planes (n, d) of the collidable mesh geoms, pooled (depth camera)
+  std::vector<int> face_adr, face_num;
+  real* d_faces = nullptr;
+  int *d_face_adr = nullptr, *d_face_num = nullptr;
   bool finalized = false;
   int device = -1;
   RcsbModel* d_model = nullptr;
@@ -173,6 +322,7 @@ struct rcsb_batch {
   real *d_act_joints = nullptr, *d_act_gripper = nullptr, *d_obs = nullptr, *d_act_packed = nullptr;
   int* d_info = nullptr;
   real *h_act = nullptr, *h_obs = nullptr;
+  real* d_frames = nullptr;  // [n][nb][12] body frames for the depth camera (RCSB_OP_FRAMES)
   int act_jstride = 0, act_gstride = 0;  // non-default action row strides of the next launch (packed host path)
   // optional contact export (rcsb_batch_set_contact_export)
   int *con_n = nullptr, *con_geom = nullptr, con_cap = 0;
@@ -196,6 +346,9 @@ void rcsb_model_free(rcsb_model* m) {
   if (m->d_model_r) cudaFree(m->d_model_r);
   if (m->d_verts) cudaFree(m->d_verts);
   if (m->d_vgraph) cudaFree(m->d_vgraph);
+  if (m->d_faces) cudaFree(m->d_faces);
+  if (m->d_face_adr) cudaFree(m->d_face_adr);
+  if (m->d_face_num) cudaFree(m->d_face_num);
   delete m;
 }
 int rcsb_model_set_int(rcsb_model* m, const char* field, const int* v, int n) {
@@ -220,6 +373,18 @@ int rcsb_model_set_mesh_graph(rcsb_model* m, const int* adr, int nadr, const int
   if (adr[0] != 0 || adr[nadr - 1] != nnbr) return fail(RCSB_ERR_SIZE, "mesh graph offsets do not match the neighbour list");
   m->vgraph.assign(adr, adr + nadr);
   m->vgraph.insert(m->vgraph.end(), nbr, nbr + nnbr);
+  return RCSB_OK;
+}
+int rcsb_model_set_mesh_faces(rcsb_model* m, const double* planes, int nface, const int* geom_faceadr, const int* geom_facenum, int ng) {
+  if (!m || nface < 0 || ng < 0 || ng > RCSB_MAXG || (nface > 0 && !planes) || (ng > 0 && (!geom_faceadr || !geom_facenum)))
+    return fail(RCSB_ERR_ARG, "bad mesh faces");
+  for (int g = 0; g < ng; g++)
+    if (geom_facenum[g] < 0 || (geom_facenum[g] > 0 && (geom_faceadr[g] < 0 || geom_faceadr[g] + geom_facenum[g] > nface)))
+      return fail(RCSB_ERR_SIZE, "geom face range outside the plane pool");
+  m->faces.resize((size_t)4 * (nface > 0 ? nface : 1));
+  for (int i = 0; i < 4 * nface; i++) m->faces[i] = (real)planes[i];
+  m->face_adr.assign(RCSB_MAXG, 0); m->face_num.assign(RCSB_MAXG, 0);
+  for (int g = 0; g < ng; g++) { m->face_adr[g] = geom_facenum[g] > 0 ? geom_faceadr[g] : 0; m->face_num[g] = geom_facenum[g]; }
   return RCSB_OK;
 }
 int rcsb_model_finalize(rcsb_model* m) {
@@ -259,6 +424,13 @@ int rcsb_model_upload(rcsb_model* m, int device) {
   if (m->verts.empty()) m->verts.resize(3);
   CUDA_OK(cudaMalloc(&m->d_verts, m->verts.size() * sizeof(real)));
   CUDA_OK(cudaMemcpy(m->d_verts, m->verts.data(), m->verts.size() * sizeof(real), cudaMemcpyHostToDevice));
+  if (m->face_adr.empty()) { m->faces.assign(4, 0); m->face_adr.assign(RCSB_MAXG, 0); m->face_num.assign(RCSB_MAXG, 0); }
+  CUDA_OK(cudaMalloc(&m->d_faces, m->faces.size() * sizeof(real)));
+  CUDA_OK(cudaMemcpy(m->d_faces, m->faces.data(), m->faces.size() * sizeof(real), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&m->d_face_adr, RCSB_MAXG * sizeof(int)));
+  CUDA_OK(cudaMemcpy(m->d_face_adr, m->face_adr.data(), RCSB_MAXG * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&m->d_face_num, RCSB_MAXG * sizeof(int)));
+  CUDA_OK(cudaMemcpy(m->d_face_num, m->face_num.data(), RCSB_MAXG * sizeof(int), cudaMemcpyHostToDevice));
   if (!m->vgraph.empty()) {
     CUDA_OK(cudaMalloc(&m->d_vgraph, m->vgraph.size() * sizeof(int)));
     CUDA_OK(cudaMemcpy(m->d_vgraph, m->vgraph.data(), m->vgraph.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -337,7 +509,7 @@ rcsb_batch* rcsb_batch_new(rcsb_model* m, int n_envs, void* sr, void* sd, void* 
 }
 void rcsb_batch_free(rcsb_batch* b) {
   if (!b) return;
-  cudaFree(b->d_counter); cudaFree(b->d_overflow); cudaFree(b->d_act_joints); cudaFree(b->d_act_gripper); cudaFree(b->d_act_packed); cudaFree(b->d_obs); cudaFree(b->d_info);
+  cudaFree(b->d_counter); cudaFree(b->d_overflow); cudaFree(b->d_act_joints); cudaFree(b->d_act_gripper); cudaFree(b->d_act_packed); cudaFree(b->d_frames); cudaFree(b->d_obs); cudaFree(b->d_info);
   if (b->h_act) cudaFreeHost(b->h_act);
   if (b->h_obs) cudaFreeHost(b->h_obs);
   delete b;
@@ -390,6 +562,7 @@ int rcsb_batch_run(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps
   }
   L.obs = (real*)obs_dev; L.info = info_dev;
   L.con_n = b->con_n; L.con_geom = b->con_geom; L.con_real = b->con_real; L.con_cap = b->con_cap;
+  L.frames = b->d_frames;
   DEVICE_OK(b->m->device);
   CUDA_OK(cudaMemsetAsync(b->d_counter, 0, 4 * sizeof(int), b->stream));
   L.phase = 0; L.overflow_list = b->d_overflow; L.overflow_count = b->d_counter + 2;
@@ -486,6 +659,40 @@ int rcsb_env_step_host(rcsb_batch* b, unsigned ops, int k, int max_convergence_s
   // one copy out: the packed observation block carries the info flags as reals
   CUDA_OK(cudaMemcpyAsync(obs_host, b->d_obs, (size_t)b->n * RCSB_OBS_DIM * sizeof(real), cudaMemcpyDeviceToHost, b->stream));
   CUDA_OK(cudaStreamSynchronize(b->stream));
+  return RCSB_OK;
+}
+
+int rcsb_body_frames(rcsb_batch* b, void* frames_dev) {
+  if (!b || !frames_dev) return fail(RCSB_ERR_ARG, "null argument");
+  DEVICE_OK(b->m->device);
+  real* keep = b->d_frames;
+  b->d_frames = (real*)frames_dev;
+  int rc = rcsb_batch_run(b, RCSB_OP_FRAMES, 0, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+  b->d_frames = keep;
+  return rc;
+}
+int rcsb_camera_depth(rcsb_batch* b, int cam_body, const double* cam_pos, const double* cam_rot, double fovy_deg, int width, int height,
+                      double znear, double zfar, int physical_units, void* out_dev) {
+  if (!b || !cam_pos || !cam_rot || !out_dev || width < 1 || height < 1 || !(fovy_deg > 0 && fovy_deg < 180) || !(znear > 0 && zfar > znear))
+    return fail(RCSB_ERR_ARG, "bad camera argument");
+  if (cam_body >= b->m->h.nb) return fail(RCSB_ERR_ARG, "camera body out of range");
+  DEVICE_OK(b->m->device);
+  if (!b->d_frames) CUDA_OK(cudaMalloc(&b->d_frames, (size_t)b->n * b->m->h.nb * 12 * sizeof(real)));
+  int rc = rcsb_batch_run(b, RCSB_OP_FRAMES, 0, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  RcsbCamera cam;
+  cam.body = cam_body < 0 ? -1 : cam_body;
+  for (int i = 0; i < 3; i++) cam.pos[i] = (real)cam_pos[i];
+  for (int i = 0; i < 9; i++) cam.rot[i] = (real)cam_rot[i];
+  cam.f = (real)(0.5 * height / tan(fovy_deg * 3.14159265358979323846 / 360.0));
+  cam.W = width; cam.H = height; cam.znear = (real)znear; cam.zfar = (real)zfar; cam.physical_units = physical_units != 0;
+  const long long tiles = (long long)((width + RCSB_CAM_TILE - 1) / RCSB_CAM_TILE) * ((height + RCSB_CAM_TILE - 1) / RCSB_CAM_TILE);
+  if (tiles * b->n > 0x7fffffffLL) return fail(RCSB_ERR_ARG, "image too large for one launch");
+  dim3 block(RCSB_CAM_TILE, RCSB_CAM_TILE), grid((unsigned)(tiles * b->n));
+  rcsb_k_depth<<<grid, block, 0, b->stream>>>(b->m->d_model, b->m->d_faces, b->m->d_face_adr, b->m->d_face_num, b->d_frames, cam,
+                                             (unsigned short*)out_dev, b->n);
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
   return RCSB_OK;
 }
 

@@ -196,6 +196,7 @@ enum {
   RCSB_OP_STEP_CONV = 1 << 11,      // Sim::step_until_convergence
   RCSB_OP_OBS = 1 << 12,            // RobotEnv.get_obs + wrappers' observation/info
   RCSB_OP_ACT_GRIPPER_CONT = 1 << 13,  // GripperWrapper.action, continuous width
+  RCSB_OP_FRAMES = 1 << 14,         // export the world frames [p | R] of every moving body (camera ray-caster input)
 };
 enum { RCSB_OBS_DIM = 30, RCSB_INFO_DIM = 8 };
 // obs row: tquat[7] joints[7] xyzrpy[6] gripper[1] gripper_width[1] | the info row again, as reals (one packed block per
@@ -226,6 +227,7 @@ struct RcsbLaunch {
   int* con_geom;   // [N][con_cap][2]
   real* con_real;  // [N][con_cap][RCSB_CON_EXPORT_REALS] or null
   int con_cap;
+  real* frames;  // [N][nb][12] world frame of every moving body (position, then the row-major rotation), RCSB_OP_FRAMES
 };
 enum { RCSB_CON_EXPORT_REALS = 7 };
 

@@ -43,6 +43,9 @@ def lib():
     L.rcsb_model_set_real.argtypes = [vp, cp, dp, C.c_int]
     L.rcsb_model_set_mesh_vertices.argtypes = [vp, dp, C.c_int]
     L.rcsb_model_set_mesh_graph.argtypes = [vp, ip, C.c_int, ip, C.c_int]
+    L.rcsb_model_set_mesh_faces.argtypes = [vp, dp, C.c_int, ip, ip, C.c_int]
+    L.rcsb_camera_depth.argtypes = [vp, C.c_int, dp, dp, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, vp]
+    L.rcsb_body_frames.argtypes = [vp, vp]
     L.rcsb_model_finalize.argtypes = [vp]
     L.rcsb_model_upload.argtypes = [vp, C.c_int]
     L.rcsb_model_dims.argtypes = [vp, ip, ip, ip, ip, ip]
@@ -80,7 +83,7 @@ def check(rc: int):
 
 
 EXPORTS = ["rcsb_last_error", "rcsb_version", "rcsb_real_bytes", "rcsb_model_new", "rcsb_model_free",
-           "rcsb_model_set_int", "rcsb_model_set_real", "rcsb_model_set_mesh_vertices", "rcsb_model_set_mesh_graph", "rcsb_model_finalize",
+           "rcsb_model_set_int", "rcsb_model_set_real", "rcsb_model_set_mesh_vertices", "rcsb_model_set_mesh_graph", "rcsb_model_set_mesh_faces", "rcsb_model_finalize", "rcsb_camera_depth", "rcsb_body_frames",
            "rcsb_model_upload", "rcsb_model_dims", "rcsb_model_offsets", "rcsb_model_workspace_bytes", "rcsb_batch_new", "rcsb_batch_free",
            "rcsb_batch_init_state", "rcsb_batch_set_contact_export", "rcsb_batch_run", "rcsb_batch_run_host", "rcsb_env_step_host", "rcsb_sim_step",
            "rcsb_sim_step_until_convergence", "rcsb_sim_reset", "rcsb_robot_set_joint_position",

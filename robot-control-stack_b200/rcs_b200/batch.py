@@ -36,6 +36,8 @@ class DeviceModel:
         _lib.check(L.rcsb_model_set_mesh_vertices(self.ptr, _dp(self.verts), len(self.verts)))
         gadr, gnbr = devmodel.build_mesh_graph(M)
         _lib.check(L.rcsb_model_set_mesh_graph(self.ptr, _ip(gadr), len(gadr), _ip(gnbr), int(gadr[-1])))
+        planes, fadr, fnum = devmodel.build_mesh_faces(M)
+        _lib.check(L.rcsb_model_set_mesh_faces(self.ptr, _dp(planes), int(fnum.sum()), _ip(fadr), _ip(fnum), len(fadr)))
         _lib.check(L.rcsb_model_finalize(self.ptr))
         d = [C.c_int(0) for _ in range(5)]
         _lib.check(L.rcsb_model_dims(self.ptr, *[C.byref(x) for x in d]))
@@ -161,6 +163,25 @@ class Batch:
         _lib.check(_lib.lib().rcsb_env_step_host(self.ptr, ops, k, max_convergence_steps, act_host.data_ptr(), float(max_mov),
                                                  _dp(lo) if lo is not None else None, _dp(hi) if hi is not None else None,
                                                  obs_host.data_ptr()))
+
+    def body_frames(self) -> torch.Tensor:
+        """[n, nb, 12] world frames (position, row-major rotation) of the moving bodies at the current qpos."""
+        nb = int(self.model.fields["nb"][0][0])
+        out = torch.empty((self.n, nb, 12), dtype=torch.float64, device=self.dev)
+        _lib.check(_lib.lib().rcsb_body_frames(self.ptr, out.data_ptr()))
+        return out
+
+    def camera_depth(self, cam_body: int, cam_pos, cam_rot, fovy_deg: float, width: int, height: int, znear: float, zfar: float,
+                     physical_units: bool, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Depth frame of every environment for one camera (rcsb_camera_depth): [n, height, width] uint16."""
+        if out is None:
+            out = torch.empty((self.n, height, width), dtype=torch.uint16, device=self.dev)
+        assert out.shape == (self.n, height, width) and out.dtype == torch.uint16 and out.is_contiguous()
+        p = np.ascontiguousarray(cam_pos, dtype=np.float64)
+        r = np.ascontiguousarray(cam_rot, dtype=np.float64).reshape(9)
+        _lib.check(_lib.lib().rcsb_camera_depth(self.ptr, int(cam_body), _dp(p), _dp(r), float(fovy_deg), int(width), int(height),
+                                                float(znear), float(zfar), int(bool(physical_units)), out.data_ptr()))
+        return out
 
     def ik_inverse(self, pose: torch.Tensor, q0: torch.Tensor):
         nqm = int(self.model.fields["rb_ik_nq"][0][0])

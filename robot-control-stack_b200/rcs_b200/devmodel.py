@@ -49,6 +49,44 @@ def build_mesh_graph(M: dict):
     return np.array(gadr, dtype=np.int32), np.array(gnbr if gnbr else [0], dtype=np.int32)[:max(len(gnbr), 1)]
 
 
+def _collidable(M: dict):
+    col = [g for g in range(M["ngeom"]) if M["geom_contype"][g] or M["geom_conaffinity"][g]]
+    used = {int(g) for pr in M["pair_geom"] for g in pr}
+    return [g for g in col if g in used]
+
+
+def build_mesh_faces(M: dict):
+    """Hull face planes restricted to the device geom list: (planes[nface, 4], faceadr[ng], facenum[ng])."""
+    col = _collidable(M)
+    adr, num, pool, n = [], [], [], 0
+    for g in col:
+        k = int(M["geom_facenum"][g]) if "geom_facenum" in M else 0
+        if k > 0:
+            a = int(M["geom_faceadr"][g])
+            adr.append(n); num.append(k); pool.append(np.asarray(M["mesh_face"][a:a + k], dtype=np.float64)); n += k
+        else:
+            adr.append(0); num.append(0)
+    planes = np.concatenate(pool, axis=0) if pool else np.zeros((1, 4))
+    return np.ascontiguousarray(planes), np.array(adr, dtype=np.int32), np.array(num, dtype=np.int32)
+
+
+def fold_frame(M: dict, body: int, pos, quat):
+    """A frame given in (original) body `body` re-expressed in the device model's body tree: returns (moving body index or
+    -1 for the world, position, row-major rotation matrix). Jointless bodies are folded into their nearest moving ancestor
+    exactly as build_device_fields folds them."""
+    parent = M["body_parentid"]
+    moving = [b for b in range(M["nbody"]) if M["body_jntnum"][b] > 0]
+    mb_of = {b: i for i, b in enumerate(moving)}
+    p, q = np.asarray(pos, dtype=np.float64), np.asarray(quat, dtype=np.float64)
+    b = int(body)
+    while b != 0 and b not in mb_of:  # climb through the welded chain, composing the static offsets
+        p = M["body_pos"][b] + quat_to_mat(M["body_quat"][b]) @ p
+        q = quat_mul(M["body_quat"][b], q)
+        b = int(parent[b])
+    q = q / np.linalg.norm(q)
+    return (mb_of[b] if b != 0 else -1), p, quat_to_mat(q)
+
+
 def build_device_fields(M: dict, robot_cfg=None, gripper_cfg=None, maxcon: int | None = None,
                         fast_maxcon: int | None = None) -> tuple[dict, np.ndarray]:
     """Returns ({field: (np.ndarray, is_real)}, mesh_vert[nvert,3]).

@@ -33,8 +33,6 @@ class SimEnvCreator:
             device = 0
         if hand_cfg is not None:
             raise NotImplementedError("SimTilburgHand is out of scope (SURVEY.md 2 row 15)")
-        if cameras is not None:
-            raise NotImplementedError("SimCameraSet is a 'next' row (SURVEY.md 8f-2)")
         simulation = sim.Sim(robot_cfg.mjcf_scene_path, sim_cfg, num_envs=num_envs, device=device)
         ik = sim.Pin(robot_cfg.kinematic_model_path, robot_cfg.attachment_site,
                      urdf=robot_cfg.kinematic_model_path.endswith(".urdf"))
@@ -43,6 +41,10 @@ class SimEnvCreator:
         env = SimVectorEnv(simulation, robot, gripper, control_mode, max_relative_movement, relative_to)
         if sim_wrapper is not None:  # creators.py:101-103: the task layer wraps the sim env
             env = sim_wrapper(env, simulation)
+        if cameras is not None:  # creators.py:105-110: SimCameraSet + CameraSetWrapper (depth frames of every environment)
+            from rcs_b200.camera.sim import CameraSetWrapper, SimCameraSet
+            camera_set = SimCameraSet(simulation, cameras, physical_units=True, render_on_demand=True)
+            env = CameraSetWrapper(env, camera_set, include_depth=True)
         if shard:
             from rcs_b200.envs.sharded import ShardedVectorEnv
             env = ShardedVectorEnv(env, n_total)

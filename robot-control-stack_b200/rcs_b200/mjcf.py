@@ -228,6 +228,41 @@ def hull_edge_graph(hv):
     return [sorted(x) for x in nbr]
 
 
+def hull_face_planes(hv):
+    """Supporting planes of the convex hull of hv: rows (n, d) with n . x + d <= 0 inside, unit normals, coplanar
+    (triangulated) facets merged. Used by the depth ray-caster (ray / convex polytope clipping)."""
+    from scipy.spatial import ConvexHull
+
+    if len(hv) < 4:
+        return np.zeros((0, 4))
+    try:
+        eq = ConvexHull(hv).equations
+    except Exception:
+        return np.zeros((0, 4))
+    out = []
+    for e in eq:
+        e = e / np.linalg.norm(e[:3])
+        if not any(np.abs(e - o).max() < 1e-7 for o in out):
+            out.append(e)
+    return np.array(out)
+
+
+def mesh_face_arrays(M):
+    """Pooled hull face planes: (mesh_face[nface, 4], geom_faceadr[ngeom], geom_facenum[ngeom])."""
+    adr = -np.ones(M["ngeom"], dtype=np.int32)
+    num = np.zeros(M["ngeom"], dtype=np.int32)
+    pool, n = [], 0
+    for g in range(M["ngeom"]):
+        a, k = int(M["geom_vertadr"][g]), int(M["geom_vertnum"][g])
+        if k <= 0:
+            continue
+        pl = hull_face_planes(np.asarray(M["mesh_vert"][a:a + k]))
+        adr[g], num[g] = n, len(pl)
+        pool.append(pl)
+        n += len(pl)
+    return (np.concatenate(pool, axis=0) if pool else np.zeros((0, 4))), adr, num
+
+
 def mesh_graph_arrays(M):
     """CSR form of hull_edge_graph over the pooled hull vertices: (adr[nmeshvert + 1], nbr[...] local vertex ids)."""
     nvert = len(M["mesh_vert"])
@@ -759,6 +794,7 @@ def compile_mjcf(path: str) -> dict:
     M["geom_vertadr"], M["geom_vertnum"] = vert_adr, vert_num
     M["mesh_vert"] = np.concatenate(pool, axis=0) if pool else np.zeros((0, 3))
     M["mesh_graphadr"], M["mesh_graph"] = mesh_graph_arrays(M)
+    M["mesh_face"], M["geom_faceadr"], M["geom_facenum"] = mesh_face_arrays(M)
     # local AABB (centre, half-size) in the geom frame for the mid-phase box test
     aabb = np.zeros((ngeom, 6))
     for gi, g in enumerate(geoms):
