@@ -349,6 +349,49 @@ def measure(h, workload, n_per_gpu, K, W, sampler=None, want_e2e=True):
     return rec
 
 
+def measure_depth(h, n_per_gpu, width=128, height=128, K=10, W=3):
+    """SimCameraSet depth frames: one wrist-camera frame of every environment per step, after a physics
+    env.step(). The depth kernel writes N x H x W uint16: the one kernel of this repository whose roof is HBM writes."""
+    torch = h.torch
+    from rcs_b200 import sim
+    from rcs_b200.camera import SimCameraConfig, SimCameraSet
+    from rcs_b200.envs.base import ControlMode
+    from rcs_b200.envs.creators import SimEnvCreator
+    from rcs_b200.envs.utils import default_sim_gripper_cfg, default_sim_robot_cfg
+    env = SimEnvCreator()(ControlMode.JOINTS, default_sim_robot_cfg("fr3_simple_pick_up"), gripper_cfg=default_sim_gripper_cfg(),
+                          sim_cfg=sim.SimConfig(async_control=True, frequency=30), max_relative_movement=MAX_MOV, num_envs=n_per_gpu,
+                          device=h.local)
+    cams = SimCameraSet(env.sim, {"wrist": SimCameraConfig("wrist_0", 30, width, height)}, physical_units=True)
+    env.reset()
+    gen = torch.Generator(device=h.dev).manual_seed(7)
+    ms = []
+    for i in range(K + W):
+        a = {"joints": (torch.rand((n_per_gpu, 7), dtype=torch.float64, device=h.dev, generator=gen) * 2 - 1) * MAX_MOV,
+             "gripper": torch.randint(0, 2, (n_per_gpu,), device=h.dev, generator=gen).to(torch.float64)}
+        env.step_packed(a)
+        h.flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(h.stream)
+        cams.render()
+        e1.record(h.stream)
+        torch.cuda.synchronize()
+        if i >= W:
+            ms.append(e0.elapsed_time(e1))
+    t = h.max_over_ranks(float(np.mean(ms)))
+    peak, peak_src = measured_peak()
+    nbytes = n_per_gpu * width * height * 2
+    rec = {"workload": "depth", "scene": "fr3_simple_pick_up", "envs_per_gpu": n_per_gpu, "camera": "wrist_0", "resolution": [width, height],
+           "value": h.world * n_per_gpu / (t * 1e-3), "unit": "depth frames/s", "ms_per_step": t,
+           "roofline": {"bound": "hbm", "achieved": nbytes / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": nbytes / (t * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
+                        "traffic": None,
+                        "note": "frames export launch + ray-cast launch; bytes = uint16 pixels written. Compute bound in practice "
+                                "(every ray is tested against up to 25 geoms / hundreds of hull planes in float64)"}}
+    del env
+    torch.cuda.empty_cache()
+    return rec
+
+
 def kernel_time_ms(h, n_per_gpu, K=20):
     """Average duration of the dominant kernel (one fused env.step launch) timed alone with CUDA events on its stream."""
     torch = h.torch
@@ -395,6 +438,10 @@ def run_ours(args):
                 sweep.append(measure(h, wl, n, k, w))
             except Exception as e:  # a sub-record never takes the headline down
                 sweep.append({"workload": wl, "envs_per_gpu": n, "error": f"{type(e).__name__}: {e}"})
+        try:
+            sweep.append(measure_depth(h, 4096))
+        except Exception as e:
+            sweep.append({"workload": "depth", "envs_per_gpu": 4096, "error": f"{type(e).__name__}: {e}"})
     if h.rank == 0:
         peak, peak_src = measured_peak()
         bpe = bytes_per_env_step("fr3_empty_world")

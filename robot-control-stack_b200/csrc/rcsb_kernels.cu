@@ -182,6 +182,18 @@ __device__ __forceinline__ bool ray_geom(const RcsbModel& m, int g, const real* 
     if (best < (real)1e299) t = best;
   } else if (type == RCSB_GEOM_MESH) {
     real t0 = 0, t1 = tmax;
+    {  // the hull lies inside its local AABB: a slab test first (most rays that pass the bounding sphere miss the box)
+      const real* ab = m.g_aabb[g];
+      for (int k = 0; k < 3; k++) {
+        if (d[k] != 0) {
+          real ta = (ab[k] - ab[3 + k] - o[k]) / d[k], tb = (ab[k] + ab[3 + k] - o[k]) / d[k];
+          if (ta > tb) { real sw = ta; ta = tb; tb = sw; }
+          t0 = ta > t0 ? ta : t0; t1 = tb < t1 ? tb : t1;
+        } else if (o[k] < ab[k] - ab[3 + k] || o[k] > ab[k] + ab[3 + k]) t1 = -1;
+      }
+      if (t0 > t1) return false;
+      t0 = 0; t1 = tmax;  // the planes decide alone: the result stays independent of the pre-test
+    }
     const real* pl = faces + 4 * (size_t)face_adr[g];
     const int n = face_num[g];
     for (int i = 0; i < n && t0 <= t1; i++) {
