@@ -392,6 +392,68 @@ def measure_depth(h, n_per_gpu, width=128, height=128, K=10, W=3):
     return rec
 
 
+def measure_fleet(h, n_per_type=4096, K=10, W=3):
+    """Config C5 (BASELINE.json configs[4]), declared SYNTHETIC and REDUCED: a mixed fleet of FR3 (fr3_empty_world), xArm7
+    (xarm7_empty_world) and FR3 + cube (fr3_simple_pick_up, standing in for the UR5e, of which the reference ships joint
+    limits only: include/rcs/Robot.h:43-59) with n_per_type environments each per GPU, JOINTS control, stepped concurrently
+    on three streams (rcs_b200.envs.fleet), plus one 64 x 64 wrist depth frame per FR3 environment per step."""
+    torch = h.torch
+    from rcs_b200 import sim, workloads as WL
+    from rcs_b200.camera import SimCameraConfig, SimCameraSet
+    from rcs_b200.envs.base import ControlMode
+    from rcs_b200.envs.creators import SimEnvCreator
+    from rcs_b200.envs.fleet import FleetVectorEnv
+    from rcs_b200.envs.utils import default_sim_gripper_cfg, default_sim_robot_cfg
+    cfg = sim.SimConfig(async_control=True, frequency=30)
+
+    def fr3(scene):
+        return lambda: SimEnvCreator()(ControlMode.JOINTS, default_sim_robot_cfg(scene), gripper_cfg=default_sim_gripper_cfg(), sim_cfg=cfg,
+                                       max_relative_movement=MAX_MOV, num_envs=n_per_type, device=h.local)
+    fleet = FleetVectorEnv({"fr3": fr3("fr3_empty_world"),
+                            "xarm7": lambda: SimEnvCreator()(ControlMode.JOINTS, WL.xarm7_robot_cfg(), gripper_cfg=None, sim_cfg=cfg,
+                                                             max_relative_movement=MAX_MOV, num_envs=n_per_type, device=h.local),
+                            "fr3_cube": fr3("fr3_simple_pick_up")}, device=h.local)
+    cams = {k: SimCameraSet(fleet.envs[k].sim, {"wrist": SimCameraConfig("wrist_0", 30, 64, 64)}, physical_units=True) for k in ("fr3", "fr3_cube")}
+    fleet.reset()
+    gen = torch.Generator(device=h.dev).manual_seed(3)
+
+    def acts():
+        a = {}
+        for k, e in fleet.envs.items():
+            a[k] = {"joints": (torch.rand((n_per_type, 7), dtype=torch.float64, device=h.dev, generator=gen) * 2 - 1) * MAX_MOV}
+            if e.gripper is not None:
+                a[k]["gripper"] = torch.randint(0, 2, (n_per_type,), device=h.dev, generator=gen).to(torch.float64)
+        return a
+
+    def one():
+        fleet.step_packed(acts())
+        for k, c in cams.items():
+            with torch.cuda.stream(fleet.streams[k]):
+                c.render()
+        for s in fleet.streams.values():
+            ev = torch.cuda.Event(); ev.record(s); h.stream.wait_event(ev)
+
+    for _ in range(W):
+        one()
+    h.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for i in range(K):
+        h.flush.zero_()
+        ev[i][0].record(h.stream)
+        one()
+        ev[i][1].record(h.stream)
+    h.barrier()
+    ms = h.max_over_ranks(sum(a.elapsed_time(c) for a, c in ev))
+    total = 3 * n_per_type
+    rec = {"workload": "c5_fleet", "envs_per_gpu": total, "groups": {k: n_per_type for k in fleet.envs}, "depth": "64x64 wrist frame per FR3 env",
+           "value": h.world * total * K / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms / K, "physics_steps_per_s": h.world * total * K / (ms * 1e-3) * SUBSTEPS,
+           "warps_per_cta": None, "variant": "fr3_reduced + generic + fr3_pickup",
+           "note": "synthetic and reduced: UR5e replaced by the FR3 pick-up scene (no UR5e model in the reference)"}
+    del fleet, cams
+    torch.cuda.empty_cache()
+    return rec
+
+
 def kernel_time_ms(h, n_per_gpu, K=20):
     """Average duration of the dominant kernel (one fused env.step launch) timed alone with CUDA events on its stream."""
     torch = h.torch
@@ -438,6 +500,10 @@ def run_ours(args):
                 sweep.append(measure(h, wl, n, k, w))
             except Exception as e:  # a sub-record never takes the headline down
                 sweep.append({"workload": wl, "envs_per_gpu": n, "error": f"{type(e).__name__}: {e}"})
+        try:
+            sweep.append(measure_fleet(h, 4096))
+        except Exception as e:
+            sweep.append({"workload": "c5_fleet", "envs_per_gpu": 3 * 4096, "error": f"{type(e).__name__}: {e}"})
         try:
             sweep.append(measure_depth(h, 4096))
         except Exception as e:

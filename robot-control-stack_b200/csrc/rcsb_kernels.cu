@@ -341,6 +341,18 @@ struct rcsb_batch {
   real* con_real = nullptr;
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per kernel, not per batch: batches of different scenes share the generic
+// kernel, so the attribute only ever grows
+#include <map>
+static cudaError_t ensure_smem(rcsb_smem_fn fn, size_t bytes) {
+  static std::map<rcsb_smem_fn, size_t> granted;
+  size_t& have = granted[fn];
+  if (bytes <= have) return cudaSuccess;
+  cudaError_t e = fn(bytes);
+  if (e == cudaSuccess) have = bytes;
+  return e;
+}
+
 extern "C" {
 const char* rcsb_last_error(void) { return g_err.c_str(); }
 int rcsb_version(void) { return 100; }
@@ -507,7 +519,7 @@ rcsb_batch* rcsb_batch_new(rcsb_model* m, int n_envs, void* sr, void* sd, void* 
   if (ok && m->has_reduced) ok = shape(m->h, b->var_full, b->ws_bytes_full, b->warps_full, b->smem_full, b->grid_full);
   if (!ok) { fail(RCSB_ERR_MODEL, "workspace does not fit in shared memory"); delete b; return nullptr; }
   const size_t smem_max = b->smem > b->smem_full ? b->smem : b->smem_full;  // both phases may use the same kernel
-  if (b->var.set_smem(smem_max) != cudaSuccess || (m->has_reduced && b->var_full.set_smem(smem_max) != cudaSuccess) ||
+  if (ensure_smem(b->var.set_smem, smem_max) != cudaSuccess || (m->has_reduced && ensure_smem(b->var_full.set_smem, smem_max) != cudaSuccess) ||
       cudaFuncSetAttribute(rcsb_k_ik, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCSB_SMEM_HEADER) != cudaSuccess ||
       cudaFuncSetAttribute(rcsb_k_cart_action, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCSB_SMEM_HEADER) != cudaSuccess ||
       cudaFuncSetAttribute(rcsb_k_ik8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCSB_SMEM_HEADER) != cudaSuccess ||

@@ -131,9 +131,11 @@ class SimVectorEnv:
         obs, info, truncated = self.unpack(self.step_packed(action))  # tensors allocated for this step: never overwritten later
         return obs, torch.zeros_like(self._zeros), torch.zeros_like(self._false), truncated, info
 
-    def step_packed(self, action: dict, obs_out: torch.Tensor | None = None) -> torch.Tensor:
+    def step_packed(self, action: dict, obs_out: torch.Tensor | None = None, mask: torch.Tensor | None = None) -> torch.Tensor:
         """env.step() that returns the packed observation rows [n, obs_dim] (see unpack); with obs_out the kernel writes
-        them straight into that tensor (this rank's slice of the multi-GPU gather buffer)."""
+        them straight into that tensor (this rank's slice of the multi-GPU gather buffer). mask ([n] uint8, JOINTS control):
+        environments with mask == 0 are left untouched -- not a bit of their state changes and their rows of the result
+        are unspecified (CollisionGuard overwrites them with the last observation)."""
         b = self.sim.batch
         ops, cfg = self._step_ops()
         aj = ag = None
@@ -175,7 +177,7 @@ class SimVectorEnv:
             ag = action["gripper"].to(device=self.dev, dtype=torch.float64).reshape(-1).contiguous()
         b.run(ops, k=self._substeps(), max_convergence_steps=cfg.max_convergence_steps, act_joints=aj, act_gripper=ag,
               max_mov=float(self.max_mov) if (self.relative and self.control_mode == ControlMode.JOINTS) else 0.0,
-              jlow=self.jlow, jhigh=self.jhigh, want_obs=True, fresh_obs=True, obs_out=obs_out)
+              jlow=self.jlow, jhigh=self.jhigh, want_obs=True, fresh_obs=True, obs_out=obs_out, mask=mask)
         return b.obs
 
     def _to_pose7(self, a: torch.Tensor) -> torch.Tensor:

@@ -315,10 +315,14 @@ class SimRobot(common.Robot):
         b = self.sim.batch
         b.run(_lib.SET_JOINTS, act_joints=self._as_dev(q, b.model.njoints))
 
-    def get_joint_position(self):
+    def get_joint_position_tensor(self) -> torch.Tensor:
+        """[num_envs, njoints] joint positions of every environment (a fresh device tensor)."""
         b = self.sim.batch
         idx = torch.as_tensor(np.asarray(b.model.fields["rb_qadr"][0]), device=b.dev, dtype=torch.long)
-        return _scalarize(b.qpos.index_select(1, idx), self._n)
+        return b.qpos.index_select(1, idx)
+
+    def get_joint_position(self):
+        return _scalarize(self.get_joint_position_tensor(), self._n)
 
     def move_home(self):
         self.set_joint_position(self._meta.q_home)

@@ -359,3 +359,69 @@ def test_cartesian_configured_origin_matches_reference_math(mode_name):
         assert okn.sum() > N // 2 and np.array_equal(info["ik_success"].cpu().numpy(), okn), step
         ctrl = b.ctrl[:, :7].cpu().numpy()
         assert np.abs(ctrl[okn] - q_exp.cpu().numpy()[okn, :7]).max() < 1e-8, step
+
+
+def test_mixed_fleet_steps_groups_concurrently_and_matches_separate_envs():
+    """FleetVectorEnv: an FR3 group and an xArm7 group stepped on their own streams give exactly
+    the observations of the same envs stepped alone."""
+    from rcs_b200 import sim, workloads as WL
+    from rcs_b200.envs.base import ControlMode
+    from rcs_b200.envs.creators import SimEnvCreator
+    from rcs_b200.envs.fleet import FleetVectorEnv
+    from rcs_b200.envs.utils import default_sim_gripper_cfg, default_sim_robot_cfg
+    cfg = sim.SimConfig(async_control=True)
+    mk = {"fr3": lambda: SimEnvCreator()(ControlMode.JOINTS, default_sim_robot_cfg("fr3_empty_world"), gripper_cfg=default_sim_gripper_cfg(),
+                                         sim_cfg=cfg, max_relative_movement=float(np.deg2rad(5)), num_envs=96),
+          "xarm7": lambda: SimEnvCreator()(ControlMode.JOINTS, WL.xarm7_robot_cfg(), gripper_cfg=None, sim_cfg=cfg,
+                                           max_relative_movement=float(np.deg2rad(5)), num_envs=64)}
+    fleet = FleetVectorEnv(mk)
+    alone = {k: f() for k, f in mk.items()}
+    obs, _ = fleet.reset()
+    for k, e in alone.items():
+        o, _ = e.reset()
+        assert torch.equal(o["joints"], obs[k]["joints"])
+    torch.manual_seed(0)
+    for _ in range(4):
+        acts = fleet.sample_actions()
+        res = fleet.step(acts)
+        torch.cuda.synchronize()
+        for k, e in alone.items():
+            o, _, _, _, info = e.step(acts[k])
+            assert torch.equal(o["joints"], res[k][0]["joints"]) and torch.equal(o["tquat"], res[k][0]["tquat"])
+            assert torch.equal(info["ik_success"], res[k][4]["ik_success"])
+    assert res["fr3"][0]["joints"].shape == (96, 7) and res["xarm7"][0]["joints"].shape == (64, 7)
+
+
+def test_collision_guard_vetoes_per_environment_and_multi_robot_wrapper():
+    """CollisionGuard (envs/sim.py:156-287) on vector envs: the shadow env executes every action first; environments whose
+    action drives the arm into the floor are vetoed -- masked out of the launch (state bit-identical), last observation
+    returned with terminated = truncated = True -- while the others step. MultiRobotWrapper (base.py:310-355) steps a dict of
+    envs and ORs the flags."""
+    from rcs_b200.envs.base import ControlMode
+    from rcs_b200.envs.guard import CollisionGuard, MultiRobotWrapper
+    N = 12
+    env = _mk(ControlMode.JOINTS, num_envs=N, gripper=False)            # sync control: step_until_convergence
+    shadow = _mk(ControlMode.JOINTS, num_envs=N, gripper=False)
+    guard = CollisionGuard(env, env.sim, shadow, check_home_collision=True)
+    obs, _ = guard.reset()
+    q0 = obs["joints"].clone()
+    ok = q0 + 0.05
+    obs, rew, term, trunc, info = guard.step({"joints": ok})
+    assert not bool(term.any()) and not bool(info["guard_collision"].any())
+    assert float((obs["joints"] - ok).abs().max()) < 0.01
+    before = env.sim.batch.sr.clone()
+    act = obs["joints"].clone() + 0.03
+    floor = torch.tensor([0, 1.78, 0, -1.45, 0, 0, 0.0], dtype=torch.float64, device=act.device)  # test_sim_envs.py:347-360
+    act[::3] = floor
+    obs2, rew, term, trunc, info = guard.step({"joints": act})
+    coll = info["guard_collision"].cpu().numpy()
+    assert coll[::3].all() and not coll[1::3].any() and not coll[2::3].any()
+    assert torch.equal(term.cpu(), torch.as_tensor(coll)) and bool(trunc[::3].all())
+    assert torch.equal(env.sim.batch.sr[::3], before[::3]), "vetoed environments must not change at all"
+    assert torch.equal(obs2["joints"][::3], obs["joints"][::3])        # they report their last observation
+    assert float((obs2["joints"][1::3] - act[1::3]).abs().max()) < 0.01  # the others moved
+    multi = MultiRobotWrapper({"a": _mk(ControlMode.JOINTS, num_envs=4, gripper=False, async_control=True),
+                               "b": _mk(ControlMode.JOINTS, num_envs=4, gripper=False, async_control=True)})
+    o, i = multi.reset()
+    o, r, t, tr, i = multi.step({"a": {"joints": o["a"]["joints"] + 0.02}, "b": {"joints": o["b"]["joints"] - 0.02}})
+    assert set(o) == {"a", "b"} and r.shape == (4,) and not bool(t.any()) and "truncated" in i["a"]

@@ -12,6 +12,6 @@ for r in d.get("sweep", []):
         print(f"  sweep depth    {r['envs_per_gpu']:6d}/gpu  {r['value']:.0f} frames/s  {r['ms_per_step']:.3f} ms  {r['roofline']['achieved']:.1f} GB/s  frac {r['roofline']['frac']:.4f}")
     else:
         print(f"  sweep {r['workload']:8s} {r['envs_per_gpu']:6d}/gpu  {r['value']:.0f} env-steps/s  {r['ms_per_step']:.3f} ms  phys {r['physics_steps_per_s']:.3e}  "
-              f"e2e {(r.get('e2e') or {}).get('value', 0):.0f}  warps {r['warps_per_cta']} {r['variant']}")
+              f"e2e {(r.get('e2e') or {}).get('value', 0):.0f}  warps {r.get('warps_per_cta')} {r.get('variant')}")
 if "cpu_baseline" in d:
     print("  cpu", {k: d["cpu_baseline"].get(k) for k in ("value", "cores")})
