@@ -120,6 +120,14 @@ int rcsb_ik_inverse(rcsb_batch* b, const void* pose_dev, const void* q0_dev, voi
 /* SimRobot::set_cartesian_position for every env (SimRobot.cpp:145-155) */
 int rcsb_robot_set_cartesian_position(rcsb_batch* b, const void* pose_dev);
 
+/* Host-pointer variants for bindings that own no device memory (the compiled rcs_b200._core module):
+ * synchronous, temporary device buffers per call. pose7_host [n][7], q0_host [n][njoints], q_out_host [n][ik_nq]. */
+int rcsb_batch_info(rcsb_batch* b, int* n_envs, int* njoints, int* ik_nq, int* nq, int* nv, int* nu);
+int rcsb_batch_read_row(rcsb_batch* b, int env, double* sr_row, double* sd_row, int* si_row); /* one environment's state rows */
+int rcsb_robot_set_cartesian_position_host(rcsb_batch* b, const double* pose7_host);
+int rcsb_ik_inverse_host(rcsb_batch* b, const double* pose7_host, const double* q0_host, double* q_out_host, int* success_host,
+                         int* iters_host);
+
 /* Cartesian Gym action for every env: RelativeActionSpace.action (python/rcs/envs/base.py:490-578, RelativeTo.LAST_STEP
  * when relative != 0: offset clipped to max_trans [m] / max_rot [rad], applied to the current Cartesian position, xyz
  * clipped to the workspace box) + RobotEnv.step's dedupe against the previous action and dispatch (base.py:255-288) +

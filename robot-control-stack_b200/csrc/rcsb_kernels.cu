@@ -811,6 +811,64 @@ int rcsb_env_cartesian_action(rcsb_batch* b, const void* act_dev, int kind, int 
   if (relative != 0 && relative != 1) return fail(RCSB_ERR_ARG, "bad argument");
   return rcsb_env_cartesian_action_origin(b, act_dev, kind, relative, max_trans, max_rot, nullptr, nullptr, nullptr);
 }
+// ---- host-pointer variants for bindings that own no device memory (the compiled rcs_b200._core module): slow path,
+//      synchronous, temporary device buffers per call
+struct DevTmp {
+  void* p = nullptr;
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  ~DevTmp() { if (p) cudaFree(p); }
+};
+int rcsb_batch_info(rcsb_batch* b, int* n_envs, int* njoints, int* ik_nq, int* nq, int* nv, int* nu) {
+  if (!b) return fail(RCSB_ERR_ARG, "null batch");
+  if (n_envs) *n_envs = b->n;
+  if (njoints) *njoints = b->m->h.rb_njoints;
+  if (ik_nq) *ik_nq = b->m->h.rb_ik_nq < 9 ? b->m->h.rb_ik_nq : 9;
+  if (nq) *nq = b->m->h.nq;
+  if (nv) *nv = b->m->h.nv;
+  if (nu) *nu = b->m->h.nu;
+  return RCSB_OK;
+}
+int rcsb_batch_read_row(rcsb_batch* b, int env, double* sr_row, double* sd_row, int* si_row) {
+  if (!b || env < 0 || env >= b->n) return fail(RCSB_ERR_ARG, "bad environment index");
+  if (sizeof(real) != sizeof(double)) return fail(RCSB_ERR_ARG, "float64 build required");
+  DEVICE_OK(b->m->device);
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  const int nsr = b->m->h.lay.nsr;
+  if (sr_row) CUDA_OK(cudaMemcpy(sr_row, b->sr + (size_t)env * nsr, nsr * sizeof(real), cudaMemcpyDeviceToHost));
+  if (sd_row) CUDA_OK(cudaMemcpy(sd_row, b->sd + (size_t)env * RCSB_D_TAIL, RCSB_D_TAIL * sizeof(double), cudaMemcpyDeviceToHost));
+  if (si_row) CUDA_OK(cudaMemcpy(si_row, b->si + (size_t)env * RCSB_I_TAIL, RCSB_I_TAIL * sizeof(int), cudaMemcpyDeviceToHost));
+  return RCSB_OK;
+}
+int rcsb_robot_set_cartesian_position_host(rcsb_batch* b, const double* pose7_host) {
+  if (!b || !pose7_host) return fail(RCSB_ERR_ARG, "null argument");
+  DEVICE_OK(b->m->device);
+  DevTmp p;
+  CUDA_OK(p.alloc((size_t)b->n * 7 * sizeof(real)));
+  CUDA_OK(cudaMemcpyAsync(p.p, pose7_host, (size_t)b->n * 7 * sizeof(real), cudaMemcpyHostToDevice, b->stream));
+  int rc = launch_ik(b, p.p, nullptr, nullptr, nullptr, nullptr, 1);
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  return rc;
+}
+int rcsb_ik_inverse_host(rcsb_batch* b, const double* pose7_host, const double* q0_host, double* q_out_host, int* success_host,
+                         int* iters_host) {
+  if (!b || !pose7_host || !q0_host || !q_out_host || !success_host) return fail(RCSB_ERR_ARG, "null argument");
+  DEVICE_OK(b->m->device);
+  const int nj = b->m->h.rb_njoints, nqm = b->m->h.rb_ik_nq < 9 ? b->m->h.rb_ik_nq : 9;
+  const size_t n = (size_t)b->n;
+  DevTmp p, q0, q, ok, it;
+  CUDA_OK(p.alloc(n * 7 * sizeof(real))); CUDA_OK(q0.alloc(n * nj * sizeof(real))); CUDA_OK(q.alloc(n * nqm * sizeof(real)));
+  CUDA_OK(ok.alloc(n * sizeof(int))); CUDA_OK(it.alloc(n * sizeof(int)));
+  CUDA_OK(cudaMemcpyAsync(p.p, pose7_host, n * 7 * sizeof(real), cudaMemcpyHostToDevice, b->stream));
+  CUDA_OK(cudaMemcpyAsync(q0.p, q0_host, n * nj * sizeof(real), cudaMemcpyHostToDevice, b->stream));
+  CUDA_OK(cudaMemsetAsync(q.p, 0, n * nqm * sizeof(real), b->stream));
+  int rc = launch_ik(b, p.p, q0.p, q.p, (int*)ok.p, (int*)it.p, 0);
+  if (rc) return rc;
+  CUDA_OK(cudaMemcpyAsync(q_out_host, q.p, n * nqm * sizeof(real), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_OK(cudaMemcpyAsync(success_host, ok.p, n * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  if (iters_host) CUDA_OK(cudaMemcpyAsync(iters_host, it.p, n * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  return RCSB_OK;
+}
 int rcsb_ik_inverse(rcsb_batch* b, const void* pose_dev, const void* q0_dev, void* q_out_dev, int* success_dev, int* iters_dev) {
   if (!q0_dev || !q_out_dev || !success_dev) return fail(RCSB_ERR_ARG, "null argument");
   return launch_ik(b, pose_dev, q0_dev, q_out_dev, success_dev, iters_dev, 0);

@@ -83,7 +83,8 @@ def check(rc: int):
 
 
 EXPORTS = ["rcsb_last_error", "rcsb_version", "rcsb_real_bytes", "rcsb_model_new", "rcsb_model_free",
-           "rcsb_model_set_int", "rcsb_model_set_real", "rcsb_model_set_mesh_vertices", "rcsb_model_set_mesh_graph", "rcsb_model_set_mesh_faces", "rcsb_model_finalize", "rcsb_camera_depth", "rcsb_body_frames",
+           "rcsb_model_set_int", "rcsb_model_set_real", "rcsb_model_set_mesh_vertices", "rcsb_model_set_mesh_graph", "rcsb_model_set_mesh_faces", "rcsb_model_finalize", "rcsb_camera_depth", "rcsb_body_frames", "rcsb_batch_info", "rcsb_batch_read_row",
+           "rcsb_robot_set_cartesian_position_host", "rcsb_ik_inverse_host",
            "rcsb_model_upload", "rcsb_model_dims", "rcsb_model_offsets", "rcsb_model_workspace_bytes", "rcsb_batch_new", "rcsb_batch_free",
            "rcsb_batch_init_state", "rcsb_batch_set_contact_export", "rcsb_batch_run", "rcsb_batch_run_host", "rcsb_env_step_host", "rcsb_sim_step",
            "rcsb_sim_step_until_convergence", "rcsb_sim_reset", "rcsb_robot_set_joint_position",
