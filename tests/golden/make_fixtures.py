@@ -23,6 +23,7 @@ CASES = [  # scene, number of states, steps, seed, spread around home
     ("fr3_empty_world", 6, 60, 2, 0.3),
     ("xarm7_empty_world", 6, 40, 3, 0.3),
     ("fr3_simple_pick_up", 3, 30, 4, 0.1),
+    ("xarm7_tabletop", 4, 40, 5, 0.2),
 ]
 
 
@@ -32,6 +33,8 @@ def initial_states(scene, n, seed, spread):
     nq, nv, nu = M["nq"], M["nv"], M["nu"]
     q = np.tile(M["qpos0"], (n, 1)).astype(float)
     home = H.XARM_Q_HOME if scene.startswith("xarm7") else H.Q_HOME
+    if scene == "xarm7_tabletop":
+        q[:, 7:9] += rng.uniform(-0.03, 0.03, (n, 2))  # the brick somewhere on the table
     q[:, :7] = home + rng.uniform(-spread, spread, (n, 7))
     v = np.zeros((n, nv)); v[:, :7] = rng.uniform(-0.5, 0.5, (n, 7))
     ctrl = np.zeros((n, nu)); ctrl[:, :7] = q[:, :7] + rng.uniform(-0.15, 0.15, (n, 7))
@@ -58,6 +61,24 @@ def floor_case():
     return np.array(ncon), np.array(pairs), np.array(q)
 
 
+def grasp_case():
+    """grasp-and-lift on fr3_simple_pick_up (helpers.grasp_and_lift_script): contact count, geom pairs and qpos every 50 steps"""
+    M = H.scene("fr3_simple_pick_up")
+    m, s = H.oracle_sim(M, tcp=H.FRANKA_HAND_TCP)
+    s.gripper_reset(); s.reset(); s.robot_reset(); s.step(1)
+    ncon, pairs, q = [], [], []
+    for qt, w, n in H.grasp_and_lift_script(M):
+        s.set_joint_position(qt); s.gripper_set_normalized_width(w)
+        for _ in range(n // 50):
+            s.step(50)
+            k = int(s.data.ncon[0])
+            ncon.append(k)
+            g = s.data.int("contact_geom").reshape(-1, 2)[:k]
+            pairs.append(np.pad(g, ((0, 40 - k), (0, 0)), constant_values=-1))
+            q.append(s.data.qpos.copy())
+    return np.array(ncon), np.array(pairs), np.array(q)
+
+
 def main():
     out = {"source": np.array("oracle (CPU restatement; libmujoco 3.2.6 not importable here)")}
     try:
@@ -79,6 +100,7 @@ def main():
                           ("qvel_out", v1), ("ncon_out", nc)):
             out[f"c{ci}_{name}"] = arr
     out["floor_ncon"], out["floor_pairs"], out["floor_qpos"] = floor_case()
+    out["grasp_ncon"], out["grasp_pairs"], out["grasp_qpos"] = grasp_case()
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "step_vectors.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-function dynamic instruction totals from an `ncu --page source --csv` export.
 usage: ncu_funcs.py src.csv <git-rev of the profiled sources> [steps_per_launch]"""
-import csv, collections, re, subprocess, sys
+import csv, collections, os, re, subprocess, sys
 rows = list(csv.reader(open(sys.argv[1])))
 rev = sys.argv[2] if len(sys.argv) > 2 else "HEAD"
 units = float(sys.argv[3]) if len(sys.argv) > 3 else 4096 * 17
@@ -20,6 +20,9 @@ for path in {k[0] for k in tot}:
     rel = path.split("/root/repo/")[-1]
     try: text = subprocess.run(["git", "show", f"{rev}:{rel}"], capture_output=True, text=True, cwd="/root/repo").stdout.split("\n")
     except Exception: text = []
+    if len(text) < 5:  # no git history next to the sources (the GPU box): the working tree is what was profiled
+        try: text = open(os.path.join("/root/repo", rel)).read().split("\n")
+        except Exception: text = []
     name = "?"
     starts = []
     for i, line in enumerate(text, 1):
