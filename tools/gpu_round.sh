@@ -8,7 +8,7 @@ nproc >> gpurun_out/${tag}_smi.txt
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_pytest_gpu.log
 timeout 900 python bench.py --steps 50 --warmup 5 > gpurun_out/${tag}_bench.json 2> gpurun_out/bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 12 --warmup 3 --cpu-seconds 0.2 --no-sweep > gpurun_out/ncu_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k rcsb_k_run_fr3_reduced -s 4 -c 1 -o gpurun_out/run_full -f python bench.py --steps 4 --warmup 3 --cpu-seconds 0.2 --no-sweep > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k rcsb_k_run_fr3_reduced -s 9 -c 1 -o gpurun_out/run_full -f python bench.py --steps 6 --warmup 4 --cpu-seconds 0.2 --no-sweep > gpurun_out/ncu_full.log 2>&1
 bash tools/export_profiles.sh gpurun_out/run_full.ncu-rep gpurun_out/${tag}_ncu 69632
 timeout 900 ncu --set full --clock-control none --import-source on -k rcsb_k_run_fr3_pickup -s 6 -c 1 -o gpurun_out/run_c3 -f python tools/bench_c3.py 4096 4 > gpurun_out/ncu_c3.log 2>&1
 bash tools/export_profiles.sh gpurun_out/run_c3.ncu-rep gpurun_out/${tag}_c3_ncu 69632
