@@ -146,12 +146,13 @@ int rcsb_env_cartesian_action_origin(rcsb_batch* b, const void* act_dev, int kin
  * cam_body (-1: world), vertical field of view fovy_deg, width x height pixels; out_dev [n_envs][height][width] uint16,
  * row 0 = top, = (uint16)(1000 * eye-space depth in metres clipped to [znear, zfar]) with physical_units, else
  * (uint16)(1000 * OpenGL window-space depth in [0, 1]). Rays are cast against the collidable geoms (convex hulls for
- * meshes), not rasterised visual meshes. */
-/* world frames of the moving bodies at the current qpos (mjData.xpos / xmat of the bodies that carry a joint):
- * frames_dev [n_envs][nb][12] reals, position then the row-major rotation; used for camera extrinsics */
-int rcsb_body_frames(rcsb_batch* b, void* frames_dev);
+ * meshes), not rasterised visual meshes. cam_frames_dev (optional) [n_envs][12] reals receives the camera's world frame
+ * of every environment (position, then the row-major rotation: mjData.cam_xpos / cam_xmat, for the extrinsics). */
 int rcsb_camera_depth(rcsb_batch* b, int cam_body, const double* cam_pos, const double* cam_rot, double fovy_deg, int width, int height,
-                      double znear, double zfar, int physical_units, void* out_dev);
+                      double znear, double zfar, int physical_units, void* out_dev, void* cam_frames_dev);
+/* world frames of the moving bodies at the current qpos (mjData.xpos / xmat of the bodies that carry a joint):
+ * frames_dev [n_envs][nb][12] reals, position then the row-major rotation */
+int rcsb_body_frames(rcsb_batch* b, void* frames_dev);
 
 /* evidence counters */
 long long rcsb_launch_count(void); /* kernels launched by this library since load */

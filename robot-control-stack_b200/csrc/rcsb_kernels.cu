@@ -211,11 +211,13 @@ __device__ __forceinline__ bool ray_geom(const RcsbModel& m, int g, const real* 
 }
 __global__ void __launch_bounds__(RCSB_CAM_TILE * RCSB_CAM_TILE)
 rcsb_k_depth(const RcsbModel* __restrict__ gm, const real* __restrict__ faces, const int* __restrict__ face_adr,
-             const int* __restrict__ face_num, const real* __restrict__ frames, RcsbCamera cam, unsigned short* __restrict__ out, int N) {
+             const int* __restrict__ face_num, const real* __restrict__ frames, RcsbCamera cam, unsigned short* __restrict__ out, real* __restrict__ cam_frames_out,
+             int N) {
   const RcsbModel& m = *gm;
   __shared__ real gfr[RCSB_MAXG][12];   // world frame of every geom: position, row-major rotation
   __shared__ real gbs[RCSB_MAXG][4];    // bounding sphere: centre, radius
   __shared__ real cfr[12];              // camera frame in the world
+  __shared__ unsigned tile_geoms;       // geoms whose bounding sphere can meet a ray of this tile (planes always)
   const int tiles_x = (cam.W + RCSB_CAM_TILE - 1) / RCSB_CAM_TILE, tiles_y = (cam.H + RCSB_CAM_TILE - 1) / RCSB_CAM_TILE;
   const int env = blockIdx.x / (tiles_x * tiles_y), tile = blockIdx.x - env * tiles_x * tiles_y;
   const int tid = threadIdx.y * RCSB_CAM_TILE + threadIdx.x;
@@ -239,6 +241,48 @@ rcsb_k_depth(const RcsbModel* __restrict__ gm, const real* __restrict__ faces, c
       cfr[r] = p[r] + R[3 * r] * cam.pos[0] + R[3 * r + 1] * cam.pos[1] + R[3 * r + 2] * cam.pos[2];
       for (int k = 0; k < 3; k++) cfr[3 + 3 * r + k] = R[3 * r] * cam.rot[k] + R[3 * r + 1] * cam.rot[3 + k] + R[3 * r + 2] * cam.rot[6 + k];
     }
+    if (cam_frames_out && tile == 0)  // the camera's world frame of this environment (extrinsics), written once
+      for (int i = 0; i < 12; i++) cam_frames_out[(size_t)env * 12 + i] = cfr[i];
+  }
+  __syncthreads();
+  if (tid < 32) {
+    // Tile culling: the tile's rays lie in a cone about its centre ray (half-angle alpha, from the farthest corner); a
+    // sphere of radius r at distance dist subtends asin(r / dist). Geom g can only be hit if the angle between the centre
+    // ray and the sphere centre is at most alpha + beta (tested through cosines, with a little slack: the test is
+    // conservative, so culling never changes a pixel).
+    const int g = tid;
+    int keep = 0;
+    if (g < m.ng) {
+      const real u0 = (tile % tiles_x) * RCSB_CAM_TILE, v0 = (tile / tiles_x) * RCSB_CAM_TILE;
+      const real uc = u0 + (real)0.5 * RCSB_CAM_TILE, vc = v0 + (real)0.5 * RCSB_CAM_TILE;
+      real dcn[3] = {(uc - (real)0.5 * cam.W) / cam.f, -(vc - (real)0.5 * cam.H) / cam.f, (real)-1};
+      const real nc = sqrt(dcn[0] * dcn[0] + dcn[1] * dcn[1] + dcn[2] * dcn[2]);
+      real cosa = 1;
+      for (int k = 0; k < 4; k++) {
+        const real uk = u0 + ((k & 1) ? (real)RCSB_CAM_TILE : (real)0), vk = v0 + ((k & 2) ? (real)RCSB_CAM_TILE : (real)0);
+        const real e[3] = {(uk - (real)0.5 * cam.W) / cam.f, -(vk - (real)0.5 * cam.H) / cam.f, (real)-1};
+        const real ce = (e[0] * dcn[0] + e[1] * dcn[1] + e[2] * dcn[2]) / (nc * sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]));
+        cosa = ce < cosa ? ce : cosa;
+      }
+      cosa = cosa - (real)1e-9;
+      const real sina = sqrt(1 - cosa * cosa > 0 ? 1 - cosa * cosa : (real)0);
+      if (m.g_type[g] == RCSB_GEOM_PLANE) keep = 1;
+      else {
+        real cw[3];  // centre ray in the world
+        for (int r = 0; r < 3; r++) cw[r] = (cfr[3 + 3 * r] * dcn[0] + cfr[3 + 3 * r + 1] * dcn[1] + cfr[3 + 3 * r + 2] * dcn[2]) / nc;
+        const real cx = gbs[g][0] - cfr[0], cy = gbs[g][1] - cfr[1], cz = gbs[g][2] - cfr[2], rr = gbs[g][3] * (real)1.000001 + (real)1e-9;
+        const real dist2 = cx * cx + cy * cy + cz * cz;
+        if (dist2 <= rr * rr) keep = 1;  // the camera sits inside the sphere
+        else {
+          const real dist = sqrt(dist2), sinb = rr / dist, cosb = sqrt(1 - sinb * sinb);
+          const real cost = (cx * cw[0] + cy * cw[1] + cz * cw[2]) / dist;
+          const real cosab = cosa * cosb - sina * sinb;                 // cos(alpha + beta)
+          keep = cost >= cosab;  // alpha, beta < 90 degrees: alpha + beta < 180, where the cosine is monotonic
+        }
+      }
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (tid == 0) tile_geoms = mask;
   }
   __syncthreads();
   const int u = (tile % tiles_x) * RCSB_CAM_TILE + threadIdx.x, v = (tile / tiles_x) * RCSB_CAM_TILE + threadIdx.y;
@@ -247,12 +291,13 @@ rcsb_k_depth(const RcsbModel* __restrict__ gm, const real* __restrict__ faces, c
   const real dc[3] = {(u + (real)0.5 - (real)0.5 * cam.W) / cam.f, -(v + (real)0.5 - (real)0.5 * cam.H) / cam.f, (real)-1};
   real dw[3], ow[3] = {cfr[0], cfr[1], cfr[2]};
   for (int r = 0; r < 3; r++) dw[r] = cfr[3 + 3 * r] * dc[0] + cfr[3 + 3 * r + 1] * dc[1] + cfr[3 + 3 * r + 2] * dc[2];
-  const real dlen2 = dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2];
+  const real dlen2 = dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2], inv_dlen2 = (real)1 / dlen2;
   real tbest = cam.zfar;
-  for (int g = 0; g < m.ng; g++) {
+  for (unsigned rest = tile_geoms; rest; rest &= rest - 1) {
+    const int g = __ffs(rest) - 1;
     if (m.g_type[g] != RCSB_GEOM_PLANE) {  // bounding sphere: closest approach of the ray to the centre
       const real cx = gbs[g][0] - ow[0], cy = gbs[g][1] - ow[1], cz = gbs[g][2] - ow[2];
-      const real tc = (cx * dw[0] + cy * dw[1] + cz * dw[2]) / dlen2;
+      const real tc = (cx * dw[0] + cy * dw[1] + cz * dw[2]) * inv_dlen2;
       const real ex = cx - tc * dw[0], ey = cy - tc * dw[1], ez = cz - tc * dw[2], rr = gbs[g][3];
       if (ex * ex + ey * ey + ez * ez > rr * rr) continue;
       if ((tc - tbest) * (tc - tbest) * dlen2 > rr * rr && tc > tbest) continue;  // entirely behind the best hit
@@ -696,7 +741,7 @@ int rcsb_body_frames(rcsb_batch* b, void* frames_dev) {
   return rc;
 }
 int rcsb_camera_depth(rcsb_batch* b, int cam_body, const double* cam_pos, const double* cam_rot, double fovy_deg, int width, int height,
-                      double znear, double zfar, int physical_units, void* out_dev) {
+                      double znear, double zfar, int physical_units, void* out_dev, void* cam_frames_dev) {
   if (!b || !cam_pos || !cam_rot || !out_dev || width < 1 || height < 1 || !(fovy_deg > 0 && fovy_deg < 180) || !(znear > 0 && zfar > znear))
     return fail(RCSB_ERR_ARG, "bad camera argument");
   if (cam_body >= b->m->h.nb) return fail(RCSB_ERR_ARG, "camera body out of range");
@@ -714,7 +759,7 @@ int rcsb_camera_depth(rcsb_batch* b, int cam_body, const double* cam_pos, const 
   if (tiles * b->n > 0x7fffffffLL) return fail(RCSB_ERR_ARG, "image too large for one launch");
   dim3 block(RCSB_CAM_TILE, RCSB_CAM_TILE), grid((unsigned)(tiles * b->n));
   rcsb_k_depth<<<grid, block, 0, b->stream>>>(b->m->d_model, b->m->d_faces, b->m->d_face_adr, b->m->d_face_num, b->d_frames, cam,
-                                             (unsigned short*)out_dev, b->n);
+                                             (unsigned short*)out_dev, (real*)cam_frames_dev, b->n);
   g_launches++;
   CUDA_OK(cudaGetLastError());
   return RCSB_OK;

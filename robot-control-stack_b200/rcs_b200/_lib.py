@@ -44,7 +44,7 @@ def lib():
     L.rcsb_model_set_mesh_vertices.argtypes = [vp, dp, C.c_int]
     L.rcsb_model_set_mesh_graph.argtypes = [vp, ip, C.c_int, ip, C.c_int]
     L.rcsb_model_set_mesh_faces.argtypes = [vp, dp, C.c_int, ip, ip, C.c_int]
-    L.rcsb_camera_depth.argtypes = [vp, C.c_int, dp, dp, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, vp]
+    L.rcsb_camera_depth.argtypes = [vp, C.c_int, dp, dp, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, vp, vp]
     L.rcsb_body_frames.argtypes = [vp, vp]
     L.rcsb_model_finalize.argtypes = [vp]
     L.rcsb_model_upload.argtypes = [vp, C.c_int]

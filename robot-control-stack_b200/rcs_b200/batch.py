@@ -172,15 +172,17 @@ class Batch:
         return out
 
     def camera_depth(self, cam_body: int, cam_pos, cam_rot, fovy_deg: float, width: int, height: int, znear: float, zfar: float,
-                     physical_units: bool, out: torch.Tensor | None = None) -> torch.Tensor:
-        """Depth frame of every environment for one camera (rcsb_camera_depth): [n, height, width] uint16."""
+                     physical_units: bool, out: torch.Tensor | None = None, cam_frames: torch.Tensor | None = None) -> torch.Tensor:
+        """Depth frame of every environment for one camera (rcsb_camera_depth): [n, height, width] uint16. cam_frames
+        ([n, 12] float64, optional) receives the camera's world frame of every environment."""
         if out is None:
             out = torch.empty((self.n, height, width), dtype=torch.uint16, device=self.dev)
         assert out.shape == (self.n, height, width) and out.dtype == torch.uint16 and out.is_contiguous()
         p = np.ascontiguousarray(cam_pos, dtype=np.float64)
         r = np.ascontiguousarray(cam_rot, dtype=np.float64).reshape(9)
         _lib.check(_lib.lib().rcsb_camera_depth(self.ptr, int(cam_body), _dp(p), _dp(r), float(fovy_deg), int(width), int(height),
-                                                float(znear), float(zfar), int(bool(physical_units)), out.data_ptr()))
+                                                float(znear), float(zfar), int(bool(physical_units)), out.data_ptr(),
+                                                cam_frames.data_ptr() if cam_frames is not None else None))
         return out
 
     def ik_inverse(self, pose: torch.Tensor, q0: torch.Tensor):

@@ -51,6 +51,7 @@ class SimCameraSet(BaseCameraSet):
         extent = float(M.get("stat_extent", 1.0))
         self._near, self._far = ZNEAR * extent, ZFAR * extent
         self._latest: FrameSet | None = None
+        self._flip = torch.tensor([1.0, -1.0, -1.0], dtype=torch.float64, device=simulation.batch.dev)
 
     # ---- reference surface
     def buffer_size(self) -> int:
@@ -81,28 +82,15 @@ class SimCameraSet(BaseCameraSet):
         fx = fy = 0.5 * cfg.resolution_height / np.tan(fovy * np.pi / 360)
         return np.array([[fx, 0, (cfg.resolution_width - 1) / 2, 0], [0, fy, (cfg.resolution_height - 1) / 2, 0], [0, 0, 1, 0]])
 
-    def _camera_world_frames(self, camera_name):
-        """[n, 3] positions and [n, 3, 3] rotations of the camera in the world, from the exported body frames."""
-        b = self._sim.batch
-        c = self._cams[camera_name]
-        n = b.n
-        pos = torch.as_tensor(c["pos"], device=b.dev).expand(n, 3)
-        rot = torch.as_tensor(c["rot"], device=b.dev).expand(n, 3, 3)
-        if c["body"] < 0:
-            return pos, rot
-        fr = b.body_frames()[:, c["body"]]  # [n, 12]
-        R = fr[:, 3:].reshape(n, 3, 3)
-        return fr[:, :3] + torch.einsum("nij,nj->ni", R, pos), torch.einsum("nij,njk->nik", R, rot)
-
-    def _extrinsics(self, camera_name) -> torch.Tensor:  # camera/sim.py:109-119: (cam * Rx(pi))^-1 as 4 x 4
-        p, R = self._camera_world_frames(camera_name)
-        flip = torch.tensor([[1.0, 0, 0], [0, -1, 0], [0, 0, -1]], dtype=torch.float64, device=p.device)
-        Rc = R @ flip
+    def _extrinsics(self, cam_frames: torch.Tensor) -> torch.Tensor:  # camera/sim.py:109-119: (cam * Rx(pi))^-1 as 4 x 4
+        """cam_frames [n, 12]: the camera's world frame of every environment, as the depth kernel wrote it."""
+        p, R = cam_frames[:, :3], cam_frames[:, 3:].reshape(-1, 3, 3)
+        Rc = R * self._flip                      # columns y and z negated: the pi rotation about x
         E = torch.zeros((p.shape[0], 4, 4), dtype=torch.float64, device=p.device)
         E[:, :3, :3] = Rc.transpose(1, 2)
         E[:, :3, 3] = -torch.einsum("nji,nj->ni", Rc, p)
         E[:, 3, 3] = 1
-        return E[0] if p.shape[0] == 1 and self._sim.num_envs == 1 else E
+        return E[0] if self._sim.num_envs == 1 else E
 
     def render(self) -> FrameSet:
         b = self._sim.batch
@@ -110,9 +98,10 @@ class SimCameraSet(BaseCameraSet):
         ts = b.time.clone()
         for name, cfg in self.cameras.items():
             c = self._cams[name]
+            cf = torch.empty((b.n, 12), dtype=torch.float64, device=b.dev)
             d = b.camera_depth(c["body"], c["pos"], c["rot"], c["fovy"], cfg.resolution_width, cfg.resolution_height, self._near,
-                               self._far, self.physical_units)
-            depth = DataFrame(data=d.unsqueeze(-1), timestamp=ts, intrinsics=self._intrinsics(name), extrinsics=self._extrinsics(name))
+                               self._far, self.physical_units, cam_frames=cf)
+            depth = DataFrame(data=d.unsqueeze(-1), timestamp=ts, intrinsics=self._intrinsics(name), extrinsics=self._extrinsics(cf))
             frames[name] = Frame(camera=CameraFrame(color=None, depth=depth), avg_timestamp=ts)
         self._latest = FrameSet(frames=frames, avg_timestamp=ts)
         return self._latest
