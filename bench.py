@@ -272,7 +272,10 @@ def measure(h, workload, n_per_gpu, K, W, sampler=None, want_e2e=True):
 
     def one_step(i):
         if i % EPISODE == 0:
-            env.reset()
+            if sharded or workload == "c3":
+                env.reset()
+            else:
+                env.reset_packed()  # the packed twin of reset(), as step_packed is of step()
         if sharded:  # consume the previous step's gathered observation, launch this one, leave its gather in flight
             if pending[0] is not None:
                 pending[0].rows()

@@ -563,14 +563,25 @@ RCSB_DEV void st_com(const Ctx& c) {
 RCSB_DEV void st_crb(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
   int nv = MD(nv);
-  // composite inertias: every body starts from its own inertia, children fold into parents from the leaves up
-  PFOR(e, MD(nb) * 10) { WR(crb)[e] = WR(cinert)[e]; }
-  RCSB_SYNC();
-  for (int b = MD(nb) - 1; b > 0; b--) {
-    const int p = m.b_parent[b];
-    if (p >= 0) PFOR1(k, 10) { WR(crb)[10 * p + k] += WR(crb)[10 * b + k]; }
-    RCSB_SYNC();
+  // composite inertias: every body sums the inertias of its subtree (descendant mask, leaves first) - one lane per
+  // (body, component), no serial leaf-to-root chain through shared memory
+  {
+    const int nb = MD(nb), n = nb * 10;
+#pragma unroll
+    for (int base = 0; base < n; base += RCSB_NLANES) {
+      const int e = base + c.lane, bmin = base / 10;
+      if (e < n) {
+        const int b = e / 10, k = e - 10 * b;
+        const unsigned mask = (unsigned)m.b_descmask[b];
+        real s = 0;
+#pragma unroll
+        for (int d = nb - 1; d >= bmin; d--)
+          if ((mask >> d) & 1u) s += WR(cinert)[10 * d + k];
+        WR(crb)[e] = s;
+      }
+    }
   }
+  RCSB_SYNC();
   real* buf = WR(crbbuf);
   PFOR(i, nv) { mul_inert_vec(buf + 6 * i, WR(crb) + 10 * m.d_body[i], WR(cdof) + 6 * i); }
   RCSB_SYNC();
@@ -598,13 +609,26 @@ RCSB_DEV void st_velocity(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
   const int nv = MD(nv), nb = MD(nb);
   const real* v = WR(v);
-  // pass A, root to leaves along the dof chain, one lane per component: spatial velocity accumulated up to and including
-  // every dof (a body's velocity is that of its last dof)
-  for (int j = 0; j < nv; j++) {
-    const int pj = m.d_parent[j];
-    PFOR1(k, 6) { WR(cvel)[6 * j + k] = (pj >= 0 ? WR(cvel)[6 * pj + k] : (real)0) + WR(cdof)[6 * j + k] * v[j]; }
-    RCSB_SYNC();
+  // pass A: spatial velocity accumulated up to and including every dof (a body's velocity is that of its last dof) -
+  // one lane per (dof, component) sums over the dof's ancestor mask in root-to-leaf order
+  {
+    const int n = nv * 6;
+#pragma unroll
+    for (int base = 0; base < n; base += RCSB_NLANES) {
+      const int e = base + c.lane;
+      const int jmax = (base + RCSB_NLANES - 1) / 6 < nv - 1 ? (base + RCSB_NLANES - 1) / 6 : nv - 1;
+      if (e < n) {
+        const int j = e / 6, k = e - 6 * j;
+        const unsigned mask = (unsigned)m.d_ancmask[j];
+        real s = 0;
+#pragma unroll
+        for (int a = 0; a <= jmax; a++)
+          if ((mask >> a) & 1u) s += WR(cdof)[6 * a + k] * v[a];
+        WR(cvel)[e] = s;
+      }
+    }
   }
+  RCSB_SYNC();
   // time derivative of every motion axis: (velocity accumulated before the dof) x axis
   PFOR(j, nv) {
     real* cdd = WR(cdofdot) + 6 * j;
@@ -616,14 +640,25 @@ RCSB_DEV void st_velocity(const Ctx& c) {
     }
   }
   RCSB_SYNC();
-  // pass B: spatial acceleration with qacc = 0 and gravity folded into the root
-  for (int j = 0; j < nv; j++) {
-    const int pj = m.d_parent[j];
-    PFOR1(k, 6) {
-      WR(cacc)[6 * j + k] = (pj >= 0 ? WR(cacc)[6 * pj + k] : (k >= 3 ? -m.gravity[k - 3] : (real)0)) + WR(cdofdot)[6 * j + k] * v[j];
+  // pass B: spatial acceleration with qacc = 0 and gravity folded into the root, same ancestor-mask sum
+  {
+    const int n = nv * 6;
+#pragma unroll
+    for (int base = 0; base < n; base += RCSB_NLANES) {
+      const int e = base + c.lane;
+      const int jmax = (base + RCSB_NLANES - 1) / 6 < nv - 1 ? (base + RCSB_NLANES - 1) / 6 : nv - 1;
+      if (e < n) {
+        const int j = e / 6, k = e - 6 * j;
+        const unsigned mask = (unsigned)m.d_ancmask[j];
+        real s = k >= 3 ? -m.gravity[k - 3] : (real)0;
+#pragma unroll
+        for (int a = 0; a <= jmax; a++)
+          if ((mask >> a) & 1u) s += WR(cdofdot)[6 * a + k] * v[a];
+        WR(cacc)[e] = s;
+      }
     }
-    RCSB_SYNC();
   }
+  RCSB_SYNC();
   PFOR(b, nb) {
     const int jl = m.b_lastdof[b];
     real Ia[6], Iv[6], x[6];

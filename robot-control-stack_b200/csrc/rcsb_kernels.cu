@@ -563,6 +563,12 @@ rcsb_batch* rcsb_batch_new(rcsb_model* m, int n_envs, void* sr, void* sd, void* 
   bool ok = shape(m->has_reduced ? m->hr : m->h, b->var, b->ws_bytes, b->warps, b->smem, b->grid);
   if (ok && m->has_reduced) ok = shape(m->h, b->var_full, b->ws_bytes_full, b->warps_full, b->smem_full, b->grid_full);
   if (!ok) { fail(RCSB_ERR_MODEL, "workspace does not fit in shared memory"); delete b; return nullptr; }
+  // Per-step alignment groups. A launch that gives every warp a single environment (one round) takes as long as its
+  // slowest CTA, and a CTA as long as the sum over the steps of its slowest warp: two groups that align separately shorten
+  // that (a straggler holds back 13 warps instead of 27; 0.737 -> 0.716 ms for 4096 x fr3_empty_world). With several
+  // rounds per warp the CTAs even out anyway and the second code region in the instruction cache costs more than it
+  // saves (5.77 -> 5.57 M env-steps/s at 16384), as it does for the generic kernel and for a dozen-warp CTA.
+  if (!getenv("RCSB_BAR_GROUPS")) b->bar_groups = (b->warps >= 24 && b->var.fixed && n_envs <= b->grid * b->warps) ? 2 : 1;
   const size_t smem_max = b->smem > b->smem_full ? b->smem : b->smem_full;  // both phases may use the same kernel
   if (ensure_smem(b->var.set_smem, smem_max) != cudaSuccess || (m->has_reduced && ensure_smem(b->var_full.set_smem, smem_max) != cudaSuccess) ||
       cudaFuncSetAttribute(rcsb_k_ik, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCSB_SMEM_HEADER) != cudaSuccess ||

@@ -78,6 +78,10 @@ RCSB_KERNEL(const RcsbModel* __restrict__ gm, const real* __restrict__ verts, co
       } else {
         for (int i = 0; i < nbar; i++) RCSB_GROUP_BARRIER();
       }
+#ifndef RCSB_HOST_EMU
+      // groups that align separately drift apart by up to a step per round; bring them back together between rounds
+      if (L.bar_groups > 1 && r + 1 < rounds) __syncthreads();
+#endif
     }
     return;
   }
