@@ -715,6 +715,14 @@ int rcsb_batch_run_host(rcsb_batch* b, unsigned ops, int k, int max_convergence_
   return RCSB_OK;
 }
 
+// device-side alias of a page-locked host buffer (cudaHostAlloc / cudaHostRegister / torch pin_memory), if it is one
+static bool mapped_host_pointer(const void* host, void** dev) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return false;
+  *dev = a.devicePointer;
+  return true;
+}
 int rcsb_env_step_host(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps, const double* act_host, double max_mov,
                        const double* jlow, const double* jhigh, double* obs_host) {
   if (sizeof(real) != sizeof(double)) return fail(RCSB_ERR_ARG, "host-buffer path requires a float64 build");
@@ -725,6 +733,23 @@ int rcsb_env_step_host(rcsb_batch* b, unsigned ops, int k, int max_convergence_s
   const int nj = b->m->h.rb_njoints, stride = nj + 1;
   // one copy in: the packed action block lands in the joint staging array ([n][MAXJ] reals are reserved, nj + 1 <= MAXJ + 1)
   if ((size_t)stride > (size_t)RCSB_MAXJ + 1) return fail(RCSB_ERR_ARG, "too many joints");
+  // Pinned (page-locked, device-mapped) buffers are read and written by the kernel itself: every warp fetches its own
+  // 64-byte action row over PCIe when it starts and posts its 240-byte observation row when it is done, so both
+  // transfers hide behind the other warps' physics and the two copy launches disappear. Pageable buffers take the
+  // staged copies below. RCSB_HOST_ZEROCOPY=0 forces the staged path.
+  {
+    static const bool zero_copy = !(getenv("RCSB_HOST_ZEROCOPY") && atoi(getenv("RCSB_HOST_ZEROCOPY")) == 0);
+    void *act_map = nullptr, *obs_map = nullptr;
+    if (zero_copy && mapped_host_pointer(act_host, &act_map) && mapped_host_pointer(obs_host, &obs_map)) {
+      b->act_jstride = stride; b->act_gstride = stride;
+      rc = rcsb_batch_run(b, ops | RCSB_OP_OBS, k, max_convergence_steps, act_map, (const real*)act_map + nj, nullptr, max_mov, jlow, jhigh,
+                          obs_map, nullptr);
+      b->act_jstride = 0; b->act_gstride = 0;
+      if (rc) return rc;
+      CUDA_OK(cudaStreamSynchronize(b->stream));
+      return RCSB_OK;
+    }
+  }
   CUDA_OK(cudaMemcpyAsync(b->d_act_packed, act_host, (size_t)b->n * stride * sizeof(real), cudaMemcpyHostToDevice, b->stream));
   b->act_jstride = stride; b->act_gstride = stride;
   rc = rcsb_batch_run(b, ops | RCSB_OP_OBS, k, max_convergence_steps, b->d_act_packed, b->d_act_packed + nj, nullptr, max_mov, jlow, jhigh,

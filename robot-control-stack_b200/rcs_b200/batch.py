@@ -158,11 +158,15 @@ class Batch:
                   obs_host: torch.Tensor):
         """env.step() through one packed pinned block each way (rcsb_env_step_host): act_host [n, njoints + 1],
         obs_host [n, obs_dim] (info flags in the last 8 columns)."""
-        lo = np.ascontiguousarray(jlow, dtype=np.float64) if jlow is not None else None
-        hi = np.ascontiguousarray(jhigh, dtype=np.float64) if jhigh is not None else None
+        key = (id(jlow), id(jhigh))
+        if getattr(self, "_host_limits_key", None) != key:  # the limits are the same arrays on every step of an env
+            lo = np.ascontiguousarray(jlow, dtype=np.float64) if jlow is not None else None
+            hi = np.ascontiguousarray(jhigh, dtype=np.float64) if jhigh is not None else None
+            self._host_limits = (lo, hi, _dp(lo) if lo is not None else None, _dp(hi) if hi is not None else None, jlow, jhigh)
+            self._host_limits_key = key
+        _, _, plo, phi, _, _ = self._host_limits
         _lib.check(_lib.lib().rcsb_env_step_host(self.ptr, ops, k, max_convergence_steps, act_host.data_ptr(), float(max_mov),
-                                                 _dp(lo) if lo is not None else None, _dp(hi) if hi is not None else None,
-                                                 obs_host.data_ptr()))
+                                                 plo, phi, obs_host.data_ptr()))
 
     def body_frames(self) -> torch.Tensor:
         """[n, nb, 12] world frames (position, row-major rotation) of the moving bodies at the current qpos."""

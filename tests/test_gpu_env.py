@@ -130,6 +130,30 @@ def test_batched_relative_joint_env_async():
     assert torch.equal(oh["joints"], env.sim.batch.qpos[:, :7].cpu())  # the host block is what the device state says
 
 
+def test_step_host_pinned_and_pageable_paths_agree():
+    """rcsb_env_step_host with page-locked buffers (the kernel reads the actions and writes the observation rows through
+    the mapped host pointers) and with pageable buffers (staged copies): bit-identical rows, equal to the device-resident
+    step_packed on the same actions."""
+    from rcs_b200.envs.base import ControlMode
+    N = 300
+    envs = [_mk(ControlMode.JOINTS, num_envs=N, gripper=True, max_rel=np.deg2rad(5), async_control=True) for _ in range(3)]
+    for e in envs:
+        e.reset()
+    g = torch.Generator().manual_seed(3)
+    for t in range(4):
+        a = torch.cat([(torch.rand((N, 7), dtype=torch.float64, generator=g) * 2 - 1) * np.deg2rad(5),
+                       torch.randint(0, 2, (N, 1), generator=g).to(torch.float64)], dim=1).contiguous()
+        pinned = envs[0].step_host(a.clone().pin_memory()).clone()
+        b1 = envs[1].sim.batch
+        ops, cfg = envs[1]._step_ops()
+        pageable = torch.zeros((N, 30), dtype=torch.float64)
+        assert not a.is_pinned() and not pageable.is_pinned()
+        b1.step_host(ops, envs[1]._substeps(), cfg.max_convergence_steps, a, float(envs[1].max_mov), envs[1].jlow, envs[1].jhigh, pageable)
+        dev = envs[2].step_packed({"joints": a[:, :7].cuda(), "gripper": a[:, 7].cuda()}).cpu()
+        assert torch.equal(pinned, pageable)
+        assert torch.equal(pinned, dev)
+
+
 @pytest.mark.parametrize("mode_name", ["CARTESIAN_TRPY", "CARTESIAN_TQuat"])
 def test_relative_cartesian_actions_match_reference_math(mode_name):
     """RelativeActionSpace (base.py:490-578, LAST_STEP) on the device: offset clipping (translation length, rotation
