@@ -148,7 +148,8 @@ __device__ __forceinline__ bool ray_geom(const RcsbModel& m, int g, const real* 
     real t0 = 0, t1 = tmax;
     for (int k = 0; k < 3; k++) {
       if (d[k] != 0) {
-        real ta = (-sz[k] - o[k]) / d[k], tb = (sz[k] - o[k]) / d[k];
+        const real inv = (real)1 / d[k];
+        real ta = (-sz[k] - o[k]) * inv, tb = (sz[k] - o[k]) * inv;
         if (ta > tb) { real s = ta; ta = tb; tb = s; }
         t0 = ta > t0 ? ta : t0; t1 = tb < t1 ? tb : t1;
       } else if (o[k] < -sz[k] || o[k] > sz[k]) t1 = -1;
@@ -181,34 +182,44 @@ __device__ __forceinline__ bool ray_geom(const RcsbModel& m, int g, const real* 
     }
     if (best < (real)1e299) t = best;
   } else if (type == RCSB_GEOM_MESH) {
-    real t0 = 0, t1 = tmax;
-    {  // the hull lies inside its local AABB: a slab test first (most rays that pass the bounding sphere miss the box)
+    {  // the hull lies inside its local AABB: a slab test first (most rays that pass the bounding sphere miss the box);
+       // one reciprocal per axis and a little slack - the test only has to be conservative, the planes decide alone
       const real* ab = m.g_aabb[g];
+      real t0 = 0, t1 = tmax;
       for (int k = 0; k < 3; k++) {
         if (d[k] != 0) {
-          real ta = (ab[k] - ab[3 + k] - o[k]) / d[k], tb = (ab[k] + ab[3 + k] - o[k]) / d[k];
+          const real inv = (real)1 / d[k];
+          real ta = (ab[k] - ab[3 + k] - o[k]) * inv, tb = (ab[k] + ab[3 + k] - o[k]) * inv;
           if (ta > tb) { real sw = ta; ta = tb; tb = sw; }
           t0 = ta > t0 ? ta : t0; t1 = tb < t1 ? tb : t1;
         } else if (o[k] < ab[k] - ab[3 + k] || o[k] > ab[k] + ab[3 + k]) t1 = -1;
       }
-      if (t0 > t1) return false;
-      t0 = 0; t1 = tmax;  // the planes decide alone: the result stays independent of the pre-test
+      if (t0 > t1 * (real)1.000000001 + (real)1e-12) return false;
     }
+    // Clip the ray against the hull's face planes. The entry / exit parameters are kept as fractions with positive
+    // denominators and compared by cross-multiplication: one division per geom instead of one per face.
+    real t0n = 0, t0d = 1, t1n = tmax, t1d = 1;
     const real* pl = faces + 4 * (size_t)face_adr[g];
     const int n = face_num[g];
-    for (int i = 0; i < n && t0 <= t1; i++) {
+    bool open = true;
+    for (int i = 0; i < n && open; i++) {
       const real nx = __ldg(pl + 4 * i), ny = __ldg(pl + 4 * i + 1), nz = __ldg(pl + 4 * i + 2), dd = __ldg(pl + 4 * i + 3);
       const real den = nx * d[0] + ny * d[1] + nz * d[2], num = -(nx * o[0] + ny * o[1] + nz * o[2] + dd);
-      if (den < 0) { const real tt = num / den; t0 = tt > t0 ? tt : t0; }
-      else if (den > 0) { const real tt = num / den; t1 = tt < t1 ? tt : t1; }
-      else if (num < 0) t1 = -1;
+      if (den < 0) { if (-num * t0d > t0n * -den) { t0n = -num; t0d = -den; } }   // entering: t = num / den
+      else if (den > 0) { if (num * t1d < t1n * den) { t1n = num; t1d = den; } }  // leaving
+      else if (num < 0) open = false;
+      open = open && t0n * t1d <= t1n * t0d;
     }
-    if (n > 0 && t0 <= t1) t = t0;
+    if (n > 0 && open) t = t0n / t0d;
   }
   if (t < 0 || t > tmax) return false;
   *t_out = t;
   return true;
 }
+// One block renders RCSB_CAM_CHUNK tiles of one environment's image: the geom frames and the camera frame are set up once
+// per block (a block per tile spent more time on that prologue than on its 256 rays), every warp culls the geoms of a few
+// tiles, then the block walks through its tiles without further barriers.
+#define RCSB_CAM_CHUNK 32
 __global__ void __launch_bounds__(RCSB_CAM_TILE * RCSB_CAM_TILE)
 rcsb_k_depth(const RcsbModel* __restrict__ gm, const real* __restrict__ faces, const int* __restrict__ face_adr,
              const int* __restrict__ face_num, const real* __restrict__ frames, RcsbCamera cam, unsigned short* __restrict__ out, real* __restrict__ cam_frames_out,
@@ -217,9 +228,11 @@ rcsb_k_depth(const RcsbModel* __restrict__ gm, const real* __restrict__ faces, c
   __shared__ real gfr[RCSB_MAXG][12];   // world frame of every geom: position, row-major rotation
   __shared__ real gbs[RCSB_MAXG][4];    // bounding sphere: centre, radius
   __shared__ real cfr[12];              // camera frame in the world
-  __shared__ unsigned tile_geoms;       // geoms whose bounding sphere can meet a ray of this tile (planes always)
+  __shared__ unsigned tile_geoms[RCSB_CAM_CHUNK];  // per tile: geoms whose bounding sphere can meet one of its rays (planes always)
   const int tiles_x = (cam.W + RCSB_CAM_TILE - 1) / RCSB_CAM_TILE, tiles_y = (cam.H + RCSB_CAM_TILE - 1) / RCSB_CAM_TILE;
-  const int env = blockIdx.x / (tiles_x * tiles_y), tile = blockIdx.x - env * tiles_x * tiles_y;
+  const int tiles = tiles_x * tiles_y, chunks = (tiles + RCSB_CAM_CHUNK - 1) / RCSB_CAM_CHUNK;
+  const int env = blockIdx.x / chunks, tile_lo = (blockIdx.x - env * chunks) * RCSB_CAM_CHUNK;
+  const int ntile = tiles - tile_lo < RCSB_CAM_CHUNK ? tiles - tile_lo : RCSB_CAM_CHUNK;
   const int tid = threadIdx.y * RCSB_CAM_TILE + threadIdx.x;
   const real* fr = frames + (size_t)env * m.nb * 12;
   if (tid < m.ng) {
@@ -241,16 +254,16 @@ rcsb_k_depth(const RcsbModel* __restrict__ gm, const real* __restrict__ faces, c
       cfr[r] = p[r] + R[3 * r] * cam.pos[0] + R[3 * r + 1] * cam.pos[1] + R[3 * r + 2] * cam.pos[2];
       for (int k = 0; k < 3; k++) cfr[3 + 3 * r + k] = R[3 * r] * cam.rot[k] + R[3 * r + 1] * cam.rot[3 + k] + R[3 * r + 2] * cam.rot[6 + k];
     }
-    if (cam_frames_out && tile == 0)  // the camera's world frame of this environment (extrinsics), written once
+    if (cam_frames_out && tile_lo == 0)  // the camera's world frame of this environment (extrinsics), written once
       for (int i = 0; i < 12; i++) cam_frames_out[(size_t)env * 12 + i] = cfr[i];
   }
   __syncthreads();
-  if (tid < 32) {
-    // Tile culling: the tile's rays lie in a cone about its centre ray (half-angle alpha, from the farthest corner); a
-    // sphere of radius r at distance dist subtends asin(r / dist). Geom g can only be hit if the angle between the centre
-    // ray and the sphere centre is at most alpha + beta (tested through cosines, with a little slack: the test is
-    // conservative, so culling never changes a pixel).
-    const int g = tid;
+  // Tile culling, one warp per tile and one lane per geom: the tile's rays lie in a cone about its centre ray (half-angle
+  // alpha, from the farthest corner); a sphere of radius r at distance dist subtends asin(r / dist). Geom g can only be
+  // hit if the angle between the centre ray and the sphere centre is at most alpha + beta (tested through cosines, with
+  // a little slack: the test is conservative, so culling never changes a pixel).
+  for (int i = tid >> 5; i < ntile; i += (RCSB_CAM_TILE * RCSB_CAM_TILE) >> 5) {
+    const int tile = tile_lo + i, g = tid & 31;
     int keep = 0;
     if (g < m.ng) {
       const real u0 = (tile % tiles_x) * RCSB_CAM_TILE, v0 = (tile / tiles_x) * RCSB_CAM_TILE;
@@ -282,41 +295,45 @@ rcsb_k_depth(const RcsbModel* __restrict__ gm, const real* __restrict__ faces, c
       }
     }
     const unsigned mask = __ballot_sync(0xffffffffu, keep);
-    if (tid == 0) tile_geoms = mask;
+    if ((tid & 31) == 0) tile_geoms[i] = mask;
   }
   __syncthreads();
-  const int u = (tile % tiles_x) * RCSB_CAM_TILE + threadIdx.x, v = (tile / tiles_x) * RCSB_CAM_TILE + threadIdx.y;
-  if (u >= cam.W || v >= cam.H) return;
-  // pixel centre -> ray in the camera frame (x right, y up, looking along -z), scaled so that t is the eye-space depth
-  const real dc[3] = {(u + (real)0.5 - (real)0.5 * cam.W) / cam.f, -(v + (real)0.5 - (real)0.5 * cam.H) / cam.f, (real)-1};
-  real dw[3], ow[3] = {cfr[0], cfr[1], cfr[2]};
-  for (int r = 0; r < 3; r++) dw[r] = cfr[3 + 3 * r] * dc[0] + cfr[3 + 3 * r + 1] * dc[1] + cfr[3 + 3 * r + 2] * dc[2];
-  const real dlen2 = dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2], inv_dlen2 = (real)1 / dlen2;
-  real tbest = cam.zfar;
-  for (unsigned rest = tile_geoms; rest; rest &= rest - 1) {
-    const int g = __ffs(rest) - 1;
-    if (m.g_type[g] != RCSB_GEOM_PLANE) {  // bounding sphere: closest approach of the ray to the centre
-      const real cx = gbs[g][0] - ow[0], cy = gbs[g][1] - ow[1], cz = gbs[g][2] - ow[2];
-      const real tc = (cx * dw[0] + cy * dw[1] + cz * dw[2]) * inv_dlen2;
-      const real ex = cx - tc * dw[0], ey = cy - tc * dw[1], ez = cz - tc * dw[2], rr = gbs[g][3];
-      if (ex * ex + ey * ey + ez * ez > rr * rr) continue;
-      if ((tc - tbest) * (tc - tbest) * dlen2 > rr * rr && tc > tbest) continue;  // entirely behind the best hit
+  const real ow[3] = {cfr[0], cfr[1], cfr[2]};
+  for (int i = 0; i < ntile; i++) {
+    const int tile = tile_lo + i;
+    const int u = (tile % tiles_x) * RCSB_CAM_TILE + threadIdx.x, v = (tile / tiles_x) * RCSB_CAM_TILE + threadIdx.y;
+    if (u >= cam.W || v >= cam.H) continue;
+    // pixel centre -> ray in the camera frame (x right, y up, looking along -z), scaled so that t is the eye-space depth
+    const real dc[3] = {(u + (real)0.5 - (real)0.5 * cam.W) / cam.f, -(v + (real)0.5 - (real)0.5 * cam.H) / cam.f, (real)-1};
+    real dw[3];
+    for (int r = 0; r < 3; r++) dw[r] = cfr[3 + 3 * r] * dc[0] + cfr[3 + 3 * r + 1] * dc[1] + cfr[3 + 3 * r + 2] * dc[2];
+    const real dlen2 = dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2], inv_dlen2 = (real)1 / dlen2;
+    real tbest = cam.zfar;
+    for (unsigned rest = tile_geoms[i]; rest; rest &= rest - 1) {
+      const int g = __ffs(rest) - 1;
+      if (m.g_type[g] != RCSB_GEOM_PLANE) {  // bounding sphere: closest approach of the ray to the centre
+        const real cx = gbs[g][0] - ow[0], cy = gbs[g][1] - ow[1], cz = gbs[g][2] - ow[2];
+        const real tc = (cx * dw[0] + cy * dw[1] + cz * dw[2]) * inv_dlen2;
+        const real ex = cx - tc * dw[0], ey = cy - tc * dw[1], ez = cz - tc * dw[2], rr = gbs[g][3];
+        if (ex * ex + ey * ey + ez * ez > rr * rr) continue;
+        if ((tc - tbest) * (tc - tbest) * dlen2 > rr * rr && tc > tbest) continue;  // entirely behind the best hit
+      }
+      real og[3], dg[3], rel[3] = {ow[0] - gfr[g][0], ow[1] - gfr[g][1], ow[2] - gfr[g][2]};
+      const real* R = &gfr[g][3];
+      for (int k = 0; k < 3; k++) {
+        og[k] = R[k] * rel[0] + R[3 + k] * rel[1] + R[6 + k] * rel[2];
+        dg[k] = R[k] * dw[0] + R[3 + k] * dw[1] + R[6 + k] * dw[2];
+      }
+      real t;
+      if (ray_geom(m, g, faces, face_adr, face_num, og, dg, tbest, &t) && t < tbest) tbest = t;
     }
-    real og[3], dg[3], rel[3] = {ow[0] - gfr[g][0], ow[1] - gfr[g][1], ow[2] - gfr[g][2]};
-    const real* R = &gfr[g][3];
-    for (int k = 0; k < 3; k++) {
-      og[k] = R[k] * rel[0] + R[3 + k] * rel[1] + R[6 + k] * rel[2];
-      dg[k] = R[k] * dw[0] + R[3 + k] * dw[1] + R[6 + k] * dw[2];
-    }
-    real t;
-    if (ray_geom(m, g, faces, face_adr, face_num, og, dg, tbest, &t) && t < tbest) tbest = t;
+    real z = tbest < cam.znear ? cam.znear : tbest;  // eye-space depth, clipped like the view frustum
+    real val;
+    if (cam.physical_units) val = z * (real)1000;                               // camera/sim.py:65-72 then x DEPTH_SCALE
+    else val = (1 - cam.znear / z) / (1 - cam.znear / cam.zfar) * (real)1000;   // window-space depth x DEPTH_SCALE
+    val = val < 0 ? (real)0 : (val > (real)65535 ? (real)65535 : val);
+    out[((size_t)env * cam.H + v) * cam.W + u] = (unsigned short)val;           // astype(np.uint16): truncation
   }
-  real z = tbest < cam.znear ? cam.znear : tbest;  // eye-space depth, clipped like the view frustum
-  real val;
-  if (cam.physical_units) val = z * (real)1000;                               // camera/sim.py:65-72 then x DEPTH_SCALE
-  else val = (1 - cam.znear / z) / (1 - cam.znear / cam.zfar) * (real)1000;   // window-space depth x DEPTH_SCALE
-  val = val < 0 ? (real)0 : (val > (real)65535 ? (real)65535 : val);
-  out[((size_t)env * cam.H + v) * cam.W + u] = (unsigned short)val;           // astype(np.uint16): truncation
 }
 #undef MD
 #undef LAY
@@ -787,8 +804,9 @@ int rcsb_camera_depth(rcsb_batch* b, int cam_body, const double* cam_pos, const 
   cam.f = (real)(0.5 * height / tan(fovy_deg * 3.14159265358979323846 / 360.0));
   cam.W = width; cam.H = height; cam.znear = (real)znear; cam.zfar = (real)zfar; cam.physical_units = physical_units != 0;
   const long long tiles = (long long)((width + RCSB_CAM_TILE - 1) / RCSB_CAM_TILE) * ((height + RCSB_CAM_TILE - 1) / RCSB_CAM_TILE);
-  if (tiles * b->n > 0x7fffffffLL) return fail(RCSB_ERR_ARG, "image too large for one launch");
-  dim3 block(RCSB_CAM_TILE, RCSB_CAM_TILE), grid((unsigned)(tiles * b->n));
+  const long long chunks = (tiles + RCSB_CAM_CHUNK - 1) / RCSB_CAM_CHUNK;  // blocks per environment
+  if (chunks * b->n > 0x7fffffffLL) return fail(RCSB_ERR_ARG, "image too large for one launch");
+  dim3 block(RCSB_CAM_TILE, RCSB_CAM_TILE), grid((unsigned)(chunks * b->n));
   rcsb_k_depth<<<grid, block, 0, b->stream>>>(b->m->d_model, b->m->d_faces, b->m->d_face_adr, b->m->d_face_num, b->d_frames, cam,
                                              (unsigned short*)out_dev, (real*)cam_frames_dev, b->n);
   g_launches++;

@@ -29,7 +29,8 @@ def test_oracle_depth_conventions_closed_form():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("scene,cam,res", [("fr3_simple_pick_up", "bird_eye_cam", (96, 64)), ("fr3_simple_pick_up", "wrist_0", (64, 64)),
-                                           ("fr3_simple_pick_up", "side_view", (80, 60)), ("fr3_empty_world", "wrist_0", (48, 48))])
+                                           ("fr3_simple_pick_up", "side_view", (80, 60)), ("fr3_empty_world", "wrist_0", (48, 48)),
+                                           ("fr3_simple_pick_up", "bird_eye_cam", (136, 100))])  # 63 tiles: two blocks per image, ragged edges
 def test_depth_kernel_matches_oracle(scene, cam, res):
     import rcs_b200
     from rcs_b200 import sim
