@@ -739,7 +739,6 @@ RCSB_DEV void support(const Ctx& c, int g, const real* gp, const real* gR, const
     if (n > RCSB_MINVAL) { v[0] = dl[0] / n * m.g_size[g][0]; v[1] = dl[1] / n * m.g_size[g][0]; }
     v[2] = dl[2] > 0 ? m.g_size[g][1] : (dl[2] < 0 ? -m.g_size[g][1] : (real)0);
   }
-  // out may be shared by the warp (MPR portal): every lane stores the same finished value, never a read-modify-write
   real o[3];
   mulmat3(o, gR, v);
   out[0] = o[0] + gp[0]; out[1] = o[1] + gp[1]; out[2] = o[2] + gp[2];
@@ -779,10 +778,12 @@ RCSB_DEV void pair_frames(const Ctx& c, PairFrames& pf) {
 }
 RCSB_DEV void mink_support(const Ctx& c, const PairFrames& pf, const real* dir, Sup& s) {
   real nd[3] = {-dir[0], -dir[1], -dir[2]};
+  real a[3], b[3];
+  support(c, pf.g1, pf.p1, pf.R1, dir, a);
+  support(c, pf.g2, pf.p2, pf.R2, nd, b);
   RCSB_SYNC();  // s is shared by the warp: no lane may still be reading the record this call overwrites
-  support(c, pf.g1, pf.p1, pf.R1, dir, s.v1);
-  support(c, pf.g2, pf.p2, pf.R2, nd, s.v2);
-  s.v[0] = s.v1[0] - s.v2[0]; s.v[1] = s.v1[1] - s.v2[1]; s.v[2] = s.v1[2] - s.v2[2];
+  // every lane holds the same finished values in registers and stores them: writes only, nothing is read back here
+  for (int k = 0; k < 3; k++) { s.v1[k] = a[k]; s.v2[k] = b[k]; s.v[k] = a[k] - b[k]; }
 }
 RCSB_DEV real origin_tri_dist(const real* A, const real* B, const real* C, real* w) {
   // closest point of triangle ABC to the origin (Ericson, Real-Time Collision Detection 5.1.5)
