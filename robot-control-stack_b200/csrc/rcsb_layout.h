@@ -258,6 +258,19 @@ static inline int rcsb_model_finalize_layout(RcsbModel* m) {
       m->d_tree_hi[j] = ok ? hi[r] : m->nv;
     }
   }
+  {  // trees whose dofs carry no velocity-dependent force: build_integrator_matrix leaves their block of M as it is
+    int plain = (1 << m->nroot) - 1;
+    for (int j = 0; j < m->nv; j++) {
+      int vel = m->d_damping[j] != 0 || (m->implicitfast && m->d_kvdiag[j] != 0);
+      if (m->implicitfast)
+        for (int sa = 0; sa < m->n_special; sa++) {
+          const int a = m->a_special[sa];
+          if (m->a_bias[a][2] != 0 && m->a_moment[a][j] != 0) vel = 1;
+        }
+      if (vel) plain &= ~(1 << m->b_root[m->d_body[j]]);
+    }
+    m->root_plain = plain;
+  }
   for (int i = 0, t = 0; i < RCSB_MAXV; i++)
     for (int j = 0; j <= i; j++, t++) { m->tri_i[t] = (uint8_t)i; m->tri_j[t] = (uint8_t)j; }
   return 0;

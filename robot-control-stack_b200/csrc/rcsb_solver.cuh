@@ -103,7 +103,23 @@ RCSB_DEV void st_make_constraint(const Ctx& c) {
       if (b1 >= 0 && b2 >= 0 && m.b_root[b1] != m.b_root[b2]) coupled = 1;
     }
   }
-  if (c.lane == 0) { WI(misc)[MI_NEFC] = nefc; WI(misc)[MI_NE] = ne; WI(misc)[MI_NF] = nf; WI(misc)[MI_NL] = nl; WI(misc)[MI_COUPLED] = coupled; }
+  // kinematic trees touched by the rows the noslip pass works on (bits 8.. of the same slot; all of them when there are
+  // friction-loss rows)
+  unsigned nsroots = 0;
+  if (MD(noslip_iterations) > 0 && MD(nroot) > 1) {
+    if (nf > 0) nsroots = 0xffu;
+    for (int ci = 0; ci < ncon; ci++) {
+      const int* cii = WI(con) + RCSB_CI_INTS * ci;
+      if (cii[RCSB_CI_EFC] < 0 || cii[RCSB_CI_DIM] < 3) continue;
+      const int b1 = m.g_body[cii[RCSB_CI_G0]], b2 = m.g_body[cii[RCSB_CI_G1]];
+      if (b1 >= 0) nsroots |= 1u << m.b_root[b1];
+      if (b2 >= 0) nsroots |= 1u << m.b_root[b2];
+    }
+  }
+  if (c.lane == 0) {
+    WI(misc)[MI_NEFC] = nefc; WI(misc)[MI_NE] = ne; WI(misc)[MI_NF] = nf; WI(misc)[MI_NL] = nl;
+    WI(misc)[MI_COUPLED] = coupled | (int)(nsroots << 8);
+  }
   RCSB_SYNC();
   // ---- Jacobian
   PFOR(e, nefc * nv) {
@@ -507,7 +523,11 @@ RCSB_DEV void row_dof_range(const Ctx& c, const real* row, int* lo_out, int* hi_
   *lo_out = lo; *hi_out = hi;
 }
 // ------------------------------------------------------------------ noslip post-pass
-RCSB_DEV_NOINLINE void solve_noslip(const Ctx& c, int nefc, int ncon) {
+// roots == 0: o_L holds M's factor and qacc_smooth is up to date. roots != 0 (bit r = kinematic tree r): o_L holds the
+// integrator matrix's factor, whose blocks of the trees in `roots` are M's own; every friction row lies inside those trees,
+// so only their dofs are read and written (the other trees keep the acceleration the solver gave them: their constraint
+// forces do not change).
+RCSB_DEV_NOINLINE void solve_noslip(const Ctx& c, int nefc, int ncon, unsigned roots) {
   const RcsbModel& m = CMODEL(c);
   const int nv = MD(nv);
   int ne = WI(misc)[MI_NE], nf = WI(misc)[MI_NF];
@@ -515,6 +535,10 @@ RCSB_DEV_NOINLINE void solve_noslip(const Ctx& c, int nefc, int ncon) {
   for (int ci = 0; ci < ncon; ci++)
     if (WI(con)[RCSB_CI_INTS * ci + RCSB_CI_EFC] >= 0 && WI(con)[RCSB_CI_INTS * ci + RCSB_CI_DIM] >= 3) any = 1;
   if (!any) return;
+  if (roots) {  // qacc_smooth of the touched trees (the entries of the other trees are not M^-1 qfrc_smooth: never read)
+    PFOR(k, nv) { WR(qacc_smooth)[k] = WR(smooth)[k]; }
+    chol_solve_blocks(c, WR(L), WR(L) + nv * nv, nv, WR(qacc_smooth), WR(tmp));
+  }
   // unregularised residual offsets b = J*qacc_smooth - aref
   PFOR(r, nefc) {
     real s = 0;
@@ -616,6 +640,13 @@ RCSB_DEV_NOINLINE void solve_noslip(const Ctx& c, int nefc, int ncon) {
     }
     if (improvement * scale < m.noslip_tolerance) break;
   }
+  if (roots) {
+    PFOR(k, nv) { WR(search)[k] = WR(qfc)[k]; }
+    chol_solve_blocks(c, WR(L), WR(L) + nv * nv, nv, WR(search), WR(tmp));
+    PFOR(k, nv) { if ((roots >> m.b_root[m.d_body[k]]) & 1u) WR(qacc)[k] = WR(search)[k] + WR(qacc_smooth)[k]; }
+    RCSB_SYNC();
+    return;
+  }
   PFOR(k, nv) { WR(qacc)[k] = WR(qfc)[k]; }
   chol_solve_blocks(c, WR(L), WR(L) + nv * nv, nv, WR(qacc), WR(tmp));
   PFOR(k, nv) { WR(qacc)[k] += WR(qacc_smooth)[k]; }
@@ -662,7 +693,7 @@ RCSB_DEV_NOINLINE void newton_solve(const Ctx& c, int nefc, int ncon) {
       WR(H)[b * nv + a] = h;
     }
     PFOR(k, nv) { WR(search)[k] = WR(grad)[k]; }
-    chol_factor_solve(c, WR(H), WR(H) + nv * nv, nv, WR(search), WR(tmp), nullptr, nullptr, !WI(misc)[MI_COUPLED]);
+    chol_factor_solve(c, WR(H), WR(H) + nv * nv, nv, WR(search), WR(tmp), nullptr, nullptr, !(WI(misc)[MI_COUPLED] & 1));
     PFOR(k, nv) { WR(search)[k] = -WR(search)[k]; }
     RCSB_SYNC();
     real qG1 = 0, qG2 = 0, sn = 0;
@@ -705,7 +736,7 @@ RCSB_DEV_NOINLINE void newton_solve(const Ctx& c, int nefc, int ncon) {
   compute_qfc(c, nefc);
   PFOR(k, nv) { WR(warm)[k] = WR(qacc)[k]; }  // mj_fwdConstraint saves the warm start before the noslip post-pass
   RCSB_SYNC();
-  if (MD(noslip_iterations) > 0) solve_noslip(c, nefc, ncon);
+  if (MD(noslip_iterations) > 0) solve_noslip(c, nefc, ncon, 0);
 }
 
 // ------------------------------------------------------------------ constrained acceleration (Newton)
@@ -753,6 +784,11 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
     RCSB_SYNC();
     // noslip needs M's own factor in o_L afterwards, so the integrator matrix is not factored alongside then
     const int need_noslip = MD(noslip_iterations) > 0 && (WI(misc)[MI_NF] > 0 || ncon > 0);
+    // The noslip rows only touch kinematic trees whose block of the integrator's matrix IS M's block (a free object: no
+    // damping, no actuator) and no row couples two trees: the noslip pass then works on those blocks of the integrator's
+    // factor and M is never factored on its own (one factorisation less per step; the resting-cube steps of pick-up).
+    const unsigned nsroots = (unsigned)WI(misc)[MI_COUPLED] >> 8;
+    const int ns_plain = need_noslip && MD(nroot) > 1 && !(WI(misc)[MI_COUPLED] & 1) && nsroots != 0 && (nsroots & ~(unsigned)m.root_plain) == 0;
     int verified = 0, attempt = 0;
     for (; attempt < 3 && !verified; attempt++) {
       PFOR(t, nv * (nv + 1) / 2) {
@@ -775,10 +811,10 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
       }
       // the integrator's matrix does not depend on the constraint forces: on the first pass it is factored in the
       // idle half of the warp (o_L is free here: M's own factor is only needed by the Newton / noslip path)
-      const int dual = attempt == 0 && nv <= 16 && !WI(misc)[MI_HAVE_L] && !need_noslip;
+      const int dual = attempt == 0 && nv <= 16 && !WI(misc)[MI_HAVE_L] && (!need_noslip || ns_plain);
       if (dual) build_integrator_matrix(c, WR(L));
       chol_factor_solve(c, WR(H), WR(H) + nv * nv, nv, WR(qacc), WR(tmp), dual ? WR(L) : nullptr, dual ? WR(L) + nv * nv : nullptr,
-                        !WI(misc)[MI_COUPLED]);
+                        !(WI(misc)[MI_COUPLED] & 1));
       if (dual && c.lane == 0) WI(misc)[MI_HAVE_H2] = 1;
       int changed = 0, on_cone = 0;
       PFOR(r, nefc) {
@@ -838,8 +874,12 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
       PFOR(k, nv) { WR(warm)[k] = WR(qacc)[k]; }  // saved before noslip, as mj_fwdConstraint does
       RCSB_SYNC();
       if (need_noslip) {  // the post-pass works on M's own factor and the unconstrained acceleration
-        compute_qacc_smooth(c);
-        solve_noslip(c, nefc, ncon);
+        if (ns_plain && WI(misc)[MI_HAVE_H2]) {
+          solve_noslip(c, nefc, ncon, nsroots);
+        } else {
+          compute_qacc_smooth(c);
+          solve_noslip(c, nefc, ncon, 0);
+        }
       }
       return;
     }

@@ -95,6 +95,7 @@ struct RcsbModel {
   // ---- sizes / options
   int nq, nv, nu, nb, ng, npair, nt, neq, nroot, nmeshvert;
   int nfl;  // dofs with frictionloss > 0, derived in rcsb_model_finalize_layout
+  int root_plain;  // bit r: the implicit integrator's matrix block of kinematic tree r is M's own block (no damping, no velocity-dependent actuator on its dofs); derived
   int cone_elliptic, implicitfast, iterations, ls_iterations, noslip_iterations;
   int maxcon, maxefc;  // per-env capacities of the contact / constraint workspaces
   // Two workspace layouts share one kernel: the full-capacity one above and a reduced one (fast_maxcon / fast_maxefc,
