@@ -59,7 +59,9 @@ RCSB_DECLARE_VARIANT(rcsb_xarm7_tabletop)
 typedef void (*rcsb_launch_fn)(int, int, size_t, cudaStream_t, const RcsbModel*, const real*, const int*, real*, double*, int*,
                                const RcsbLaunch&, int*, size_t);
 typedef cudaError_t (*rcsb_smem_fn)(size_t);
-struct RcsbVariant { const char* name; int fixed; RcsbShape shape; rcsb_launch_fn launch; rcsb_smem_fn set_smem; int max_warps; };
+// lockstep: where the warps of a CTA re-align inside a physics step (bit i = before stage i, bit 9 = at its end; rcsb_warp.cuh),
+// measured per kernel: after the collision stage for the FR3 kernels, at the step's end for the tabletop kernel (+12 %)
+struct RcsbVariant { const char* name; int fixed; RcsbShape shape; rcsb_launch_fn launch; rcsb_smem_fn set_smem; int max_warps; int lockstep; };
 static bool shape_equal(const RcsbShape& a, const RcsbShape& b) { return memcmp(&a, &b, sizeof(RcsbShape)) == 0; }
 // the most specialised variant compiled for this model's shape (the generic one always matches)
 static RcsbVariant pick_variant(const RcsbModel& h) {
@@ -67,13 +69,13 @@ static RcsbVariant pick_variant(const RcsbModel& h) {
   const char* force = getenv("RCSB_VARIANT");  // "generic" disables the fixed-shape kernels (testing / tuning)
   if (!(force && !strcmp(force, "generic"))) {
 #ifndef RCSB_NO_FIXED_VARIANTS
-    if (shape_equal(s, rcsb_fr3_reduced::shape())) return {"fr3_reduced", 1, s, rcsb_fr3_reduced::launch, rcsb_fr3_reduced::set_smem, rcsb_fr3_reduced::max_warps()};
-    if (shape_equal(s, rcsb_fr3_full::shape())) return {"fr3_full", 1, s, rcsb_fr3_full::launch, rcsb_fr3_full::set_smem, rcsb_fr3_full::max_warps()};
-    if (shape_equal(s, rcsb_fr3_pickup::shape())) return {"fr3_pickup", 1, s, rcsb_fr3_pickup::launch, rcsb_fr3_pickup::set_smem, rcsb_fr3_pickup::max_warps()};
-    if (shape_equal(s, rcsb_xarm7_tabletop::shape())) return {"xarm7_tabletop", 1, s, rcsb_xarm7_tabletop::launch, rcsb_xarm7_tabletop::set_smem, rcsb_xarm7_tabletop::max_warps()};
+    if (shape_equal(s, rcsb_fr3_reduced::shape())) return {"fr3_reduced", 1, s, rcsb_fr3_reduced::launch, rcsb_fr3_reduced::set_smem, rcsb_fr3_reduced::max_warps(), 0x010};
+    if (shape_equal(s, rcsb_fr3_full::shape())) return {"fr3_full", 1, s, rcsb_fr3_full::launch, rcsb_fr3_full::set_smem, rcsb_fr3_full::max_warps(), 0x010};
+    if (shape_equal(s, rcsb_fr3_pickup::shape())) return {"fr3_pickup", 1, s, rcsb_fr3_pickup::launch, rcsb_fr3_pickup::set_smem, rcsb_fr3_pickup::max_warps(), 0x010};
+    if (shape_equal(s, rcsb_xarm7_tabletop::shape())) return {"xarm7_tabletop", 1, s, rcsb_xarm7_tabletop::launch, rcsb_xarm7_tabletop::set_smem, rcsb_xarm7_tabletop::max_warps(), 0x200};
 #endif
   }
-  return {"generic", 0, s, rcsb_generic::launch, rcsb_generic::set_smem, rcsb_generic::max_warps()};
+  return {"generic", 0, s, rcsb_generic::launch, rcsb_generic::set_smem, rcsb_generic::max_warps(), 0x010};
 }
 
 // IK kernel: one environment per thread
@@ -565,6 +567,7 @@ rcsb_batch* rcsb_batch_new(rcsb_model* m, int n_envs, void* sr, void* sd, void* 
   }
   b->var = pick_variant(m->has_reduced ? m->hr : m->h);
   b->var_full = pick_variant(m->h);
+  if (!getenv("RCSB_LOCKSTEP")) b->lockstep = b->var.lockstep;
   auto shape = [&](const RcsbModel& h, const RcsbVariant& var, size_t& ws, int& warps, size_t& smem, int& grid) {
     ws = rcsb_ws_bytes(&h);
     warps = (int)((avail - RCSB_SMEM_HEADER) / ws);

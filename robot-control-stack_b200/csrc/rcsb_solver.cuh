@@ -899,6 +899,8 @@ RCSB_DEV void build_integrator_matrix(const Ctx& c, real* dst) {
     if (MD(implicitfast)) {
       for (int sa = 0; sa < m.n_special; sa++) {
         int a = m.a_special[sa];
+        // a joint transmission has one non-zero moment entry: it only reaches the diagonal entry of its own dof
+        if (m.a_trntype[a] == RCSB_TRN_JOINT && (i != j || m.a_trnid[a] != i)) continue;
         real bv = m.a_bias[a][2];
         if (bv == 0) continue;
         real fa = WR(aforce)[a];
