@@ -98,7 +98,11 @@ int rcsb_batch_run_host(rcsb_batch* b, unsigned ops, int k, int max_convergence_
 /* One env.step() of every environment through ONE packed host block each way: act_host [n_envs][njoints + 1] (joint
  * action, then the gripper action; pinned) -> H2D, the fused launch (`ops` as for rcsb_batch_run, RCSB_RUN_OBS implied),
  * D2H of obs_host [n_envs][obs_dim] -- the observation row carries the info flags as reals in its last 8 columns --
- * and a stream synchronise. Replaces the host round trip of SimEnvCreator's env.step (python/rcs/envs/sim.py:49-66). */
+ * and a stream synchronise. Replaces the host round trip of SimEnvCreator's env.step (python/rcs/envs/sim.py:49-66).
+ * Page-locked buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are not copied: the kernel reads the action rows
+ * and writes the observation rows through their device-mapped pointers, so the transfers overlap the physics (the device
+ * copy of the observation block is then NOT updated); pageable buffers take staged copies. Same results either way.
+ * RCSB_HOST_ZEROCOPY=0 in the environment forces the staged copies. */
 int rcsb_env_step_host(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps, const double* act_host, double max_mov,
                        const double* jlow, const double* jhigh, double* obs_host);
 
