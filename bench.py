@@ -50,13 +50,24 @@ def bytes_per_env_step(scene, substeps=SUBSTEPS):
 
 def profiled_traffic():
     """DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
-    for tag in ("r02", "r01"):
+    for tag in ("r02_ncu", "r01"):  # tools/export_profiles.sh writes <round>_ncu_traffic.json for the headline kernel
         try:
             with open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json")) as f:
                 return json.load(f)
         except Exception:
             continue
     return None
+
+
+def profiled_sub(tag):
+    """DRAM bytes per launch of another profiled kernel (profiles/r02_<tag>_ncu_traffic.json: c3, c4, depth), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", f"r02_{tag}_ncu_traffic.json")) as f:
+            t = json.load(f)
+        return {"bytes": t["dram_bytes_read"] + t["dram_bytes_write"], "ipc_active": t.get("ipc_active"), "source": t.get("source"),
+                "note": "captured at 4096 environments per launch"}
+    except Exception:
+        return None
 
 
 def measured_peak():
@@ -327,6 +338,8 @@ def measure(h, workload, n_per_gpu, K, W, sampler=None, want_e2e=True):
     achieved = value / h.world * bpe / 1e9  # per GPU: algorithmic bytes per env.step x env.steps per second per GPU
     rec["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                        "algorithmic_bytes_per_env_step": bpe, "peak_source": peak_src, "traffic": None}
+    if workload in ("c3", "c4"):
+        rec["roofline"]["ncu"] = profiled_sub(workload)
     # ---- end to end through host buffers: env.step_host (JOINTS control with a gripper)
     if want_e2e and workload in ("c2", "c2_sync"):
         act_cpu = torch.cat([aj, ag.unsqueeze(-1)], dim=-1).cpu()
@@ -387,9 +400,10 @@ def measure_depth(h, n_per_gpu, width=128, height=128, K=10, W=3):
            "value": h.world * n_per_gpu / (t * 1e-3), "unit": "depth frames/s", "ms_per_step": t,
            "roofline": {"bound": "hbm", "achieved": nbytes / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": nbytes / (t * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
-                        "traffic": None,
+                        "traffic": (profiled_sub("depth") or {}).get("bytes") if (n_per_gpu, width, height) == (4096, 128, 128) else None,
+                        "ncu": profiled_sub("depth"),
                         "note": "frames export launch + ray-cast launch; bytes = uint16 pixels written. Compute bound in practice "
-                                "(every ray is tested against up to 25 geoms / hundreds of hull planes in float64)"}}
+                                "(every ray is tested against the tile's surviving geoms / hundreds of hull planes in float64)"}}
     del env
     torch.cuda.empty_cache()
     return rec

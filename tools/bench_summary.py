@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """One-screen summary of a bench.py JSON line."""
 import json, sys
-d = json.loads(open(sys.argv[1]).readline())
+d = json.loads([l for l in open(sys.argv[1]) if l.startswith("{")][-1])
 e = d.get("e2e") or {}
 print(f"headline n_gpus={d['n_gpus']} value {d['value']:.0f} env-steps/s  ms/step {d['ms_per_step']:.3f}  kernel_ms {d['roofline']['kernel_ms']:.3f}  "
       f"e2e {e.get('value', 0):.0f}  warps {d['config']['warps_per_cta']}  frac {d['roofline']['frac']:.4f}  clocks {d.get('clocks')}")
