@@ -657,20 +657,26 @@ RCSB_DEV_NOINLINE void solve_noslip(const Ctx& c, int nefc, int ncon, unsigned r
 // post-pass. Out of line: the direct solve in st_constraint_solve handles almost every step, so this code stays out of
 // the hot instruction stream.
 RCSB_DEV void build_integrator_matrix(const Ctx& c, real* dst);
-RCSB_DEV_NOINLINE void newton_solve(const Ctx& c, int nefc, int ncon) {
+RCSB_DEV_NOINLINE void newton_solve(const Ctx& c, int nefc, int ncon, int have_direct) {
   const RcsbModel& m = CMODEL(c);
   const int nv = MD(nv);
   compute_qacc_smooth(c);
-  // warm start: keep qacc_warmstart only if its cost beats qacc_smooth's
+  // warm start: keep qacc_warmstart only if its cost beats qacc_smooth's. have_direct: o_qacc holds the last direct
+  // active-set solution (the exact minimiser for zones that turned out not to be the final ones); when it costs less than
+  // both it is the starting point - the minimiser the iteration converges to is the same, it is just reached sooner.
   real gauss;
   real cost_smooth = total_cost(c, WR(qacc_smooth), nefc, ncon, 0, nullptr);
+  real cost_direct = have_direct ? total_cost(c, WR(qacc), nefc, ncon, 0, nullptr) : (real)1e300;
   real cost = total_cost(c, WR(warm), nefc, ncon, 1, &gauss);
   const int use_warm = cost < cost_smooth;
-  const real* start = use_warm ? WR(warm) : WR(qacc_smooth);
-  PFOR(k, nv) { WR(qacc)[k] = start[k]; }
+  const int use_direct = cost_direct < (use_warm ? cost : cost_smooth);
+  if (!use_direct) {
+    const real* start = use_warm ? WR(warm) : WR(qacc_smooth);
+    PFOR(k, nv) { WR(qacc)[k] = start[k]; }
+  }
   RCSB_SYNC();
   real scale = (real)1 / (m.meaninertia * (nv > 1 ? nv : 1));
-  if (!use_warm) cost = total_cost(c, WR(qacc), nefc, ncon, 1, &gauss);
+  if (use_direct || !use_warm) cost = total_cost(c, WR(qacc), nefc, ncon, 1, &gauss);
   int iter = 0;
   const int* state = EFCI(RCSB_EI_STATE);
   while (iter < m.iterations) {
@@ -888,7 +894,7 @@ RCSB_DEV void st_constraint_solve(const Ctx& c) {
       return;
     }
   }
-  newton_solve(c, nefc, ncon);
+  newton_solve(c, nefc, ncon, 1);
 }
 
 // ------------------------------------------------------------------ implicitfast / Euler integration + mj_advance
