@@ -128,7 +128,7 @@ rcsb_k_cart_action8(const RcsbModel* __restrict__ gm, int nch, const real* __res
 struct RcsbCamera {
   int body;              // moving body the camera rides on (-1: fixed in the world)
   real pos[3], rot[9];   // camera frame in that body's frame (MuJoCo convention: looks along -z, +y up)
-  real f;                // focal length in pixels: 0.5 * H / tan(fovy / 2)
+  real f, inv_f;         // focal length in pixels: 0.5 * H / tan(fovy / 2), and its reciprocal (no division per ray)
   int W, H;
   real znear, zfar;      // clip planes in metres (mjVisual.map.znear / zfar x mjStatistic.extent)
   int physical_units;    // 1: millimetres of eye-space depth; 0: 1000 x the OpenGL window-space depth in [0, 1]
@@ -270,12 +270,12 @@ rcsb_k_depth(const RcsbModel* __restrict__ gm, const real* __restrict__ faces, c
     if (g < m.ng) {
       const real u0 = (tile % tiles_x) * RCSB_CAM_TILE, v0 = (tile / tiles_x) * RCSB_CAM_TILE;
       const real uc = u0 + (real)0.5 * RCSB_CAM_TILE, vc = v0 + (real)0.5 * RCSB_CAM_TILE;
-      real dcn[3] = {(uc - (real)0.5 * cam.W) / cam.f, -(vc - (real)0.5 * cam.H) / cam.f, (real)-1};
+      real dcn[3] = {(uc - (real)0.5 * cam.W) * cam.inv_f, -(vc - (real)0.5 * cam.H) * cam.inv_f, (real)-1};
       const real nc = sqrt(dcn[0] * dcn[0] + dcn[1] * dcn[1] + dcn[2] * dcn[2]);
       real cosa = 1;
       for (int k = 0; k < 4; k++) {
         const real uk = u0 + ((k & 1) ? (real)RCSB_CAM_TILE : (real)0), vk = v0 + ((k & 2) ? (real)RCSB_CAM_TILE : (real)0);
-        const real e[3] = {(uk - (real)0.5 * cam.W) / cam.f, -(vk - (real)0.5 * cam.H) / cam.f, (real)-1};
+        const real e[3] = {(uk - (real)0.5 * cam.W) * cam.inv_f, -(vk - (real)0.5 * cam.H) * cam.inv_f, (real)-1};
         const real ce = (e[0] * dcn[0] + e[1] * dcn[1] + e[2] * dcn[2]) / (nc * sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]));
         cosa = ce < cosa ? ce : cosa;
       }
@@ -301,24 +301,25 @@ rcsb_k_depth(const RcsbModel* __restrict__ gm, const real* __restrict__ faces, c
   }
   __syncthreads();
   const real ow[3] = {cfr[0], cfr[1], cfr[2]};
-  for (int i = 0; i < ntile; i++) {
-    const int tile = tile_lo + i;
-    const int u = (tile % tiles_x) * RCSB_CAM_TILE + threadIdx.x, v = (tile / tiles_x) * RCSB_CAM_TILE + threadIdx.y;
+  int tx = tile_lo % tiles_x, ty = tile_lo / tiles_x;  // the tile walk is row-major: no division per tile and thread
+  for (int i = 0; i < ntile; i++, tx++) {
+    if (tx == tiles_x) { tx = 0; ty++; }
+    const int u = tx * RCSB_CAM_TILE + threadIdx.x, v = ty * RCSB_CAM_TILE + threadIdx.y;
     if (u >= cam.W || v >= cam.H) continue;
     // pixel centre -> ray in the camera frame (x right, y up, looking along -z), scaled so that t is the eye-space depth
-    const real dc[3] = {(u + (real)0.5 - (real)0.5 * cam.W) / cam.f, -(v + (real)0.5 - (real)0.5 * cam.H) / cam.f, (real)-1};
+    const real dc[3] = {(u + (real)0.5 - (real)0.5 * cam.W) * cam.inv_f, -(v + (real)0.5 - (real)0.5 * cam.H) * cam.inv_f, (real)-1};
     real dw[3];
     for (int r = 0; r < 3; r++) dw[r] = cfr[3 + 3 * r] * dc[0] + cfr[3 + 3 * r + 1] * dc[1] + cfr[3 + 3 * r + 2] * dc[2];
-    const real dlen2 = dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2], inv_dlen2 = (real)1 / dlen2;
+    const real dlen2 = dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2];
     real tbest = cam.zfar;
     for (unsigned rest = tile_geoms[i]; rest; rest &= rest - 1) {
       const int g = __ffs(rest) - 1;
-      if (m.g_type[g] != RCSB_GEOM_PLANE) {  // bounding sphere: closest approach of the ray to the centre
-        const real cx = gbs[g][0] - ow[0], cy = gbs[g][1] - ow[1], cz = gbs[g][2] - ow[2];
-        const real tc = (cx * dw[0] + cy * dw[1] + cz * dw[2]) * inv_dlen2;
-        const real ex = cx - tc * dw[0], ey = cy - tc * dw[1], ez = cz - tc * dw[2], rr = gbs[g][3];
-        if (ex * ex + ey * ey + ez * ez > rr * rr) continue;
-        if ((tc - tbest) * (tc - tbest) * dlen2 > rr * rr && tc > tbest) continue;  // entirely behind the best hit
+      if (m.g_type[g] != RCSB_GEOM_PLANE) {  // bounding sphere, tested without a division: |c x d|^2 > r^2 |d|^2 misses it
+        const real cx = gbs[g][0] - ow[0], cy = gbs[g][1] - ow[1], cz = gbs[g][2] - ow[2], rr = gbs[g][3];
+        const real cd = cx * dw[0] + cy * dw[1] + cz * dw[2], cc = cx * cx + cy * cy + cz * cz;
+        if (cc * dlen2 - cd * cd > rr * rr * dlen2) continue;
+        const real behind = cd - tbest * dlen2;  // (closest approach - best hit) x |d|^2
+        if (behind > 0 && behind * behind > rr * rr * dlen2) continue;  // entirely behind the best hit
       }
       real og[3], dg[3], rel[3] = {ow[0] - gfr[g][0], ow[1] - gfr[g][1], ow[2] - gfr[g][2]};
       const real* R = &gfr[g][3];
@@ -805,6 +806,7 @@ int rcsb_camera_depth(rcsb_batch* b, int cam_body, const double* cam_pos, const 
   for (int i = 0; i < 3; i++) cam.pos[i] = (real)cam_pos[i];
   for (int i = 0; i < 9; i++) cam.rot[i] = (real)cam_rot[i];
   cam.f = (real)(0.5 * height / tan(fovy_deg * 3.14159265358979323846 / 360.0));
+  cam.inv_f = (real)1 / cam.f;
   cam.W = width; cam.H = height; cam.znear = (real)znear; cam.zfar = (real)zfar; cam.physical_units = physical_units != 0;
   const long long tiles = (long long)((width + RCSB_CAM_TILE - 1) / RCSB_CAM_TILE) * ((height + RCSB_CAM_TILE - 1) / RCSB_CAM_TILE);
   const long long chunks = (tiles + RCSB_CAM_CHUNK - 1) / RCSB_CAM_CHUNK;  // blocks per environment
