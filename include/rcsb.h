@@ -99,10 +99,10 @@ int rcsb_batch_run_host(rcsb_batch* b, unsigned ops, int k, int max_convergence_
  * action, then the gripper action; pinned) -> H2D, the fused launch (`ops` as for rcsb_batch_run, RCSB_RUN_OBS implied),
  * D2H of obs_host [n_envs][obs_dim] -- the observation row carries the info flags as reals in its last 8 columns --
  * and a stream synchronise. Replaces the host round trip of SimEnvCreator's env.step (python/rcs/envs/sim.py:49-66).
- * Page-locked buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are not copied: the kernel reads the action rows
- * and writes the observation rows through their device-mapped pointers, so the transfers overlap the physics (the device
- * copy of the observation block is then NOT updated); pageable buffers take staged copies. Same results either way.
- * RCSB_HOST_ZEROCOPY=0 in the environment forces the staged copies. */
+ * A page-locked action block (cudaHostAlloc / cudaHostRegister / torch pin_memory) is not copied: the kernel reads the
+ * action rows through the block's device-mapped pointer, so that transfer overlaps the physics; a pageable block takes a
+ * staged copy. The observation block always leaves through one DMA copy. Same results either way.
+ * RCSB_HOST_ZEROCOPY=0 in the environment forces the staged copy. */
 int rcsb_env_step_host(rcsb_batch* b, unsigned ops, int k, int max_convergence_steps, const double* act_host, double max_mov,
                        const double* jlow, const double* jhigh, double* obs_host);
 

@@ -754,19 +754,21 @@ int rcsb_env_step_host(rcsb_batch* b, unsigned ops, int k, int max_convergence_s
   const int nj = b->m->h.rb_njoints, stride = nj + 1;
   // one copy in: the packed action block lands in the joint staging array ([n][MAXJ] reals are reserved, nj + 1 <= MAXJ + 1)
   if ((size_t)stride > (size_t)RCSB_MAXJ + 1) return fail(RCSB_ERR_ARG, "too many joints");
-  // Pinned (page-locked, device-mapped) buffers are read and written by the kernel itself: every warp fetches its own
-  // 64-byte action row over PCIe when it starts and posts its 240-byte observation row when it is done, so both
-  // transfers hide behind the other warps' physics and the two copy launches disappear. Pageable buffers take the
-  // staged copies below. RCSB_HOST_ZEROCOPY=0 forces the staged path.
+  // A page-locked (device-mapped) action block is read by the kernel itself: every warp fetches its own 64-byte action row
+  // over PCIe when it starts, which hides behind the other warps' physics and saves the copy launch. The observation rows
+  // always go through the device block and ONE DMA copy: 240-byte rows posted by 4096 warps cross PCIe as small
+  // transactions and take 40-70 us longer than the copy engine (measured, tools/diag_e2e.py). A pageable action block takes
+  // the staged copy below. RCSB_HOST_ZEROCOPY=0 forces the staged path.
   {
     static const bool zero_copy = !(getenv("RCSB_HOST_ZEROCOPY") && atoi(getenv("RCSB_HOST_ZEROCOPY")) == 0);
-    void *act_map = nullptr, *obs_map = nullptr;
-    if (zero_copy && mapped_host_pointer(act_host, &act_map) && mapped_host_pointer(obs_host, &obs_map)) {
+    void* act_map = nullptr;
+    if (zero_copy && mapped_host_pointer(act_host, &act_map)) {
       b->act_jstride = stride; b->act_gstride = stride;
       rc = rcsb_batch_run(b, ops | RCSB_OP_OBS, k, max_convergence_steps, act_map, (const real*)act_map + nj, nullptr, max_mov, jlow, jhigh,
-                          obs_map, nullptr);
+                          b->d_obs, nullptr);
       b->act_jstride = 0; b->act_gstride = 0;
       if (rc) return rc;
+      CUDA_OK(cudaMemcpyAsync(obs_host, b->d_obs, (size_t)b->n * RCSB_OBS_DIM * sizeof(real), cudaMemcpyDeviceToHost, b->stream));
       CUDA_OK(cudaStreamSynchronize(b->stream));
       return RCSB_OK;
     }

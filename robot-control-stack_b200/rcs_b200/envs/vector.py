@@ -74,11 +74,11 @@ class SimVectorEnv:
 
     # ------------------------------------------------------------------ helpers
     def _substeps(self):
-        cfg = self.sim.get_config()
+        cfg = self.sim._cfg  # read-only use: no copy on the per-step path
         return round(1 / cfg.frequency / self.sim.model.opt.timestep)  # envs/sim.py:53
 
     def _step_ops(self):
-        cfg = self.sim.get_config()
+        cfg = self.sim._cfg
         ops = _lib.OBS | (_lib.STEP_K if cfg.async_control else _lib.STEP_CONV)
         if self.control_mode == ControlMode.JOINTS:
             ops |= _lib.ACT_JOINTS_REL if self.relative else _lib.ACT_JOINTS_ABS
