@@ -151,7 +151,8 @@ int rcsb_env_cartesian_action_origin(rcsb_batch* b, const void* act_dev, int kin
  * row 0 = top, = (uint16)(1000 * eye-space depth in metres clipped to [znear, zfar]) with physical_units, else
  * (uint16)(1000 * OpenGL window-space depth in [0, 1]). Rays are cast against the collidable geoms (convex hulls for
  * meshes), not rasterised visual meshes. cam_frames_dev (optional) [n_envs][12] reals receives the camera's world frame
- * of every environment (position, then the row-major rotation: mjData.cam_xpos / cam_xmat, for the extrinsics). */
+ * of every environment (position, then the row-major rotation: mjData.cam_xpos / cam_xmat, for the extrinsics).
+ * Rays are traced in float (frames and tile culling in double); RCSB_DEPTH_F64=1 in the environment selects double rays. */
 int rcsb_camera_depth(rcsb_batch* b, int cam_body, const double* cam_pos, const double* cam_rot, double fovy_deg, int width, int height,
                       double znear, double zfar, int physical_units, void* out_dev, void* cam_frames_dev);
 /* world frames of the moving bodies at the current qpos (mjData.xpos / xmat of the bodies that carry a joint):

@@ -134,79 +134,79 @@ struct RcsbCamera {
   int physical_units;    // 1: millimetres of eye-space depth; 0: 1000 x the OpenGL window-space depth in [0, 1]
 };
 enum { RCSB_CAM_TILE = 16 };
-__device__ __forceinline__ bool ray_geom(const RcsbModel& m, int g, const real* __restrict__ faces, const int* __restrict__ face_adr,
-                                         const int* __restrict__ face_num, const real* o, const real* d, real tmax, real* t_out) {
+template <typename T>
+__device__ __forceinline__ bool ray_geom(const RcsbModel& m, int g, const T* __restrict__ faces, const int* __restrict__ face_adr,
+                                         const int* __restrict__ face_num, const T* sz, const T* ab, const T* o, const T* d, T tmax,
+                                         T* t_out) {
   // o, d: ray in the geom frame (d not normalised: t is in units of it)
   const int type = m.g_type[g];
-  const real* sz = m.g_size[g];
-  real t = -1;
+  T t = -1;
   if (type == RCSB_GEOM_PLANE) {
     if (d[2] < 0) t = -o[2] / d[2];
   } else if (type == RCSB_GEOM_SPHERE) {
-    const real a = d[0] * d[0] + d[1] * d[1] + d[2] * d[2], b = o[0] * d[0] + o[1] * d[1] + o[2] * d[2];
-    const real cc = o[0] * o[0] + o[1] * o[1] + o[2] * o[2] - sz[0] * sz[0], disc = b * b - a * cc;
+    const T a = d[0] * d[0] + d[1] * d[1] + d[2] * d[2], b = o[0] * d[0] + o[1] * d[1] + o[2] * d[2];
+    const T cc = o[0] * o[0] + o[1] * o[1] + o[2] * o[2] - sz[0] * sz[0], disc = b * b - a * cc;
     if (disc >= 0) t = (-b - sqrt(disc)) / a;
   } else if (type == RCSB_GEOM_BOX) {
-    real t0 = 0, t1 = tmax;
+    T t0 = 0, t1 = tmax;
     for (int k = 0; k < 3; k++) {
       if (d[k] != 0) {
-        const real inv = (real)1 / d[k];
-        real ta = (-sz[k] - o[k]) * inv, tb = (sz[k] - o[k]) * inv;
-        if (ta > tb) { real s = ta; ta = tb; tb = s; }
+        const T inv = (T)1 / d[k];
+        T ta = (-sz[k] - o[k]) * inv, tb = (sz[k] - o[k]) * inv;
+        if (ta > tb) { T s = ta; ta = tb; tb = s; }
         t0 = ta > t0 ? ta : t0; t1 = tb < t1 ? tb : t1;
       } else if (o[k] < -sz[k] || o[k] > sz[k]) t1 = -1;
     }
     if (t0 <= t1) t = t0;
   } else if (type == RCSB_GEOM_CAPSULE || type == RCSB_GEOM_CYLINDER) {
-    const real r = sz[0], hl = sz[1];
+    const T r = sz[0], hl = sz[1];
     // side: infinite cylinder about z, accepted while |z| <= hl
-    const real a = d[0] * d[0] + d[1] * d[1], b = o[0] * d[0] + o[1] * d[1], cc = o[0] * o[0] + o[1] * o[1] - r * r;
-    real best = (real)1e300;
+    const T a = d[0] * d[0] + d[1] * d[1], b = o[0] * d[0] + o[1] * d[1], cc = o[0] * o[0] + o[1] * o[1] - r * r;
+    T best = (T)1e30;
     if (a > 0) {
-      const real disc = b * b - a * cc;
+      const T disc = b * b - a * cc;
       if (disc >= 0) {
-        const real ts = (-b - sqrt(disc)) / a, z = o[2] + ts * d[2];
+        const T ts = (-b - sqrt(disc)) / a, z = o[2] + ts * d[2];
         if (ts >= 0 && z >= -hl && z <= hl) best = ts;
       }
     }
     for (int s = -1; s <= 1; s += 2) {
       if (type == RCSB_GEOM_CAPSULE) {  // end spheres
-        const real oz = o[2] - s * hl;
-        const real A = a + d[2] * d[2], B = b + oz * d[2], C = o[0] * o[0] + o[1] * o[1] + oz * oz - r * r, disc = B * B - A * C;
+        const T oz = o[2] - s * hl;
+        const T A = a + d[2] * d[2], B = b + oz * d[2], C = o[0] * o[0] + o[1] * o[1] + oz * oz - r * r, disc = B * B - A * C;
         if (disc >= 0) {
-          const real ts = (-B - sqrt(disc)) / A;
+          const T ts = (-B - sqrt(disc)) / A;
           if (ts >= 0 && s * (o[2] + ts * d[2]) >= hl && ts < best) best = ts;
         }
       } else if (d[2] != 0) {           // end caps
-        const real ts = (s * hl - o[2]) / d[2], x = o[0] + ts * d[0], y = o[1] + ts * d[1];
+        const T ts = (s * hl - o[2]) / d[2], x = o[0] + ts * d[0], y = o[1] + ts * d[1];
         if (ts >= 0 && s * d[2] < 0 && x * x + y * y <= r * r && ts < best) best = ts;
       }
     }
-    if (best < (real)1e299) t = best;
+    if (best < (T)1e29) t = best;
   } else if (type == RCSB_GEOM_MESH) {
     {  // the hull lies inside its local AABB: a slab test first (most rays that pass the bounding sphere miss the box);
        // one reciprocal per axis and a little slack - the test only has to be conservative, the planes decide alone
-      const real* ab = m.g_aabb[g];
-      real t0 = 0, t1 = tmax;
+      T t0 = 0, t1 = tmax;
       for (int k = 0; k < 3; k++) {
         if (d[k] != 0) {
-          const real inv = (real)1 / d[k];
-          real ta = (ab[k] - ab[3 + k] - o[k]) * inv, tb = (ab[k] + ab[3 + k] - o[k]) * inv;
-          if (ta > tb) { real sw = ta; ta = tb; tb = sw; }
+          const T inv = (T)1 / d[k];
+          T ta = (ab[k] - ab[3 + k] - o[k]) * inv, tb = (ab[k] + ab[3 + k] - o[k]) * inv;
+          if (ta > tb) { T sw = ta; ta = tb; tb = sw; }
           t0 = ta > t0 ? ta : t0; t1 = tb < t1 ? tb : t1;
         } else if (o[k] < ab[k] - ab[3 + k] || o[k] > ab[k] + ab[3 + k]) t1 = -1;
       }
-      if (t0 > t1 * (real)1.000000001 + (real)1e-12) return false;
+      if (t0 > t1 * (sizeof(T) == 4 ? (T)1.00001 : (T)1.000000001) + (sizeof(T) == 4 ? (T)1e-6 : (T)1e-12)) return false;
     }
     // Clip the ray against the hull's face planes. The entry / exit parameters are kept as fractions with positive
     // denominators and compared by cross-multiplication: one division per geom instead of one per face.
-    real t0n = 0, t0d = 1, t1n = tmax, t1d = 1;
-    const real* pl = faces + 4 * (size_t)face_adr[g];
+    T t0n = 0, t0d = 1, t1n = tmax, t1d = 1;
+    const T* pl = faces + 4 * (size_t)face_adr[g];
     const int n = face_num[g];
     bool open = true;
     for (int i = 0; i < n && open; i++) {
-      const real nx = __ldg(pl + 4 * i), ny = __ldg(pl + 4 * i + 1), nz = __ldg(pl + 4 * i + 2), dd = __ldg(pl + 4 * i + 3);
-      const real den = nx * d[0] + ny * d[1] + nz * d[2], num = -(nx * o[0] + ny * o[1] + nz * o[2] + dd);
+      const T nx = __ldg(pl + 4 * i), ny = __ldg(pl + 4 * i + 1), nz = __ldg(pl + 4 * i + 2), dd = __ldg(pl + 4 * i + 3);
+      const T den = nx * d[0] + ny * d[1] + nz * d[2], num = -(nx * o[0] + ny * o[1] + nz * o[2] + dd);
       if (den < 0) { if (-num * t0d > t0n * -den) { t0n = -num; t0d = -den; } }   // entering: t = num / den
       else if (den > 0) { if (num * t1d < t1n * den) { t1n = num; t1d = den; } }  // leaving
       else if (num < 0) open = false;
@@ -222,8 +222,12 @@ __device__ __forceinline__ bool ray_geom(const RcsbModel& m, int g, const real* 
 // per block (a block per tile spent more time on that prologue than on its 256 rays), every warp culls the geoms of a few
 // tiles, then the block walks through its tiles without further barriers.
 #define RCSB_CAM_CHUNK 32
+// T: arithmetic type of the rays (float by default: the reference's depth buffer is float32 and a float ray is good to a few
+// micrometres, three orders below the millimetre the output is quantised to; double on request). Frames and the
+// conservative tile culling stay in double.
+template <typename T>
 __global__ void __launch_bounds__(RCSB_CAM_TILE * RCSB_CAM_TILE)
-rcsb_k_depth(const RcsbModel* __restrict__ gm, const real* __restrict__ faces, const int* __restrict__ face_adr,
+rcsb_k_depth(const RcsbModel* __restrict__ gm, const T* __restrict__ faces, const int* __restrict__ face_adr,
              const int* __restrict__ face_num, const real* __restrict__ frames, RcsbCamera cam, unsigned short* __restrict__ out, real* __restrict__ cam_frames_out,
              int N) {
   const RcsbModel& m = *gm;
@@ -231,6 +235,7 @@ rcsb_k_depth(const RcsbModel* __restrict__ gm, const real* __restrict__ faces, c
   __shared__ real gbs[RCSB_MAXG][4];    // bounding sphere: centre, radius
   __shared__ real cfr[12];              // camera frame in the world
   __shared__ unsigned tile_geoms[RCSB_CAM_CHUNK];  // per tile: geoms whose bounding sphere can meet one of its rays (planes always)
+  __shared__ T rfr[RCSB_MAXG][12], rbs[RCSB_MAXG][4], rsz[RCSB_MAXG][3], rab[RCSB_MAXG][6], rcf[12];  // the rays' copies, in T
   const int tiles_x = (cam.W + RCSB_CAM_TILE - 1) / RCSB_CAM_TILE, tiles_y = (cam.H + RCSB_CAM_TILE - 1) / RCSB_CAM_TILE;
   const int tiles = tiles_x * tiles_y, chunks = (tiles + RCSB_CAM_CHUNK - 1) / RCSB_CAM_CHUNK;
   const int env = blockIdx.x / chunks, tile_lo = (blockIdx.x - env * chunks) * RCSB_CAM_CHUNK;
@@ -248,6 +253,10 @@ rcsb_k_depth(const RcsbModel* __restrict__ gm, const real* __restrict__ faces, c
       for (int k = 0; k < 3; k++) gfr[g][3 + 3 * r + k] = R[3 * r] * Rl[k] + R[3 * r + 1] * Rl[3 + k] + R[3 * r + 2] * Rl[6 + k];
     }
     gbs[g][3] = m.g_rbound[g];
+    for (int i = 0; i < 12; i++) rfr[g][i] = (T)gfr[g][i];
+    for (int i = 0; i < 4; i++) rbs[g][i] = (T)gbs[g][i];
+    for (int i = 0; i < 3; i++) rsz[g][i] = (T)m.g_size[g][i];
+    for (int i = 0; i < 6; i++) rab[g][i] = (T)m.g_aabb[g][i];
   }
   if (tid == 64) {
     real p[3] = {0, 0, 0}, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -258,6 +267,7 @@ rcsb_k_depth(const RcsbModel* __restrict__ gm, const real* __restrict__ faces, c
     }
     if (cam_frames_out && tile_lo == 0)  // the camera's world frame of this environment (extrinsics), written once
       for (int i = 0; i < 12; i++) cam_frames_out[(size_t)env * 12 + i] = cfr[i];
+    for (int i = 0; i < 12; i++) rcf[i] = (T)cfr[i];
   }
   __syncthreads();
   // Tile culling, one warp per tile and one lane per geom: the tile's rays lie in a cone about its centre ray (half-angle
@@ -300,41 +310,44 @@ rcsb_k_depth(const RcsbModel* __restrict__ gm, const real* __restrict__ faces, c
     if ((tid & 31) == 0) tile_geoms[i] = mask;
   }
   __syncthreads();
-  const real ow[3] = {cfr[0], cfr[1], cfr[2]};
+  const T ow[3] = {rcf[0], rcf[1], rcf[2]};
+  const T inv_f = (T)cam.inv_f, half_w = (T)0.5 * cam.W, half_h = (T)0.5 * cam.H;
+  // a float sphere test keeps a sliver of slack so that rounding never drops a geom a double test would keep
+  const T slack = sizeof(T) == 4 ? (T)1.0001 : (T)1;
   int tx = tile_lo % tiles_x, ty = tile_lo / tiles_x;  // the tile walk is row-major: no division per tile and thread
   for (int i = 0; i < ntile; i++, tx++) {
     if (tx == tiles_x) { tx = 0; ty++; }
     const int u = tx * RCSB_CAM_TILE + threadIdx.x, v = ty * RCSB_CAM_TILE + threadIdx.y;
     if (u >= cam.W || v >= cam.H) continue;
     // pixel centre -> ray in the camera frame (x right, y up, looking along -z), scaled so that t is the eye-space depth
-    const real dc[3] = {(u + (real)0.5 - (real)0.5 * cam.W) * cam.inv_f, -(v + (real)0.5 - (real)0.5 * cam.H) * cam.inv_f, (real)-1};
-    real dw[3];
-    for (int r = 0; r < 3; r++) dw[r] = cfr[3 + 3 * r] * dc[0] + cfr[3 + 3 * r + 1] * dc[1] + cfr[3 + 3 * r + 2] * dc[2];
-    const real dlen2 = dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2];
-    real tbest = cam.zfar;
+    const T dc[3] = {(u + (T)0.5 - half_w) * inv_f, -(v + (T)0.5 - half_h) * inv_f, (T)-1};
+    T dw[3];
+    for (int r = 0; r < 3; r++) dw[r] = rcf[3 + 3 * r] * dc[0] + rcf[3 + 3 * r + 1] * dc[1] + rcf[3 + 3 * r + 2] * dc[2];
+    const T dlen2 = dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2];
+    T tbest = (T)cam.zfar;
     for (unsigned rest = tile_geoms[i]; rest; rest &= rest - 1) {
       const int g = __ffs(rest) - 1;
       if (m.g_type[g] != RCSB_GEOM_PLANE) {  // bounding sphere, tested without a division: |c x d|^2 > r^2 |d|^2 misses it
-        const real cx = gbs[g][0] - ow[0], cy = gbs[g][1] - ow[1], cz = gbs[g][2] - ow[2], rr = gbs[g][3];
-        const real cd = cx * dw[0] + cy * dw[1] + cz * dw[2], cc = cx * cx + cy * cy + cz * cz;
+        const T cx = rbs[g][0] - ow[0], cy = rbs[g][1] - ow[1], cz = rbs[g][2] - ow[2], rr = rbs[g][3] * slack;
+        const T cd = cx * dw[0] + cy * dw[1] + cz * dw[2], cc = cx * cx + cy * cy + cz * cz;
         if (cc * dlen2 - cd * cd > rr * rr * dlen2) continue;
-        const real behind = cd - tbest * dlen2;  // (closest approach - best hit) x |d|^2
+        const T behind = cd - tbest * dlen2;  // (closest approach - best hit) x |d|^2
         if (behind > 0 && behind * behind > rr * rr * dlen2) continue;  // entirely behind the best hit
       }
-      real og[3], dg[3], rel[3] = {ow[0] - gfr[g][0], ow[1] - gfr[g][1], ow[2] - gfr[g][2]};
-      const real* R = &gfr[g][3];
+      T og[3], dg[3], rel[3] = {ow[0] - rfr[g][0], ow[1] - rfr[g][1], ow[2] - rfr[g][2]};
+      const T* R = &rfr[g][3];
       for (int k = 0; k < 3; k++) {
         og[k] = R[k] * rel[0] + R[3 + k] * rel[1] + R[6 + k] * rel[2];
         dg[k] = R[k] * dw[0] + R[3 + k] * dw[1] + R[6 + k] * dw[2];
       }
-      real t;
-      if (ray_geom(m, g, faces, face_adr, face_num, og, dg, tbest, &t) && t < tbest) tbest = t;
+      T t;
+      if (ray_geom<T>(m, g, faces, face_adr, face_num, rsz[g], rab[g], og, dg, tbest, &t) && t < tbest) tbest = t;
     }
-    real z = tbest < cam.znear ? cam.znear : tbest;  // eye-space depth, clipped like the view frustum
-    real val;
-    if (cam.physical_units) val = z * (real)1000;                               // camera/sim.py:65-72 then x DEPTH_SCALE
-    else val = (1 - cam.znear / z) / (1 - cam.znear / cam.zfar) * (real)1000;   // window-space depth x DEPTH_SCALE
-    val = val < 0 ? (real)0 : (val > (real)65535 ? (real)65535 : val);
+    const T zn = (T)cam.znear, z = tbest < zn ? zn : tbest;  // eye-space depth, clipped like the view frustum
+    T val;
+    if (cam.physical_units) val = z * (T)1000;                                  // camera/sim.py:65-72 then x DEPTH_SCALE
+    else val = (1 - zn / z) / (1 - zn / (T)cam.zfar) * (T)1000;                 // window-space depth x DEPTH_SCALE
+    val = val < 0 ? (T)0 : (val > (T)65535 ? (T)65535 : val);
     out[((size_t)env * cam.H + v) * cam.W + u] = (unsigned short)val;           // astype(np.uint16): truncation
   }
 }
@@ -376,6 +389,7 @@ struct rcsb_model {
   std::vector<real> faces;  // hull face planes (n, d) of the collidable mesh geoms, pooled (depth camera)
   std::vector<int> face_adr, face_num;
   real* d_faces = nullptr;
+  float* d_faces32 = nullptr;  // the same planes for float rays
   int *d_face_adr = nullptr, *d_face_num = nullptr;
   bool finalized = false;
   int device = -1;
@@ -436,6 +450,7 @@ void rcsb_model_free(rcsb_model* m) {
   if (m->d_verts) cudaFree(m->d_verts);
   if (m->d_vgraph) cudaFree(m->d_vgraph);
   if (m->d_faces) cudaFree(m->d_faces);
+  if (m->d_faces32) cudaFree(m->d_faces32);
   if (m->d_face_adr) cudaFree(m->d_face_adr);
   if (m->d_face_num) cudaFree(m->d_face_num);
   delete m;
@@ -516,6 +531,11 @@ int rcsb_model_upload(rcsb_model* m, int device) {
   if (m->face_adr.empty()) { m->faces.assign(4, 0); m->face_adr.assign(RCSB_MAXG, 0); m->face_num.assign(RCSB_MAXG, 0); }
   CUDA_OK(cudaMalloc(&m->d_faces, m->faces.size() * sizeof(real)));
   CUDA_OK(cudaMemcpy(m->d_faces, m->faces.data(), m->faces.size() * sizeof(real), cudaMemcpyHostToDevice));
+  {
+    std::vector<float> f32(m->faces.begin(), m->faces.end());
+    CUDA_OK(cudaMalloc(&m->d_faces32, f32.size() * sizeof(float)));
+    CUDA_OK(cudaMemcpy(m->d_faces32, f32.data(), f32.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   CUDA_OK(cudaMalloc(&m->d_face_adr, RCSB_MAXG * sizeof(int)));
   CUDA_OK(cudaMemcpy(m->d_face_adr, m->face_adr.data(), RCSB_MAXG * sizeof(int), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMalloc(&m->d_face_num, RCSB_MAXG * sizeof(int)));
@@ -814,8 +834,14 @@ int rcsb_camera_depth(rcsb_batch* b, int cam_body, const double* cam_pos, const 
   const long long chunks = (tiles + RCSB_CAM_CHUNK - 1) / RCSB_CAM_CHUNK;  // blocks per environment
   if (chunks * b->n > 0x7fffffffLL) return fail(RCSB_ERR_ARG, "image too large for one launch");
   dim3 block(RCSB_CAM_TILE, RCSB_CAM_TILE), grid((unsigned)(chunks * b->n));
-  rcsb_k_depth<<<grid, block, 0, b->stream>>>(b->m->d_model, b->m->d_faces, b->m->d_face_adr, b->m->d_face_num, b->d_frames, cam,
-                                             (unsigned short*)out_dev, (real*)cam_frames_dev, b->n);
+  // float rays unless RCSB_DEPTH_F64=1 asks for double ones (the oracle comparison at the last digit)
+  const char* f64 = getenv("RCSB_DEPTH_F64");
+  if (f64 && atoi(f64) != 0)
+    rcsb_k_depth<real><<<grid, block, 0, b->stream>>>(b->m->d_model, b->m->d_faces, b->m->d_face_adr, b->m->d_face_num, b->d_frames, cam,
+                                                     (unsigned short*)out_dev, (real*)cam_frames_dev, b->n);
+  else
+    rcsb_k_depth<float><<<grid, block, 0, b->stream>>>(b->m->d_model, b->m->d_faces32, b->m->d_face_adr, b->m->d_face_num, b->d_frames, cam,
+                                                      (unsigned short*)out_dev, (real*)cam_frames_dev, b->n);
   g_launches++;
   CUDA_OK(cudaGetLastError());
   return RCSB_OK;

@@ -31,7 +31,17 @@ def test_oracle_depth_conventions_closed_form():
 @pytest.mark.parametrize("scene,cam,res", [("fr3_simple_pick_up", "bird_eye_cam", (96, 64)), ("fr3_simple_pick_up", "wrist_0", (64, 64)),
                                            ("fr3_simple_pick_up", "side_view", (80, 60)), ("fr3_empty_world", "wrist_0", (48, 48)),
                                            ("fr3_simple_pick_up", "bird_eye_cam", (136, 100))])  # 63 tiles: two blocks per image, ragged edges
-def test_depth_kernel_matches_oracle(scene, cam, res):
+def test_depth_kernel_matches_oracle(scene, cam, res, monkeypatch):
+    """float rays (the default) on every case; the (96, 64) and (136, 100) cases also with double rays (RCSB_DEPTH_F64=1)"""
+    for f64 in ((False, True) if res in ((96, 64), (136, 100)) else (False,)):
+        if f64:
+            monkeypatch.setenv("RCSB_DEPTH_F64", "1")
+        else:
+            monkeypatch.delenv("RCSB_DEPTH_F64", raising=False)
+        _depth_case(scene, cam, res)
+
+
+def _depth_case(scene, cam, res):
     import rcs_b200
     from rcs_b200 import sim
     from rcs_b200.camera import SimCameraConfig, SimCameraSet
