@@ -168,6 +168,11 @@ int rcsb_kernel_occupancy(rcsb_batch* b, int* warps_per_cta, int* smem_bytes, in
 const char* rcsb_kernel_variant(rcsb_batch* b, int phase);
 /* profiling build only (-DRCSB_STAGE_TIMING): accumulated clock64() cycles per physics stage of warp 0 / CTA 0, then reset */
 int rcsb_debug_stage_cycles(unsigned long long* out16);
+/* Profiling build only: cycles of stage i (0..8) of the first max_steps (<= 256) physics steps every warp of CTA 0 ran since
+ * the last call, out[max_steps][10][32] (step, stage, warp; stage 9 = the narrow phase inside the collision stage), followed
+ * by [max_steps][32] collision counts (due groups | broad-phase survivors << 8 | mid-phase survivors << 16); the call also
+ * clears the trace. */
+int rcsb_debug_stage_trace(unsigned* out, int max_steps);
 
 #ifdef __cplusplus
 }

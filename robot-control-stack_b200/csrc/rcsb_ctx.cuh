@@ -50,4 +50,10 @@ enum { MI_NCON = 0, MI_NEFC, MI_NE, MI_NF, MI_NL, MI_HAVE_L, MI_SOLVER_ITER, MI_
 #define WI(name) (CWI(c) + LAY.oi_##name)
 #if defined(RCSB_STAGE_TIMING) && !defined(RCSB_HOST_EMU)
 __device__ unsigned long long rcsb_stage_cycles[16];  // profiling build = one translation unit (RCSB_SINGLE_TU)
+// per-warp trace of CTA 0: cycles of stage i (0..8; 9 = whole step incl. barrier waits) of the first RCSB_TRACE_STEPS physics
+// steps each warp runs after the last reset of the trace
+#define RCSB_TRACE_STEPS 256
+__device__ unsigned rcsb_trace[RCSB_TRACE_STEPS][10][32];
+__device__ unsigned rcsb_trace_step[32];
+__device__ unsigned rcsb_trace_aux[RCSB_TRACE_STEPS][32];  // collision stage: due groups | broad survivors << 8 | mid survivors << 16
 #endif

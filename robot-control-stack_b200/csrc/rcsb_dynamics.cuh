@@ -1375,6 +1375,11 @@ RCSB_DEV void st_collision(const Ctx& c) {
   }
   RCSB_SYNC();
   // ---- narrow phase, candidates in pair order
+#if defined(RCSB_STAGE_TIMING) && !defined(RCSB_HOST_EMU)
+  const long long t_narrow_ = clock64();
+  if (blockIdx.x == 0 && c.lane == 0 && rcsb_trace_step[threadIdx.x >> 5] < RCSB_TRACE_STEPS)  // due groups | broad | mid survivors
+    rcsb_trace_aux[rcsb_trace_step[threadIdx.x >> 5]][threadIdx.x >> 5] = (unsigned)(__popc(act[0]) + __popc(act[1])) | ((unsigned)ncandA << 8) | ((unsigned)ncand << 16);
+#endif
   int ncon = 0;
   for (int ic = 0; ic < ncand; ic++) {
     int p = candB[ic];
@@ -1457,4 +1462,8 @@ RCSB_DEV void st_collision(const Ctx& c) {
   }
   if (c.lane == 0) WI(misc)[MI_NCON] = ncon;
   RCSB_SYNC();
+#if defined(RCSB_STAGE_TIMING) && !defined(RCSB_HOST_EMU)
+  if (blockIdx.x == 0 && c.lane == 0 && rcsb_trace_step[threadIdx.x >> 5] < RCSB_TRACE_STEPS)
+    rcsb_trace[rcsb_trace_step[threadIdx.x >> 5]][9][threadIdx.x >> 5] = (unsigned)(clock64() - t_narrow_);
+#endif
 }

@@ -642,6 +642,25 @@ int rcsb_debug_stage_cycles(unsigned long long* out16) {
   return fail(RCSB_ERR_ARG, "library built without RCSB_STAGE_TIMING");
 #endif
 }
+int rcsb_debug_stage_trace(unsigned* out, int max_steps) {
+#ifdef RCSB_STAGE_TIMING
+  CUDA_OK(cudaDeviceSynchronize());
+  if (out && max_steps > 0) {  // out[max_steps][10][32] stage cycles, then out2[max_steps][32] collision counts
+    if (max_steps > RCSB_TRACE_STEPS) max_steps = RCSB_TRACE_STEPS;
+    CUDA_OK(cudaMemcpyFromSymbol(out, rcsb_trace, (size_t)max_steps * 10 * 32 * sizeof(unsigned)));
+    CUDA_OK(cudaMemcpyFromSymbol(out + (size_t)max_steps * 10 * 32, rcsb_trace_aux, (size_t)max_steps * 32 * sizeof(unsigned)));
+  }
+  static unsigned zt[RCSB_TRACE_STEPS][10][32];
+  CUDA_OK(cudaMemcpyToSymbol(rcsb_trace_aux, zt, sizeof(unsigned) * RCSB_TRACE_STEPS * 32));
+  unsigned zs[32] = {0};
+  CUDA_OK(cudaMemcpyToSymbol(rcsb_trace, zt, sizeof(zt)));
+  CUDA_OK(cudaMemcpyToSymbol(rcsb_trace_step, zs, sizeof(zs)));
+  return RCSB_OK;
+#else
+  (void)out; (void)max_steps;
+  return fail(RCSB_ERR_ARG, "library built without RCSB_STAGE_TIMING");
+#endif
+}
 int rcsb_model_workspace_bytes(const rcsb_model* m, int* reduced_bytes, int* full_bytes, int* smem_header_bytes) {
   if (!m->finalized) return fail(RCSB_ERR_MODEL, "rcsb_model_finalize not called");
   if (reduced_bytes) *reduced_bytes = m->has_reduced ? (int)rcsb_ws_bytes(&m->hr) : 0;

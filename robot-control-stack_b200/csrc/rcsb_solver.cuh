@@ -1094,7 +1094,10 @@ RCSB_DEV void reset_data(const Ctx& c, double* time) {  // mj_resetData
     RCSB_STAGE_SYNC(idx);                                                                            \
     long long t0_ = clock64();                                                                       \
     call;                                                                                            \
-    if (blockIdx.x == 0 && threadIdx.x == 0) rcsb_stage_cycles[idx] += (unsigned long long)(clock64() - t0_); \
+    long long dt_ = clock64() - t0_;                                                                 \
+    if (blockIdx.x == 0 && threadIdx.x == 0) rcsb_stage_cycles[idx] += (unsigned long long)dt_;      \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && rcsb_trace_step[threadIdx.x >> 5] < RCSB_TRACE_STEPS) \
+      rcsb_trace[rcsb_trace_step[threadIdx.x >> 5]][idx][threadIdx.x >> 5] = (unsigned)dt_;          \
   } while (0)
 #else
 #define RCSB_STAGE(idx, call) do { RCSB_STAGE_SYNC(idx); call; } while (0)
@@ -1132,6 +1135,9 @@ RCSB_DEV int physics_step(const Ctx& c, double* time) {
   RCSB_STAGE(7, st_constraint_solve(c));
   RCSB_STAGE(8, st_integrate(c));
   RCSB_STEP_SYNC();
+#if defined(RCSB_STAGE_TIMING) && !defined(RCSB_HOST_EMU)
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) rcsb_trace_step[threadIdx.x >> 5] += 1;
+#endif
   if (c.lane == 0) {  // the clock lives in shared memory: one writer
     *time += (double)m.timestep;
     RI(RCSB_I_TOTAL_STEPS) += 1;

@@ -90,4 +90,4 @@ EXPORTS = ["rcsb_last_error", "rcsb_version", "rcsb_real_bytes", "rcsb_model_new
            "rcsb_sim_step_until_convergence", "rcsb_sim_reset", "rcsb_robot_set_joint_position",
            "rcsb_robot_set_joints_hard", "rcsb_robot_reset", "rcsb_gripper_set_normalized_width",
            "rcsb_gripper_reset", "rcsb_env_get_obs", "rcsb_ik_inverse", "rcsb_robot_set_cartesian_position", "rcsb_env_cartesian_action", "rcsb_env_cartesian_action_origin",
-           "rcsb_launch_count", "rcsb_kernel_occupancy", "rcsb_kernel_variant", "rcsb_debug_stage_cycles"]
+           "rcsb_launch_count", "rcsb_kernel_occupancy", "rcsb_kernel_variant", "rcsb_debug_stage_cycles", "rcsb_debug_stage_trace"]
