@@ -170,8 +170,9 @@ const char* rcsb_kernel_variant(rcsb_batch* b, int phase);
 int rcsb_debug_stage_cycles(unsigned long long* out16);
 /* Profiling build only: cycles of stage i (0..8) of the first max_steps (<= 256) physics steps every warp of CTA 0 ran since
  * the last call, out[max_steps][10][32] (step, stage, warp; stage 9 = the narrow phase inside the collision stage), followed
- * by [max_steps][32] collision counts (due groups | broad-phase survivors << 8 | mid-phase survivors << 16); the call also
- * clears the trace. */
+ * by [max_steps][32] collision counts (due groups | broad-phase survivors << 8 | mid-phase survivors << 16) and by [max_steps][3][32]
+ * cycles from the start of the collision stage to the end of the geom-centre pass | the broad phase | the mid phase; the call
+ * also clears the trace. */
 int rcsb_debug_stage_trace(unsigned* out, int max_steps);
 
 #ifdef __cplusplus

@@ -55,5 +55,6 @@ __device__ unsigned long long rcsb_stage_cycles[16];  // profiling build = one t
 #define RCSB_TRACE_STEPS 256
 __device__ unsigned rcsb_trace[RCSB_TRACE_STEPS][10][32];
 __device__ unsigned rcsb_trace_step[32];
+__device__ unsigned rcsb_trace_col[RCSB_TRACE_STEPS][3][32];  // collision stage of an event: cycles up to the geom centres | the broad phase | the mid phase
 __device__ unsigned rcsb_trace_aux[RCSB_TRACE_STEPS][32];  // collision stage: due groups | broad survivors << 8 | mid survivors << 16
 #endif

@@ -1277,9 +1277,21 @@ RCSB_DEV void budget_advance(const Ctx& c) {
     bud[g] -= (float)(h * s * (real)1.000001) + 1e-6f;
   }
 }
+#if defined(RCSB_STAGE_TIMING) && !defined(RCSB_HOST_EMU)
+#define RCSB_COL_PROBE(i)                                                                                               \
+  do {                                                                                                                  \
+    if (blockIdx.x == 0 && c.lane == 0 && rcsb_trace_step[threadIdx.x >> 5] < RCSB_TRACE_STEPS)                         \
+      rcsb_trace_col[rcsb_trace_step[threadIdx.x >> 5]][i][threadIdx.x >> 5] = (unsigned)(clock64() - t_col_);          \
+  } while (0)
+#else
+#define RCSB_COL_PROBE(i) ((void)0)
+#endif
 RCSB_DEV void st_collision(const Ctx& c) {
   const RcsbModel& m = CMODEL(c);
   float* bud = (float*)WR(cbud);
+#if defined(RCSB_STAGE_TIMING) && !defined(RCSB_HOST_EMU)
+  const long long t_col_ = clock64();
+#endif
   // ---- groups whose separation budget is used up go through the phases; the others cannot be in contact
   uint32_t act[(RCSB_MAXGRP + 31) / 32] = {0, 0};
 #ifdef RCSB_HOST_EMU
@@ -1310,10 +1322,13 @@ RCSB_DEV void st_collision(const Ctx& c) {
     }
   }
   RCSB_SYNC();
+  RCSB_COL_PROBE(0);
   uint16_t* candA = (uint16_t*)WR(cand);  // candidate lists live in the stage-local union next to the geom centres
   uint16_t* candB = candA + RCSB_MAXCAND;
   int ncandA = 0;
   for (int base = 0; base < MD(npair); base += RCSB_NLANES) {
+    // an event has one or two due groups: most 32-pair blocks hold none of their pairs and are skipped as a whole
+    if (!((act[0] & m.pair_blk_grps[base >> 5][0]) | (act[1] & m.pair_blk_grps[base >> 5][1]))) continue;
     int p = base + c.lane, hit = 0;
     if (p < MD(npair)) {
       const int grp = m.pair_grp[p];
@@ -1330,7 +1345,8 @@ RCSB_DEV void st_collision(const Ctx& c) {
         } else {
           real bound = m.g_rbound[g1] + m.g_rbound[g2] + margin;
           hit = !(dot3(d, d) > bound * bound);
-          gap = hit ? (real)0 : r_sqrt(dot3(d, d)) - bound;
+          // a single-precision root, shortened by more than its rounding error: the gap only has to be a lower bound
+          gap = hit ? (real)0 : (real)(sqrtf((float)dot3(d, d)) * 0.9999997f) - bound;
         }
         if (!hit) budget_min(c, bud, grp, gap);
       }
@@ -1344,6 +1360,7 @@ RCSB_DEV void st_collision(const Ctx& c) {
     PFOR(g, MD(ngrp)) { if ((act[g >> 5] >> (g & 31)) & 1u) bud[g] = 0; }
   }
   RCSB_SYNC();
+  RCSB_COL_PROBE(1);
   // ---- mid phase: oriented boxes (local AABBs) by separating axes, one candidate per lane. Conservative: a
   //      rejected pair cannot intersect (the hull lies inside its box), so the contact set is unchanged.
   int ncand = 0;
@@ -1374,6 +1391,7 @@ RCSB_DEV void st_collision(const Ctx& c) {
     ncand = compact_append(c, hit, p, ncand, candB);
   }
   RCSB_SYNC();
+  RCSB_COL_PROBE(2);
   // ---- narrow phase, candidates in pair order
 #if defined(RCSB_STAGE_TIMING) && !defined(RCSB_HOST_EMU)
   const long long t_narrow_ = clock64();

@@ -649,9 +649,11 @@ int rcsb_debug_stage_trace(unsigned* out, int max_steps) {
     if (max_steps > RCSB_TRACE_STEPS) max_steps = RCSB_TRACE_STEPS;
     CUDA_OK(cudaMemcpyFromSymbol(out, rcsb_trace, (size_t)max_steps * 10 * 32 * sizeof(unsigned)));
     CUDA_OK(cudaMemcpyFromSymbol(out + (size_t)max_steps * 10 * 32, rcsb_trace_aux, (size_t)max_steps * 32 * sizeof(unsigned)));
+    CUDA_OK(cudaMemcpyFromSymbol(out + (size_t)max_steps * 11 * 32, rcsb_trace_col, (size_t)max_steps * 3 * 32 * sizeof(unsigned)));
   }
   static unsigned zt[RCSB_TRACE_STEPS][10][32];
   CUDA_OK(cudaMemcpyToSymbol(rcsb_trace_aux, zt, sizeof(unsigned) * RCSB_TRACE_STEPS * 32));
+  CUDA_OK(cudaMemcpyToSymbol(rcsb_trace_col, zt, sizeof(unsigned) * RCSB_TRACE_STEPS * 3 * 32));
   unsigned zs[32] = {0};
   CUDA_OK(cudaMemcpyToSymbol(rcsb_trace, zt, sizeof(zt)));
   CUDA_OK(cudaMemcpyToSymbol(rcsb_trace_step, zs, sizeof(zs)));

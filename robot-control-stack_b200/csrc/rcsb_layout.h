@@ -179,6 +179,8 @@ static inline int rcsb_model_finalize_layout(RcsbModel* m) {
       }
       m->pair_grp[p] = (uint8_t)g;
     }
+    memset(m->pair_blk_grps, 0, sizeof(m->pair_blk_grps));
+    for (int p = 0; p < m->npair; p++) m->pair_blk_grps[p >> 5][m->pair_grp[p] >> 5] |= 1u << (m->pair_grp[p] & 31);
     // E[x]: extent of body x's own collidable geoms about its frame origin; off[x]: bound of |origin of x in its parent|
     real E[RCSB_MAXB], off[RCSB_MAXB];
     for (int x = 0; x < m->nb; x++) {

@@ -146,6 +146,7 @@ struct RcsbModel {
   // bodies; sum over them of |dq_j| * grp_reach[g][j] (cold tail) bounds the relative displacement of the group's geoms.
   int ngrp;
   uint8_t pair_grp[RCSB_MAXPAIR];
+  uint32_t pair_blk_grps[(RCSB_MAXPAIR + 31) / 32][2];  // bit mask of the collision groups that own a pair of the 32-pair block; derived
   uint32_t grp_mask[RCSB_MAXGRP];
   // ---- tendons, equalities, actuators
   real t_coef[RCSB_MAXT][RCSB_MAXV];

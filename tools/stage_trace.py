@@ -33,11 +33,12 @@ L.rcsb_debug_stage_trace(None, 0)  # clear
 for _ in range(3):
     env.step(act())
 S = 3 * 17
-raw = np.zeros(S * 10 * 32 + S * 32, dtype=np.uint32)
+raw = np.zeros(S * 14 * 32, dtype=np.uint32)
 L.rcsb_debug_stage_trace(raw.ctypes.data, S)
 buf = raw[:S * 10 * 32].reshape(S, 10, 32)
-aux = raw[S * 10 * 32:].reshape(S, 32)
+aux = raw[S * 10 * 32:S * 11 * 32].reshape(S, 32)
 W = b.occupancy()["warps_per_cta"]
+colp = raw[S * 11 * 32:].reshape(S, 3, 32)[:, :, :W].astype(np.float64)
 t = buf[:, :9, :W].astype(np.float64)          # [step, stage, warp]
 tot = t.sum(axis=1)                            # [step, warp]
 names = ["kinematics", "com", "crb", "collision", "velocity", "make_constraint", "actuation", "constraint_solve", "integrate"]
@@ -58,6 +59,7 @@ print(f"collision events: {100 * ev.mean():.1f} % of the warp-steps have a due g
 if ev.any():
     print(f"  per event: due groups {due[ev].mean():.1f}, broad-phase survivors {broad[ev].mean():.1f}, mid-phase survivors {mid[ev].mean():.2f}")
     print(f"  collision stage {col[ev].mean():.0f} cycles (no event: {col[~ev].mean():.0f}); of it the narrow phase {nar[ev].mean():.0f}")
+    print(f"  inside an event (cycles from the stage's start): geom centres {colp[:, 0, :][ev].mean():.0f}, broad phase done {colp[:, 1, :][ev].mean():.0f}, mid phase done {colp[:, 2, :][ev].mean():.0f}")
     for k in range(0, int(mid.max()) + 1):
         sel = ev & (mid == k)
         if sel.any():
