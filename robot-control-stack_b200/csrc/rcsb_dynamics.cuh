@@ -1085,33 +1085,47 @@ RCSB_DEV_NOINLINE void box_box(const Ctx& c, int& ncon, const PairFrames& pf, re
     if (r_abs(dk) > md) { md = r_abs(dk); iax = k; isg = dk > 0 ? (real)-1 : (real)1; }
   }
   const int u1 = (iax + 1) % 3, u2 = (iax + 2) % 3, r1 = (ax + 1) % 3, r2 = (ax + 2) % 3;
-  real poly[16][3], tmp[16][3];
+  // The clip polygons (a quadrilateral cut by four half-planes: 8 vertices at most) live in the warp's shared workspace, in
+  // the slots of the Minkowski portal that this pair type does not use: as thread-local arrays they were indexed
+  // dynamically, i.e. in local memory, and the serial walk over them was two thirds of the tabletop scene's collision
+  // stage. Lane 0 stores, everybody reads after a warp barrier; the control flow stays uniform.
+  real (*poly)[3] = (real (*)[3])WR(sup);
+  real (*tmp)[3] = poly + 8;
   int np = 4;
+  RCSB_SYNC();  // the previous user of the portal slots is done
   for (int v = 0; v < 4; v++) {
     const real c0 = (v == 0 || v == 3) ? (real)1 : (real)-1, c1 = v < 2 ? (real)1 : (real)-1;
     real e[3];
     for (int cc = 0; cc < 3; cc++)
       e[cc] = pi[cc] + isg * si[iax] * Ri[3 * cc + iax] + c0 * si[u1] * Ri[3 * cc + u1] + c1 * si[u2] * Ri[3 * cc + u2] - pr[cc];
-    poly[v][0] = e[0] * Rr[r1] + e[1] * Rr[3 + r1] + e[2] * Rr[6 + r1];
-    poly[v][1] = e[0] * Rr[r2] + e[1] * Rr[3 + r2] + e[2] * Rr[6 + r2];
-    poly[v][2] = dot3(e, nr) - sr[ax];
+    if (c.lane == 0) {
+      poly[v][0] = e[0] * Rr[r1] + e[1] * Rr[3 + r1] + e[2] * Rr[6 + r1];
+      poly[v][1] = e[0] * Rr[r2] + e[1] * Rr[3 + r2] + e[2] * Rr[6 + r2];
+      poly[v][2] = dot3(e, nr) - sr[ax];
+    }
   }
+  RCSB_SYNC();
   for (int side = 0; side < 4 && np > 0; side++) {  // Sutherland-Hodgman against the reference rectangle
     const int cx = side >> 1;
     const real sg = (side & 1) ? (real)-1 : (real)1, lim = cx == 0 ? sr[r1] : sr[r2];
     int nq = 0;
     for (int v = 0; v < np; v++) {
-      const real *A = poly[v], *B = poly[(v + 1) % np];
-      real da = lim - sg * A[cx], db = lim - sg * B[cx];
-      if (da >= 0) { copy3(tmp[nq], A); nq++; }
+      const real *A = poly[v], *B = poly[v + 1 == np ? 0 : v + 1];
+      const real a3[3] = {A[0], A[1], A[2]}, b3[3] = {B[0], B[1], B[2]};
+      real da = lim - sg * a3[cx], db = lim - sg * b3[cx];
+      if (da >= 0) {
+        if (c.lane == 0 && nq < 8) copy3(tmp[nq], a3);
+        nq++;
+      }
       if ((da >= 0) != (db >= 0)) {
         real f = da / (da - db);
-        for (int k = 0; k < 3; k++) tmp[nq][k] = A[k] + f * (B[k] - A[k]);
+        if (c.lane == 0 && nq < 8) for (int k = 0; k < 3; k++) tmp[nq][k] = a3[k] + f * (b3[k] - a3[k]);
         nq++;
       }
     }
-    np = nq;
-    for (int v = 0; v < np; v++) copy3(poly[v], tmp[v]);
+    np = nq < 8 ? nq : 8;
+    RCSB_SYNC();  // the clipped polygon is complete: it is the next side's input (the two buffers swap roles)
+    real (*sw)[3] = poly; poly = tmp; tmp = sw;
   }
   real nw[3] = {nr[0], nr[1], nr[2]};
   if (code >= 3) { nw[0] = -nw[0]; nw[1] = -nw[1]; nw[2] = -nw[2]; }  // contact normal runs from geom 1 to geom 2

@@ -106,7 +106,7 @@ RCSB_HD constexpr RcsbLayout rcsb_make_layout(const RcsbShape& s) {
   u_end = RCSB_MAX(u_end, o); o = u_begin;
   RCSB_ALLOC(o_gpos, 3 * s.ng); RCSB_ALLOC(o_cand, (2 * RCSB_MAXCAND * (int)sizeof(uint16_t) + (int)sizeof(real) - 1) / (int)sizeof(real));
   RCSB_ALLOC(o_pairfr, 24);  // narrow phase: world frames [p | R] of the pair being tested
-  RCSB_ALLOC(o_sup, 45);     // narrow phase: portal of the Minkowski refinement, 5 support records
+  RCSB_ALLOC(o_sup, 48);     // narrow phase: portal of the Minkowski refinement, 5 support records (45) | box-box clip polygons 2 x [8][3]
   u_end = RCSB_MAX(u_end, o); o = u_begin;
   RCSB_ALLOC(o_cdofdot, 6 * nv); RCSB_ALLOC(o_cvel, 6 * nv); RCSB_ALLOC(o_cacc, 6 * nv);
   y.o_gcw = y.o_cacc;  // gravity-compensation wrenches replace the accelerations, body b in the slot of its last dof
