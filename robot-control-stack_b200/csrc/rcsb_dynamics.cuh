@@ -950,8 +950,11 @@ RCSB_DEV_NOINLINE int mpr_penetration(const Ctx& c, const PairFrames& pf, real* 
 }
 
 // append one contact (all lanes call with identical arguments; lane 0 writes)
+// like_prev: the previous contact of the list belongs to the same geom pair and has the same normal (the other points of
+// a plane-box, plane-capsule, plane-hull or box-box face contact): its frame and mixed solver parameters are copied instead
+// of being derived again (identical values; the derivation is a serial chain with a square root and divisions in lane 0)
 RCSB_DEV void add_contact(const Ctx& c, int& ncon, int g1, int g2, real dist, const real* pos, const real* normal,
-                          real margin, real gap) {
+                          real margin, real gap, int like_prev = 0) {
   const RcsbModel& m = CMODEL(c);
   if (ncon >= MD(maxcon)) {  // reduced layout: the full-capacity launch redoes this step; full layout: drop and count
     if (c.lane == 0) WI(misc)[MD(cap_reduced) ? MI_OVERFLOW : MI_WARN] += 1;
@@ -960,6 +963,18 @@ RCSB_DEV void add_contact(const Ctx& c, int& ncon, int g1, int g2, real dist, co
   if (c.lane == 0) {
     real* cr = WR(con) + RCSB_C_REALS * ncon;
     int* ci = WI(con) + RCSB_CI_INTS * ncon;
+    if (like_prev && ncon > 0) {
+      const real* pr = cr - RCSB_C_REALS;
+      const int* pi = ci - RCSB_CI_INTS;
+      for (int k = 0; k < RCSB_C_REALS; k++) cr[k] = pr[k];
+      ci[RCSB_CI_G0] = g1; ci[RCSB_CI_G1] = g2; ci[RCSB_CI_DIM] = pi[RCSB_CI_DIM]; ci[RCSB_CI_EFC] = -1;
+      cr[RCSB_C_DIST] = dist;
+      copy3(cr + RCSB_C_POS, pos);
+      cr[RCSB_C_INCMARGIN] = margin - gap;
+      cr[RCSB_C_MU] = 0;
+      ncon++;
+      return;
+    }
     cr[RCSB_C_DIST] = dist;
     copy3(cr + RCSB_C_POS, pos);
     copy3(cr + RCSB_C_FRAME, normal);
@@ -1136,7 +1151,7 @@ RCSB_DEV_NOINLINE void box_box(const Ctx& c, int& ncon, const PairFrames& pf, re
     real pos[3];
     for (int cc = 0; cc < 3; cc++)
       pos[cc] = pr[cc] + poly[v][0] * Rr[3 * cc + r1] + poly[v][1] * Rr[3 * cc + r2] + (sr[ax] + (real)0.5 * dist) * nr[cc];
-    add_contact(c, ncon, pf.g1, pf.g2, dist, pos, nw, margin, gap);
+    add_contact(c, ncon, pf.g1, pf.g2, dist, pos, nw, margin, gap, cnt > 0);
     cnt++;
   }
 }
@@ -1185,7 +1200,7 @@ RCSB_DEV_NOINLINE void plane_mesh(const Ctx& c, int& ncon, const PairFrames& pf,
     for (int t = 0; t < 3; t++) if (t == count) copy3(taken[t], v);
     count++;
     for (int kk = 0; kk < 3; kk++) pos[kk] = v[kk] - (real)0.5 * dist * n[kk];
-    add_contact(c, ncon, pf.g1, pf.g2, dist, pos, n, margin, gap);
+    add_contact(c, ncon, pf.g1, pf.g2, dist, pos, n, margin, gap, count > 1);
   }
 }
 
@@ -1438,7 +1453,7 @@ RCSB_DEV void st_collision(const Ctx& c) {
           mind = dist < mind ? dist : mind;
           if (dist > margin) continue;
           for (int k = 0; k < 3; k++) pos[k] = cw[k] - (real)0.5 * dist * n[k];
-          add_contact(c, ncon, pf.g1, pf.g2, dist, pos, n, margin, gap);
+          add_contact(c, ncon, pf.g1, pf.g2, dist, pos, n, margin, gap, cnt > 0);
           cnt++;
         }
         if (cnt == 0) clear = mind - margin;
@@ -1454,7 +1469,7 @@ RCSB_DEV void st_collision(const Ctx& c) {
           mind = dist < mind ? dist : mind;
           if (dist > margin) continue;
           for (int k = 0; k < 3; k++) pos[k] = cw[k] - n[k] * (r + (real)0.5 * dist);
-          add_contact(c, ncon, pf.g1, pf.g2, dist, pos, n, margin, gap);
+          add_contact(c, ncon, pf.g1, pf.g2, dist, pos, n, margin, gap, cnt > 0);
           cnt++;
         }
         if (cnt == 0) clear = mind - margin;
