@@ -1011,8 +1011,8 @@ RCSB_DEV void add_contact(const Ctx& c, int& ncon, int g1, int g2, real dist, co
 
 
 // ---- box-box (mjc_BoxBox, restated as separating axes + face clipping; see oracle/mj_collision.c): up to 8 contacts.
-// Every lane runs the same scalar code on identical data (add_contact lets lane 0 write); out of line and rare (finger
-// pads against the cube or each other), so the clipping polygon may live in thread-local memory.
+// Every lane runs the same scalar code on identical data (add_contact lets lane 0 write); out of line. The clip polygons
+// live in the warp's shared workspace (the tabletop scene runs this every step for the brick on the table).
 RCSB_DEV_NOINLINE void box_box(const Ctx& c, int& ncon, const PairFrames& pf, real margin, real gap, real* clear_out) {
   const RcsbModel& m = CMODEL(c);
   const real *R1 = pf.R1, *R2 = pf.R2, *p1 = pf.p1, *p2 = pf.p2;
